@@ -1,0 +1,105 @@
+"""oracle/dae.py: the two independent formulations (NumPy float64 hand-derived gradients
+vs torch-CPU autograd) agree, plus hand-computed micro cases of the Keras-2.5
+conventions (reference src/ml/model.py:20-125, src/ml/train.py:83-88).
+PARITY UNPINNED vs TensorFlow (not installable) -- see oracle/dae.py header."""
+import numpy as np
+import torch
+
+from oracle import dae, graph
+from cubecobrarecommender_b200.synth import synth_cubes_csr, csr_to_dense
+
+
+def _setup(c=96, k=40, b=12, seed=3):
+    ip, ix = synth_cubes_csr(k, c, size_lo=6, size_hi=30, seed=seed)
+    dense = csr_to_dense(ip, ix, c)
+    adj = graph.create_adjacency_matrix(dense)
+    mh = graph.m_hat(adj)
+    rng = np.random.default_rng(seed)
+    x = dense[:b].copy()
+    y = x.copy()
+    # a fixed "noise" outcome: drop two cards from x (one of them from y), add one
+    for r in range(b):
+        inc = np.where(x[r] == 1)[0]; exc = np.where(x[r] == 0)[0]
+        x[r, inc[:2]] = 0; y[r, inc[0]] = 0; x[r, exc[rng.integers(len(exc))]] = 1
+    reg_rows = rng.integers(0, c, size=b)
+    params = dae.init_params(c, seed=0)
+    # non-zero biases so bias gradients matter
+    for kname in params:
+        if kname.endswith("bias"):
+            params[kname] = (rng.standard_normal(params[kname].shape) * 0.05).astype(np.float32)
+    return params, x, y, reg_rows, mh[reg_rows]
+
+
+def test_param_count_matches_shipped_checkpoint():
+    # 1538*C + 518848 parameters, C = 20884 -> 32 638 440
+    n = sum(fi * fo + fo for _, fi, fo in dae.layer_specs(20884))
+    assert n == 32_638_440
+
+
+def test_numpy_vs_torch_autograd_float64():
+    params, x, y, reg_rows, t = _setup()
+    (tot, bce, kl), grads = dae.loss_and_grads_np(params, x, y, reg_rows, t, reg=0.1)
+    tm = dae.TorchDAE(params, dtype=torch.float64)
+    total, bce_t, kl_t = tm.loss(torch.tensor(x), torch.tensor(y), torch.tensor(reg_rows),
+                                 torch.tensor(t), 0.1)
+    total.backward()
+    assert abs(float(total) - tot) < 1e-12 and abs(float(bce_t) - bce) < 1e-12
+    assert abs(float(kl_t) - kl) < 1e-12
+    tg = tm.grads()
+    for kname, g in grads.items():
+        scale = np.abs(g).max() + 1e-30
+        assert np.abs(tg[kname] - g).max() / scale < 1e-9, kname
+
+
+def test_kl_clip_gradient_mask():
+    """q below 1e-7 is clipped: no gradient flows through those entries (S excludes them)."""
+    z = np.array([[0.0, -30.0, 1.0]])
+    t = np.array([[0.5, 0.0, 0.5]])
+    q = dae.softmax_np(z)
+    assert q[0, 1] < 1e-7
+    zt = torch.tensor(z, requires_grad=True)
+    qt = torch.softmax(zt, 1)
+    tc = torch.clamp(torch.tensor(t), 1e-7, 1.0)
+    loss = (tc * torch.log(tc / torch.clamp(qt, 1e-7, 1.0))).sum(1).mean()
+    loss.backward()
+    tcn = np.clip(t, 1e-7, 1)
+    unclipped = q >= 1e-7
+    s = (tcn * unclipped).sum(1, keepdims=True)
+    expect = q * s - tcn * unclipped
+    assert np.allclose(zt.grad.numpy(), expect, atol=1e-15)
+    assert abs(dae.kld_np(t, q) - float(loss)) < 1e-15
+
+
+def test_bce_logits_micro_case():
+    z = np.array([[0.0, 2.0], [-3.0, 50.0]]); y = np.array([[1.0, 0.0], [0.0, 1.0]])
+    hand = np.mean([np.log(2), 2 + np.log1p(np.exp(-2)), np.log1p(np.exp(-3)), np.log1p(np.exp(-50.0))])
+    assert abs(dae.bce_from_logits_np(z, y) - hand) < 1e-15
+
+
+def test_adam_tf_style_first_steps():
+    p = {"w": np.array([1.0, -2.0])}; g = {"w": np.array([0.5, -0.25])}
+    m = {"w": np.zeros(2)}; v = {"w": np.zeros(2)}
+    dae.adam_step_np(p, g, m, v, 1)
+    # step 1: m = .1 g, v = .001 g^2, lr_t = 1e-3*sqrt(.001)/.1
+    lr_t = 1e-3 * np.sqrt(1 - 0.999) / (1 - 0.9)
+    expect = np.array([1.0, -2.0]) - lr_t * (0.1 * g["w"]) / (np.sqrt(0.001 * g["w"] ** 2) + 1e-7)
+    assert np.allclose(p["w"], expect, rtol=0, atol=1e-15)
+
+
+def test_float32_train_steps_track_float64():
+    params, x, y, reg_rows, t = _setup()
+    p64 = {k: v.astype(np.float64) for k, v in params.items()}
+    m = {k: np.zeros_like(v) for k, v in p64.items()}; v_ = {k: np.zeros_like(v) for k, v in p64.items()}
+    tm = dae.TorchDAE(params)
+    xt, yt = torch.tensor(x, dtype=torch.float32), torch.tensor(y, dtype=torch.float32)
+    rt, tt = torch.tensor(reg_rows), torch.tensor(t, dtype=torch.float32)
+    for step in range(1, 4):
+        (tot, _, _), grads = dae.loss_and_grads_np(p64, x, y, reg_rows, t, reg=0.1)
+        dae.adam_step_np(p64, grads, m, v_, step)
+        tot32, _, _ = tm.train_step(xt, yt, rt, tt, 0.1)
+        assert abs(tot32 - tot) / abs(tot) < 1e-5
+
+
+def test_rank_additions_tie_rule():
+    res = np.array([0.5, 0.9, 0.9, 0.1, 0.9]); in_cube = np.array([0, 0, 1, 0, 0])
+    assert dae.rank_additions(res, in_cube, 3) == [4, 1, 0]
