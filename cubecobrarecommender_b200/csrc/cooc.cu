@@ -1,0 +1,335 @@
+// Co-occurrence graph build: bit-pack -> popcount count -> row normalise.
+//
+// Replaces reference src/non_ml/utils.py:75-92 (create_adjacency_matrix),
+// src/ml/train.py:69-71 (M-hat) and src/ml/generator.py:30 (neg_sampler).
+//
+// Data layout in HBM
+//   bits   uint32 [Kw_pad][Cpad]   word w, card c: bit (k & 31) of bits[k>>5][c] is set
+//                                  iff cube k contains card c ("word-major": a tile of
+//                                  128 cards x KC words is KC contiguous 512-byte rows,
+//                                  so tiles land in shared memory with no transpose)
+//   counts int32  [C][ld]          counts[i][j] = |{k : i in cube k and j in cube k}|
+//   M      float64 [C][C]          counts[i][j]/counts[i][i]   (utils.py:85-89)
+//   M-hat  float32 [C][ld_mhat]    diag<-1, row / row sum      (train.py:69-71)
+#include "cc_common.cuh"
+
+namespace cc {
+
+// ------------------------------------------------------------------ bit-pack
+__global__ void bitpack_kernel(const int64_t* __restrict__ indptr,
+                               const int32_t* __restrict__ indices, int64_t num_cubes,
+                               int32_t num_cards, uint32_t* __restrict__ bits, int64_t cpad,
+                               int* __restrict__ bad) {
+  // one warp per cube; duplicates collapse because OR is idempotent (utils.py:71)
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= num_cubes) return;
+  const int64_t beg = indptr[warp], end = indptr[warp + 1];
+  uint32_t* row = bits + (warp >> 5) * cpad;
+  const uint32_t bit = 1u << (warp & 31);
+  for (int64_t p = beg + lane; p < end; p += 32) {
+    const int32_t c = indices[p];
+    if (c < 0 || c >= num_cards) { atomicExch(bad, 1); continue; }
+    atomicOr(row + c, bit);
+  }
+}
+
+// ------------------------------------------------------------- popcount count
+// One CTA = one 128x128 tile of counts on or above the diagonal; 256 threads, each
+// 8x8 outputs.  The K (cube) dimension streams through shared memory in stages of
+// KC words with cp.async double buffering; every word pair costs AND + POPC + IADD.
+constexpr int TILE = 128;
+constexpr int KC = 16;
+constexpr int COUNT_THREADS = 256;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+__global__ void __launch_bounds__(COUNT_THREADS, 2)
+cooc_count_kernel(const uint32_t* __restrict__ bits, int64_t kw_pad, int64_t cpad, int32_t num_cards,
+                  int32_t* __restrict__ counts, int64_t ld, int accumulate) {
+  const int ti = blockIdx.y, tj = blockIdx.x;
+  if (tj < ti) return;  // lower triangle is written as the transpose of the upper one
+  __shared__ __align__(16) uint32_t sA[2][KC][TILE];
+  __shared__ __align__(16) uint32_t sB[2][KC][TILE];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const uint32_t* gA = bits + int64_t(ti) * TILE;
+  const uint32_t* gB = bits + int64_t(tj) * TILE;
+
+  auto load_stage = [&](int buf, int64_t w0) {
+    // KC rows x 32 16-byte chunks per operand
+#pragma unroll
+    for (int it = 0; it < (KC * 32) / COUNT_THREADS; ++it) {
+      const int chunk = tid + it * COUNT_THREADS;
+      const int r = chunk >> 5, c4 = (chunk & 31) << 2;
+      cp_async16(&sA[buf][r][c4], gA + (w0 + r) * cpad + c4);
+      cp_async16(&sB[buf][r][c4], gB + (w0 + r) * cpad + c4);
+    }
+    cp_async_commit();
+  };
+
+  int acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0;
+
+  const int64_t stages = kw_pad / KC;
+  load_stage(0, 0);
+  for (int64_t s = 0; s < stages; ++s) {
+    const int buf = int(s & 1);
+    if (s + 1 < stages) { load_stage(buf ^ 1, (s + 1) * KC); cp_async_wait<1>(); }
+    else                { cp_async_wait<0>(); }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < KC; ++w) {
+      // rows  i = ty*8 .. ty*8+7          (two broadcast LDS.128)
+      // cols  j = tx*4 .. +3 and 64 + tx*4 .. +3   (two conflict-free LDS.128)
+      const uint4 a0 = *reinterpret_cast<const uint4*>(&sA[buf][w][ty * 8]);
+      const uint4 a1 = *reinterpret_cast<const uint4*>(&sA[buf][w][ty * 8 + 4]);
+      const uint4 b0 = *reinterpret_cast<const uint4*>(&sB[buf][w][tx * 4]);
+      const uint4 b1 = *reinterpret_cast<const uint4*>(&sB[buf][w][64 + tx * 4]);
+      const uint32_t a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const uint32_t b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] += __popc(a[i] & b[j]);
+    }
+    __syncthreads();
+  }
+
+  // write the tile, and its transpose when off the diagonal
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gi = ti * TILE + ty * 8 + i;
+    if (gi >= num_cards) continue;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int gj0 = tj * TILE + h * 64 + tx * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gj = gj0 + j;
+        if (gj >= num_cards) continue;
+        const int v = acc[i][h * 4 + j];
+        int32_t* p = counts + int64_t(gi) * ld + gj;
+        *p = accumulate ? *p + v : v;
+        if (ti != tj) {
+          int32_t* q = counts + int64_t(gj) * ld + gi;
+          *q = accumulate ? *q + v : v;
+        }
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------- row normalise
+// One CTA per card i.  Emits, from the int32 counts row:
+//   M[i,:]      float64  = cnt/cnt[i,i] if cnt[i,i] != 0 else cnt      (utils.py:85-89)
+//   rowsum[i]   float64  = sum_j y[i,j], y = M with diagonal forced to 1 (train.py:69-70)
+//   Mhat[i,:]   float32  = y[i,:]/rowsum[i]                              (train.py:71)
+__global__ void __launch_bounds__(256)
+row_normalise_kernel(const int32_t* __restrict__ counts, int64_t ld, int32_t num_cards,
+                     double* __restrict__ m64, int64_t ld_m, float* __restrict__ mhat, int64_t ld_mhat,
+                     double* __restrict__ rowsum, int has_force_diag, double force_diag) {
+  const int i = blockIdx.x;
+  const int32_t* row = counts + int64_t(i) * ld;
+  const int32_t d = row[i];
+  const double dd = double(d);
+  __shared__ double red[8];
+  double s = 0.0;
+  for (int j = threadIdx.x; j < num_cards; j += blockDim.x) {
+    const double c = double(row[j]);
+    double v = d != 0 ? c / dd : c;
+    if (m64) m64[int64_t(i) * ld_m + j] = (has_force_diag && j == i) ? force_diag : v;
+    s += (j == i) ? 1.0 : v;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  const double total = red[0];
+  if (threadIdx.x == 0 && rowsum) rowsum[i] = total;
+  if (mhat) {
+    for (int j = threadIdx.x; j < num_cards; j += blockDim.x) {
+      const double c = double(row[j]);
+      const double v = (j == i) ? 1.0 : (d != 0 ? c / dd : c);
+      mhat[int64_t(i) * ld_mhat + j] = float(v / total);
+    }
+  }
+}
+
+// column mass of M-hat in float64: partial[chunk][j] = sum_{i in chunk} y[i,j]/rowsum[i]
+constexpr int COL_ROWS = 256;
+__global__ void __launch_bounds__(128)
+col_mass_partial_kernel(const int32_t* __restrict__ counts, int64_t ld, int32_t num_cards,
+                        const double* __restrict__ rowsum, double* __restrict__ partial) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i0 = blockIdx.y * COL_ROWS;
+  const int i1 = min(i0 + COL_ROWS, num_cards);
+  if (j >= num_cards) return;
+  double s = 0.0;
+  for (int i = i0; i < i1; ++i) {
+    const int32_t d = counts[int64_t(i) * ld + i];  // broadcast load
+    const double c = double(counts[int64_t(i) * ld + j]);
+    const double v = (j == i) ? 1.0 : (d != 0 ? c / double(d) : c);
+    s += v / rowsum[i];
+  }
+  partial[int64_t(blockIdx.y) * num_cards + j] = s;
+}
+__global__ void col_mass_final_kernel(const double* __restrict__ partial, int chunks, int32_t num_cards,
+                                      double* __restrict__ neg_sampler) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= num_cards) return;
+  double s = 0.0;
+  for (int c = 0; c < chunks; ++c) s += partial[int64_t(c) * num_cards + j];
+  // M-hat.sum() == number of rows (each row sums to 1) up to rounding; the reference
+  // divides by the actual total (generator.py:30), so do the same deterministic sum
+  neg_sampler[j] = s;
+}
+__global__ void col_mass_scale_kernel(double* __restrict__ neg_sampler, int32_t num_cards) {
+  // single CTA: total = sum_j neg[j] (fixed order), then neg /= total
+  __shared__ double red[32];
+  __shared__ double total_s;
+  double s = 0.0;
+  for (int j = threadIdx.x; j < num_cards; j += blockDim.x) s += neg_sampler[j];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) total_s = t;
+  }
+  __syncthreads();
+  const double total = total_s;
+  for (int j = threadIdx.x; j < num_cards; j += blockDim.x) neg_sampler[j] /= total;
+}
+
+}  // namespace cc
+
+using namespace cc;
+
+extern "C" {
+
+int64_t cc_bits_words(int64_t num_cubes) { return ceil_div<int64_t>(ceil_div<int64_t>(num_cubes, 32), KC) * KC; }
+int64_t cc_bits_cpad(int32_t num_cards) { return ceil_div<int64_t>(num_cards, TILE) * TILE; }
+
+int cc_bitpack_cubes(const int64_t* indptr, const int32_t* indices, int64_t num_cubes, int32_t num_cards,
+                     uint32_t* bits, int* bad_flag, void* stream) {
+  CC_REQUIRE(num_cubes >= 0 && num_cards > 0, "cc_bitpack_cubes: bad sizes K=%lld C=%d", (long long)num_cubes, num_cards);
+  CC_REQUIRE(bits && bad_flag, "cc_bitpack_cubes: null output");
+  cudaStream_t st = as_stream(stream);
+  const int64_t kw = cc_bits_words(num_cubes), cpad = cc_bits_cpad(num_cards);
+  CC_CHECK_CUDA(cudaMemsetAsync(bits, 0, size_t(kw) * cpad * sizeof(uint32_t), st));
+  CC_CHECK_CUDA(cudaMemsetAsync(bad_flag, 0, sizeof(int), st));
+  if (num_cubes == 0) return CC_OK;
+  const int threads = 256;
+  const int64_t blocks = ceil_div<int64_t>(num_cubes * 32, threads);
+  bitpack_kernel<<<(unsigned)blocks, threads, 0, st>>>(indptr, indices, num_cubes, num_cards, bits, cpad, bad_flag);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+int cc_cooc_count(const uint32_t* bits, int64_t num_cubes, int32_t num_cards, int32_t* counts, int64_t ld,
+                  int accumulate, void* stream) {
+  CC_REQUIRE(bits && counts && num_cards > 0 && ld >= num_cards, "cc_cooc_count: bad arguments");
+  const int64_t kw = cc_bits_words(num_cubes), cpad = cc_bits_cpad(num_cards);
+  const int tiles = int(cpad / TILE);
+  cudaStream_t st = as_stream(stream);
+  if (kw == 0) {
+    if (!accumulate) CC_CHECK_CUDA(cudaMemset2DAsync(counts, ld * 4, 0, size_t(num_cards) * 4, num_cards, st));
+    return CC_OK;
+  }
+  dim3 grid(tiles, tiles);
+  cooc_count_kernel<<<grid, COUNT_THREADS, 0, st>>>(bits, kw, cpad, num_cards, counts, ld, accumulate);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+int cc_row_normalise(const int32_t* counts, int64_t ld, int32_t num_cards, double* m64, int64_t ld_m,
+                     float* mhat, int64_t ld_mhat, double* rowsum, int has_force_diag, double force_diag,
+                     void* stream) {
+  CC_REQUIRE(counts && num_cards > 0 && ld >= num_cards, "cc_row_normalise: bad arguments");
+  CC_REQUIRE(!m64 || ld_m >= num_cards, "cc_row_normalise: ld_m too small");
+  CC_REQUIRE(!mhat || ld_mhat >= num_cards, "cc_row_normalise: ld_mhat too small");
+  row_normalise_kernel<<<num_cards, 256, 0, as_stream(stream)>>>(counts, ld, num_cards, m64, ld_m, mhat, ld_mhat,
+                                                                 rowsum, has_force_diag, force_diag);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+int64_t cc_col_mass_workspace_bytes(int32_t num_cards) {
+  return int64_t(ceil_div(num_cards, COL_ROWS)) * num_cards * int64_t(sizeof(double));
+}
+
+int cc_col_mass(const int32_t* counts, int64_t ld, int32_t num_cards, const double* rowsum, double* workspace,
+                double* neg_sampler, void* stream) {
+  CC_REQUIRE(counts && rowsum && workspace && neg_sampler, "cc_col_mass: null pointer");
+  const int chunks = ceil_div(num_cards, COL_ROWS);
+  cudaStream_t st = as_stream(stream);
+  dim3 grid(ceil_div(num_cards, 128), chunks);
+  col_mass_partial_kernel<<<grid, 128, 0, st>>>(counts, ld, num_cards, rowsum, workspace);
+  CC_CHECK_LAUNCH();
+  col_mass_final_kernel<<<ceil_div(num_cards, 256), 256, 0, st>>>(workspace, chunks, num_cards, neg_sampler);
+  CC_CHECK_LAUNCH();
+  col_mass_scale_kernel<<<1, 1024, 0, st>>>(neg_sampler, num_cards);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+// Host-buffer entry: the drop-in for utils.create_adjacency_matrix (utils.py:75-92) on
+// CSR cubes.  Copies H2D, builds on `device`'s current context, copies M back (float64).
+int cc_create_adjacency_matrix_host(const int64_t* indptr_host, const int32_t* indices_host, int64_t num_cubes,
+                                    int32_t num_cards, int has_force_diag, double force_diag, double* m_host,
+                                    int32_t* counts_host /* nullable */) {
+  CC_REQUIRE(indptr_host && indices_host && m_host, "cc_create_adjacency_matrix_host: null pointer");
+  CC_REQUIRE(num_cards > 0 && num_cubes >= 0, "cc_create_adjacency_matrix_host: bad sizes");
+  const int64_t nnz = indptr_host[num_cubes];
+  const int64_t kw = cc_bits_words(num_cubes), cpad = cc_bits_cpad(num_cards);
+  int64_t* d_indptr = nullptr; int32_t* d_indices = nullptr; uint32_t* d_bits = nullptr;
+  int32_t* d_counts = nullptr; double* d_m = nullptr; int* d_bad = nullptr;
+  int rc = CC_OK;
+  cudaStream_t st = nullptr;
+#define CC_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { rc = cuda_fail(_e, #expr, __FILE__, __LINE__); goto done; } } while (0)
+  CC_TRY(cudaStreamCreate(&st));
+  CC_TRY(cudaMalloc(&d_indptr, size_t(num_cubes + 1) * 8));
+  CC_TRY(cudaMalloc(&d_indices, size_t(nnz > 0 ? nnz : 1) * 4));
+  CC_TRY(cudaMalloc(&d_bits, size_t(kw > 0 ? kw : 1) * cpad * 4));
+  CC_TRY(cudaMalloc(&d_counts, size_t(num_cards) * num_cards * 4));
+  CC_TRY(cudaMalloc(&d_m, size_t(num_cards) * num_cards * 8));
+  CC_TRY(cudaMalloc(&d_bad, sizeof(int)));
+  CC_TRY(cudaMemcpyAsync(d_indptr, indptr_host, size_t(num_cubes + 1) * 8, cudaMemcpyHostToDevice, st));
+  CC_TRY(cudaMemcpyAsync(d_indices, indices_host, size_t(nnz) * 4, cudaMemcpyHostToDevice, st));
+  if ((rc = cc_bitpack_cubes(d_indptr, d_indices, num_cubes, num_cards, d_bits, d_bad, st)) != CC_OK) goto done;
+  if ((rc = cc_cooc_count(d_bits, num_cubes, num_cards, d_counts, num_cards, 0, st)) != CC_OK) goto done;
+  if ((rc = cc_row_normalise(d_counts, num_cards, num_cards, d_m, num_cards, nullptr, 0, nullptr, has_force_diag,
+                             force_diag, st)) != CC_OK) goto done;
+  CC_TRY(cudaMemcpyAsync(m_host, d_m, size_t(num_cards) * num_cards * 8, cudaMemcpyDeviceToHost, st));
+  if (counts_host)
+    CC_TRY(cudaMemcpyAsync(counts_host, d_counts, size_t(num_cards) * num_cards * 4, cudaMemcpyDeviceToHost, st));
+  {
+    int bad = 0;
+    CC_TRY(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CC_TRY(cudaStreamSynchronize(st));
+    if (bad) { set_error("cc_create_adjacency_matrix_host: card index out of range [0,%d)", num_cards); rc = CC_ERR_ARGUMENT; }
+  }
+done:
+#undef CC_TRY
+  cudaFree(d_indptr); cudaFree(d_indices); cudaFree(d_bits); cudaFree(d_counts); cudaFree(d_m); cudaFree(d_bad);
+  if (st) cudaStreamDestroy(st);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,264 @@
+// Losses of the regularised DAE and the optimiser (Keras 2.5 conventions).
+//
+// Replaces reference src/ml/train.py:83-88:
+//   compile(optimizer='adam', loss=['binary_crossentropy','kullback_leibler_divergence'],
+//           loss_weights=[1.0, reg])
+// * BCE on the sigmoid tower is evaluated from the logits (Keras-2.5 graph path):
+//     l = max(z,0) - z*y + log1p(exp(-|z|)),  mean over B*C;  dl/dz = (sigmoid(z)-y)/(B*C)
+// * KLD on the softmax tower: t' = clip(t,1e-7,1), q' = clip(softmax(z),1e-7,1),
+//     kl = mean_r sum_c t' log(t'/q');  d/dz_c = reg*(q_c*S - t'_c*1[q_c unclipped])/R,
+//     S = sum over unclipped c of t'_c
+// * Adam: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v updates; theta -= lr_t*m/(sqrt(v)+eps),
+//   eps = 1e-7 outside the bias correction, dense over every parameter.
+// These are the unfused forms; gemm_tc.cu carries the BCE math inside the GEMM epilogue.
+#include "cc_common.cuh"
+
+namespace cc {
+
+constexpr float KERAS_EPS = 1e-7f;
+
+__device__ __forceinline__ double block_sum_double(double v, double* red /* smem[32] */) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (wid == 0) {
+    t = lane < (blockDim.x >> 5) ? red[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) red[0] = t;
+  }
+  __syncthreads();
+  t = red[0];
+  return t;
+}
+__device__ __forceinline__ float block_max_float(float v, float* red /* smem[32] */) {
+  v = warp_max(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float t;
+  if (wid == 0) {
+    t = lane < (blockDim.x >> 5) ? red[lane] : -INFINITY;
+    t = warp_max(t);
+    if (lane == 0) red[0] = t;
+  }
+  __syncthreads();
+  t = red[0];
+  return t;
+}
+
+// ---------------------------------------------------------------- sigmoid-BCE
+__global__ void __launch_bounds__(256)
+bce_rows_kernel(const float* __restrict__ z, int64_t ldz, const uint32_t* __restrict__ ybits, int64_t ywords,
+                int32_t num_cards, int32_t ncols_pad, float inv_count, float* __restrict__ dz, int64_t lddz,
+                double* __restrict__ row_loss) {
+  __shared__ double red[32];
+  const int b = blockIdx.x;
+  const float* zr = z + int64_t(b) * ldz;
+  const uint32_t* yr = ybits + int64_t(b) * ywords;
+  float* dr = dz ? dz + int64_t(b) * lddz : nullptr;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < ncols_pad; c += blockDim.x) {
+    if (c < num_cards) {
+      const float v = zr[c];
+      const float y = float((yr[c >> 5] >> (c & 31)) & 1u);
+      const float e = expf(-fabsf(v));
+      s += fmaxf(v, 0.f) - v * y + log1pf(e);
+      if (dr) {
+        const float sig = v >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+        dr[c] = (sig - y) * inv_count;
+      }
+    } else if (dr) {
+      dr[c] = 0.f;
+    }
+  }
+  const double tot = block_sum_double(double(s), red);
+  if (threadIdx.x == 0) row_loss[b] = tot;
+}
+
+// ---------------------------------------------------------------- softmax-KL
+template <bool CACHE>
+__global__ void __launch_bounds__(1024)
+softmax_kl_rows_kernel(const float* __restrict__ z, int64_t ldz, const float* __restrict__ target, int64_t ldt,
+                       const int32_t* __restrict__ target_rows, int32_t num_cards, int32_t ncols_pad,
+                       float grad_scale /* reg / R */, float* __restrict__ dz, int64_t lddz,
+                       double* __restrict__ row_loss) {
+  extern __shared__ __align__(16) float srow[];   // CACHE: z row then t row
+  __shared__ double redd[32];
+  __shared__ float redf[32];
+  const int r = blockIdx.x;
+  const float* zr = z + int64_t(r) * ldz;
+  const float* tr = target + int64_t(target_rows ? target_rows[r] : r) * ldt;
+  float* dr = dz ? dz + int64_t(r) * lddz : nullptr;
+  float* sz = srow;
+  float* stt = srow + num_cards;
+
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < num_cards; c += blockDim.x) {
+    const float v = zr[c];
+    if (CACHE) sz[c] = v;
+    mx = fmaxf(mx, v);
+  }
+  mx = block_max_float(mx, redf);
+  float se = 0.f;
+  for (int c = threadIdx.x; c < num_cards; c += blockDim.x) se += expf((CACHE ? sz[c] : zr[c]) - mx);
+  const double sumexp = block_sum_double(double(se), redd);
+  const float inv_sum = float(1.0 / sumexp);
+
+  float loss = 0.f, sun = 0.f;
+  for (int c = threadIdx.x; c < num_cards; c += blockDim.x) {
+    const float q = expf((CACHE ? sz[c] : zr[c]) - mx) * inv_sum;
+    const float t = tr[c];
+    if (CACHE) stt[c] = t;
+    const float tc = fminf(fmaxf(t, KERAS_EPS), 1.f);
+    const float qc = fminf(fmaxf(q, KERAS_EPS), 1.f);
+    loss += tc * logf(tc / qc);
+    if (q >= KERAS_EPS && q <= 1.f) sun += tc;
+  }
+  const double row = block_sum_double(double(loss), redd);
+  const float S = float(block_sum_double(double(sun), redd));
+  if (threadIdx.x == 0) row_loss[r] = row;
+  if (dr) {
+    for (int c = threadIdx.x; c < ncols_pad; c += blockDim.x) {
+      float g = 0.f;
+      if (c < num_cards) {
+        const float q = expf((CACHE ? sz[c] : zr[c]) - mx) * inv_sum;
+        const float t = CACHE ? stt[c] : tr[c];
+        const float tc = fminf(fmaxf(t, KERAS_EPS), 1.f);
+        const bool un = (q >= KERAS_EPS && q <= 1.f);
+        g = (q * S - (un ? tc : 0.f)) * grad_scale;
+      }
+      dr[c] = g;
+    }
+  }
+}
+
+// loss[0] = bce mean, loss[1] = kl mean, loss[2] = bce + reg*kl   (fixed summation order)
+__global__ void __launch_bounds__(1024)
+loss_finalize_kernel(const double* __restrict__ bce_rows, int nb, double bce_div, const double* __restrict__ kl_rows,
+                     int nr, double kl_div, double reg, double* __restrict__ out) {
+  __shared__ double red[32];
+  double a = 0.0, k = 0.0;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) a += bce_rows[i];
+  for (int i = threadIdx.x; i < nr; i += blockDim.x) k += kl_rows[i];
+  a = block_sum_double(a, red);
+  k = block_sum_double(k, red);
+  if (threadIdx.x == 0) {
+    const double bce = bce_div > 0 ? a / bce_div : 0.0, kl = kl_div > 0 ? k / kl_div : 0.0;
+    out[0] = bce; out[1] = kl; out[2] = bce + reg * kl;
+  }
+}
+
+// ------------------------------------------------------------------- Adam
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            int64_t n, const int64_t* __restrict__ step_ptr, float lr, float b1, float b2, float eps) {
+  const double t = double(*step_ptr + 1);
+  const float lr_t = float(double(lr) * sqrt(1.0 - pow(double(b2), t)) / (1.0 - pow(double(b1), t)));
+  const int64_t i4 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i4 + 3 < n) {
+    float4 pv = *reinterpret_cast<float4*>(p + i4);
+    const float4 gv = *reinterpret_cast<const float4*>(g + i4);
+    float4 mv = *reinterpret_cast<float4*>(m + i4);
+    float4 vv = *reinterpret_cast<float4*>(v + i4);
+#define CC_ADAM1(X)                                   \
+    mv.X = b1 * mv.X + (1.f - b1) * gv.X;             \
+    vv.X = b2 * vv.X + (1.f - b2) * gv.X * gv.X;      \
+    pv.X = pv.X - lr_t * mv.X / (sqrtf(vv.X) + eps);
+    CC_ADAM1(x) CC_ADAM1(y) CC_ADAM1(z) CC_ADAM1(w)
+#undef CC_ADAM1
+    *reinterpret_cast<float4*>(p + i4) = pv;
+    *reinterpret_cast<float4*>(m + i4) = mv;
+    *reinterpret_cast<float4*>(v + i4) = vv;
+  } else {
+    for (int64_t i = i4; i < n; ++i) {
+      const float gi = g[i];
+      const float mi = b1 * m[i] + (1.f - b1) * gi;
+      const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+      m[i] = mi; v[i] = vi;
+      p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+    }
+  }
+}
+
+// sigmoid of the winners / in-cube scores: probs = 1/(1+exp(-z))
+__global__ void sigmoid_kernel(const float* __restrict__ z, float* __restrict__ out, int64_t n) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = 1.f / (1.f + expf(-z[i]));
+}
+
+}  // namespace cc
+
+using namespace cc;
+
+extern "C" {
+
+int cc_bce_logits_fwd_bwd(const float* z, int64_t ldz, const uint32_t* ybits, int64_t ywords, int32_t batch,
+                          int32_t num_cards, int32_t ncols_pad, double count /* global B*C */, float* dz,
+                          int64_t lddz, double* row_loss, void* stream) {
+  CC_REQUIRE(z && ybits && row_loss, "cc_bce_logits_fwd_bwd: null pointer");
+  CC_REQUIRE(num_cards > 0 && ncols_pad >= num_cards && ywords * 32 >= num_cards && count > 0,
+             "cc_bce_logits_fwd_bwd: bad sizes");
+  CC_REQUIRE(!dz || lddz >= ncols_pad, "cc_bce_logits_fwd_bwd: lddz too small");
+  if (batch == 0) return CC_OK;
+  bce_rows_kernel<<<batch, 256, 0, as_stream(stream)>>>(z, ldz, ybits, ywords, num_cards, ncols_pad,
+                                                       float(1.0 / count), dz, lddz, row_loss);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+int cc_softmax_kl_fwd_bwd(const float* z, int64_t ldz, const float* target, int64_t ldt, const int32_t* target_rows,
+                          int32_t rows, int32_t num_cards, int32_t ncols_pad, double grad_scale, float* dz,
+                          int64_t lddz, double* row_loss, void* stream) {
+  CC_REQUIRE(z && target && row_loss, "cc_softmax_kl_fwd_bwd: null pointer");
+  CC_REQUIRE(num_cards > 0 && ncols_pad >= num_cards, "cc_softmax_kl_fwd_bwd: bad sizes");
+  CC_REQUIRE(!dz || lddz >= ncols_pad, "cc_softmax_kl_fwd_bwd: lddz too small");
+  if (rows == 0) return CC_OK;
+  const size_t cache_bytes = size_t(num_cards) * 2 * sizeof(float);
+  cudaStream_t st = as_stream(stream);
+  if (cache_bytes <= 200 * 1024) {
+    CC_CHECK_CUDA(cudaFuncSetAttribute(softmax_kl_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)cache_bytes));
+    softmax_kl_rows_kernel<true><<<rows, 1024, cache_bytes, st>>>(z, ldz, target, ldt, target_rows, num_cards,
+                                                                 ncols_pad, float(grad_scale), dz, lddz, row_loss);
+  } else {
+    softmax_kl_rows_kernel<false><<<rows, 1024, 0, st>>>(z, ldz, target, ldt, target_rows, num_cards, ncols_pad,
+                                                         float(grad_scale), dz, lddz, row_loss);
+  }
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+int cc_loss_finalize(const double* bce_rows, int32_t nb, double bce_div, const double* kl_rows, int32_t nr,
+                     double kl_div, double reg, double* out3, void* stream) {
+  CC_REQUIRE(out3 && (nb == 0 || bce_rows) && (nr == 0 || kl_rows), "cc_loss_finalize: null pointer");
+  loss_finalize_kernel<<<1, 1024, 0, as_stream(stream)>>>(bce_rows, nb, bce_div, kl_rows, nr, kl_div, reg, out3);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+int cc_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, const int64_t* step_ptr, float lr,
+                 float beta1, float beta2, float eps, void* stream) {
+  CC_REQUIRE(params && grads && m && v && step_ptr && n >= 0, "cc_adam_step: bad arguments");
+  CC_REQUIRE((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(m) |
+              reinterpret_cast<uintptr_t>(v)) % 16 == 0, "cc_adam_step: buffers must be 16-byte aligned");
+  if (n == 0) return CC_OK;
+  const int64_t threads = ceil_div<int64_t>(n, 4);
+  adam_kernel<<<(unsigned)ceil_div<int64_t>(threads, 256), 256, 0, as_stream(stream)>>>(params, grads, m, v, n, step_ptr,
+                                                                                      lr, beta1, beta2, eps);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+int cc_sigmoid_f32(const float* z, float* out, int64_t n, void* stream) {
+  CC_REQUIRE(z && out && n >= 0, "cc_sigmoid_f32: bad arguments");
+  if (n == 0) return CC_OK;
+  sigmoid_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, as_stream(stream)>>>(z, out, n);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,385 @@
+// Graph scoring (gather-sum of rows of M in NumPy's pairwise order) and masked top-N.
+//
+// Replaces reference src/scripts/recommend.py:7-18 (simple_recs), cut_cards.py:7-18
+// (simple_cuts) and the ranking walk of src/scripts/ml_recommend.py:87-104 /
+// web/ml_recommend_web.py:46-60.
+#include "cc_common.cuh"
+
+namespace cc {
+
+// ------------------------------------------------------------- pairwise gather
+// recommend.py:10-13 sums an F-ordered fancy-index copy along its contiguous axis, so
+// NumPy evaluates every column with its pairwise algorithm (blocks <= 128 rows with 8
+// interleaved accumulators, recursive halving above that).  Reproducing that order
+// makes the float64 scores bit-identical to the reference's, hence identical ranks.
+struct Leaf { int32_t start, len, merges, cube; };
+
+__global__ void __launch_bounds__(128)
+gather_leaf_kernel(const double* __restrict__ m, int64_t ld, int32_t num_cards,
+                   const int32_t* __restrict__ rows, const int64_t* __restrict__ row_ptr,
+                   const Leaf* __restrict__ leaves, int zero_diag, double* __restrict__ partial) {
+  const Leaf lf = leaves[blockIdx.y];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= num_cards) return;
+  const int32_t* r = rows + row_ptr[lf.cube] + lf.start;
+  auto at = [&](int k) -> double {
+    const int32_t i = r[k];
+    return (zero_diag && i == j) ? 0.0 : m[int64_t(i) * ld + j];
+  };
+  double res;
+  const int n = lf.len;
+  if (n < 8) {
+    res = 0.0;
+    for (int k = 0; k < n; ++k) res += at(k);
+  } else {
+    double a[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] = at(q);
+    int k = 8;
+    for (; k < n - (n % 8); k += 8) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q] += at(k + q);
+    }
+    res = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+    for (; k < n; ++k) res += at(k);
+  }
+  partial[int64_t(blockIdx.y) * num_cards + j] = res;
+}
+
+__global__ void __launch_bounds__(128)
+gather_combine_kernel(const double* __restrict__ partial, int32_t num_cards, const Leaf* __restrict__ leaves,
+                      const int32_t* __restrict__ leaf_ptr, double* __restrict__ scores, int64_t ld_scores) {
+  const int cube = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= num_cards) return;
+  double stack[24];
+  int sp = 0;
+  for (int l = leaf_ptr[cube]; l < leaf_ptr[cube + 1]; ++l) {
+    stack[sp++] = partial[int64_t(l) * num_cards + j];
+    for (int mgs = leaves[l].merges; mgs > 0; --mgs) {
+      const double b = stack[--sp];
+      stack[sp - 1] = stack[sp - 1] + b;
+    }
+  }
+  // ufunc reduce starts from the additive identity: out = 0.0 + pairwise(...)
+  scores[int64_t(cube) * ld_scores + j] = sp > 0 ? 0.0 + stack[0] : 0.0;
+}
+
+// ---------------------------------------------------------------- masked top-N
+template <typename T> struct KeyOf;
+template <> struct KeyOf<float> {
+  using U = uint32_t; using K = unsigned long long; static constexpr int BITS = 64;
+  __device__ static U ord(float v) { v += 0.0f; U b = __float_as_uint(v); return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u); }
+};
+template <> struct KeyOf<double> {
+  using U = unsigned long long; using K = unsigned __int128; static constexpr int BITS = 96;
+  __device__ static U ord(double v) {
+    v += 0.0; U b = (U)__double_as_longlong(v);
+    return b ^ ((b >> 63) ? 0xffffffffffffffffull : 0x8000000000000000ull);
+  }
+};
+
+// composite key: (orderable score, tie word); all keys of one cube are distinct, so the
+// n-th largest is unique and {key >= it} has exactly n members.
+//   descending: larger score first, ties -> larger index first  (argsort(stable)[::-1])
+//   ascending : smaller score first, ties -> smaller index first (argsort(stable))
+template <typename T>
+__device__ __forceinline__ typename KeyOf<T>::K make_key(T v, uint32_t idx, int descending) {
+  using KO = KeyOf<T>;
+  typename KO::U u = KO::ord(v);
+  uint32_t t = idx;
+  if (!descending) { u = ~u; t = ~idx; }
+  return (typename KO::K(u) << 32) | typename KO::K(t);
+}
+
+constexpr int TOPN_THREADS = 512;
+constexpr int TOPN_MAX_SMEM_N = 2048;
+
+template <typename T>
+__global__ void __launch_bounds__(TOPN_THREADS)
+topn_masked_kernel(const T* __restrict__ scores, int64_t ld, int32_t num_cards,
+                   const int64_t* __restrict__ mask_ptr, const int32_t* __restrict__ mask_idx,
+                   int mode_only_listed, int descending, int32_t n, int32_t n_pad,
+                   int32_t* __restrict__ out_ids, T* __restrict__ out_vals, int32_t* __restrict__ out_count) {
+  using KO = KeyOf<T>;
+  using K = typename KO::K;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  K* cand = reinterpret_cast<K*>(smem_raw);                          // n_pad keys
+  uint32_t* mask = reinterpret_cast<uint32_t*>(cand + n_pad);        // ceil(C/32) words
+  __shared__ int hist[256];
+  __shared__ int s_need, s_bucket, s_digit, s_cnt;
+
+  const int cube = blockIdx.x;
+  const T* sc = scores + int64_t(cube) * ld;
+  const int words = (num_cards + 31) >> 5;
+  for (int w = threadIdx.x; w < words; w += blockDim.x) mask[w] = 0;
+  __syncthreads();
+  const int64_t mb = mask_ptr[cube], me = mask_ptr[cube + 1];
+  for (int64_t p = mb + threadIdx.x; p < me; p += blockDim.x) {
+    const int32_t c = mask_idx[p];
+    if (c >= 0 && c < num_cards) atomicOr(&mask[c >> 5], 1u << (c & 31));
+  }
+  __syncthreads();
+  // number of candidates
+  int local = 0;
+  for (int w = threadIdx.x; w < words; w += blockDim.x) local += __popc(mask[w]);
+  local = warp_sum(local);
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt, local);
+  __syncthreads();
+  const int listed = s_cnt;
+  const int m = mode_only_listed ? listed : num_cards - listed;
+  const int n_eff = min(n, m);
+  __syncthreads();
+  auto is_cand = [&](int e) -> bool {
+    const bool in = (mask[e >> 5] >> (e & 31)) & 1u;
+    return mode_only_listed ? in : !in;
+  };
+
+  K prefix = 0;
+  bool exact_bucket = false;
+  if (n_eff > 0) {
+    if (threadIdx.x == 0) s_need = n_eff;
+    for (int pass = 0; pass < KO::BITS / 8; ++pass) {
+      const int shift = KO::BITS - 8 * (pass + 1);
+      for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
+      __syncthreads();
+      for (int e = threadIdx.x; e < num_cards; e += blockDim.x) {
+        if (!is_cand(e)) continue;
+        const K key = make_key<T>(sc[e], (uint32_t)e, descending);
+        if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8)))
+          atomicAdd(&hist[int((key >> shift) & 0xff)], 1);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int need = s_need, cum = 0, b = 255;
+        for (; b > 0; --b) {
+          if (cum + hist[b] >= need) break;
+          cum += hist[b];
+        }
+        s_need = need - cum; s_digit = b; s_bucket = hist[b];
+      }
+      __syncthreads();
+      prefix |= K((unsigned)s_digit) << shift;
+      if (s_bucket == s_need) { exact_bucket = true; break; }   // whole bucket is taken
+    }
+  }
+  (void)exact_bucket;
+  // collect {key >= prefix}: exactly n_eff keys
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  if (n_eff > 0) {
+    for (int e = threadIdx.x; e < num_cards; e += blockDim.x) {
+      if (!is_cand(e)) continue;
+      const K key = make_key<T>(sc[e], (uint32_t)e, descending);
+      if (key >= prefix) {
+        const int slot = atomicAdd(&s_cnt, 1);
+        if (slot < n_pad) cand[slot] = key;
+      }
+    }
+  }
+  __syncthreads();
+  const int got = min(s_cnt, n_pad);
+  for (int i = got + threadIdx.x; i < n_pad; i += blockDim.x) cand[i] = 0;
+  __syncthreads();
+  // bitonic sort, descending
+  for (int k = 2; k <= n_pad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const K a = cand[i], b = cand[ixj];
+          const bool up = (i & k) == 0;      // "up" blocks hold larger keys first
+          if (up ? (a < b) : (a > b)) { cand[i] = b; cand[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int32_t id = -1; T v = T(0);
+    if (i < n_eff) {
+      uint32_t t = (uint32_t)(cand[i] & 0xffffffffu);
+      if (!descending) t = ~t;
+      id = (int32_t)t; v = sc[id];
+    }
+    out_ids[int64_t(cube) * n + i] = id;
+    if (out_vals) out_vals[int64_t(cube) * n + i] = v;
+  }
+  if (threadIdx.x == 0 && out_count) out_count[cube] = n_eff;
+}
+
+// Full ranking (n > TOPN_MAX_SMEM_N): one CTA per cube bitonic-sorts every composite key
+// in a global (L2-resident) workspace of next_pow2(C) keys.
+template <typename T>
+__global__ void __launch_bounds__(1024)
+rank_all_kernel(const T* __restrict__ scores, int64_t ld, int32_t num_cards,
+                const int64_t* __restrict__ mask_ptr, const int32_t* __restrict__ mask_idx,
+                int mode_only_listed, int descending, int32_t n, int32_t p2,
+                typename KeyOf<T>::K* __restrict__ work, int32_t* __restrict__ out_ids, T* __restrict__ out_vals,
+                int32_t* __restrict__ out_count) {
+  using K = typename KeyOf<T>::K;
+  extern __shared__ uint32_t mask[];
+  __shared__ int s_cnt;
+  const int cube = blockIdx.x;
+  const T* sc = scores + int64_t(cube) * ld;
+  K* keys = work + int64_t(cube) * p2;
+  const int words = (num_cards + 31) >> 5;
+  for (int w = threadIdx.x; w < words; w += blockDim.x) mask[w] = 0;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  for (int64_t p = mask_ptr[cube] + threadIdx.x; p < mask_ptr[cube + 1]; p += blockDim.x) {
+    const int32_t c = mask_idx[p];
+    if (c >= 0 && c < num_cards) atomicOr(&mask[c >> 5], 1u << (c & 31));
+  }
+  __syncthreads();
+  int local = 0;
+  for (int e = threadIdx.x; e < p2; e += blockDim.x) {
+    K key = 0;
+    if (e < num_cards) {
+      const bool in = (mask[e >> 5] >> (e & 31)) & 1u;
+      if (mode_only_listed ? in : !in) { key = make_key<T>(sc[e], (uint32_t)e, descending); ++local; }
+    }
+    keys[e] = key;
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt, local);
+  __syncthreads();
+  const int n_eff = min(n, s_cnt);
+  for (int k = 2; k <= p2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < p2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const K a = keys[i], b = keys[ixj];
+          const bool up = (i & k) == 0;
+          if (up ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int32_t id = -1; T v = T(0);
+    if (i < n_eff) {
+      uint32_t t = (uint32_t)(keys[i] & 0xffffffffu);
+      if (!descending) t = ~t;
+      id = (int32_t)t; v = sc[id];
+    }
+    out_ids[int64_t(cube) * n + i] = id;
+    if (out_vals) out_vals[int64_t(cube) * n + i] = v;
+  }
+  if (threadIdx.x == 0 && out_count) out_count[cube] = n_eff;
+}
+
+static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+template <typename T>
+int topn_launch(const T* scores, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
+                const int32_t* mask_idx, int mode_only_listed, int descending, int32_t n, void* workspace,
+                int64_t workspace_bytes, int32_t* out_ids, T* out_vals, int32_t* out_count, cudaStream_t st) {
+  using K = typename KeyOf<T>::K;
+  CC_REQUIRE(scores && mask_ptr && out_ids, "cc_topn_masked: null pointer");
+  CC_REQUIRE(num_cards > 0 && batch >= 0 && n > 0 && ld >= num_cards, "cc_topn_masked: bad sizes");
+  CC_REQUIRE(mask_idx || true, "unused");
+  if (batch == 0) return CC_OK;
+  const size_t mask_bytes = size_t((num_cards + 31) / 32) * 4;
+  if (n <= TOPN_MAX_SMEM_N) {
+    const int n_pad = next_pow2(n < 2 ? 2 : n);
+    const size_t smem = size_t(n_pad) * sizeof(K) + mask_bytes;
+    CC_REQUIRE(smem <= 200 * 1024, "cc_topn_masked: C=%d needs %zu bytes of shared memory", num_cards, smem);
+    CC_CHECK_CUDA(cudaFuncSetAttribute(topn_masked_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topn_masked_kernel<T><<<batch, TOPN_THREADS, smem, st>>>(scores, ld, num_cards, mask_ptr, mask_idx,
+                                                            mode_only_listed, descending, n, n_pad, out_ids,
+                                                            out_vals, out_count);
+  } else {
+    const int p2 = next_pow2(num_cards);
+    const int64_t need = int64_t(batch) * p2 * int64_t(sizeof(K));
+    CC_REQUIRE(workspace && workspace_bytes >= need,
+               "cc_topn_masked: full ranking needs a %lld-byte workspace (got %lld)", (long long)need,
+               (long long)workspace_bytes);
+    CC_REQUIRE(mask_bytes <= 200 * 1024, "cc_topn_masked: C too large for the mask");
+    CC_CHECK_CUDA(cudaFuncSetAttribute(rank_all_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mask_bytes));
+    rank_all_kernel<T><<<batch, 1024, mask_bytes, st>>>(scores, ld, num_cards, mask_ptr, mask_idx, mode_only_listed,
+                                                        descending, n, p2, reinterpret_cast<K*>(workspace), out_ids,
+                                                        out_vals, out_count);
+  }
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+// host-side leaf plan of NumPy's pairwise sum over n rows
+static void plan_pairwise(int start, int n, int cube, Leaf* out, int* count) {
+  if (n <= 128) { out[(*count)++] = Leaf{start, n, 0, cube}; return; }
+  int n2 = n / 2; n2 -= n2 % 8;
+  plan_pairwise(start, n2, cube, out, count);
+  plan_pairwise(start + n2, n - n2, cube, out, count);
+  out[*count - 1].merges += 1;
+}
+
+}  // namespace cc
+
+using namespace cc;
+
+extern "C" {
+
+int64_t cc_pairwise_leaf_count(int64_t n_rows) {
+  if (n_rows <= 128) return 1;
+  int64_t n2 = n_rows / 2; n2 -= n2 % 8;
+  return cc_pairwise_leaf_count(n2) + cc_pairwise_leaf_count(n_rows - n2);
+}
+
+// Builds the leaf plan on the host (plan_host: int32 [total_leaves][4], leaf_ptr_host: int32 [batch+1]).
+int cc_pairwise_plan_host(const int64_t* row_ptr_host, int32_t batch, int32_t* plan_host, int32_t* leaf_ptr_host) {
+  CC_REQUIRE(row_ptr_host && plan_host && leaf_ptr_host && batch >= 0, "cc_pairwise_plan_host: bad arguments");
+  int count = 0;
+  leaf_ptr_host[0] = 0;
+  for (int b = 0; b < batch; ++b) {
+    const int64_t n = row_ptr_host[b + 1] - row_ptr_host[b];
+    CC_REQUIRE(n >= 0 && n < (1 << 30), "cc_pairwise_plan_host: bad row count");
+    if (n > 0) plan_pairwise(0, (int)n, b, reinterpret_cast<Leaf*>(plan_host), &count);
+    leaf_ptr_host[b + 1] = count;
+  }
+  return CC_OK;
+}
+
+int cc_score_gather_f64(const double* m, int64_t ld, int32_t num_cards, const int32_t* rows, const int64_t* row_ptr,
+                        int32_t batch, const int32_t* plan, const int32_t* leaf_ptr, int32_t total_leaves,
+                        int zero_diag, double* partial_ws, double* scores, int64_t ld_scores, void* stream) {
+  CC_REQUIRE(m && rows && row_ptr && plan && leaf_ptr && partial_ws && scores, "cc_score_gather_f64: null pointer");
+  CC_REQUIRE(num_cards > 0 && batch >= 0 && ld >= num_cards && ld_scores >= num_cards, "cc_score_gather_f64: bad sizes");
+  if (batch == 0) return CC_OK;
+  cudaStream_t st = as_stream(stream);
+  const int cb = ceil_div(num_cards, 128);
+  if (total_leaves > 0) {
+    gather_leaf_kernel<<<dim3(cb, total_leaves), 128, 0, st>>>(m, ld, num_cards, rows, row_ptr,
+                                                              reinterpret_cast<const Leaf*>(plan), zero_diag, partial_ws);
+    CC_CHECK_LAUNCH();
+  }
+  gather_combine_kernel<<<dim3(cb, batch), 128, 0, st>>>(partial_ws, num_cards, reinterpret_cast<const Leaf*>(plan),
+                                                         leaf_ptr, scores, ld_scores);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+int64_t cc_topn_workspace_bytes(int32_t num_cards, int32_t batch, int32_t n, int is_f64) {
+  if (n <= TOPN_MAX_SMEM_N) return 0;
+  return int64_t(batch) * next_pow2(num_cards) * (is_f64 ? 16 : 8);
+}
+
+int cc_topn_masked_f32(const float* scores, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
+                       const int32_t* mask_idx, int mode_only_listed, int descending, int32_t n, void* workspace,
+                       int64_t workspace_bytes, int32_t* out_ids, float* out_vals, int32_t* out_count, void* stream) {
+  return topn_launch<float>(scores, ld, num_cards, batch, mask_ptr, mask_idx, mode_only_listed, descending, n,
+                            workspace, workspace_bytes, out_ids, out_vals, out_count, as_stream(stream));
+}
+
+int cc_topn_masked_f64(const double* scores, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
+                       const int32_t* mask_idx, int mode_only_listed, int descending, int32_t n, void* workspace,
+                       int64_t workspace_bytes, int32_t* out_ids, double* out_vals, int32_t* out_count, void* stream) {
+  return topn_launch<double>(scores, ld, num_cards, batch, mask_ptr, mask_idx, mode_only_listed, descending, n,
+                             workspace, workspace_bytes, out_ids, out_vals, out_count, as_stream(stream));
+}
+
+}  // extern "C"

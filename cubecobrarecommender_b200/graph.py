@@ -1,0 +1,165 @@
+"""Device-side co-occurrence graph and graph recommender (host logic above the C ABI).
+
+Mirrors, on CSR cubes resident in HBM:
+  * ``utils.create_adjacency_matrix``   reference ``src/non_ml/utils.py:75-92``
+  * ``y_mtx`` / ``neg_sampler``         reference ``src/ml/train.py:69-71``, ``src/ml/generator.py:30``
+  * ``simple_recs`` / ``simple_cuts``   reference ``src/scripts/recommend.py:7-18``, ``cut_cards.py:7-18``
+
+Multi-GPU: cubes are sharded across ranks; each rank counts its own shard into a private
+int32 ``(C, C)`` and one NCCL ``all_reduce(SUM)`` combines them (exact, order independent).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+from .sparse import CubeCSR
+
+
+@dataclass
+class CoocGraph:
+    num_cards: int
+    counts: torch.Tensor                 # int32 (C, C)
+    m64: torch.Tensor | None = None      # float64 (C, C)   M   (utils.py:85-89)
+    mhat: torch.Tensor | None = None     # float32 (C, ld)  M-hat (train.py:69-71)
+    rowsum: torch.Tensor | None = None   # float64 (C,)
+    neg_sampler: torch.Tensor | None = None   # float64 (C,)  (generator.py:30)
+
+
+def upload_csr(csr: CubeCSR, device):
+    indptr = torch.from_numpy(np.ascontiguousarray(csr.indptr, dtype=np.int64)).to(device)
+    indices = torch.from_numpy(np.ascontiguousarray(csr.indices, dtype=np.int32)).to(device)
+    return indptr, indices
+
+
+def count_cooccurrence(indptr: torch.Tensor, indices: torch.Tensor, num_cubes: int, num_cards: int,
+                       counts: torch.Tensor | None = None, accumulate: bool = False,
+                       bits: torch.Tensor | None = None) -> torch.Tensor:
+    """int32 counts of the cubes in (indptr, indices); bit-pack + popcount kernels."""
+    lib = _lib.load()
+    dev = indptr.device
+    kw, cpad = lib.cc_bits_words(num_cubes), lib.cc_bits_cpad(num_cards)
+    if bits is None:
+        bits = torch.empty((max(kw, 1), cpad), dtype=torch.int32, device=dev)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    if counts is None:
+        counts = torch.empty((num_cards, num_cards), dtype=torch.int32, device=dev)
+        accumulate = False
+    st = stream_ptr()
+    call("cc_bitpack_cubes", ptr(indptr), ptr(indices), num_cubes, num_cards, ptr(bits), ptr(bad), st)
+    call("cc_cooc_count", ptr(bits), num_cubes, num_cards, ptr(counts), counts.stride(0), int(accumulate), st)
+    if int(bad.item()):
+        raise ValueError(f"card index out of range [0, {num_cards})")
+    return counts
+
+
+def normalise(counts: torch.Tensor, *, want_m64=True, want_mhat=True, want_neg=True, force_diag=None,
+              mhat_ld: int | None = None) -> CoocGraph:
+    c = counts.shape[0]
+    dev = counts.device
+    m64 = torch.empty((c, c), dtype=torch.float64, device=dev) if want_m64 else None
+    mhat = None
+    if want_mhat:
+        ld = mhat_ld or c
+        mhat = torch.zeros((c, ld), dtype=torch.float32, device=dev) if ld != c else \
+            torch.empty((c, c), dtype=torch.float32, device=dev)
+    rowsum = torch.empty(c, dtype=torch.float64, device=dev)
+    st = stream_ptr()
+    call("cc_row_normalise", ptr(counts), counts.stride(0), c, ptr(m64), c, ptr(mhat),
+         mhat.stride(0) if mhat is not None else 0, ptr(rowsum), int(force_diag is not None),
+         float(force_diag or 0.0), st)
+    neg = None
+    if want_neg:
+        ws = torch.empty(_lib.load().cc_col_mass_workspace_bytes(c) // 8, dtype=torch.float64, device=dev)
+        neg = torch.empty(c, dtype=torch.float64, device=dev)
+        call("cc_col_mass", ptr(counts), counts.stride(0), c, ptr(rowsum), ptr(ws), ptr(neg), st)
+    return CoocGraph(c, counts, m64, mhat, rowsum, neg)
+
+
+def build_graph(csr: CubeCSR, device="cuda", *, allreduce=True, group=None, **kw) -> CoocGraph:
+    """Counts of this rank's cubes (+ all_reduce when torch.distributed is initialised with
+    more than one rank, i.e. the cubes are sharded) and the normalised matrices."""
+    import torch.distributed as dist
+    indptr, indices = upload_csr(csr, device)
+    counts = count_cooccurrence(indptr, indices, csr.num_cubes, csr.num_cards)
+    if allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    return normalise(counts, **kw)
+
+
+def create_adjacency_matrix_host(csr: CubeCSR, force_diag=None, return_counts=False):
+    """Host in / host out through the single C-ABI call a reference binding would make."""
+    c = csr.num_cards
+    m = np.empty((c, c), dtype=np.float64)
+    counts = np.empty((c, c), dtype=np.int32) if return_counts else None
+    indptr = np.ascontiguousarray(csr.indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(csr.indices, dtype=np.int32)
+    call("cc_create_adjacency_matrix_host", ptr(indptr), ptr(indices), csr.num_cubes, c,
+         int(force_diag is not None), float(force_diag or 0.0), ptr(m), ptr(counts))
+    return (m, counts) if return_counts else m
+
+
+# --------------------------------------------------------------------------- top-N
+def topn_masked(scores: torch.Tensor, mask_ptr: torch.Tensor, mask_idx: torch.Tensor, n: int, *,
+                only_listed=False, descending=True, want_vals=True):
+    """Rank each row of ``scores`` (float32 or float64, (batch, >=C)); see cc_topn_masked_*."""
+    lib = _lib.load()
+    batch = scores.shape[0]
+    c = int(scores.shape[1])
+    dev = scores.device
+    is64 = scores.dtype == torch.float64
+    if scores.dtype not in (torch.float32, torch.float64):
+        raise TypeError("scores must be float32 or float64")
+    ids = torch.empty((batch, n), dtype=torch.int32, device=dev)
+    vals = torch.empty((batch, n), dtype=scores.dtype, device=dev) if want_vals else None
+    cnt = torch.empty(batch, dtype=torch.int32, device=dev)
+    wsb = lib.cc_topn_workspace_bytes(c, batch, n, int(is64))
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
+    call("cc_topn_masked_f64" if is64 else "cc_topn_masked_f32", ptr(scores), scores.stride(0), c, batch,
+         ptr(mask_ptr), ptr(mask_idx), int(only_listed), int(descending), n, ptr(ws), wsb, ptr(ids), ptr(vals),
+         ptr(cnt), stream_ptr())
+    return ids, vals, cnt
+
+
+class GraphRecommender:
+    """M resident in HBM (float64); batched ``simple_recs`` / ``simple_cuts``."""
+
+    def __init__(self, m64: torch.Tensor):
+        assert m64.dtype == torch.float64 and m64.dim() == 2
+        self.m = m64.contiguous()
+        self.num_cards = m64.shape[0]
+
+    def scores(self, csr: CubeCSR, zero_diag=False) -> torch.Tensor:
+        lib = _lib.load()
+        dev = self.m.device
+        batch = csr.num_cubes
+        row_ptr_h = np.ascontiguousarray(csr.indptr, dtype=np.int64)
+        total_leaves = int(sum(lib.cc_pairwise_leaf_count(int(n)) for n in np.diff(row_ptr_h) if n > 0))
+        plan_h = np.zeros((max(total_leaves, 1), 4), dtype=np.int32)
+        leaf_ptr_h = np.zeros(batch + 1, dtype=np.int32)
+        call("cc_pairwise_plan_host", ptr(row_ptr_h), batch, ptr(plan_h), ptr(leaf_ptr_h))
+        rows = torch.from_numpy(np.ascontiguousarray(csr.indices, dtype=np.int32)).to(dev)
+        row_ptr = torch.from_numpy(row_ptr_h).to(dev)
+        plan = torch.from_numpy(plan_h).to(dev)
+        leaf_ptr = torch.from_numpy(leaf_ptr_h).to(dev)
+        partial = torch.empty((max(total_leaves, 1), self.num_cards), dtype=torch.float64, device=dev)
+        scores = torch.empty((batch, self.num_cards), dtype=torch.float64, device=dev)
+        call("cc_score_gather_f64", ptr(self.m), self.m.stride(0), self.num_cards, ptr(rows), ptr(row_ptr), batch,
+             ptr(plan), ptr(leaf_ptr), total_leaves, int(zero_diag), ptr(partial), ptr(scores), scores.stride(0),
+             stream_ptr())
+        return scores, row_ptr, rows
+
+    def recs(self, csr: CubeCSR, n: int):
+        """Top-``n`` missing cards per cube, descending score (recommend.py:7-18)."""
+        scores, row_ptr, rows = self.scores(csr, zero_diag=False)
+        return topn_masked(scores, row_ptr, rows, n, only_listed=False, descending=True)
+
+    def cuts(self, csr: CubeCSR, n: int):
+        """``n`` lowest-scored in-cube cards per cube, ascending (cut_cards.py:7-18)."""
+        scores, row_ptr, rows = self.scores(csr, zero_diag=True)
+        return topn_masked(scores, row_ptr, rows, n, only_listed=True, descending=False)

@@ -1,0 +1,219 @@
+"""One training step of the regularised DAE on one GPU (and its data-parallel form).
+
+Reference: ``autoencoder.fit(generator)`` -- per step ``DataGenerator.__getitem__``
+(``src/ml/generator.py:38-61``) followed by the Keras train step compiled at
+``src/ml/train.py:83-88``:
+
+    loss = 1.0 * BCE(y, D1(E(x))) + reg * KLD(M-hat[r], D2(E(I[r])))       Adam(lr=1e-3)
+
+Everything stays in HBM: cubes as CSR, x as index lists, y as bit rows, I[r] as the row
+ids r, M-hat as a float32 (C, ld) matrix whose rows r are read in place.
+
+Data parallel (one process per GPU): each rank takes B/G cubes and R/G regulariser rows,
+scales its losses by the GLOBAL B*C and R, and one all_reduce(SUM) over the flat gradient
+buffer makes every rank apply the same Adam update.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .._lib import call, ptr, stream_ptr
+from .model import (CC_Recommender, ENC_NAMES, HIDDEN, SparseBatch, bag_bwd, bag_fwd, colsum, dec_names, gemm)
+
+KERAS_ADAM = dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)
+
+
+def alias_table(p: np.ndarray, device):
+    """Vose alias table of a probability vector (neg_sampler, reference generator.py:30)."""
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    prob = np.empty(len(p), dtype=np.float32)
+    alias = np.empty(len(p), dtype=np.int32)
+    call("cc_alias_build_host", ptr(p), len(p), ptr(prob), ptr(alias))
+    return torch.from_numpy(prob).to(device), torch.from_numpy(alias).to(device)
+
+
+class DAEEngine:
+    def __init__(self, model: CC_Recommender, mhat: torch.Tensor, *, batch: int, reg_rows: int | None = None,
+                 reg: float = 0.1, max_cube_size: int = 720, global_batch: int | None = None,
+                 global_reg_rows: int | None = None, group=None, adam=None):
+        self.model = model
+        self.store = model.store
+        self.dev = model.device
+        self.C = model.N
+        self.cpad = (self.C + 127) // 128 * 128
+        self.B = int(batch)
+        self.R = int(reg_rows if reg_rows is not None else batch)
+        self.reg = float(reg)
+        self.global_B = int(global_batch or self.B)
+        self.global_R = int(global_reg_rows or self.R)
+        self.group = group
+        self.adam = dict(KERAS_ADAM, **(adam or {}))
+        self.mhat = mhat
+        assert mhat.dtype == torch.float32 and mhat.shape[0] == self.C and mhat.shape[1] >= self.C
+        self.precision = model.precision
+        self.max_cube_size = int(max_cube_size)
+        self.x_stride = (int(max_cube_size * 1.8) + 8 + 3) // 4 * 4
+        self.yw = self.cpad // 32
+        self.launches = 0          # kernels launched by the last step (for bench's gpu_launches)
+        self._alloc()
+
+    # -- buffers --------------------------------------------------------------------
+    def _alloc(self):
+        d, f32 = self.dev, torch.float32
+        B, R, T = self.B, self.R, self.B + self.R
+        e = lambda *s: torch.empty(s, dtype=f32, device=d)
+        self.x_idx = torch.zeros((B, self.x_stride), dtype=torch.int32, device=d)
+        self.x_len = torch.zeros(B, dtype=torch.int32, device=d)
+        self.x_start = torch.arange(B, dtype=torch.int64, device=d) * self.x_stride
+        self.y_bits = torch.zeros((B, self.yw), dtype=torch.int32, device=d)
+        self.reg_rows = torch.zeros(max(R, 1), dtype=torch.int32, device=d)
+        self.reg_start = torch.arange(max(R, 1), dtype=torch.int64, device=d)
+        self.reg_len = torch.ones(max(R, 1), dtype=torch.int32, device=d)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=d)
+        self.flips = torch.zeros(B, dtype=torch.int32, device=d)
+        # activations (encoder runs main rows then reg rows in one matrix)
+        self.a = [e(T, w) for w in HIDDEN]                          # a1..a4
+        self.md = [e(B, w) for w in (128, 256, 512)]
+        self.rd = [e(max(R, 1), w) for w in (128, 256, 512)]
+        self.z1 = e(B, self.cpad)                                    # logits -> dlogits in place
+        self.z2 = e(max(R, 1), self.cpad)
+        self.ga = [e(T, w) for w in HIDDEN]
+        self.gmd = [e(B, w) for w in (128, 256, 512)]
+        self.grd = [e(max(R, 1), w) for w in (128, 256, 512)]
+        self.row_bce = torch.zeros(B, dtype=torch.float64, device=d)
+        self.row_kl = torch.zeros(max(R, 1), dtype=torch.float64, device=d)
+        self.loss3 = torch.zeros(3, dtype=torch.float64, device=d)
+        lib = _lib.load()
+        ws = max(lib.cc_colsum_workspace_bytes(T, max(self.cpad, max(HIDDEN))), 1024)
+        self.cs_ws = torch.empty(ws // 4, dtype=f32, device=d)
+
+    # -- inputs ---------------------------------------------------------------------
+    def set_batch(self, x: SparseBatch, y_bits: torch.Tensor, reg_rows: torch.Tensor):
+        """Inject a fixed (x, y, r) batch (parity tests hold the noise output fixed)."""
+        assert x.batch == self.B
+        self._x = x
+        self.y_bits.zero_()
+        self.y_bits[:, :y_bits.shape[1]].copy_(y_bits)
+        if self.R:
+            self.reg_rows[:self.R].copy_(reg_rows.to(torch.int32))
+
+    def sample_batch(self, indptr, indices, batch_ids, alias_prob, alias_idx, noise=0.2, noise_std=0.1, seed=0):
+        """Noise function F + reg-row draw on the device (reference generator.py:38-103)."""
+        st = stream_ptr()
+        call("cc_noise", ptr(indptr), ptr(indices), ptr(batch_ids), self.B, self.C, ptr(alias_prob), ptr(alias_idx),
+             float(noise), float(noise_std), int(seed), ptr(self.store.step), self.max_cube_size, self.x_stride,
+             ptr(self.x_idx), ptr(self.x_len), ptr(self.y_bits), self.yw, ptr(self.flips), ptr(self.overflow), st)
+        if self.R:
+            call("cc_sample_reg_rows", ptr(alias_prob), ptr(alias_idx), self.C, self.R, int(seed) ^ 0x5DEECE66D,
+                 ptr(self.store.step), ptr(self.reg_rows), st)
+        self._x = SparseBatch(self.x_idx, self.x_start, self.x_len)
+        self.launches += 2
+
+    # -- the step -------------------------------------------------------------------
+    def forward_backward(self):
+        s, B, R, T = self.store, self.B, self.R, self.B + self.R
+        pr = self.precision
+        x = self._x
+        P, G = s.p, s.g
+        n_launch = 0
+        # ---------------- forward ----------------
+        a1 = self.a[0]
+        bag_fwd(P("encoder_e1/kernel"), x.idx, x.row_start, x.row_len, P("encoder_e1/bias"), a1[:B]); n_launch += 1
+        if R:
+            bag_fwd(P("encoder_e1/kernel"), self.reg_rows, self.reg_start, self.reg_len, P("encoder_e1/bias"), a1[B:])
+            n_launch += 1
+        for i, name in enumerate(ENC_NAMES[1:]):
+            gemm(self.a[i], P(name + "/kernel"), self.a[i + 1], bias=P(name + "/bias"), relu=True, precision=pr)
+            n_launch += 1
+        towers = [("main", self.a[3][:B], self.md, self.z1, B)]
+        if R:
+            towers.append(("reg", self.a[3][B:], self.rd, self.z2, R))
+        for prefix, h, acts, z, rows in towers:
+            names = dec_names(prefix)
+            for i in range(3):
+                gemm(h, P(names[i] + "/kernel"), acts[i], bias=P(names[i] + "/bias"), relu=True, precision=pr)
+                h = acts[i]; n_launch += 1
+            gemm(h, P(names[3] + "/kernel"), z[:, :self.C], bias=P(names[3] + "/bias"), precision=pr); n_launch += 1
+        # ---------------- losses (logits -> dlogits in place) ----------------
+        st = stream_ptr()
+        call("cc_bce_logits_fwd_bwd", ptr(self.z1), self.z1.stride(0), ptr(self.y_bits), self.yw, B, self.C, self.cpad,
+             float(self.global_B) * float(self.C), ptr(self.z1), self.z1.stride(0), ptr(self.row_bce), st)
+        n_launch += 1
+        if R:
+            call("cc_softmax_kl_fwd_bwd", ptr(self.z2), self.z2.stride(0), ptr(self.mhat), self.mhat.stride(0),
+                 ptr(self.reg_rows), R, self.C, self.cpad, self.reg / float(self.global_R), ptr(self.z2),
+                 self.z2.stride(0), ptr(self.row_kl), st)
+            n_launch += 1
+        call("cc_loss_finalize", ptr(self.row_bce), B, float(self.global_B) * float(self.C), ptr(self.row_kl), R,
+             float(self.global_R), self.reg, ptr(self.loss3), st)
+        n_launch += 1
+        # ---------------- backward: decoders ----------------
+        ga4 = self.ga[3]
+        gtowers = [("main", self.a[3][:B], self.md, self.gmd, self.z1, ga4[:B])]
+        if R:
+            gtowers.append(("reg", self.a[3][B:], self.rd, self.grd, self.z2, ga4[B:]))
+        for prefix, h_in, acts, gacts, dz, g_in in gtowers:
+            names = dec_names(prefix)
+            dzc = dz[:, :self.C]
+            gemm(acts[2], dzc, G(names[3] + "/kernel"), transa=True, precision=pr)
+            colsum(dzc, G(names[3] + "/bias"), self.cs_ws)
+            gemm(dzc, P(names[3] + "/kernel"), gacts[2], transb=True, mask=acts[2], precision=pr)
+            n_launch += 4
+            for i in (2, 1):
+                gemm(acts[i - 1], gacts[i], G(names[i] + "/kernel"), transa=True, precision=pr)
+                colsum(gacts[i], G(names[i] + "/bias"), self.cs_ws)
+                gemm(gacts[i], P(names[i] + "/kernel"), gacts[i - 1], transb=True, mask=acts[i - 1], precision=pr)
+                n_launch += 4
+            gemm(h_in, gacts[0], G(names[0] + "/kernel"), transa=True, precision=pr)
+            colsum(gacts[0], G(names[0] + "/bias"), self.cs_ws)
+            gemm(gacts[0], P(names[0] + "/kernel"), g_in, transb=True, mask=h_in, precision=pr)
+            n_launch += 4
+        if not R:
+            for prefix in ("reg",):
+                for n_ in dec_names(prefix):
+                    G(n_ + "/kernel").zero_(); G(n_ + "/bias").zero_()
+        # ---------------- backward: shared encoder (main + reg rows together) ----------------
+        for i in (3, 2, 1):
+            name = ENC_NAMES[i]
+            gemm(self.a[i - 1], self.ga[i], G(name + "/kernel"), transa=True, precision=pr)
+            colsum(self.ga[i], G(name + "/bias"), self.cs_ws)
+            gemm(self.ga[i], P(name + "/kernel"), self.ga[i - 1], transb=True, mask=self.a[i - 1], precision=pr)
+            n_launch += 4
+        g1 = self.ga[0]
+        colsum(g1, G("encoder_e1/bias"), self.cs_ws); n_launch += 2
+        gw1 = G("encoder_e1/kernel")
+        gw1.zero_(); n_launch += 1
+        bag_bwd(g1[:B], x.idx, x.row_start, x.row_len, gw1); n_launch += 1
+        if R:
+            bag_bwd(g1[B:], self.reg_rows, self.reg_start, self.reg_len, gw1); n_launch += 1
+        self.launches += n_launch
+
+    def allreduce_grads(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.store.grads, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(self.loss3, op=dist.ReduceOp.SUM, group=self.group)
+
+    def apply_adam(self):
+        s, a = self.store, self.adam
+        st = stream_ptr()
+        call("cc_adam_step", ptr(s.params), ptr(s.grads), ptr(s.adam_m), ptr(s.adam_v), s.total, ptr(s.step),
+             a["lr"], a["beta1"], a["beta2"], a["eps"], st)
+        call("cc_step_increment", ptr(s.step), st)
+        self.launches += 2
+
+    def train_step(self):
+        """forward + backward + (all_reduce) + Adam on the batch set by set_batch/sample_batch.
+        Returns the device tensor loss3 = [bce, kl, bce + reg*kl] (no synchronisation)."""
+        self.forward_backward()
+        self.allreduce_grads()
+        self.apply_adam()
+        return self.loss3
+
+    def check_overflow(self):
+        v = int(self.overflow.item())
+        if v:
+            raise RuntimeError("noise kernel overflow: " + ("cube larger than max_cube_size" if v == 1
+                                                            else "x list longer than x_stride"))

@@ -1,0 +1,281 @@
+"""Regularised denoising auto-encoder: host-side mirror of reference ``src/ml/model.py``.
+
+``CC_Recommender(num_cards)`` keeps the reference's surface -- attributes ``encoder``,
+``decoder``, ``decoder_for_reg`` and ``call((x, identity)) -> (reconstruction,
+decoded_for_reg)`` (reference ``model.py:89-125``) -- over flat float32 parameter buffers in
+HBM and the kernels of libcubecobra_b200.so.  The 24 tensors carry the Keras names
+(``encoder_e1/kernel`` ... ``reg_reconstruction/bias``), kernels stored ``(in, out)``.
+
+``DAEEngine`` is the train step of reference ``src/ml/train.py:83-102`` (one ``fit`` step):
+forward of both towers, BCE + reg*KLD, backward, TF-style Adam.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .._lib import call, ptr, stream_ptr
+from ..sparse import CubeCSR
+
+HIDDEN = (512, 256, 128, 64)
+ENC_NAMES = ("encoder_e1", "encoder_e2", "encoder_e3", "encoder_bottleneck")
+
+
+def dec_names(prefix):
+    return (f"{prefix}_d1", f"{prefix}_d2", f"{prefix}_d3", f"{prefix}_reconstruction")
+
+
+def layer_specs(num_cards: int):
+    c = num_cards
+    enc = [("encoder_e1", c, 512), ("encoder_e2", 512, 256), ("encoder_e3", 256, 128),
+           ("encoder_bottleneck", 128, 64)]
+    def dec(p):
+        return [(f"{p}_d1", 64, 128), (f"{p}_d2", 128, 256), (f"{p}_d3", 256, 512),
+                (f"{p}_reconstruction", 512, c)]
+    return enc + dec("main") + dec("reg")
+
+
+def _round4(n):
+    return (n + 3) // 4 * 4
+
+
+class ParamStore:
+    """Flat float32 buffers (params, grads, Adam m and v) with named 2-D/1-D views.
+    One buffer = one Adam launch and one NCCL all_reduce."""
+
+    def __init__(self, num_cards: int, device):
+        self.num_cards = num_cards
+        self.device = torch.device(device)
+        self.layout = {}
+        off = 0
+        for name, fi, fo in layer_specs(num_cards):
+            self.layout[name + "/kernel"] = (off, (fi, fo)); off += _round4(fi * fo)
+            self.layout[name + "/bias"] = (off, (fo,)); off += _round4(fo)
+        self.total = off
+        self.params = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.grads = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.adam_m = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.adam_v = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.step = torch.zeros(1, dtype=torch.int64, device=self.device)   # completed steps
+
+    def view(self, buf, key):
+        off, shape = self.layout[key]
+        return buf[off:off + int(np.prod(shape))].view(*shape)
+
+    def p(self, key): return self.view(self.params, key)
+    def g(self, key): return self.view(self.grads, key)
+
+    def num_parameters(self):
+        return sum(int(np.prod(s)) for _, s in self.layout.values())
+
+    def load_dict(self, params: dict):
+        for k, (off, shape) in self.layout.items():
+            t = torch.as_tensor(np.asarray(params[k]), dtype=torch.float32).reshape(shape)
+            self.p(k).copy_(t)
+
+    def to_dict(self, buf=None) -> dict:
+        buf = self.params if buf is None else buf
+        return {k: self.view(buf, k).detach().cpu().numpy().copy() for k in self.layout}
+
+    def init_glorot(self, seed=0):
+        """Keras defaults: glorot_uniform kernels, zero biases (SURVEY.md §8d seeding)."""
+        from ..synth import glorot_uniform
+        gen = torch.Generator().manual_seed(seed)
+        out = {}
+        for name, fi, fo in layer_specs(self.num_cards):
+            out[name + "/kernel"] = glorot_uniform(fi, fo, gen)
+            out[name + "/bias"] = np.zeros(fo, dtype=np.float32)
+        self.load_dict(out)
+
+
+# ------------------------------------------------------------------ kernel wrappers
+def gemm(a, b, c, *, transa=False, transb=False, bias=None, relu=False, mask=None, accumulate=False,
+         precision="fp32"):
+    """c = epi(op(a) @ op(b)) on 2-D row-major float32 tensors (strides = leading dims)."""
+    m, n = c.shape
+    k = a.shape[0] if transa else a.shape[1]
+    if precision == "fp32":
+        call("cc_gemm_f32_simt", int(transa), int(transb), m, n, k, ptr(a), a.stride(0), ptr(b), b.stride(0),
+             ptr(c), c.stride(0), ptr(bias), int(relu), ptr(mask), mask.stride(0) if mask is not None else 0,
+             int(accumulate), stream_ptr())
+    else:
+        from . import tensorcore
+        tensorcore.gemm(a, b, c, transa=transa, transb=transb, bias=bias, relu=relu, mask=mask,
+                        accumulate=accumulate, precision=precision)
+    return c
+
+
+def colsum(x, out, ws, accumulate=False):
+    m, n = x.shape
+    call("cc_colsum_f32", ptr(x), x.stride(0), m, n, ptr(ws), ptr(out), int(accumulate), stream_ptr())
+
+
+def bag_fwd(w, idx, row_start, row_len, bias, out, relu=True):
+    call("cc_bag_fwd", ptr(w), w.stride(0), w.shape[1], ptr(idx), ptr(row_start), ptr(row_len), out.shape[0],
+         ptr(bias), ptr(out), out.stride(0), int(relu), stream_ptr())
+
+
+def bag_bwd(g, idx, row_start, row_len, dw):
+    call("cc_bag_bwd", ptr(g), g.stride(0), dw.shape[1], ptr(idx), ptr(row_start), ptr(row_len), g.shape[0],
+         ptr(dw), dw.stride(0), stream_ptr())
+
+
+class SparseBatch:
+    """Index lists on the device: row b = idx[row_start[b] : row_start[b] + row_len[b]]."""
+
+    def __init__(self, idx, row_start, row_len):
+        self.idx, self.row_start, self.row_len = idx, row_start, row_len
+
+    @property
+    def batch(self): return self.row_len.shape[0]
+
+    @classmethod
+    def from_csr(cls, csr: CubeCSR, device):
+        idx = torch.from_numpy(np.ascontiguousarray(csr.indices, dtype=np.int32)).to(device)
+        start = torch.from_numpy(np.ascontiguousarray(csr.indptr[:-1], dtype=np.int64)).to(device)
+        ln = torch.from_numpy(np.diff(csr.indptr).astype(np.int32)).to(device)
+        if idx.numel() == 0:
+            idx = torch.zeros(1, dtype=torch.int32, device=device)
+        return cls(idx, start, ln)
+
+    @classmethod
+    def from_rows(cls, rows: torch.Tensor):
+        n = rows.shape[0]
+        return cls(rows, torch.arange(n, dtype=torch.int64, device=rows.device),
+                   torch.ones(n, dtype=torch.int32, device=rows.device))
+
+
+def _as_sparse(x, num_cards, device) -> SparseBatch:
+    if isinstance(x, SparseBatch):
+        return x
+    if isinstance(x, CubeCSR):
+        return SparseBatch.from_csr(x, device)
+    if isinstance(x, torch.Tensor):
+        x = x.detach().cpu().numpy()
+    x = np.asarray(x)
+    if x.ndim == 1:
+        x = x[None, :]
+    if x.shape[1] != num_cards:
+        raise ValueError(f"expected (batch, {num_cards}) cube vectors, got {x.shape}")
+    if not np.isin(x, (0, 1)).all():
+        raise ValueError("the sparse first layer needs binary cube vectors")
+    return SparseBatch.from_csr(CubeCSR.from_dense(x), device)
+
+
+class _Tower:
+    """``model.encoder`` / ``model.decoder`` / ``model.decoder_for_reg`` callables."""
+
+    def __init__(self, model, kind):
+        self.model, self.kind = model, kind
+
+    def __call__(self, x, training=None):
+        m = self.model
+        if self.kind == "encoder":
+            return m._encode(_as_sparse(x, m.N, m.device))
+        h = torch.as_tensor(x, dtype=torch.float32, device=m.device) if not isinstance(x, torch.Tensor) else x.to(m.device)
+        z = m._decode(h, "main" if self.kind == "decoder" else "reg")
+        if self.kind == "decoder":
+            out = torch.empty_like(z)
+            call("cc_sigmoid_f32", ptr(z), ptr(out), z.numel(), stream_ptr())
+            return out
+        return torch.softmax(z, dim=1)   # API-parity path only; the train step uses the fused loss kernel
+
+
+class CC_Recommender:
+    """Reference ``model.py:82-125``: encoder E, sigmoid decoder D1, softmax decoder D2."""
+
+    def __init__(self, num_cards, device="cuda", seed=0, precision="fp32"):
+        _lib.load()
+        self.N = int(num_cards)
+        self.device = torch.device(device)
+        self.precision = precision
+        self.store = ParamStore(self.N, self.device)
+        self.store.init_glorot(seed)
+        self.encoder = _Tower(self, "encoder")
+        self.decoder = _Tower(self, "decoder")
+        self.decoder_for_reg = _Tower(self, "reg")
+
+    # -- pieces ---------------------------------------------------------------
+    def _encode(self, sb: SparseBatch) -> torch.Tensor:
+        s = self.store
+        b = sb.batch
+        h = torch.empty((b, 512), dtype=torch.float32, device=self.device)
+        bag_fwd(s.p("encoder_e1/kernel"), sb.idx, sb.row_start, sb.row_len, s.p("encoder_e1/bias"), h)
+        for name, width in zip(ENC_NAMES[1:], HIDDEN[1:]):
+            o = torch.empty((b, width), dtype=torch.float32, device=self.device)
+            gemm(h, s.p(name + "/kernel"), o, bias=s.p(name + "/bias"), relu=True, precision=self.precision)
+            h = o
+        return h
+
+    def _decode(self, h: torch.Tensor, prefix: str) -> torch.Tensor:
+        """Logits (batch, C) of decoder ``prefix`` ('main' | 'reg')."""
+        s = self.store
+        b = h.shape[0]
+        names = dec_names(prefix)
+        for name, width in zip(names[:3], (128, 256, 512)):
+            o = torch.empty((b, width), dtype=torch.float32, device=self.device)
+            gemm(h.contiguous(), s.p(name + "/kernel"), o, bias=s.p(name + "/bias"), relu=True,
+                 precision=self.precision)
+            h = o
+        z = torch.empty((b, self.N), dtype=torch.float32, device=self.device)
+        gemm(h, s.p(names[3] + "/kernel"), z, bias=s.p(names[3] + "/bias"), precision=self.precision)
+        return z
+
+    def call(self, inputs, training=None):
+        """``(x, identity) -> (reconstruction, decoded_for_reg)`` (reference model.py:100-125).
+        ``identity`` may be one-hot rows of I or an integer vector of row ids."""
+        x, identity = inputs
+        rec = self.decoder(self.encoder(x))
+        if isinstance(identity, (np.ndarray, torch.Tensor)) and np.asarray(identity.cpu() if isinstance(identity, torch.Tensor) else identity).ndim == 2:
+            ident = np.asarray(identity.cpu() if isinstance(identity, torch.Tensor) else identity)
+            if not ((ident.sum(1) == 1).all() and np.isin(ident, (0, 1)).all()):
+                raise ValueError("identity rows must be one-hot")
+            rows = ident.argmax(1)
+        else:
+            rows = np.asarray(identity.cpu() if isinstance(identity, torch.Tensor) else identity)
+        rows_t = torch.as_tensor(rows, dtype=torch.int32, device=self.device)
+        reg = self.decoder_for_reg(self._encode(SparseBatch.from_rows(rows_t)))
+        return rec, reg
+
+    __call__ = call
+
+    # -- weights ----------------------------------------------------------------
+    def get_weights_dict(self):
+        return self.store.to_dict()
+
+    def set_weights_dict(self, params):
+        self.store.load_dict(params)
+
+    def save(self, path):
+        """Own checkpoint format (npz of the 24 Keras-named tensors + Adam slots + step);
+        replaces ``autoencoder.save(dest, save_format='tf')`` (reference train.py:112-115)."""
+        import os
+        os.makedirs(path, exist_ok=True)
+        blob = {k: v for k, v in self.store.to_dict().items()}
+        blob.update({"adam_m/" + k: v for k, v in self.store.to_dict(self.store.adam_m).items()})
+        blob.update({"adam_v/" + k: v for k, v in self.store.to_dict(self.store.adam_v).items()})
+        blob["step"] = self.store.step.cpu().numpy()
+        blob["num_cards"] = np.int64(self.N)
+        np.savez(os.path.join(path, "cc_recommender.npz"), **blob)
+
+    @classmethod
+    def load(cls, path, device="cuda", precision="fp32"):
+        import os
+        blob = np.load(os.path.join(path, "cc_recommender.npz"))
+        model = cls(int(blob["num_cards"]), device=device, precision=precision)
+        model.store.load_dict({k: blob[k] for k in model.store.layout})
+        for k in model.store.layout:
+            if "adam_m/" + k in blob:
+                model.store.view(model.store.adam_m, k).copy_(torch.as_tensor(blob["adam_m/" + k]))
+                model.store.view(model.store.adam_v, k).copy_(torch.as_tensor(blob["adam_v/" + k]))
+        if "step" in blob:
+            model.store.step.copy_(torch.as_tensor(blob["step"]))
+        return model
+
+
+def load_model(path, device="cuda", precision="fp32"):
+    """Stand-in for ``tensorflow.keras.models.load_model`` (reference ml_recommend.py:54)."""
+    return CC_Recommender.load(path, device=device, precision=precision)

@@ -1,0 +1,78 @@
+"""Sparse cube containers (host CSR and device batches).
+
+The reference keeps cubes as a dense float64 ``(K, C)`` matrix
+(reference ``src/non_ml/utils.py:57-73``); every kernel here consumes CSR instead:
+``indptr`` int64 ``[K+1]`` and ``indices`` int32 ``[nnz]``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass
+class CubeCSR:
+    indptr: np.ndarray      # int64 [K+1]
+    indices: np.ndarray     # int32 [nnz]
+    num_cards: int
+
+    @property
+    def num_cubes(self) -> int:
+        return len(self.indptr) - 1
+
+    @property
+    def max_size(self) -> int:
+        return int(np.diff(self.indptr).max()) if self.num_cubes else 0
+
+    @classmethod
+    def from_dense(cls, cubes) -> "CubeCSR":
+        from .synth import dense_to_csr
+        cubes = np.asarray(cubes)
+        if cubes.ndim == 1:
+            cubes = cubes[None, :]
+        ip, ix = dense_to_csr(cubes)
+        return cls(ip, ix, cubes.shape[1])
+
+    @classmethod
+    def from_lists(cls, lists, num_cards: int) -> "CubeCSR":
+        # duplicates collapse, like `cubes[counter, card_ids] = 1` (utils.py:71)
+        rows = [np.unique(np.asarray(l, dtype=np.int64)) for l in lists]
+        sizes = np.array([len(r) for r in rows], dtype=np.int64)
+        indptr = np.zeros(len(rows) + 1, dtype=np.int64)
+        np.cumsum(sizes, out=indptr[1:])
+        indices = (np.concatenate(rows) if rows else np.zeros(0)).astype(np.int32)
+        if len(indices) and (indices.min() < 0 or indices.max() >= num_cards):
+            raise ValueError("card index out of range")
+        return cls(indptr, indices, num_cards)
+
+    def to_dense(self, dtype=np.float64) -> np.ndarray:
+        from .synth import csr_to_dense
+        return csr_to_dense(self.indptr, self.indices, self.num_cards, dtype)
+
+    def rows(self, sel) -> "CubeCSR":
+        sel = np.asarray(sel, dtype=np.int64)
+        sizes = self.indptr[sel + 1] - self.indptr[sel]
+        indptr = np.zeros(len(sel) + 1, dtype=np.int64)
+        np.cumsum(sizes, out=indptr[1:])
+        if len(sel):
+            take = np.concatenate([np.arange(self.indptr[s], self.indptr[s + 1]) for s in sel]) \
+                if len(sel) < 4096 else _gather_ranges(self.indptr, sel, indptr)
+            indices = self.indices[take]
+        else:
+            indices = np.zeros(0, dtype=np.int32)
+        return CubeCSR(indptr, indices, self.num_cards)
+
+    def shard(self, rank: int, world: int) -> "CubeCSR":
+        """Contiguous cube shard for data-parallel ranks."""
+        k = self.num_cubes
+        lo, hi = (k * rank) // world, (k * (rank + 1)) // world
+        ip = self.indptr[lo:hi + 1] - self.indptr[lo]
+        return CubeCSR(ip.copy(), self.indices[self.indptr[lo]:self.indptr[hi]].copy(), self.num_cards)
+
+
+def _gather_ranges(src_indptr, sel, dst_indptr):
+    total = int(dst_indptr[-1])
+    out = np.arange(total, dtype=np.int64)
+    starts = np.repeat(src_indptr[sel] - dst_indptr[:-1], np.diff(dst_indptr))
+    return out + starts

@@ -1,0 +1,168 @@
+/* cubecobra_b200.h -- C ABI of libcubecobra_b200.so (sm_100a only).
+ *
+ * The reference (CubeArtisan/CubeCobraRecommender) is pure Python and defines no FFI;
+ * these entry points are what a ctypes binding inside the reference's own functions
+ * would call (INTEGRATION.md shows the stubs).  Each group cites the reference code it
+ * replaces as file:line relative to the reference repository root.
+ *
+ * Conventions
+ *   - every function returns int: CC_OK (0) or a negative CC_ERR_*; the message is
+ *     available per host thread from cc_last_error();
+ *   - unless a name ends in `_host`, every pointer is a DEVICE pointer on the current
+ *     CUDA device; the caller owns every buffer, including workspaces (sizes from the
+ *     matching *_bytes() helper); nothing is allocated, freed or synchronised behind the
+ *     caller's back (the `_host` entry points are the exception: they own their device
+ *     scratch and return after their stream has drained);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it;
+ *   - matrices are row-major with an explicit leading dimension in ELEMENTS;
+ *   - re-entrant across devices: one host thread (or process) per GPU, no global state.
+ */
+#ifndef CUBECOBRA_B200_H
+#define CUBECOBRA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CC_VERSION 100
+#define CC_OK 0
+#define CC_ERR_ARGUMENT (-1)
+#define CC_ERR_CUDA (-2)
+#define CC_ERR_DEVICE (-3)
+#define CC_ERR_UNSUPPORTED (-4)
+
+const char* cc_last_error(void);
+int cc_version(void);
+int cc_device_check(void);
+
+/* ------------------------------------------------------------------------------------
+ * (1) Co-occurrence / conditional-probability graph
+ *     replaces utils.create_adjacency_matrix          src/non_ml/utils.py:75-92
+ *              y_mtx (M-hat) construction             src/ml/train.py:69-71
+ *              DataGenerator.neg_sampler              src/ml/generator.py:30
+ * Cubes arrive as CSR (indptr int64 [K+1], indices int32 [nnz]) instead of the dense
+ * float64 (K, C) matrix of utils.build_cubes (src/non_ml/utils.py:57-73).
+ * ---------------------------------------------------------------------------------- */
+int64_t cc_bits_words(int64_t num_cubes);   /* rows  of the bit matrix (32 cubes per word, padded) */
+int64_t cc_bits_cpad(int32_t num_cards);    /* columns of the bit matrix (cards, padded to the tile) */
+/* bits: uint32 [cc_bits_words(K)][cc_bits_cpad(C)], zeroed and filled; *bad_flag != 0 afterwards
+ * if a card index was outside [0, C). */
+int cc_bitpack_cubes(const int64_t* indptr, const int32_t* indices, int64_t num_cubes, int32_t num_cards,
+                     uint32_t* bits, int* bad_flag, void* stream);
+/* counts[i][j] (int32, ld >= C) = number of cubes containing both i and j; accumulate != 0 adds. */
+int cc_cooc_count(const uint32_t* bits, int64_t num_cubes, int32_t num_cards, int32_t* counts, int64_t ld,
+                  int accumulate, void* stream);
+/* From counts: M (float64, nullable), M-hat (float32, nullable), rowsum of y (float64, nullable). */
+int cc_row_normalise(const int32_t* counts, int64_t ld, int32_t num_cards, double* m64, int64_t ld_m,
+                     float* mhat, int64_t ld_mhat, double* rowsum, int has_force_diag, double force_diag,
+                     void* stream);
+int64_t cc_col_mass_workspace_bytes(int32_t num_cards);
+/* neg_sampler[j] = sum_i Mhat[i][j] / sum(Mhat), float64, deterministic order. */
+int cc_col_mass(const int32_t* counts, int64_t ld, int32_t num_cards, const double* rowsum, double* workspace,
+                double* neg_sampler, void* stream);
+/* Host-buffer drop-in for utils.create_adjacency_matrix: CSR in, float64 (C, C) out
+ * (and the int32 counts if counts_host != NULL).  H2D + kernels + D2H inside the call. */
+int cc_create_adjacency_matrix_host(const int64_t* indptr_host, const int32_t* indices_host, int64_t num_cubes,
+                                    int32_t num_cards, int has_force_diag, double force_diag, double* m_host,
+                                    int32_t* counts_host);
+
+/* ------------------------------------------------------------------------------------
+ * (2) Graph scoring and masked top-N
+ *     replaces simple_recs                            src/scripts/recommend.py:7-18
+ *              simple_cuts                            src/scripts/cut_cards.py:7-18
+ *              ranking walk of ml_recommend           src/scripts/ml_recommend.py:87-104
+ *                                                     web/ml_recommend_web.py:46-60
+ * Scores are summed in NumPy's pairwise order so float64 scores are bit-identical.
+ * Tie rule: descending -> larger index first; ascending -> smaller index first
+ * (== numpy argsort(kind='stable'), reversed for descending).
+ * ---------------------------------------------------------------------------------- */
+int64_t cc_pairwise_leaf_count(int64_t n_rows);
+/* plan_host: int32 [total_leaves][4]; leaf_ptr_host: int32 [batch+1] */
+int cc_pairwise_plan_host(const int64_t* row_ptr_host, int32_t batch, int32_t* plan_host, int32_t* leaf_ptr_host);
+/* scores[b][j] = sum over rows[row_ptr[b]..row_ptr[b+1]) of M[row][j]  (M[i][i] read as 0 if zero_diag);
+ * partial_ws: float64 [total_leaves][C]. */
+int cc_score_gather_f64(const double* m, int64_t ld, int32_t num_cards, const int32_t* rows, const int64_t* row_ptr,
+                        int32_t batch, const int32_t* plan, const int32_t* leaf_ptr, int32_t total_leaves,
+                        int zero_diag, double* partial_ws, double* scores, int64_t ld_scores, void* stream);
+int64_t cc_topn_workspace_bytes(int32_t num_cards, int32_t batch, int32_t n, int is_f64);
+/* Per cube b: rank the cards NOT listed in mask (mode_only_listed == 0) or ONLY the listed ones (== 1);
+ * out_ids int32 [batch][n] (-1 padded), out_vals [batch][n] (nullable), out_count int32 [batch] (nullable). */
+int cc_topn_masked_f32(const float* scores, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
+                       const int32_t* mask_idx, int mode_only_listed, int descending, int32_t n, void* workspace,
+                       int64_t workspace_bytes, int32_t* out_ids, float* out_vals, int32_t* out_count, void* stream);
+int cc_topn_masked_f64(const double* scores, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
+                       const int32_t* mask_idx, int mode_only_listed, int descending, int32_t n, void* workspace,
+                       int64_t workspace_bytes, int32_t* out_ids, double* out_vals, int32_t* out_count, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (3) Noise function F and batch assembly
+ *     replaces DataGenerator.generate_data            src/ml/generator.py:74-103
+ *              reg_indices draw                       src/ml/generator.py:47-51
+ * ---------------------------------------------------------------------------------- */
+int cc_alias_build_host(const double* p_host, int32_t n, float* prob_host, int32_t* alias_host);
+int64_t cc_noise_smem_bytes(int32_t num_cards, int32_t max_size);
+/* batch_ids (nullable): which cubes of the CSR form this batch.  Outputs: x_idx int32 [batch][x_stride],
+ * x_len int32 [batch], y_bits uint32 [batch][y_words] (nullable), flips_out int32 [batch] (nullable),
+ * *overflow_flag != 0 if a cube exceeded max_size (1) or x_stride (2).  step_ptr: device int64 step counter
+ * (nullable = 0) mixed into the Philox counter so CUDA-graph replays draw fresh noise. */
+int cc_noise(const int64_t* indptr, const int32_t* indices, const int32_t* batch_ids, int32_t batch,
+             int32_t num_cards, const float* alias_prob, const int32_t* alias_idx, float noise_mean, float noise_std,
+             uint64_t seed, const int64_t* step_ptr, int32_t max_size, int32_t x_stride, int32_t* x_idx,
+             int32_t* x_len, uint32_t* y_bits, int64_t y_words, int32_t* flips_out, int* overflow_flag, void* stream);
+int cc_sample_reg_rows(const float* alias_prob, const int32_t* alias_idx, int32_t num_cards, int32_t n, uint64_t seed,
+                       const int64_t* step_ptr, int32_t* rows, void* stream);
+int cc_cubes_to_bits(const int32_t* idx, const int64_t* row_start, const int32_t* row_len, int32_t batch,
+                     int32_t num_cards, uint32_t* bits, int64_t words, void* stream);
+int cc_step_increment(int64_t* step_ptr, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (4) Encoder first layer on sparse cubes (embedding bag)
+ *     replaces Dense(512)(x) on 0/1 rows              src/ml/model.py:27,36 (and :122 for I[r])
+ * ---------------------------------------------------------------------------------- */
+int cc_bag_fwd(const float* w, int64_t ldw, int32_t hidden, const int32_t* idx, const int64_t* row_start,
+               const int32_t* row_len, int32_t batch, const float* bias, float* out, int64_t ldo, int relu,
+               void* stream);
+int cc_bag_bwd(const float* g, int64_t ldg, int32_t hidden, const int32_t* idx, const int64_t* row_start,
+               const int32_t* row_len, int32_t batch, float* dw, int64_t ldw, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (5) Dense layers
+ *     replaces Dense layers of Encoder / Decoder      src/ml/model.py:27-33, 58-64
+ * C[M,N] = epi(op(A) op(B)); transa: A given as [K,M]; transb: B given as [N,K].
+ * epilogue order: + bias[N], relu, * (mask[M,N] > 0), then store or accumulate.
+ * ---------------------------------------------------------------------------------- */
+int cc_gemm_f32_simt(int transa, int transb, int m, int n, int k, const float* a, int64_t lda, const float* b,
+                     int64_t ldb, float* c, int64_t ldc, const float* bias, int relu, const float* mask,
+                     int64_t ldmask, int accumulate, void* stream);
+int64_t cc_colsum_workspace_bytes(int m, int n);
+int cc_colsum_f32(const float* x, int64_t ld, int m, int n, float* workspace, float* out, int accumulate,
+                  void* stream);
+int cc_relu_mask_f32(float* x, int64_t ldx, const float* act, int64_t lda, int m, int n, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (6) Losses and optimiser (Keras 2.5 conventions)
+ *     replaces compile(adam, [bce, kld], loss_weights) src/ml/train.py:83-88
+ * ---------------------------------------------------------------------------------- */
+/* row_loss[b] = sum_c bce(z[b][c], y[b][c]); dz = (sigmoid(z) - y)/count (nullable); columns
+ * [num_cards, ncols_pad) of dz are zeroed. */
+int cc_bce_logits_fwd_bwd(const float* z, int64_t ldz, const uint32_t* ybits, int64_t ywords, int32_t batch,
+                          int32_t num_cards, int32_t ncols_pad, double count, float* dz, int64_t lddz,
+                          double* row_loss, void* stream);
+/* row r uses target row target_rows[r] (nullable = r); dz = grad_scale*(q*S - t'*1[unclipped]). */
+int cc_softmax_kl_fwd_bwd(const float* z, int64_t ldz, const float* target, int64_t ldt, const int32_t* target_rows,
+                          int32_t rows, int32_t num_cards, int32_t ncols_pad, double grad_scale, float* dz,
+                          int64_t lddz, double* row_loss, void* stream);
+/* out3 (float64 [3]) = { sum(bce_rows)/bce_div, sum(kl_rows)/kl_div, bce + reg*kl } */
+int cc_loss_finalize(const double* bce_rows, int32_t nb, double bce_div, const double* kl_rows, int32_t nr,
+                     double kl_div, double reg, double* out3, void* stream);
+/* TF-style Adam over flat buffers; the step number is *step_ptr + 1 (device int64). */
+int cc_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, const int64_t* step_ptr, float lr,
+                 float beta1, float beta2, float eps, void* stream);
+int cc_sigmoid_f32(const float* z, float* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUBECOBRA_B200_H */

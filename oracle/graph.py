@@ -27,7 +27,7 @@ def cooc_counts(indptr: np.ndarray, indices: np.ndarray, num_cards: int) -> np.n
                       shape=(k, num_cards))
     x.sum_duplicates()
     x.data[:] = 1  # duplicates collapse: build_cubes assigns 1 (utils.py:71)
-    return np.asarray((x.T @ x).todense(), dtype=np.int64)
+    return np.ascontiguousarray((x.T @ x).todense(), dtype=np.int64)
 
 
 def adjacency_from_counts(cnt: np.ndarray, force_diag=None) -> np.ndarray:
@@ -35,7 +35,7 @@ def adjacency_from_counts(cnt: np.ndarray, force_diag=None) -> np.ndarray:
     (reference ``utils.py:85-89``); optional ``fill_diagonal`` (``:90-91``)."""
     cnt = np.asarray(cnt)
     diag = np.diagonal(cnt).astype(np.float64)
-    m = cnt.astype(np.float64)
+    m = np.ascontiguousarray(cnt, dtype=np.float64).copy()
     nz = diag != 0
     m[nz] = m[nz] / diag[nz, None]
     if force_diag is not None:

@@ -1,0 +1,196 @@
+"""CUDA DAE kernels and train step vs the oracle (fixed weights, fixed noise output), through
+the C ABI.  Tolerances: fp32 path loss <= 1e-5 rel (north-star bar 1e-3), grads <= 2e-4 of max."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from cubecobrarecommender_b200.ml import engine as E, model as M
+from cubecobrarecommender_b200.sparse import CubeCSR
+from cubecobrarecommender_b200.synth import csr_to_dense, synth_cubes_csr
+from oracle import dae as od, graph as og
+
+
+def _bits_from_dense(y):
+    b, c = y.shape
+    w = (c + 127) // 128 * 128 // 32
+    out = np.zeros((b, w), dtype=np.uint32)
+    rr, cc = np.nonzero(y == 1)
+    np.bitwise_or.at(out, (rr, cc // 32), (np.uint32(1) << (cc % 32).astype(np.uint32)))
+    return out.view(np.int32)
+
+
+def _problem(c=300, k=200, b=64, r=48, seed=11):
+    ip, ix = synth_cubes_csr(k, c, size_lo=10, size_hi=60, seed=seed)
+    dense = csr_to_dense(ip, ix, c)
+    mh = og.m_hat(og.create_adjacency_matrix(dense))
+    rng = np.random.default_rng(seed)
+    x = dense[:b].copy(); y = dense[:b].copy()
+    for i in range(b):
+        inc = np.where(x[i] == 1)[0]; exc = np.where(x[i] == 0)[0]
+        cut = rng.choice(inc, size=max(1, len(inc) // 5), replace=False)
+        x[i, cut] = 0; y[i, cut[:len(cut) // 4]] = 0
+        x[i, rng.choice(exc, size=len(cut), replace=False)] = 1
+    rows = rng.integers(0, c, size=r)
+    return c, x, y, rows, mh
+
+
+@pytest.mark.parametrize("ta,tb,m,n,k", [(0, 0, 130, 70, 33), (0, 1, 64, 257, 100), (1, 0, 129, 128, 300),
+                                         (1, 1, 17, 19, 23), (0, 0, 256, 512, 64)])
+def test_gemm_simt_all_layouts(ta, tb, m, n, k):
+    g = torch.Generator(device="cuda").manual_seed(m * n + k)
+    a = torch.randn((k, m) if ta else (m, k), device="cuda", generator=g)
+    b = torch.randn((n, k) if tb else (k, n), device="cuda", generator=g)
+    bias = torch.randn(n, device="cuda", generator=g)
+    mask = torch.randn(m, n, device="cuda", generator=g)
+    ref = (a.t() if ta else a).double() @ (b.t() if tb else b).double() + bias.double()
+    ref = torch.relu(ref) * (mask > 0)
+    c = torch.full((m, n), 7.0, device="cuda")
+    M.gemm(a, b, c, transa=bool(ta), transb=bool(tb), bias=bias, relu=True, mask=mask)
+    assert torch.allclose(c.double(), ref, atol=1e-4, rtol=1e-5)
+    c2 = torch.ones((m, n), device="cuda")
+    M.gemm(a, b, c2, transa=bool(ta), transb=bool(tb), accumulate=True)
+    ref2 = (a.t() if ta else a).double() @ (b.t() if tb else b).double() + 1
+    assert torch.allclose(c2.double(), ref2, atol=1e-4, rtol=1e-5)
+
+
+def test_bag_fwd_bwd_vs_dense():
+    c, h, b = 700, 512, 37
+    g = torch.Generator(device="cuda").manual_seed(3)
+    w = torch.randn(c, h, device="cuda", generator=g)
+    bias = torch.randn(h, device="cuda", generator=g)
+    ip, ix = synth_cubes_csr(b, c, size_lo=0, size_hi=300, seed=4)
+    ip[1] = ip[0]                      # noqa: an empty cube row is legal
+    csr = CubeCSR(ip, ix, c)
+    # rebuild a valid CSR with an empty first cube
+    lists = [ix[ip[i]:ip[i + 1]] for i in range(b)]; lists[0] = np.zeros(0, np.int32)
+    csr = CubeCSR.from_lists(lists, c)
+    sb = M.SparseBatch.from_csr(csr, "cuda")
+    out = torch.empty(b, h, device="cuda")
+    M.bag_fwd(w, sb.idx, sb.row_start, sb.row_len, bias, out, relu=True)
+    x = torch.tensor(csr.to_dense(np.float32)).cuda()
+    ref = torch.relu(x.double() @ w.double() + bias.double())
+    assert torch.allclose(out.double(), ref, atol=2e-4, rtol=1e-5)
+    gout = torch.randn(b, h, device="cuda", generator=g) * (torch.rand(b, h, device="cuda", generator=g) > 0.5)
+    dw = torch.zeros(c, h, device="cuda")
+    M.bag_bwd(gout, sb.idx, sb.row_start, sb.row_len, dw)
+    assert torch.allclose(dw.double(), x.double().t() @ gout.double(), atol=2e-4, rtol=1e-5)
+
+
+def test_loss_kernels_vs_oracle():
+    c, b = 333, 21
+    cpad = (c + 127) // 128 * 128
+    rng = np.random.default_rng(0)
+    z = (rng.standard_normal((b, c)) * 4).astype(np.float32); z[0, :5] = [60, -60, 0, 100, -100]
+    y = (rng.random((b, c)) < 0.1).astype(np.float64)
+    zt = torch.zeros(b, cpad, device="cuda"); zt[:, :c] = torch.tensor(z).cuda()
+    dz = torch.full((b, cpad), 9.0, device="cuda")
+    rl = torch.zeros(b, dtype=torch.float64, device="cuda")
+    yb = torch.tensor(_bits_from_dense(y)).cuda()
+    E.call("cc_bce_logits_fwd_bwd", E.ptr(zt), cpad, E.ptr(yb), yb.shape[1], b, c, cpad, float(b * c), E.ptr(dz), cpad,
+           E.ptr(rl), E.stream_ptr())
+    z64 = z.astype(np.float64)
+    assert abs(rl.sum().item() / (b * c) - od.bce_from_logits_np(z64, y)) < 1e-6
+    ref_dz = (1 / (1 + np.exp(-z64)) - y) / (b * c)
+    assert np.abs(dz[:, :c].cpu().numpy() - ref_dz).max() < 1e-9
+    assert (dz[:, c:] == 0).all()
+    # softmax-KL with clipped entries (a huge logit drives most q below 1e-7)
+    z2 = (rng.standard_normal((b, c)) * 3).astype(np.float32); z2[3, 7] = 40.0
+    t = rng.random((c, c)); t[t < 0.7] = 0; t /= t.sum(1, keepdims=True)
+    rows = rng.integers(0, c, size=b).astype(np.int32)
+    z2t = torch.zeros(b, cpad, device="cuda"); z2t[:, :c] = torch.tensor(z2).cuda()
+    tt = torch.tensor(t.astype(np.float32)).cuda()
+    dz2 = torch.full((b, cpad), 9.0, device="cuda")
+    E.call("cc_softmax_kl_fwd_bwd", E.ptr(z2t), cpad, E.ptr(tt), c, E.ptr(torch.tensor(rows).cuda()), b, c, cpad,
+           0.1 / b, E.ptr(dz2), cpad, E.ptr(rl), E.stream_ptr())
+    t32 = t.astype(np.float32).astype(np.float64)[rows]
+    q = od.softmax_np(z2.astype(np.float64))
+    assert abs(rl.sum().item() / b - od.kld_np(t32, q)) < 2e-6 * abs(od.kld_np(t32, q))
+    tc = np.clip(t32, 1e-7, 1); un = (q >= 1e-7) & (q <= 1)
+    ref = 0.1 / b * (q * (tc * un).sum(1, keepdims=True) - tc * un)
+    got = dz2[:, :c].cpu().numpy()
+    # entries whose q sits within float rounding of the 1e-7 clip may flip sides
+    edge = np.abs(q - 1e-7) < 1e-12
+    assert np.abs(got - ref)[~edge].max() < 1e-8
+    assert (dz2[:, c:] == 0).all()
+
+
+def test_adam_matches_tf_style_oracle():
+    n = 1003
+    rng = np.random.default_rng(1)
+    p = rng.standard_normal(n).astype(np.float32); g = rng.standard_normal(n).astype(np.float32)
+    pt, gt = torch.tensor(p).cuda(), torch.tensor(g).cuda()
+    buf = torch.zeros(1008, device="cuda"); buf[:n] = pt
+    gb = torch.zeros(1008, device="cuda"); gb[:n] = gt
+    m = torch.zeros(1008, device="cuda"); v = torch.zeros(1008, device="cuda")
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    P = {"w": p.astype(np.float64)}; Mo = {"w": np.zeros(n)}; Vo = {"w": np.zeros(n)}
+    for t in range(1, 4):
+        E.call("cc_adam_step", E.ptr(buf), E.ptr(gb), E.ptr(m), E.ptr(v), n, E.ptr(step), 1e-3, 0.9, 0.999, 1e-7,
+               E.stream_ptr())
+        E.call("cc_step_increment", E.ptr(step), E.stream_ptr())
+        od.adam_step_np(P, {"w": g.astype(np.float64)}, Mo, Vo, t)
+        assert np.abs(buf[:n].cpu().numpy() - P["w"]).max() < 5e-7
+    assert int(step.item()) == 3 and (buf[n:] == 0).all()
+
+
+@pytest.mark.parametrize("r", [48, 0])
+def test_train_steps_match_oracle(r):
+    c, x, y, rows, mh = _problem(r=max(r, 1))
+    rows = rows[:r]
+    params = od.init_params(c, seed=0)
+    rng = np.random.default_rng(5)
+    for kname in params:
+        if kname.endswith("bias"):
+            params[kname] = (rng.standard_normal(params[kname].shape) * 0.05).astype(np.float32)
+    model = M.CC_Recommender(c, device="cuda")
+    model.set_weights_dict(params)
+    mhat = torch.tensor(mh.astype(np.float32)).cuda()
+    eng = E.DAEEngine(model, mhat, batch=x.shape[0], reg_rows=r, reg=0.1, max_cube_size=80)
+    sb = M.SparseBatch.from_csr(CubeCSR.from_dense(x), "cuda")
+    eng.set_batch(sb, torch.tensor(_bits_from_dense(y)).cuda(), torch.tensor(rows).cuda())
+    # oracle in float64 on the float32 targets Keras would see
+    p64 = {k: v.astype(np.float64) for k, v in params.items()}
+    m64 = {k: np.zeros_like(v) for k, v in p64.items()}; v64 = {k: np.zeros_like(v) for k, v in p64.items()}
+    t32 = mh.astype(np.float32).astype(np.float64)[rows] if r else np.zeros((0, c))
+    for step in range(1, 4):
+        if r:
+            (tot, bce, kl), grads = od.loss_and_grads_np(p64, x, y, rows, t32, 0.1)
+        else:
+            (tot, bce, kl), grads = od.loss_and_grads_np(p64, x, y, np.zeros(0, np.int64), np.zeros((0, c)), 0.0)
+            tot = bce
+        eng.forward_backward()
+        got = eng.loss3.cpu().numpy()
+        assert abs(got[0] - bce) / bce < 1e-5
+        if r:
+            assert abs(got[1] - kl) / kl < 1e-5
+            assert abs(got[2] - tot) / tot < 1e-5
+        gd = model.store.to_dict(model.store.grads)
+        for kname, gref in grads.items():
+            if not r and kname.startswith("reg_"):
+                continue
+            scale = np.abs(gref).max() + 1e-30
+            assert np.abs(gd[kname] - gref).max() / scale < 2e-4, (step, kname)
+        eng.apply_adam()
+        od.adam_step_np(p64, grads, m64, v64, step)
+    pd = model.get_weights_dict()
+    for kname, pref in p64.items():
+        if not r and kname.startswith("reg_"):
+            continue
+        assert np.abs(pd[kname] - pref).max() < 3e-4, kname   # 3 Adam steps move weights by <= 3e-3
+
+
+def test_model_call_api_parity():
+    c, x, y, rows, mh = _problem(c=200, b=8, r=5)
+    params = od.init_params(c, seed=1)
+    model = M.CC_Recommender(c, device="cuda")
+    model.set_weights_dict(params)
+    eye_rows = np.zeros((5, c)); eye_rows[np.arange(5), rows] = 1
+    rec, reg = model((x, eye_rows))
+    z1, z2, _ = od.forward_np(params, x, rows)
+    assert np.abs(rec.cpu().numpy() - 1 / (1 + np.exp(-z1))).max() < 1e-5
+    assert np.abs(reg.cpu().numpy() - od.softmax_np(z2)).max() < 1e-6
+    lat = model.encoder(x)
+    assert lat.shape == (8, 64)

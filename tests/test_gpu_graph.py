@@ -1,0 +1,156 @@
+"""CUDA graph build / scoring / top-N vs the oracle and the golden fixtures, through the C ABI.
+Bar: counts and ids bit-exact, M bit-exact in float64 (<=1e-6 rel required), M-hat <=1e-6 rel."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from cubecobrarecommender_b200 import graph as G
+from cubecobrarecommender_b200.sparse import CubeCSR
+from cubecobrarecommender_b200.synth import csr_to_dense, synth_cubes_csr
+from oracle import graph as og
+
+
+def _golden_csr(g):
+    return CubeCSR(g["indptr"], g["indices"], int(g["num_cards"]))
+
+
+def test_golden_adjacency_host_entry(graph_golden):
+    g = graph_golden
+    csr = _golden_csr(g)
+    m, counts = G.create_adjacency_matrix_host(csr, return_counts=True)
+    assert np.array_equal(m, g["adj"])                                  # bit-exact float64
+    assert np.array_equal(counts, og.cooc_counts(csr.indptr, csr.indices, csr.num_cards))
+    m2 = G.create_adjacency_matrix_host(csr, force_diag=0.5)
+    assert np.array_equal(m2, g["adj_force_diag"])
+
+
+@pytest.mark.parametrize("k,c,lo,hi", [(1, 5, 1, 5), (33, 130, 3, 60), (700, 1000, 20, 200), (2100, 300, 5, 40)])
+def test_counts_and_normalise_vs_oracle(k, c, lo, hi):
+    ip, ix = synth_cubes_csr(k, c, size_lo=lo, size_hi=hi, seed=k + c)
+    csr = CubeCSR(ip, ix, c)
+    gr = G.build_graph(csr, "cuda")
+    cnt = og.cooc_counts(ip, ix, c)
+    assert np.array_equal(gr.counts.cpu().numpy(), cnt)
+    m = og.adjacency_from_counts(cnt)
+    assert np.array_equal(gr.m64.cpu().numpy(), m)
+    mh = og.m_hat(m)
+    got = gr.mhat.cpu().numpy().astype(np.float64)
+    assert np.abs(got - mh).max() <= 1e-6 * mh.max()
+    nz = mh > 0
+    assert (np.abs(got[nz] - mh[nz]) / mh[nz]).max() < 1e-6
+    ns = og.neg_sampler(mh)
+    assert np.abs(gr.neg_sampler.cpu().numpy() - ns).max() < 1e-12
+    assert abs(gr.neg_sampler.sum().item() - 1) < 1e-12
+
+
+def test_empty_and_ragged_cubes():
+    # empty cubes, a cube with every card, duplicate ids collapse
+    csr = CubeCSR.from_lists([[], [0, 1, 2, 3, 4, 5, 6], [3, 3, 3], [], [6, 0]], 7)
+    gr = G.build_graph(csr, "cuda")
+    cnt = og.cooc_counts(csr.indptr, csr.indices, 7)
+    assert np.array_equal(gr.counts.cpu().numpy(), cnt)
+    with pytest.raises(ValueError):
+        bad = CubeCSR(np.array([0, 2]), np.array([1, 9], dtype=np.int32), 7)
+        G.build_graph(bad, "cuda")
+
+
+def test_accumulate_equals_single_pass():
+    ip, ix = synth_cubes_csr(300, 257, size_lo=5, size_hi=50, seed=5)
+    csr = CubeCSR(ip, ix, 257)
+    whole = G.build_graph(csr, "cuda", want_m64=False, want_mhat=False, want_neg=False).counts
+    acc = None
+    for r in range(3):
+        sh = csr.shard(r, 3)
+        a, b = G.upload_csr(sh, "cuda")
+        acc = G.count_cooccurrence(a, b, sh.num_cubes, 257, counts=acc, accumulate=acc is not None)
+    assert torch.equal(acc, whole)          # "checksum of checksums": shards sum to the whole
+
+
+def test_size_independent_properties_large():
+    ip, ix = synth_cubes_csr(4096, 4000, cfg=1)
+    csr = CubeCSR(ip, ix, 4000)
+    gr = G.build_graph(csr, "cuda")
+    cnt = gr.counts
+    assert torch.equal(cnt, cnt.t())                                       # symmetric
+    sizes = torch.from_numpy(np.diff(ip)).cuda()
+    assert int(cnt.diagonal().sum()) == int(sizes.sum())                   # diag = card frequency
+    assert int(cnt.sum()) == int((sizes * sizes).sum())                    # sum = sum of s^2
+    d = gr.m64.diagonal()
+    assert set(d.unique().tolist()) <= {0.0, 1.0}
+    assert torch.allclose(gr.mhat.double().sum(1), torch.ones(4000, dtype=torch.float64, device="cuda"), atol=1e-5)
+
+
+def _rank_check(scores, ids, expected_ids):
+    ids = np.asarray(ids); expected_ids = np.asarray(expected_ids)
+    assert np.array_equal(ids, expected_ids)
+
+
+def test_golden_recs_and_cuts(graph_golden, pairwise_golden):
+    for g, live in ((graph_golden, 120), (pairwise_golden, None)):
+        c = int(g["num_cards"])
+        csr_all = CubeCSR(g["indptr"], g["indices"], c)
+        dense = csr_to_dense(g["indptr"], g["indices"], c) if live is None else \
+            np.pad(csr_to_dense(g["indptr"], g["indices"], live), ((0, 0), (0, c - live)))
+        adj = og.create_adjacency_matrix(dense)
+        rec = G.GraphRecommender(torch.from_numpy(adj).cuda())
+        rows = g["rec_cube_rows"]
+        sub = csr_all.rows(rows)
+        scores, _, _ = rec.scores(sub)
+        scores = scores.cpu().numpy()
+        for n, r in enumerate(rows):
+            missing = dense[r] == 0
+            assert np.array_equal(scores[n][missing], g["rec_scores"][n][missing])   # bit-identical float64
+        ids, vals, cnt = rec.recs(sub, 50)
+        ids = ids.cpu().numpy()
+        for n, r in enumerate(rows):
+            expect = np.array(og.simple_recs(dense[r], adj))[:50]
+            assert np.array_equal(ids[n], expect)
+            # the reference's own (unstable-sort) answer: same scores in the same order
+            s = g["rec_scores"][n]
+            assert np.array_equal(s[ids[n]], s[g["recs_top50"][n]])
+        ncut = int(dense[rows].sum(1).max())
+        cids, cvals, ccnt = rec.cuts(sub, ncut)
+        cids = cids.cpu().numpy(); ccnt = ccnt.cpu().numpy()
+        for n, r in enumerate(rows):
+            expect = np.array(og.simple_cuts(dense[r], adj.copy()))
+            assert ccnt[n] == len(expect)
+            assert np.array_equal(cids[n][:ccnt[n]], expect)
+            assert (cids[n][ccnt[n]:] == -1).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("n", [1, 50, 2048, 3000])
+def test_topn_masked_ties_and_full_ranking(dtype, n):
+    rng = np.random.default_rng(7)
+    c, batch = 5000, 6
+    # heavy ties: scores drawn from 40 distinct values, plus -0.0/+0.0
+    vals = rng.integers(0, 40, size=(batch, c)).astype(np.float64) / 8 - 2
+    vals[0, :100] = -0.0
+    scores = torch.tensor(vals, dtype=dtype).cuda()
+    lists = [np.sort(rng.choice(c, size=rng.integers(0, 600), replace=False)) for _ in range(batch)]
+    csr = CubeCSR.from_lists(lists, c)
+    mp = torch.from_numpy(csr.indptr).cuda(); mi = torch.from_numpy(csr.indices).cuda()
+    if len(csr.indices) == 0:
+        mi = torch.zeros(1, dtype=torch.int32).cuda()
+    sv = scores.cpu().numpy()
+    ids, v, cnt = G.topn_masked(scores, mp, mi, n, only_listed=False, descending=True)
+    ids = ids.cpu().numpy(); cnt = cnt.cpu().numpy(); v = v.cpu().numpy()
+    for b in range(batch):
+        order = sv[b].argsort(kind="stable")[::-1]
+        inm = np.zeros(c, bool); inm[lists[b]] = True
+        expect = [i for i in order if not inm[i]][:n]
+        assert cnt[b] == len(expect)
+        assert np.array_equal(ids[b][:cnt[b]], expect)
+        assert np.array_equal(v[b][:cnt[b]], sv[b][expect])
+    ids, v, cnt = G.topn_masked(scores, mp, mi, n, only_listed=True, descending=False)
+    ids = ids.cpu().numpy(); cnt = cnt.cpu().numpy()
+    for b in range(batch):
+        order = sv[b].argsort(kind="stable")
+        inm = np.zeros(c, bool); inm[lists[b]] = True
+        expect = [i for i in order if inm[i]][:n]
+        assert cnt[b] == len(expect)
+        assert np.array_equal(ids[b][:cnt[b]], expect)
+        assert (ids[b][cnt[b]:] == -1).all()
