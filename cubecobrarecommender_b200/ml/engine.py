@@ -57,6 +57,7 @@ class DAEEngine:
         self.x_stride = (int(max_cube_size * 1.8) + 8 + 3) // 4 * 4
         self.yw = self.cpad // 32
         self.launches = 0          # kernels launched by the last step (for bench's gpu_launches)
+        self.prof = None
         self._alloc()
 
     # -- buffers --------------------------------------------------------------------
@@ -89,6 +90,32 @@ class DAEEngine:
         ws = max(lib.cc_colsum_workspace_bytes(T, max(self.cpad, max(HIDDEN))), 1024)
         self.cs_ws = torch.empty(ws // 4, dtype=f32, device=d)
 
+    # -- per-kernel CUDA-event timing (bench.py's roofline leg) ------------------------
+    def enable_kernel_timing(self, on=True):
+        self.prof = {} if on else None
+
+    def _timed(self, name):
+        eng = self
+
+        class _Ctx:
+            def __enter__(self_c):
+                if eng.prof is not None:
+                    self_c.a = torch.cuda.Event(enable_timing=True); self_c.b = torch.cuda.Event(enable_timing=True)
+                    self_c.a.record()
+                return self_c
+
+            def __exit__(self_c, *exc):
+                if eng.prof is not None:
+                    self_c.b.record()
+                    eng.prof.setdefault(name, []).append((self_c.a, self_c.b))
+                return False
+        return _Ctx()
+
+    def kernel_times_ms(self):
+        """{name: (launches, total ms)} of the timed kernels since enable_kernel_timing()."""
+        torch.cuda.synchronize()
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (self.prof or {}).items()}
+
     # -- inputs ---------------------------------------------------------------------
     def set_batch(self, x: SparseBatch, y_bits: torch.Tensor, reg_rows: torch.Tensor):
         """Inject a fixed (x, y, r) batch (parity tests hold the noise output fixed)."""
@@ -102,9 +129,11 @@ class DAEEngine:
     def sample_batch(self, indptr, indices, batch_ids, alias_prob, alias_idx, noise=0.2, noise_std=0.1, seed=0):
         """Noise function F + reg-row draw on the device (reference generator.py:38-103)."""
         st = stream_ptr()
-        call("cc_noise", ptr(indptr), ptr(indices), ptr(batch_ids), self.B, self.C, ptr(alias_prob), ptr(alias_idx),
-             float(noise), float(noise_std), int(seed), ptr(self.store.step), self.max_cube_size, self.x_stride,
-             ptr(self.x_idx), ptr(self.x_len), ptr(self.y_bits), self.yw, ptr(self.flips), ptr(self.overflow), st)
+        with self._timed("noise"):
+            call("cc_noise", ptr(indptr), ptr(indices), ptr(batch_ids), self.B, self.C, ptr(alias_prob),
+                 ptr(alias_idx), float(noise), float(noise_std), int(seed), ptr(self.store.step), self.max_cube_size,
+                 self.x_stride, ptr(self.x_idx), ptr(self.x_len), ptr(self.y_bits), self.yw, ptr(self.flips),
+                 ptr(self.overflow), st)
         if self.R:
             call("cc_sample_reg_rows", ptr(alias_prob), ptr(alias_idx), self.C, self.R, int(seed) ^ 0x5DEECE66D,
                  ptr(self.store.step), ptr(self.reg_rows), st)
@@ -120,7 +149,9 @@ class DAEEngine:
         n_launch = 0
         # ---------------- forward ----------------
         a1 = self.a[0]
-        bag_fwd(P("encoder_e1/kernel"), x.idx, x.row_start, x.row_len, P("encoder_e1/bias"), a1[:B]); n_launch += 1
+        with self._timed("bag_fwd"):
+            bag_fwd(P("encoder_e1/kernel"), x.idx, x.row_start, x.row_len, P("encoder_e1/bias"), a1[:B])
+        n_launch += 1
         if R:
             bag_fwd(P("encoder_e1/kernel"), self.reg_rows, self.reg_start, self.reg_len, P("encoder_e1/bias"), a1[B:])
             n_launch += 1
@@ -135,16 +166,20 @@ class DAEEngine:
             for i in range(3):
                 gemm(h, P(names[i] + "/kernel"), acts[i], bias=P(names[i] + "/bias"), relu=True, precision=pr)
                 h = acts[i]; n_launch += 1
-            gemm(h, P(names[3] + "/kernel"), z[:, :self.C], bias=P(names[3] + "/bias"), precision=pr); n_launch += 1
+            with self._timed("big_gemm"):
+                gemm(h, P(names[3] + "/kernel"), z[:, :self.C], bias=P(names[3] + "/bias"), precision=pr)
+            n_launch += 1
         # ---------------- losses (logits -> dlogits in place) ----------------
         st = stream_ptr()
-        call("cc_bce_logits_fwd_bwd", ptr(self.z1), self.z1.stride(0), ptr(self.y_bits), self.yw, B, self.C, self.cpad,
-             float(self.global_B) * float(self.C), ptr(self.z1), self.z1.stride(0), ptr(self.row_bce), st)
+        with self._timed("bce"):
+            call("cc_bce_logits_fwd_bwd", ptr(self.z1), self.z1.stride(0), ptr(self.y_bits), self.yw, B, self.C,
+                 self.cpad, float(self.global_B) * float(self.C), ptr(self.z1), self.z1.stride(0), ptr(self.row_bce), st)
         n_launch += 1
         if R:
-            call("cc_softmax_kl_fwd_bwd", ptr(self.z2), self.z2.stride(0), ptr(self.mhat), self.mhat.stride(0),
-                 ptr(self.reg_rows), R, self.C, self.cpad, self.reg / float(self.global_R), ptr(self.z2),
-                 self.z2.stride(0), ptr(self.row_kl), st)
+            with self._timed("softmax_kl"):
+                call("cc_softmax_kl_fwd_bwd", ptr(self.z2), self.z2.stride(0), ptr(self.mhat), self.mhat.stride(0),
+                     ptr(self.reg_rows), R, self.C, self.cpad, self.reg / float(self.global_R), ptr(self.z2),
+                     self.z2.stride(0), ptr(self.row_kl), st)
             n_launch += 1
         call("cc_loss_finalize", ptr(self.row_bce), B, float(self.global_B) * float(self.C), ptr(self.row_kl), R,
              float(self.global_R), self.reg, ptr(self.loss3), st)
@@ -157,9 +192,12 @@ class DAEEngine:
         for prefix, h_in, acts, gacts, dz, g_in in gtowers:
             names = dec_names(prefix)
             dzc = dz[:, :self.C]
-            gemm(acts[2], dzc, G(names[3] + "/kernel"), transa=True, precision=pr)
-            colsum(dzc, G(names[3] + "/bias"), self.cs_ws)
-            gemm(dzc, P(names[3] + "/kernel"), gacts[2], transb=True, mask=acts[2], precision=pr)
+            with self._timed("big_gemm"):
+                gemm(acts[2], dzc, G(names[3] + "/kernel"), transa=True, precision=pr)
+            with self._timed("colsum_big"):
+                colsum(dzc, G(names[3] + "/bias"), self.cs_ws)
+            with self._timed("big_gemm"):
+                gemm(dzc, P(names[3] + "/kernel"), gacts[2], transb=True, mask=acts[2], precision=pr)
             n_launch += 4
             for i in (2, 1):
                 gemm(acts[i - 1], gacts[i], G(names[i] + "/kernel"), transa=True, precision=pr)
@@ -185,7 +223,9 @@ class DAEEngine:
         colsum(g1, G("encoder_e1/bias"), self.cs_ws); n_launch += 2
         gw1 = G("encoder_e1/kernel")
         gw1.zero_(); n_launch += 1
-        bag_bwd(g1[:B], x.idx, x.row_start, x.row_len, gw1); n_launch += 1
+        with self._timed("bag_bwd"):
+            bag_bwd(g1[:B], x.idx, x.row_start, x.row_len, gw1)
+        n_launch += 1
         if R:
             bag_bwd(g1[B:], self.reg_rows, self.reg_start, self.reg_len, gw1); n_launch += 1
         self.launches += n_launch
@@ -199,8 +239,9 @@ class DAEEngine:
     def apply_adam(self):
         s, a = self.store, self.adam
         st = stream_ptr()
-        call("cc_adam_step", ptr(s.params), ptr(s.grads), ptr(s.adam_m), ptr(s.adam_v), s.total, ptr(s.step),
-             a["lr"], a["beta1"], a["beta2"], a["eps"], st)
+        with self._timed("adam"):
+            call("cc_adam_step", ptr(s.params), ptr(s.grads), ptr(s.adam_m), ptr(s.adam_v), s.total, ptr(s.step),
+                 a["lr"], a["beta1"], a["beta2"], a["eps"], st)
         call("cc_step_increment", ptr(s.step), st)
         self.launches += 2
 
