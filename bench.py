@@ -305,7 +305,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("CC_PRECISION", "fp32"), choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("CC_PRECISION", "tf32"), choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -48,18 +48,22 @@ SIGNATURES = {
     "cc_cubes_to_bits": (I, [P, P, P, I32, I32, P, I64, P]),
     "cc_step_increment": (I, [P, P]),
     # (4) bag
-    "cc_bag_fwd": (I, [P, I64, I32, P, P, P, I32, P, P, I64, I, P]),
+    "cc_bag_fwd": (I, [P, I64, I32, P, P, P, I32, P, P, I64, I, I, P]),
     "cc_bag_bwd": (I, [P, I64, I32, P, P, P, I32, P, I64, P]),
     # (5) dense
     "cc_gemm_f32_simt": (I, [I, I, I, I, I, P, I64, P, I64, P, I64, P, I, P, I64, I, P]),
+    "cc_gemm_tc": (I, [I, I, I, I, I, I, P, I64, P, I64, P, I64, P, I, P, I64, I, I, I, P]),
+    "cc_gemm_bce_tc": (I, [I, I, I, I, P, I64, P, I64, P, P, I64, D, P, I64, P, I, P]),
+    "cc_gemm_bce_partial_count": (I64, [I, I]),
     "cc_colsum_workspace_bytes": (I64, [I, I]),
     "cc_colsum_f32": (I, [P, I64, I, I, P, P, I, P]),
     "cc_relu_mask_f32": (I, [P, I64, P, I64, I, I, P]),
     # (6) losses / optimiser
     "cc_bce_logits_fwd_bwd": (I, [P, I64, P, I64, I32, I32, I32, D, P, I64, P, P]),
-    "cc_softmax_kl_fwd_bwd": (I, [P, I64, P, I64, P, I32, I32, I32, D, P, I64, P, P]),
+    "cc_softmax_kl_fwd_bwd": (I, [P, I64, P, I64, P, I32, I32, I32, D, P, I64, P, I, P]),
     "cc_loss_finalize": (I, [P, I32, D, P, I32, D, D, P, P]),
-    "cc_adam_step": (I, [P, P, P, P, I64, P, F, F, F, F, P]),
+    "cc_adam_step": (I, [P, P, P, P, I64, P, F, F, F, F, P, P]),
+    "cc_round_tf32": (I, [P, P, I64, P]),
     "cc_sigmoid_f32": (I, [P, P, I64, P]),
 }
 

@@ -15,7 +15,7 @@ constexpr int BAG_CHUNK = 256;
 __global__ void bag_fwd_kernel(const float* __restrict__ w, int64_t ldw, int32_t h4,
                                const int32_t* __restrict__ idx, const int64_t* __restrict__ row_start,
                                const int32_t* __restrict__ row_len, const float* __restrict__ bias,
-                               float* __restrict__ out, int64_t ldo, int relu) {
+                               float* __restrict__ out, int64_t ldo, int relu, int round_tf32) {
   __shared__ int32_t sidx[BAG_CHUNK];
   const int b = blockIdx.x, t = threadIdx.x;
   const int len = row_len[b];
@@ -48,6 +48,10 @@ __global__ void bag_fwd_kernel(const float* __restrict__ w, int64_t ldw, int32_t
       acc.x += bv.x; acc.y += bv.y; acc.z += bv.z; acc.w += bv.w;
     }
     if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+    if (round_tf32) {
+      acc.x = rn_tf32(acc.x); acc.y = rn_tf32(acc.y);
+      acc.z = rn_tf32(acc.z); acc.w = rn_tf32(acc.w);
+    }
     reinterpret_cast<float4*>(out + int64_t(b) * ldo)[t] = acc;
   }
 }
@@ -89,7 +93,7 @@ extern "C" {
 
 int cc_bag_fwd(const float* w, int64_t ldw, int32_t hidden, const int32_t* idx, const int64_t* row_start,
                const int32_t* row_len, int32_t batch, const float* bias, float* out, int64_t ldo, int relu,
-               void* stream) {
+               int round_tf32, void* stream) {
   CC_REQUIRE(w && idx && row_start && row_len && out, "cc_bag_fwd: null pointer");
   CC_REQUIRE(hidden > 0 && hidden % 4 == 0 && hidden <= 4096 && ldw % 4 == 0 && ldo % 4 == 0 && ldw >= hidden &&
                  ldo >= hidden, "cc_bag_fwd: hidden=%d ldw=%lld ldo=%lld must be multiples of 4", hidden,
@@ -99,7 +103,7 @@ int cc_bag_fwd(const float* w, int64_t ldw, int32_t hidden, const int32_t* idx, 
   if (batch == 0) return CC_OK;
   const int h4 = hidden / 4;
   const int threads = ((h4 + 31) / 32) * 32;
-  bag_fwd_kernel<<<batch, threads, 0, as_stream(stream)>>>(w, ldw, h4, idx, row_start, row_len, bias, out, ldo, relu);
+  bag_fwd_kernel<<<batch, threads, 0, as_stream(stream)>>>(w, ldw, h4, idx, row_start, row_len, bias, out, ldo, relu, round_tf32);
   CC_CHECK_LAUNCH();
   return CC_OK;
 }

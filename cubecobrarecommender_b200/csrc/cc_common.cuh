@@ -63,6 +63,14 @@ __device__ __forceinline__ int warp_sum(int v) {
   return v;
 }
 
+// round-to-nearest fp32 -> tf32 (the tensor core's kind::tf32 truncates the low 13 mantissa bits, which
+// biases every product towards zero; operands are rounded once, where they are produced)
+__device__ __forceinline__ float rn_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 // streaming 128-bit loads that do not pollute L1 (data is read once per CTA)
 __device__ __forceinline__ uint4 ld_nc_u4(const void* p) {
   uint4 r;

@@ -1,0 +1,484 @@
+// tcgen05 tensor-core GEMM for sm_100a: TMA-fed, TMEM accumulators, fused epilogues.
+//
+// Replaces the dense matmuls behind the Dense layers of reference src/ml/model.py:27-33,
+// 58-64 and their gradients, and carries the sigmoid-BCE loss of src/ml/train.py:85-86
+// inside the epilogue of the 512 -> C decoder GEMM, so the C-wide logits never reach HBM
+// (only dlogits do).
+//
+//   C[M,N] = epi(op(A) op(B)),   fp32 storage, kind::tf32 (10-bit mantissa products, fp32
+//   accumulation in TMEM) or bf16 storage, kind::f16.
+//
+// Structure (one persistent CTA per SM, 256 threads):
+//   warp 0   TMA producer: cp.async.bulk.tensor boxes -> 128B-swizzled smem ring (6 stages)
+//   warp 1   MMA issuer : one elected lane issues tcgen05.mma (128 x BN x 8|16), commits to
+//            the stage's "empty" mbarrier and, per tile, to the accumulator's "full" barrier
+//   warp 2   TMEM allocator (2 accumulator buffers: MMA of tile i+1 overlaps epilogue of tile i)
+//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns, bias/ReLU/mask or BCE, global stores
+// Operands may be K-major ([rows, K], K contiguous) or MN-major ([K, rows], rows contiguous);
+// both are loaded with SWIZZLE_128B boxes and described to the MMA by shared-memory matrix
+// descriptors (LBO/SBO as in the PTX ISA "canonical layouts").
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include "cc_common.cuh"
+
+namespace cc {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BN = 128;
+constexpr int STAGES = 6;
+constexpr int STAGE_A_BYTES = BM * 128;          // 128 rows x one 128-byte swizzle row
+constexpr int STAGE_B_BYTES = BN * 128;
+constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
+constexpr int NUM_ACC = 2;
+constexpr int TMEM_COLS = NUM_ACC * BN;          // 256 fp32 columns
+constexpr int THREADS = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+enum Epilogue : int { EPI_STORE = 0, EPI_BCE = 1 };
+
+struct Params {
+  int m, n, k;
+  int m_tiles, n_tiles, k_blocks;       // k_blocks per split
+  int split_k, total_k_blocks;
+  float* c; long long ldc;
+  const float* bias;
+  const float* mask; long long ldmask;
+  int relu, atomic_add, round_tf32;
+  // EPI_BCE
+  const uint32_t* ybits; long long ywords;
+  float inv_count;
+  double* loss_partial;                  // [n_tiles][m]
+  int a_mn_major, b_mn_major;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) break;
+    if (++spins > (1u << 28)) __trap();      // watchdog: a protocol bug must not hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <bool BF16>
+__device__ __forceinline__ void tcgen05_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (BF16) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (SWIZZLE_128B, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                             uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr >> 4) & 0x3fffu);
+  d |= uint64_t((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= uint64_t((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= uint64_t(1) << 46;        // descriptor version (Blackwell)
+  d |= uint64_t(layout_type) << 61;   // 2 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B with 32-byte atoms
+  return d;
+}
+
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// ------------------------------------------------------------------------ kernel
+template <bool BF16, int EPI>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+  constexpr int ELEM = BF16 ? 2 : 4;
+  constexpr int BK = 128 / ELEM;                 // elements per 128-byte swizzle row (32 | 64)
+  constexpr int UMMA_K = 32 / ELEM;              // 8 | 16
+  constexpr int MMAS_PER_STAGE = BK / UMMA_K;    // 4
+  constexpr int MN_BOX = BK;                     // MN-major boxes are [BK rows(k)] x [BK elems (128 B)]
+  constexpr int MN_BOX_BYTES = BK * 128;
+  constexpr int MN_BOXES = 128 / MN_BOX;         // boxes per 128-wide operand tile (4 | 2)
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + NUM_ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + NUM_ACC);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.split_k;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < NUM_ACC; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile % p.m_tiles;
+        const int nt = (tile / p.m_tiles) % p.n_tiles;
+        const int ks = tile / (p.m_tiles * p.n_tiles);
+        const int kb0 = ks * p.k_blocks;
+        const int kb1 = min(kb0 + p.k_blocks, p.total_k_blocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + STAGE_A_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          if (p.a_mn_major) {
+#pragma unroll
+            for (int j = 0; j < MN_BOXES; ++j)
+              tma_load_2d(sa + j * MN_BOX_BYTES, &map_a, &full_bar[stage], mt * BM + j * MN_BOX, kb * BK);
+          } else {
+            tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, mt * BM);
+          }
+          if (p.b_mn_major) {
+#pragma unroll
+            for (int j = 0; j < MN_BOXES; ++j)
+              tma_load_2d(sb + j * MN_BOX_BYTES, &map_b, &full_bar[stage], nt * BN + j * MN_BOX, kb * BK);
+          } else {
+            tma_load_2d(sb, &map_b, &full_bar[stage], kb * BK, nt * BN);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((BF16 ? 1u : 2u) << 7) | ((BF16 ? 1u : 2u) << 10) |
+                             (uint32_t(p.a_mn_major) << 15) | (uint32_t(p.b_mn_major) << 16) |
+                             (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+      // K-major: rows 128 B apart, 8-row groups 1024 B apart (SBO); K advance 32 B inside the swizzle row.
+      // MN-major: 128-byte MN atoms LBO apart, 8-row k groups 1024 B apart (SBO); K advance UMMA_K rows.
+      // 32-bit (tf32) MN-major operands only exist in the "128B swizzle, 32-byte atom" layout: atoms of 4 k-rows
+      // (SBO = 512 B); every other case uses the plain 128B swizzle with 8-row atoms (SBO = 1024 B).
+      const uint32_t a_lbo = p.a_mn_major ? MN_BOX_BYTES : 16, b_lbo = p.b_mn_major ? MN_BOX_BYTES : 16;
+      const uint32_t a_lt = (!BF16 && p.a_mn_major) ? 1u : 2u, b_lt = (!BF16 && p.b_mn_major) ? 1u : 2u;
+      const uint32_t a_sbo = a_lt == 1u ? 512u : 1024u, b_sbo = b_lt == 1u ? 512u : 1024u;
+      const uint32_t a_kstep = p.a_mn_major ? UMMA_K * 128 : 32, b_kstep = p.b_mn_major ? UMMA_K * 128 : 32;
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int ks = tile / (p.m_tiles * p.n_tiles);
+        const int kb0 = ks * p.k_blocks;
+        const int kb1 = min(kb0 + p.k_blocks, p.total_k_blocks);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + STAGE_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < MMAS_PER_STAGE; ++k) {
+            const uint64_t adesc = make_desc(sa + k * a_kstep, a_lbo, a_sbo, a_lt);
+            const uint64_t bdesc = make_desc(sb + k * b_kstep, b_lbo, b_sbo, b_lt);
+            tcgen05_mma<BF16>(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tcgen05_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tcgen05_commit(&tmem_full[acc]);              // accumulator complete -> epilogue
+        if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile % p.m_tiles;
+      const int nt = (tile / p.m_tiles) % p.n_tiles;
+      const int ks = tile / (p.m_tiles * p.n_tiles);
+      const bool has_k = ks * p.k_blocks < p.total_k_blocks;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const int row = mt * BM + q * 32 + lane;
+      const bool row_ok = row < p.m;
+      float row_loss = 0.f;
+#pragma unroll 1
+      for (int cb = 0; cb < BN / 32; ++cb) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + cb * 32), v);
+        const int col0 = nt * BN + cb * 32;
+        if (!row_ok || !has_k || col0 >= (EPI == EPI_BCE ? int(p.ldc) : p.n)) continue;
+        if (EPI == EPI_BCE) {
+          const uint32_t ybw = p.ybits[(long long)row * p.ywords + (col0 >> 5)];
+          float* dst = p.c + (long long)row * p.ldc + col0;
+          float out[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            float z = __uint_as_float(v[j]);
+            float g = 0.f;
+            if (col < p.n) {
+              z += __ldg(p.bias + col);
+              const float y = float((ybw >> j) & 1u);
+              const float e = __expf(-fabsf(z));
+              row_loss += fmaxf(z, 0.f) - z * y + log1pf(e);
+              const float r = __fdividef(1.f, 1.f + e);
+              g = ((z >= 0.f ? r : e * r) - y) * p.inv_count;
+              if (p.round_tf32) g = rn_tf32(g);
+            }
+            out[j] = g;
+          }
+          // dlogits, pad columns [n, ldc) written as zero so later GEMMs may read full rows
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (col0 + j < p.ldc)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
+        } else {
+          float* dst = p.c + (long long)row * p.ldc + col0;
+          const float* mrow = p.mask ? p.mask + (long long)row * p.ldmask + col0 : nullptr;
+          const bool vec_ok = (col0 + 32 <= p.n) && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
+          float out[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float z = __uint_as_float(v[j]);
+            const int col = col0 + j;
+            if (col < p.n) {
+              if (p.bias) z += __ldg(p.bias + col);
+              if (p.relu) z = fmaxf(z, 0.f);
+              if (mrow) z = (__ldg(mrow + j) > 0.f) ? z : 0.f;
+              if (p.round_tf32) z = rn_tf32(z);
+            }
+            out[j] = z;
+          }
+          if (p.atomic_add) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.n) red_add_f32(dst + j, out[j]);
+          } else if (vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.n) dst[j] = out[j];
+          }
+        }
+      }
+      if (EPI == EPI_BCE && row_ok) p.loss_partial[(long long)nt * p.m + row] = double(row_loss);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host helpers
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// 2-D row-major matrix [rows][cols] (cols contiguous, leading dimension ld elements);
+// box = box_rows x (128 bytes of columns), SWIZZLE_128B.
+static int make_map(CUtensorMap* map, const void* base, bool bf16, long long rows, long long cols, long long ld,
+                    int box_rows, bool mn_major) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return CC_ERR_CUDA; }
+  const int elem = bf16 ? 2 : 4;
+  cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  cuuint64_t strides[1] = {cuuint64_t(ld) * elem};
+  cuuint32_t box[2] = {cuuint32_t(128 / elem), cuuint32_t(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  static const bool tf32_map = getenv("CC_TC_TF32_MAP") != nullptr;
+  const CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                  : (tf32_map ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32), 2,
+                        const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        (!bf16 && mn_major) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): base=%p rows=%lld cols=%lld ld=%lld", int(r), base, rows, cols, ld);
+    return CC_ERR_CUDA;
+  }
+  return CC_OK;
+}
+
+struct Problem {
+  int transa, transb, m, n, k;
+  const void* a; long long lda;
+  const void* b; long long ldb;
+  bool bf16;
+};
+
+template <bool BF16, int EPI>
+static int launch(const Problem& pr, Params p, cudaStream_t st) {
+  const int elem = BF16 ? 2 : 4;
+  const int bk = 128 / elem;
+  CC_REQUIRE((reinterpret_cast<uintptr_t>(pr.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(pr.b) & 15) == 0,
+             "cc_gemm_tc: operand base pointers must be 16-byte aligned");
+  CC_REQUIRE((pr.lda * elem) % 16 == 0 && (pr.ldb * elem) % 16 == 0,
+             "cc_gemm_tc: leading dimensions must be multiples of 16 bytes (lda=%lld ldb=%lld)", pr.lda, pr.ldb);
+  CUtensorMap map_a, map_b;
+  int rc;
+  // transa=0: A is [M][K] (K-major)  -> box 128 rows x 128 B;  transa=1: A is [K][M] (MN-major) -> box bk rows x 128 B
+  if (pr.transa) rc = make_map(&map_a, pr.a, BF16, pr.k, pr.m, pr.lda, bk, true);
+  else           rc = make_map(&map_a, pr.a, BF16, pr.m, pr.k, pr.lda, BM, false);
+  if (rc != CC_OK) return rc;
+  // transb=1: B is [N][K] (K-major);  transb=0: B is [K][N] (MN-major)
+  if (pr.transb) rc = make_map(&map_b, pr.b, BF16, pr.n, pr.k, pr.ldb, BN, false);
+  else           rc = make_map(&map_b, pr.b, BF16, pr.k, pr.n, pr.ldb, bk, true);
+  if (rc != CC_OK) return rc;
+  p.a_mn_major = pr.transa ? 1 : 0;
+  p.b_mn_major = pr.transb ? 0 : 1;
+  p.m_tiles = ceil_div(pr.m, BM);
+  p.n_tiles = ceil_div(pr.n, BN);
+  p.total_k_blocks = ceil_div(pr.k, bk);
+  if (p.split_k < 1) p.split_k = 1;
+  p.k_blocks = ceil_div(p.total_k_blocks, p.split_k);
+  p.split_k = ceil_div(p.total_k_blocks, p.k_blocks);
+  const int tiles = p.m_tiles * p.n_tiles * p.split_k;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  auto kern = gemm_tc_kernel<BF16, EPI>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_done = true;
+  }
+  kern<<<grid, THREADS, SMEM_BYTES, st>>>(map_a, map_b, p);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+}  // namespace tc
+}  // namespace cc
+
+using namespace cc;
+
+extern "C" {
+
+// precision: 1 = tf32 (float operands), 2 = bf16 (__nv_bfloat16 operands; C, bias, mask stay float)
+int cc_gemm_tc(int precision, int transa, int transb, int m, int n, int k, const void* a, int64_t lda, const void* b,
+               int64_t ldb, float* c, int64_t ldc, const float* bias, int relu, const float* mask, int64_t ldmask,
+               int accumulate, int split_k, int round_tf32, void* stream) {
+  CC_REQUIRE(a && b && c, "cc_gemm_tc: null pointer");
+  CC_REQUIRE(precision == 1 || precision == 2, "cc_gemm_tc: precision must be 1 (tf32) or 2 (bf16)");
+  CC_REQUIRE(m >= 0 && n >= 0 && k > 0, "cc_gemm_tc: bad sizes m=%d n=%d k=%d", m, n, k);
+  if (m == 0 || n == 0) return CC_OK;
+  CC_REQUIRE(split_k <= 1 || (!bias && !relu && !mask), "cc_gemm_tc: split-K cannot carry a non-linear epilogue");
+  cudaStream_t st = as_stream(stream);
+  tc::Params p{};
+  p.m = m; p.n = n; p.k = k;
+  p.c = c; p.ldc = ldc; p.bias = bias; p.mask = mask; p.ldmask = ldmask; p.relu = relu;
+  p.round_tf32 = round_tf32;
+  p.split_k = split_k < 1 ? 1 : split_k;
+  p.atomic_add = (accumulate || p.split_k > 1) ? 1 : 0;
+  if (p.split_k > 1 && !accumulate)
+    CC_CHECK_CUDA(cudaMemset2DAsync(c, size_t(ldc) * 4, 0, size_t(n) * 4, m, st));
+  tc::Problem pr{transa, transb, m, n, k, a, lda, b, ldb, precision == 2};
+  if (precision == 2) return tc::launch<true, tc::EPI_STORE>(pr, p, st);
+  return tc::launch<false, tc::EPI_STORE>(pr, p, st);
+}
+
+// Fused decoder output layer + sigmoid-BCE:  z = A[M,K] W[K,N] + bias;  loss partials and
+// dlogits = (sigmoid(z) - y)/count written to dz[M][lddz] (columns [N, lddz) zeroed).
+// loss_partial: float64 [ceil(N/128)][M]  (sum it with cc_loss_finalize).
+int cc_gemm_bce_tc(int precision, int m, int n, int k, const void* a, int64_t lda, const void* w, int64_t ldw,
+                   const float* bias, const uint32_t* ybits, int64_t ywords, double count, float* dz, int64_t lddz,
+                   double* loss_partial, int round_tf32, void* stream) {
+  CC_REQUIRE(a && w && bias && ybits && dz && loss_partial, "cc_gemm_bce_tc: null pointer");
+  CC_REQUIRE(precision == 1 || precision == 2, "cc_gemm_bce_tc: precision must be 1 (tf32) or 2 (bf16)");
+  CC_REQUIRE(m > 0 && n > 0 && k > 0 && count > 0, "cc_gemm_bce_tc: bad sizes");
+  CC_REQUIRE(lddz % 128 == 0 && lddz >= n && ywords * 32 >= lddz && (reinterpret_cast<uintptr_t>(dz) & 15) == 0,
+             "cc_gemm_bce_tc: lddz must be a multiple of 128 >= n, ywords*32 >= lddz, dz 16-byte aligned");
+  tc::Params p{};
+  p.m = m; p.n = n; p.k = k;
+  p.c = dz; p.ldc = lddz; p.bias = bias; p.split_k = 1;
+  p.round_tf32 = round_tf32;
+  p.ybits = ybits; p.ywords = ywords; p.inv_count = float(1.0 / count); p.loss_partial = loss_partial;
+  tc::Problem pr{0, 0, m, n, k, a, lda, w, ldw, precision == 2};
+  if (precision == 2) return tc::launch<true, tc::EPI_BCE>(pr, p, as_stream(stream));
+  return tc::launch<false, tc::EPI_BCE>(pr, p, as_stream(stream));
+}
+
+int64_t cc_gemm_bce_partial_count(int m, int n) { return int64_t(ceil_div(n, tc::BN)) * m; }
+
+}  // extern "C"

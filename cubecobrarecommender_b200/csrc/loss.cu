@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(1024)
 softmax_kl_rows_kernel(const float* __restrict__ z, int64_t ldz, const float* __restrict__ target, int64_t ldt,
                        const int32_t* __restrict__ target_rows, int32_t num_cards, int32_t ncols_pad,
                        float grad_scale /* reg / R */, float* __restrict__ dz, int64_t lddz,
-                       double* __restrict__ row_loss) {
+                       double* __restrict__ row_loss, int round_tf32) {
   extern __shared__ __align__(16) float srow[];   // CACHE: z row then t row
   __shared__ double redd[32];
   __shared__ float redf[32];
@@ -130,6 +130,7 @@ softmax_kl_rows_kernel(const float* __restrict__ z, int64_t ldz, const float* __
         const float tc = fminf(fmaxf(t, KERAS_EPS), 1.f);
         const bool un = (q >= KERAS_EPS && q <= 1.f);
         g = (q * S - (un ? tc : 0.f)) * grad_scale;
+        if (round_tf32) g = rn_tf32(g);
       }
       dr[c] = g;
     }
@@ -155,7 +156,8 @@ loss_finalize_kernel(const double* __restrict__ bce_rows, int nb, double bce_div
 // ------------------------------------------------------------------- Adam
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-            int64_t n, const int64_t* __restrict__ step_ptr, float lr, float b1, float b2, float eps) {
+            int64_t n, const int64_t* __restrict__ step_ptr, float lr, float b1, float b2, float eps,
+            float* __restrict__ shadow_tf32) {
   const double t = double(*step_ptr + 1);
   const float lr_t = float(double(lr) * sqrt(1.0 - pow(double(b2), t)) / (1.0 - pow(double(b1), t)));
   const int64_t i4 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
@@ -171,6 +173,12 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     CC_ADAM1(x) CC_ADAM1(y) CC_ADAM1(z) CC_ADAM1(w)
 #undef CC_ADAM1
     *reinterpret_cast<float4*>(p + i4) = pv;
+    if (shadow_tf32) {   // tf32 (round-to-nearest) copy of the weights for the tensor-core GEMMs
+      float4 sv = pv;
+      sv.x = rn_tf32(sv.x); sv.y = rn_tf32(sv.y);
+      sv.z = rn_tf32(sv.z); sv.w = rn_tf32(sv.w);
+      *reinterpret_cast<float4*>(shadow_tf32 + i4) = sv;
+    }
     *reinterpret_cast<float4*>(m + i4) = mv;
     *reinterpret_cast<float4*>(v + i4) = vv;
   } else {
@@ -179,9 +187,16 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
       const float mi = b1 * m[i] + (1.f - b1) * gi;
       const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
       m[i] = mi; v[i] = vi;
-      p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+      const float pi = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+      p[i] = pi;
+      if (shadow_tf32) { float sv = pi; sv = rn_tf32(sv); shadow_tf32[i] = sv; }
     }
   }
+}
+
+__global__ void round_tf32_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) { float v = x[i]; v = rn_tf32(v); out[i] = v; }
 }
 
 // sigmoid of the winners / in-cube scores: probs = 1/(1+exp(-z))
@@ -212,7 +227,7 @@ int cc_bce_logits_fwd_bwd(const float* z, int64_t ldz, const uint32_t* ybits, in
 
 int cc_softmax_kl_fwd_bwd(const float* z, int64_t ldz, const float* target, int64_t ldt, const int32_t* target_rows,
                           int32_t rows, int32_t num_cards, int32_t ncols_pad, double grad_scale, float* dz,
-                          int64_t lddz, double* row_loss, void* stream) {
+                          int64_t lddz, double* row_loss, int round_tf32, void* stream) {
   CC_REQUIRE(z && target && row_loss, "cc_softmax_kl_fwd_bwd: null pointer");
   CC_REQUIRE(num_cards > 0 && ncols_pad >= num_cards, "cc_softmax_kl_fwd_bwd: bad sizes");
   CC_REQUIRE(!dz || lddz >= ncols_pad, "cc_softmax_kl_fwd_bwd: lddz too small");
@@ -223,10 +238,10 @@ int cc_softmax_kl_fwd_bwd(const float* z, int64_t ldz, const float* target, int6
     CC_CHECK_CUDA(cudaFuncSetAttribute(softmax_kl_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)cache_bytes));
     softmax_kl_rows_kernel<true><<<rows, 1024, cache_bytes, st>>>(z, ldz, target, ldt, target_rows, num_cards,
-                                                                 ncols_pad, float(grad_scale), dz, lddz, row_loss);
+                                                                 ncols_pad, float(grad_scale), dz, lddz, row_loss, round_tf32);
   } else {
     softmax_kl_rows_kernel<false><<<rows, 1024, 0, st>>>(z, ldz, target, ldt, target_rows, num_cards, ncols_pad,
-                                                         float(grad_scale), dz, lddz, row_loss);
+                                                         float(grad_scale), dz, lddz, row_loss, round_tf32);
   }
   CC_CHECK_LAUNCH();
   return CC_OK;
@@ -241,14 +256,22 @@ int cc_loss_finalize(const double* bce_rows, int32_t nb, double bce_div, const d
 }
 
 int cc_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, const int64_t* step_ptr, float lr,
-                 float beta1, float beta2, float eps, void* stream) {
+                 float beta1, float beta2, float eps, float* shadow_tf32, void* stream) {
   CC_REQUIRE(params && grads && m && v && step_ptr && n >= 0, "cc_adam_step: bad arguments");
   CC_REQUIRE((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(m) |
               reinterpret_cast<uintptr_t>(v)) % 16 == 0, "cc_adam_step: buffers must be 16-byte aligned");
   if (n == 0) return CC_OK;
   const int64_t threads = ceil_div<int64_t>(n, 4);
   adam_kernel<<<(unsigned)ceil_div<int64_t>(threads, 256), 256, 0, as_stream(stream)>>>(params, grads, m, v, n, step_ptr,
-                                                                                      lr, beta1, beta2, eps);
+                                                                                      lr, beta1, beta2, eps, shadow_tf32);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+int cc_round_tf32(const float* x, float* out, int64_t n, void* stream) {
+  CC_REQUIRE(x && out && n >= 0, "cc_round_tf32: bad arguments");
+  if (n == 0) return CC_OK;
+  round_tf32_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, as_stream(stream)>>>(x, out, n);
   CC_CHECK_LAUNCH();
   return CC_OK;
 }

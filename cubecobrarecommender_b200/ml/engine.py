@@ -86,6 +86,12 @@ class DAEEngine:
         self.row_bce = torch.zeros(B, dtype=torch.float64, device=d)
         self.row_kl = torch.zeros(max(R, 1), dtype=torch.float64, device=d)
         self.loss3 = torch.zeros(3, dtype=torch.float64, device=d)
+        self.bce_partial = None
+        if self.precision != "fp32":
+            if self.C % 4:
+                raise ValueError("tensor-core precision modes need num_cards % 4 == 0 (16-byte TMA rows)")
+            from . import tensorcore
+            self.bce_partial = torch.zeros(tensorcore.bce_partial_count(B, self.C), dtype=torch.float64, device=d)
         lib = _lib.load()
         ws = max(lib.cc_colsum_workspace_bytes(T, max(self.cpad, max(HIDDEN))), 1024)
         self.cs_ws = torch.empty(ws // 4, dtype=f32, device=d)
@@ -144,44 +150,59 @@ class DAEEngine:
     def forward_backward(self):
         s, B, R, T = self.store, self.B, self.R, self.B + self.R
         pr = self.precision
+        tc = pr != "fp32"               # tensor-core modes: operands rounded to tf32 where produced
         x = self._x
-        P, G = s.p, s.g
+        P, G, W = s.p, s.g, s.w         # master params, grads, the copy of the kernels the GEMMs read
         n_launch = 0
+        st = stream_ptr()
         # ---------------- forward ----------------
         a1 = self.a[0]
         with self._timed("bag_fwd"):
-            bag_fwd(P("encoder_e1/kernel"), x.idx, x.row_start, x.row_len, P("encoder_e1/bias"), a1[:B])
+            bag_fwd(P("encoder_e1/kernel"), x.idx, x.row_start, x.row_len, P("encoder_e1/bias"), a1[:B], round_tf32=tc)
         n_launch += 1
         if R:
-            bag_fwd(P("encoder_e1/kernel"), self.reg_rows, self.reg_start, self.reg_len, P("encoder_e1/bias"), a1[B:])
+            bag_fwd(P("encoder_e1/kernel"), self.reg_rows, self.reg_start, self.reg_len, P("encoder_e1/bias"), a1[B:],
+                    round_tf32=tc)
             n_launch += 1
         for i, name in enumerate(ENC_NAMES[1:]):
-            gemm(self.a[i], P(name + "/kernel"), self.a[i + 1], bias=P(name + "/bias"), relu=True, precision=pr)
+            gemm(self.a[i], W(name + "/kernel"), self.a[i + 1], bias=P(name + "/bias"), relu=True, precision=pr,
+                 round_out=tc)
             n_launch += 1
         towers = [("main", self.a[3][:B], self.md, self.z1, B)]
         if R:
             towers.append(("reg", self.a[3][B:], self.rd, self.z2, R))
+        bce_rows, bce_n = self.row_bce, B
         for prefix, h, acts, z, rows in towers:
             names = dec_names(prefix)
             for i in range(3):
-                gemm(h, P(names[i] + "/kernel"), acts[i], bias=P(names[i] + "/bias"), relu=True, precision=pr)
+                gemm(h, W(names[i] + "/kernel"), acts[i], bias=P(names[i] + "/bias"), relu=True, precision=pr,
+                     round_out=tc)
                 h = acts[i]; n_launch += 1
-            with self._timed("big_gemm"):
-                gemm(h, P(names[3] + "/kernel"), z[:, :self.C], bias=P(names[3] + "/bias"), precision=pr)
+            if tc and prefix == "main":
+                # fused 512 -> C layer + sigmoid-BCE: logits stay in TMEM, only dlogits are written
+                from . import tensorcore
+                with self._timed("big_gemm"):
+                    tensorcore.gemm_bce(h, W(names[3] + "/kernel"), P(names[3] + "/bias"), self.y_bits,
+                                        float(self.global_B) * float(self.C), self.z1, self.bce_partial, precision=pr)
+                bce_rows, bce_n = self.bce_partial, self.bce_partial.numel()
+            else:
+                with self._timed("big_gemm"):
+                    gemm(h, W(names[3] + "/kernel"), z[:, :self.C], bias=P(names[3] + "/bias"), precision=pr)
             n_launch += 1
         # ---------------- losses (logits -> dlogits in place) ----------------
-        st = stream_ptr()
-        with self._timed("bce"):
-            call("cc_bce_logits_fwd_bwd", ptr(self.z1), self.z1.stride(0), ptr(self.y_bits), self.yw, B, self.C,
-                 self.cpad, float(self.global_B) * float(self.C), ptr(self.z1), self.z1.stride(0), ptr(self.row_bce), st)
-        n_launch += 1
+        if not tc:
+            with self._timed("bce"):
+                call("cc_bce_logits_fwd_bwd", ptr(self.z1), self.z1.stride(0), ptr(self.y_bits), self.yw, B, self.C,
+                     self.cpad, float(self.global_B) * float(self.C), ptr(self.z1), self.z1.stride(0),
+                     ptr(self.row_bce), st)
+            n_launch += 1
         if R:
             with self._timed("softmax_kl"):
                 call("cc_softmax_kl_fwd_bwd", ptr(self.z2), self.z2.stride(0), ptr(self.mhat), self.mhat.stride(0),
                      ptr(self.reg_rows), R, self.C, self.cpad, self.reg / float(self.global_R), ptr(self.z2),
-                     self.z2.stride(0), ptr(self.row_kl), st)
+                     self.z2.stride(0), ptr(self.row_kl), int(tc), st)
             n_launch += 1
-        call("cc_loss_finalize", ptr(self.row_bce), B, float(self.global_B) * float(self.C), ptr(self.row_kl), R,
+        call("cc_loss_finalize", ptr(bce_rows), bce_n, float(self.global_B) * float(self.C), ptr(self.row_kl), R,
              float(self.global_R), self.reg, ptr(self.loss3), st)
         n_launch += 1
         # ---------------- backward: decoders ----------------
@@ -197,32 +218,34 @@ class DAEEngine:
             with self._timed("colsum_big"):
                 colsum(dzc, G(names[3] + "/bias"), self.cs_ws)
             with self._timed("big_gemm"):
-                gemm(dzc, P(names[3] + "/kernel"), gacts[2], transb=True, mask=acts[2], precision=pr)
+                gemm(dzc, W(names[3] + "/kernel"), gacts[2], transb=True, mask=acts[2], precision=pr, round_out=tc)
             n_launch += 4
             for i in (2, 1):
                 gemm(acts[i - 1], gacts[i], G(names[i] + "/kernel"), transa=True, precision=pr)
                 colsum(gacts[i], G(names[i] + "/bias"), self.cs_ws)
-                gemm(gacts[i], P(names[i] + "/kernel"), gacts[i - 1], transb=True, mask=acts[i - 1], precision=pr)
+                gemm(gacts[i], W(names[i] + "/kernel"), gacts[i - 1], transb=True, mask=acts[i - 1], precision=pr,
+                     round_out=tc)
                 n_launch += 4
             gemm(h_in, gacts[0], G(names[0] + "/kernel"), transa=True, precision=pr)
             colsum(gacts[0], G(names[0] + "/bias"), self.cs_ws)
-            gemm(gacts[0], P(names[0] + "/kernel"), g_in, transb=True, mask=h_in, precision=pr)
+            gemm(gacts[0], W(names[0] + "/kernel"), g_in, transb=True, mask=h_in, precision=pr, round_out=tc)
             n_launch += 4
         if not R:
-            for prefix in ("reg",):
-                for n_ in dec_names(prefix):
-                    G(n_ + "/kernel").zero_(); G(n_ + "/bias").zero_()
+            for n_ in dec_names("reg"):
+                G(n_ + "/kernel").zero_(); G(n_ + "/bias").zero_()
         # ---------------- backward: shared encoder (main + reg rows together) ----------------
         for i in (3, 2, 1):
             name = ENC_NAMES[i]
             gemm(self.a[i - 1], self.ga[i], G(name + "/kernel"), transa=True, precision=pr)
             colsum(self.ga[i], G(name + "/bias"), self.cs_ws)
-            gemm(self.ga[i], P(name + "/kernel"), self.ga[i - 1], transb=True, mask=self.a[i - 1], precision=pr)
+            # ga[0] (= g1) feeds the scatter-add and a column sum, not a GEMM: it keeps full fp32
+            gemm(self.ga[i], W(name + "/kernel"), self.ga[i - 1], transb=True, mask=self.a[i - 1], precision=pr,
+                 round_out=tc and i > 1)
             n_launch += 4
         g1 = self.ga[0]
         colsum(g1, G("encoder_e1/bias"), self.cs_ws); n_launch += 2
         gw1 = G("encoder_e1/kernel")
-        gw1.zero_(); n_launch += 1
+        gw1.zero_()
         with self._timed("bag_bwd"):
             bag_bwd(g1[:B], x.idx, x.row_start, x.row_len, gw1)
         n_launch += 1
@@ -241,7 +264,7 @@ class DAEEngine:
         st = stream_ptr()
         with self._timed("adam"):
             call("cc_adam_step", ptr(s.params), ptr(s.grads), ptr(s.adam_m), ptr(s.adam_v), s.total, ptr(s.step),
-                 a["lr"], a["beta1"], a["beta2"], a["eps"], st)
+                 a["lr"], a["beta1"], a["beta2"], a["eps"], ptr(s.shadow), st)
         call("cc_step_increment", ptr(s.step), st)
         self.launches += 2
 

@@ -60,6 +60,20 @@ class ParamStore:
         self.adam_m = torch.zeros(off, dtype=torch.float32, device=self.device)
         self.adam_v = torch.zeros(off, dtype=torch.float32, device=self.device)
         self.step = torch.zeros(1, dtype=torch.int64, device=self.device)   # completed steps
+        self.shadow = None        # tf32 (round-to-nearest) copy of params for the tensor-core GEMMs
+
+    def enable_tf32_shadow(self):
+        if self.shadow is None:
+            self.shadow = torch.zeros_like(self.params)
+        self.sync_shadow()
+
+    def sync_shadow(self):
+        if self.shadow is not None:
+            call("cc_round_tf32", ptr(self.params), ptr(self.shadow), self.total, stream_ptr())
+
+    def w(self, key):
+        """The copy of a kernel the GEMMs read (tf32-rounded shadow when enabled)."""
+        return self.view(self.shadow if self.shadow is not None else self.params, key)
 
     def view(self, buf, key):
         off, shape = self.layout[key]
@@ -75,6 +89,7 @@ class ParamStore:
         for k, (off, shape) in self.layout.items():
             t = torch.as_tensor(np.asarray(params[k]), dtype=torch.float32).reshape(shape)
             self.p(k).copy_(t)
+        self.sync_shadow()
 
     def to_dict(self, buf=None) -> dict:
         buf = self.params if buf is None else buf
@@ -93,7 +108,7 @@ class ParamStore:
 
 # ------------------------------------------------------------------ kernel wrappers
 def gemm(a, b, c, *, transa=False, transb=False, bias=None, relu=False, mask=None, accumulate=False,
-         precision="fp32"):
+         precision="fp32", round_out=False):
     """c = epi(op(a) @ op(b)) on 2-D row-major float32 tensors (strides = leading dims)."""
     m, n = c.shape
     k = a.shape[0] if transa else a.shape[1]
@@ -104,7 +119,7 @@ def gemm(a, b, c, *, transa=False, transb=False, bias=None, relu=False, mask=Non
     else:
         from . import tensorcore
         tensorcore.gemm(a, b, c, transa=transa, transb=transb, bias=bias, relu=relu, mask=mask,
-                        accumulate=accumulate, precision=precision)
+                        accumulate=accumulate, precision=precision, round_out=round_out)
     return c
 
 
@@ -113,9 +128,9 @@ def colsum(x, out, ws, accumulate=False):
     call("cc_colsum_f32", ptr(x), x.stride(0), m, n, ptr(ws), ptr(out), int(accumulate), stream_ptr())
 
 
-def bag_fwd(w, idx, row_start, row_len, bias, out, relu=True):
+def bag_fwd(w, idx, row_start, row_len, bias, out, relu=True, round_tf32=False):
     call("cc_bag_fwd", ptr(w), w.stride(0), w.shape[1], ptr(idx), ptr(row_start), ptr(row_len), out.shape[0],
-         ptr(bias), ptr(out), out.stride(0), int(relu), stream_ptr())
+         ptr(bias), ptr(out), out.stride(0), int(relu), int(round_tf32), stream_ptr())
 
 
 def bag_bwd(g, idx, row_start, row_len, dw):
@@ -193,6 +208,10 @@ class CC_Recommender:
         self.device = torch.device(device)
         self.precision = precision
         self.store = ParamStore(self.N, self.device)
+        if precision == "tf32":
+            self.store.enable_tf32_shadow()
+        elif precision not in ("fp32",):
+            raise NotImplementedError(f"precision {precision!r}: supported modes are 'fp32' (exact FFMA) and 'tf32' (tcgen05)")
         self.store.init_glorot(seed)
         self.encoder = _Tower(self, "encoder")
         self.decoder = _Tower(self, "decoder")
@@ -203,10 +222,12 @@ class CC_Recommender:
         s = self.store
         b = sb.batch
         h = torch.empty((b, 512), dtype=torch.float32, device=self.device)
-        bag_fwd(s.p("encoder_e1/kernel"), sb.idx, sb.row_start, sb.row_len, s.p("encoder_e1/bias"), h)
+        rnd = self.precision == "tf32"
+        bag_fwd(s.p("encoder_e1/kernel"), sb.idx, sb.row_start, sb.row_len, s.p("encoder_e1/bias"), h, round_tf32=rnd)
         for name, width in zip(ENC_NAMES[1:], HIDDEN[1:]):
             o = torch.empty((b, width), dtype=torch.float32, device=self.device)
-            gemm(h, s.p(name + "/kernel"), o, bias=s.p(name + "/bias"), relu=True, precision=self.precision)
+            gemm(h, s.w(name + "/kernel"), o, bias=s.p(name + "/bias"), relu=True, precision=self.precision,
+                 round_out=rnd)
             h = o
         return h
 
@@ -215,13 +236,20 @@ class CC_Recommender:
         s = self.store
         b = h.shape[0]
         names = dec_names(prefix)
+        rnd = self.precision == "tf32"
+        h = h.contiguous()
+        if rnd:   # a caller-supplied latent is an operand of a kind::tf32 GEMM: round it like every other one
+            hr = torch.empty_like(h)
+            call("cc_round_tf32", ptr(h), ptr(hr), h.numel(), stream_ptr())
+            h = hr
         for name, width in zip(names[:3], (128, 256, 512)):
             o = torch.empty((b, width), dtype=torch.float32, device=self.device)
-            gemm(h.contiguous(), s.p(name + "/kernel"), o, bias=s.p(name + "/bias"), relu=True,
-                 precision=self.precision)
+            gemm(h, s.w(name + "/kernel"), o, bias=s.p(name + "/bias"), relu=True, precision=self.precision,
+                 round_out=rnd)
             h = o
-        z = torch.empty((b, self.N), dtype=torch.float32, device=self.device)
-        gemm(h, s.p(names[3] + "/kernel"), z, bias=s.p(names[3] + "/bias"), precision=self.precision)
+        cpad = (self.N + 3) // 4 * 4
+        z = torch.empty((b, cpad), dtype=torch.float32, device=self.device)[:, :self.N]
+        gemm(h, s.w(names[3] + "/kernel"), z, bias=s.p(names[3] + "/bias"), precision=self.precision)
         return z
 
     def call(self, inputs, training=None):

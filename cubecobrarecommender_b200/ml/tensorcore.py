@@ -1,0 +1,56 @@
+"""tcgen05 tensor-core GEMM wrappers (precision modes "tf32" and "bf16"); see csrc/gemm_tc.cu."""
+from __future__ import annotations
+
+import torch
+
+from .. import _lib
+from .._lib import call, ptr, stream_ptr
+
+PRECISION_CODE = {"tf32": 1, "bf16": 2}
+_SMS = None
+
+
+def _sms():
+    global _SMS
+    if _SMS is None:
+        _SMS = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    return _SMS
+
+
+def pick_split_k(m, n, k, precision):
+    """Spread long reductions with few output tiles (the dW GEMMs of the narrow layers) over
+    the SMs: one CTA per (tile, k-slice), float atomics into a zeroed C."""
+    tiles = ((m + 127) // 128) * ((n + 127) // 128)
+    kb = (k + (31 if precision == "tf32" else 63)) // (32 if precision == "tf32" else 64)
+    if tiles * 2 > _sms() or kb < 16:
+        return 1
+    return max(1, min(_sms() // tiles, kb // 8))
+
+
+def gemm(a, b, c, *, transa=False, transb=False, bias=None, relu=False, mask=None, accumulate=False,
+         precision="tf32", split_k=None, round_out=False):
+    m, n = c.shape
+    k = a.shape[0] if transa else a.shape[1]
+    want = torch.float32 if precision == "tf32" else torch.bfloat16
+    if a.dtype != want or b.dtype != want:
+        raise TypeError(f"precision {precision} needs {want} operands, got {a.dtype} / {b.dtype}")
+    plain = bias is None and not relu and mask is None
+    if split_k is None:
+        split_k = pick_split_k(m, n, k, precision) if plain else 1
+    call("cc_gemm_tc", PRECISION_CODE[precision], int(transa), int(transb), m, n, k, ptr(a), a.stride(0), ptr(b),
+         b.stride(0), ptr(c), c.stride(0), ptr(bias), int(relu), ptr(mask), mask.stride(0) if mask is not None else 0,
+         int(accumulate), int(split_k), int(round_out and precision == "tf32"), stream_ptr())
+    return c
+
+
+def gemm_bce(a, w, bias, ybits, count, dz, loss_partial, precision="tf32", round_out=True):
+    """Fused  z = a @ w + bias -> BCE loss partials + dlogits  (z never stored)."""
+    m, k = a.shape
+    n = w.shape[1]
+    call("cc_gemm_bce_tc", PRECISION_CODE[precision], m, n, k, ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(bias),
+         ptr(ybits), ybits.stride(0), float(count), ptr(dz), dz.stride(0), ptr(loss_partial),
+         int(round_out and precision == "tf32"), stream_ptr())
+
+
+def bce_partial_count(m, n):
+    return _lib.load().cc_gemm_bce_partial_count(m, n)

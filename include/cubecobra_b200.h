@@ -123,7 +123,7 @@ int cc_step_increment(int64_t* step_ptr, void* stream);
  * ---------------------------------------------------------------------------------- */
 int cc_bag_fwd(const float* w, int64_t ldw, int32_t hidden, const int32_t* idx, const int64_t* row_start,
                const int32_t* row_len, int32_t batch, const float* bias, float* out, int64_t ldo, int relu,
-               void* stream);
+               int round_tf32, void* stream);
 int cc_bag_bwd(const float* g, int64_t ldg, int32_t hidden, const int32_t* idx, const int64_t* row_start,
                const int32_t* row_len, int32_t batch, float* dw, int64_t ldw, void* stream);
 
@@ -136,6 +136,19 @@ int cc_bag_bwd(const float* g, int64_t ldg, int32_t hidden, const int32_t* idx, 
 int cc_gemm_f32_simt(int transa, int transb, int m, int n, int k, const float* a, int64_t lda, const float* b,
                      int64_t ldb, float* c, int64_t ldc, const float* bias, int relu, const float* mask,
                      int64_t ldmask, int accumulate, void* stream);
+/* tcgen05 tensor-core GEMM (TMA + TMEM).  precision: 1 = tf32 (float operands), 2 = bf16
+ * (__nv_bfloat16 operands; C, bias and mask stay float).  split_k > 1 spreads the reduction over
+ * CTAs with float atomics (plain epilogue only); operands need 16-byte aligned bases and rows. */
+int cc_gemm_tc(int precision, int transa, int transb, int m, int n, int k, const void* a, int64_t lda, const void* b,
+               int64_t ldb, float* c, int64_t ldc, const float* bias, int relu, const float* mask, int64_t ldmask,
+               int accumulate, int split_k, int round_tf32, void* stream);
+/* Fused decoder output layer + sigmoid-BCE (model.py:64,94 + train.py:85): z = A[M,K] W[K,N] + bias is
+ * never stored; dz[M][lddz] = (sigmoid(z) - y)/count (columns [N, lddz) zeroed), loss_partial float64
+ * [cc_gemm_bce_partial_count(m, n)] holds per-(column tile, row) loss sums for cc_loss_finalize. */
+int cc_gemm_bce_tc(int precision, int m, int n, int k, const void* a, int64_t lda, const void* w, int64_t ldw,
+                   const float* bias, const uint32_t* ybits, int64_t ywords, double count, float* dz, int64_t lddz,
+                   double* loss_partial, int round_tf32, void* stream);
+int64_t cc_gemm_bce_partial_count(int m, int n);
 int64_t cc_colsum_workspace_bytes(int m, int n);
 int cc_colsum_f32(const float* x, int64_t ld, int m, int n, float* workspace, float* out, int accumulate,
                   void* stream);
@@ -153,13 +166,17 @@ int cc_bce_logits_fwd_bwd(const float* z, int64_t ldz, const uint32_t* ybits, in
 /* row r uses target row target_rows[r] (nullable = r); dz = grad_scale*(q*S - t'*1[unclipped]). */
 int cc_softmax_kl_fwd_bwd(const float* z, int64_t ldz, const float* target, int64_t ldt, const int32_t* target_rows,
                           int32_t rows, int32_t num_cards, int32_t ncols_pad, double grad_scale, float* dz,
-                          int64_t lddz, double* row_loss, void* stream);
+                          int64_t lddz, double* row_loss, int round_tf32, void* stream);
 /* out3 (float64 [3]) = { sum(bce_rows)/bce_div, sum(kl_rows)/kl_div, bce + reg*kl } */
 int cc_loss_finalize(const double* bce_rows, int32_t nb, double bce_div, const double* kl_rows, int32_t nr,
                      double kl_div, double reg, double* out3, void* stream);
-/* TF-style Adam over flat buffers; the step number is *step_ptr + 1 (device int64). */
+/* TF-style Adam over flat buffers; the step number is *step_ptr + 1 (device int64).  shadow_tf32 (nullable)
+ * receives the updated weights rounded to tf32 (round-to-nearest) for the tensor-core GEMMs.
+ * round_tf32 flags elsewhere: outputs that feed a kind::tf32 GEMM are rounded to nearest where they are
+ * produced, because the tensor core itself truncates (biased). */
 int cc_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, const int64_t* step_ptr, float lr,
-                 float beta1, float beta2, float eps, void* stream);
+                 float beta1, float beta2, float eps, float* shadow_tf32, void* stream);
+int cc_round_tf32(const float* x, float* out, int64_t n, void* stream);
 int cc_sigmoid_f32(const float* z, float* out, int64_t n, void* stream);
 
 #ifdef __cplusplus
