@@ -52,7 +52,7 @@ SIGNATURES = {
     "cc_bag_bwd": (I, [P, I64, I32, P, P, P, I32, P, I64, P]),
     # (5) dense
     "cc_gemm_f32_simt": (I, [I, I, I, I, I, P, I64, P, I64, P, I64, P, I, P, I64, I, P]),
-    "cc_gemm_tc": (I, [I, I, I, I, I, I, P, I64, P, I64, P, I64, P, I, P, I64, I, I, I, P]),
+    "cc_gemm_tc": (I, [I, I, I, I, I, I, P, I64, P, I64, P, I64, P, I, P, I64, I, I, I, I, P]),
     "cc_gemm_bce_tc": (I, [I, I, I, I, P, I64, P, I64, P, P, I64, D, P, I64, P, I, P]),
     "cc_gemm_bce_partial_count": (I64, [I, I]),
     "cc_colsum_workspace_bytes": (I64, [I, I]),

@@ -9,14 +9,18 @@
 //   accumulation in TMEM) or bf16 storage, kind::f16.
 //
 // Structure (one persistent CTA per SM, 256 threads):
-//   warp 0   TMA producer: cp.async.bulk.tensor boxes -> 128B-swizzled smem ring (6 stages)
+//   warp 0   TMA producer: cp.async.bulk.tensor boxes -> 128B-swizzled smem ring
 //   warp 1   MMA issuer : one elected lane issues tcgen05.mma (128 x BN x 8|16), commits to
 //            the stage's "empty" mbarrier and, per tile, to the accumulator's "full" barrier
 //   warp 2   TMEM allocator (2 accumulator buffers: MMA of tile i+1 overlaps epilogue of tile i)
-//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns, bias/ReLU/mask or BCE, global stores
+//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns -> bias/ReLU/mask or BCE -> swizzled
+//            smem staging -> TMA store (or TMA reduce-add for split-K), so global writes are
+//            full 128-byte lines issued by the copy engine, not by the warps
 // Operands may be K-major ([rows, K], K contiguous) or MN-major ([K, rows], rows contiguous);
-// both are loaded with SWIZZLE_128B boxes and described to the MMA by shared-memory matrix
+// both are loaded with 128B-swizzle boxes and described to the MMA by shared-memory matrix
 // descriptors (LBO/SBO as in the PTX ISA "canonical layouts").
+// Tile = 128 x BN with BN in {128, 256}: with 4-byte operands a 128x128 tile needs 32 KB of
+// L2->SM traffic per MFLOP and saturates L2 bandwidth near 380 TFLOP/s; 128x256 cuts that by 25%.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -27,15 +31,19 @@ namespace cc {
 namespace tc {
 
 constexpr int BM = 128;
-constexpr int BN = 128;
-constexpr int STAGES = 6;
-constexpr int STAGE_A_BYTES = BM * 128;          // 128 rows x one 128-byte swizzle row
-constexpr int STAGE_B_BYTES = BN * 128;
-constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
 constexpr int NUM_ACC = 2;
-constexpr int TMEM_COLS = NUM_ACC * BN;          // 256 fp32 columns
 constexpr int THREADS = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int STAGE_A_BYTES = BM * 128;                 // 128 rows x one 128-byte swizzle row
+constexpr int EPI_STAGE_BYTES = 4 * 2 * 4096;           // 4 warps x 2 buffers x (32 rows x 128 B)
+constexpr int BAR_BYTES = 1024;
+
+template <int BN> struct Cfg {
+  static constexpr int STAGE_B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int TMEM_COLS = NUM_ACC * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + BAR_BYTES + 1024 /*align slack*/;
+};
 
 enum Epilogue : int { EPI_STORE = 0, EPI_BCE = 1 };
 
@@ -43,14 +51,14 @@ struct Params {
   int m, n, k;
   int m_tiles, n_tiles, k_blocks;       // k_blocks per split
   int split_k, total_k_blocks;
-  float* c; long long ldc;
   const float* bias;
   const float* mask; long long ldmask;
-  int relu, atomic_add, round_tf32;
+  int relu, reduce_add, round_tf32;
+  int n_store;                           // columns the store map covers (EPI_BCE: ldc, pad columns get zeros)
   // EPI_BCE
   const uint32_t* ybits; long long ywords;
   float inv_count;
-  double* loss_partial;                  // [n_tiles][m]
+  double* loss_partial;                  // [tiles][4 warps]
   int a_mn_major, b_mn_major;
 };
 
@@ -85,6 +93,19 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
@@ -114,41 +135,42 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// shared-memory matrix descriptor (SWIZZLE_128B, version 1)
+// shared-memory matrix descriptor (version 1)
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                              uint32_t layout_type) {
   uint64_t d = 0;
   d |= uint64_t((smem_addr >> 4) & 0x3fffu);
   d |= uint64_t((lbo_bytes >> 4) & 0x3fffu) << 16;
   d |= uint64_t((sbo_bytes >> 4) & 0x3fffu) << 32;
-  d |= uint64_t(1) << 46;        // descriptor version (Blackwell)
+  d |= uint64_t(1) << 46;             // descriptor version (Blackwell)
   d |= uint64_t(layout_type) << 61;   // 2 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B with 32-byte atoms
   return d;
 }
 
-__device__ __forceinline__ void red_add_f32(float* p, float v) {
-  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
-}
-
 // ------------------------------------------------------------------------ kernel
-template <bool BF16, int EPI>
+template <bool BF16, int EPI, int BN>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_c, const Params p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int STAGE_BYTES = C::STAGE_BYTES;
   constexpr int ELEM = BF16 ? 2 : 4;
   constexpr int BK = 128 / ELEM;                 // elements per 128-byte swizzle row (32 | 64)
   constexpr int UMMA_K = 32 / ELEM;              // 8 | 16
   constexpr int MMAS_PER_STAGE = BK / UMMA_K;    // 4
   constexpr int MN_BOX = BK;                     // MN-major boxes are [BK rows(k)] x [BK elems (128 B)]
   constexpr int MN_BOX_BYTES = BK * 128;
-  constexpr int MN_BOXES = 128 / MN_BOX;         // boxes per 128-wide operand tile (4 | 2)
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;                       // 1024-byte aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + NUM_ACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + NUM_ACC);
+  float* bias_smem = reinterpret_cast<float*>(epi_smem + EPI_STAGE_BYTES + 256);   // 4 warps x 32 floats, 16-B aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles * p.split_k;
@@ -156,6 +178,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -163,7 +186,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
@@ -188,14 +211,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           if (p.a_mn_major) {
 #pragma unroll
-            for (int j = 0; j < MN_BOXES; ++j)
+            for (int j = 0; j < BM / MN_BOX; ++j)
               tma_load_2d(sa + j * MN_BOX_BYTES, &map_a, &full_bar[stage], mt * BM + j * MN_BOX, kb * BK);
           } else {
             tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, mt * BM);
           }
           if (p.b_mn_major) {
 #pragma unroll
-            for (int j = 0; j < MN_BOXES; ++j)
+            for (int j = 0; j < BN / MN_BOX; ++j)
               tma_load_2d(sb + j * MN_BOX_BYTES, &map_b, &full_bar[stage], nt * BN + j * MN_BOX, kb * BK);
           } else {
             tma_load_2d(sb, &map_b, &full_bar[stage], kb * BK, nt * BN);
@@ -211,7 +234,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                              (uint32_t(p.a_mn_major) << 15) | (uint32_t(p.b_mn_major) << 16) |
                              (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
       // K-major: rows 128 B apart, 8-row groups 1024 B apart (SBO); K advance 32 B inside the swizzle row.
-      // MN-major: 128-byte MN atoms LBO apart, 8-row k groups 1024 B apart (SBO); K advance UMMA_K rows.
+      // MN-major: 128-byte MN atoms LBO apart, k-row groups SBO apart; K advance UMMA_K rows.
       // 32-bit (tf32) MN-major operands only exist in the "128B swizzle, 32-byte atom" layout: atoms of 4 k-rows
       // (SBO = 512 B); every other case uses the plain 128B swizzle with 8-row atoms (SBO = 1024 B).
       const uint32_t a_lbo = p.a_mn_major ? MN_BOX_BYTES : 16, b_lbo = p.b_mn_major ? MN_BOX_BYTES : 16;
@@ -248,6 +271,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp >= 4) {
     // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
     const int q = warp & 3;
+    uint8_t* stage_buf = epi_smem + q * 8192;             // two 4 KB buffers (32 rows x 128 B, 128B-swizzled)
+    float* bsm = bias_smem + q * 32;
+    int buf = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt = tile % p.m_tiles;
@@ -256,87 +282,114 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool has_k = ks * p.k_blocks < p.total_k_blocks;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      const int row = mt * BM + q * 32 + lane;
+      const int row0 = mt * BM + q * 32;
+      const int row = row0 + lane;
       const bool row_ok = row < p.m;
       float row_loss = 0.f;
 #pragma unroll 1
       for (int cb = 0; cb < BN / 32; ++cb) {
+        const int col0 = nt * BN + cb * 32;
+        if (col0 >= p.n_store || row0 >= p.m || !has_k) break;      // warp-uniform
         uint32_t v[32];
         __syncwarp();
         tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + cb * 32), v);
-        const int col0 = nt * BN + cb * 32;
-        if (!row_ok || !has_k || col0 >= (EPI == EPI_BCE ? int(p.ldc) : p.n)) continue;
+        if (p.bias) {
+          bsm[lane] = (col0 + lane < p.n) ? __ldg(p.bias + col0 + lane) : 0.f;
+          __syncwarp();
+        }
+        float out[32];
         if (EPI == EPI_BCE) {
-          const uint32_t ybw = p.ybits[(long long)row * p.ywords + (col0 >> 5)];
-          float* dst = p.c + (long long)row * p.ldc + col0;
-          float out[32];
+          const uint32_t ybw = row_ok ? p.ybits[(long long)row * p.ywords + (col0 >> 5)] : 0u;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            float z = __uint_as_float(v[j]);
-            float g = 0.f;
-            if (col < p.n) {
-              z += __ldg(p.bias + col);
+          for (int j4 = 0; j4 < 32; j4 += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bsm + j4);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = j4 + jj;
+              const float z = __uint_as_float(v[j]) + bb[jj];
               const float y = float((ybw >> j) & 1u);
+              // softplus(z) - z*y and sigmoid(z) from one exp: e = exp(-|z|)
               const float e = __expf(-fabsf(z));
-              row_loss += fmaxf(z, 0.f) - z * y + log1pf(e);
-              const float r = __fdividef(1.f, 1.f + e);
-              g = ((z >= 0.f ? r : e * r) - y) * p.inv_count;
-              if (p.round_tf32) g = rn_tf32(g);
+              const float r = __frcp_rn(1.f + e);
+              const float l = fmaxf(z, 0.f) - z * y + __logf(1.f + e);
+              float g = ((z >= 0.f ? r : e * r) - y) * p.inv_count;
+              const bool live = (col0 + j < p.n);
+              row_loss += live ? l : 0.f;
+              g = live ? g : 0.f;
+              out[j] = p.round_tf32 ? rn_tf32(g) : g;
             }
-            out[j] = g;
           }
-          // dlogits, pad columns [n, ldc) written as zero so later GEMMs may read full rows
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            if (col0 + j < p.ldc)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
         } else {
-          float* dst = p.c + (long long)row * p.ldc + col0;
-          const float* mrow = p.mask ? p.mask + (long long)row * p.ldmask + col0 : nullptr;
-          const bool vec_ok = (col0 + 32 <= p.n) && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
-          float out[32];
+          const float* mrow = (p.mask && row_ok) ? p.mask + (long long)row * p.ldmask + col0 : nullptr;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float z = __uint_as_float(v[j]);
-            const int col = col0 + j;
-            if (col < p.n) {
-              if (p.bias) z += __ldg(p.bias + col);
-              if (p.relu) z = fmaxf(z, 0.f);
-              if (mrow) z = (__ldg(mrow + j) > 0.f) ? z : 0.f;
-              if (p.round_tf32) z = rn_tf32(z);
+          for (int j4 = 0; j4 < 32; j4 += 4) {
+            float bb[4] = {0.f, 0.f, 0.f, 0.f};
+            if (p.bias) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bsm + j4);
+              bb[0] = b4.x; bb[1] = b4.y; bb[2] = b4.z; bb[3] = b4.w;
             }
-            out[j] = z;
-          }
-          if (p.atomic_add) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.n) red_add_f32(dst + j, out[j]);
-          } else if (vec_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.n) dst[j] = out[j];
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = j4 + jj;
+              float z = __uint_as_float(v[j]) + bb[jj];
+              if (p.relu) z = fmaxf(z, 0.f);
+              if (mrow && col0 + j < p.n) z = (__ldg(mrow + j) > 0.f) ? z : 0.f;
+              out[j] = p.round_tf32 ? rn_tf32(z) : z;
+            }
           }
         }
+        // registers -> swizzled staging (row = lane, 16-byte chunk c at position c ^ (lane & 7)) -> TMA store
+        uint8_t* sbuf = stage_buf + buf * 4096;
+        if (lane == 0) tma_wait_group_read<1>();        // the store that last read this buffer has drained
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(sbuf + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+              make_float4(out[4 * c], out[4 * c + 1], out[4 * c + 2], out[4 * c + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (p.reduce_add) tma_reduce_add_2d(&map_c, sbuf, col0, row0);
+          else              tma_store_2d(&map_c, sbuf, col0, row0);
+          tma_commit_group();
+        }
+        buf ^= 1;
       }
-      if (EPI == EPI_BCE && row_ok) p.loss_partial[(long long)nt * p.m + row] = double(row_loss);
+      if (EPI == EPI_BCE) {
+        // one float64 partial per (tile, warp): fixed summation order downstream
+        const float s = row_ok ? row_loss : 0.f;
+        const double d = warp_sum(double(s));
+        if (lane == 0) p.loss_partial[(long long)tile * 4 + q] = d;
+      }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
   }
 
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
   }
+}
+
+// elementwise epilogue for split-K GEMMs whose epilogue is not linear: c = round(mask(relu(c + bias)))
+__global__ void post_epilogue_kernel(float* __restrict__ c, long long ldc, int m, int n, const float* __restrict__ bias,
+                                     int relu, const float* __restrict__ mask, long long ldmask, int round_tf32) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)m * n) return;
+  const int r = int(i / n), col = int(i % n);
+  float z = c[(long long)r * ldc + col];
+  if (bias) z += bias[col];
+  if (relu) z = fmaxf(z, 0.f);
+  if (mask) z = (mask[(long long)r * ldmask + col] > 0.f) ? z : 0.f;
+  if (round_tf32) z = rn_tf32(z);
+  c[(long long)r * ldc + col] = z;
 }
 
 // ---------------------------------------------------------------- host helpers
@@ -358,23 +411,19 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 2-D row-major matrix [rows][cols] (cols contiguous, leading dimension ld elements);
-// box = box_rows x (128 bytes of columns), SWIZZLE_128B.
-static int make_map(CUtensorMap* map, const void* base, bool bf16, long long rows, long long cols, long long ld,
-                    int box_rows, bool mn_major) {
+// box = box_rows x (128 bytes of columns), 128B swizzle (32-byte atoms for 4-byte MN-major operands).
+static int make_map(CUtensorMap* map, const void* base, int elem, bool bf16, long long rows, long long cols,
+                    long long ld, int box_rows, bool atom32) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return CC_ERR_CUDA; }
-  const int elem = bf16 ? 2 : 4;
   cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
   cuuint64_t strides[1] = {cuuint64_t(ld) * elem};
   cuuint32_t box[2] = {cuuint32_t(128 / elem), cuuint32_t(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  static const bool tf32_map = getenv("CC_TC_TF32_MAP") != nullptr;
-  const CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
-                                  : (tf32_map ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32), 2,
+  const CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                         const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        (!bf16 && mn_major) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): base=%p rows=%lld cols=%lld ld=%lld", int(r), base, rows, cols, ld);
     return CC_ERR_CUDA;
@@ -386,46 +435,74 @@ struct Problem {
   int transa, transb, m, n, k;
   const void* a; long long lda;
   const void* b; long long ldb;
+  float* c; long long ldc;
   bool bf16;
 };
 
-template <bool BF16, int EPI>
-static int launch(const Problem& pr, Params p, cudaStream_t st) {
+// waves-based efficiency of (BN, split) on `sms` persistent CTAs
+static double plan_eff(int m, int n, int kblocks, int bn, int split, int sms) {
+  const long long tiles = (long long)ceil_div(m, BM) * ceil_div(n, bn) * split;
+  const int kb = ceil_div(kblocks, split);
+  const long long waves = ceil_div<long long>(tiles, (long long)sms);
+  // a tile costs kb*bn (+ a fixed prologue/epilogue worth ~6 k-blocks)
+  const double busy = double(ceil_div(m, BM)) * ceil_div(n, bn) * kblocks * bn;
+  const double span = double(waves) * sms * (kb + 6) * bn;
+  double eff = busy / span;
+  if (bn == 128) eff *= 0.85;       // 128-wide tiles are L2-bandwidth limited with 4-byte operands
+  if (split > 1) eff *= 0.97;       // reduce traffic + zero fill
+  return eff;
+}
+
+template <bool BF16, int EPI, int BN>
+static int launch_bn(const Problem& pr, Params p, cudaStream_t st) {
+  using C = Cfg<BN>;
   const int elem = BF16 ? 2 : 4;
   const int bk = 128 / elem;
-  CC_REQUIRE((reinterpret_cast<uintptr_t>(pr.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(pr.b) & 15) == 0,
-             "cc_gemm_tc: operand base pointers must be 16-byte aligned");
-  CC_REQUIRE((pr.lda * elem) % 16 == 0 && (pr.ldb * elem) % 16 == 0,
-             "cc_gemm_tc: leading dimensions must be multiples of 16 bytes (lda=%lld ldb=%lld)", pr.lda, pr.ldb);
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_c;
   int rc;
   // transa=0: A is [M][K] (K-major)  -> box 128 rows x 128 B;  transa=1: A is [K][M] (MN-major) -> box bk rows x 128 B
-  if (pr.transa) rc = make_map(&map_a, pr.a, BF16, pr.k, pr.m, pr.lda, bk, true);
-  else           rc = make_map(&map_a, pr.a, BF16, pr.m, pr.k, pr.lda, BM, false);
+  if (pr.transa) rc = make_map(&map_a, pr.a, elem, BF16, pr.k, pr.m, pr.lda, bk, !BF16);
+  else           rc = make_map(&map_a, pr.a, elem, BF16, pr.m, pr.k, pr.lda, BM, false);
   if (rc != CC_OK) return rc;
   // transb=1: B is [N][K] (K-major);  transb=0: B is [K][N] (MN-major)
-  if (pr.transb) rc = make_map(&map_b, pr.b, BF16, pr.n, pr.k, pr.ldb, BN, false);
-  else           rc = make_map(&map_b, pr.b, BF16, pr.k, pr.n, pr.ldb, bk, true);
+  if (pr.transb) rc = make_map(&map_b, pr.b, elem, BF16, pr.n, pr.k, pr.ldb, BN, false);
+  else           rc = make_map(&map_b, pr.b, elem, BF16, pr.k, pr.n, pr.ldb, bk, !BF16);
+  if (rc != CC_OK) return rc;
+  // C: fp32 [M][n_store] boxes of 32 rows x 32 columns (TMA clips rows >= M and columns >= n_store)
+  rc = make_map(&map_c, pr.c, 4, false, pr.m, p.n_store, pr.ldc, 32, false);
   if (rc != CC_OK) return rc;
   p.a_mn_major = pr.transa ? 1 : 0;
   p.b_mn_major = pr.transb ? 0 : 1;
   p.m_tiles = ceil_div(pr.m, BM);
-  p.n_tiles = ceil_div(pr.n, BN);
+  p.n_tiles = ceil_div(p.n_store, BN);
   p.total_k_blocks = ceil_div(pr.k, bk);
   if (p.split_k < 1) p.split_k = 1;
   p.k_blocks = ceil_div(p.total_k_blocks, p.split_k);
   p.split_k = ceil_div(p.total_k_blocks, p.k_blocks);
   const int tiles = p.m_tiles * p.n_tiles * p.split_k;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  auto kern = gemm_tc_kernel<BF16, EPI>;
+  auto kern = gemm_tc_kernel<BF16, EPI, BN>;
   static bool attr_done = false;
   if (!attr_done) {
-    CC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    CC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_done = true;
   }
-  kern<<<grid, THREADS, SMEM_BYTES, st>>>(map_a, map_b, p);
+  kern<<<grid, THREADS, C::SMEM_BYTES, st>>>(map_a, map_b, map_c, p);
   CC_CHECK_LAUNCH();
   return CC_OK;
+}
+
+template <bool BF16, int EPI>
+static int launch(const Problem& pr, Params p, int bn, cudaStream_t st) {
+  const int elem = BF16 ? 2 : 4;
+  CC_REQUIRE((reinterpret_cast<uintptr_t>(pr.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(pr.b) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(pr.c) & 15) == 0,
+             "cc_gemm_tc: base pointers must be 16-byte aligned");
+  CC_REQUIRE((pr.lda * elem) % 16 == 0 && (pr.ldb * elem) % 16 == 0 && (pr.ldc * 4) % 16 == 0,
+             "cc_gemm_tc: leading dimensions must be multiples of 16 bytes (lda=%lld ldb=%lld ldc=%lld)", pr.lda,
+             pr.ldb, pr.ldc);
+  if (bn == 256) return launch_bn<BF16, EPI, 256>(pr, p, st);
+  return launch_bn<BF16, EPI, 128>(pr, p, st);
 }
 
 }  // namespace tc
@@ -435,50 +512,76 @@ using namespace cc;
 
 extern "C" {
 
-// precision: 1 = tf32 (float operands), 2 = bf16 (__nv_bfloat16 operands; C, bias, mask stay float)
+// precision: 1 = tf32 (float operands), 2 = bf16 (__nv_bfloat16 operands; C, bias, mask stay float).
+// split_k: 0 = choose (tile width and split) automatically, >= 1 = as given (tile_n: 0 auto | 128 | 256).
 int cc_gemm_tc(int precision, int transa, int transb, int m, int n, int k, const void* a, int64_t lda, const void* b,
                int64_t ldb, float* c, int64_t ldc, const float* bias, int relu, const float* mask, int64_t ldmask,
-               int accumulate, int split_k, int round_tf32, void* stream) {
+               int accumulate, int split_k, int tile_n, int round_tf32, void* stream) {
   CC_REQUIRE(a && b && c, "cc_gemm_tc: null pointer");
   CC_REQUIRE(precision == 1 || precision == 2, "cc_gemm_tc: precision must be 1 (tf32) or 2 (bf16)");
   CC_REQUIRE(m >= 0 && n >= 0 && k > 0, "cc_gemm_tc: bad sizes m=%d n=%d k=%d", m, n, k);
+  CC_REQUIRE(tile_n == 0 || tile_n == 128 || tile_n == 256, "cc_gemm_tc: tile_n must be 0, 128 or 256");
   if (m == 0 || n == 0) return CC_OK;
-  CC_REQUIRE(split_k <= 1 || (!bias && !relu && !mask), "cc_gemm_tc: split-K cannot carry a non-linear epilogue");
   cudaStream_t st = as_stream(stream);
+  const int kblocks = ceil_div(k, precision == 2 ? 64 : 32);
+  const int sms = sm_count();
+  int bn = tile_n, split = split_k;
+  if (split <= 0 || bn == 0) {
+    double best = -1.0;
+    const int bns[2] = {256, 128};
+    for (int bi = 0; bi < 2; ++bi) {
+      if (tile_n && bns[bi] != tile_n) continue;
+      if (!tile_n && bns[bi] == 256 && n <= 128) continue;
+      const int smax = split_k > 0 ? split_k : (kblocks >= 16 ? (kblocks / 8 < 64 ? kblocks / 8 : 64) : 1);
+      for (int s = (split_k > 0 ? split_k : 1); s <= smax; ++s) {
+        const double e = tc::plan_eff(m, n, kblocks, bns[bi], s, sms);
+        if (e > best + 1e-9) { best = e; bn = bns[bi]; split = s; }
+      }
+    }
+  }
+  const bool nonlinear = bias || relu || mask || round_tf32;
+  const bool two_pass = split > 1 && nonlinear;
+  CC_REQUIRE(!(two_pass && accumulate), "cc_gemm_tc: accumulate with a split-K non-linear epilogue is not supported");
   tc::Params p{};
-  p.m = m; p.n = n; p.k = k;
-  p.c = c; p.ldc = ldc; p.bias = bias; p.mask = mask; p.ldmask = ldmask; p.relu = relu;
-  p.round_tf32 = round_tf32;
-  p.split_k = split_k < 1 ? 1 : split_k;
-  p.atomic_add = (accumulate || p.split_k > 1) ? 1 : 0;
-  if (p.split_k > 1 && !accumulate)
+  p.m = m; p.n = n; p.k = k; p.n_store = n;
+  p.bias = two_pass ? nullptr : bias; p.mask = two_pass ? nullptr : mask; p.ldmask = ldmask;
+  p.relu = two_pass ? 0 : relu; p.round_tf32 = two_pass ? 0 : round_tf32;
+  p.split_k = split;
+  p.reduce_add = (accumulate || split > 1) ? 1 : 0;
+  if (split > 1 && !accumulate)
     CC_CHECK_CUDA(cudaMemset2DAsync(c, size_t(ldc) * 4, 0, size_t(n) * 4, m, st));
-  tc::Problem pr{transa, transb, m, n, k, a, lda, b, ldb, precision == 2};
-  if (precision == 2) return tc::launch<true, tc::EPI_STORE>(pr, p, st);
-  return tc::launch<false, tc::EPI_STORE>(pr, p, st);
+  tc::Problem pr{transa, transb, m, n, k, a, lda, b, ldb, c, ldc, precision == 2};
+  int rc = precision == 2 ? tc::launch<true, tc::EPI_STORE>(pr, p, bn, st) : tc::launch<false, tc::EPI_STORE>(pr, p, bn, st);
+  if (rc != CC_OK) return rc;
+  if (two_pass) {
+    const long long total = (long long)m * n;
+    tc::post_epilogue_kernel<<<(unsigned)ceil_div<long long>(total, 256LL), 256, 0, st>>>(c, ldc, m, n, bias, relu, mask,
+                                                                                         ldmask, round_tf32);
+    CC_CHECK_LAUNCH();
+  }
+  return CC_OK;
 }
 
 // Fused decoder output layer + sigmoid-BCE:  z = A[M,K] W[K,N] + bias;  loss partials and
 // dlogits = (sigmoid(z) - y)/count written to dz[M][lddz] (columns [N, lddz) zeroed).
-// loss_partial: float64 [ceil(N/128)][M]  (sum it with cc_loss_finalize).
+// loss_partial: float64 [cc_gemm_bce_partial_count(m, lddz)]  (sum it with cc_loss_finalize).
 int cc_gemm_bce_tc(int precision, int m, int n, int k, const void* a, int64_t lda, const void* w, int64_t ldw,
                    const float* bias, const uint32_t* ybits, int64_t ywords, double count, float* dz, int64_t lddz,
                    double* loss_partial, int round_tf32, void* stream) {
   CC_REQUIRE(a && w && bias && ybits && dz && loss_partial, "cc_gemm_bce_tc: null pointer");
   CC_REQUIRE(precision == 1 || precision == 2, "cc_gemm_bce_tc: precision must be 1 (tf32) or 2 (bf16)");
   CC_REQUIRE(m > 0 && n > 0 && k > 0 && count > 0, "cc_gemm_bce_tc: bad sizes");
-  CC_REQUIRE(lddz % 128 == 0 && lddz >= n && ywords * 32 >= lddz && (reinterpret_cast<uintptr_t>(dz) & 15) == 0,
-             "cc_gemm_bce_tc: lddz must be a multiple of 128 >= n, ywords*32 >= lddz, dz 16-byte aligned");
+  CC_REQUIRE(lddz % 32 == 0 && lddz >= n && ywords * 32 >= lddz,
+             "cc_gemm_bce_tc: lddz must be a multiple of 32 >= n and ywords*32 >= lddz");
   tc::Params p{};
-  p.m = m; p.n = n; p.k = k;
-  p.c = dz; p.ldc = lddz; p.bias = bias; p.split_k = 1;
-  p.round_tf32 = round_tf32;
+  p.m = m; p.n = n; p.k = k; p.n_store = int(lddz);
+  p.bias = bias; p.split_k = 1; p.round_tf32 = round_tf32;
   p.ybits = ybits; p.ywords = ywords; p.inv_count = float(1.0 / count); p.loss_partial = loss_partial;
-  tc::Problem pr{0, 0, m, n, k, a, lda, w, ldw, precision == 2};
-  if (precision == 2) return tc::launch<true, tc::EPI_BCE>(pr, p, as_stream(stream));
-  return tc::launch<false, tc::EPI_BCE>(pr, p, as_stream(stream));
+  tc::Problem pr{0, 0, m, n, k, a, lda, w, ldw, dz, lddz, precision == 2};
+  if (precision == 2) return tc::launch<true, tc::EPI_BCE>(pr, p, 256, as_stream(stream));
+  return tc::launch<false, tc::EPI_BCE>(pr, p, 256, as_stream(stream));
 }
 
-int64_t cc_gemm_bce_partial_count(int m, int n) { return int64_t(ceil_div(n, tc::BN)) * m; }
+int64_t cc_gemm_bce_partial_count(int m, int lddz) { return int64_t(ceil_div(m, tc::BM)) * ceil_div(lddz, 256) * 4; }
 
 }  // extern "C"

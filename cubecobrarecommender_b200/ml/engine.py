@@ -91,7 +91,7 @@ class DAEEngine:
             if self.C % 4:
                 raise ValueError("tensor-core precision modes need num_cards % 4 == 0 (16-byte TMA rows)")
             from . import tensorcore
-            self.bce_partial = torch.zeros(tensorcore.bce_partial_count(B, self.C), dtype=torch.float64, device=d)
+            self.bce_partial = torch.zeros(tensorcore.bce_partial_count(B, self.cpad), dtype=torch.float64, device=d)
         lib = _lib.load()
         ws = max(lib.cc_colsum_workspace_bytes(T, max(self.cpad, max(HIDDEN))), 1024)
         self.cs_ws = torch.empty(ws // 4, dtype=f32, device=d)

@@ -17,29 +17,18 @@ def _sms():
     return _SMS
 
 
-def pick_split_k(m, n, k, precision):
-    """Spread long reductions with few output tiles (the dW GEMMs of the narrow layers) over
-    the SMs: one CTA per (tile, k-slice), float atomics into a zeroed C."""
-    tiles = ((m + 127) // 128) * ((n + 127) // 128)
-    kb = (k + (31 if precision == "tf32" else 63)) // (32 if precision == "tf32" else 64)
-    if tiles * 2 > _sms() or kb < 16:
-        return 1
-    return max(1, min(_sms() // tiles, kb // 8))
-
-
 def gemm(a, b, c, *, transa=False, transb=False, bias=None, relu=False, mask=None, accumulate=False,
-         precision="tf32", split_k=None, round_out=False):
+         precision="tf32", split_k=0, tile_n=0, round_out=False):
+    """split_k = 0 / tile_n = 0: the library picks the tile width (128 | 256) and the K split from a
+    wave-quantisation model (csrc/gemm_tc.cu plan_eff)."""
     m, n = c.shape
     k = a.shape[0] if transa else a.shape[1]
     want = torch.float32 if precision == "tf32" else torch.bfloat16
     if a.dtype != want or b.dtype != want:
         raise TypeError(f"precision {precision} needs {want} operands, got {a.dtype} / {b.dtype}")
-    plain = bias is None and not relu and mask is None
-    if split_k is None:
-        split_k = pick_split_k(m, n, k, precision) if plain else 1
     call("cc_gemm_tc", PRECISION_CODE[precision], int(transa), int(transb), m, n, k, ptr(a), a.stride(0), ptr(b),
          b.stride(0), ptr(c), c.stride(0), ptr(bias), int(relu), ptr(mask), mask.stride(0) if mask is not None else 0,
-         int(accumulate), int(split_k), int(round_out and precision == "tf32"), stream_ptr())
+         int(accumulate), int(split_k or 0), int(tile_n), int(round_out and precision == "tf32"), stream_ptr())
     return c
 
 
@@ -52,5 +41,5 @@ def gemm_bce(a, w, bias, ybits, count, dz, loss_partial, precision="tf32", round
          int(round_out and precision == "tf32"), stream_ptr())
 
 
-def bce_partial_count(m, n):
-    return _lib.load().cc_gemm_bce_partial_count(m, n)
+def bce_partial_count(m, lddz):
+    return _lib.load().cc_gemm_bce_partial_count(m, lddz)

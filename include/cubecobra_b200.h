@@ -136,19 +136,21 @@ int cc_bag_bwd(const float* g, int64_t ldg, int32_t hidden, const int32_t* idx, 
 int cc_gemm_f32_simt(int transa, int transb, int m, int n, int k, const float* a, int64_t lda, const float* b,
                      int64_t ldb, float* c, int64_t ldc, const float* bias, int relu, const float* mask,
                      int64_t ldmask, int accumulate, void* stream);
-/* tcgen05 tensor-core GEMM (TMA + TMEM).  precision: 1 = tf32 (float operands), 2 = bf16
- * (__nv_bfloat16 operands; C, bias and mask stay float).  split_k > 1 spreads the reduction over
- * CTAs with float atomics (plain epilogue only); operands need 16-byte aligned bases and rows. */
+/* tcgen05 tensor-core GEMM (TMA + TMEM, TMA-store epilogue).  precision: 1 = tf32 (float operands),
+ * 2 = bf16 (__nv_bfloat16 operands; C, bias and mask stay float).  split_k: 0 = choose tile width and
+ * K split automatically, > 1 = spread the reduction over CTAs (TMA reduce-add into C; a non-linear
+ * epilogue then runs as a second elementwise pass).  tile_n: 0 (auto) | 128 | 256.  A, B and C need
+ * 16-byte aligned bases and leading dimensions that are multiples of 16 bytes. */
 int cc_gemm_tc(int precision, int transa, int transb, int m, int n, int k, const void* a, int64_t lda, const void* b,
                int64_t ldb, float* c, int64_t ldc, const float* bias, int relu, const float* mask, int64_t ldmask,
-               int accumulate, int split_k, int round_tf32, void* stream);
+               int accumulate, int split_k, int tile_n, int round_tf32, void* stream);
 /* Fused decoder output layer + sigmoid-BCE (model.py:64,94 + train.py:85): z = A[M,K] W[K,N] + bias is
- * never stored; dz[M][lddz] = (sigmoid(z) - y)/count (columns [N, lddz) zeroed), loss_partial float64
- * [cc_gemm_bce_partial_count(m, n)] holds per-(column tile, row) loss sums for cc_loss_finalize. */
+ * never stored; dz[M][lddz] = (sigmoid(z) - y)/count (columns [N, lddz) zeroed, lddz % 32 == 0), loss_partial
+ * float64 [cc_gemm_bce_partial_count(m, lddz)] holds per-(tile, warp) loss sums for cc_loss_finalize. */
 int cc_gemm_bce_tc(int precision, int m, int n, int k, const void* a, int64_t lda, const void* w, int64_t ldw,
                    const float* bias, const uint32_t* ybits, int64_t ywords, double count, float* dz, int64_t lddz,
                    double* loss_partial, int round_tf32, void* stream);
-int64_t cc_gemm_bce_partial_count(int m, int n);
+int64_t cc_gemm_bce_partial_count(int m, int lddz);
 int64_t cc_colsum_workspace_bytes(int m, int n);
 int cc_colsum_f32(const float* x, int64_t ld, int m, int n, float* workspace, float* out, int accumulate,
                   void* stream);

@@ -141,10 +141,12 @@ def _rn_tf32(x):
     return ((xi + 0x0FFF + ((xi >> 13) & 1)) & ~0x1FFF).view(torch.float32)
 
 
+@pytest.mark.parametrize("tile_n", [128, 256])
 @pytest.mark.parametrize("ta,tb,m,n,k,split", [(0, 0, 130, 72, 132, 1), (0, 1, 64, 260, 100, 1), (1, 0, 132, 128, 300, 1),
                                                (1, 1, 20, 24, 36, 1), (0, 0, 4096, 512, 256, 1), (1, 0, 512, 64, 8192, 0),
-                                               (1, 0, 128, 260, 4100, 7), (0, 1, 300, 260, 20884, 1)])
-def test_gemm_tcgen05_tf32_all_layouts(ta, tb, m, n, k, split):
+                                               (1, 0, 128, 260, 4100, 7), (0, 1, 300, 260, 20884, 1),
+                                               (0, 1, 300, 520, 20884, 0)])
+def test_gemm_tcgen05_tf32_all_layouts(ta, tb, m, n, k, split, tile_n):
     """tcgen05 kind::tf32 GEMM vs float64 on operands already rounded to tf32 (so the products are exact
     and only fp32 accumulation differs): K-major and MN-major operands, ragged tiles, split-K."""
     from cubecobrarecommender_b200.ml import tensorcore as TC
@@ -155,7 +157,7 @@ def test_gemm_tcgen05_tf32_all_layouts(ta, tb, m, n, k, split):
     ref = opa @ opb
     scale = ref.abs().max().item()
     c = torch.full((m, n), 7.0, device="cuda")
-    TC.gemm(a, b, c, transa=bool(ta), transb=bool(tb), precision="tf32", split_k=split or None)
+    TC.gemm(a, b, c, transa=bool(ta), transb=bool(tb), precision="tf32", split_k=split, tile_n=tile_n if split else 0)
     tol = 2e-5 + 4e-9 * k                 # fp32 accumulation in TMEM over k terms
     assert (c.double() - ref).abs().max().item() / scale < tol
     if split == 1:
@@ -163,13 +165,20 @@ def test_gemm_tcgen05_tf32_all_layouts(ta, tb, m, n, k, split):
         mask = torch.randn(m, n, device="cuda", generator=g)
         c2 = torch.full((m, n), 7.0, device="cuda")
         TC.gemm(a, b, c2, transa=bool(ta), transb=bool(tb), bias=bias, relu=True, mask=mask, precision="tf32",
-                round_out=True)
+                round_out=True, split_k=1, tile_n=tile_n)
         ref2 = torch.relu(ref + bias.double()) * (mask > 0)
         assert (c2.double() - ref2).abs().max().item() / scale < 6e-4       # output rounded to tf32 (2^-11)
         assert torch.equal(c2, _rn_tf32(c2))
         c3 = torch.ones((m, n), device="cuda")
-        TC.gemm(a, b, c3, transa=bool(ta), transb=bool(tb), accumulate=True, precision="tf32")
+        TC.gemm(a, b, c3, transa=bool(ta), transb=bool(tb), accumulate=True, precision="tf32", split_k=1,
+                tile_n=tile_n)
         assert (c3.double() - ref - 1).abs().max().item() / scale < tol
+    if split != 1:      # split-K with a non-linear epilogue = reduce-add pass + elementwise pass
+        bias = torch.randn(n, device="cuda", generator=g)
+        c4 = torch.full((m, n), 7.0, device="cuda")
+        TC.gemm(a, b, c4, transa=bool(ta), transb=bool(tb), bias=bias, relu=True, precision="tf32", split_k=split,
+                tile_n=tile_n if split else 0)
+        assert (c4.double() - torch.relu(ref + bias.double())).abs().max().item() / scale < tol
 
 
 def test_gemm_bce_fused_epilogue_vs_oracle():
@@ -183,7 +192,7 @@ def test_gemm_bce_fused_epilogue_vs_oracle():
     y = (torch.rand(m, c, device="cuda", generator=g) < 0.05).double().cpu().numpy()
     yb = torch.tensor(_bits_from_dense(y)).cuda()
     dz = torch.full((m, cpad), 9.0, device="cuda")
-    part = torch.zeros(TC.bce_partial_count(m, c), dtype=torch.float64, device="cuda")
+    part = torch.zeros(TC.bce_partial_count(m, cpad), dtype=torch.float64, device="cuda")
     TC.gemm_bce(a, w, bias, yb, float(m * c), dz, part, precision="tf32", round_out=False)
     z = (a.double() @ w.double() + bias.double()).cpu().numpy()
     ref_loss = od.bce_from_logits_np(z, y)
