@@ -35,7 +35,7 @@ constexpr int NUM_ACC = 2;
 constexpr int THREADS = 256;
 constexpr int STAGE_A_BYTES = BM * 128;                 // 128 rows x one 128-byte swizzle row
 constexpr int EPI_STAGE_BYTES = 4 * 2 * 4096;           // 4 warps x 2 buffers x (32 rows x 128 B)
-constexpr int BAR_BYTES = 1024;
+constexpr int BAR_BYTES = 256;
 
 template <int BN> struct Cfg {
   static constexpr int STAGE_B_BYTES = BN * 128;
@@ -60,6 +60,7 @@ struct Params {
   float inv_count;
   double* loss_partial;                  // [tiles][4 warps]
   int a_mn_major, b_mn_major;
+  int debug;                             // experiment switches (CC_TC_DEBUG), 0 in production
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -135,6 +136,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ float exp2f_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float lg2_approx(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 // shared-memory matrix descriptor (version 1)
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                              uint32_t layout_type) {
@@ -170,7 +175,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + NUM_ACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + NUM_ACC);
-  float* bias_smem = reinterpret_cast<float*>(epi_smem + EPI_STAGE_BYTES + 256);   // 4 warps x 32 floats, 16-B aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles * p.split_k;
@@ -272,7 +276,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
     const int q = warp & 3;
     uint8_t* stage_buf = epi_smem + q * 8192;             // two 4 KB buffers (32 rows x 128 B, 128B-swizzled)
-    float* bsm = bias_smem + q * 32;
     int buf = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -280,11 +283,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int nt = (tile / p.m_tiles) % p.n_tiles;
       const int ks = tile / (p.m_tiles * p.n_tiles);
       const bool has_k = ks * p.k_blocks < p.total_k_blocks;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tcgen05_fence_after();
       const int row0 = mt * BM + q * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.m;
+      // operands of the epilogue that live in global memory (the bias slice, and for BCE this row's y bits)
+      // are fetched one 32-column chunk ahead, the first one while the MMAs of this tile still run.
+      // Lane l holds the bias of column col0 + l; element j of the chunk gets it by shuffle from lane j.
+      auto fetch_bias = [&](int col0) -> float {
+        const int col = col0 + lane;
+        return (p.bias && col < p.n) ? __ldg(p.bias + col) : 0.f;
+      };
+      auto fetch_y = [&](int col0) -> uint32_t {
+        return (EPI == EPI_BCE && row_ok && col0 < p.n_store) ? __ldg(p.ybits + (long long)row * p.ywords + (col0 >> 5)) : 0u;
+      };
+      float b_next = fetch_bias(nt * BN);
+      uint32_t y_next = fetch_y(nt * BN);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
       float row_loss = 0.f;
 #pragma unroll 1
       for (int cb = 0; cb < BN / 32; ++cb) {
@@ -292,55 +307,60 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (col0 >= p.n_store || row0 >= p.m || !has_k) break;      // warp-uniform
         uint32_t v[32];
         __syncwarp();
+        if (p.debug & 4) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0;
+        } else
         tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + cb * 32), v);
-        if (p.bias) {
-          bsm[lane] = (col0 + lane < p.n) ? __ldg(p.bias + col0 + lane) : 0.f;
-          __syncwarp();
-        }
+        const float b_cur = b_next;
+        const uint32_t ybw = y_next;
+        if (cb + 1 < BN / 32) { b_next = fetch_bias(col0 + 32); y_next = fetch_y(col0 + 32); }
         float out[32];
         if (EPI == EPI_BCE) {
-          const uint32_t ybw = row_ok ? p.ybits[(long long)row * p.ywords + (col0 >> 5)] : 0u;
+          const bool full = col0 + 32 <= p.n;           // warp-uniform: only the last column tile is ragged
 #pragma unroll
-          for (int j4 = 0; j4 < 32; j4 += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bsm + j4);
-            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const int j = j4 + jj;
-              const float z = __uint_as_float(v[j]) + bb[jj];
+          for (int j = 0; j < 32; ++j) {
+            {
+              const float z = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, b_cur, j);
               const float y = float((ybw >> j) & 1u);
-              // softplus(z) - z*y and sigmoid(z) from one exp: e = exp(-|z|)
-              const float e = __expf(-fabsf(z));
-              const float r = __frcp_rn(1.f + e);
-              const float l = fmaxf(z, 0.f) - z * y + __logf(1.f + e);
+              // softplus(z) - z*y and sigmoid(z) from one exp: e = exp(-|z|) (ex2, rcp, lg2: 3 MUFU ops)
+              const float e = exp2f_approx(-1.4426950408889634f * fabsf(z));
+              const float s1 = 1.f + e;
+              const float r = rcp_approx(s1);
+              const float l = fmaf(-z, y, fmaxf(z, 0.f)) + 0.6931471805599453f * lg2_approx(s1);
               float g = ((z >= 0.f ? r : e * r) - y) * p.inv_count;
-              const bool live = (col0 + j < p.n);
-              row_loss += live ? l : 0.f;
-              g = live ? g : 0.f;
+              if (!full) {
+                const bool live = (col0 + j < p.n);
+                row_loss += live ? l : 0.f;
+                g = live ? g : 0.f;
+              } else {
+                row_loss += l;
+              }
               out[j] = p.round_tf32 ? rn_tf32(g) : g;
             }
           }
         } else {
-          const float* mrow = (p.mask && row_ok) ? p.mask + (long long)row * p.ldmask + col0 : nullptr;
+          // branch-free inner loops: bias is 0 when absent, ReLU is a max with -inf when off
+          const float floor_v = p.relu ? 0.f : -INFINITY;
 #pragma unroll
-          for (int j4 = 0; j4 < 32; j4 += 4) {
-            float bb[4] = {0.f, 0.f, 0.f, 0.f};
-            if (p.bias) {
-              const float4 b4 = *reinterpret_cast<const float4*>(bsm + j4);
-              bb[0] = b4.x; bb[1] = b4.y; bb[2] = b4.z; bb[3] = b4.w;
-            }
+          for (int j = 0; j < 32; ++j)
+            out[j] = fmaxf(__uint_as_float(v[j]) + __shfl_sync(0xffffffffu, b_cur, j), floor_v);
+          if (p.mask) {           // ReLU backward: keep the gradient where the forward activation was positive
+            if (row_ok) {
+              const float* mrow = p.mask + (long long)row * p.ldmask + col0;
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const int j = j4 + jj;
-              float z = __uint_as_float(v[j]) + bb[jj];
-              if (p.relu) z = fmaxf(z, 0.f);
-              if (mrow && col0 + j < p.n) z = (__ldg(mrow + j) > 0.f) ? z : 0.f;
-              out[j] = p.round_tf32 ? rn_tf32(z) : z;
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.n) out[j] = (__ldg(mrow + j) > 0.f) ? out[j] : 0.f;
             }
+          }
+          if (p.round_tf32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) out[j] = rn_tf32(out[j]);
           }
         }
         // registers -> swizzled staging (row = lane, 16-byte chunk c at position c ^ (lane & 7)) -> TMA store
         uint8_t* sbuf = stage_buf + buf * 4096;
+        if (p.debug & 2) { if (out[lane] == 12345.678f) sbuf[0] = 1; continue; }
         if (lane == 0) tma_wait_group_read<1>();        // the store that last read this buffer has drained
         __syncwarp();
 #pragma unroll
@@ -349,7 +369,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               make_float4(out[4 * c], out[4 * c + 1], out[4 * c + 2], out[4 * c + 3]);
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && !(p.debug & 1)) {
           if (p.reduce_add) tma_reduce_add_2d(&map_c, sbuf, col0, row0);
           else              tma_store_2d(&map_c, sbuf, col0, row0);
           tma_commit_group();
@@ -473,6 +493,8 @@ static int launch_bn(const Problem& pr, Params p, cudaStream_t st) {
   if (rc != CC_OK) return rc;
   p.a_mn_major = pr.transa ? 1 : 0;
   p.b_mn_major = pr.transb ? 0 : 1;
+  static const int dbg = getenv("CC_TC_DEBUG") ? atoi(getenv("CC_TC_DEBUG")) : 0;
+  p.debug = dbg;
   p.m_tiles = ceil_div(pr.m, BM);
   p.n_tiles = ceil_div(p.n_store, BN);
   p.total_k_blocks = ceil_div(pr.k, bk);
