@@ -1,0 +1,46 @@
+"""Host-side data-parallel plumbing (one process per GPU, torch.distributed; NCCL on GPUs, gloo in
+the CPU tests).  SURVEY.md §8e: the path shards by cubes with one exchange step per phase --
+
+* graph build: every rank counts its own cube shard, ``all_reduce(SUM)`` of the int32 counts (exact);
+* train step : batch and regulariser rows split B/G and R/G per rank, each rank scales its loss
+  terms by the GLOBAL B*C and R, ``all_reduce(SUM)`` of the flat gradient buffer and of the 3 loss
+  scalars; weights and Adam state are replicated and stay bit-identical across ranks;
+* inference  : cubes are independent, no collective.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous [lo, hi) of ``n`` items for ``rank`` (sizes differ by at most one)."""
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def shard_batch_ids(batch_ids: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """The slice of a global batch this rank trains on (global batch must divide evenly so every
+    rank launches identical kernel shapes)."""
+    n = len(batch_ids)
+    if n % world:
+        raise ValueError(f"global batch {n} is not divisible by {world} ranks")
+    per = n // world
+    return batch_ids[rank * per:(rank + 1) * per]
+
+
+def env_rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def all_reduce_sum_(tensor, group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=group)
+    return tensor
+
+
+def loss_scales(global_batch: int, global_reg_rows: int, num_cards: int, reg: float):
+    """(1/(B*C), reg/R) with the GLOBAL sizes: summing the per-rank gradients then reproduces the
+    single-process gradient of  mean_{b,c} BCE + reg * mean_r KL  (reference train.py:83-88)."""
+    return 1.0 / (float(global_batch) * float(num_cards)), (reg / float(global_reg_rows)) if global_reg_rows else 0.0

@@ -1,0 +1,103 @@
+"""Drop-in for reference ``src/ml/train.py``.
+
+    python -m cubecobrarecommender_b200.ml.train epochs batch_size name reg noise [seed]
+
+Same positional arguments (reference train.py:28-38), same inputs (``data/maps/nameToId.json``,
+``data/cube/*.json``, ``output/full_adj_mtx.npy``), same M-hat construction (train.py:69-71), loss and
+optimiser (train.py:83-88).  The model is saved under ``ml_files/<name>/`` in this package's npz
+checkpoint format (TensorFlow SavedModel is not available).  Under ``torchrun`` the cubes
+of every batch and the regulariser rows are sharded over the ranks and gradients are all-reduced.
+"""
+from __future__ import annotations
+
+import os
+import random
+import sys
+import time
+
+import numpy as np
+import torch
+
+
+def reset_random_seeds(seed):
+    os.environ['PYTHONHASHSEED'] = str(seed)
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    random.seed(seed)
+
+
+def fit(model, generator, epochs, reg, *, group=None, log=print, steps_per_epoch=None, max_cube_size=None):
+    """``autoencoder.fit(generator, epochs=epochs)`` (reference train.py:99-102).  Returns the history
+    ``[{"loss", "output_1_loss", "output_2_loss"}]`` per epoch (means over the epoch's steps)."""
+    import torch.distributed as dist
+    from .engine import DAEEngine
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    gb = generator.batch_size
+    if gb % world:
+        raise ValueError(f"batch_size {gb} must be divisible by the number of ranks {world}")
+    lb = gb // world
+    eng = DAEEngine(model, generator.mhat_device(), batch=lb, reg_rows=lb, reg=reg,
+                    max_cube_size=max_cube_size or max(generator.csr.max_size, 1), global_batch=gb,
+                    global_reg_rows=gb, group=group)
+    history = []
+    nsteps = steps_per_epoch or len(generator)
+    for epoch in range(epochs):
+        log(f"Epoch {epoch + 1}/{epochs}")
+        t0 = time.time()
+        acc = torch.zeros(3, dtype=torch.float64, device=model.device)
+        for b in range(nsteps):
+            ids = generator.indices[b * gb:(b + 1) * gb][rank * lb:(rank + 1) * lb]
+            ids_t = torch.from_numpy(np.ascontiguousarray(ids, dtype=np.int32)).to(model.device)
+            eng.sample_batch(generator.indptr, generator.indices_dev, ids_t, generator.alias_prob, generator.alias_idx,
+                             generator.noise, generator.noise_std, seed=generator.seed + 7919 * rank)
+            acc += eng.train_step()
+        eng.check_overflow()
+        mean = (acc / max(nsteps, 1)).cpu().numpy()
+        history.append({"loss": float(mean[2]), "output_1_loss": float(mean[0]), "output_2_loss": float(mean[1])})
+        log(f"{nsteps}/{nsteps} - {time.time() - t0:.0f}s - loss: {mean[2]:.4f} - output_1_loss: {mean[0]:.4f} "
+            f"- output_2_loss: {mean[1]:.4f}")
+        generator.on_epoch_end()
+    return history
+
+
+def main(argv=None):
+    from ..non_ml import utils
+    from .generator import DataGenerator
+    from .model import CC_Recommender
+    args = sys.argv[1:] if argv is None else argv
+    epochs, batch_size, name = int(args[0]), int(args[1]), args[2]
+    reg, noise = float(args[3]), float(args[4])
+    seed = 0
+    if len(args) == 6:
+        seed = int(args[5])
+        reset_random_seeds(seed)
+    import torch.distributed as dist
+    if "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+    map_file = '././data/maps/nameToId.json'
+    folder = "././data/cube/"
+    print('Loading Cube Data . . .\n')
+    num_cards, name_lookup, card_to_int, int_to_card = utils.get_card_maps(map_file)
+    cubes = utils.build_cubes_csr(folder, num_cards, name_lookup, card_to_int)
+    print('Loading Adjacency Matrix . . .\n')
+    adj_mtx = np.load('././output/full_adj_mtx.npy')
+    print('Creating Graph for Regularization . . . \n')
+    y_mtx = adj_mtx.copy()
+    np.fill_diagonal(y_mtx, 1)
+    y_mtx = (y_mtx / y_mtx.sum(1)[:, None])                                   # train.py:69-71
+    print('Setting Up Data for Training . . .\n')
+    print('Setting Up Model . . . \n')
+    autoencoder = CC_Recommender(num_cards, device="cuda", seed=seed, precision=os.environ.get("CC_PRECISION", "tf32"))
+    generator = DataGenerator(y_mtx, cubes, batch_size=batch_size, noise=noise, seed=seed)
+    fit(autoencoder, generator, epochs, reg)
+    dest = f'././ml_files/{name}'
+    if not dist.is_initialized() or dist.get_rank() == 0:
+        autoencoder.save(dest)
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,135 @@
+"""Drop-in surface on the GPU: create_mtx files, simple_recs/simple_cuts signatures, ML recommendation
+(ids bit-exact vs the oracle ranking of the same scores), DataGenerator mirror, fit(), save/load."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from cubecobrarecommender_b200.ml import generator as GEN, inference as INF, model as M, train as T
+from cubecobrarecommender_b200.non_ml import create_mtx, utils
+from cubecobrarecommender_b200.scripts import cut_cards, recommend
+from cubecobrarecommender_b200.sparse import CubeCSR
+from cubecobrarecommender_b200.synth import csr_to_dense, synth_cubes_csr
+from oracle import dae as od, graph as og, noise as on
+
+
+def _write_dataset(root, k=60, c=90, seed=5):
+    ip, ix = synth_cubes_csr(k, c, size_lo=5, size_hi=30, seed=seed)
+    names = {f"card {i}": [f"id{i}a", f"id{i}b"] for i in range(c)}
+    os.makedirs(root / "data/maps"); os.makedirs(root / "data/cube")
+    json.dump(names, open(root / "data/maps/nameToId.json", "w"))
+    cubes = [{"_id": f"c{r}", "cards": [{"cardID": f"id{j}{'ab'[j % 2]}"} for j in ix[ip[r]:ip[r + 1]]]} for r in range(k)]
+    json.dump(cubes[:30], open(root / "data/cube/a.json", "w"))
+    json.dump(cubes[30:], open(root / "data/cube/b.json", "w"))
+    return c
+
+
+def test_create_mtx_cli_files(tmp_path, capsys):
+    c = _write_dataset(tmp_path)
+    adj = create_mtx.main(str(tmp_path))
+    out = capsys.readouterr().out
+    assert out.startswith("getting data\ncreating matrix\n1 / 90\n")
+    saved = np.load(tmp_path / "output/full_adj_mtx.npy")
+    assert saved.dtype == np.float64 and saved.shape == (c, c) and np.array_equal(saved, adj)
+    i2c = json.load(open(tmp_path / "output/int_to_card.json"))
+    assert i2c["0"] == "card 0" and len(i2c) == c
+    # same answer as the oracle on the dense cubes the reference loader builds
+    n, lookup, c2i, _ = utils.get_card_maps(str(tmp_path / "data/maps/nameToId.json"))
+    dense = utils.build_cubes(str(tmp_path / "data/cube"), utils.get_num_cubes(str(tmp_path / "data/cube")), n, lookup, c2i)
+    assert np.array_equal(saved, og.create_adjacency_matrix(dense))
+    assert np.array_equal(utils.create_adjacency_matrix(dense, verbose=False, force_diag=0.0),
+                          og.create_adjacency_matrix(dense, force_diag=0.0))
+
+
+def test_simple_recs_and_cuts_dropin(pairwise_golden):
+    g = pairwise_golden
+    c = int(g["num_cards"])
+    dense = csr_to_dense(g["indptr"], g["indices"], c)
+    adj = og.create_adjacency_matrix(dense)
+    i2c = {i: f"n{i}" for i in range(c)}
+    for n, row in enumerate(g["rec_cube_rows"]):
+        cube = dense[row]
+        full = recommend.simple_recs(cube, adj)
+        assert full == [int(i) for i in og.simple_recs(cube, adj)]              # whole ranking, ids exact
+        assert len(full) == int((cube == 0).sum())
+        assert recommend.simple_recs(cube, adj, i2c)[:5] == [i2c[i] for i in full[:5]]
+        a2 = adj.copy()
+        cuts = cut_cards.simple_cuts(cube, a2)
+        assert (np.diagonal(a2) == 0).all()                                      # mutates like the reference
+        assert cuts == [int(i) for i in og.simple_cuts(cube, adj.copy())]
+        s = g["rec_scores"][n]
+        assert np.array_equal(s[full[:50]], s[g["recs_top50"][n]])              # the reference's own answer
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_ml_recommend_batched(precision):
+    c, k = 400, 37
+    ip, ix = synth_cubes_csr(k, c, size_lo=0, size_hi=120, seed=2)
+    lists = [ix[ip[i]:ip[i + 1]] for i in range(k)]; lists[3] = np.zeros(0, np.int32)
+    csr = CubeCSR.from_lists(lists, c)
+    params = od.init_params(c, seed=4)
+    rng = np.random.default_rng(0)
+    for kk in params:      # larger weights -> a wide spread of probabilities, some saturated at exactly 1.0
+        params[kk] = (params[kk] * 2 + (rng.standard_normal(params[kk].shape) * 0.1 if kk.endswith("bias") else 0)).astype(np.float32)
+    model = M.CC_Recommender(c, device="cuda", precision=precision)
+    model.set_weights_dict(params)
+    rec = INF.MLRecommender(model, chunk=16)
+    probs = rec.probabilities(csr).cpu().numpy()
+    ref = od.recommend_np(params, csr.to_dense())
+    assert np.abs(probs - ref).max() < (1e-4 if precision == "fp32" else 2e-2)
+    ids, vals, cnt = rec.recommend(csr, 50)
+    dense = csr.to_dense()
+    for r in range(k):
+        expect = od.rank_additions(probs[r], dense[r], 50)          # oracle ranking of the SAME scores
+        assert cnt[r] == len(expect)
+        assert ids[r, :cnt[r]].tolist() == expect                   # ids bit-exact, ties included
+        assert np.array_equal(vals[r, :cnt[r]], probs[r][expect])
+    i2c = {i: f"card{i}" for i in range(c)}
+    out = rec.recommend_one([int(v) for v in lists[5]], 7, i2c)
+    assert list(out) == ["additions", "cuts"] and len(out["additions"]) == 7
+    assert set(out["cuts"]) == {i2c[int(v)] for v in lists[5]}
+    assert list(out["additions"]) == [i2c[i] for i in od.rank_additions(probs[5], dense[5], 7)]
+
+
+def test_web_get_ml_recommend_resident(tmp_path, monkeypatch):
+    from cubecobrarecommender_b200.web import ml_recommend_web as W
+    c = 120
+    model = M.CC_Recommender(c, device="cuda", seed=3)
+    model.save(str(tmp_path / "ml_files/recommender"))
+    json.dump({str(i): f"card {i}" for i in range(c)}, open(tmp_path / "idmap.json", "w"))
+    monkeypatch.setenv("CUBECOBRA_MODEL_DIR", str(tmp_path / "ml_files/recommender"))
+    monkeypatch.setenv("CUBECOBRA_ID_MAP", str(tmp_path / "idmap.json"))
+    monkeypatch.setitem(W._state, "rec", None)
+    names = ["Card 5", "CARD 17", "not a card", "card 99"]
+    out = W.get_ml_recommend("ignored", 10, card_names=names)
+    assert len(out["additions"]) == 10 and set(out["cuts"]) == {"card 5", "card 17", "card 99"}
+    assert not set(out["additions"]) & set(out["cuts"])
+    assert all(isinstance(v, float) and 0 <= v <= 1 for v in out["additions"].values())
+    loaded = M.load_model(str(tmp_path / "ml_files/recommender"))
+    a, b = model.get_weights_dict(), loaded.get_weights_dict()
+    assert all(np.array_equal(a[k], b[k]) for k in a)
+
+
+def test_datagenerator_mirror_and_fit():
+    c, k, b = 256, 96, 32
+    ip, ix = synth_cubes_csr(k, c, size_lo=10, size_hi=60, seed=8)
+    dense = csr_to_dense(ip, ix, c)
+    mh = og.m_hat(og.create_adjacency_matrix(dense))
+    np.random.seed(0)
+    gen = GEN.DataGenerator(mh, dense, batch_size=b, noise=0.2, seed=11)
+    assert len(gen) == 3 and gen.N_cubes == k and gen.N_cards == c
+    assert np.abs(gen.neg_sampler - og.neg_sampler(mh)).max() < 1e-15
+    (x, xr), (y, yr) = gen[1]
+    assert x.shape == (b, c) and x.dtype == np.float64 and xr.shape == (b, c) and yr.shape == (b, c)
+    assert (xr.sum(1) == 1).all() and np.array_equal(yr, mh[np.argmax(xr, 1)])
+    on.check_noise_invariants(dense[gen.indices[b:2 * b]], x, y)
+    model = M.CC_Recommender(c, device="cuda", seed=0, precision="tf32")
+    hist = T.fit(model, gen, epochs=6, reg=0.1, log=lambda *_: None)
+    assert len(hist) == 6 and hist[-1]["loss"] < hist[0]["loss"]                 # it trains
+    assert abs(hist[0]["loss"] - (hist[0]["output_1_loss"] + 0.1 * hist[0]["output_2_loss"])) < 1e-9
+    assert int(model.store.step.item()) == 18
