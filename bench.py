@@ -145,6 +145,93 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------ extras
+def measure_extras(dev, peaks, log):
+    """The other two sub-metrics BASELINE.json names, on one GPU: the co-occurrence graph build
+    (configs[0]: 20k cubes x 21k cards) and batched top-50 ML recommendation (configs[3])."""
+    import torch
+    from cubecobrarecommender_b200 import _lib, graph as G
+    from cubecobrarecommender_b200.ml import inference as INF, model as M
+    from cubecobrarecommender_b200.workload import make_cubes
+    from oracle import dae as od, graph as og
+    out = {}
+    # ---------------- graph build: K = 20 000 cubes, C = 21 000 cards ----------------
+    K, C = 20000, 21000
+    t0 = time.time()
+    csr = make_cubes(K, C, cfg=1)
+    log(f"extras: {K} synthetic cubes in {time.time() - t0:.1f}s")
+    indptr, indices = G.upload_csr(csr, dev)
+    lib = _lib.load()
+    bits = torch.empty((lib.cc_bits_words(K), lib.cc_bits_cpad(C)), dtype=torch.int32, device=dev)
+    counts = torch.empty((C, C), dtype=torch.int32, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    times = []
+    for it in range(3):
+        ev[0].record()
+        G.count_cooccurrence(indptr, indices, K, C, counts=counts, bits=bits)
+        ev[1].record()
+        gr = G.normalise(counts)
+        ev[2].record()
+        torch.cuda.synchronize()
+        times.append((ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])))
+        del gr
+    t_cnt, t_norm = min(t[0] for t in times), min(t[1] for t in times)
+    algo_bytes = K * C / 8 + 4.0 * C * C + 4.0 * C * C + 8.0 * C * C          # SURVEY.md 8d config 1a: 7.11 GB
+    pair_words = C * (C + 1) / 2 * (K / 32.0)                                  # AND+POPC word pairs (upper triangle)
+    t1 = time.time()
+    m_host = G.create_adjacency_matrix_host(csr)
+    t_host = time.time() - t1
+    del m_host
+    # CPU comparator: line-by-line restatement of utils.create_adjacency_matrix on a cube subsample;
+    # its cost is linear in nnz (SURVEY.md 3.1), so the full build is extrapolated by nnz
+    ksub = 120
+    sub = csr.rows(np.arange(ksub)).to_dense()
+    t2 = time.time()
+    og.create_adjacency_matrix_loop(sub)
+    t_cpu_sub = time.time() - t2
+    nnz_ratio = float(csr.indptr[-1]) / float(csr.indptr[ksub])
+    out["graph_build"] = {
+        "workload": f"create_mtx: K={K} cubes x C={C} cards, nnz={int(csr.indptr[-1])}",
+        "count_ms": t_cnt, "normalise_ms": t_norm, "device_seconds": (t_cnt + t_norm) / 1e3,
+        "e2e_host_seconds": t_host, "e2e_note": "CSR H2D + kernels + 3.5 GB float64 M D2H through cc_create_adjacency_matrix_host",
+        "roofline": {"kernel": "cooc_count_kernel", "bound": "hbm", "achieved": algo_bytes / ((t_cnt + t_norm) * 1e-3) / 1e9,
+                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": algo_bytes / ((t_cnt + t_norm) * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "traffic": None, "note": "compute-bound at this K (SURVEY.md 7): the popcount pipe, not HBM, is the limit",
+                     "popc_word_pairs_per_s": pair_words / (t_cnt * 1e-3)},
+        "cpu_baseline": {"seconds_extrapolated": t_cpu_sub * nnz_ratio, "cores": 1, "kind": "port",
+                         "sample": f"create_adjacency_matrix loop restatement on {ksub} cubes x {C} cards: {t_cpu_sub:.1f}s, scaled by nnz x{nnz_ratio:.0f}"},
+    }
+    del counts, bits
+    torch.cuda.empty_cache()
+    # ---------------- batched ML recommend: top-50 with in-cube masking ----------------
+    C2, K2 = 20884, 16384
+    csr2 = make_cubes(K2, C2, cfg=4)
+    model = M.CC_Recommender(C2, device=dev, seed=0, precision="tf32")
+    rec = INF.MLRecommender(model, chunk=2048)
+    rec.recommend(csr2.rows(np.arange(2048)), 50)
+    torch.cuda.synchronize()
+    t3 = time.time()
+    ids, vals, cnt = rec.recommend(csr2, 50)
+    t_rec = time.time() - t3
+    params = model.get_weights_dict()
+    nb = 32
+    dense = csr2.rows(np.arange(nb)).to_dense()
+    t4 = time.time()
+    tm = od.TorchDAE(params)
+    with torch.no_grad():
+        probs = torch.sigmoid(tm.tower(torch.from_numpy(dense.astype(np.float32)), "main")).numpy()
+    for r in range(nb):
+        od.rank_additions(probs[r], dense[r], 50)
+    t_cpu = time.time() - t4
+    out["ml_recommend"] = {
+        "workload": f"ml_recommend top-50, {K2} cubes, C={C2}, in-cube masking, host CSR in / host ids out",
+        "recs_per_s": K2 / t_rec, "seconds": t_rec,
+        "cpu_baseline": {"value": nb / t_cpu, "unit": "cubes/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{nb} cubes: torch-CPU forward + argsort walk (model load excluded)"},
+    }
+    return out
+
+
 # ------------------------------------------------------------------------------ native
 def run_native(args, rank, world, local_rank):
     import torch
@@ -155,6 +242,11 @@ def run_native(args, rank, world, local_rank):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl native needs a CUDA device (there is no CPU fallback)")
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner)
+    # is diverted to stderr, and the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -279,6 +371,14 @@ def run_native(args, rank, world, local_rank):
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                "sample": f"3 steps x {r['batch']} cubes at C={C}: generator {r['gen_seconds']:.2f}s + "
                          f"torch-CPU step {r['model_seconds']:.2f}s (host has {os.cpu_count()} cpus)"}
+    extras = None
+    if world == 1 and not args.no_extras:
+        del eng, model
+        torch.cuda.empty_cache()
+        try:
+            extras = measure_extras(dev, peaks, log)
+        except Exception as e:  # the headline line must survive a failure in the side measurements
+            extras = {"error": repr(e)}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -292,9 +392,10 @@ def run_native(args, rank, world, local_rank):
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 24,
                 "ms_per_step": 1e3 * float(e2e_s.item()) / args.steps},
-        "gpu_launches": launches, "clocks": clock_info,
+        "gpu_launches": launches, "clocks": clock_info, "extras": extras,
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
@@ -307,6 +408,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--precision", default=os.environ.get("CC_PRECISION", "tf32"), choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the graph-build and ml_recommend side measurements")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
