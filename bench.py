@@ -344,6 +344,8 @@ def run_native(args, rank, world, local_rank):
     # ---- roofline of the dominant kernel: the six 512<->C GEMM passes per step ----
     peaks = load_peaks()
     n_big, ms_big = ktimes.get("big_gemm", (0, 0.0))
+    n_dw1, ms_dw1 = ktimes.get("dw1_gemm", (0, 0.0))      # dW1 = x^T g1 is an 8th-of-a-kind 2*B*512*C pass
+    n_big, ms_big = n_big + n_dw1, ms_big + ms_dw1
     flops_per_launch = 2.0 * B * 512 * C
     # fp32 / tf32 kinds run at half the bf16 tensor rate; the step is long -> sustained figure
     tensor_peak = peaks["bf16_sustained"] * (1.0 if args.precision == "bf16" else 0.5)

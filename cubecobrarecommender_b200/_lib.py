@@ -43,7 +43,7 @@ SIGNATURES = {
     # (3) noise
     "cc_alias_build_host": (I, [P, I32, P, P]),
     "cc_noise_smem_bytes": (I64, [I32, I32]),
-    "cc_noise": (I, [P, P, P, I32, I32, P, P, F, F, U64, P, I32, I32, P, P, P, I64, P, P, P]),
+    "cc_noise": (I, [P, P, P, I32, I32, P, P, F, F, U64, P, I32, I32, P, P, P, I64, P, P, P, I64, P]),
     "cc_sample_reg_rows": (I, [P, P, I32, I32, U64, P, P, P]),
     "cc_cubes_to_bits": (I, [P, P, P, I32, I32, P, I64, P]),
     "cc_step_increment": (I, [P, P]),

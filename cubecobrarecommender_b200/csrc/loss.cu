@@ -137,6 +137,110 @@ softmax_kl_rows_kernel(const float* __restrict__ z, int64_t ldz, const float* __
   }
 }
 
+
+// Fast path (C*4 bytes <= ~100 KB, C % 4 == 0): two 512-thread CTAs per SM, the logits row cached in shared
+// memory, 128-bit loads/stores, log q taken from the logits (z - max - lse) instead of a log per element.
+//   HBM traffic per row: z read once, target row read once (+ one L2 re-read), dlogits written once.
+__device__ __forceinline__ float fast_exp(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f)); return r; }
+__device__ __forceinline__ float fast_log(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r * 0.6931471805599453f; }
+
+constexpr int KL_THREADS = 512;
+
+__device__ __forceinline__ float2 block_sum2(float a, float b, float2* red /* smem[16] */) {
+  a = warp_sum(a); b = warp_sum(b);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = make_float2(a, b);
+  __syncthreads();
+  float2 t = lane < (KL_THREADS >> 5) ? red[lane] : make_float2(0.f, 0.f);
+  t.x = warp_sum(t.x); t.y = warp_sum(t.y);
+  return t;      // every warp reduces the same 16 partials: identical result in all threads
+}
+__device__ __forceinline__ float block_max1(float a, float2* red) {
+  a = warp_max(a);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid].x = a;
+  __syncthreads();
+  float t = lane < (KL_THREADS >> 5) ? red[lane].x : -INFINITY;
+  return warp_max(t);
+}
+
+template <bool FAST>   // FAST: MUFU approximations (tensor-core modes); otherwise expf/logf (exact-fp32 mode)
+__global__ void __launch_bounds__(KL_THREADS, 2)
+softmax_kl_rows_fast_kernel(const float* __restrict__ z, int64_t ldz, const float* __restrict__ target, int64_t ldt,
+                            const int32_t* __restrict__ target_rows, int32_t num_cards, int32_t ncols_pad,
+                            float grad_scale, float* __restrict__ dz, int64_t lddz, double* __restrict__ row_loss,
+                            int round_tf32) {
+  auto EXPF = [](float x) { return FAST ? fast_exp(x) : expf(x); };
+  auto LOGF = [](float x) { return FAST ? fast_log(x) : logf(x); };
+  extern __shared__ __align__(16) float sz[];
+  __shared__ float2 red[KL_THREADS / 32];
+  const int r = blockIdx.x;
+  const float4* z4 = reinterpret_cast<const float4*>(z + int64_t(r) * ldz);
+  const float4* t4 = reinterpret_cast<const float4*>(target + int64_t(target_rows ? target_rows[r] : r) * ldt);
+  float4* s4 = reinterpret_cast<float4*>(sz);
+  const int n4 = num_cards >> 2;
+
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < n4; i += KL_THREADS) {
+    const float4 v = ld_nc_f4(z4 + i);
+    s4[i] = v;
+    mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  mx = block_max1(mx, red);
+  float se = 0.f;
+  for (int i = threadIdx.x; i < n4; i += KL_THREADS) {
+    const float4 v = s4[i];
+    se += (EXPF(v.x - mx) + EXPF(v.y - mx)) + (EXPF(v.z - mx) + EXPF(v.w - mx));
+  }
+  const float sumexp = block_sum2(se, 0.f, red).x;
+  const float inv_sum = 1.f / sumexp;
+  const float lse = mx + LOGF(sumexp);
+  const float log_eps = -16.11809565095832f;               // log(1e-7)
+  float loss = 0.f, sun = 0.f;
+  for (int i = threadIdx.x; i < n4; i += KL_THREADS) {
+    const float4 v = s4[i];
+    const float4 t = __ldg(t4 + i);
+    const float zz[4] = {v.x, v.y, v.z, v.w}, tt[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float q = EXPF(zz[k] - mx) * inv_sum;
+      const float tc = fminf(fmaxf(tt[k], KERAS_EPS), 1.f);
+      const bool un = (q >= KERAS_EPS) && (q <= 1.f);
+      const float logq = q >= KERAS_EPS ? fminf(zz[k] - lse, 0.f) : log_eps;   // log(clip(q, 1e-7, 1))
+      loss += tc * (LOGF(tc) - logq);
+      sun += un ? tc : 0.f;
+    }
+  }
+  const float2 ls = block_sum2(loss, sun, red);
+  if (threadIdx.x == 0) row_loss[r] = double(ls.x);
+  const float S = ls.y;
+  if (dz) {
+    float4* d4 = reinterpret_cast<float4*>(dz + int64_t(r) * lddz);
+    const int p4 = ncols_pad >> 2;
+    for (int i = threadIdx.x; i < p4; i += KL_THREADS) {
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < n4) {
+        const float4 v = s4[i];
+        const float4 t = __ldg(t4 + i);
+        const float zz[4] = {v.x, v.y, v.z, v.w}, tt[4] = {t.x, t.y, t.z, t.w};
+        float gg[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float q = EXPF(zz[k] - mx) * inv_sum;
+          const float tc = fminf(fmaxf(tt[k], KERAS_EPS), 1.f);
+          const bool un = (q >= KERAS_EPS) && (q <= 1.f);
+          gg[k] = (q * S - (un ? tc : 0.f)) * grad_scale;
+          if (round_tf32) gg[k] = rn_tf32(gg[k]);
+        }
+        g = make_float4(gg[0], gg[1], gg[2], gg[3]);
+      }
+      d4[i] = g;
+    }
+  }
+}
+
 // loss[0] = bce mean, loss[1] = kl mean, loss[2] = bce + reg*kl   (fixed summation order)
 __global__ void __launch_bounds__(1024)
 loss_finalize_kernel(const double* __restrict__ bce_rows, int nb, double bce_div, const double* __restrict__ kl_rows,
@@ -234,7 +338,21 @@ int cc_softmax_kl_fwd_bwd(const float* z, int64_t ldz, const float* target, int6
   if (rows == 0) return CC_OK;
   const size_t cache_bytes = size_t(num_cards) * 2 * sizeof(float);
   cudaStream_t st = as_stream(stream);
-  if (cache_bytes <= 200 * 1024) {
+  const bool aligned = (num_cards % 4 == 0) && (ldz % 4 == 0) && (ldt % 4 == 0) && (ncols_pad % 4 == 0) &&
+                       (!dz || lddz % 4 == 0) &&
+                       ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(dz)) % 16 == 0);
+  if (aligned && size_t(num_cards) * 4 <= 100 * 1024) {
+    const size_t smem = size_t(num_cards) * 4;
+    if (round_tf32) {
+      CC_CHECK_CUDA(cudaFuncSetAttribute(softmax_kl_rows_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      softmax_kl_rows_fast_kernel<true><<<rows, KL_THREADS, smem, st>>>(z, ldz, target, ldt, target_rows, num_cards, ncols_pad,
+                                                                       float(grad_scale), dz, lddz, row_loss, 1);
+    } else {
+      CC_CHECK_CUDA(cudaFuncSetAttribute(softmax_kl_rows_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      softmax_kl_rows_fast_kernel<false><<<rows, KL_THREADS, smem, st>>>(z, ldz, target, ldt, target_rows, num_cards, ncols_pad,
+                                                                        float(grad_scale), dz, lddz, row_loss, 0);
+    }
+  } else if (cache_bytes <= 200 * 1024) {
     CC_CHECK_CUDA(cudaFuncSetAttribute(softmax_kl_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)cache_bytes));
     softmax_kl_rows_kernel<true><<<rows, 1024, cache_bytes, st>>>(z, ldz, target, ldt, target_rows, num_cards,

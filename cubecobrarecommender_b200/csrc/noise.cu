@@ -72,7 +72,8 @@ noise_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ ind
              float noise_mean, float noise_std, uint64_t seed, const int64_t* __restrict__ step_ptr,
              int32_t max_size, int32_t x_stride,
              int32_t* __restrict__ x_idx, int32_t* __restrict__ x_len, uint32_t* __restrict__ y_bits,
-             int64_t y_words, int32_t* __restrict__ flips_out, int* __restrict__ overflow) {
+             int64_t y_words, int32_t* __restrict__ flips_out, int* __restrict__ overflow,
+             float* __restrict__ x_dense, int64_t ld_dense) {
   extern __shared__ uint32_t sm[];
   const int W = (num_cards + 31) >> 5;
   const int FW = (max_size + 31) >> 5;
@@ -167,6 +168,20 @@ noise_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ ind
     uint32_t* yo = y_bits + int64_t(b) * y_words;
     for (int w = threadIdx.x; w < y_words; w += blockDim.x) yo[w] = (w < W) ? y_mask[w] : 0u;
   }
+  if (x_dense) {
+    // dense 0/1 row of x (the MN-major operand of the tensor-core dW1 = x^T g1 GEMM): x = (cube & ~removed) | added.
+    // removed cards are cleared from cube_mask first (positions -> cards), then the row is expanded 4 columns a store
+    for (int p = threadIdx.x; p < s; p += blockDim.x)
+      if ((rem_flag[p >> 5] >> (p & 31)) & 1u) atomicAnd(&cube_mask[inc[p] >> 5], ~(1u << (inc[p] & 31)));
+    __syncthreads();
+    float4* xo4 = reinterpret_cast<float4*>(x_dense + int64_t(b) * ld_dense);
+    const int groups = int(ld_dense >> 2);
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+      const int w = g >> 3, sh = (g & 7) << 2;
+      const uint32_t bits = (w < W) ? ((cube_mask[w] | add_mask[w]) >> sh) & 0xfu : 0u;
+      xo4[g] = make_float4(float(bits & 1u), float((bits >> 1) & 1u), float((bits >> 2) & 1u), float((bits >> 3) & 1u));
+    }
+  }
 }
 
 // reg_indices = choice(C, n, p=neg_sampler) (generator.py:47-51), with replacement
@@ -236,8 +251,11 @@ int64_t cc_noise_smem_bytes(int32_t num_cards, int32_t max_size) {
 int cc_noise(const int64_t* indptr, const int32_t* indices, const int32_t* batch_ids, int32_t batch,
              int32_t num_cards, const float* alias_prob, const int32_t* alias_idx, float noise_mean, float noise_std,
              uint64_t seed, const int64_t* step_ptr, int32_t max_size, int32_t x_stride, int32_t* x_idx,
-             int32_t* x_len, uint32_t* y_bits, int64_t y_words, int32_t* flips_out, int* overflow_flag, void* stream) {
+             int32_t* x_len, uint32_t* y_bits, int64_t y_words, int32_t* flips_out, int* overflow_flag,
+             float* x_dense, int64_t ld_dense, void* stream) {
   CC_REQUIRE(indptr && indices && alias_prob && alias_idx && x_idx && x_len && overflow_flag, "cc_noise: null pointer");
+  CC_REQUIRE(!x_dense || (ld_dense % 4 == 0 && ld_dense >= num_cards && (reinterpret_cast<uintptr_t>(x_dense) & 15) == 0),
+             "cc_noise: x_dense needs ld_dense % 4 == 0, ld_dense >= num_cards and a 16-byte aligned base");
   CC_REQUIRE(batch >= 0 && num_cards > 0 && max_size > 0 && x_stride > 0, "cc_noise: bad sizes");
   CC_REQUIRE(!y_bits || y_words * 32 >= num_cards, "cc_noise: y_words too small");
   if (batch == 0) return CC_OK;
@@ -247,7 +265,7 @@ int cc_noise(const int64_t* indptr, const int32_t* indices, const int32_t* batch
   CC_CHECK_CUDA(cudaFuncSetAttribute(noise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   noise_kernel<<<batch, NOISE_THREADS, smem, as_stream(stream)>>>(
       indptr, indices, batch_ids, batch, num_cards, alias_prob, alias_idx, noise_mean, noise_std, seed, step_ptr,
-      max_size, x_stride, x_idx, x_len, y_bits, y_words, flips_out, overflow_flag);
+      max_size, x_stride, x_idx, x_len, y_bits, y_words, flips_out, overflow_flag, x_dense, ld_dense);
   CC_CHECK_LAUNCH();
   return CC_OK;
 }

@@ -91,7 +91,7 @@ class DataGenerator:
         ovf = torch.zeros(1, dtype=torch.int32, device=dev)
         call("cc_noise", ptr(self.indptr), ptr(self.indices_dev), ptr(ids), b, c, ptr(self.alias_prob),
              ptr(self.alias_idx), float(self.noise), float(self.noise_std), self.seed, ptr(self._step), max_size,
-             x_stride, ptr(x_idx), ptr(x_len), ptr(yb), yw, None, ptr(ovf), stream_ptr())
+             x_stride, ptr(x_idx), ptr(x_len), ptr(yb), yw, None, ptr(ovf), None, 0, stream_ptr())
         call("cc_step_increment", ptr(self._step), stream_ptr())
         if int(ovf.item()):
             raise RuntimeError("noise kernel overflow")

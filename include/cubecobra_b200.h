@@ -110,7 +110,8 @@ int64_t cc_noise_smem_bytes(int32_t num_cards, int32_t max_size);
 int cc_noise(const int64_t* indptr, const int32_t* indices, const int32_t* batch_ids, int32_t batch,
              int32_t num_cards, const float* alias_prob, const int32_t* alias_idx, float noise_mean, float noise_std,
              uint64_t seed, const int64_t* step_ptr, int32_t max_size, int32_t x_stride, int32_t* x_idx,
-             int32_t* x_len, uint32_t* y_bits, int64_t y_words, int32_t* flips_out, int* overflow_flag, void* stream);
+             int32_t* x_len, uint32_t* y_bits, int64_t y_words, int32_t* flips_out, int* overflow_flag,
+             float* x_dense /* nullable: dense 0/1 rows of x, [batch][ld_dense] */, int64_t ld_dense, void* stream);
 int cc_sample_reg_rows(const float* alias_prob, const int32_t* alias_idx, int32_t num_cards, int32_t n, uint64_t seed,
                        const int64_t* step_ptr, int32_t* rows, void* stream);
 int cc_cubes_to_bits(const int32_t* idx, const int64_t* row_start, const int32_t* row_len, int32_t batch,

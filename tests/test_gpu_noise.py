@@ -29,7 +29,7 @@ def _run_noise(csr, ns, steps, noise=0.2, std=0.1, seed=123, max_size=128):
     for _ in range(steps):
         E.call("cc_noise", E.ptr(indptr), E.ptr(indices), None, b, c, E.ptr(prob), E.ptr(alias), noise, std, seed,
                E.ptr(step), max_size, x_stride, E.ptr(x_idx), E.ptr(x_len), E.ptr(yb), yw, E.ptr(flips), E.ptr(ovf),
-               E.stream_ptr())
+               None, 0, E.stream_ptr())
         E.call("cc_step_increment", E.ptr(step), E.stream_ptr())
         xi, xl = x_idx.cpu().numpy(), x_len.cpu().numpy()
         x = np.zeros((b, c), dtype=np.int8)
