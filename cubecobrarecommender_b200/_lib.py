@@ -29,6 +29,9 @@ SIGNATURES = {
     "cc_bits_cpad": (I64, [I32]),
     "cc_bitpack_cubes": (I, [P, P, I64, I32, P, P, P]),
     "cc_cooc_count": (I, [P, I64, I32, P, I64, I, P]),
+    "cc_cooc_tc_chunk_cubes": (I64, [I64]),
+    "cc_cooc_tc_workspace_bytes": (I64, [I64, I32]),
+    "cc_cooc_count_tc": (I, [P, P, I64, I32, P, I64, P, I64, I, P, P]),
     "cc_row_normalise": (I, [P, I64, I32, P, I64, P, I64, P, I, D, P]),
     "cc_col_mass_workspace_bytes": (I64, [I32]),
     "cc_col_mass": (I, [P, I64, I32, P, P, P, P]),
@@ -55,6 +58,7 @@ SIGNATURES = {
     "cc_gemm_tc": (I, [I, I, I, I, I, I, P, I64, P, I64, P, I64, P, I, P, I64, I, I, I, I, P]),
     "cc_gemm_bce_tc": (I, [I, I, I, I, P, I64, P, I64, P, P, I64, D, P, I64, P, I, P]),
     "cc_gemm_bce_partial_count": (I64, [I, I]),
+    "cc_gemm_tc_set_pair_mode": (I, [I]),
     "cc_colsum_workspace_bytes": (I64, [I, I]),
     "cc_colsum_f32": (I, [P, I64, I, I, P, P, I, P]),
     "cc_relu_mask_f32": (I, [P, I64, P, I64, I, I, P]),

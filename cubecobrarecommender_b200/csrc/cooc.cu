@@ -134,6 +134,10 @@ cooc_count_kernel(const uint32_t* __restrict__ bits, int64_t kw_pad, int64_t cpa
 //   M[i,:]      float64  = cnt/cnt[i,i] if cnt[i,i] != 0 else cnt      (utils.py:85-89)
 //   rowsum[i]   float64  = sum_j y[i,j], y = M with diagonal forced to 1 (train.py:69-70)
 //   Mhat[i,:]   float32  = y[i,:]/rowsum[i]                              (train.py:71)
+// Streaming form: 16-byte loads of the counts row, 32-byte runs of float64 stores.  Only M needs the IEEE
+// division cnt/cnt[i,i] (bit-exact float64 output); M-hat is float32 (bar 1e-6 relative), so its two divisions
+// collapse into one multiply by 1/(cnt[i,i]*rowsum) computed once per row.
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 row_normalise_kernel(const int32_t* __restrict__ counts, int64_t ld, int32_t num_cards,
                      double* __restrict__ m64, int64_t ld_m, float* __restrict__ mhat, int64_t ld_mhat,
@@ -144,10 +148,28 @@ row_normalise_kernel(const int32_t* __restrict__ counts, int64_t ld, int32_t num
   const double dd = double(d);
   __shared__ double red[8];
   double s = 0.0;
-  for (int j = threadIdx.x; j < num_cards; j += blockDim.x) {
+  double* mrow = m64 ? m64 + int64_t(i) * ld_m : nullptr;
+  const int nvec = VEC ? (num_cards >> 2) : 0;
+  for (int q = threadIdx.x; q < nvec; q += blockDim.x) {
+    const int4 c4 = *reinterpret_cast<const int4*>(row + 4 * q);
+    const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
+    double v[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const double c = double(cc[t]);
+      v[t] = d != 0 ? c / dd : c;
+      s += (4 * q + t == i) ? 1.0 : v[t];
+      if (has_force_diag && 4 * q + t == i) v[t] = force_diag;
+    }
+    if (mrow) {
+      *reinterpret_cast<double2*>(mrow + 4 * q) = make_double2(v[0], v[1]);
+      *reinterpret_cast<double2*>(mrow + 4 * q + 2) = make_double2(v[2], v[3]);
+    }
+  }
+  for (int j = 4 * nvec + threadIdx.x; j < num_cards; j += blockDim.x) {
     const double c = double(row[j]);
-    double v = d != 0 ? c / dd : c;
-    if (m64) m64[int64_t(i) * ld_m + j] = (has_force_diag && j == i) ? force_diag : v;
+    const double v = d != 0 ? c / dd : c;
+    if (mrow) mrow[j] = (has_force_diag && j == i) ? force_diag : v;
     s += (j == i) ? 1.0 : v;
   }
   s = warp_sum(s);
@@ -162,11 +184,19 @@ row_normalise_kernel(const int32_t* __restrict__ counts, int64_t ld, int32_t num
   const double total = red[0];
   if (threadIdx.x == 0 && rowsum) rowsum[i] = total;
   if (mhat) {
-    for (int j = threadIdx.x; j < num_cards; j += blockDim.x) {
-      const double c = double(row[j]);
-      const double v = (j == i) ? 1.0 : (d != 0 ? c / dd : c);
-      mhat[int64_t(i) * ld_mhat + j] = float(v / total);
+    const double scale = d != 0 ? 1.0 / (dd * total) : 1.0 / total;     // y[i,j]/rowsum = cnt * scale off the diagonal
+    const float diag = float(1.0 / total);
+    float* hrow = mhat + int64_t(i) * ld_mhat;
+    for (int q = threadIdx.x; q < nvec; q += blockDim.x) {
+      const int4 c4 = *reinterpret_cast<const int4*>(row + 4 * q);
+      float4 o = make_float4(float(double(c4.x) * scale), float(double(c4.y) * scale), float(double(c4.z) * scale),
+                             float(double(c4.w) * scale));
+      const int t = i - 4 * q;
+      if (t == 0) o.x = diag; else if (t == 1) o.y = diag; else if (t == 2) o.z = diag; else if (t == 3) o.w = diag;
+      *reinterpret_cast<float4*>(hrow + 4 * q) = o;
     }
+    for (int j = 4 * nvec + threadIdx.x; j < num_cards; j += blockDim.x)
+      hrow[j] = (j == i) ? diag : float(double(row[j]) * scale);
   }
 }
 
@@ -264,8 +294,16 @@ int cc_row_normalise(const int32_t* counts, int64_t ld, int32_t num_cards, doubl
   CC_REQUIRE(counts && num_cards > 0 && ld >= num_cards, "cc_row_normalise: bad arguments");
   CC_REQUIRE(!m64 || ld_m >= num_cards, "cc_row_normalise: ld_m too small");
   CC_REQUIRE(!mhat || ld_mhat >= num_cards, "cc_row_normalise: ld_mhat too small");
-  row_normalise_kernel<<<num_cards, 256, 0, as_stream(stream)>>>(counts, ld, num_cards, m64, ld_m, mhat, ld_mhat,
-                                                                 rowsum, has_force_diag, force_diag);
+  // 16-byte vector path when every row of every buffer starts 16-byte aligned
+  const bool vec = ld % 4 == 0 && (reinterpret_cast<uintptr_t>(counts) & 15) == 0 &&
+                   (!m64 || (ld_m % 2 == 0 && (reinterpret_cast<uintptr_t>(m64) & 15) == 0)) &&
+                   (!mhat || (ld_mhat % 4 == 0 && (reinterpret_cast<uintptr_t>(mhat) & 15) == 0));
+  if (vec)
+    row_normalise_kernel<true><<<num_cards, 256, 0, as_stream(stream)>>>(counts, ld, num_cards, m64, ld_m, mhat, ld_mhat,
+                                                                        rowsum, has_force_diag, force_diag);
+  else
+    row_normalise_kernel<false><<<num_cards, 256, 0, as_stream(stream)>>>(counts, ld, num_cards, m64, ld_m, mhat,
+                                                                         ld_mhat, rowsum, has_force_diag, force_diag);
   CC_CHECK_LAUNCH();
   return CC_OK;
 }
@@ -300,20 +338,29 @@ int cc_create_adjacency_matrix_host(const int64_t* indptr_host, const int32_t* i
   const int64_t kw = cc_bits_words(num_cubes), cpad = cc_bits_cpad(num_cards);
   int64_t* d_indptr = nullptr; int32_t* d_indices = nullptr; uint32_t* d_bits = nullptr;
   int32_t* d_counts = nullptr; double* d_m = nullptr; int* d_bad = nullptr;
+  // tensor-core contraction when the counts rows meet TMA's 16-byte rule, bit-packed popcount tiles otherwise
+  const bool tensor = num_cards % 4 == 0;
+  const int64_t ws_bytes = tensor ? cc_cooc_tc_workspace_bytes(num_cubes, num_cards) : size_t(kw > 0 ? kw : 1) * cpad * 4;
   int rc = CC_OK;
   cudaStream_t st = nullptr;
 #define CC_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { rc = cuda_fail(_e, #expr, __FILE__, __LINE__); goto done; } } while (0)
   CC_TRY(cudaStreamCreate(&st));
   CC_TRY(cudaMalloc(&d_indptr, size_t(num_cubes + 1) * 8));
   CC_TRY(cudaMalloc(&d_indices, size_t(nnz > 0 ? nnz : 1) * 4));
-  CC_TRY(cudaMalloc(&d_bits, size_t(kw > 0 ? kw : 1) * cpad * 4));
+  CC_TRY(cudaMalloc(&d_bits, size_t(ws_bytes)));
   CC_TRY(cudaMalloc(&d_counts, size_t(num_cards) * num_cards * 4));
   CC_TRY(cudaMalloc(&d_m, size_t(num_cards) * num_cards * 8));
   CC_TRY(cudaMalloc(&d_bad, sizeof(int)));
   CC_TRY(cudaMemcpyAsync(d_indptr, indptr_host, size_t(num_cubes + 1) * 8, cudaMemcpyHostToDevice, st));
   CC_TRY(cudaMemcpyAsync(d_indices, indices_host, size_t(nnz) * 4, cudaMemcpyHostToDevice, st));
-  if ((rc = cc_bitpack_cubes(d_indptr, d_indices, num_cubes, num_cards, d_bits, d_bad, st)) != CC_OK) goto done;
-  if ((rc = cc_cooc_count(d_bits, num_cubes, num_cards, d_counts, num_cards, 0, st)) != CC_OK) goto done;
+  if (tensor) {
+    CC_TRY(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    if ((rc = cc_cooc_count_tc(d_indptr, d_indices, num_cubes, num_cards, d_bits, ws_bytes, d_counts, num_cards, 0, d_bad,
+                               st)) != CC_OK) goto done;
+  } else {
+    if ((rc = cc_bitpack_cubes(d_indptr, d_indices, num_cubes, num_cards, d_bits, d_bad, st)) != CC_OK) goto done;
+    if ((rc = cc_cooc_count(d_bits, num_cubes, num_cards, d_counts, num_cards, 0, st)) != CC_OK) goto done;
+  }
   if ((rc = cc_row_normalise(d_counts, num_cards, num_cards, d_m, num_cards, nullptr, 0, nullptr, has_force_diag,
                              force_diag, st)) != CC_OK) goto done;
   CC_TRY(cudaMemcpyAsync(m_host, d_m, size_t(num_cards) * num_cards * 8, cudaMemcpyDeviceToHost, st));

@@ -37,15 +37,21 @@ constexpr int STAGE_A_BYTES = BM * 128;                 // 128 rows x one 128-by
 constexpr int EPI_STAGE_BYTES = 4 * 2 * 4096;           // 4 warps x 2 buffers x (32 rows x 128 B)
 constexpr int BAR_BYTES = 256;
 
-template <int BN> struct Cfg {
-  static constexpr int STAGE_B_BYTES = BN * 128;
+// CTAS = 2: a CTA pair (cluster of two SMs of one TPC) works on a 256 x BN tile with
+// tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and only HALF of the B tile
+// (BN/2 rows), so the L2->SM operand traffic per flop drops by a third at BN = 256.
+template <int BN, int CTAS> struct Cfg {
+  static constexpr int STAGE_B_BYTES = (BN / CTAS) * 128;
   static constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int STAGES = STAGE_BYTES >= 49152 ? 4 : 6;
   static constexpr int TMEM_COLS = NUM_ACC * BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + BAR_BYTES + 1024 /*align slack*/;
 };
 
-enum Epilogue : int { EPI_STORE = 0, EPI_BCE = 1 };
+enum Epilogue : int { EPI_STORE = 0, EPI_BCE = 1, EPI_COUNT = 2 };
+// operand kinds: fp32 storage / kind::tf32, bf16 storage / kind::f16, uint8 storage / kind::i8 (int32 accumulators:
+// the co-occurrence contraction X^T X over 0/1 bytes is exact)
+enum Kind : int { KIND_TF32 = 0, KIND_BF16 = 1, KIND_U8 = 2 };
 
 struct Params {
   int m, n, k;
@@ -60,6 +66,10 @@ struct Params {
   float inv_count;
   double* loss_partial;                  // [tiles][4 warps]
   int a_mn_major, b_mn_major;
+  // EPI_COUNT: C = A A^T is symmetric -> only tiles with nt >= mt are computed (square 256 x 256 pair tiles) and every
+  // off-diagonal tile is also written transposed
+  int symmetric;
+  int* count_out; long long ldcount;
   int debug;                             // experiment switches (CC_TC_DEBUG), 0 in production
 };
 
@@ -109,21 +119,53 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+// ---- CTA-pair (cluster of 2) helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
 }
-template <bool BF16>
-__device__ __forceinline__ void tcgen05_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  if (BF16) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of a pair; completion bytes are credited to a barrier that may live in the
+// peer CTA (the leader's "full" barrier), hence the cluster-space barrier address and .cta_group::2
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+
+template <int CTAS>
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  if (CTAS == 2) {   // arrives on the barrier at this offset in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
   } else {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
   }
 }
+#define CC_TCGEN05_MMA(GROUP, KINDSTR)                                                                  \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                      \
+               "tcgen05.mma.cta_group::" GROUP ".kind::" KINDSTR " [%0], %1, %2, %3, p;\n\t}"            \
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory")
+template <int KIND, int CTAS>
+__device__ __forceinline__ void tcgen05_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (CTAS == 2) {
+    if (KIND == KIND_BF16) CC_TCGEN05_MMA("2", "f16");
+    else if (KIND == KIND_U8) CC_TCGEN05_MMA("2", "i8");
+    else CC_TCGEN05_MMA("2", "tf32");
+  } else {
+    if (KIND == KIND_BF16) CC_TCGEN05_MMA("1", "f16");
+    else if (KIND == KIND_U8) CC_TCGEN05_MMA("1", "i8");
+    else CC_TCGEN05_MMA("1", "tf32");
+  }
+}
+#undef CC_TCGEN05_MMA
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -153,16 +195,36 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
 }
 
 // ------------------------------------------------------------------------ kernel
-template <bool BF16, int EPI, int BN>
+// upper-triangle tile order of the symmetric count GEMM: row r of the n x n tile grid holds tiles (r, r..n-1)
+__device__ __forceinline__ int tri_row_start(int r, int n) { return r * n - (r * (r - 1)) / 2; }
+__device__ __forceinline__ void decode_tile(const Params& p, int tile, int& mt, int& nt, int& ks) {
+  if (p.symmetric) {
+    const int n = p.n_tiles;
+    const double nn = 2.0 * n + 1.0;
+    int r = int((nn - sqrt(nn * nn - 8.0 * double(tile))) * 0.5);
+    r = max(0, min(r, n - 1));
+    while (r > 0 && tri_row_start(r, n) > tile) --r;
+    while (r + 1 < n && tri_row_start(r + 1, n) <= tile) ++r;
+    mt = r; nt = r + (tile - tri_row_start(r, n)); ks = 0;
+  } else {
+    mt = tile % p.m_tiles;
+    nt = (tile / p.m_tiles) % p.n_tiles;
+    ks = tile / (p.m_tiles * p.n_tiles);
+  }
+}
+
+template <int KIND, int EPI, int BN, int CTAS>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const Params p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CTAS>;
+  constexpr bool BF16 = KIND == KIND_BF16;
+  constexpr int BN_LOAD = BN / CTAS;             // rows of the B tile this CTA stages
   constexpr int STAGES = C::STAGES;
   constexpr int STAGE_BYTES = C::STAGE_BYTES;
-  constexpr int ELEM = BF16 ? 2 : 4;
-  constexpr int BK = 128 / ELEM;                 // elements per 128-byte swizzle row (32 | 64)
-  constexpr int UMMA_K = 32 / ELEM;              // 8 | 16
+  constexpr int ELEM = KIND == KIND_U8 ? 1 : (BF16 ? 2 : 4);
+  constexpr int BK = 128 / ELEM;                 // elements per 128-byte swizzle row (32 | 64 | 128)
+  constexpr int UMMA_K = 32 / ELEM;              // 8 | 16 | 32
   constexpr int MMAS_PER_STAGE = BK / UMMA_K;    // 4
   constexpr int MN_BOX = BK;                     // MN-major boxes are [BK rows(k)] x [BK elems (128 B)]
   constexpr int MN_BOX_BYTES = BK * 128;
@@ -177,7 +239,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + NUM_ACC);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles * p.split_k;
+  // tiles of (BM*CTAS) x BN; the symmetric count GEMM only visits the upper triangle of its square tile grid
+  const int total_tiles = p.symmetric ? (p.n_tiles * (p.n_tiles + 1)) / 2 : p.m_tiles * p.n_tiles * p.split_k;
+  const int cta_rank = CTAS == 2 ? int(cluster_ctarank()) : 0;
+  const int first_tile = CTAS == 2 ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int tile_step = CTAS == 2 ? int(gridDim.x >> 1) : int(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -186,15 +252,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < NUM_ACC; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    for (int a = 0; a < NUM_ACC; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4 * CTAS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();      // the peer's barriers are initialised before anything signals them
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -202,30 +274,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile % p.m_tiles;
-        const int nt = (tile / p.m_tiles) % p.n_tiles;
-        const int ks = tile / (p.m_tiles * p.n_tiles);
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        int mt, nt, ks;
+        decode_tile(p, tile, mt, nt, ks);
         const int kb0 = ks * p.k_blocks;
         const int kb1 = min(kb0 + p.k_blocks, p.total_k_blocks);
+        const int a_row0 = (mt * CTAS + cta_rank) * BM;             // this CTA's 128 rows of the (pair) tile
+        const int b_row0 = nt * BN + cta_rank * BN_LOAD;            // and its share of the B tile
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + STAGE_A_BYTES;
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          if (p.a_mn_major) {
+          if (CTAS == 2) {
+            // both CTAs' boxes are credited to the LEADER's full barrier (the MMA issuer waits there)
+            const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+            if (p.a_mn_major) {
 #pragma unroll
-            for (int j = 0; j < BM / MN_BOX; ++j)
-              tma_load_2d(sa + j * MN_BOX_BYTES, &map_a, &full_bar[stage], mt * BM + j * MN_BOX, kb * BK);
-          } else {
-            tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, mt * BM);
-          }
-          if (p.b_mn_major) {
+              for (int j = 0; j < BM / MN_BOX; ++j)
+                tma_load_2d_pair(sa + j * MN_BOX_BYTES, &map_a, bar, a_row0 + j * MN_BOX, kb * BK);
+            } else {
+              tma_load_2d_pair(sa, &map_a, bar, kb * BK, a_row0);
+            }
+            if (p.b_mn_major) {
 #pragma unroll
-            for (int j = 0; j < BN / MN_BOX; ++j)
-              tma_load_2d(sb + j * MN_BOX_BYTES, &map_b, &full_bar[stage], nt * BN + j * MN_BOX, kb * BK);
+              for (int j = 0; j < BN_LOAD / MN_BOX; ++j)
+                tma_load_2d_pair(sb + j * MN_BOX_BYTES, &map_b, bar, b_row0 + j * MN_BOX, kb * BK);
+            } else {
+              tma_load_2d_pair(sb, &map_b, bar, kb * BK, b_row0);
+            }
           } else {
-            tma_load_2d(sb, &map_b, &full_bar[stage], kb * BK, nt * BN);
+            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+            if (p.a_mn_major) {
+#pragma unroll
+              for (int j = 0; j < BM / MN_BOX; ++j)
+                tma_load_2d(sa + j * MN_BOX_BYTES, &map_a, &full_bar[stage], a_row0 + j * MN_BOX, kb * BK);
+            } else {
+              tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, a_row0);
+            }
+            if (p.b_mn_major) {
+#pragma unroll
+              for (int j = 0; j < BN / MN_BOX; ++j)
+                tma_load_2d(sb + j * MN_BOX_BYTES, &map_b, &full_bar[stage], b_row0 + j * MN_BOX, kb * BK);
+            } else {
+              tma_load_2d(sb, &map_b, &full_bar[stage], kb * BK, b_row0);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -233,22 +326,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | ((BF16 ? 1u : 2u) << 7) | ((BF16 ? 1u : 2u) << 10) |
+    if (lane == 0 && cta_rank == 0) {       // in a pair only the leader CTA issues (cta_group::2 drives both SMs)
+      // instruction descriptor: D format (1 = f32, 2 = s32), A/B formats (tf32 = 2, bf16 = 1, u8 = 0), major-ness, N, M
+      constexpr uint32_t FMT = KIND == KIND_TF32 ? 2u : (KIND == KIND_BF16 ? 1u : 0u);
+      const uint32_t idesc = ((KIND == KIND_U8 ? 2u : 1u) << 4) | (FMT << 7) | (FMT << 10) |
                              (uint32_t(p.a_mn_major) << 15) | (uint32_t(p.b_mn_major) << 16) |
-                             (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+                             (uint32_t(BN >> 3) << 17) | (uint32_t((BM * CTAS) >> 4) << 24);
       // K-major: rows 128 B apart, 8-row groups 1024 B apart (SBO); K advance 32 B inside the swizzle row.
       // MN-major: 128-byte MN atoms LBO apart, k-row groups SBO apart; K advance UMMA_K rows.
       // 32-bit (tf32) MN-major operands only exist in the "128B swizzle, 32-byte atom" layout: atoms of 4 k-rows
       // (SBO = 512 B); every other case uses the plain 128B swizzle with 8-row atoms (SBO = 1024 B).
       const uint32_t a_lbo = p.a_mn_major ? MN_BOX_BYTES : 16, b_lbo = p.b_mn_major ? MN_BOX_BYTES : 16;
-      const uint32_t a_lt = (!BF16 && p.a_mn_major) ? 1u : 2u, b_lt = (!BF16 && p.b_mn_major) ? 1u : 2u;
+      const uint32_t a_lt = (KIND == KIND_TF32 && p.a_mn_major) ? 1u : 2u, b_lt = (KIND == KIND_TF32 && p.b_mn_major) ? 1u : 2u;
       const uint32_t a_sbo = a_lt == 1u ? 512u : 1024u, b_sbo = b_lt == 1u ? 512u : 1024u;
       const uint32_t a_kstep = p.a_mn_major ? UMMA_K * 128 : 32, b_kstep = p.b_mn_major ? UMMA_K * 128 : 32;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int ks = tile / (p.m_tiles * p.n_tiles);
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        int mt_, nt_, ks;
+        decode_tile(p, tile, mt_, nt_, ks);
         const int kb0 = ks * p.k_blocks;
         const int kb1 = min(kb0 + p.k_blocks, p.total_k_blocks);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -263,12 +359,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int k = 0; k < MMAS_PER_STAGE; ++k) {
             const uint64_t adesc = make_desc(sa + k * a_kstep, a_lbo, a_sbo, a_lt);
             const uint64_t bdesc = make_desc(sb + k * b_kstep, b_lbo, b_sbo, b_lt);
-            tcgen05_mma<BF16>(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            tcgen05_mma<KIND, CTAS>(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          tcgen05_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+          tcgen05_commit<CTAS>(&empty_bar[stage]);    // frees the smem slot (in both CTAs) when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit(&tmem_full[acc]);              // accumulator complete -> epilogue
+        tcgen05_commit<CTAS>(&tmem_full[acc]);        // accumulator complete -> epilogue (of both CTAs)
         if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -278,12 +374,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint8_t* stage_buf = epi_smem + q * 8192;             // two 4 KB buffers (32 rows x 128 B, 128B-swizzled)
     int buf = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mt = tile % p.m_tiles;
-      const int nt = (tile / p.m_tiles) % p.n_tiles;
-      const int ks = tile / (p.m_tiles * p.n_tiles);
+    const uint32_t leader_tmem_empty = CTAS == 2 ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : 0u;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+      int mt, nt, ks;
+      decode_tile(p, tile, mt, nt, ks);
       const bool has_k = ks * p.k_blocks < p.total_k_blocks;
-      const int row0 = mt * BM + q * 32;
+      const int row0 = (mt * CTAS + cta_rank) * BM + q * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.m;
       // operands of the epilogue that live in global memory (the bias slice, and for BCE this row's y bits)
@@ -316,7 +412,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t ybw = y_next;
         if (cb + 1 < BN / 32) { b_next = fetch_bias(col0 + 32); y_next = fetch_y(col0 + 32); }
         float out[32];
-        if (EPI == EPI_BCE) {
+        if (EPI == EPI_COUNT) {
+          // int32 accumulators pass through bit for bit; an off-diagonal tile is also written transposed
+          // (for a fixed column the 32 lanes hold 32 consecutive rows -> one 128-byte line per store)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) out[j] = __uint_as_float(v[j]);
+          if (p.symmetric && nt != mt && row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (col0 + j < p.n) {
+                int* dst = p.count_out + (long long)(col0 + j) * p.ldcount + row;
+                if (p.reduce_add) atomicAdd(dst, int(v[j]));
+                else *dst = int(v[j]);
+              }
+            }
+          }
+        } else if (EPI == EPI_BCE) {
           const bool full = col0 + 32 <= p.n;           // warp-uniform: only the last column tile is ragged
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -380,21 +491,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // one float64 partial per (tile, warp): fixed summation order downstream
         const float s = row_ok ? row_loss : 0.f;
         const double d = warp_sum(double(s));
-        if (lane == 0) p.loss_partial[(long long)tile * 4 + q] = d;
+        if (lane == 0) p.loss_partial[((long long)tile * CTAS + cta_rank) * 4 + q] = d;
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (CTAS == 2) mbar_arrive_cluster(leader_tmem_empty + acc * 8);   // the leader's issuer waits for both CTAs
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();      // neither CTA may retire while the other can still signal its barriers
+  else __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+    if (CTAS == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
   }
 }
 
@@ -432,7 +550,8 @@ static EncodeTiledFn encode_fn() {
 
 // 2-D row-major matrix [rows][cols] (cols contiguous, leading dimension ld elements);
 // box = box_rows x (128 bytes of columns), 128B swizzle (32-byte atoms for 4-byte MN-major operands).
-static int make_map(CUtensorMap* map, const void* base, int elem, bool bf16, long long rows, long long cols,
+enum MapType : int { MAP_F32 = 0, MAP_BF16 = 1, MAP_U8 = 2, MAP_S32 = 3 };
+static int make_map(CUtensorMap* map, const void* base, int elem, int mtype, long long rows, long long cols,
                     long long ld, int box_rows, bool atom32) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return CC_ERR_CUDA; }
@@ -440,7 +559,10 @@ static int make_map(CUtensorMap* map, const void* base, int elem, bool bf16, lon
   cuuint64_t strides[1] = {cuuint64_t(ld) * elem};
   cuuint32_t box[2] = {cuuint32_t(128 / elem), cuuint32_t(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+  const CUtensorMapDataType dt = mtype == MAP_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                 : mtype == MAP_U8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                 : mtype == MAP_S32 ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUresult r = fn(map, dt, 2,
                         const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -456,75 +578,138 @@ struct Problem {
   const void* a; long long lda;
   const void* b; long long ldb;
   float* c; long long ldc;
-  bool bf16;
+  int kind;
 };
 
-// waves-based efficiency of (BN, split) on `sms` persistent CTAs
-static double plan_eff(int m, int n, int kblocks, int bn, int split, int sms) {
-  const long long tiles = (long long)ceil_div(m, BM) * ceil_div(n, bn) * split;
+// waves-based efficiency of (BN, split, CTA pairing) on `sms` SMs: with ctas = 2 the scheduling
+// unit is a 256 x bn tile on one of sms/2 CTA pairs
+static double plan_eff(int m, int n, int kblocks, int bn, int split, int sms, int ctas) {
+  const int units = sms / ctas;
+  const long long tiles = (long long)ceil_div(m, BM * ctas) * ceil_div(n, bn) * split;
   const int kb = ceil_div(kblocks, split);
-  const long long waves = ceil_div<long long>(tiles, (long long)sms);
-  // a tile costs kb*bn (+ a fixed prologue/epilogue worth ~6 k-blocks)
-  const double busy = double(ceil_div(m, BM)) * ceil_div(n, bn) * kblocks * bn;
-  const double span = double(waves) * sms * (kb + 6) * bn;
+  const long long waves = ceil_div<long long>(tiles, (long long)units);
+  // a tile costs kb*bn (+ a fixed prologue/epilogue worth ~6 k-blocks); rows beyond m are wasted work
+  const double busy = double(m) / (BM * ctas) * ceil_div(n, bn) * kblocks * bn;
+  const double span = double(waves) * units * (kb + 6) * bn;
   double eff = busy / span;
-  if (bn == 128) eff *= 0.85;       // 128-wide tiles are L2-bandwidth limited with 4-byte operands
+  // L2->SM operand bytes per flop: 128x128 tiles are bandwidth-limited with 4-byte operands, 128x256 less so,
+  // a 256x256 pair tile moves a third less than that
+  if (ctas == 1) eff *= (bn == 128 ? 0.68 : 0.80);
   if (split > 1) eff *= 0.97;       // reduce traffic + zero fill
   return eff;
 }
 
-template <bool BF16, int EPI, int BN>
+// -1 = planner decides, 0 = never pair, 1 = always pair (cc_gemm_tc_set_pair_mode; experiments and tests)
+static int g_pair_mode = -1;
+
+static int max_pair_clusters(const void* kern, int smem_bytes) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(sm_count() / 2 * 2));
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = size_t(smem_bytes);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+template <int KIND, int EPI, int BN, int CTAS>
 static int launch_bn(const Problem& pr, Params p, cudaStream_t st) {
-  using C = Cfg<BN>;
-  const int elem = BF16 ? 2 : 4;
+  using C = Cfg<BN, CTAS>;
+  constexpr bool BF16 = KIND == KIND_BF16;
+  constexpr bool TF32 = KIND == KIND_TF32;
+  const int elem = KIND == KIND_U8 ? 1 : (BF16 ? 2 : 4);
+  const int mt = KIND == KIND_U8 ? MAP_U8 : (BF16 ? MAP_BF16 : MAP_F32);
   const int bk = 128 / elem;
   CUtensorMap map_a, map_b, map_c;
   int rc;
   // transa=0: A is [M][K] (K-major)  -> box 128 rows x 128 B;  transa=1: A is [K][M] (MN-major) -> box bk rows x 128 B
-  if (pr.transa) rc = make_map(&map_a, pr.a, elem, BF16, pr.k, pr.m, pr.lda, bk, !BF16);
-  else           rc = make_map(&map_a, pr.a, elem, BF16, pr.m, pr.k, pr.lda, BM, false);
+  if (pr.transa) rc = make_map(&map_a, pr.a, elem, mt, pr.k, pr.m, pr.lda, bk, TF32);
+  else           rc = make_map(&map_a, pr.a, elem, mt, pr.m, pr.k, pr.lda, BM, false);
   if (rc != CC_OK) return rc;
-  // transb=1: B is [N][K] (K-major);  transb=0: B is [K][N] (MN-major)
-  if (pr.transb) rc = make_map(&map_b, pr.b, elem, BF16, pr.n, pr.k, pr.ldb, BN, false);
-  else           rc = make_map(&map_b, pr.b, elem, BF16, pr.k, pr.n, pr.ldb, bk, !BF16);
+  // transb=1: B is [N][K] (K-major);  transb=0: B is [K][N] (MN-major); a CTA of a pair loads BN/2 rows
+  if (pr.transb) rc = make_map(&map_b, pr.b, elem, mt, pr.n, pr.k, pr.ldb, BN / CTAS, false);
+  else           rc = make_map(&map_b, pr.b, elem, mt, pr.k, pr.n, pr.ldb, bk, TF32);
   if (rc != CC_OK) return rc;
-  // C: fp32 [M][n_store] boxes of 32 rows x 32 columns (TMA clips rows >= M and columns >= n_store)
-  rc = make_map(&map_c, pr.c, 4, false, pr.m, p.n_store, pr.ldc, 32, false);
+  // C: fp32 (int32 counts) [M][n_store] boxes of 32 rows x 32 columns (TMA clips rows >= M and columns >= n_store)
+  rc = make_map(&map_c, pr.c, 4, EPI == EPI_COUNT ? MAP_S32 : MAP_F32, pr.m, p.n_store, pr.ldc, 32, false);
   if (rc != CC_OK) return rc;
   p.a_mn_major = pr.transa ? 1 : 0;
   p.b_mn_major = pr.transb ? 0 : 1;
   static const int dbg = getenv("CC_TC_DEBUG") ? atoi(getenv("CC_TC_DEBUG")) : 0;
   p.debug = dbg;
-  p.m_tiles = ceil_div(pr.m, BM);
+  p.m_tiles = ceil_div(pr.m, BM * CTAS);
   p.n_tiles = ceil_div(p.n_store, BN);
   p.total_k_blocks = ceil_div(pr.k, bk);
   if (p.split_k < 1) p.split_k = 1;
   p.k_blocks = ceil_div(p.total_k_blocks, p.split_k);
   p.split_k = ceil_div(p.total_k_blocks, p.k_blocks);
-  const int tiles = p.m_tiles * p.n_tiles * p.split_k;
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  auto kern = gemm_tc_kernel<BF16, EPI, BN>;
+  const int tiles = p.symmetric ? p.n_tiles * (p.n_tiles + 1) / 2 : p.m_tiles * p.n_tiles * p.split_k;
+  auto kern = gemm_tc_kernel<KIND, EPI, BN, CTAS>;
   static bool attr_done = false;
+  static int max_clusters = 0;
   if (!attr_done) {
     CC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    if (CTAS == 2) {
+      max_clusters = max_pair_clusters(reinterpret_cast<const void*>(kern), C::SMEM_BYTES);
+      if (max_clusters <= 0) { set_error("cc_gemm_tc: no CTA-pair cluster can be resident (occupancy query)"); return CC_ERR_CUDA; }
+      if (max_clusters > sm_count() / 2) max_clusters = sm_count() / 2;
+    }
     attr_done = true;
   }
-  kern<<<grid, THREADS, C::SMEM_BYTES, st>>>(map_a, map_b, map_c, p);
+  if (CTAS == 2) {
+    const int clusters = tiles < max_clusters ? tiles : max_clusters;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(2 * clusters));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_c, p));
+  } else {
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    kern<<<grid, THREADS, C::SMEM_BYTES, st>>>(map_a, map_b, map_c, p);
+  }
   CC_CHECK_LAUNCH();
   return CC_OK;
 }
 
-template <bool BF16, int EPI>
-static int launch(const Problem& pr, Params p, int bn, cudaStream_t st) {
-  const int elem = BF16 ? 2 : 4;
+template <int KIND, int EPI>
+static int launch(const Problem& pr, Params p, int bn, int ctas, cudaStream_t st) {
+  const int elem = KIND == KIND_U8 ? 1 : (KIND == KIND_BF16 ? 2 : 4);
   CC_REQUIRE((reinterpret_cast<uintptr_t>(pr.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(pr.b) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(pr.c) & 15) == 0,
              "cc_gemm_tc: base pointers must be 16-byte aligned");
   CC_REQUIRE((pr.lda * elem) % 16 == 0 && (pr.ldb * elem) % 16 == 0 && (pr.ldc * 4) % 16 == 0,
              "cc_gemm_tc: leading dimensions must be multiples of 16 bytes (lda=%lld ldb=%lld ldc=%lld)", pr.lda,
              pr.ldb, pr.ldc);
-  if (bn == 256) return launch_bn<BF16, EPI, 256>(pr, p, st);
-  return launch_bn<BF16, EPI, 128>(pr, p, st);
+  if (ctas == 2) return launch_bn<KIND, EPI, 256, 2>(pr, p, st);
+  if (EPI == EPI_COUNT) { set_error("count GEMM runs on CTA pairs only"); return CC_ERR_ARGUMENT; }
+  if (bn == 256) return launch_bn<KIND, EPI == EPI_COUNT ? EPI_STORE : EPI, 256, 1>(pr, p, st);
+  return launch_bn<KIND, EPI == EPI_COUNT ? EPI_STORE : EPI, 128, 1>(pr, p, st);
+}
+
+// ------------------------------------------------------------------ co-occurrence counts on the tensor cores
+// Bytes X^T[c][k - k0] = 1 for every card c of cube k of the chunk [k0, k0 + chunk): one warp per cube.
+__global__ void expand_cubes_u8_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                       long long k0, int chunk, int num_cards, uint8_t* __restrict__ xt, long long ldx,
+                                       int32_t* __restrict__ bad) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int w = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  if (w >= chunk) return;
+  const int lane = threadIdx.x & 31;
+  const long long lo = indptr[k0 + w], hi = indptr[k0 + w + 1];
+  for (long long i = lo + lane; i < hi; i += 32) {
+    const int c = indices[i];
+    if (c < 0 || c >= num_cards) { if (bad) atomicOr(bad, 1); continue; }
+    xt[(long long)c * ldx + w] = 1;
+  }
 }
 
 }  // namespace tc
@@ -547,17 +732,21 @@ int cc_gemm_tc(int precision, int transa, int transb, int m, int n, int k, const
   cudaStream_t st = as_stream(stream);
   const int kblocks = ceil_div(k, precision == 2 ? 64 : 32);
   const int sms = sm_count();
-  int bn = tile_n, split = split_k;
-  if (split <= 0 || bn == 0) {
+  // candidates: (tile width, CTA pairing, K split); pairs only come as 256 x 256 tiles
+  int bn = tile_n, split = split_k, ctas = 1;
+  {
     double best = -1.0;
-    const int bns[2] = {256, 128};
-    for (int bi = 0; bi < 2; ++bi) {
+    const int bns[3] = {256, 256, 128};
+    const int cts[3] = {2, 1, 1};
+    for (int bi = 0; bi < 3; ++bi) {
       if (tile_n && bns[bi] != tile_n) continue;
       if (!tile_n && bns[bi] == 256 && n <= 128) continue;
+      if (cts[bi] == 2 && tc::g_pair_mode == 0) continue;
+      if (cts[bi] == 1 && tc::g_pair_mode == 1 && (tile_n == 0 || tile_n == 256) && n > 128) continue;
       const int smax = split_k > 0 ? split_k : (kblocks >= 16 ? (kblocks / 8 < 64 ? kblocks / 8 : 64) : 1);
       for (int s = (split_k > 0 ? split_k : 1); s <= smax; ++s) {
-        const double e = tc::plan_eff(m, n, kblocks, bns[bi], s, sms);
-        if (e > best + 1e-9) { best = e; bn = bns[bi]; split = s; }
+        const double e = tc::plan_eff(m, n, kblocks, bns[bi], s, sms, cts[bi]);
+        if (e > best + 1e-9) { best = e; bn = bns[bi]; split = s; ctas = cts[bi]; }
       }
     }
   }
@@ -572,8 +761,9 @@ int cc_gemm_tc(int precision, int transa, int transb, int m, int n, int k, const
   p.reduce_add = (accumulate || split > 1) ? 1 : 0;
   if (split > 1 && !accumulate)
     CC_CHECK_CUDA(cudaMemset2DAsync(c, size_t(ldc) * 4, 0, size_t(n) * 4, m, st));
-  tc::Problem pr{transa, transb, m, n, k, a, lda, b, ldb, c, ldc, precision == 2};
-  int rc = precision == 2 ? tc::launch<true, tc::EPI_STORE>(pr, p, bn, st) : tc::launch<false, tc::EPI_STORE>(pr, p, bn, st);
+  tc::Problem pr{transa, transb, m, n, k, a, lda, b, ldb, c, ldc, precision == 2 ? tc::KIND_BF16 : tc::KIND_TF32};
+  int rc = precision == 2 ? tc::launch<tc::KIND_BF16, tc::EPI_STORE>(pr, p, bn, ctas, st)
+                          : tc::launch<tc::KIND_TF32, tc::EPI_STORE>(pr, p, bn, ctas, st);
   if (rc != CC_OK) return rc;
   if (two_pass) {
     const long long total = (long long)m * n;
@@ -599,11 +789,69 @@ int cc_gemm_bce_tc(int precision, int m, int n, int k, const void* a, int64_t ld
   p.m = m; p.n = n; p.k = k; p.n_store = int(lddz);
   p.bias = bias; p.split_k = 1; p.round_tf32 = round_tf32;
   p.ybits = ybits; p.ywords = ywords; p.inv_count = float(1.0 / count); p.loss_partial = loss_partial;
-  tc::Problem pr{0, 0, m, n, k, a, lda, w, ldw, dz, lddz, precision == 2};
-  if (precision == 2) return tc::launch<true, tc::EPI_BCE>(pr, p, 256, as_stream(stream));
-  return tc::launch<false, tc::EPI_BCE>(pr, p, 256, as_stream(stream));
+  tc::Problem pr{0, 0, m, n, k, a, lda, w, ldw, dz, lddz, precision == 2 ? tc::KIND_BF16 : tc::KIND_TF32};
+  const int ctas = tc::g_pair_mode == 0 ? 1 : 2;
+  if (precision == 2) return tc::launch<tc::KIND_BF16, tc::EPI_BCE>(pr, p, 256, ctas, as_stream(stream));
+  return tc::launch<tc::KIND_TF32, tc::EPI_BCE>(pr, p, 256, ctas, as_stream(stream));
 }
 
-int64_t cc_gemm_bce_partial_count(int m, int lddz) { return int64_t(ceil_div(m, tc::BM)) * ceil_div(lddz, 256) * 4; }
+// one float64 per (128-row block, 256-column tile, epilogue warp); sized for the CTA-pair tiling (256-row
+// tiles, both CTAs) -- entries a launch does not cover stay untouched (the caller zero-initialises once)
+int64_t cc_gemm_bce_partial_count(int m, int lddz) { return int64_t(ceil_div(m, 2 * tc::BM)) * 2 * ceil_div(lddz, 256) * 4; }
+
+// Co-occurrence counts cnt = X^T X on the tensor cores (reference src/non_ml/utils.py:82-84): the cubes of a chunk
+// are expanded to a K-major byte matrix X^T [C][chunk] and contracted with tcgen05.mma kind::i8 (0/1 bytes, int32
+// accumulators -> exact), upper-triangle tiles only, each off-diagonal tile mirrored by the epilogue.
+static const int64_t kCountChunk = 32768;      // cubes per pass (the byte matrix is C x chunk)
+
+int64_t cc_cooc_tc_chunk_cubes(int64_t num_cubes) {
+  const int64_t k = num_cubes < kCountChunk ? num_cubes : kCountChunk;
+  return (k + 127) / 128 * 128;
+}
+int64_t cc_cooc_tc_workspace_bytes(int64_t num_cubes, int32_t num_cards) {
+  return cc_cooc_tc_chunk_cubes(num_cubes) * int64_t(num_cards) + 1024;
+}
+
+int cc_cooc_count_tc(const int64_t* indptr, const int32_t* indices, int64_t num_cubes, int32_t num_cards,
+                     void* workspace, int64_t workspace_bytes, int32_t* counts, int64_t ldc, int accumulate,
+                     int32_t* bad, void* stream) {
+  CC_REQUIRE(indptr && indices && workspace && counts, "cc_cooc_count_tc: null pointer");
+  CC_REQUIRE(num_cubes >= 0 && num_cards > 0 && ldc >= num_cards, "cc_cooc_count_tc: bad sizes");
+  CC_REQUIRE(ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(counts) & 15) == 0,
+             "cc_cooc_count_tc: counts needs a 16-byte aligned base and ldc %% 4 == 0 (ldc=%lld)", (long long)ldc);
+  CC_REQUIRE(workspace_bytes >= cc_cooc_tc_workspace_bytes(num_cubes, num_cards), "cc_cooc_count_tc: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  if (num_cubes == 0) {
+    if (!accumulate) CC_CHECK_CUDA(cudaMemset2DAsync(counts, size_t(ldc) * 4, 0, size_t(num_cards) * 4, num_cards, st));
+    return CC_OK;
+  }
+  bool add = accumulate != 0;           // the first pass of a fresh build stores (every element is covered), later ones add
+  uint8_t* xt = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+  const int64_t ldx = cc_cooc_tc_chunk_cubes(num_cubes);
+  for (int64_t k0 = 0; k0 < num_cubes; k0 += kCountChunk) {
+    const int chunk = int(num_cubes - k0 < kCountChunk ? num_cubes - k0 : kCountChunk);
+    const int kpad = (chunk + 127) / 128 * 128;
+    CC_CHECK_CUDA(cudaMemset2DAsync(xt, size_t(ldx), 0, size_t(kpad), num_cards, st));
+    const int wpb = 8;
+    tc::expand_cubes_u8_kernel<<<ceil_div(chunk, wpb), wpb * 32, 0, st>>>(indptr, indices, k0, chunk, num_cards, xt, ldx, bad);
+    CC_CHECK_LAUNCH();
+    tc::Params p{};
+    p.m = num_cards; p.n = num_cards; p.k = kpad; p.n_store = num_cards;
+    p.split_k = 1; p.symmetric = 1;
+    p.reduce_add = add ? 1 : 0;
+    add = true;
+    p.count_out = counts; p.ldcount = ldc;
+    tc::Problem pr{0, 1, num_cards, num_cards, kpad, xt, ldx, xt, ldx, reinterpret_cast<float*>(counts), ldc, tc::KIND_U8};
+    const int rc = tc::launch<tc::KIND_U8, tc::EPI_COUNT>(pr, p, 256, 2, st);
+    if (rc != CC_OK) return rc;
+  }
+  return CC_OK;
+}
+
+int cc_gemm_tc_set_pair_mode(int mode) {
+  CC_REQUIRE(mode >= -1 && mode <= 1, "cc_gemm_tc_set_pair_mode: mode must be -1 (auto), 0 (off) or 1 (on)");
+  tc::g_pair_mode = mode;
+  return CC_OK;
+}
 
 }  // extern "C"

@@ -44,3 +44,37 @@ def loss_scales(global_batch: int, global_reg_rows: int, num_cards: int, reg: fl
     """(1/(B*C), reg/R) with the GLOBAL sizes: summing the per-rank gradients then reproduces the
     single-process gradient of  mean_{b,c} BCE + reg * mean_r KL  (reference train.py:83-88)."""
     return 1.0 / (float(global_batch) * float(num_cards)), (reg / float(global_reg_rows)) if global_reg_rows else 0.0
+
+
+class GradBuckets:
+    """Contiguous slices of the flat gradient buffer in the order backward finishes them:
+    "main" decoder, "reg" decoder, then the shared "enc"oder (whose 512 x C first-layer gradient is
+    the last thing backward produces).  Each bucket is all_reduced asynchronously as soon as it is
+    complete, so the exchange of the two decoders (2/3 of all parameters) overlaps the rest of backward,
+    and Adam runs bucket by bucket as the reductions land."""
+
+    ORDER = ("main", "reg", "enc")
+
+    def __init__(self, layout: dict, total: int):
+        def span(prefix):
+            offs = [(off, off + int(np.prod(shape))) for k, (off, shape) in layout.items() if k.startswith(prefix)]
+            return min(o for o, _ in offs), max(e for _, e in offs)
+        enc, main, reg = span("encoder_"), span("main_"), span("reg_")
+        # the flat buffer is laid out encoder | main | reg with 4-float padding between tensors: extend every
+        # bucket to the start of the next one so the three slices tile [0, total) exactly
+        assert enc[0] == 0 and enc[1] <= main[0] and main[1] <= reg[0] and reg[1] <= total
+        self.ranges = {"enc": (0, main[0]), "main": (main[0], reg[0]), "reg": (reg[0], total)}
+        self.works = {}
+
+    def slice(self, flat, name):
+        lo, hi = self.ranges[name]
+        return flat[lo:hi]
+
+    def launch(self, flat, name, group=None):
+        import torch.distributed as dist
+        self.works[name] = dist.all_reduce(self.slice(flat, name), op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+    def wait(self, name):
+        w = self.works.pop(name, None)
+        if w is not None:
+            w.wait()

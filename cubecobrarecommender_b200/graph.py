@@ -39,20 +39,41 @@ def upload_csr(csr: CubeCSR, device):
 
 def count_cooccurrence(indptr: torch.Tensor, indices: torch.Tensor, num_cubes: int, num_cards: int,
                        counts: torch.Tensor | None = None, accumulate: bool = False,
-                       bits: torch.Tensor | None = None) -> torch.Tensor:
-    """int32 counts of the cubes in (indptr, indices); bit-pack + popcount kernels."""
+                       bits: torch.Tensor | None = None, method: str = "auto",
+                       workspace: torch.Tensor | None = None) -> torch.Tensor:
+    """int32 counts of the cubes in (indptr, indices), ``cnt = X^T X`` (reference utils.py:82-84).
+
+    method "tensor": byte-expanded X^T contracted with tcgen05.mma kind::i8 (exact int32);
+    method "popcount": bit-packed cubes, AND + POPC tiles;
+    "auto" takes the tensor-core path whenever the counts buffer meets TMA's 16-byte rules."""
     lib = _lib.load()
     dev = indptr.device
-    kw, cpad = lib.cc_bits_words(num_cubes), lib.cc_bits_cpad(num_cards)
-    if bits is None:
-        bits = torch.empty((max(kw, 1), cpad), dtype=torch.int32, device=dev)
     bad = torch.zeros(1, dtype=torch.int32, device=dev)
     if counts is None:
-        counts = torch.empty((num_cards, num_cards), dtype=torch.int32, device=dev)
+        ld = (num_cards + 3) // 4 * 4           # TMA rows are multiples of 16 bytes
+        counts = torch.zeros((num_cards, ld), dtype=torch.int32, device=dev)[:, :num_cards] if ld != num_cards \
+            else torch.empty((num_cards, num_cards), dtype=torch.int32, device=dev)
         accumulate = False
     st = stream_ptr()
-    call("cc_bitpack_cubes", ptr(indptr), ptr(indices), num_cubes, num_cards, ptr(bits), ptr(bad), st)
-    call("cc_cooc_count", ptr(bits), num_cubes, num_cards, ptr(counts), counts.stride(0), int(accumulate), st)
+    tensor_ok = counts.stride(0) % 4 == 0 and counts.data_ptr() % 16 == 0 and counts.stride(1) == 1
+    if method == "auto":
+        method = "tensor" if tensor_ok else "popcount"
+    if method == "tensor":
+        if not tensor_ok:
+            raise ValueError("tensor-core count path needs a 16-byte aligned counts buffer with stride % 4 == 0")
+        wsb = lib.cc_cooc_tc_workspace_bytes(num_cubes, num_cards)
+        if workspace is None or workspace.numel() * workspace.element_size() < wsb:
+            workspace = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        call("cc_cooc_count_tc", ptr(indptr), ptr(indices), num_cubes, num_cards, ptr(workspace),
+             workspace.numel() * workspace.element_size(), ptr(counts), counts.stride(0), int(accumulate), ptr(bad), st)
+    elif method == "popcount":
+        kw, cpad = lib.cc_bits_words(num_cubes), lib.cc_bits_cpad(num_cards)
+        if bits is None:
+            bits = torch.empty((max(kw, 1), cpad), dtype=torch.int32, device=dev)
+        call("cc_bitpack_cubes", ptr(indptr), ptr(indices), num_cubes, num_cards, ptr(bits), ptr(bad), st)
+        call("cc_cooc_count", ptr(bits), num_cubes, num_cards, ptr(counts), counts.stride(0), int(accumulate), st)
+    else:
+        raise ValueError(f"unknown count method {method!r}")
     if int(bad.item()):
         raise ValueError(f"card index out of range [0, {num_cards})")
     return counts
@@ -81,14 +102,15 @@ def normalise(counts: torch.Tensor, *, want_m64=True, want_mhat=True, want_neg=T
     return CoocGraph(c, counts, m64, mhat, rowsum, neg)
 
 
-def build_graph(csr: CubeCSR, device="cuda", *, allreduce=True, group=None, **kw) -> CoocGraph:
+def build_graph(csr: CubeCSR, device="cuda", *, allreduce=True, group=None, method="auto", **kw) -> CoocGraph:
     """Counts of this rank's cubes (+ all_reduce when torch.distributed is initialised with
     more than one rank, i.e. the cubes are sharded) and the normalised matrices."""
     import torch.distributed as dist
     indptr, indices = upload_csr(csr, device)
-    counts = count_cooccurrence(indptr, indices, csr.num_cubes, csr.num_cards)
+    counts = count_cooccurrence(indptr, indices, csr.num_cubes, csr.num_cards, method=method)
     if allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+        buf = counts if counts.is_contiguous() else counts._base      # padded rows: reduce the whole buffer
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     return normalise(counts, **kw)
 
 

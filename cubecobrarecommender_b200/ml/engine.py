@@ -58,6 +58,12 @@ class DAEEngine:
         self.yw = self.cpad // 32
         self.launches = 0          # kernels launched by the last step (for bench's gpu_launches)
         self.prof = None
+        # data parallel: bucketed, asynchronous gradient all_reduce overlapped with backward (dist.GradBuckets);
+        # CC_DP_OVERLAP=0 falls back to one blocking all_reduce of the whole flat buffer after backward
+        import os
+        from ..dist import GradBuckets
+        self.buckets = GradBuckets(self.store.layout, self.store.total)
+        self.overlap = os.environ.get("CC_DP_OVERLAP", "1") != "0"
         self._alloc()
 
     # -- buffers --------------------------------------------------------------------
@@ -239,9 +245,11 @@ class DAEEngine:
             colsum(gacts[0], G(names[0] + "/bias"), self.cs_ws)
             gemm(gacts[0], W(names[0] + "/kernel"), g_in, transb=True, mask=h_in, precision=pr, round_out=tc)
             n_launch += 4
+            self._grads_ready(prefix)
         if not R:
             for n_ in dec_names("reg"):
                 G(n_ + "/kernel").zero_(); G(n_ + "/bias").zero_()
+            self._grads_ready("reg")
         # ---------------- backward: shared encoder (main + reg rows together) ----------------
         for i in (3, 2, 1):
             name = ENC_NAMES[i]
@@ -264,29 +272,58 @@ class DAEEngine:
         n_launch += 1
         if R:
             bag_bwd(g1[B:], self.reg_rows, self.reg_start, self.reg_len, gw1); n_launch += 1
+        self._grads_ready("enc")
         self.launches += n_launch
 
-    def allreduce_grads(self):
+    # -- data-parallel exchange ---------------------------------------------------------
+    def _distributed(self):
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            dist.all_reduce(self.store.grads, op=dist.ReduceOp.SUM, group=self.group)
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _grads_ready(self, bucket):
+        """Backward has finished every gradient of `bucket`: start its all_reduce (NCCL's own stream; it first
+        waits for the kernels enqueued so far) while the compute stream carries on with the next bucket."""
+        if self.overlap and self._distributed():
+            self.buckets.launch(self.store.grads, bucket, self.group)
+
+    def allreduce_grads(self):
+        """Blocking form: one all_reduce over the whole flat gradient buffer (CC_DP_OVERLAP=0)."""
+        import torch.distributed as dist
+        if self._distributed():
+            if not self.overlap:
+                dist.all_reduce(self.store.grads, op=dist.ReduceOp.SUM, group=self.group)
             dist.all_reduce(self.loss3, op=dist.ReduceOp.SUM, group=self.group)
 
     def apply_adam(self):
+        """TF-style Adam over all parameters, then the step counter advances."""
+        self._adam_range(None)
+        call("cc_step_increment", ptr(self.store.step), stream_ptr())
+        self.launches += 1
+
+    def _adam_range(self, bucket=None):
+        """Adam over the whole flat buffer, or over one gradient bucket of it (the step counter is untouched)."""
         s, a = self.store, self.adam
         st = stream_ptr()
+        lo, hi = (0, s.total) if bucket is None else self.buckets.ranges[bucket]
+        sl = lambda t: t[lo:hi] if t is not None else None
         with self._timed("adam"):
-            call("cc_adam_step", ptr(s.params), ptr(s.grads), ptr(s.adam_m), ptr(s.adam_v), s.total, ptr(s.step),
-                 a["lr"], a["beta1"], a["beta2"], a["eps"], ptr(s.shadow), st)
-        call("cc_step_increment", ptr(s.step), st)
-        self.launches += 2
+            call("cc_adam_step", ptr(sl(s.params)), ptr(sl(s.grads)), ptr(sl(s.adam_m)), ptr(sl(s.adam_v)), hi - lo,
+                 ptr(s.step), a["lr"], a["beta1"], a["beta2"], a["eps"], ptr(sl(s.shadow)), st)
+        self.launches += 1
 
     def train_step(self):
         """forward + backward + (all_reduce) + Adam on the batch set by set_batch/sample_batch.
         Returns the device tensor loss3 = [bce, kl, bce + reg*kl] (no synchronisation)."""
         self.forward_backward()
         self.allreduce_grads()
-        self.apply_adam()
+        if self.overlap and self._distributed():
+            for bucket in self.buckets.ORDER:          # Adam follows the reductions bucket by bucket
+                self.buckets.wait(bucket)
+                self._adam_range(bucket)
+            call("cc_step_increment", ptr(self.store.step), stream_ptr())
+            self.launches += 1
+        else:
+            self.apply_adam()
         return self.loss3
 
     def check_overflow(self):

@@ -54,6 +54,16 @@ int cc_bitpack_cubes(const int64_t* indptr, const int32_t* indices, int64_t num_
 /* counts[i][j] (int32, ld >= C) = number of cubes containing both i and j; accumulate != 0 adds. */
 int cc_cooc_count(const uint32_t* bits, int64_t num_cubes, int32_t num_cards, int32_t* counts, int64_t ld,
                   int accumulate, void* stream);
+/* The same counts on the tensor cores: cubes are expanded to a K-major 0/1 byte matrix X^T [C][chunk] (in the
+ * caller's workspace, cc_cooc_tc_workspace_bytes) and contracted as X^T X with tcgen05.mma kind::i8 (int32
+ * accumulators, exact), upper-triangle 256x256 tiles mirrored by the epilogue; cubes are processed in chunks of
+ * cc_cooc_tc_chunk_cubes.  counts: 16-byte aligned, ldc % 4 == 0.  bad (optional) is set to 1 on an
+ * out-of-range card id.  Duplicate ids inside a cube collapse, as in utils.build_cubes (utils.py:66-71). */
+int64_t cc_cooc_tc_chunk_cubes(int64_t num_cubes);
+int64_t cc_cooc_tc_workspace_bytes(int64_t num_cubes, int32_t num_cards);
+int cc_cooc_count_tc(const int64_t* indptr, const int32_t* indices, int64_t num_cubes, int32_t num_cards,
+                     void* workspace, int64_t workspace_bytes, int32_t* counts, int64_t ldc, int accumulate,
+                     int32_t* bad, void* stream);
 /* From counts: M (float64, nullable), M-hat (float32, nullable), rowsum of y (float64, nullable). */
 int cc_row_normalise(const int32_t* counts, int64_t ld, int32_t num_cards, double* m64, int64_t ld_m,
                      float* mhat, int64_t ld_mhat, double* rowsum, int has_force_diag, double force_diag,
@@ -152,6 +162,9 @@ int cc_gemm_bce_tc(int precision, int m, int n, int k, const void* a, int64_t ld
                    const float* bias, const uint32_t* ybits, int64_t ywords, double count, float* dz, int64_t lddz,
                    double* loss_partial, int round_tf32, void* stream);
 int64_t cc_gemm_bce_partial_count(int m, int lddz);
+/* CTA-pair tiling of the tcgen05 GEMMs (256 x 256 tiles on two SMs, tcgen05.mma.cta_group::2):
+ * -1 = the planner decides per problem (default), 0 = never, 1 = whenever the shape allows it. */
+int cc_gemm_tc_set_pair_mode(int mode);
 int64_t cc_colsum_workspace_bytes(int m, int n);
 int cc_colsum_f32(const float* x, int64_t ld, int m, int n, float* workspace, float* out, int accumulate,
                   void* stream);

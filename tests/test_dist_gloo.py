@@ -106,3 +106,28 @@ def test_shard_helpers():
     csr = CubeCSR.from_lists([[0], [1, 2], [], [3]], 5)
     parts = [csr.shard(r, 2) for r in range(2)]
     assert sum(p.num_cubes for p in parts) == 4 and parts[1].indices.tolist() == [3]
+
+
+def _bucket_job(rank, world):
+    from cubecobrarecommender_b200.ml.model import ParamStore
+    store = ParamStore(64, "cpu")
+    bk = D.GradBuckets(store.layout, store.total)
+    g = torch.Generator().manual_seed(rank)
+    store.grads.copy_(torch.randn(store.total, generator=g))
+    whole = store.grads.clone()
+    for name in bk.ORDER:                       # asynchronous per-bucket reductions, in backward's order
+        bk.launch(store.grads, name)
+    for name in bk.ORDER:
+        bk.wait(name)
+    D.all_reduce_sum_(whole)
+    return store.grads.numpy(), whole.numpy(), bk.ranges, store.total
+
+
+def test_gradient_buckets_tile_the_flat_buffer_and_match_one_allreduce():
+    out = _spawn(_bucket_job)
+    for bucketed, whole, ranges, total in out:
+        assert np.array_equal(bucketed, whole)
+        spans = sorted(ranges.values())
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))          # no gap, no overlap
+        assert all(lo % 4 == 0 for lo, _ in spans)                          # 16-byte aligned for the Adam kernel

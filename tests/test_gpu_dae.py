@@ -141,15 +141,29 @@ def _rn_tf32(x):
     return ((xi + 0x0FFF + ((xi >> 13) & 1)) & ~0x1FFF).view(torch.float32)
 
 
-@pytest.mark.parametrize("tile_n", [128, 256])
+@pytest.fixture
+def pair_mode():
+    """Sets the CTA-pair (cta_group::2) tiling mode of the tcgen05 GEMMs for one test, then restores 'auto'."""
+    from cubecobrarecommender_b200 import _lib
+
+    def set_mode(mode):
+        _lib.call("cc_gemm_tc_set_pair_mode", int(mode))
+    yield set_mode
+    set_mode(-1)
+
+
+@pytest.mark.parametrize("tile_n", [128, 256, "pair"])
 @pytest.mark.parametrize("ta,tb,m,n,k,split", [(0, 0, 130, 72, 132, 1), (0, 1, 64, 260, 100, 1), (1, 0, 132, 128, 300, 1),
                                                (1, 1, 20, 24, 36, 1), (0, 0, 4096, 512, 256, 1), (1, 0, 512, 64, 8192, 0),
                                                (1, 0, 128, 260, 4100, 7), (0, 1, 300, 260, 20884, 1),
                                                (0, 1, 300, 520, 20884, 0)])
-def test_gemm_tcgen05_tf32_all_layouts(ta, tb, m, n, k, split, tile_n):
+def test_gemm_tcgen05_tf32_all_layouts(ta, tb, m, n, k, split, tile_n, pair_mode):
     """tcgen05 kind::tf32 GEMM vs float64 on operands already rounded to tf32 (so the products are exact
-    and only fp32 accumulation differs): K-major and MN-major operands, ragged tiles, split-K."""
+    and only fp32 accumulation differs): K-major and MN-major operands, ragged tiles, split-K; single-CTA
+    128x128 / 128x256 tiles and 256x256 CTA-pair tiles (cta_group::2)."""
     from cubecobrarecommender_b200.ml import tensorcore as TC
+    pair_mode(1 if tile_n == "pair" else 0)
+    tile_n = 256 if tile_n == "pair" else tile_n
     g = torch.Generator(device="cuda").manual_seed(m * n + k)
     a = _rn_tf32(torch.randn((k, m) if ta else (m, k), device="cuda", generator=g))
     b = _rn_tf32(torch.randn((n, k) if tb else (k, n), device="cuda", generator=g))
@@ -181,9 +195,12 @@ def test_gemm_tcgen05_tf32_all_layouts(ta, tb, m, n, k, split, tile_n):
         assert (c4.double() - torch.relu(ref + bias.double())).abs().max().item() / scale < tol
 
 
-def test_gemm_bce_fused_epilogue_vs_oracle():
+@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("m,c", [(200, 1000), (300, 1100)])
+def test_gemm_bce_fused_epilogue_vs_oracle(m, c, pair, pair_mode):
     from cubecobrarecommender_b200.ml import tensorcore as TC
-    m, k, c = 200, 512, 1000
+    pair_mode(pair)
+    k = 512
     cpad = (c + 127) // 128 * 128
     g = torch.Generator(device="cuda").manual_seed(1)
     a = _rn_tf32(torch.randn(m, k, device="cuda", generator=g))

@@ -27,11 +27,16 @@ def test_golden_adjacency_host_entry(graph_golden):
     assert np.array_equal(m2, g["adj_force_diag"])
 
 
-@pytest.mark.parametrize("k,c,lo,hi", [(1, 5, 1, 5), (33, 130, 3, 60), (700, 1000, 20, 200), (2100, 300, 5, 40)])
-def test_counts_and_normalise_vs_oracle(k, c, lo, hi):
+METHODS = ["tensor", "popcount"]     # tcgen05 kind::i8 contraction | bit-packed AND+POPC tiles
+
+
+@pytest.mark.parametrize("method", METHODS)
+@pytest.mark.parametrize("k,c,lo,hi", [(1, 5, 1, 5), (33, 130, 3, 60), (700, 1000, 20, 200), (2100, 300, 5, 40),
+                                       (300, 515, 100, 400)])
+def test_counts_and_normalise_vs_oracle(k, c, lo, hi, method):
     ip, ix = synth_cubes_csr(k, c, size_lo=lo, size_hi=hi, seed=k + c)
     csr = CubeCSR(ip, ix, c)
-    gr = G.build_graph(csr, "cuda")
+    gr = G.build_graph(csr, "cuda", method=method)
     cnt = og.cooc_counts(ip, ix, c)
     assert np.array_equal(gr.counts.cpu().numpy(), cnt)
     m = og.adjacency_from_counts(cnt)
@@ -46,34 +51,51 @@ def test_counts_and_normalise_vs_oracle(k, c, lo, hi):
     assert abs(gr.neg_sampler.sum().item() - 1) < 1e-12
 
 
-def test_empty_and_ragged_cubes():
+@pytest.mark.parametrize("method", METHODS)
+def test_empty_and_ragged_cubes(method):
     # empty cubes, a cube with every card, duplicate ids collapse
     csr = CubeCSR.from_lists([[], [0, 1, 2, 3, 4, 5, 6], [3, 3, 3], [], [6, 0]], 7)
-    gr = G.build_graph(csr, "cuda")
+    gr = G.build_graph(csr, "cuda", method=method)
     cnt = og.cooc_counts(csr.indptr, csr.indices, 7)
     assert np.array_equal(gr.counts.cpu().numpy(), cnt)
     with pytest.raises(ValueError):
         bad = CubeCSR(np.array([0, 2]), np.array([1, 9], dtype=np.int32), 7)
-        G.build_graph(bad, "cuda")
+        G.build_graph(bad, "cuda", method=method)
 
 
-def test_accumulate_equals_single_pass():
+@pytest.mark.parametrize("method", METHODS)
+def test_accumulate_equals_single_pass(method):
     ip, ix = synth_cubes_csr(300, 257, size_lo=5, size_hi=50, seed=5)
     csr = CubeCSR(ip, ix, 257)
-    whole = G.build_graph(csr, "cuda", want_m64=False, want_mhat=False, want_neg=False).counts
+    whole = G.build_graph(csr, "cuda", want_m64=False, want_mhat=False, want_neg=False, method="popcount").counts
     acc = None
     for r in range(3):
         sh = csr.shard(r, 3)
         a, b = G.upload_csr(sh, "cuda")
-        acc = G.count_cooccurrence(a, b, sh.num_cubes, 257, counts=acc, accumulate=acc is not None)
+        acc = G.count_cooccurrence(a, b, sh.num_cubes, 257, counts=acc, accumulate=acc is not None, method=method)
     assert torch.equal(acc, whole)          # "checksum of checksums": shards sum to the whole
+
+
+def test_tensor_count_chunks_over_cubes():
+    """More cubes than one pass of the byte matrix holds (cc_cooc_tc_chunk_cubes): passes accumulate."""
+    from cubecobrarecommender_b200 import _lib
+    k, c = 40000, 264
+    assert _lib.load().cc_cooc_tc_chunk_cubes(k) < k
+    ip, ix = synth_cubes_csr(k, c, size_lo=2, size_hi=30, seed=9)
+    a, b = G.upload_csr(CubeCSR(ip, ix, c), "cuda")
+    t = G.count_cooccurrence(a, b, k, c, method="tensor")
+    p = G.count_cooccurrence(a, b, k, c, method="popcount")
+    assert torch.equal(t, p)
+    assert np.array_equal(t.cpu().numpy(), og.cooc_counts(ip, ix, c))
 
 
 def test_size_independent_properties_large():
     ip, ix = synth_cubes_csr(4096, 4000, cfg=1)
     csr = CubeCSR(ip, ix, 4000)
-    gr = G.build_graph(csr, "cuda")
+    gr = G.build_graph(csr, "cuda", method="tensor")
     cnt = gr.counts
+    assert torch.equal(cnt, G.build_graph(csr, "cuda", method="popcount", want_m64=False, want_mhat=False,
+                                          want_neg=False).counts)      # the two count kernels agree bit for bit
     assert torch.equal(cnt, cnt.t())                                       # symmetric
     sizes = torch.from_numpy(np.diff(ip)).cuda()
     assert int(cnt.diagonal().sum()) == int(sizes.sum())                   # diag = card frequency
