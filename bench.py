@@ -47,22 +47,31 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md).  The poller is
+    started before warm-up (nvidia-smi needs a few hundred ms before its first sample); only samples whose
+    timestamp falls between mark_begin() and mark_end() are reported."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "10", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
@@ -73,20 +82,30 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.thread.join(timeout=2)
-        sm, mx, reasons, power = [], [], set(), []
+        import datetime
+        rows = []
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
+            if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[2]), float(f[3]), float(f[4]), f[5:9]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+        inside = [r for r in rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1]
+        window = "timed region"
+        if not inside:      # region shorter than the sampling period: fall back to everything sampled under load
+            inside, window = rows, "warm-up + timed region"
+        reasons = set()
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        sm = [r[1] for r in inside]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(r[2] for r in inside) if inside else None,
+                "power_w_max": max(r[3] for r in inside) if inside else None, "samples": len(inside), "window": window,
+                "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------ CPU comparator
@@ -163,19 +182,22 @@ def measure_extras(dev, peaks, log):
     indptr, indices = G.upload_csr(csr, dev)
     lib = _lib.load()
     bits = torch.empty((lib.cc_bits_words(K), lib.cc_bits_cpad(C)), dtype=torch.int32, device=dev)
+    ws = torch.empty(lib.cc_cooc_tc_workspace_bytes(K, C), dtype=torch.uint8, device=dev)
     counts = torch.empty((C, C), dtype=torch.int32, device=dev)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    times = []
-    for it in range(3):
-        ev[0].record()
-        G.count_cooccurrence(indptr, indices, K, C, counts=counts, bits=bits)
-        ev[1].record()
-        gr = G.normalise(counts)
-        ev[2].record()
-        torch.cuda.synchronize()
-        times.append((ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])))
-        del gr
-    t_cnt, t_norm = min(t[0] for t in times), min(t[1] for t in times)
+    times = {"tensor": [], "popcount": []}
+    for method in ("popcount", "tensor"):          # "tensor" (tcgen05 kind::i8) last: it is the product path
+        for it in range(3):
+            ev[0].record()
+            G.count_cooccurrence(indptr, indices, K, C, counts=counts, bits=bits, workspace=ws, method=method)
+            ev[1].record()
+            gr = G.normalise(counts)
+            ev[2].record()
+            torch.cuda.synchronize()
+            times[method].append((ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])))
+            del gr
+    t_cnt, t_norm = min(t[0] for t in times["tensor"]), min(t[1] for t in times["tensor"])
+    t_cnt_popc = min(t[0] for t in times["popcount"])
     algo_bytes = K * C / 8 + 4.0 * C * C + 4.0 * C * C + 8.0 * C * C          # 7.11 GB
     pair_words = C * (C + 1) / 2 * (K / 32.0)                                  # AND+POPC word pairs (upper triangle)
     t1 = time.time()
@@ -192,27 +214,38 @@ def measure_extras(dev, peaks, log):
     nnz_ratio = float(csr.indptr[-1]) / float(csr.indptr[ksub])
     out["graph_build"] = {
         "workload": f"create_mtx: K={K} cubes x C={C} cards, nnz={int(csr.indptr[-1])}",
-        "count_ms": t_cnt, "normalise_ms": t_norm, "device_seconds": (t_cnt + t_norm) / 1e3,
+        "count_ms": t_cnt, "count_kernel": "expand_cubes_u8 + gemm_tc_kernel<u8, kind::i8> (X^T X, upper triangle mirrored)",
+        "count_tensor_top_per_s": 2.0 * K * C * C / (t_cnt * 1e-3) / 1e12,
+        "count_popcount_ms": t_cnt_popc, "normalise_ms": t_norm, "device_seconds": (t_cnt + t_norm) / 1e3,
         "e2e_host_seconds": t_host, "e2e_note": "CSR H2D + kernels + 3.5 GB float64 M D2H through cc_create_adjacency_matrix_host",
-        "roofline": {"kernel": "cooc_count_kernel", "bound": "hbm", "achieved": algo_bytes / ((t_cnt + t_norm) * 1e-3) / 1e9,
+        "roofline": {"kernel": "count (tcgen05 kind::i8) + row_normalise", "bound": "hbm", "achieved": algo_bytes / ((t_cnt + t_norm) * 1e-3) / 1e9,
                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": algo_bytes / ((t_cnt + t_norm) * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                     "traffic": None, "note": "compute-bound at this K (SURVEY.md 7): the popcount pipe, not HBM, is the limit",
-                     "popc_word_pairs_per_s": pair_words / (t_cnt * 1e-3)},
+                     "traffic": None,
+                     "note": "algorithmic bytes of SURVEY.md 8d (7.11 GB) over count + normalise; the count itself is a "
+                             "2*K*C^2 contraction (tensor-bound at this K), the normalise pass is the HBM-bound part",
+                     "normalise_GBps": 16.0 * C * C / (t_norm * 1e-3) / 1e9,
+                     "popcount_kernel_word_pairs_per_s": pair_words / (t_cnt_popc * 1e-3)},
         "cpu_baseline": {"seconds_extrapolated": t_cpu_sub * nnz_ratio, "cores": 1, "kind": "port",
                          "sample": f"create_adjacency_matrix loop restatement on {ksub} cubes x {C} cards: {t_cpu_sub:.1f}s, scaled by nnz x{nnz_ratio:.0f}"},
     }
-    del counts, bits
+    del counts, bits, ws
     torch.cuda.empty_cache()
     # ---------------- batched ML recommend: top-50 with in-cube masking ----------------
-    C2, K2 = 20884, 16384
+    C2, K2 = 20884, 100000                      # configs[3]: 100k cubes, top-50, in-cube masking
     csr2 = make_cubes(K2, C2, cfg=4)
     model = M.CC_Recommender(C2, device=dev, seed=0, precision="tf32")
-    rec = INF.MLRecommender(model, chunk=2048)
-    rec.recommend(csr2.rows(np.arange(2048)), 50)
+    rec = INF.MLRecommender(model, chunk=4096)
+    rec.recommend(csr2.rows(np.arange(4096)), 50)
     torch.cuda.synchronize()
     t3 = time.time()
     ids, vals, cnt = rec.recommend(csr2, 50)
     t_rec = time.time() - t3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rec.recommend_device(csr2, 50)
+    e1.record()
+    torch.cuda.synchronize()
+    t_rec_dev = e0.elapsed_time(e1) / 1e3
     params = model.get_weights_dict()
     nb = 32
     dense = csr2.rows(np.arange(nb)).to_dense()
@@ -225,7 +258,8 @@ def measure_extras(dev, peaks, log):
     t_cpu = time.time() - t4
     out["ml_recommend"] = {
         "workload": f"ml_recommend top-50, {K2} cubes, C={C2}, in-cube masking, host CSR in / host ids out",
-        "recs_per_s": K2 / t_rec, "seconds": t_rec,
+        "recs_per_s": K2 / t_rec, "seconds": t_rec, "device_recs_per_s": K2 / t_rec_dev,
+        "device_note": "CUDA-event time of the same call without the final D2H of ids/scores (CSR H2D included)",
         "cpu_baseline": {"value": nb / t_cpu, "unit": "cubes/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{nb} cubes: torch-CPU forward + argsort walk (model load excluded)"},
     }
@@ -278,21 +312,23 @@ def run_native(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     for i in range(args.warmup):
         step(i)
     eng.check_overflow()
     barrier()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     eng.enable_kernel_timing(True)
     eng.launches = 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.mark_begin()
     ev0.record()
     for i in range(args.steps):
         loss = step(args.warmup + i)
     ev1.record()
     barrier()
+    clocks.mark_end()
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -405,7 +441,7 @@ def run_native(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--precision", default=os.environ.get("CC_PRECISION", "tf32"), choices=["fp32", "tf32", "bf16"])

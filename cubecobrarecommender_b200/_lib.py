@@ -42,6 +42,8 @@ SIGNATURES = {
     "cc_score_gather_f64": (I, [P, I64, I32, P, P, I32, P, P, I32, I, P, P, I64, P]),
     "cc_topn_workspace_bytes": (I64, [I32, I32, I32, I]),
     "cc_topn_masked_f32": (I, [P, I64, I32, I32, P, P, I, I, I32, P, I64, P, P, P, P]),
+    "cc_topn_masked_sigmoid_f32": (I, [P, I64, I32, I32, P, P, I, I, I32, P, P, P, P]),
+    "cc_topn_set_force_radix": (I, [I]),
     "cc_topn_masked_f64": (I, [P, I64, I32, I32, P, P, I, I, I32, P, I64, P, P, P, P]),
     # (3) noise
     "cc_alias_build_host": (I, [P, I32, P, P]),
@@ -56,7 +58,7 @@ SIGNATURES = {
     # (5) dense
     "cc_gemm_f32_simt": (I, [I, I, I, I, I, P, I64, P, I64, P, I64, P, I, P, I64, I, P]),
     "cc_gemm_tc": (I, [I, I, I, I, I, I, P, I64, P, I64, P, I64, P, I, P, I64, I, I, I, I, P]),
-    "cc_gemm_bce_tc": (I, [I, I, I, I, P, I64, P, I64, P, P, I64, D, P, I64, P, I, P]),
+    "cc_gemm_bce_tc": (I, [I, I, I, I, P, I64, P, I64, P, P, I64, D, P, I64, P, P, I, P]),
     "cc_gemm_bce_partial_count": (I64, [I, I]),
     "cc_gemm_tc_set_pair_mode": (I, [I]),
     "cc_colsum_workspace_bytes": (I64, [I, I]),

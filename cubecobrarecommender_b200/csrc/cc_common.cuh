@@ -71,6 +71,10 @@ __device__ __forceinline__ float rn_tf32(float x) {
   return __uint_as_float(r);
 }
 
+// sigmoid of a logit as the recommenders report it (reference ml_recommend.py:78-80 reads float32 sigmoid
+// outputs); ONE definition, so the fused select and the standalone sigmoid pass give identical bits
+__device__ __forceinline__ float sigmoid_f32(float z) { return 1.f / (1.f + expf(-z)); }
+
 // streaming 128-bit loads that do not pollute L1 (data is read once per CTA)
 __device__ __forceinline__ uint4 ld_nc_u4(const void* p) {
   uint4 r;

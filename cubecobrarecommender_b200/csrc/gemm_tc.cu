@@ -65,12 +65,12 @@ struct Params {
   const uint32_t* ybits; long long ywords;
   float inv_count;
   double* loss_partial;                  // [tiles][4 warps]
+  float* dbias;                          // EPI_BCE: column sums of dlogits (= the output layer's bias gradient), atomically added
   int a_mn_major, b_mn_major;
   // EPI_COUNT: C = A A^T is symmetric -> only tiles with nt >= mt are computed (square 256 x 256 pair tiles) and every
   // off-diagonal tile is also written transposed
   int symmetric;
   int* count_out; long long ldcount;
-  int debug;                             // experiment switches (CC_TC_DEBUG), 0 in production
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -382,35 +382,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int row0 = (mt * CTAS + cta_rank) * BM + q * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.m;
-      // operands of the epilogue that live in global memory (the bias slice, and for BCE this row's y bits)
-      // are fetched one 32-column chunk ahead, the first one while the MMAs of this tile still run.
+      // operands of the epilogue that live in global memory (the tile's bias slice, and for BCE this row's y bits:
+      // BN/32 consecutive words = one or two 16-byte loads) are fetched for the WHOLE tile while its MMAs still
+      // run, so no chunk of the epilogue waits on a global load.
       // Lane l holds the bias of column col0 + l; element j of the chunk gets it by shuffle from lane j.
-      auto fetch_bias = [&](int col0) -> float {
-        const int col = col0 + lane;
-        return (p.bias && col < p.n) ? __ldg(p.bias + col) : 0.f;
-      };
-      auto fetch_y = [&](int col0) -> uint32_t {
-        return (EPI == EPI_BCE && row_ok && col0 < p.n_store) ? __ldg(p.ybits + (long long)row * p.ywords + (col0 >> 5)) : 0u;
-      };
-      float b_next = fetch_bias(nt * BN);
-      uint32_t y_next = fetch_y(nt * BN);
+      float bias_r[BN / 32];
+      uint32_t y_r[BN / 32];
+#pragma unroll
+      for (int cb = 0; cb < BN / 32; ++cb) {
+        const int col = nt * BN + cb * 32 + lane;
+        bias_r[cb] = (p.bias && col < p.n) ? __ldg(p.bias + col) : 0.f;
+        y_r[cb] = 0u;
+      }
+      if (EPI == EPI_BCE && row_ok) {
+        const uint32_t* yrow = p.ybits + (long long)row * p.ywords + ((nt * BN) >> 5);
+        if (nt * BN + BN <= p.ywords * 32 && (((long long)row * p.ywords) & 3) == 0 &&
+            (reinterpret_cast<uintptr_t>(p.ybits) & 15) == 0) {
+#pragma unroll
+          for (int q4 = 0; q4 < BN / 128; ++q4) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4*>(yrow) + q4);
+            y_r[4 * q4] = w.x; y_r[4 * q4 + 1] = w.y; y_r[4 * q4 + 2] = w.z; y_r[4 * q4 + 3] = w.w;
+          }
+        } else {
+#pragma unroll
+          for (int cb = 0; cb < BN / 32; ++cb)
+            if (nt * BN + cb * 32 < p.n_store) y_r[cb] = __ldg(yrow + cb);
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       float row_loss = 0.f;
-#pragma unroll 1
+      // The BCE body is ~800 instructions per 32-column chunk: unrolling it 8x overflows the instruction cache
+      // (measured: 300 -> 442 us), so it stays a rolled loop and the prefetched registers are ROTATED instead
+      // of indexed (static index 0 every iteration); the short store body is fully unrolled.
+#pragma unroll(EPI == EPI_BCE ? 1 : BN / 32)
       for (int cb = 0; cb < BN / 32; ++cb) {
         const int col0 = nt * BN + cb * 32;
         if (col0 >= p.n_store || row0 >= p.m || !has_k) break;      // warp-uniform
         uint32_t v[32];
         __syncwarp();
-        if (p.debug & 4) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0;
-        } else
         tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + cb * 32), v);
-        const float b_cur = b_next;
-        const uint32_t ybw = y_next;
-        if (cb + 1 < BN / 32) { b_next = fetch_bias(col0 + 32); y_next = fetch_y(col0 + 32); }
+        const float b_cur = bias_r[0];
+        const uint32_t ybw = y_r[0];
+#pragma unroll
+        for (int r = 0; r + 1 < BN / 32; ++r) { bias_r[r] = bias_r[r + 1]; y_r[r] = y_r[r + 1]; }
         float out[32];
         if (EPI == EPI_COUNT) {
           // int32 accumulators pass through bit for bit; an off-diagonal tile is also written transposed
@@ -447,6 +462,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               } else {
                 row_loss += l;
               }
+              g = row_ok ? g : 0.f;              // rows beyond m are clipped by the store but feed the column sums
               out[j] = p.round_tf32 ? rn_tf32(g) : g;
             }
           }
@@ -471,7 +487,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         // registers -> swizzled staging (row = lane, 16-byte chunk c at position c ^ (lane & 7)) -> TMA store
         uint8_t* sbuf = stage_buf + buf * 4096;
-        if (p.debug & 2) { if (out[lane] == 12345.678f) sbuf[0] = 1; continue; }
         if (lane == 0) tma_wait_group_read<1>();        // the store that last read this buffer has drained
         __syncwarp();
 #pragma unroll
@@ -480,10 +495,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               make_float4(out[4 * c], out[4 * c + 1], out[4 * c + 2], out[4 * c + 3]);
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0 && !(p.debug & 1)) {
+        if (lane == 0) {
           if (p.reduce_add) tma_reduce_add_2d(&map_c, sbuf, col0, row0);
           else              tma_store_2d(&map_c, sbuf, col0, row0);
           tma_commit_group();
+        }
+        if (EPI == EPI_BCE && p.dbias) {
+          // bias gradient = column sums of dlogits: lane j adds up column j of the staged 32 x 32 block (for a fixed
+          // row the 32 lanes hit 32 different banks of the swizzled row) and issues one coalesced RED per chunk.
+          // Rows beyond m and columns beyond n hold zeros.
+          float cs = 0.f;
+#pragma unroll
+          for (int r = 0; r < 32; ++r)
+            cs += *reinterpret_cast<const float*>(sbuf + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
+          if (col0 + lane < p.n) atomicAdd(p.dbias + col0 + lane, cs);
         }
         buf ^= 1;
       }
@@ -639,8 +664,6 @@ static int launch_bn(const Problem& pr, Params p, cudaStream_t st) {
   if (rc != CC_OK) return rc;
   p.a_mn_major = pr.transa ? 1 : 0;
   p.b_mn_major = pr.transb ? 0 : 1;
-  static const int dbg = getenv("CC_TC_DEBUG") ? atoi(getenv("CC_TC_DEBUG")) : 0;
-  p.debug = dbg;
   p.m_tiles = ceil_div(pr.m, BM * CTAS);
   p.n_tiles = ceil_div(p.n_store, BN);
   p.total_k_blocks = ceil_div(pr.k, bk);
@@ -742,6 +765,8 @@ int cc_gemm_tc(int precision, int transa, int transb, int m, int n, int k, const
       if (tile_n && bns[bi] != tile_n) continue;
       if (!tile_n && bns[bi] == 256 && n <= 128) continue;
       if (cts[bi] == 2 && tc::g_pair_mode == 0) continue;
+      // small layers are latency-bound: single CTAs spread them over more SMs and skip the cluster handshakes
+      if (cts[bi] == 2 && tc::g_pair_mode < 0 && 2.0 * m * n * double(k) < 2.0e10) continue;
       if (cts[bi] == 1 && tc::g_pair_mode == 1 && (tile_n == 0 || tile_n == 256) && n > 128) continue;
       const int smax = split_k > 0 ? split_k : (kblocks >= 16 ? (kblocks / 8 < 64 ? kblocks / 8 : 64) : 1);
       for (int s = (split_k > 0 ? split_k : 1); s <= smax; ++s) {
@@ -779,7 +804,7 @@ int cc_gemm_tc(int precision, int transa, int transb, int m, int n, int k, const
 // loss_partial: float64 [cc_gemm_bce_partial_count(m, lddz)]  (sum it with cc_loss_finalize).
 int cc_gemm_bce_tc(int precision, int m, int n, int k, const void* a, int64_t lda, const void* w, int64_t ldw,
                    const float* bias, const uint32_t* ybits, int64_t ywords, double count, float* dz, int64_t lddz,
-                   double* loss_partial, int round_tf32, void* stream) {
+                   double* loss_partial, float* dbias, int round_tf32, void* stream) {
   CC_REQUIRE(a && w && bias && ybits && dz && loss_partial, "cc_gemm_bce_tc: null pointer");
   CC_REQUIRE(precision == 1 || precision == 2, "cc_gemm_bce_tc: precision must be 1 (tf32) or 2 (bf16)");
   CC_REQUIRE(m > 0 && n > 0 && k > 0 && count > 0, "cc_gemm_bce_tc: bad sizes");
@@ -789,6 +814,8 @@ int cc_gemm_bce_tc(int precision, int m, int n, int k, const void* a, int64_t ld
   p.m = m; p.n = n; p.k = k; p.n_store = int(lddz);
   p.bias = bias; p.split_k = 1; p.round_tf32 = round_tf32;
   p.ybits = ybits; p.ywords = ywords; p.inv_count = float(1.0 / count); p.loss_partial = loss_partial;
+  p.dbias = dbias;
+  if (dbias) CC_CHECK_CUDA(cudaMemsetAsync(dbias, 0, size_t(n) * sizeof(float), as_stream(stream)));
   tc::Problem pr{0, 0, m, n, k, a, lda, w, ldw, dz, lddz, precision == 2 ? tc::KIND_BF16 : tc::KIND_TF32};
   const int ctas = tc::g_pair_mode == 0 ? 1 : 2;
   if (precision == 2) return tc::launch<tc::KIND_BF16, tc::EPI_BCE>(pr, p, 256, ctas, as_stream(stream));

@@ -306,7 +306,7 @@ __global__ void round_tf32_kernel(const float* __restrict__ x, float* __restrict
 // sigmoid of the winners / in-cube scores: probs = 1/(1+exp(-z))
 __global__ void sigmoid_kernel(const float* __restrict__ z, float* __restrict__ out, int64_t n) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = 1.f / (1.f + expf(-z[i]));
+  if (i < n) out[i] = sigmoid_f32(z[i]);
 }
 
 }  // namespace cc

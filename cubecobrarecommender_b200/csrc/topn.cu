@@ -273,6 +273,133 @@ rank_all_kernel(const T* __restrict__ scores, int64_t ld, int32_t num_cards,
   if (threadIdx.x == 0 && out_count) out_count[cube] = n_eff;
 }
 
+// ------------------------------------------------------------- warp-per-cube streaming select (float32, n <= 128)
+// One pass over the scores: a warp keeps the best keys seen so far in a 256-slot shared buffer and a running
+// threshold (the n-th best key); a score only enters the buffer when its composite key beats the threshold,
+// and the buffer is sorted and cut back to n whenever it fills.  After the first few hundred elements almost
+// nothing passes (expected insertions ~ n ln(C/n)), so the kernel is one coalesced read of the row plus a
+// handful of 256-key bitonic sorts -- against up to eight passes with shared-memory histogram atomics in the
+// radix-select kernel above.  Same total order (score, then index) => identical ids.
+constexpr int WS_WARPS = 8;
+constexpr int WS_CAP = 256;
+constexpr int WS_MAX_N = 128;
+
+__device__ __forceinline__ void warp_bitonic_desc(unsigned long long* buf, int lane) {
+  for (int k = 2; k <= WS_CAP; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int t = 0; t < WS_CAP / 64; ++t) {
+        const int p = lane + 32 * t;                              // compare-exchange pair index
+        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));      // element with bit j clear
+        const int x = i | j;
+        const unsigned long long a = buf[i], b = buf[x];
+        const bool up = (i & k) == 0;                             // "up" blocks hold larger keys first
+        if (up ? (a < b) : (a > b)) { buf[i] = b; buf[x] = a; }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <bool SIGMOID>
+__global__ void __launch_bounds__(WS_WARPS * 32)
+topn_warpselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_cards, int32_t batch,
+                       const int64_t* __restrict__ mask_ptr, const int32_t* __restrict__ mask_idx,
+                       int mode_only_listed, int descending, int32_t n, int32_t* __restrict__ out_ids,
+                       float* __restrict__ out_vals, int32_t* __restrict__ out_count) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int words = (num_cards + 31) >> 5;
+  unsigned long long* buf = reinterpret_cast<unsigned long long*>(smem_raw) + warp * WS_CAP;
+  uint32_t* mask = reinterpret_cast<uint32_t*>(smem_raw + size_t(WS_WARPS) * WS_CAP * 8) + size_t(warp) * words;
+  const int cube = blockIdx.x * WS_WARPS + warp;
+  if (cube >= batch) return;                    // warps are independent: no CTA-wide barrier below
+  for (int w = lane; w < words; w += 32) mask[w] = 0;
+  __syncwarp();
+  const int64_t mb = mask_ptr[cube], me = mask_ptr[cube + 1];
+  for (int64_t p = mb + lane; p < me; p += 32) {
+    const int32_t c = mask_idx[p];
+    if (c >= 0 && c < num_cards) atomicOr(&mask[c >> 5], 1u << (c & 31));
+  }
+  __syncwarp();
+  int listed = 0;
+  for (int w = lane; w < words; w += 32) listed += __popc(mask[w]);
+  listed = warp_sum(listed);
+  const int m = mode_only_listed ? listed : num_cards - listed;
+  const int n_eff = min(n, m);
+  const float* sc = scores + int64_t(cube) * ld;
+  unsigned long long thr = 0;                   // keys must beat this to enter the buffer
+  int cnt = 0;                                  // live keys in buf (warp-uniform)
+
+  auto prune = [&]() {
+    __syncwarp();
+    for (int i = cnt + lane; i < WS_CAP; i += 32) buf[i] = 0;
+    __syncwarp();
+    warp_bitonic_desc(buf, lane);
+    if (cnt >= n_eff && n_eff > 0) { thr = buf[n_eff - 1]; cnt = n_eff; }
+  };
+
+  if (n_eff > 0) {
+    for (int base = 0; base < num_cards; base += 128) {
+      float v[4];
+      bool cand[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {               // four independent 128-byte row segments in flight
+        const int e = base + 32 * u + lane;
+        const int wi = (base >> 5) + u;
+        const uint32_t mw = wi < words ? mask[wi] : 0u;
+        cand[u] = e < num_cards && ((((mw >> lane) & 1u) != 0) == (mode_only_listed != 0));
+        v[u] = cand[u] ? sc[e] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = base + 32 * u + lane;
+        unsigned long long key = 0;
+        if (cand[u]) key = make_key<float>(SIGMOID ? sigmoid_f32(v[u]) : v[u], (uint32_t)e, descending);
+        const bool pass = key > thr;
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (bal) {
+          if (pass) buf[cnt + __popc(bal & ((1u << lane) - 1u))] = key;
+          cnt += __popc(bal);
+          if (cnt > WS_CAP - 32) prune();
+        }
+      }
+    }
+    prune();
+  }
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    int32_t id = -1; float val = 0.f;
+    if (i < n_eff) {
+      const unsigned long long key = buf[i];
+      uint32_t t = (uint32_t)(key & 0xffffffffu), u = (uint32_t)(key >> 32);
+      if (!descending) { t = ~t; u = ~u; }
+      id = (int32_t)t;
+      val = __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);      // inverse of KeyOf<float>::ord
+    }
+    out_ids[int64_t(cube) * n + i] = id;
+    if (out_vals) out_vals[int64_t(cube) * n + i] = val;
+  }
+  if (lane == 0 && out_count) out_count[cube] = n_eff;
+}
+
+template <bool SIGMOID>
+static int warpselect_launch(const float* scores, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
+                             const int32_t* mask_idx, int mode_only_listed, int descending, int32_t n,
+                             int32_t* out_ids, float* out_vals, int32_t* out_count, cudaStream_t st) {
+  const size_t smem = size_t(WS_WARPS) * (WS_CAP * 8 + size_t((num_cards + 31) / 32) * 4);
+  CC_REQUIRE(smem <= 200 * 1024, "cc_topn_masked: C=%d needs %zu bytes of shared memory", num_cards, smem);
+  if (smem > 48 * 1024)
+    CC_CHECK_CUDA(cudaFuncSetAttribute(topn_warpselect_kernel<SIGMOID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  topn_warpselect_kernel<SIGMOID><<<ceil_div(batch, WS_WARPS), WS_WARPS * 32, smem, st>>>(
+      scores, ld, num_cards, batch, mask_ptr, mask_idx, mode_only_listed, descending, n, out_ids, out_vals, out_count);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+// the radix-select kernel stays the general path (any n, float64); float32 with n <= 128 takes the streaming select
+static int g_topn_force_radix = 0;
+
 static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 template <typename T>
@@ -285,6 +412,11 @@ int topn_launch(const T* scores, int64_t ld, int32_t num_cards, int32_t batch, c
   CC_REQUIRE(mask_idx || true, "unused");
   if (batch == 0) return CC_OK;
   const size_t mask_bytes = size_t((num_cards + 31) / 32) * 4;
+  if constexpr (sizeof(T) == 4) {
+    if (n <= WS_MAX_N && !g_topn_force_radix)
+      return warpselect_launch<false>(scores, ld, num_cards, batch, mask_ptr, mask_idx, mode_only_listed, descending, n,
+                                      out_ids, out_vals, out_count, st);
+  }
   if (n <= TOPN_MAX_SMEM_N) {
     const int n_pad = next_pow2(n < 2 ? 2 : n);
     const size_t smem = size_t(n_pad) * sizeof(K) + mask_bytes;
@@ -374,6 +506,22 @@ int cc_topn_masked_f32(const float* scores, int64_t ld, int32_t num_cards, int32
   return topn_launch<float>(scores, ld, num_cards, batch, mask_ptr, mask_idx, mode_only_listed, descending, n,
                             workspace, workspace_bytes, out_ids, out_vals, out_count, as_stream(stream));
 }
+
+// logits in, float32 sigmoid probabilities ranked (ml_recommend.py:78-104): the sigmoid is applied on the fly, so the
+// C-wide probability rows are never written.  n <= 128.
+int cc_topn_masked_sigmoid_f32(const float* logits, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
+                               const int32_t* mask_idx, int mode_only_listed, int descending, int32_t n,
+                               int32_t* out_ids, float* out_probs, int32_t* out_count, void* stream) {
+  CC_REQUIRE(logits && mask_ptr && out_ids, "cc_topn_masked_sigmoid_f32: null pointer");
+  CC_REQUIRE(num_cards > 0 && batch >= 0 && n > 0 && ld >= num_cards, "cc_topn_masked_sigmoid_f32: bad sizes");
+  CC_REQUIRE(n <= WS_MAX_N, "cc_topn_masked_sigmoid_f32: n must be <= %d (use cc_sigmoid_f32 + cc_topn_masked_f32)", WS_MAX_N);
+  if (batch == 0) return CC_OK;
+  return warpselect_launch<true>(logits, ld, num_cards, batch, mask_ptr, mask_idx, mode_only_listed, descending, n,
+                                 out_ids, out_probs, out_count, as_stream(stream));
+}
+
+// 1 = keep float32 top-N on the radix-select kernel even for small n (tests compare the two kernels)
+int cc_topn_set_force_radix(int on) { g_topn_force_radix = on ? 1 : 0; return CC_OK; }
 
 int cc_topn_masked_f64(const double* scores, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
                        const int32_t* mask_idx, int mode_only_listed, int descending, int32_t n, void* workspace,

@@ -128,8 +128,12 @@ def create_adjacency_matrix_host(csr: CubeCSR, force_diag=None, return_counts=Fa
 
 # --------------------------------------------------------------------------- top-N
 def topn_masked(scores: torch.Tensor, mask_ptr: torch.Tensor, mask_idx: torch.Tensor, n: int, *,
-                only_listed=False, descending=True, want_vals=True):
-    """Rank each row of ``scores`` (float32 or float64, (batch, >=C)); see cc_topn_masked_*."""
+                only_listed=False, descending=True, want_vals=True, sigmoid=False, out=None):
+    """Rank each row of ``scores`` (float32 or float64, (batch, >=C)); see cc_topn_masked_*.
+
+    ``sigmoid=True`` (float32, n <= 128): ``scores`` are logits, the ranking and the returned values are
+    their float32 sigmoid probabilities, computed on the fly (cc_topn_masked_sigmoid_f32).
+    ``out=(ids, vals, cnt)``: write into caller-owned (batch, n) / (batch,) tensors instead of allocating."""
     lib = _lib.load()
     batch = scores.shape[0]
     c = int(scores.shape[1])
@@ -137,9 +141,18 @@ def topn_masked(scores: torch.Tensor, mask_ptr: torch.Tensor, mask_idx: torch.Te
     is64 = scores.dtype == torch.float64
     if scores.dtype not in (torch.float32, torch.float64):
         raise TypeError("scores must be float32 or float64")
-    ids = torch.empty((batch, n), dtype=torch.int32, device=dev)
-    vals = torch.empty((batch, n), dtype=scores.dtype, device=dev) if want_vals else None
-    cnt = torch.empty(batch, dtype=torch.int32, device=dev)
+    if out is not None:
+        ids, vals, cnt = out
+    else:
+        ids = torch.empty((batch, n), dtype=torch.int32, device=dev)
+        vals = torch.empty((batch, n), dtype=scores.dtype, device=dev) if want_vals else None
+        cnt = torch.empty(batch, dtype=torch.int32, device=dev)
+    if sigmoid:
+        if is64:
+            raise TypeError("the fused sigmoid select ranks float32 logits")
+        call("cc_topn_masked_sigmoid_f32", ptr(scores), scores.stride(0), c, batch, ptr(mask_ptr), ptr(mask_idx),
+             int(only_listed), int(descending), n, ptr(ids), ptr(vals), ptr(cnt), stream_ptr())
+        return ids, vals, cnt
     wsb = lib.cc_topn_workspace_bytes(c, batch, n, int(is64))
     ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
     call("cc_topn_masked_f64" if is64 else "cc_topn_masked_f32", ptr(scores), scores.stride(0), c, batch,

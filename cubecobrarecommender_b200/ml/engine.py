@@ -80,10 +80,23 @@ class DAEEngine:
         self.reg_len = torch.ones(max(R, 1), dtype=torch.int32, device=d)
         self.overflow = torch.zeros(1, dtype=torch.int32, device=d)
         self.flips = torch.zeros(B, dtype=torch.int32, device=d)
-        # activations (encoder runs main rows then reg rows in one matrix)
-        self.a = [e(T, w) for w in HIDDEN]                          # a1..a4
-        self.md = [e(B, w) for w in (128, 256, 512)]
-        self.rd = [e(max(R, 1), w) for w in (128, 256, 512)]
+        # activations (encoder runs main rows then reg rows in one matrix).  Every activation buffer carries a
+        # column of ones right after its last feature (row stride = width + 4): the weight-gradient GEMM then runs
+        # on [x | 1]^T dY, whose extra last row IS the bias gradient -- no separate column-sum kernels.
+        def act(rows, w):
+            buf = torch.zeros((rows, w + 4), dtype=f32, device=d)
+            buf[:, w] = 1.0
+            return buf
+        self.a_buf = [act(T, w) for w in HIDDEN]                    # a1..a4 with their ones column
+        self.md_buf = [act(B, w) for w in (128, 256, 512)]
+        self.rd_buf = [act(max(R, 1), w) for w in (128, 256, 512)]
+        self.a = [b_[:, :w] for b_, w in zip(self.a_buf, HIDDEN)]
+        self.md = [b_[:, :w] for b_, w in zip(self.md_buf, (128, 256, 512))]
+        self.rd = [b_[:, :w] for b_, w in zip(self.rd_buf, (128, 256, 512))]
+        # the same activations widened by their column of ones: A operands of the [x | 1]^T dY gradient GEMMs
+        self.a_1 = [b_[:, :w + 1] for b_, w in zip(self.a_buf, HIDDEN)]
+        self.md_1 = [b_[:, :w + 1] for b_, w in zip(self.md_buf, (128, 256, 512))]
+        self.rd_1 = [b_[:, :w + 1] for b_, w in zip(self.rd_buf, (128, 256, 512))]
         self.z1 = e(B, self.cpad)                                    # logits -> dlogits in place
         self.z2 = e(max(R, 1), self.cpad)
         self.ga = [e(T, w) for w in HIDDEN]
@@ -196,9 +209,10 @@ class DAEEngine:
             if tc and prefix == "main":
                 # fused 512 -> C layer + sigmoid-BCE: logits stay in TMEM, only dlogits are written
                 from . import tensorcore
-                with self._timed("big_gemm"):
+                with self._timed("big_gemm"):       # the epilogue also reduces dlogits' columns into the bias gradient
                     tensorcore.gemm_bce(h, W(names[3] + "/kernel"), P(names[3] + "/bias"), self.y_bits,
-                                        float(self.global_B) * float(self.C), self.z1, self.bce_partial, precision=pr)
+                                        float(self.global_B) * float(self.C), self.z1, self.bce_partial, precision=pr,
+                                        dbias=G(names[3] + "/bias"))
                 bce_rows, bce_n = self.bce_partial, self.bce_partial.numel()
             else:
                 with self._timed("big_gemm"):
@@ -222,29 +236,31 @@ class DAEEngine:
         n_launch += 1
         # ---------------- backward: decoders ----------------
         ga4 = self.ga[3]
-        gtowers = [("main", self.a[3][:B], self.md, self.gmd, self.z1, ga4[:B])]
+        GKB = s.g_kernel_and_bias           # (in + 1, out) view: kernel gradient rows + the bias gradient row
+        gtowers = [("main", self.a[3][:B], self.a_1[3][:B], self.md, self.md_1, self.gmd, self.z1, ga4[:B])]
         if R:
-            gtowers.append(("reg", self.a[3][B:], self.rd, self.grd, self.z2, ga4[B:]))
-        for prefix, h_in, acts, gacts, dz, g_in in gtowers:
+            gtowers.append(("reg", self.a[3][B:], self.a_1[3][B:], self.rd, self.rd_1, self.grd, self.z2, ga4[B:]))
+        for prefix, h_in, h_in_1, acts, acts_1, gacts, dz, g_in in gtowers:
             names = dec_names(prefix)
             dzc = dz[:, :self.C]
             with self._timed("big_gemm"):
                 gemm(acts[2], dzc, G(names[3] + "/kernel"), transa=True, precision=pr)
-            with self._timed("colsum_big"):
-                colsum(dzc, G(names[3] + "/bias"), self.cs_ws)
+            n_launch += 1
+            if not (tc and prefix == "main"):       # (the fused BCE epilogue already produced the main tower's)
+                with self._timed("colsum_big"):
+                    colsum(dzc, G(names[3] + "/bias"), self.cs_ws)
+                n_launch += 2
             with self._timed("big_gemm"):
                 gemm(dzc, W(names[3] + "/kernel"), gacts[2], transb=True, mask=acts[2], precision=pr, round_out=tc)
-            n_launch += 4
+            n_launch += 1
             for i in (2, 1):
-                gemm(acts[i - 1], gacts[i], G(names[i] + "/kernel"), transa=True, precision=pr)
-                colsum(gacts[i], G(names[i] + "/bias"), self.cs_ws)
+                gemm(acts_1[i - 1], gacts[i], GKB(names[i]), transa=True, precision=pr)
                 gemm(gacts[i], W(names[i] + "/kernel"), gacts[i - 1], transb=True, mask=acts[i - 1], precision=pr,
                      round_out=tc)
-                n_launch += 4
-            gemm(h_in, gacts[0], G(names[0] + "/kernel"), transa=True, precision=pr)
-            colsum(gacts[0], G(names[0] + "/bias"), self.cs_ws)
+                n_launch += 2
+            gemm(h_in_1, gacts[0], GKB(names[0]), transa=True, precision=pr)
             gemm(gacts[0], W(names[0] + "/kernel"), g_in, transb=True, mask=h_in, precision=pr, round_out=tc)
-            n_launch += 4
+            n_launch += 2
             self._grads_ready(prefix)
         if not R:
             for n_ in dec_names("reg"):
@@ -253,11 +269,10 @@ class DAEEngine:
         # ---------------- backward: shared encoder (main + reg rows together) ----------------
         for i in (3, 2, 1):
             name = ENC_NAMES[i]
-            gemm(self.a[i - 1], self.ga[i], G(name + "/kernel"), transa=True, precision=pr)
-            colsum(self.ga[i], G(name + "/bias"), self.cs_ws)
+            gemm(self.a_1[i - 1], self.ga[i], GKB(name), transa=True, precision=pr)
             gemm(self.ga[i], W(name + "/kernel"), self.ga[i - 1], transb=True, mask=self.a[i - 1], precision=pr,
                  round_out=tc)
-            n_launch += 4
+            n_launch += 2
         g1 = self.ga[0]
         colsum(g1, G("encoder_e1/bias"), self.cs_ws); n_launch += 2
         gw1 = G("encoder_e1/kernel")

@@ -37,23 +37,42 @@ class MLRecommender:
         call("cc_sigmoid_f32", ptr(full), ptr(full), full.numel(), stream_ptr())
         return z
 
-    def recommend(self, csr: CubeCSR, amount: int):
-        """Returns (add_ids int32 (K, n), add_scores float32 (K, n), counts int32 (K,)) on the host."""
+    FUSED_MAX_N = 128        # cc_topn_masked_sigmoid_f32's limit (warp-per-cube streaming select)
+
+    def recommend_device(self, csr: CubeCSR, amount: int):
+        """Device-resident form: the whole CSR is uploaded once, the cubes run through encoder, decoder and the
+        masked select in chunks of ``self.chunk`` with NO host synchronisation in between, and the results stay
+        on the device: (add_ids int32 (K, n), add_scores float32 (K, n), counts int32 (K,))."""
+        m = self.model
+        dev = m.device
         k = csr.num_cubes
         n = max(1, min(int(amount), csr.num_cards))
-        ids = np.full((k, n), -1, dtype=np.int32)
-        vals = np.zeros((k, n), dtype=np.float32)
-        cnts = np.zeros(k, dtype=np.int32)
-        dev = self.model.device
+        indptr = torch.from_numpy(np.ascontiguousarray(csr.indptr, dtype=np.int64)).to(dev, non_blocking=True)
+        idx_h = np.ascontiguousarray(csr.indices, dtype=np.int32)
+        indices = torch.from_numpy(idx_h if len(idx_h) else np.zeros(1, np.int32)).to(dev, non_blocking=True)
+        row_len = (indptr[1:] - indptr[:-1]).to(torch.int32)
+        ids = torch.empty((k, n), dtype=torch.int32, device=dev)
+        vals = torch.empty((k, n), dtype=torch.float32, device=dev)
+        cnts = torch.empty(k, dtype=torch.int32, device=dev)
+        fused = n <= self.FUSED_MAX_N
         for lo in range(0, k, self.chunk):
             hi = min(lo + self.chunk, k)
-            sub = csr.rows(np.arange(lo, hi))
-            probs = self.probabilities(sub)
-            mp = torch.from_numpy(sub.indptr).to(dev)
-            mi = torch.from_numpy(sub.indices if len(sub.indices) else np.zeros(1, np.int32)).to(dev)
-            i_, v_, c_ = topn_masked(probs, mp, mi, n, only_listed=False, descending=True)
-            ids[lo:hi] = i_.cpu().numpy(); vals[lo:hi] = v_.cpu().numpy(); cnts[lo:hi] = c_.cpu().numpy()
+            # rows lo..hi of the resident CSR: absolute offsets into `indices`, nothing is copied
+            sb = SparseBatch(indices, indptr[lo:hi], row_len[lo:hi])
+            z = m._decode(m._encode(sb), "main")
+            out = (ids[lo:hi], vals[lo:hi], cnts[lo:hi])
+            if fused:    # sigmoid applied inside the select: the probability rows are never written
+                topn_masked(z, indptr[lo:hi + 1], indices, n, sigmoid=True, out=out)
+            else:
+                full = z._base if z._base is not None else z
+                call("cc_sigmoid_f32", ptr(full), ptr(full), full.numel(), stream_ptr())
+                topn_masked(z, indptr[lo:hi + 1], indices, n, out=out)
         return ids, vals, cnts
+
+    def recommend(self, csr: CubeCSR, amount: int):
+        """Returns (add_ids int32 (K, n), add_scores float32 (K, n), counts int32 (K,)) on the host."""
+        ids, vals, cnts = self.recommend_device(csr, amount)
+        return ids.cpu().numpy(), vals.cpu().numpy(), cnts.cpu().numpy()
 
     def recommend_one(self, cube_indices, amount, int_to_card):
         """The ``{"additions": {...}, "cuts": {...}}`` dict of reference web/ml_recommend_web.py:48-67."""

@@ -82,6 +82,15 @@ class ParamStore:
     def p(self, key): return self.view(self.params, key)
     def g(self, key): return self.view(self.grads, key)
 
+    def g_kernel_and_bias(self, layer):
+        """Gradient of ``layer``'s kernel AND bias as one (in + 1, out) matrix: the bias follows its kernel in
+        the flat buffer, so the last row of  [x | 1]^T dY  lands exactly on the bias gradient."""
+        off, (fi, fo) = self.layout[layer + "/kernel"]
+        boff, _ = self.layout[layer + "/bias"]
+        if boff != off + fi * fo:
+            raise ValueError(f"{layer}: bias does not follow the kernel contiguously (in*out % 4 != 0)")
+        return self.grads[off:off + (fi + 1) * fo].view(fi + 1, fo)
+
     def num_parameters(self):
         return sum(int(np.prod(s)) for _, s in self.layout.values())
 

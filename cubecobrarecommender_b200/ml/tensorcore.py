@@ -32,12 +32,13 @@ def gemm(a, b, c, *, transa=False, transb=False, bias=None, relu=False, mask=Non
     return c
 
 
-def gemm_bce(a, w, bias, ybits, count, dz, loss_partial, precision="tf32", round_out=True):
-    """Fused  z = a @ w + bias -> BCE loss partials + dlogits  (z never stored)."""
+def gemm_bce(a, w, bias, ybits, count, dz, loss_partial, precision="tf32", round_out=True, dbias=None):
+    """Fused  z = a @ w + bias -> BCE loss partials + dlogits  (z never stored); ``dbias`` (optional, float [n])
+    receives the column sums of dlogits = the gradient of ``bias``."""
     m, k = a.shape
     n = w.shape[1]
     call("cc_gemm_bce_tc", PRECISION_CODE[precision], m, n, k, ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(bias),
-         ptr(ybits), ybits.stride(0), float(count), ptr(dz), dz.stride(0), ptr(loss_partial),
+         ptr(ybits), ybits.stride(0), float(count), ptr(dz), dz.stride(0), ptr(loss_partial), ptr(dbias),
          int(round_out and precision == "tf32"), stream_ptr())
 
 

@@ -102,6 +102,14 @@ int64_t cc_topn_workspace_bytes(int32_t num_cards, int32_t batch, int32_t n, int
 int cc_topn_masked_f32(const float* scores, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
                        const int32_t* mask_idx, int mode_only_listed, int descending, int32_t n, void* workspace,
                        int64_t workspace_bytes, int32_t* out_ids, float* out_vals, int32_t* out_count, void* stream);
+/* float32 with n <= 128 runs as a warp-per-cube streaming select (one pass over the row); larger n and float64 use
+ * the radix select / full bitonic ranking.  cc_topn_masked_sigmoid_f32 takes LOGITS, ranks sigmoid(logit) (the float32
+ * probabilities the reference ranks, ml_recommend.py:78-104) and returns the winners' probabilities; n <= 128.
+ * cc_topn_set_force_radix(1) pins float32 top-N to the radix kernel (tests compare the two). */
+int cc_topn_masked_sigmoid_f32(const float* logits, int64_t ld, int32_t num_cards, int32_t batch,
+                               const int64_t* mask_ptr, const int32_t* mask_idx, int mode_only_listed, int descending,
+                               int32_t n, int32_t* out_ids, float* out_probs, int32_t* out_count, void* stream);
+int cc_topn_set_force_radix(int on);
 int cc_topn_masked_f64(const double* scores, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
                        const int32_t* mask_idx, int mode_only_listed, int descending, int32_t n, void* workspace,
                        int64_t workspace_bytes, int32_t* out_ids, double* out_vals, int32_t* out_count, void* stream);
@@ -157,10 +165,12 @@ int cc_gemm_tc(int precision, int transa, int transb, int m, int n, int k, const
                int accumulate, int split_k, int tile_n, int round_tf32, void* stream);
 /* Fused decoder output layer + sigmoid-BCE (model.py:64,94 + train.py:85): z = A[M,K] W[K,N] + bias is
  * never stored; dz[M][lddz] = (sigmoid(z) - y)/count (columns [N, lddz) zeroed, lddz % 32 == 0), loss_partial
- * float64 [cc_gemm_bce_partial_count(m, lddz)] holds per-(tile, warp) loss sums for cc_loss_finalize. */
+ * float64 [cc_gemm_bce_partial_count(m, lddz)] holds per-(tile, warp) loss sums for cc_loss_finalize.  dbias (nullable,
+ * float [n]) receives the column sums of dz, i.e. the gradient of the layer's bias (zeroed, then accumulated with float
+ * atomics by the epilogue: summation order, hence the last bits, can differ between runs). */
 int cc_gemm_bce_tc(int precision, int m, int n, int k, const void* a, int64_t lda, const void* w, int64_t ldw,
                    const float* bias, const uint32_t* ybits, int64_t ywords, double count, float* dz, int64_t lddz,
-                   double* loss_partial, int round_tf32, void* stream);
+                   double* loss_partial, float* dbias, int round_tf32, void* stream);
 int64_t cc_gemm_bce_partial_count(int m, int lddz);
 /* CTA-pair tiling of the tcgen05 GEMMs (256 x 256 tiles on two SMs, tcgen05.mma.cta_group::2):
  * -1 = the planner decides per problem (default), 0 = never, 1 = whenever the shape allows it. */

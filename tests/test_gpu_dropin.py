@@ -89,6 +89,10 @@ def test_ml_recommend_batched(precision):
         assert cnt[r] == len(expect)
         assert ids[r, :cnt[r]].tolist() == expect                   # ids bit-exact, ties included
         assert np.array_equal(vals[r, :cnt[r]], probs[r][expect])
+    ids2, vals2, cnt2 = rec.recommend(csr, 200)      # n > 128: sigmoid pass + radix select instead of the fused select
+    for r in range(k):
+        expect = od.rank_additions(probs[r], dense[r], 200)
+        assert cnt2[r] == len(expect) and ids2[r, :cnt2[r]].tolist() == expect
     i2c = {i: f"card{i}" for i in range(c)}
     out = rec.recommend_one([int(v) for v in lists[5]], 7, i2c)
     assert list(out) == ["additions", "cuts"] and len(out["additions"]) == 7

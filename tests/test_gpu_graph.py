@@ -144,8 +144,10 @@ def test_golden_recs_and_cuts(graph_golden, pairwise_golden):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-@pytest.mark.parametrize("n", [1, 50, 2048, 3000])
+@pytest.mark.parametrize("n", [1, 50, 128, 129, 2048, 3000])
 def test_topn_masked_ties_and_full_ranking(dtype, n):
+    """float32 with n <= 128 runs the warp-per-cube streaming select, larger n / float64 the radix select and the
+    full bitonic ranking: all three against numpy's stable argsort under the documented tie rule."""
     rng = np.random.default_rng(7)
     c, batch = 5000, 6
     # heavy ties: scores drawn from 40 distinct values, plus -0.0/+0.0
@@ -176,3 +178,58 @@ def test_topn_masked_ties_and_full_ranking(dtype, n):
         assert cnt[b] == len(expect)
         assert np.array_equal(ids[b][:cnt[b]], expect)
         assert (ids[b][cnt[b]:] == -1).all()
+
+
+@pytest.mark.parametrize("c,batch,n", [(5000, 6, 50), (4999, 11, 128), (97, 3, 7), (20884, 9, 50)])
+def test_topn_streaming_select_equals_radix_select(c, batch, n):
+    """The two float32 kernels implement one total order (score, then index): identical ids and values on
+    heavy ties, on ascending-sorted rows (every element beats the running threshold: worst case for the
+    streaming select), on descending rows, and when the mask leaves fewer than n candidates."""
+    from cubecobrarecommender_b200 import _lib
+    rng = np.random.default_rng(c + n)
+    vals = rng.integers(0, 30, size=(batch, c)).astype(np.float32) / 4 - 3
+    vals[0] = np.sort(rng.standard_normal(c).astype(np.float32))              # ascending
+    if batch > 1:
+        vals[1] = np.sort(rng.standard_normal(c).astype(np.float32))[::-1]    # descending
+    lists = [np.sort(rng.choice(c, size=rng.integers(0, min(c, 700)), replace=False)) for _ in range(batch)]
+    lists[-1] = np.arange(3, c)                                               # only 3 candidates left
+    csr = CubeCSR.from_lists(lists, c)
+    mp = torch.from_numpy(csr.indptr).cuda(); mi = torch.from_numpy(csr.indices).cuda()
+    scores = torch.from_numpy(vals).cuda()
+    for only_listed, desc in ((False, True), (True, False), (False, False), (True, True)):
+        a = G.topn_masked(scores, mp, mi, n, only_listed=only_listed, descending=desc)
+        _lib.call("cc_topn_set_force_radix", 1)
+        try:
+            b = G.topn_masked(scores, mp, mi, n, only_listed=only_listed, descending=desc)
+        finally:
+            _lib.call("cc_topn_set_force_radix", 0)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    # numpy cross-check of the descending / not-listed case
+    ids, v, cnt = (t.cpu().numpy() for t in G.topn_masked(scores, mp, mi, n))
+    for r in range(batch):
+        order = vals[r].argsort(kind="stable")[::-1]
+        inm = np.zeros(c, bool); inm[lists[r]] = True
+        expect = [i for i in order if not inm[i]][:n]
+        assert cnt[r] == len(expect) and np.array_equal(ids[r][:cnt[r]], expect)
+        assert (ids[r][cnt[r]:] == -1).all()
+
+
+def test_topn_fused_sigmoid_equals_sigmoid_then_select():
+    """cc_topn_masked_sigmoid_f32 ranks float32 sigmoid(logit) computed on the fly: same ids and the same
+    probability bits as cc_sigmoid_f32 followed by cc_topn_masked_f32 (saturated logits tie at exactly 1.0)."""
+    from cubecobrarecommender_b200._lib import call, ptr, stream_ptr
+    rng = np.random.default_rng(3)
+    c, batch, n = 3001, 13, 50
+    z = (rng.standard_normal((batch, c)) * 12).astype(np.float32)            # many saturate to 1.0 / underflow to 0
+    lists = [np.sort(rng.choice(c, size=rng.integers(1, 500), replace=False)) for _ in range(batch)]
+    csr = CubeCSR.from_lists(lists, c)
+    mp = torch.from_numpy(csr.indptr).cuda(); mi = torch.from_numpy(csr.indices).cuda()
+    logits = torch.from_numpy(z).cuda()
+    fused = G.topn_masked(logits, mp, mi, n, sigmoid=True)
+    probs = torch.empty_like(logits)
+    call("cc_sigmoid_f32", ptr(logits), ptr(probs), logits.numel(), stream_ptr())
+    two_pass = G.topn_masked(probs, mp, mi, n)
+    for x, y in zip(fused, two_pass):
+        assert torch.equal(x, y)
+    assert (fused[1] == 1.0).any()          # the tie rule was exercised on saturated scores
