@@ -71,6 +71,13 @@ __device__ __forceinline__ float rn_tf32(float x) {
   return __uint_as_float(r);
 }
 
+// the same rounding (nearest, ties away from zero) as two integer operations: add half a tf32 ulp to the
+// magnitude bits, clear the 13 low bits (cvt.rna.tf32.f32 expands to more, with Inf/NaN handling the gradients
+// and activations rounded in the GEMM epilogues never need)
+__device__ __forceinline__ float rn_tf32_bits(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
 // sigmoid of a logit as the recommenders report it (reference ml_recommend.py:78-80 reads float32 sigmoid
 // outputs); ONE definition, so the fused select and the standalone sigmoid pass give identical bits
 __device__ __forceinline__ float sigmoid_f32(float z) { return 1.f / (1.f + expf(-z)); }

@@ -13,7 +13,7 @@
 //   warp 1   MMA issuer : one elected lane issues tcgen05.mma (128 x BN x 8|16), commits to
 //            the stage's "empty" mbarrier and, per tile, to the accumulator's "full" barrier
 //   warp 2   TMEM allocator (2 accumulator buffers: MMA of tile i+1 overlaps epilogue of tile i)
-//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns -> bias/ReLU/mask or BCE -> swizzled
+//   warps 4-11 epilogue: tcgen05.ld 32 lanes x 32 columns -> bias/ReLU/mask or BCE -> swizzled
 //            smem staging -> TMA store (or TMA reduce-add for split-K), so global writes are
 //            full 128-byte lines issued by the copy engine, not by the warps
 // Operands may be K-major ([rows, K], K contiguous) or MN-major ([K, rows], rows contiguous);
@@ -32,9 +32,10 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int NUM_ACC = 2;
-constexpr int THREADS = 256;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 128 + 32 * EPI_WARPS;           // warps 0-3: TMA producer, MMA issuer, TMEM allocator, idle
 constexpr int STAGE_A_BYTES = BM * 128;                 // 128 rows x one 128-byte swizzle row
-constexpr int EPI_STAGE_BYTES = 4 * 2 * 4096;           // 4 warps x 2 buffers x (32 rows x 128 B)
+constexpr int EPI_STAGE_BYTES = EPI_WARPS * 4096;       // one (32 rows x 128 B) staging buffer per epilogue warp
 constexpr int BAR_BYTES = 256;
 
 // CTAS = 2: a CTA pair (cluster of two SMs of one TPC) works on a 256 x BN tile with
@@ -64,7 +65,7 @@ struct Params {
   // EPI_BCE
   const uint32_t* ybits; long long ywords;
   float inv_count;
-  double* loss_partial;                  // [tiles][4 warps]
+  double* loss_partial;                  // [tiles][EPI_WARPS]
   float* dbias;                          // EPI_BCE: column sums of dlogits (= the output layer's bias gradient), atomically added
   int a_mn_major, b_mn_major;
   // EPI_COUNT: C = A A^T is symmetric -> only tiles with nt >= mt are computed (square 256 x 256 pair tiles) and every
@@ -252,7 +253,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < NUM_ACC; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4 * CTAS); }
+    for (int a = 0; a < NUM_ACC; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EPI_WARPS * CTAS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -369,10 +370,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
+    // ===================== epilogue (8 warps) =====================
+    // A warp may only read the TMEM lane quarter warp % 4, so warps w and w + 4 share a 32-row quarter and split
+    // the tile's columns in halves.  Two epilogue warps per scheduler hide each other's latencies (TMEM loads,
+    // MUFU chains, staging-buffer turnaround); with one warp per scheduler the fused BCE epilogue was the
+    // bottleneck of its GEMM (16 us per 128 x 256 tile against 10 us for the MMAs).
     const int q = warp & 3;
-    uint8_t* stage_buf = epi_smem + q * 8192;             // two 4 KB buffers (32 rows x 128 B, 128B-swizzled)
-    int buf = 0;
+    const int half = (warp - 4) >> 2;
+    constexpr int NCH = BN / 64;                            // 32-column chunks per warp
+    uint8_t* sbuf = epi_smem + (warp - 4) * 4096;           // one 4 KB staging buffer (32 rows x 128 B, 128B-swizzled)
     int acc = 0; uint32_t acc_phase = 0;
     const uint32_t leader_tmem_empty = CTAS == 2 ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : 0u;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
@@ -382,50 +388,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int row0 = (mt * CTAS + cta_rank) * BM + q * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.m;
-      // operands of the epilogue that live in global memory (the tile's bias slice, and for BCE this row's y bits:
-      // BN/32 consecutive words = one or two 16-byte loads) are fetched for the WHOLE tile while its MMAs still
-      // run, so no chunk of the epilogue waits on a global load.
-      // Lane l holds the bias of column col0 + l; element j of the chunk gets it by shuffle from lane j.
-      float bias_r[BN / 32];
-      uint32_t y_r[BN / 32];
+      const int colw = nt * BN + half * (BN / 2);           // first column of this warp's half of the tile
+      // operands of the epilogue that live in global memory (the bias slice, and for BCE this row's y bits: NCH
+      // consecutive words) are fetched for the warp's whole half tile while its MMAs still run, so no chunk waits
+      // on a global load.  Lane l holds the bias of column col0 + l; element j gets it by shuffle from lane j.
+      float bias_r[NCH];
+      uint32_t y_r[NCH];
 #pragma unroll
-      for (int cb = 0; cb < BN / 32; ++cb) {
-        const int col = nt * BN + cb * 32 + lane;
+      for (int cb = 0; cb < NCH; ++cb) {
+        const int col = colw + cb * 32 + lane;
         bias_r[cb] = (p.bias && col < p.n) ? __ldg(p.bias + col) : 0.f;
         y_r[cb] = 0u;
       }
       if (EPI == EPI_BCE && row_ok) {
-        const uint32_t* yrow = p.ybits + (long long)row * p.ywords + ((nt * BN) >> 5);
-        if (nt * BN + BN <= p.ywords * 32 && (((long long)row * p.ywords) & 3) == 0 &&
-            (reinterpret_cast<uintptr_t>(p.ybits) & 15) == 0) {
-#pragma unroll
-          for (int q4 = 0; q4 < BN / 128; ++q4) {
-            const uint4 w = __ldg(reinterpret_cast<const uint4*>(yrow) + q4);
-            y_r[4 * q4] = w.x; y_r[4 * q4 + 1] = w.y; y_r[4 * q4 + 2] = w.z; y_r[4 * q4 + 3] = w.w;
-          }
+        const uint32_t* yrow = p.ybits + (long long)row * p.ywords + (colw >> 5);
+        const bool in_range = colw + BN / 2 <= p.ywords * 32;
+        if (NCH == 4 && in_range && ((reinterpret_cast<uintptr_t>(yrow) & 15) == 0)) {
+          const uint4 w = __ldg(reinterpret_cast<const uint4*>(yrow));
+          y_r[0] = w.x; y_r[1] = w.y; y_r[NCH > 2 ? 2 : 0] = w.z; y_r[NCH > 2 ? 3 : 0] = w.w;
         } else {
 #pragma unroll
-          for (int cb = 0; cb < BN / 32; ++cb)
-            if (nt * BN + cb * 32 < p.n_store) y_r[cb] = __ldg(yrow + cb);
+          for (int cb = 0; cb < NCH; ++cb)
+            if (colw + cb * 32 < p.n_store) y_r[cb] = __ldg(yrow + cb);
         }
       }
+      const float inv_row = row_ok ? p.inv_count : 0.f;     // rows beyond m: zero gradient (they feed the column sums)
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       float row_loss = 0.f;
-      // The BCE body is ~800 instructions per 32-column chunk: unrolling it 8x overflows the instruction cache
-      // (measured: 300 -> 442 us), so it stays a rolled loop and the prefetched registers are ROTATED instead
-      // of indexed (static index 0 every iteration); the short store body is fully unrolled.
-#pragma unroll(EPI == EPI_BCE ? 1 : BN / 32)
-      for (int cb = 0; cb < BN / 32; ++cb) {
-        const int col0 = nt * BN + cb * 32;
+      // The BCE body is long (a rolled loop keeps it inside the instruction cache: unrolling it 8x cost 300 -> 442 us),
+      // so the prefetched registers are ROTATED instead of indexed; the short store body is fully unrolled.
+#pragma unroll(EPI == EPI_BCE ? 1 : NCH)
+      for (int cb = 0; cb < NCH; ++cb) {
+        const int col0 = colw + cb * 32;
         if (col0 >= p.n_store || row0 >= p.m || !has_k) break;      // warp-uniform
         uint32_t v[32];
         __syncwarp();
-        tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + cb * 32), v);
+        tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + half * (BN / 2) + cb * 32), v);
         const float b_cur = bias_r[0];
         const uint32_t ybw = y_r[0];
 #pragma unroll
-        for (int r = 0; r + 1 < BN / 32; ++r) { bias_r[r] = bias_r[r + 1]; y_r[r] = y_r[r + 1]; }
+        for (int r = 0; r + 1 < NCH; ++r) { bias_r[r] = bias_r[r + 1]; y_r[r] = y_r[r + 1]; }
         float out[32];
         if (EPI == EPI_COUNT) {
           // int32 accumulators pass through bit for bit; an off-diagonal tile is also written transposed
@@ -443,27 +446,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
         } else if (EPI == EPI_BCE) {
-          const bool full = col0 + 32 <= p.n;           // warp-uniform: only the last column tile is ragged
+          // softplus(z) - z*y and sigmoid(z) from one exp: e = exp(-|z|) (ex2, rcp, lg2: 3 MUFU ops per element)
+          auto bce_elem = [&](int j, float& l, float& g) {
+            const float z = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, b_cur, j);
+            const float y = float((ybw >> j) & 1u);
+            const float e = exp2f_approx(-1.4426950408889634f * fabsf(z));
+            const float s1 = 1.f + e;
+            const float r = rcp_approx(s1);
+            l = fmaf(-z, y, fmaxf(z, 0.f)) + 0.6931471805599453f * lg2_approx(s1);
+            g = ((z >= 0.f ? r : e * r) - y) * inv_row;
+          };
+          if (col0 + 32 <= p.n) {                       // warp-uniform: only the last column tile is ragged
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            {
-              const float z = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, b_cur, j);
-              const float y = float((ybw >> j) & 1u);
-              // softplus(z) - z*y and sigmoid(z) from one exp: e = exp(-|z|) (ex2, rcp, lg2: 3 MUFU ops)
-              const float e = exp2f_approx(-1.4426950408889634f * fabsf(z));
-              const float s1 = 1.f + e;
-              const float r = rcp_approx(s1);
-              const float l = fmaf(-z, y, fmaxf(z, 0.f)) + 0.6931471805599453f * lg2_approx(s1);
-              float g = ((z >= 0.f ? r : e * r) - y) * p.inv_count;
-              if (!full) {
-                const bool live = (col0 + j < p.n);
-                row_loss += live ? l : 0.f;
-                g = live ? g : 0.f;
-              } else {
-                row_loss += l;
-              }
-              g = row_ok ? g : 0.f;              // rows beyond m are clipped by the store but feed the column sums
-              out[j] = p.round_tf32 ? rn_tf32(g) : g;
+            for (int j = 0; j < 32; ++j) {
+              float l, g;
+              bce_elem(j, l, g);
+              row_loss += l;
+              out[j] = p.round_tf32 ? rn_tf32_bits(g) : g;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float l, g;
+              bce_elem(j, l, g);
+              const bool live = (col0 + j < p.n);
+              row_loss += live ? l : 0.f;
+              g = live ? g : 0.f;
+              out[j] = p.round_tf32 ? rn_tf32_bits(g) : g;
             }
           }
         } else {
@@ -482,12 +491,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           if (p.round_tf32) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) out[j] = rn_tf32(out[j]);
+            for (int j = 0; j < 32; ++j) out[j] = rn_tf32_bits(out[j]);
           }
         }
         // registers -> swizzled staging (row = lane, 16-byte chunk c at position c ^ (lane & 7)) -> TMA store
-        uint8_t* sbuf = stage_buf + buf * 4096;
-        if (lane == 0) tma_wait_group_read<1>();        // the store that last read this buffer has drained
+        if (lane == 0) tma_wait_group_read<0>();        // the store that last read this buffer has drained
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < 8; ++c)
@@ -510,13 +518,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             cs += *reinterpret_cast<const float*>(sbuf + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
           if (col0 + lane < p.n) atomicAdd(p.dbias + col0 + lane, cs);
         }
-        buf ^= 1;
       }
       if (EPI == EPI_BCE) {
         // one float64 partial per (tile, warp): fixed summation order downstream
         const float s = row_ok ? row_loss : 0.f;
         const double d = warp_sum(double(s));
-        if (lane == 0) p.loss_partial[((long long)tile * CTAS + cta_rank) * 4 + q] = d;
+        if (lane == 0) p.loss_partial[((long long)tile * CTAS + cta_rank) * EPI_WARPS + (warp - 4)] = d;
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -824,7 +831,9 @@ int cc_gemm_bce_tc(int precision, int m, int n, int k, const void* a, int64_t ld
 
 // one float64 per (128-row block, 256-column tile, epilogue warp); sized for the CTA-pair tiling (256-row
 // tiles, both CTAs) -- entries a launch does not cover stay untouched (the caller zero-initialises once)
-int64_t cc_gemm_bce_partial_count(int m, int lddz) { return int64_t(ceil_div(m, 2 * tc::BM)) * 2 * ceil_div(lddz, 256) * 4; }
+int64_t cc_gemm_bce_partial_count(int m, int lddz) {
+  return int64_t(ceil_div(m, 2 * tc::BM)) * 2 * ceil_div(lddz, 256) * tc::EPI_WARPS;
+}
 
 // Co-occurrence counts cnt = X^T X on the tensor cores (reference src/non_ml/utils.py:82-84): the cubes of a chunk
 // are expanded to a K-major byte matrix X^T [C][chunk] and contracted with tcgen05.mma kind::i8 (0/1 bytes, int32

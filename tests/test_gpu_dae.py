@@ -210,13 +210,16 @@ def test_gemm_bce_fused_epilogue_vs_oracle(m, c, pair, pair_mode):
     yb = torch.tensor(_bits_from_dense(y)).cuda()
     dz = torch.full((m, cpad), 9.0, device="cuda")
     part = torch.zeros(TC.bce_partial_count(m, cpad), dtype=torch.float64, device="cuda")
-    TC.gemm_bce(a, w, bias, yb, float(m * c), dz, part, precision="tf32", round_out=False)
+    dbias = torch.full((c,), 5.0, device="cuda")
+    TC.gemm_bce(a, w, bias, yb, float(m * c), dz, part, precision="tf32", round_out=False, dbias=dbias)
     z = (a.double() @ w.double() + bias.double()).cpu().numpy()
     ref_loss = od.bce_from_logits_np(z, y)
     assert abs(part.sum().item() / (m * c) - ref_loss) / ref_loss < 1e-5
     ref_dz = (1 / (1 + np.exp(-z)) - y) / (m * c)
     assert np.abs(dz[:, :c].cpu().numpy() - ref_dz).max() < 2e-6 / (m * c) * 1e3 + 1e-9
     assert (dz[:, c:] == 0).all()
+    # bias gradient = column sums of dlogits, reduced by the epilogue (float atomics over 32-row blocks)
+    assert np.abs(dbias.cpu().numpy() - ref_dz.sum(0)).max() < 2e-6 * np.abs(ref_dz.sum(0)).max() + 1e-12
 
 
 # tf32: the north-star bar is the per-step loss (1e-3 relative).  Gradients are held to 1e-2 of their max on
