@@ -68,6 +68,7 @@ struct Params {
   double* loss_partial;                  // [tiles][EPI_WARPS]
   float* dbias;                          // EPI_BCE: column sums of dlogits (= the output layer's bias gradient), atomically added
   int a_mn_major, b_mn_major;
+  int* sched;                            // {next-tile counter, finished units}: self-resetting (see TileRing)
   // EPI_COUNT: C = A A^T is symmetric -> only tiles with nt >= mt are computed (square 256 x 256 pair tiles) and every
   // off-diagonal tile is also written transposed
   int symmetric;
@@ -139,6 +140,47 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) break;
+    if (++spins > (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ void st_shared_cluster_u32(uint32_t cluster_addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+
+// ---- dynamic tile scheduler ------------------------------------------------------------------------------
+// Tiles are handed out at run time: unit u (a CTA, or a CTA pair) starts on tile u and then draws further tiles
+// from a global atomic counter, so a unit that starts late or shares its SM (an NCCL all_reduce overlapping
+// backward) simply takes fewer tiles instead of stretching the whole kernel.  One scheduler thread per unit
+// (warp 3 of the leader CTA) publishes tile ids through a small shared-memory ring to the unit's TMA producer(s),
+// MMA issuer and epilogue warps; -1 ends the kernel.  The counters reset themselves: the unit that draws the last
+// terminal value zeroes them for the next launch.
+constexpr int SCHED_DEPTH = 4;
+struct TileRing {
+  uint64_t* full;        // [SCHED_DEPTH]  scheduler -> consumers (count 1)
+  uint64_t* empty;       // [SCHED_DEPTH]  consumers -> scheduler (lives in the leader CTA)
+  volatile int* ids;     // [SCHED_DEPTH]
+  uint32_t empty_cluster_addr;   // leader's `empty` array in cluster address space (pairs), 0 otherwise
+  int slot; uint32_t phase;
+};
+template <int CTAS>
+__device__ __forceinline__ int ring_next(TileRing& r) {
+  if (CTAS == 2) mbar_wait_cluster(&r.full[r.slot], r.phase); else mbar_wait(&r.full[r.slot], r.phase);
+  const int t = r.ids[r.slot];
+  if (CTAS == 2) mbar_arrive_cluster(r.empty_cluster_addr + r.slot * 8); else mbar_arrive(&r.empty[r.slot]);
+  if (++r.slot == SCHED_DEPTH) { r.slot = 0; r.phase ^= 1; }
+  return t;
 }
 
 template <int CTAS>
@@ -237,14 +279,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + NUM_ACC;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + NUM_ACC);
+  uint64_t* sched_full = tmem_empty + NUM_ACC;
+  uint64_t* sched_empty = sched_full + SCHED_DEPTH;
+  int* sched_ids = reinterpret_cast<int*>(sched_empty + SCHED_DEPTH);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched_ids + SCHED_DEPTH);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // tiles of (BM*CTAS) x BN; the symmetric count GEMM only visits the upper triangle of its square tile grid
   const int total_tiles = p.symmetric ? (p.n_tiles * (p.n_tiles + 1)) / 2 : p.m_tiles * p.n_tiles * p.split_k;
   const int cta_rank = CTAS == 2 ? int(cluster_ctarank()) : 0;
-  const int first_tile = CTAS == 2 ? int(blockIdx.x >> 1) : int(blockIdx.x);
-  const int tile_step = CTAS == 2 ? int(gridDim.x >> 1) : int(gridDim.x);
+  const int unit = CTAS == 2 ? int(blockIdx.x >> 1) : int(blockIdx.x);       // scheduling unit: CTA or CTA pair
+  const int num_units = CTAS == 2 ? int(gridDim.x >> 1) : int(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -254,6 +299,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < NUM_ACC; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EPI_WARPS * CTAS); }
+    // ring consumers: per CTA its TMA producer and epilogue warps, plus the leader's MMA issuer
+    for (int d = 0; d < SCHED_DEPTH; ++d) { mbar_init(&sched_full[d], 1); mbar_init(&sched_empty[d], (1 + EPI_WARPS) * CTAS + 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -270,12 +317,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  TileRing ring{sched_full, sched_empty, sched_ids, CTAS == 2 ? mapa_shared(smem_u32(sched_empty), 0) : 0u, 0, 0u};
+  const bool dynamic = p.sched != nullptr;
+  // static mode: unit u walks tiles u, u + num_units, ... with no ring traffic at all
+  auto next_tile = [&](int cur) -> int {
+    if (dynamic) return ring_next<CTAS>(ring);
+    const int t = cur < 0 ? unit : cur + num_units;
+    return t < total_tiles ? t : -1;
+  };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+      for (int tile = next_tile(-1); tile >= 0; tile = next_tile(tile)) {
         int mt, nt, ks;
         decode_tile(p, tile, mt, nt, ks);
         const int kb0 = ks * p.k_blocks;
@@ -343,7 +398,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t a_kstep = p.a_mn_major ? UMMA_K * 128 : 32, b_kstep = p.b_mn_major ? UMMA_K * 128 : 32;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+      for (int tile = next_tile(-1); tile >= 0; tile = next_tile(tile)) {
         int mt_, nt_, ks;
         decode_tile(p, tile, mt_, nt_, ks);
         const int kb0 = ks * p.k_blocks;
@@ -369,6 +424,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if (warp == 3) {
+    // ===================== tile scheduler (leader CTA only) =====================
+    if (lane == 0 && cta_rank == 0 && dynamic) {
+      const uint32_t peer_ids = CTAS == 2 ? mapa_shared(smem_u32(sched_ids), 1) : 0u;
+      const uint32_t peer_full = CTAS == 2 ? mapa_shared(smem_u32(sched_full), 1) : 0u;
+      int slot = 0; uint32_t phase = 0;
+      int tile = unit < total_tiles ? unit : -1;
+      while (true) {
+        if (CTAS == 2) mbar_wait_cluster(&sched_empty[slot], phase ^ 1); else mbar_wait(&sched_empty[slot], phase ^ 1);
+        sched_ids[slot] = tile;
+        if (CTAS == 2) {
+          st_shared_cluster_u32(peer_ids + slot * 4, uint32_t(tile));
+          mbar_arrive_cluster(peer_full + slot * 8);           // release.cluster: orders the store above
+        }
+        mbar_arrive(&sched_full[slot]);
+        if (tile < 0) break;
+        if (++slot == SCHED_DEPTH) { slot = 0; phase ^= 1; }
+        tile = num_units + atomicAdd(p.sched, 1);
+        if (tile >= total_tiles) {
+          tile = -1;
+          // every unit draws exactly one terminal value; the last one to do so re-arms the counters
+          if (atomicAdd(p.sched + 1, 1) == num_units - 1) { p.sched[0] = 0; p.sched[1] = 0; }
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
     // A warp may only read the TMEM lane quarter warp % 4, so warps w and w + 4 share a 32-row quarter and split
@@ -381,7 +461,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint8_t* sbuf = epi_smem + (warp - 4) * 4096;           // one 4 KB staging buffer (32 rows x 128 B, 128B-swizzled)
     int acc = 0; uint32_t acc_phase = 0;
     const uint32_t leader_tmem_empty = CTAS == 2 ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : 0u;
-    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+    int tile = -1;
+    while (true) {
+      if (dynamic) {
+        if (lane == 0) tile = ring_next<CTAS>(ring);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+      } else {
+        tile = next_tile(tile);
+      }
+      if (tile < 0) break;
       int mt, nt, ks;
       decode_tile(p, tile, mt, nt, ks);
       const bool has_k = ks * p.k_blocks < p.total_k_blocks;
@@ -631,6 +719,28 @@ static double plan_eff(int m, int n, int kblocks, int bn, int split, int sms, in
   return eff;
 }
 
+// Scheduler counters: a per-device pool of {next tile, finished units} pairs, handed out round-robin so GEMMs that
+// are in flight at the same time (other streams) never share a pair; each pair zeroes itself when its launch ends.
+constexpr int SCHED_POOL = 4096;
+static int* sched_slot() {
+  static int* pools[64] = {nullptr};
+  static unsigned next[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!pools[dev]) {
+    int* ptr = nullptr;
+    if (cudaMalloc(&ptr, SCHED_POOL * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+    if (cudaMemset(ptr, 0, SCHED_POOL * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+    pools[dev] = ptr;
+  }
+  return pools[dev] + 2 * (next[dev]++ % SCHED_POOL);
+}
+
+// 0 = static round-robin tiles (default: on an undisturbed GPU it is ~3% faster, nothing is claimed ahead),
+// 1 = dynamic tile scheduler (cc_gemm_tc_set_dynamic_tiles; the data-parallel engine turns it on while all_reduces
+// overlap backward and steal SMs)
+static int g_dynamic_tiles = 0;
+
 // -1 = planner decides, 0 = never pair, 1 = always pair (cc_gemm_tc_set_pair_mode; experiments and tests)
 static int g_pair_mode = -1;
 
@@ -678,6 +788,11 @@ static int launch_bn(const Problem& pr, Params p, cudaStream_t st) {
   p.k_blocks = ceil_div(p.total_k_blocks, p.split_k);
   p.split_k = ceil_div(p.total_k_blocks, p.k_blocks);
   const int tiles = p.symmetric ? p.n_tiles * (p.n_tiles + 1) / 2 : p.m_tiles * p.n_tiles * p.split_k;
+  p.sched = nullptr;
+  if (g_dynamic_tiles) {
+    p.sched = sched_slot();
+    if (!p.sched) { set_error("cc_gemm_tc: could not allocate the tile-scheduler counters"); return CC_ERR_CUDA; }
+  }
   auto kern = gemm_tc_kernel<KIND, EPI, BN, CTAS>;
   static bool attr_done = false;
   static int max_clusters = 0;
@@ -881,6 +996,11 @@ int cc_cooc_count_tc(const int64_t* indptr, const int32_t* indices, int64_t num_
     const int rc = tc::launch<tc::KIND_U8, tc::EPI_COUNT>(pr, p, 256, 2, st);
     if (rc != CC_OK) return rc;
   }
+  return CC_OK;
+}
+
+int cc_gemm_tc_set_dynamic_tiles(int on) {
+  tc::g_dynamic_tiles = on ? 1 : 0;
   return CC_OK;
 }
 

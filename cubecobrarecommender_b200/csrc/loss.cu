@@ -298,6 +298,55 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
 }
 
+// ---------------------------------------------- Adam fused with the gradient exchange over NVLink peer memory
+// Data-parallel step, one kernel per rank instead of  all_reduce(grads) -> Adam(all parameters)  on every rank:
+// rank r owns the slice [lo, hi) of the flat parameter buffer.  For its slice it
+//   (1) loads the gradient from EVERY rank's gradient buffer (local load + peer loads through NVLink / NVSwitch)
+//       and sums them in rank order                                                   -> reduce-scatter
+//   (2) applies the TF-style Adam update to its slice of m, v, params (1/world of the work and of the HBM traffic)
+//   (3) stores the updated parameters into EVERY rank's parameter buffer (peer stores) -> all-gather
+// so the collective's transfers ride inside the optimiser pass.  The buffers live in symmetric memory
+// (torch.distributed._symmetric_memory); the caller brackets the kernel with two cross-rank barriers
+// (all gradients complete before, all parameter slices landed after).
+constexpr int P2P_MAX_WORLD = 16;
+struct PeerPtrs {
+  const float* grads[P2P_MAX_WORLD];
+  float* params[P2P_MAX_WORLD];
+};
+
+__global__ void __launch_bounds__(256, 4)
+adam_p2p_kernel(const PeerPtrs pp, int world, int rank, float* __restrict__ m, float* __restrict__ v, int64_t lo,
+                int64_t hi, const int64_t* __restrict__ step_ptr, float lr, float b1, float b2, float eps) {
+  const double t = double(*step_ptr + 1);
+  const float lr_t = float(double(lr) * sqrt(1.0 - pow(double(b2), t)) / (1.0 - pow(double(b1), t)));
+  const int64_t i4 = lo + (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= hi) return;                                   // lo, hi are multiples of 4
+  float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 part[P2P_MAX_WORLD];
+#pragma unroll
+  for (int r = 0; r < P2P_MAX_WORLD; ++r)                 // all peer loads in flight together (NVLink latency ~2 us)
+    if (r < world) part[r] = ld_nc_f4(pp.grads[r] + i4);
+#pragma unroll
+  for (int r = 0; r < P2P_MAX_WORLD; ++r)                 // fixed rank order: every rank would compute the same sum
+    if (r < world) { gv.x += part[r].x; gv.y += part[r].y; gv.z += part[r].z; gv.w += part[r].w; }
+  float4 pv = *reinterpret_cast<const float4*>(pp.params[rank] + i4);
+  float4 mv = *reinterpret_cast<float4*>(m + i4);
+  float4 vv = *reinterpret_cast<float4*>(v + i4);
+#define CC_ADAM1(X)                                   \
+  mv.X = b1 * mv.X + (1.f - b1) * gv.X;               \
+  vv.X = b2 * vv.X + (1.f - b2) * gv.X * gv.X;        \
+  pv.X = pv.X - lr_t * mv.X / (sqrtf(vv.X) + eps);
+  CC_ADAM1(x) CC_ADAM1(y) CC_ADAM1(z) CC_ADAM1(w)
+#undef CC_ADAM1
+  *reinterpret_cast<float4*>(m + i4) = mv;
+  *reinterpret_cast<float4*>(v + i4) = vv;
+#pragma unroll
+  for (int r = 0; r < P2P_MAX_WORLD; ++r)
+    if (r < world) *reinterpret_cast<float4*>(pp.params[r] + i4) = pv;
+  // no per-thread system fence (it serialises every warp on the NVLink round trip: 0.50 -> ? ms at 2 GPUs): grid
+  // completion makes the peer stores visible, and the caller's cross-rank barrier only starts after it
+}
+
 __global__ void round_tf32_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) { float v = x[i]; v = rn_tf32(v); out[i] = v; }
@@ -382,6 +431,30 @@ int cc_adam_step(float* params, const float* grads, float* m, float* v, int64_t 
   const int64_t threads = ceil_div<int64_t>(n, 4);
   adam_kernel<<<(unsigned)ceil_div<int64_t>(threads, 256), 256, 0, as_stream(stream)>>>(params, grads, m, v, n, step_ptr,
                                                                                       lr, beta1, beta2, eps, shadow_tf32);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+int cc_adam_step_p2p(const void* const* grads_ptrs, void* const* params_ptrs, int world, int rank, float* m, float* v,
+                     int64_t lo, int64_t hi, const int64_t* step_ptr, float lr, float beta1, float beta2, float eps,
+                     void* stream) {
+  CC_REQUIRE(grads_ptrs && params_ptrs && m && v && step_ptr, "cc_adam_step_p2p: null pointer");
+  CC_REQUIRE(world >= 1 && world <= P2P_MAX_WORLD && rank >= 0 && rank < world, "cc_adam_step_p2p: bad world/rank");
+  CC_REQUIRE(lo >= 0 && hi >= lo && lo % 4 == 0 && hi % 4 == 0, "cc_adam_step_p2p: the slice must be 4-element aligned");
+  PeerPtrs pp{};
+  for (int r = 0; r < world; ++r) {
+    CC_REQUIRE(grads_ptrs[r] && params_ptrs[r] &&
+                   ((reinterpret_cast<uintptr_t>(grads_ptrs[r]) | reinterpret_cast<uintptr_t>(params_ptrs[r])) & 15) == 0,
+               "cc_adam_step_p2p: rank %d buffers must be non-null and 16-byte aligned", r);
+    pp.grads[r] = static_cast<const float*>(grads_ptrs[r]);
+    pp.params[r] = static_cast<float*>(params_ptrs[r]);
+  }
+  CC_REQUIRE(((reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0,
+             "cc_adam_step_p2p: m and v must be 16-byte aligned");
+  if (hi == lo) return CC_OK;
+  const int64_t threads = (hi - lo) / 4;
+  adam_p2p_kernel<<<(unsigned)ceil_div<int64_t>(threads, 256), 256, 0, as_stream(stream)>>>(
+      pp, world, rank, m, v, lo, hi, step_ptr, lr, beta1, beta2, eps);
   CC_CHECK_LAUNCH();
   return CC_OK;
 }

@@ -58,12 +58,23 @@ class DAEEngine:
         self.yw = self.cpad // 32
         self.launches = 0          # kernels launched by the last step (for bench's gpu_launches)
         self.prof = None
-        # data parallel: bucketed, asynchronous gradient all_reduce overlapped with backward (dist.GradBuckets);
-        # CC_DP_OVERLAP=0 falls back to one blocking all_reduce of the whole flat buffer after backward
+        # data parallel (one process per GPU), CC_DP_MODE =
+        #   "p2p"  (default) Adam fused with the gradient exchange over NVLink peer memory: every rank owns 1/world of
+        #          the parameters, reduces that slice of all ranks' gradients with peer loads, updates it and stores
+        #          the result into every rank's parameters (cc_adam_step_p2p; symmetric memory)
+        #   "nccl_overlap"   bucketed asynchronous NCCL all_reduce overlapped with backward (dist.GradBuckets)
+        #   "nccl"           one blocking all_reduce of the whole flat gradient buffer after backward
         import os
         from ..dist import GradBuckets
         self.buckets = GradBuckets(self.store.layout, self.store.total)
-        self.overlap = os.environ.get("CC_DP_OVERLAP", "1") != "0"
+        self.dp_mode = os.environ.get("CC_DP_MODE", "p2p")
+        if os.environ.get("CC_DP_OVERLAP") is not None:          # older switch: 1 = overlapped buckets, 0 = blocking
+            self.dp_mode = "nccl_overlap" if os.environ["CC_DP_OVERLAP"] != "0" else "nccl"
+        if self.dp_mode not in ("p2p", "nccl_overlap", "nccl"):
+            raise ValueError(f"CC_DP_MODE={self.dp_mode!r}: expected p2p, nccl_overlap or nccl")
+        self.overlap = self.dp_mode == "nccl_overlap"
+        self._dp_ready = False
+        self._dynamic_tiles = None
         self._alloc()
 
     # -- buffers --------------------------------------------------------------------
@@ -301,13 +312,50 @@ class DAEEngine:
         if self.overlap and self._distributed():
             self.buckets.launch(self.store.grads, bucket, self.group)
 
+    def _dp_setup(self):
+        """First distributed step: move params/grads to symmetric memory for the p2p mode (collective).  If the
+        rendezvous is not possible on this system every rank falls back to the blocking NCCL all_reduce."""
+        import torch.distributed as dist
+        self._dp_ready = True
+        if not self._distributed() or self.dp_mode != "p2p":
+            return
+        ok = torch.ones(1, dtype=torch.int32, device=self.dev)
+        try:
+            self.store.make_symmetric(self.group)
+        except Exception as e:                      # no peer access / no symmetric-memory support
+            import warnings
+            warnings.warn(f"CC_DP_MODE=p2p unavailable ({e!r}); using the NCCL all_reduce path")
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            self.dp_mode = "nccl"
+        self._sync_flag = torch.zeros(1, dtype=torch.float32, device=self.dev)
+
     def allreduce_grads(self):
-        """Blocking form: one all_reduce over the whole flat gradient buffer (CC_DP_OVERLAP=0)."""
+        """NCCL modes: the blocking all_reduce of the whole flat gradient buffer (mode "nccl"), and the loss scalars."""
         import torch.distributed as dist
         if self._distributed():
-            if not self.overlap:
+            if self.dp_mode == "nccl":
                 dist.all_reduce(self.store.grads, op=dist.ReduceOp.SUM, group=self.group)
             dist.all_reduce(self.loss3, op=dist.ReduceOp.SUM, group=self.group)
+
+    def _adam_p2p(self):
+        """Reduce-scatter + Adam + all-gather in one kernel over NVLink peer memory (cc_adam_step_p2p).  The loss
+        all_reduce issued just before is the barrier "every rank's gradients are complete"; the one-element
+        all_reduce after it is the barrier "every rank's slice has landed in my parameters"."""
+        import torch.distributed as dist
+        s, a = self.store, self.adam
+        st = stream_ptr()
+        lo, hi = s.dp_slice
+        with self._timed("adam"):
+            call("cc_adam_step_p2p", ptr(s.peer_grads), ptr(s.peer_params), s.dp_world, s.dp_rank, ptr(s.adam_m),
+                 ptr(s.adam_v), lo, hi, ptr(s.step), a["lr"], a["beta1"], a["beta2"], a["eps"], st)
+        dist.all_reduce(self._sync_flag, op=dist.ReduceOp.SUM, group=self.group)
+        if s.shadow is not None:                    # tf32 copy of ALL parameters for the tensor-core GEMMs
+            call("cc_round_tf32", ptr(s.params), ptr(s.shadow), s.total, st)
+            self.launches += 1
+        call("cc_step_increment", ptr(s.step), st)
+        self.launches += 2
 
     def apply_adam(self):
         """TF-style Adam over all parameters, then the step counter advances."""
@@ -329,9 +377,21 @@ class DAEEngine:
     def train_step(self):
         """forward + backward + (all_reduce) + Adam on the batch set by set_batch/sample_batch.
         Returns the device tensor loss3 = [bce, kl, bce + reg*kl] (no synchronisation)."""
+        if self._dynamic_tiles is None:
+            # overlapped all_reduces take SMs away from the persistent GEMMs at unpredictable moments: hand tiles
+            # out dynamically then (CC_DYNAMIC_TILES=0/1 overrides)
+            import os
+            want = os.environ.get("CC_DYNAMIC_TILES")
+            self._dynamic_tiles = (self.dp_mode == "nccl_overlap" and self._distributed()) if want is None else want == "1"
+            if self.precision != "fp32":
+                call("cc_gemm_tc_set_dynamic_tiles", int(self._dynamic_tiles))
+        if not self._dp_ready:
+            self._dp_setup()
         self.forward_backward()
         self.allreduce_grads()
-        if self.overlap and self._distributed():
+        if self.dp_mode == "p2p" and self._distributed():
+            self._adam_p2p()
+        elif self.overlap and self._distributed():
             for bucket in self.buckets.ORDER:          # Adam follows the reductions bucket by bucket
                 self.buckets.wait(bucket)
                 self._adam_range(bucket)

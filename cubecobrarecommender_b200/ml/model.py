@@ -71,6 +71,41 @@ class ParamStore:
         if self.shadow is not None:
             call("cc_round_tf32", ptr(self.params), ptr(self.shadow), self.total, stream_ptr())
 
+    # -- data parallel over NVLink peer memory ---------------------------------------------------
+    def make_symmetric(self, group=None):
+        """Move params and grads into symmetric memory (torch.distributed._symmetric_memory) so that every rank
+        can load any rank's gradients and store into any rank's parameters from inside a kernel
+        (cc_adam_step_p2p).  Collective: every rank of ``group`` must call it."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        import warnings
+        with warnings.catch_warnings():             # deprecated no-op on newer torch, required on older ones
+            warnings.simplefilter("ignore")
+            try:
+                symm.enable_symm_mem_for_group(group.group_name)
+            except Exception:
+                pass
+        new_p = symm.empty(self.total, dtype=torch.float32, device=self.device)
+        new_g = symm.empty(self.total, dtype=torch.float32, device=self.device)
+        new_p.copy_(self.params)
+        new_g.zero_()
+        self._p_hdl = symm.rendezvous(new_p, group)
+        self._g_hdl = symm.rendezvous(new_g, group)
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        pp = [int(x) for x in self._p_hdl.buffer_ptrs]
+        gp = [int(x) for x in self._g_hdl.buffer_ptrs]
+        if pp[rank] != new_p.data_ptr() or gp[rank] != new_g.data_ptr() or len(pp) != world:
+            raise RuntimeError("symmetric-memory rendezvous returned unexpected buffer pointers")
+        self.params, self.grads = new_p, new_g
+        self.peer_params = np.array(pp, dtype=np.uint64)
+        self.peer_grads = np.array(gp, dtype=np.uint64)
+        self.dp_rank, self.dp_world = rank, world
+        quarter = self.total // 4                   # slices are 16-byte aligned (offsets are padded to 4 floats)
+        self.dp_slice = ((quarter * rank // world) * 4, (quarter * (rank + 1) // world) * 4 if rank + 1 < world else self.total)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group)
+
     def w(self, key):
         """The copy of a kernel the GEMMs read (tf32-rounded shadow when enabled)."""
         return self.view(self.shadow if self.shadow is not None else self.params, key)

@@ -175,6 +175,10 @@ int64_t cc_gemm_bce_partial_count(int m, int lddz);
 /* CTA-pair tiling of the tcgen05 GEMMs (256 x 256 tiles on two SMs, tcgen05.mma.cta_group::2):
  * -1 = the planner decides per problem (default), 0 = never, 1 = whenever the shape allows it. */
 int cc_gemm_tc_set_pair_mode(int mode);
+/* Tile scheduling of the persistent tcgen05 GEMMs: 0 (default) = static round-robin, 1 = tiles drawn at run time from
+ * a global atomic counter, so CTAs that start late or lose their SM to a concurrent kernel (an NCCL all_reduce
+ * overlapping backward) take fewer tiles instead of stretching the GEMM. */
+int cc_gemm_tc_set_dynamic_tiles(int on);
 int64_t cc_colsum_workspace_bytes(int m, int n);
 int cc_colsum_f32(const float* x, int64_t ld, int m, int n, float* workspace, float* out, int accumulate,
                   void* stream);
@@ -202,6 +206,15 @@ int cc_loss_finalize(const double* bce_rows, int32_t nb, double bce_div, const d
  * produced, because the tensor core itself truncates (biased). */
 int cc_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, const int64_t* step_ptr, float lr,
                  float beta1, float beta2, float eps, float* shadow_tf32, void* stream);
+/* Data-parallel form: Adam fused with the gradient exchange over NVLink peer memory.  Rank `rank` owns the slice
+ * [lo, hi) (multiples of 4) of the flat buffers: it sums that slice of the gradient buffers of ALL ranks
+ * (grads_ptrs[world]: device pointers, peers mapped through symmetric memory; summed in rank order), applies the Adam
+ * update to its slice of m, v and params, and stores the updated parameters into every rank's parameter buffer
+ * (params_ptrs[world]).  m and v are this rank's full-size buffers (only [lo, hi) is touched).  The caller puts a
+ * cross-rank barrier before (all gradients written) and after (all slices delivered) the call.  world <= 16. */
+int cc_adam_step_p2p(const void* const* grads_ptrs, void* const* params_ptrs, int world, int rank, float* m, float* v,
+                     int64_t lo, int64_t hi, const int64_t* step_ptr, float lr, float beta1, float beta2, float eps,
+                     void* stream);
 int cc_round_tf32(const float* x, float* out, int64_t n, void* stream);
 int cc_sigmoid_f32(const float* z, float* out, int64_t n, void* stream);
 

@@ -141,6 +141,43 @@ def _rn_tf32(x):
     return ((xi + 0x0FFF + ((xi >> 13) & 1)) & ~0x1FFF).view(torch.float32)
 
 
+def test_adam_p2p_emulated_ranks_equal_plain_adam():
+    """cc_adam_step_p2p (reduce-scatter + Adam + all-gather over peer pointers) with three ranks emulated on ONE
+    GPU -- three gradient and three parameter buffers on the same device, one launch per rank slice: every
+    rank's parameters must equal plain Adam on the summed gradient, bit for bit, over three steps."""
+    world, n = 3, 4 * 3001
+    g = torch.Generator(device="cuda").manual_seed(2)
+    p0 = torch.randn(n, device="cuda", generator=g)
+    params = [p0.clone() for _ in range(world)]
+    grads = [torch.empty(n, device="cuda") for _ in range(world)]
+    ms = [torch.zeros(n, device="cuda") for _ in range(world)]
+    vs = [torch.zeros(n, device="cuda") for _ in range(world)]
+    ref_p, ref_m, ref_v = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    gp = np.array([t.data_ptr() for t in grads], dtype=np.uint64)
+    pp = np.array([t.data_ptr() for t in params], dtype=np.uint64)
+    quarter = n // 4
+    bounds = [(quarter * r // world) * 4 for r in range(world)] + [n]
+    hp = (1e-3, 0.9, 0.999, 1e-7)
+    for it in range(3):
+        for t in grads:
+            t.copy_(torch.randn(n, device="cuda", generator=g) * 0.01)
+        total = grads[0].clone()
+        for t in grads[1:]:
+            total += t                                         # rank order, like the kernel
+        for r in range(world):
+            E.call("cc_adam_step_p2p", E.ptr(gp), E.ptr(pp), world, r, E.ptr(ms[r]), E.ptr(vs[r]), bounds[r], bounds[r + 1],
+                   E.ptr(step), *hp, E.stream_ptr())
+        E.call("cc_adam_step", E.ptr(ref_p), E.ptr(total), E.ptr(ref_m), E.ptr(ref_v), n, E.ptr(step), *hp, None,
+               E.stream_ptr())
+        E.call("cc_step_increment", E.ptr(step), E.stream_ptr())
+        for r in range(world):
+            assert torch.equal(params[r], ref_p)               # every rank holds the same, exact update
+            lo, hi = bounds[r], bounds[r + 1]
+            assert torch.equal(ms[r][lo:hi], ref_m[lo:hi]) and torch.equal(vs[r][lo:hi], ref_v[lo:hi])
+            assert ms[r][:lo].abs().sum() == 0 and ms[r][hi:].abs().sum() == 0      # only the own slice is touched
+
+
 @pytest.fixture
 def pair_mode():
     """Sets the CTA-pair (cta_group::2) tiling mode of the tcgen05 GEMMs for one test, then restores 'auto'."""
@@ -193,6 +230,46 @@ def test_gemm_tcgen05_tf32_all_layouts(ta, tb, m, n, k, split, tile_n, pair_mode
         TC.gemm(a, b, c4, transa=bool(ta), transb=bool(tb), bias=bias, relu=True, precision="tf32", split_k=split,
                 tile_n=tile_n if split else 0)
         assert (c4.double() - torch.relu(ref + bias.double())).abs().max().item() / scale < tol
+
+
+@pytest.mark.parametrize("pair", [0, 1])
+def test_gemm_tcgen05_dynamic_tile_scheduler_many_tiles(pair, pair_mode):
+    """Far more tiles than persistent CTAs (or CTA pairs): after its first tile every unit draws the rest from the
+    global atomic counter, which must re-arm itself for the next launch (three launches, identical results),
+    including while a second stream keeps some SMs busy."""
+    from cubecobrarecommender_b200 import _lib
+    from cubecobrarecommender_b200.ml import tensorcore as TC
+    pair_mode(pair)
+    _lib.call("cc_gemm_tc_set_dynamic_tiles", 1)
+    try:
+        _dynamic_tiles_body(TC)
+    finally:
+        _lib.call("cc_gemm_tc_set_dynamic_tiles", 0)
+
+
+def _dynamic_tiles_body(TC):
+    m, n, k = 4096 + 64, 6000, 256
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = _rn_tf32(torch.randn(m, k, device="cuda", generator=g))
+    b = _rn_tf32(torch.randn(k, n, device="cuda", generator=g))
+    ref = a.double() @ b.double()
+    scale = ref.abs().max().item()
+    outs = []
+    side = torch.cuda.Stream()
+    junk = torch.randn(4096, 4096, device="cuda")
+    for it in range(3):
+        c = torch.zeros(m, n, device="cuda")
+        if it == 2:                      # a competing kernel stream: late-starting units must just take fewer tiles
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(4):
+                    junk = torch.tanh(junk @ junk * 1e-3)
+        TC.gemm(a, b, c, precision="tf32", split_k=1, tile_n=256)
+        outs.append(c)
+    torch.cuda.synchronize()
+    for c in outs:
+        assert (c.double() - ref).abs().max().item() / scale < 3e-5
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
 
 
 @pytest.mark.parametrize("pair", [0, 1])
