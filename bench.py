@@ -9,8 +9,9 @@ noise function F + reg-row draw, both towers forward, BCE + 0.1*KLD, backward, (
 all_reduce when N > 1), TF-style Adam over all 32.6 M parameters.  Prints ONE JSON line.
 
 * `value`  : cubes/s with cubes (CSR), M-hat and weights resident in HBM, CUDA-event timed.
-* `e2e`    : the same step driven from HOST buffers: the batch's CSR is copied from pinned
-             host memory every step and the loss is read back every step.
+* `e2e`    : the same step driven from HOST buffers through the package's host-fed trainer path
+             (ml.engine.HostBatchStream): the batch's CSR is copied from pinned host memory every step
+             (double-buffered on a copy stream) and every step's loss is copied back and read on the host.
 * `roofline`: the dominant kernel (the 512<->C GEMM passes), timed with CUDA events inside the
              timed region, against MEASURED_PEAKS.json.
 * `cpu_baseline`: the oracle port of the reference CPU path (reference DataGenerator restated
@@ -44,6 +45,17 @@ def load_peaks():
         return dict(hbm_gbs=p["hbm_gbs"], bf16_burst=p["bf16_tflops"], bf16_sustained=p["bf16_tflops_sustained"],
                     source="measured")
     return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+def ncu_traffic(precision):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this workload (profiles/roofline_traffic.json; null when absent)."""
+    path = os.path.join(REPO, "profiles", "roofline_traffic.json")
+    try:
+        t = json.load(open(path))
+        return t.get(f"gemm_tc_kernel<{precision}>", {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -340,38 +352,27 @@ def run_native(args, rank, world, local_rank):
     loss_host = [float(v) for v in loss.cpu().numpy()]
     value = B * world * args.steps / (ms_total / 1e3)
 
-    # ---- e2e: host CSR -> pinned -> H2D every step, loss D2H every step ----
-    host_batches = []
-    for i in range(nb):
-        sub = csr.rows(np.arange(i * B, (i + 1) * B))
-        host_batches.append((torch.from_numpy(sub.indptr).pin_memory(), torch.from_numpy(sub.indices).pin_memory()))
-    max_nnz = max(hb[1].numel() for hb in host_batches)
-    d_indptr = torch.zeros(B + 1, dtype=torch.int64, device=dev)
-    d_indices = torch.zeros(max_nnz, dtype=torch.int32, device=dev)
-    loss_pinned = torch.zeros(3, dtype=torch.float64).pin_memory()
-
-    def e2e_step(i):
-        hp, hi = host_batches[i % nb]
-        d_indptr.copy_(hp, non_blocking=True)
-        d_indices[:hi.numel()].copy_(hi, non_blocking=True)
-        eng.sample_batch(d_indptr, d_indices, None, prob, alias, W["noise"], W["noise_std"], seed=99 + rank)
-        l3 = eng.train_step()
-        loss_pinned.copy_(l3, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(loss_pinned[2])
-
+    # ---- e2e: the package's host-fed trainer path (HostBatchStream): every step's batch CSR is copied from pinned
+    #      host memory (double-buffered on a copy stream) and every step's loss is copied back to the host ----
+    feed = E.HostBatchStream(eng, [csr.rows(np.arange(i * B, (i + 1) * B)) for i in range(nb)])
+    e2e_losses = []
     for i in range(min(args.warmup, 3)):
-        e2e_step(i)
+        feed.step(i, prob, alias, W["noise"], W["noise_std"], seed=99 + rank)
+    feed.drain()
     barrier()
     t_a = time.perf_counter()
     for i in range(args.steps):
-        e2e_step(i)
+        l = feed.step(3 + i, prob, alias, W["noise"], W["noise_std"], seed=99 + rank)
+        if l is not None:
+            e2e_losses.append(float(l[2]))
+    e2e_losses.append(float(feed.drain()[2]))                       # K losses read on the host inside the region
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t_a], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    assert len(e2e_losses) == args.steps and all(np.isfinite(e2e_losses))
     e2e_value = B * world * args.steps / float(e2e_s.item())
-    h2d = int(np.mean([hb[0].numel() * 8 + hb[1].numel() * 4 for hb in host_batches]))
+    h2d = feed.h2d_bytes
 
     if rank != 0:
         if world > 1:
@@ -388,7 +389,7 @@ def run_native(args, rank, world, local_rank):
     achieved = flops_per_launch / (ms_big / n_big * 1e-3) / 1e12 if n_big else 0.0
     roofline = {"kernel": {"fp32": "gemm_simt_kernel", "tf32": "gemm_tc_kernel<tf32>", "bf16": "gemm_tc_kernel<bf16>"}[args.precision],
                 "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                "frac": achieved / tensor_peak, "traffic": None,
+                "frac": achieved / tensor_peak, "traffic": ncu_traffic(args.precision),
                 "peak_source": f"{peaks['source']} bf16 sustained x{1.0 if args.precision == 'bf16' else 0.5} ({args.precision})",
                 "launches_timed": n_big, "avg_launch_ms": ms_big / n_big if n_big else None,
                 "share_of_step": ms_big / ms_total if ms_total else None}

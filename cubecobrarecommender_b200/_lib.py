@@ -62,6 +62,7 @@ SIGNATURES = {
     "cc_gemm_bce_partial_count": (I64, [I, I]),
     "cc_gemm_tc_set_pair_mode": (I, [I]),
     "cc_gemm_tc_set_dynamic_tiles": (I, [I]),
+    "cc_gemm_tc_set_pdl": (I, [I]),
     "cc_colsum_workspace_bytes": (I64, [I, I]),
     "cc_colsum_f32": (I, [P, I64, I, I, P, P, I, P]),
     "cc_relu_mask_f32": (I, [P, I64, P, I64, I, I, P]),
@@ -69,7 +70,7 @@ SIGNATURES = {
     "cc_bce_logits_fwd_bwd": (I, [P, I64, P, I64, I32, I32, I32, D, P, I64, P, P]),
     "cc_softmax_kl_fwd_bwd": (I, [P, I64, P, I64, P, I32, I32, I32, D, P, I64, P, I, P]),
     "cc_loss_finalize": (I, [P, I32, D, P, I32, D, D, P, P]),
-    "cc_adam_step_p2p": (I, [P, P, I, I, P, P, I64, I64, P, F, F, F, F, P]),
+    "cc_adam_step_p2p": (I, [P, P, I, I, P, P, I64, I64, P, F, F, F, F, P, P, P]),
     "cc_adam_step": (I, [P, P, P, P, I64, P, F, F, F, F, P, P]),
     "cc_round_tf32": (I, [P, P, I64, P]),
     "cc_sigmoid_f32": (I, [P, P, I64, P]),

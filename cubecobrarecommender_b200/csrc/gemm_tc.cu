@@ -284,6 +284,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   int* sched_ids = reinterpret_cast<int*>(sched_empty + SCHED_DEPTH);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched_ids + SCHED_DEPTH);
 
+  // Programmatic dependent launch: let the NEXT kernel of the stream be scheduled as soon as every CTA of this grid
+  // is running; its CTAs take whatever SMs are (or become) free, run their prologue (barrier init, TMEM
+  // allocation, descriptor prefetch) and park at griddepcontrol.wait below until this grid has completed.  The step
+  // is a chain of ~35 GEMM launches, most of them a few microseconds long: this hides launch latency and prologue.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // tiles of (BM*CTAS) x BN; the symmetric count GEMM only visits the upper triangle of its square tile grid
   const int total_tiles = p.symmetric ? (p.n_tiles * (p.n_tiles + 1)) / 2 : p.m_tiles * p.n_tiles * p.split_k;
@@ -317,6 +322,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // nothing above touched global memory; everything below may read what the previous kernel wrote (activations,
+  // parameters, scheduler counters) or overwrite what it still reads
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   TileRing ring{sched_full, sched_empty, sched_ids, CTAS == 2 ? mapa_shared(smem_u32(sched_empty), 0) : 0u, 0, 0u};
   const bool dynamic = p.sched != nullptr;
   // static mode: unit u walks tiles u, u + num_units, ... with no ring traffic at all
@@ -736,6 +744,9 @@ static int* sched_slot() {
   return pools[dev] + 2 * (next[dev]++ % SCHED_POOL);
 }
 
+// programmatic dependent launch of consecutive GEMMs (cc_gemm_tc_set_pdl; on by default, CC_GEMM_PDL=0 disables)
+static int g_pdl = getenv("CC_GEMM_PDL") ? atoi(getenv("CC_GEMM_PDL")) : 1;
+
 // 0 = static round-robin tiles (default: on an undisturbed GPU it is ~3% faster, nothing is claimed ahead),
 // 1 = dynamic tile scheduler (cc_gemm_tc_set_dynamic_tiles; the data-parallel engine turns it on while all_reduces
 // overlap backward and steal SMs)
@@ -805,21 +816,27 @@ static int launch_bn(const Problem& pr, Params p, cudaStream_t st) {
     }
     attr_done = true;
   }
-  if (CTAS == 2) {
-    const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  {
+    const int units = CTAS == 2 ? (tiles < max_clusters ? tiles : max_clusters) : (tiles < sm_count() ? tiles : sm_count());
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(unsigned(2 * clusters));
+    cfg.gridDim = dim3(unsigned(CTAS * units));
     cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (g_pdl) {       // may start while the previous kernel of the stream drains (see griddepcontrol in the kernel)
+      at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    if (CTAS == 2) {
+      at[na].id = cudaLaunchAttributeClusterDimension;
+      at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    cfg.attrs = at; cfg.numAttrs = na;
     CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_c, p));
-  } else {
-    const int grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<grid, THREADS, C::SMEM_BYTES, st>>>(map_a, map_b, map_c, p);
   }
   CC_CHECK_LAUNCH();
   return CC_OK;
@@ -996,6 +1013,11 @@ int cc_cooc_count_tc(const int64_t* indptr, const int32_t* indices, int64_t num_
     const int rc = tc::launch<tc::KIND_U8, tc::EPI_COUNT>(pr, p, 256, 2, st);
     if (rc != CC_OK) return rc;
   }
+  return CC_OK;
+}
+
+int cc_gemm_tc_set_pdl(int on) {
+  tc::g_pdl = on ? 1 : 0;
   return CC_OK;
 }
 

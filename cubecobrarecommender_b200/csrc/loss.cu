@@ -258,6 +258,14 @@ loss_finalize_kernel(const double* __restrict__ bce_rows, int nb, double bce_div
 }
 
 // ------------------------------------------------------------------- Adam
+// One definition with explicit rounding steps (no compiler-chosen FMA contraction), so the plain kernel and the
+// peer-memory kernel produce identical bits from identical inputs.
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, float b1, float b2, float lr_t,
+                                            float eps) {
+  m = __fmaf_rn(b1, m, __fmul_rn(1.f - b1, g));
+  v = __fmaf_rn(b2, v, __fmul_rn(__fmul_rn(1.f - b2, g), g));
+  p = __fsub_rn(p, __fdiv_rn(__fmul_rn(lr_t, m), __fadd_rn(__fsqrt_rn(v), eps)));
+}
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             int64_t n, const int64_t* __restrict__ step_ptr, float lr, float b1, float b2, float eps,
@@ -270,12 +278,10 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     const float4 gv = *reinterpret_cast<const float4*>(g + i4);
     float4 mv = *reinterpret_cast<float4*>(m + i4);
     float4 vv = *reinterpret_cast<float4*>(v + i4);
-#define CC_ADAM1(X)                                   \
-    mv.X = b1 * mv.X + (1.f - b1) * gv.X;             \
-    vv.X = b2 * vv.X + (1.f - b2) * gv.X * gv.X;      \
-    pv.X = pv.X - lr_t * mv.X / (sqrtf(vv.X) + eps);
-    CC_ADAM1(x) CC_ADAM1(y) CC_ADAM1(z) CC_ADAM1(w)
-#undef CC_ADAM1
+    adam_update(pv.x, gv.x, mv.x, vv.x, b1, b2, lr_t, eps);
+    adam_update(pv.y, gv.y, mv.y, vv.y, b1, b2, lr_t, eps);
+    adam_update(pv.z, gv.z, mv.z, vv.z, b1, b2, lr_t, eps);
+    adam_update(pv.w, gv.w, mv.w, vv.w, b1, b2, lr_t, eps);
     *reinterpret_cast<float4*>(p + i4) = pv;
     if (shadow_tf32) {   // tf32 (round-to-nearest) copy of the weights for the tensor-core GEMMs
       float4 sv = pv;
@@ -287,11 +293,9 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     *reinterpret_cast<float4*>(v + i4) = vv;
   } else {
     for (int64_t i = i4; i < n; ++i) {
-      const float gi = g[i];
-      const float mi = b1 * m[i] + (1.f - b1) * gi;
-      const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+      float pi = p[i], mi = m[i], vi = v[i];
+      adam_update(pi, g[i], mi, vi, b1, b2, lr_t, eps);
       m[i] = mi; v[i] = vi;
-      const float pi = p[i] - lr_t * mi / (sqrtf(vi) + eps);
       p[i] = pi;
       if (shadow_tf32) { float sv = pi; sv = rn_tf32(sv); shadow_tf32[i] = sv; }
     }
@@ -312,38 +316,85 @@ constexpr int P2P_MAX_WORLD = 16;
 struct PeerPtrs {
   const float* grads[P2P_MAX_WORLD];
   float* params[P2P_MAX_WORLD];
+  const float* grads_mc;          // multicast (NVLS) views of the same buffers, or null
+  float* params_mc;
 };
 
-__global__ void __launch_bounds__(256, 4)
+__device__ __forceinline__ float4 multimem_ld_reduce_add_f4(const float* mc) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(mc) : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_st_f4(float* mc, const float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// WORLD_CAP: compile-time bound of the rank loops (2, 4, 8, 16) so the per-rank partials stay in registers.
+// MULTICAST: the reduction and the broadcast are done by the NVSwitch (multimem.ld_reduce / multimem.st on the
+// multicast mapping): one load returns the sum over all ranks, one store reaches all ranks -- NVLink traffic per
+// GPU drops from 2 * (world-1)/world to (world+1)/world... of the buffer in the binding direction.
+template <int WORLD_CAP, bool MULTICAST>
+__global__ void __launch_bounds__(256)
 adam_p2p_kernel(const PeerPtrs pp, int world, int rank, float* __restrict__ m, float* __restrict__ v, int64_t lo,
                 int64_t hi, const int64_t* __restrict__ step_ptr, float lr, float b1, float b2, float eps) {
   const double t = double(*step_ptr + 1);
   const float lr_t = float(double(lr) * sqrt(1.0 - pow(double(b2), t)) / (1.0 - pow(double(b1), t)));
-  const int64_t i4 = lo + (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
-  if (i4 >= hi) return;                                   // lo, hi are multiples of 4
-  float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 part[P2P_MAX_WORLD];
+  // U float4 per thread, one CTA-width apart (coalesced), every remote access of all U issued before the first use:
+  // the NVLink round trip is ~2-4 us, so bytes in flight per SM decide the bandwidth
+  constexpr int U = MULTICAST ? 4 : (WORLD_CAP <= 4 ? 2 : 1);
+  const int64_t base = lo + (int64_t(blockIdx.x) * blockDim.x * U + threadIdx.x) * 4;
+  float4 gv[U];
+  bool live[U];
 #pragma unroll
-  for (int r = 0; r < P2P_MAX_WORLD; ++r)                 // all peer loads in flight together (NVLink latency ~2 us)
-    if (r < world) part[r] = ld_nc_f4(pp.grads[r] + i4);
+  for (int u = 0; u < U; ++u) {
+    const int64_t i4 = base + int64_t(u) * blockDim.x * 4;
+    live[u] = i4 < hi;                                     // lo, hi are multiples of 4
+    gv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (MULTICAST) {
 #pragma unroll
-  for (int r = 0; r < P2P_MAX_WORLD; ++r)                 // fixed rank order: every rank would compute the same sum
-    if (r < world) { gv.x += part[r].x; gv.y += part[r].y; gv.z += part[r].z; gv.w += part[r].w; }
-  float4 pv = *reinterpret_cast<const float4*>(pp.params[rank] + i4);
-  float4 mv = *reinterpret_cast<float4*>(m + i4);
-  float4 vv = *reinterpret_cast<float4*>(v + i4);
-#define CC_ADAM1(X)                                   \
-  mv.X = b1 * mv.X + (1.f - b1) * gv.X;               \
-  vv.X = b2 * vv.X + (1.f - b2) * gv.X * gv.X;        \
-  pv.X = pv.X - lr_t * mv.X / (sqrtf(vv.X) + eps);
-  CC_ADAM1(x) CC_ADAM1(y) CC_ADAM1(z) CC_ADAM1(w)
-#undef CC_ADAM1
-  *reinterpret_cast<float4*>(m + i4) = mv;
-  *reinterpret_cast<float4*>(v + i4) = vv;
+    for (int u = 0; u < U; ++u)
+      if (live[u]) gv[u] = multimem_ld_reduce_add_f4(pp.grads_mc + base + int64_t(u) * blockDim.x * 4);   // summed in the switch
+  } else {
+    float4 part[U][WORLD_CAP];
 #pragma unroll
-  for (int r = 0; r < P2P_MAX_WORLD; ++r)
-    if (r < world) *reinterpret_cast<float4*>(pp.params[r] + i4) = pv;
-  // no per-thread system fence (it serialises every warp on the NVLink round trip: 0.50 -> ? ms at 2 GPUs): grid
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int r = 0; r < WORLD_CAP; ++r)
+        if (r < world && live[u]) part[u][r] = ld_nc_f4(pp.grads[r] + base + int64_t(u) * blockDim.x * 4);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int r = 0; r < WORLD_CAP; ++r)                  // fixed rank order: every rank would compute the same sum
+        if (r < world && live[u]) {
+          gv[u].x += part[u][r].x; gv[u].y += part[u][r].y; gv[u].z += part[u][r].z; gv[u].w += part[u][r].w;
+        }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (!live[u]) continue;
+    const int64_t i4 = base + int64_t(u) * blockDim.x * 4;
+    float4 pv = *reinterpret_cast<const float4*>(pp.params[rank] + i4);
+    float4 mv = *reinterpret_cast<float4*>(m + i4);
+    float4 vv = *reinterpret_cast<float4*>(v + i4);
+    const float4 g = gv[u];
+    adam_update(pv.x, g.x, mv.x, vv.x, b1, b2, lr_t, eps);
+    adam_update(pv.y, g.y, mv.y, vv.y, b1, b2, lr_t, eps);
+    adam_update(pv.z, g.z, mv.z, vv.z, b1, b2, lr_t, eps);
+    adam_update(pv.w, g.w, mv.w, vv.w, b1, b2, lr_t, eps);
+    *reinterpret_cast<float4*>(m + i4) = mv;
+    *reinterpret_cast<float4*>(v + i4) = vv;
+    if (MULTICAST) {
+      multimem_st_f4(pp.params_mc + i4, pv);               // one store, replicated to every rank by the switch
+    } else {
+#pragma unroll
+      for (int r = 0; r < WORLD_CAP; ++r)
+        if (r < world) *reinterpret_cast<float4*>(pp.params[r] + i4) = pv;
+    }
+  }
+  // no per-thread system fence (it serialised every warp on the NVLink round trip: 0.50 -> 0.21 ms at 2 GPUs): grid
   // completion makes the peer stores visible, and the caller's cross-rank barrier only starts after it
 }
 
@@ -437,10 +488,12 @@ int cc_adam_step(float* params, const float* grads, float* m, float* v, int64_t 
 
 int cc_adam_step_p2p(const void* const* grads_ptrs, void* const* params_ptrs, int world, int rank, float* m, float* v,
                      int64_t lo, int64_t hi, const int64_t* step_ptr, float lr, float beta1, float beta2, float eps,
-                     void* stream) {
+                     const void* grads_multicast, void* params_multicast, void* stream) {
   CC_REQUIRE(grads_ptrs && params_ptrs && m && v && step_ptr, "cc_adam_step_p2p: null pointer");
   CC_REQUIRE(world >= 1 && world <= P2P_MAX_WORLD && rank >= 0 && rank < world, "cc_adam_step_p2p: bad world/rank");
   CC_REQUIRE(lo >= 0 && hi >= lo && lo % 4 == 0 && hi % 4 == 0, "cc_adam_step_p2p: the slice must be 4-element aligned");
+  CC_REQUIRE((grads_multicast == nullptr) == (params_multicast == nullptr),
+             "cc_adam_step_p2p: give both multicast pointers or neither");
   PeerPtrs pp{};
   for (int r = 0; r < world; ++r) {
     CC_REQUIRE(grads_ptrs[r] && params_ptrs[r] &&
@@ -449,12 +502,24 @@ int cc_adam_step_p2p(const void* const* grads_ptrs, void* const* params_ptrs, in
     pp.grads[r] = static_cast<const float*>(grads_ptrs[r]);
     pp.params[r] = static_cast<float*>(params_ptrs[r]);
   }
-  CC_REQUIRE(((reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0,
-             "cc_adam_step_p2p: m and v must be 16-byte aligned");
+  pp.grads_mc = static_cast<const float*>(grads_multicast);
+  pp.params_mc = static_cast<float*>(params_multicast);
+  CC_REQUIRE(((reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(grads_multicast) |
+               reinterpret_cast<uintptr_t>(params_multicast)) & 15) == 0,
+             "cc_adam_step_p2p: m, v and the multicast pointers must be 16-byte aligned");
   if (hi == lo) return CC_OK;
   const int64_t threads = (hi - lo) / 4;
-  adam_p2p_kernel<<<(unsigned)ceil_div<int64_t>(threads, 256), 256, 0, as_stream(stream)>>>(
-      pp, world, rank, m, v, lo, hi, step_ptr, lr, beta1, beta2, eps);
+  cudaStream_t st = as_stream(stream);
+  // float4 per thread: 4 on the multicast path, 2 for <= 4 ranks, 1 above (must match U in the kernel)
+#define CC_P2P_LAUNCH(CAP, MC)                                                                                   \
+  adam_p2p_kernel<CAP, MC><<<(unsigned)ceil_div<int64_t>(threads, 256 * ((MC) ? 4 : ((CAP) <= 4 ? 2 : 1))), 256, 0, st>>>( \
+      pp, world, rank, m, v, lo, hi, step_ptr, lr, beta1, beta2, eps)
+  if (grads_multicast) CC_P2P_LAUNCH(2, true);
+  else if (world <= 2) CC_P2P_LAUNCH(2, false);
+  else if (world <= 4) CC_P2P_LAUNCH(4, false);
+  else if (world <= 8) CC_P2P_LAUNCH(8, false);
+  else CC_P2P_LAUNCH(16, false);
+#undef CC_P2P_LAUNCH
   CC_CHECK_LAUNCH();
   return CC_OK;
 }

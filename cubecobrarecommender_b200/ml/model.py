@@ -98,6 +98,9 @@ class ParamStore:
         if pp[rank] != new_p.data_ptr() or gp[rank] != new_g.data_ptr() or len(pp) != world:
             raise RuntimeError("symmetric-memory rendezvous returned unexpected buffer pointers")
         self.params, self.grads = new_p, new_g
+        # NVLS multicast mappings of the two buffers (0 when the fabric has no multicast support)
+        self.mc_params = int(getattr(self._p_hdl, "multicast_ptr", 0) or 0)
+        self.mc_grads = int(getattr(self._g_hdl, "multicast_ptr", 0) or 0)
         self.peer_params = np.array(pp, dtype=np.uint64)
         self.peer_grads = np.array(gp, dtype=np.uint64)
         self.dp_rank, self.dp_world = rank, world

@@ -179,6 +179,10 @@ int cc_gemm_tc_set_pair_mode(int mode);
  * a global atomic counter, so CTAs that start late or lose their SM to a concurrent kernel (an NCCL all_reduce
  * overlapping backward) take fewer tiles instead of stretching the GEMM. */
 int cc_gemm_tc_set_dynamic_tiles(int on);
+/* Programmatic dependent launch between consecutive tcgen05 GEMMs of a stream (default on): a GEMM's CTAs may be
+ * scheduled and run their prologue while the previous kernel drains; they wait (griddepcontrol.wait) for its
+ * completion before touching global memory. */
+int cc_gemm_tc_set_pdl(int on);
 int64_t cc_colsum_workspace_bytes(int m, int n);
 int cc_colsum_f32(const float* x, int64_t ld, int m, int n, float* workspace, float* out, int accumulate,
                   void* stream);
@@ -211,10 +215,13 @@ int cc_adam_step(float* params, const float* grads, float* m, float* v, int64_t 
  * (grads_ptrs[world]: device pointers, peers mapped through symmetric memory; summed in rank order), applies the Adam
  * update to its slice of m, v and params, and stores the updated parameters into every rank's parameter buffer
  * (params_ptrs[world]).  m and v are this rank's full-size buffers (only [lo, hi) is touched).  The caller puts a
- * cross-rank barrier before (all gradients written) and after (all slices delivered) the call.  world <= 16. */
+ * cross-rank barrier before (all gradients written) and after (all slices delivered) the call.  world <= 16.
+ * grads_multicast / params_multicast (both or neither): NVLS multicast mappings of the same two buffers; when given,
+ * the sum is one multimem.ld_reduce (reduced inside the NVSwitch, order chosen by the hardware) and the broadcast one
+ * multimem.st, instead of world peer loads and world peer stores. */
 int cc_adam_step_p2p(const void* const* grads_ptrs, void* const* params_ptrs, int world, int rank, float* m, float* v,
                      int64_t lo, int64_t hi, const int64_t* step_ptr, float lr, float beta1, float beta2, float eps,
-                     void* stream);
+                     const void* grads_multicast, void* params_multicast, void* stream);
 int cc_round_tf32(const float* x, float* out, int64_t n, void* stream);
 int cc_sigmoid_f32(const float* z, float* out, int64_t n, void* stream);
 

@@ -167,7 +167,7 @@ def test_adam_p2p_emulated_ranks_equal_plain_adam():
             total += t                                         # rank order, like the kernel
         for r in range(world):
             E.call("cc_adam_step_p2p", E.ptr(gp), E.ptr(pp), world, r, E.ptr(ms[r]), E.ptr(vs[r]), bounds[r], bounds[r + 1],
-                   E.ptr(step), *hp, E.stream_ptr())
+                   E.ptr(step), *hp, None, None, E.stream_ptr())
         E.call("cc_adam_step", E.ptr(ref_p), E.ptr(total), E.ptr(ref_m), E.ptr(ref_v), n, E.ptr(step), *hp, None,
                E.stream_ptr())
         E.call("cc_step_increment", E.ptr(step), E.stream_ptr())
