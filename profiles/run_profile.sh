@@ -19,7 +19,7 @@ echo "full capture rc=$?"
 REP=$OUT/${TAG}_prof_step.ncu-rep
 if [ -f $REP ]; then
   ncu -i $REP --page raw --csv > $OUT/${TAG}_prof_step_raw.csv 2>/dev/null
-  ncu -i $REP --page source --csv -k regex:gemm_tc_kernel -c 2 -s 8 > $OUT/${TAG}_src_gemm.csv 2>/dev/null
+  ncu -i $REP --page source --csv -k regex:gemm_tc_kernelILi0ELi1 -c 1 > $OUT/${TAG}_src_gemm_bce.csv 2>/dev/null
   ls -la $REP
   [ $(stat -c %s $REP) -gt 40000000 ] && rm -f $REP
 fi

@@ -366,3 +366,44 @@ def test_model_call_api_parity():
     assert np.abs(reg.cpu().numpy() - od.softmax_np(z2)).max() < 1e-6
     lat = model.encoder(x)
     assert lat.shape == (8, 64)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_host_batch_stream_equals_device_resident_steps(precision):
+    """ml.engine.HostBatchStream (pinned host CSR -> double-buffered H2D on a copy stream, loss read back one
+    step late) must train exactly like the device-resident path: same seeds, same cubes => identical losses."""
+    from cubecobrarecommender_b200 import graph as G
+    c, k, b = 384, 96, 32
+    ip, ix = synth_cubes_csr(k, c, size_lo=12, size_hi=70, seed=7)
+    csr = CubeCSR(ip, ix, c)
+    gr = G.build_graph(csr, "cuda", want_m64=False)
+    prob, alias = E.alias_table(gr.neg_sampler.cpu().numpy(), "cuda")
+    params = od.init_params(c, seed=0)
+    losses = []
+    for mode in ("device", "host"):
+        model = M.CC_Recommender(c, device="cuda", precision=precision)
+        model.set_weights_dict(params)
+        eng = E.DAEEngine(model, gr.mhat, batch=b, reg_rows=b, reg=0.1, max_cube_size=80)
+        out = []
+        if mode == "device":
+            indptr, indices = G.upload_csr(csr, "cuda")
+            for i in range(5):
+                ids = torch.arange((i % 3) * b, (i % 3 + 1) * b, dtype=torch.int32, device="cuda")
+                eng.sample_batch(indptr, indices, ids, prob, alias, 0.2, 0.1, seed=11)
+                out.append(eng.train_step().cpu().numpy().copy())
+        else:
+            feed = E.HostBatchStream(eng, [csr.rows(np.arange(j * b, (j + 1) * b)) for j in range(3)])
+            for i in range(5):
+                l = feed.step(i, prob, alias, 0.2, 0.1, seed=11)
+                assert (l is None) == (i == 0)
+                if l is not None:
+                    out.append(l)
+            out.append(feed.drain())
+            assert feed.h2d_bytes > 0
+        eng.check_overflow()
+        losses.append(np.array(out))
+    assert losses[0].shape == (5, 3)
+    if precision == "fp32":
+        assert np.array_equal(losses[0], losses[1])
+    else:       # the fused BCE epilogue reduces the bias gradient with float atomics: last bits vary run to run
+        assert np.allclose(losses[0], losses[1], rtol=1e-5, atol=0)
