@@ -400,6 +400,26 @@ static int warpselect_launch(const float* scores, int64_t ld, int32_t num_cards,
 // the radix-select kernel stays the general path (any n, float64); float32 with n <= 128 takes the streaming select
 static int g_topn_force_radix = 0;
 
+// ------------------------------------------------------------------ card similarity
+// dist[r] = -cos(emb[r], emb[q]) with Keras' l2_normalize (x * rsqrt(max(sum x^2, 1e-12))), one warp per row
+// (reference src/scripts/similarity.py:25-29 evaluates the Keras CosineSimilarity loss once per card in a Python loop)
+__global__ void __launch_bounds__(256)
+cosine_neg_kernel(const float* __restrict__ emb, int64_t ld, int32_t rows, int32_t dim, int32_t query,
+                  float* __restrict__ out) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* a = emb + int64_t(query) * ld;
+  const float* b = emb + int64_t(r) * ld;
+  float ab = 0.f, aa = 0.f, bb = 0.f;
+  for (int k = lane; k < dim; k += 32) {
+    const float x = a[k], y = b[k];
+    ab = fmaf(x, y, ab); aa = fmaf(x, x, aa); bb = fmaf(y, y, bb);
+  }
+  ab = warp_sum(ab); aa = warp_sum(aa); bb = warp_sum(bb);
+  if (lane == 0) out[r] = -(ab * rsqrtf(fmaxf(aa, 1e-12f)) * rsqrtf(fmaxf(bb, 1e-12f)));
+}
+
 static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 template <typename T>
@@ -518,6 +538,13 @@ int cc_topn_masked_sigmoid_f32(const float* logits, int64_t ld, int32_t num_card
   if (batch == 0) return CC_OK;
   return warpselect_launch<true>(logits, ld, num_cards, batch, mask_ptr, mask_idx, mode_only_listed, descending, n,
                                  out_ids, out_probs, out_count, as_stream(stream));
+}
+
+int cc_cosine_neg_f32(const float* emb, int64_t ld, int32_t rows, int32_t dim, int32_t query, float* out, void* stream) {
+  CC_REQUIRE(emb && out && rows > 0 && dim > 0 && ld >= dim && query >= 0 && query < rows, "cc_cosine_neg_f32: bad arguments");
+  cosine_neg_kernel<<<ceil_div(rows, 8), 256, 0, as_stream(stream)>>>(emb, ld, rows, dim, query, out);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
 }
 
 // 1 = keep float32 top-N on the radix-select kernel even for small n (tests compare the two kernels)

@@ -74,6 +74,28 @@ class MLRecommender:
         ids, vals, cnts = self.recommend_device(csr, amount)
         return ids.cpu().numpy(), vals.cpu().numpy(), cnts.cpu().numpy()
 
+    # -- card similarity (reference src/scripts/similarity.py) -------------------------------------------
+    def card_embeddings(self) -> torch.Tensor:
+        """``model.encoder(I)``: the 64-d embedding of every card, (C, 64) float32 on the device.  The one-hot rows
+        are never built: row r of I is the index list [r] for the embedding-bag first layer."""
+        m = self.model
+        rows = torch.arange(m.N, dtype=torch.int32, device=m.device)
+        return m._encode(SparseBatch.from_rows(rows))
+
+    def similar(self, card_idx: int, n: int, embeddings: torch.Tensor | None = None):
+        """The ``n`` cards most similar to ``card_idx``: ``(ids, dists)`` ranked like the reference's
+        ``dists.argsort()`` (similarity.py:31), dists = Keras CosineSimilarity loss = -cosine (the card itself
+        comes first with -1).  Ties: smaller index first (stable argsort)."""
+        m = self.model
+        emb = self.card_embeddings() if embeddings is None else embeddings
+        dists = torch.empty((1, m.N), dtype=torch.float32, device=m.device)
+        call("cc_cosine_neg_f32", ptr(emb), emb.stride(0), m.N, emb.shape[1], int(card_idx), ptr(dists), stream_ptr())
+        n = max(1, min(int(n), m.N))
+        none_ptr = torch.zeros(2, dtype=torch.int64, device=m.device)          # empty mask: every card is a candidate
+        none_idx = torch.zeros(1, dtype=torch.int32, device=m.device)
+        ids, vals, cnt = topn_masked(dists, none_ptr, none_idx, n, only_listed=False, descending=False)
+        return ids[0].cpu().numpy(), vals[0].cpu().numpy()
+
     def recommend_one(self, cube_indices, amount, int_to_card):
         """The ``{"additions": {...}, "cuts": {...}}`` dict of reference web/ml_recommend_web.py:48-67."""
         num_cards = self.model.N

@@ -110,6 +110,9 @@ int cc_topn_masked_sigmoid_f32(const float* logits, int64_t ld, int32_t num_card
                                const int64_t* mask_ptr, const int32_t* mask_idx, int mode_only_listed, int descending,
                                int32_t n, int32_t* out_ids, float* out_probs, int32_t* out_count, void* stream);
 int cc_topn_set_force_radix(int on);
+/* Card similarity (src/scripts/similarity.py:25-29): out[r] = -cos(emb[r], emb[query]) with Keras' l2_normalize
+ * (epsilon 1e-12), emb float32 [rows][ld >= dim]; rank ascending with cc_topn_masked_f32. */
+int cc_cosine_neg_f32(const float* emb, int64_t ld, int32_t rows, int32_t dim, int32_t query, float* out, void* stream);
 int cc_topn_masked_f64(const double* scores, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
                        const int32_t* mask_idx, int mode_only_listed, int descending, int32_t n, void* workspace,
                        int64_t workspace_bytes, int32_t* out_ids, double* out_vals, int32_t* out_count, void* stream);

@@ -172,6 +172,24 @@ def rank_additions(results, in_cube, amount):
     return out
 
 
+def card_embeddings_np(params):
+    """``model.encoder(I)`` (reference ``src/scripts/similarity.py:19-24``): the encoder applied to every
+    one-hot card, i.e. ``relu(W1 + b1)`` pushed through the three remaining encoder layers.  float64 (C, 64)."""
+    p = {k: v.astype(np.float64) for k, v in params.items()}
+    h = np.maximum(p["encoder_e1/kernel"] + p["encoder_e1/bias"], 0.0)
+    for n in ("encoder_e2", "encoder_e3", "encoder_bottleneck"):
+        h = np.maximum(h @ p[n + "/kernel"] + p[n + "/bias"], 0.0)
+    return h
+
+
+def similarity_np(embs, idx):
+    """Keras ``CosineSimilarity()(embs[idx], x)`` for every row x (reference ``similarity.py:27-29``):
+    ``-sum(l2_normalize(a) * l2_normalize(b))`` with ``l2_normalize(v) = v / sqrt(max(sum v^2, 1e-12))``
+    [Keras-2.5 losses.cosine_similarity].  The caller ranks with ``argsort()`` ascending."""
+    n = embs / np.sqrt(np.maximum((embs * embs).sum(1, keepdims=True), 1e-12))
+    return -(n @ n[idx])
+
+
 # ---------------------------------------------------------------- torch CPU
 class TorchDAE:
     """torch restatement used (a) as the second, autograd formulation and

@@ -137,3 +137,34 @@ def test_datagenerator_mirror_and_fit():
     assert len(hist) == 6 and hist[-1]["loss"] < hist[0]["loss"]                 # it trains
     assert abs(hist[0]["loss"] - (hist[0]["output_1_loss"] + 0.1 * hist[0]["output_2_loss"])) < 1e-9
     assert int(model.store.step.item()) == 18
+
+
+def test_similarity_script_and_kernel_vs_oracle(tmp_path, capsys):
+    """scripts/similarity.py (reference src/scripts/similarity.py): encoder embeddings of all one-hot cards, Keras
+    CosineSimilarity loss against one card, ascending argsort.  Checked against the float64 restatement; ids must
+    match wherever the oracle's distances are separated by more than the float32 tolerance."""
+    from cubecobrarecommender_b200.scripts import similarity as SIM
+    c = 300
+    params = od.init_params(c, seed=3)
+    model = M.CC_Recommender(c, device="cuda", precision="fp32")
+    model.set_weights_dict(params)
+    model.save(str(tmp_path / "ml_files/high_req"))
+    i2c = {str(i): f"card {i}" for i in range(c)}
+    json.dump(i2c, open(tmp_path / "id_map.json", "w"))
+    rec = INF.MLRecommender(model)
+    emb = rec.card_embeddings().cpu().numpy()
+    ref_emb = od.card_embeddings_np(params)
+    assert np.abs(emb - ref_emb).max() < 1e-5
+    for q in (0, 17, 299):
+        ids, dists = rec.similar(q, 25)
+        ref = od.similarity_np(ref_emb, q)
+        assert ids[0] == q and abs(dists[0] + 1.0) < 1e-6                  # the card itself: cosine 1
+        assert np.abs(dists - ref[ids]).max() < 1e-5
+        order = ref.argsort(kind="stable")[:25]
+        gaps_ok = np.abs(np.diff(ref[order])) > 1e-5                       # well separated neighbours
+        same = ids == order
+        assert same[:-1][gaps_ok[:-1] & gaps_ok[1:]].all() if len(order) > 2 else True
+        assert (np.diff(dists) >= 0).all()
+    out = SIM.main(["card_17", "5"], model_dir=str(tmp_path / "ml_files/high_req"), id_map=str(tmp_path / "id_map.json"))
+    printed = capsys.readouterr().out.strip().splitlines()
+    assert len(out) == 5 and out[0][0] == "card 17" and printed[0].startswith("1: card 17 -1")

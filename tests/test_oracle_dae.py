@@ -103,3 +103,20 @@ def test_float32_train_steps_track_float64():
 def test_rank_additions_tie_rule():
     res = np.array([0.5, 0.9, 0.9, 0.1, 0.9]); in_cube = np.array([0, 0, 1, 0, 0])
     assert dae.rank_additions(res, in_cube, 3) == [4, 1, 0]
+
+
+def test_similarity_restatement_known_answers():
+    """Keras CosineSimilarity loss as the reference's similarity.py uses it: -cos, l2_normalize with eps 1e-12."""
+    from oracle import dae as od
+    embs = np.array([[3.0, 4.0], [6.0, 8.0], [4.0, -3.0], [0.0, 0.0], [-3.0, -4.0]])
+    d = od.similarity_np(embs, 0)
+    assert np.allclose(d, [-1.0, -1.0, 0.0, 0.0, 1.0])           # itself, parallel, orthogonal, zero vector, opposite
+    assert d.argsort(kind="stable")[0] == 0
+    # card_embeddings_np == encoder applied to the dense identity (what the reference feeds Keras)
+    params = od.init_params(40, seed=1)
+    eye = np.eye(40)
+    p = {k: v.astype(np.float64) for k, v in params.items()}
+    h = eye
+    for n in ("encoder_e1", "encoder_e2", "encoder_e3", "encoder_bottleneck"):
+        h = np.maximum(h @ p[n + "/kernel"] + p[n + "/bias"], 0.0)
+    assert np.allclose(od.card_embeddings_np(params), h, atol=1e-14)
