@@ -11,6 +11,9 @@
 //   counts int32  [C][ld]          counts[i][j] = |{k : i in cube k and j in cube k}|
 //   M      float64 [C][C]          counts[i][j]/counts[i][i]   (utils.py:85-89)
 //   M-hat  float32 [C][ld_mhat]    diag<-1, row / row sum      (train.py:69-71)
+#include <thread>
+#include <vector>
+
 #include "cc_common.cuh"
 
 namespace cc {
@@ -338,6 +341,60 @@ int cc_col_mass(const int32_t* counts, int64_t ld, int32_t num_cards, const doub
   return CC_OK;
 }
 
+// Device -> pageable host delivery of a large result (3.5 GB of float64 at C = 21k).  A plain cudaMemcpy into freshly
+// allocated pageable memory is bound by first-touch page faults and the driver's single staging path (0.8-3 s
+// measured); here T host threads each own a slice: D2H into their own pinned staging buffer on their own stream,
+// then memcpy into the destination -- the page faults and the copies run in parallel.
+static int copy_to_host_parallel(void* dst_host, const void* src_dev, size_t bytes) {
+  if (bytes == 0) return CC_OK;
+  unsigned hw = std::thread::hardware_concurrency();
+  int T = int(hw ? (hw < 8 ? hw : 8) : 4);
+  const size_t CH = size_t(16) << 20;                       // staging chunk per thread
+  if (bytes < 4 * CH) T = 1;
+  int dev = 0;
+  CC_CHECK_CUDA(cudaGetDevice(&dev));
+  std::vector<int> rcs(T, 0);
+  std::vector<std::thread> th;
+  const size_t per = ((bytes + T - 1) / T + 255) & ~size_t(255);
+  for (int t = 0; t < T; ++t) {
+    th.emplace_back([&, t]() {
+      const size_t lo = size_t(t) * per, hi = lo + per < bytes ? lo + per : bytes;
+      if (lo >= hi) return;
+      cudaSetDevice(dev);
+      cudaStream_t st = nullptr; void* pin[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr};
+      auto fail = [&](cudaError_t e) { rcs[t] = int(e) ? int(e) : -1; };
+      cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+      for (int b = 0; b < 2 && e == cudaSuccess; ++b) { e = cudaHostAlloc(&pin[b], CH, cudaHostAllocDefault); if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming); }
+      if (e != cudaSuccess) fail(e);
+      // two staging buffers: the DMA of chunk i+1 overlaps the memcpy of chunk i
+      size_t off = lo; int b = 0; size_t pend_off[2] = {0, 0}, pend_n[2] = {0, 0}; bool pend[2] = {false, false};
+      while (rcs[t] == 0 && (off < hi || pend[0] || pend[1])) {
+        if (pend[b]) {
+          e = cudaEventSynchronize(ev[b]);
+          if (e != cudaSuccess) { fail(e); break; }
+          memcpy(static_cast<char*>(dst_host) + pend_off[b], pin[b], pend_n[b]);
+          pend[b] = false;
+        }
+        if (off < hi) {
+          const size_t n = hi - off < CH ? hi - off : CH;
+          e = cudaMemcpyAsync(pin[b], static_cast<const char*>(src_dev) + off, n, cudaMemcpyDeviceToHost, st);
+          if (e == cudaSuccess) e = cudaEventRecord(ev[b], st);
+          if (e != cudaSuccess) { fail(e); break; }
+          pend_off[b] = off; pend_n[b] = n; pend[b] = true; off += n;
+        }
+        b ^= 1;
+      }
+      if (st) cudaStreamSynchronize(st);
+      for (int q = 0; q < 2; ++q) { if (pin[q]) cudaFreeHost(pin[q]); if (ev[q]) cudaEventDestroy(ev[q]); }
+      if (st) cudaStreamDestroy(st);
+    });
+  }
+  for (auto& x : th) x.join();
+  for (int t = 0; t < T; ++t)
+    if (rcs[t] != 0) { set_error("copy_to_host_parallel: CUDA error %d in worker %d", rcs[t], t); return CC_ERR_CUDA; }
+  return CC_OK;
+}
+
 // Host-buffer entry: the drop-in for utils.create_adjacency_matrix (utils.py:75-92) on
 // CSR cubes.  Copies H2D, builds on `device`'s current context, copies M back (float64).
 int cc_create_adjacency_matrix_host(const int64_t* indptr_host, const int32_t* indices_host, int64_t num_cubes,
@@ -374,15 +431,14 @@ int cc_create_adjacency_matrix_host(const int64_t* indptr_host, const int32_t* i
   }
   if ((rc = cc_row_normalise(d_counts, num_cards, num_cards, d_m, num_cards, nullptr, 0, nullptr, has_force_diag,
                              force_diag, st)) != CC_OK) goto done;
-  CC_TRY(cudaMemcpyAsync(m_host, d_m, size_t(num_cards) * num_cards * 8, cudaMemcpyDeviceToHost, st));
-  if (counts_host)
-    CC_TRY(cudaMemcpyAsync(counts_host, d_counts, size_t(num_cards) * num_cards * 4, cudaMemcpyDeviceToHost, st));
   {
     int bad = 0;
     CC_TRY(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     CC_TRY(cudaStreamSynchronize(st));
-    if (bad) { set_error("cc_create_adjacency_matrix_host: card index out of range [0,%d)", num_cards); rc = CC_ERR_ARGUMENT; }
+    if (bad) { set_error("cc_create_adjacency_matrix_host: card index out of range [0,%d)", num_cards); rc = CC_ERR_ARGUMENT; goto done; }
   }
+  if ((rc = copy_to_host_parallel(m_host, d_m, size_t(num_cards) * num_cards * 8)) != CC_OK) goto done;
+  if (counts_host && (rc = copy_to_host_parallel(counts_host, d_counts, size_t(num_cards) * num_cards * 4)) != CC_OK) goto done;
 done:
 #undef CC_TRY
   cudaFree(d_indptr); cudaFree(d_indices); cudaFree(d_bits); cudaFree(d_counts); cudaFree(d_m); cudaFree(d_bad);

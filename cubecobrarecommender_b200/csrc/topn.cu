@@ -330,13 +330,33 @@ topn_warpselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num
   const float* sc = scores + int64_t(cube) * ld;
   unsigned long long thr = 0;                   // keys must beat this to enter the buffer
   int cnt = 0;                                  // live keys in buf (warp-uniform)
+  // SIGMOID: a logit bound that lets almost every element skip the sigmoid (expf + division) altogether.  Keys are
+  // built from float32 sigmoid(z) so that saturated scores tie exactly as in the reference; sigmoid is monotone, so
+  // an element can only beat the threshold score p_thr if z lies on the right side of logit(p_thr).  The bound is
+  // taken 1e-6 relative (~16 float32 ulps) on the safe side of p_thr, which covers the few-ulp error of sigmoid_f32:
+  // no element whose key would enter the buffer is ever rejected.  (NaN logits fail the test and are skipped.)
+  float zbound = descending ? -INFINITY : INFINITY;
 
   auto prune = [&]() {
     __syncwarp();
     for (int i = cnt + lane; i < WS_CAP; i += 32) buf[i] = 0;
     __syncwarp();
     warp_bitonic_desc(buf, lane);
-    if (cnt >= n_eff && n_eff > 0) { thr = buf[n_eff - 1]; cnt = n_eff; }
+    if (cnt >= n_eff && n_eff > 0) {
+      thr = buf[n_eff - 1]; cnt = n_eff;
+      if (SIGMOID) {
+        uint32_t u = (uint32_t)(thr >> 32);
+        if (!descending) u = ~u;
+        const double p = double(__uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u));
+        if (descending) {
+          const double pm = p * (1.0 - 1e-6) - 1e-40;
+          zbound = pm <= 0.0 ? -INFINITY : float(log(pm / (1.0 - pm))) - 1e-3f;
+        } else {
+          const double pp = p * (1.0 + 1e-6) + 1e-40;
+          zbound = pp >= 1.0 ? INFINITY : float(log(pp / (1.0 - pp))) + 1e-3f;
+        }
+      }
+    }
   };
 
   if (n_eff > 0) {
@@ -350,6 +370,7 @@ topn_warpselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num
         const uint32_t mw = wi < words ? mask[wi] : 0u;
         cand[u] = e < num_cards && ((((mw >> lane) & 1u) != 0) == (mode_only_listed != 0));
         v[u] = cand[u] ? sc[e] : 0.f;
+        if (SIGMOID) cand[u] = cand[u] && (descending ? v[u] >= zbound : v[u] <= zbound);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {

@@ -40,37 +40,54 @@ class MLRecommender:
     FUSED_MAX_N = 128        # cc_topn_masked_sigmoid_f32's limit (warp-per-cube streaming select)
 
     def recommend_device(self, csr: CubeCSR, amount: int):
-        """Device-resident form: the whole CSR is uploaded once, the cubes run through encoder, decoder and the
-        masked select in chunks of ``self.chunk`` with NO host synchronisation in between, and the results stay
-        on the device: (add_ids int32 (K, n), add_scores float32 (K, n), counts int32 (K,))."""
+        """The cubes run through encoder, decoder and the masked select in chunks of ``self.chunk`` with NO host
+        synchronisation in between; chunk i+1's CSR rows are uploaded on a copy stream while chunk i computes, and
+        the results stay on the device: (add_ids int32 (K, n), add_scores float32 (K, n), counts int32 (K,))."""
         m = self.model
         dev = m.device
         k = csr.num_cubes
         n = max(1, min(int(amount), csr.num_cards))
-        indptr = torch.from_numpy(np.ascontiguousarray(csr.indptr, dtype=np.int64)).to(dev, non_blocking=True)
-        idx_h = np.ascontiguousarray(csr.indices, dtype=np.int32)
-        indices = torch.from_numpy(idx_h if len(idx_h) else np.zeros(1, np.int32)).to(dev, non_blocking=True)
-        row_len = (indptr[1:] - indptr[:-1]).to(torch.int32)
+        ip = np.ascontiguousarray(csr.indptr, dtype=np.int64)
+        ix = np.ascontiguousarray(csr.indices, dtype=np.int32)
         ids = torch.empty((k, n), dtype=torch.int32, device=dev)
         vals = torch.empty((k, n), dtype=torch.float32, device=dev)
         cnts = torch.empty(k, dtype=torch.int32, device=dev)
         fused = n <= self.FUSED_MAX_N
-        for lo in range(0, k, self.chunk):
+        compute = torch.cuda.current_stream(dev)
+        copier = self._copy_stream = getattr(self, "_copy_stream", None) or torch.cuda.Stream(device=dev)
+
+        def upload(lo):
             hi = min(lo + self.chunk, k)
-            # rows lo..hi of the resident CSR: absolute offsets into `indices`, nothing is copied
-            sb = SparseBatch(indices, indptr[lo:hi], row_len[lo:hi])
+            rows_h = ix[ip[lo]:ip[hi]]
+            with torch.cuda.stream(copier):
+                idx = torch.from_numpy(rows_h if len(rows_h) else np.zeros(1, np.int32)).to(dev, non_blocking=True)
+                ptr_ = torch.from_numpy(ip[lo:hi + 1] - ip[lo]).to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copier)
+            for t in (idx, ptr_):
+                t.record_stream(compute)           # allocated on the copy stream, consumed on the compute stream
+            return lo, hi, idx, ptr_, ev
+
+        nxt = upload(0) if k else None
+        while nxt is not None:
+            lo, hi, idx, ptr_, ev = nxt
+            nxt = upload(hi) if hi < k else None   # overlaps this chunk's kernels
+            compute.wait_event(ev)
+            row_len = (ptr_[1:] - ptr_[:-1]).to(torch.int32)
+            sb = SparseBatch(idx, ptr_[:-1], row_len)
             z = m._decode(m._encode(sb), "main")
             out = (ids[lo:hi], vals[lo:hi], cnts[lo:hi])
             if fused:    # sigmoid applied inside the select: the probability rows are never written
-                topn_masked(z, indptr[lo:hi + 1], indices, n, sigmoid=True, out=out)
+                topn_masked(z, ptr_, idx, n, sigmoid=True, out=out)
             else:
                 full = z._base if z._base is not None else z
                 call("cc_sigmoid_f32", ptr(full), ptr(full), full.numel(), stream_ptr())
-                topn_masked(z, indptr[lo:hi + 1], indices, n, out=out)
+                topn_masked(z, ptr_, idx, n, out=out)
         return ids, vals, cnts
 
     def recommend(self, csr: CubeCSR, amount: int):
-        """Returns (add_ids int32 (K, n), add_scores float32 (K, n), counts int32 (K,)) on the host."""
+        """Returns (add_ids int32 (K, n), add_scores float32 (K, n), counts int32 (K,)) on the host.  Pass a
+        ``csr.pin_memory()`` batch to make the chunk uploads asynchronous."""
         ids, vals, cnts = self.recommend_device(csr, amount)
         return ids.cpu().numpy(), vals.cpu().numpy(), cnts.cpu().numpy()
 

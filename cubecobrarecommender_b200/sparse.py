@@ -63,6 +63,17 @@ class CubeCSR:
             indices = np.zeros(0, dtype=np.int32)
         return CubeCSR(indptr, indices, self.num_cards)
 
+    def pin_memory(self) -> "CubeCSR":
+        """The same cubes in page-locked host memory (one host copy): uploads from it are asynchronous DMA at PCIe
+        speed instead of staged pageable copies (measured: 216 MB in 4.4 ms instead of 19 ms).  The arrays are NumPy
+        views of pinned torch tensors, which are kept alive on the returned object."""
+        import torch
+        tp = torch.from_numpy(np.ascontiguousarray(self.indptr, dtype=np.int64)).pin_memory()
+        ti = torch.from_numpy(np.ascontiguousarray(self.indices, dtype=np.int32)).pin_memory()
+        out = CubeCSR(tp.numpy(), ti.numpy(), self.num_cards)
+        out._pinned = (tp, ti)
+        return out
+
     def shard(self, rank: int, world: int) -> "CubeCSR":
         """Contiguous cube shard for data-parallel ranks."""
         k = self.num_cubes

@@ -385,11 +385,10 @@ def test_host_batch_stream_equals_device_resident_steps(precision):
         model.set_weights_dict(params)
         eng = E.DAEEngine(model, gr.mhat, batch=b, reg_rows=b, reg=0.1, max_cube_size=80)
         out = []
-        if mode == "device":
-            indptr, indices = G.upload_csr(csr, "cuda")
-            for i in range(5):
-                ids = torch.arange((i % 3) * b, (i % 3 + 1) * b, dtype=torch.int32, device="cuda")
-                eng.sample_batch(indptr, indices, ids, prob, alias, 0.2, 0.1, seed=11)
+        if mode == "device":      # the same per-step batches, uploaded synchronously (the noise draws are keyed by the
+            for i in range(5):    # cube's position in the CSR it is read from, so both paths must see the same CSRs)
+                indptr, indices = G.upload_csr(csr.rows(np.arange((i % 3) * b, (i % 3 + 1) * b)), "cuda")
+                eng.sample_batch(indptr, indices, None, prob, alias, 0.2, 0.1, seed=11)
                 out.append(eng.train_step().cpu().numpy().copy())
         else:
             feed = E.HostBatchStream(eng, [csr.rows(np.arange(j * b, (j + 1) * b)) for j in range(3)])
@@ -403,7 +402,7 @@ def test_host_batch_stream_equals_device_resident_steps(precision):
         eng.check_overflow()
         losses.append(np.array(out))
     assert losses[0].shape == (5, 3)
-    if precision == "fp32":
-        assert np.array_equal(losses[0], losses[1])
-    else:       # the fused BCE epilogue reduces the bias gradient with float atomics: last bits vary run to run
-        assert np.allclose(losses[0], losses[1], rtol=1e-5, atol=0)
+    # float atomics (first-layer scatter-add in fp32 mode, bias-gradient column sums in the fused BCE epilogue) make
+    # the last bits of a step vary from run to run, so the two runs agree to rounding, not bit for bit
+    assert np.array_equal(losses[0][0], losses[1][0])          # first step: identical weights, identical batch
+    assert np.allclose(losses[0], losses[1], rtol=1e-5, atol=0)

@@ -233,3 +233,40 @@ def test_topn_fused_sigmoid_equals_sigmoid_then_select():
     for x, y in zip(fused, two_pass):
         assert torch.equal(x, y)
     assert (fused[1] == 1.0).any()          # the tie rule was exercised on saturated scores
+    # every mode of the select (the logit pre-filter has a lower-bound and an upper-bound form), rows sorted both
+    # ways (worst / best case for the running threshold) and a row of identical logits
+    z2 = z.copy()
+    z2[0] = np.sort(z2[0]); z2[1] = np.sort(z2[1])[::-1]; z2[2] = 0.25
+    logits2 = torch.from_numpy(z2).cuda()
+    call("cc_sigmoid_f32", ptr(logits2), ptr(probs), logits2.numel(), stream_ptr())
+    for only_listed, desc in ((False, True), (True, False), (False, False), (True, True)):
+        a = G.topn_masked(logits2, mp, mi, n, sigmoid=True, only_listed=only_listed, descending=desc)
+        b = G.topn_masked(probs, mp, mi, n, only_listed=only_listed, descending=desc)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y), (only_listed, desc)
+
+
+def test_scale_up_card_count_properties():
+    """configs[4] card count (C = 100 000; the reference cannot even allocate this dense): one pass of the tensor-core
+    count kernel over 8 192 cubes, checked through size-independent properties (the oracle would take hours):
+    diag = card frequency, total = sum of s^2, symmetry on a million sampled pairs, and agreement with the popcount
+    kernel on a 2 048 x 2 048 corner block."""
+    k, c = 8192, 100_000
+    ip, ix = synth_cubes_csr(k, c, size_lo=360, size_hi=720, seed=31)
+    a, b = G.upload_csr(CubeCSR(ip, ix, c), "cuda")
+    cnt = G.count_cooccurrence(a, b, k, c, method="tensor")
+    sizes = torch.from_numpy(np.diff(ip)).cuda()
+    freq = torch.bincount(b.long(), minlength=c)
+    assert torch.equal(cnt.diagonal().long(), freq)
+    assert int(cnt.sum(dtype=torch.int64)) == int((sizes.long() ** 2).sum())
+    g = torch.Generator(device="cuda").manual_seed(1)
+    i = torch.randint(0, c, (1_000_000,), device="cuda", generator=g)
+    j = torch.randint(0, c, (1_000_000,), device="cuda", generator=g)
+    assert torch.equal(cnt[i, j], cnt[j, i])
+    # popular cards (low ids under the Zipf law) against the popcount kernel restricted to those cards
+    keep = b < 2048
+    sub_len = torch.zeros(k, dtype=torch.int64, device="cuda").scatter_add_(
+        0, torch.repeat_interleave(torch.arange(k, device="cuda"), sizes.long())[keep], torch.ones(int(keep.sum()), dtype=torch.int64, device="cuda"))
+    sub_ip = torch.cat([torch.zeros(1, dtype=torch.int64, device="cuda"), sub_len.cumsum(0)])
+    ref = G.count_cooccurrence(sub_ip, b[keep].contiguous(), k, 2048, method="popcount")
+    assert torch.equal(cnt[:2048, :2048], ref)
