@@ -330,7 +330,9 @@ topn_warpselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num
   const float* sc = scores + int64_t(cube) * ld;
   unsigned long long thr = 0;                   // keys must beat this to enter the buffer
   int cnt = 0;                                  // live keys in buf (warp-uniform)
-  // SIGMOID: a logit bound that lets almost every element skip the sigmoid (expf + division) altogether.  Keys are
+  // zbound: a bound on the RAW value that lets almost every element skip the key (and, fused, the sigmoid: expf +
+  // division) altogether.  Plain scores: the threshold's own score (ties still go through the exact key compare).
+  // SIGMOID: keys are
   // built from float32 sigmoid(z) so that saturated scores tie exactly as in the reference; sigmoid is monotone, so
   // an element can only beat the threshold score p_thr if z lies on the right side of logit(p_thr).  The bound is
   // taken 1e-6 relative (~16 float32 ulps) on the safe side of p_thr, which covers the few-ulp error of sigmoid_f32:
@@ -344,10 +346,13 @@ topn_warpselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num
     warp_bitonic_desc(buf, lane);
     if (cnt >= n_eff && n_eff > 0) {
       thr = buf[n_eff - 1]; cnt = n_eff;
-      if (SIGMOID) {
-        uint32_t u = (uint32_t)(thr >> 32);
-        if (!descending) u = ~u;
-        const double p = double(__uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u));
+      uint32_t u = (uint32_t)(thr >> 32);
+      if (!descending) u = ~u;
+      const float pthr = __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);   // the threshold's score
+      if (!SIGMOID) {
+        zbound = pthr;        // a raw score can only enter if it is >= (descending) / <= (ascending) the threshold score
+      } else {
+        const double p = double(pthr);
         if (descending) {
           const double pm = p * (1.0 - 1e-6) - 1e-40;
           zbound = pm <= 0.0 ? -INFINITY : float(log(pm / (1.0 - pm))) - 1e-3f;
@@ -359,7 +364,60 @@ topn_warpselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num
     }
   };
 
-  if (n_eff > 0) {
+  // `zbound` pre-filter: the cheap test every element takes; only survivors build a key (and, fused, a sigmoid)
+  auto maybe = [&](float x) -> bool { return descending ? x >= zbound : x <= zbound; };
+  auto offer = [&](bool c, float x, int e) {           // warp-collective: insert the lanes' surviving candidates
+    unsigned long long key = 0;
+    if (c) key = make_key<float>(SIGMOID ? sigmoid_f32(x) : x, (uint32_t)e, descending);
+    const bool pass = key > thr;
+    const unsigned bal = __ballot_sync(0xffffffffu, pass);
+    if (bal) {
+      if (pass) buf[cnt + __popc(bal & ((1u << lane) - 1u))] = key;
+      cnt += __popc(bal);
+      if (cnt > WS_CAP - 32) prune();
+    }
+  };
+  const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(scores) & 15) == 0;
+  if (n_eff > 0 && vec) {
+    // 16-byte loads: a lane takes 4 consecutive scores (and the 4 matching mask bits), two loads in flight; when none
+    // of the warp's 256 elements survives the pre-filter -- the steady state after the first few hundred elements --
+    // the iteration is two loads, eight compares and one vote
+    for (int base = 0; base < num_cards; base += 256) {
+      float4 q[2];
+      uint32_t mb[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int e0 = base + 128 * u + 4 * lane;
+        uint32_t bits = 0u;
+        if (e0 < num_cards) {
+          bits = (mask[e0 >> 5] >> (e0 & 31)) & 0xfu;
+          if (!mode_only_listed) bits ^= 0xfu;
+          if (e0 + 3 >= num_cards) bits &= (1u << (num_cards - e0)) - 1u;      // ragged end of the row
+        }
+        mb[u] = bits;
+        q[u] = bits ? ld_nc_f4(sc + e0) : make_float4(0.f, 0.f, 0.f, 0.f);      // e0 + 3 < ld (ld % 4 == 0)
+      }
+      bool c[2][4];
+      bool any = false;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float x[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { c[u][j] = ((mb[u] >> j) & 1u) && maybe(x[j]); any |= c[u][j]; }
+      }
+      if (!__any_sync(0xffffffffu, any)) continue;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float x[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          // re-test against the bound: it may have tightened since the flags were computed (a prune in between)
+          offer(c[u][j] && maybe(x[j]), x[j], base + 128 * u + 4 * lane + j);
+        }
+      }
+    }
+    prune();
+  } else if (n_eff > 0) {
     for (int base = 0; base < num_cards; base += 128) {
       float v[4];
       bool cand[4];
@@ -370,21 +428,9 @@ topn_warpselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num
         const uint32_t mw = wi < words ? mask[wi] : 0u;
         cand[u] = e < num_cards && ((((mw >> lane) & 1u) != 0) == (mode_only_listed != 0));
         v[u] = cand[u] ? sc[e] : 0.f;
-        if (SIGMOID) cand[u] = cand[u] && (descending ? v[u] >= zbound : v[u] <= zbound);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = base + 32 * u + lane;
-        unsigned long long key = 0;
-        if (cand[u]) key = make_key<float>(SIGMOID ? sigmoid_f32(v[u]) : v[u], (uint32_t)e, descending);
-        const bool pass = key > thr;
-        const unsigned bal = __ballot_sync(0xffffffffu, pass);
-        if (bal) {
-          if (pass) buf[cnt + __popc(bal & ((1u << lane) - 1u))] = key;
-          cnt += __popc(bal);
-          if (cnt > WS_CAP - 32) prune();
-        }
-      }
+      for (int u = 0; u < 4; ++u) offer(cand[u] && maybe(v[u]), v[u], base + 32 * u + lane);
     }
     prune();
   }

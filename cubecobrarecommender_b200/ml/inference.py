@@ -85,10 +85,23 @@ class MLRecommender:
                 topn_masked(z, ptr_, idx, n, out=out)
         return ids, vals, cnts
 
-    def recommend(self, csr: CubeCSR, amount: int):
+    def recommend(self, csr: CubeCSR, amount: int, copy: bool = True):
         """Returns (add_ids int32 (K, n), add_scores float32 (K, n), counts int32 (K,)) on the host.  Pass a
         ``csr.pin_memory()`` batch to make the chunk uploads asynchronous."""
         ids, vals, cnts = self.recommend_device(csr, amount)
+        if not copy:
+            # results land in page-locked buffers owned by this recommender (asynchronous DMA, no page faults on
+            # fresh host memory): the returned arrays are views, valid until the next call
+            k, n = ids.shape
+            buf = getattr(self, "_host_out", None)
+            if buf is None or buf[0].shape[0] < k or buf[0].shape[1] != n:
+                buf = self._host_out = (torch.empty((k, n), dtype=torch.int32).pin_memory(),
+                                        torch.empty((k, n), dtype=torch.float32).pin_memory(),
+                                        torch.empty(k, dtype=torch.int32).pin_memory())
+            for dst, src in zip(buf, (ids, vals, cnts)):
+                dst[:k].copy_(src, non_blocking=True)
+            torch.cuda.current_stream(self.model.device).synchronize()
+            return buf[0][:k].numpy(), buf[1][:k].numpy(), buf[2][:k].numpy()
         return ids.cpu().numpy(), vals.cpu().numpy(), cnts.cpu().numpy()
 
     # -- card similarity (reference src/scripts/similarity.py) -------------------------------------------
