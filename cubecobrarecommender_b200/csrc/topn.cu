@@ -411,8 +411,11 @@ topn_warpselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num
         const float x[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          // re-test against the bound: it may have tightened since the flags were computed (a prune in between)
-          offer(c[u][j] && maybe(x[j]), x[j], base + 128 * u + 4 * lane + j);
+          // re-test against the bound: it may have tightened since the flags were computed (a prune in between);
+          // usually one lane of one (u, j) slot survives, the other seven slots cost a single vote
+          const bool cc = c[u][j] && maybe(x[j]);
+          if (!__any_sync(0xffffffffu, cc)) continue;
+          offer(cc, x[j], base + 128 * u + 4 * lane + j);
         }
       }
     }
