@@ -77,6 +77,11 @@ class DAEEngine:
         self.overlap = self.dp_mode == "nccl_overlap"
         self._dp_ready = False
         self._dynamic_tiles = None
+        # the small layers' weight-gradient GEMMs ([x | 1]^T dY, a few microseconds each, <= 64 CTAs) run on a side
+        # stream, off the dY -> dX -> dY chain that backward is serialised on (CC_SIDE_STREAM=0 keeps one stream)
+        self.use_side = os.environ.get("CC_SIDE_STREAM", "1") != "0" and self.dp_mode != "nccl_overlap"
+        self._side = None
+        self._side_events = []
         self._alloc()
 
     # -- buffers --------------------------------------------------------------------
@@ -213,12 +218,35 @@ class DAEEngine:
         if R:
             towers.append(("reg", self.a[3][B:], self.rd, self.z2, R))
         bce_rows, bce_n = self.row_bce, B
+        main_stream = torch.cuda.current_stream(self.dev)
+        if self.use_side and self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+            self._side_events = [torch.cuda.Event() for _ in range(16)]
+        reg_small_on_side = self.use_side and R > 0
+        if reg_small_on_side:
+            # the reg tower's three small decoder layers run on the side stream, under the main tower's layers and
+            # its big fused-BCE GEMM; the main stream picks them up before the reg tower's 512 -> C GEMM
+            fork, join = self._side_events[12], self._side_events[13]
+            fork.record(main_stream)                       # the shared encoder's output is complete
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(fork)
+                names_r = dec_names("reg")
+                h_r = self.a[3][B:]
+                for i in range(3):
+                    gemm(h_r, W(names_r[i] + "/kernel"), self.rd[i], bias=P(names_r[i] + "/bias"), relu=True, precision=pr,
+                         round_out=tc)
+                    h_r = self.rd[i]; n_launch += 1
+                join.record(self._side)
         for prefix, h, acts, z, rows in towers:
             names = dec_names(prefix)
-            for i in range(3):
-                gemm(h, W(names[i] + "/kernel"), acts[i], bias=P(names[i] + "/bias"), relu=True, precision=pr,
-                     round_out=tc)
-                h = acts[i]; n_launch += 1
+            if prefix == "reg" and reg_small_on_side:
+                main_stream.wait_event(join)
+                h = acts[2]
+            else:
+                for i in range(3):
+                    gemm(h, W(names[i] + "/kernel"), acts[i], bias=P(names[i] + "/bias"), relu=True, precision=pr,
+                         round_out=tc)
+                    h = acts[i]; n_launch += 1
             if tc and prefix == "main":
                 # fused 512 -> C layer + sigmoid-BCE: logits stay in TMEM, only dlogits are written
                 from . import tensorcore
@@ -250,6 +278,18 @@ class DAEEngine:
         # ---------------- backward: decoders ----------------
         ga4 = self.ga[3]
         GKB = s.g_kernel_and_bias           # (in + 1, out) view: kernel gradient rows + the bias gradient row
+        side_used = [0]
+
+        def small_dw(a_1, gy, out):
+            """Weight (+ bias) gradient of a small layer; on the side stream it overlaps the dX chain."""
+            if not self.use_side:
+                gemm(a_1, gy, out, transa=True, precision=pr)
+                return
+            ev = self._side_events[side_used[0]]; side_used[0] += 1
+            ev.record(main_stream)                         # gy (and the activations) are complete here
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(ev)
+                gemm(a_1, gy, out, transa=True, precision=pr)
         gtowers = [("main", self.a[3][:B], self.a_1[3][:B], self.md, self.md_1, self.gmd, self.z1, ga4[:B])]
         if R:
             gtowers.append(("reg", self.a[3][B:], self.a_1[3][B:], self.rd, self.rd_1, self.grd, self.z2, ga4[B:]))
@@ -267,11 +307,11 @@ class DAEEngine:
                 gemm(dzc, W(names[3] + "/kernel"), gacts[2], transb=True, mask=acts[2], precision=pr, round_out=tc)
             n_launch += 1
             for i in (2, 1):
-                gemm(acts_1[i - 1], gacts[i], GKB(names[i]), transa=True, precision=pr)
+                small_dw(acts_1[i - 1], gacts[i], GKB(names[i]))
                 gemm(gacts[i], W(names[i] + "/kernel"), gacts[i - 1], transb=True, mask=acts[i - 1], precision=pr,
                      round_out=tc)
                 n_launch += 2
-            gemm(h_in_1, gacts[0], GKB(names[0]), transa=True, precision=pr)
+            small_dw(h_in_1, gacts[0], GKB(names[0]))
             gemm(gacts[0], W(names[0] + "/kernel"), g_in, transb=True, mask=h_in, precision=pr, round_out=tc)
             n_launch += 2
             self._grads_ready(prefix)
@@ -282,7 +322,7 @@ class DAEEngine:
         # ---------------- backward: shared encoder (main + reg rows together) ----------------
         for i in (3, 2, 1):
             name = ENC_NAMES[i]
-            gemm(self.a_1[i - 1], self.ga[i], GKB(name), transa=True, precision=pr)
+            small_dw(self.a_1[i - 1], self.ga[i], GKB(name))
             gemm(self.ga[i], W(name + "/kernel"), self.ga[i - 1], transb=True, mask=self.a[i - 1], precision=pr,
                  round_out=tc)
             n_launch += 2
@@ -300,6 +340,10 @@ class DAEEngine:
         n_launch += 1
         if R:
             bag_bwd(g1[B:], self.reg_rows, self.reg_start, self.reg_len, gw1); n_launch += 1
+        if side_used[0]:                                   # every gradient is complete before the exchange / Adam
+            done = self._side_events[-1]
+            done.record(self._side)
+            main_stream.wait_event(done)
         self._grads_ready("enc")
         self.launches += n_launch
 
