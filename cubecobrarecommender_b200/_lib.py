@@ -69,7 +69,8 @@ SIGNATURES = {
     "cc_relu_mask_f32": (I, [P, I64, P, I64, I, I, P]),
     # (6) losses / optimiser
     "cc_bce_logits_fwd_bwd": (I, [P, I64, P, I64, I32, I32, I32, D, P, I64, P, P]),
-    "cc_softmax_kl_fwd_bwd": (I, [P, I64, P, I64, P, I32, I32, I32, D, P, I64, P, I, P]),
+    "cc_softmax_kl_fuses_dbias": (I, [I32, I32, I64, I64, I64]),
+    "cc_softmax_kl_fwd_bwd": (I, [P, I64, P, I64, P, I32, I32, I32, D, P, I64, P, I, P, P]),
     "cc_loss_finalize": (I, [P, I32, D, P, I32, D, D, P, P]),
     "cc_adam_step_p2p": (I, [P, P, I, I, P, P, I64, I64, P, F, F, F, F, P, P, P]),
     "cc_adam_step": (I, [P, P, P, P, I64, P, F, F, F, F, P, P]),

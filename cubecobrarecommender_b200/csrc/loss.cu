@@ -241,6 +241,169 @@ softmax_kl_rows_fast_kernel(const float* __restrict__ z, int64_t ldz, const floa
   }
 }
 
+// Persistent form with the bias gradient fused in: one 1024-thread CTA per SM walks rows blockIdx.x, + gridDim.x, ...;
+// the NEXT row's logits stream into the second half of shared memory (cp.async) while the current row is reduced,
+// and every thread keeps the column sums of its dlogits columns in registers across all of the CTA's rows, adding
+// them to dbias once at the end (148 x C atomics per launch instead of a separate 344 MB column-sum pass).
+constexpr int KLP_THREADS = 1024;
+constexpr int KLP_ACC = 7;                 // float4 column accumulators per thread: C <= 4 * 7 * 1024 = 28 672
+
+__device__ __forceinline__ float2 block_sum2_p(float a, float b, float2* red /* smem[32] */) {
+  a = warp_sum(a); b = warp_sum(b);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = make_float2(a, b);
+  __syncthreads();
+  float2 t = red[lane];                    // 32 warps
+  t.x = warp_sum(t.x); t.y = warp_sum(t.y);
+  return t;
+}
+__device__ __forceinline__ float block_max1_p(float a, float2* red) {
+  a = warp_max(a);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid].x = a;
+  __syncthreads();
+  return warp_max(red[lane].x);
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(KLP_THREADS, 1)
+softmax_kl_persistent_kernel(const float* __restrict__ z, int64_t ldz, const float* __restrict__ target, int64_t ldt,
+                             const int32_t* __restrict__ target_rows, int32_t rows, int32_t num_cards, int32_t ncols_pad,
+                             float grad_scale, float* __restrict__ dz, int64_t lddz, double* __restrict__ row_loss,
+                             int round_tf32, float* __restrict__ dbias) {
+  auto EXPF = [](float x) { return FAST ? fast_exp(x) : expf(x); };
+  auto LOGF = [](float x) { return FAST ? fast_log(x) : logf(x); };
+  extern __shared__ __align__(16) float sz[];           // two rows of logits
+  __shared__ float2 red[KLP_THREADS / 32];
+  const int n4 = num_cards >> 2;
+  const int p4 = ncols_pad >> 2;
+  float4 acc[KLP_ACC];
+#pragma unroll
+  for (int k = 0; k < KLP_ACC; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  auto prefetch = [&](int r, int b) {
+    const float4* src = reinterpret_cast<const float4*>(z + int64_t(r) * ldz);
+    float4* dst = reinterpret_cast<float4*>(sz) + size_t(b) * n4;
+    for (int i = threadIdx.x; i < n4; i += KLP_THREADS) {
+      const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst + i));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int buf = 0;
+  int r = blockIdx.x;
+  if (r < rows) prefetch(r, 0);
+  for (; r < rows; r += gridDim.x) {
+    const int rn = r + gridDim.x;
+    if (rn < rows) {
+      prefetch(rn, buf ^ 1);
+      // the next row's TARGET row (a gather out of the 1.7 GB M-hat) is pulled into L2 now, one 128-byte line per thread
+      const char* tn = reinterpret_cast<const char*>(target + int64_t(target_rows ? target_rows[rn] : rn) * ldt);
+      for (int l = threadIdx.x; l * 128 < num_cards * 4; l += KLP_THREADS)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(tn + size_t(l) * 128));
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    }
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const float4* s4 = reinterpret_cast<const float4*>(sz) + size_t(buf) * n4;
+    const float4* t4 = reinterpret_cast<const float4*>(target + int64_t(target_rows ? target_rows[r] : r) * ldt);
+
+    // row maximum and sum of exponentials in ONE sweep and ONE block reduction: every thread keeps (m, s) with
+    // s = sum exp(v - m) over its elements, rescaling s when m grows; pairs merge the same way
+    float tm = -INFINITY, ts = 0.f;
+    for (int i = threadIdx.x; i < n4; i += KLP_THREADS) {
+      const float4 v = s4[i];
+      const float vm = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+      if (vm > tm) { ts *= EXPF(tm - vm); tm = vm; }
+      ts += (EXPF(v.x - tm) + EXPF(v.y - tm)) + (EXPF(v.z - tm) + EXPF(v.w - tm));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, tm, o), os = __shfl_xor_sync(0xffffffffu, ts, o);
+      const float nm = fmaxf(tm, om);
+      ts = (nm == -INFINITY) ? 0.f : ts * EXPF(tm - nm) + os * EXPF(om - nm);
+      tm = nm;
+    }
+    {
+      const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+      __syncthreads();
+      if (lane == 0) red[wid] = make_float2(tm, ts);
+      __syncthreads();
+      float2 t = red[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, t.x, o), os = __shfl_xor_sync(0xffffffffu, t.y, o);
+        const float nm = fmaxf(t.x, om);
+        t.y = (nm == -INFINITY) ? 0.f : t.y * EXPF(t.x - nm) + os * EXPF(om - nm);
+        t.x = nm;
+      }
+      tm = t.x; ts = t.y;
+    }
+    const float mx = tm;
+    const float sumexp = ts;
+    const float inv_sum = 1.f / sumexp;
+    const float lse = mx + LOGF(sumexp);
+    const float log_eps = -16.11809565095832f;               // log(1e-7)
+    float loss = 0.f, sun = 0.f;
+    for (int i = threadIdx.x; i < n4; i += KLP_THREADS) {
+      const float4 v = s4[i];
+      const float4 t = __ldg(t4 + i);
+      const float zz[4] = {v.x, v.y, v.z, v.w}, tt[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float q = EXPF(zz[k] - mx) * inv_sum;
+        const float tc = fminf(fmaxf(tt[k], KERAS_EPS), 1.f);
+        const bool un = (q >= KERAS_EPS) && (q <= 1.f);
+        const float logq = q >= KERAS_EPS ? fminf(zz[k] - lse, 0.f) : log_eps;   // log(clip(q, 1e-7, 1))
+        loss += tc * (LOGF(tc) - logq);
+        sun += un ? tc : 0.f;
+      }
+    }
+    const float2 ls = block_sum2_p(loss, sun, red);
+    if (threadIdx.x == 0) row_loss[r] = double(ls.x);
+    const float S = ls.y;
+    float4* d4 = reinterpret_cast<float4*>(dz + int64_t(r) * lddz);
+#pragma unroll
+    for (int k = 0; k < KLP_ACC + 1; ++k) {
+      const int i = threadIdx.x + k * KLP_THREADS;
+      if (i >= p4) break;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < n4) {
+        const float4 v = s4[i];
+        const float4 t = __ldg(t4 + i);
+        const float zz[4] = {v.x, v.y, v.z, v.w}, tt[4] = {t.x, t.y, t.z, t.w};
+        float gg[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float q = EXPF(zz[e] - mx) * inv_sum;
+          const float tc = fminf(fmaxf(tt[e], KERAS_EPS), 1.f);
+          const bool un = (q >= KERAS_EPS) && (q <= 1.f);
+          gg[e] = (q * S - (un ? tc : 0.f)) * grad_scale;
+          if (round_tf32) gg[e] = rn_tf32(gg[e]);
+        }
+        g = make_float4(gg[0], gg[1], gg[2], gg[3]);
+        if (k < KLP_ACC) { acc[k].x += g.x; acc[k].y += g.y; acc[k].z += g.z; acc[k].w += g.w; }
+      }
+      d4[i] = g;
+    }
+    __syncthreads();          // every thread is done with sz[buf] before the prefetch after next overwrites it
+    buf ^= 1;
+  }
+  if (dbias) {
+#pragma unroll
+    for (int k = 0; k < KLP_ACC; ++k) {
+      const int i = threadIdx.x + k * KLP_THREADS;
+      if (i < n4) {
+        atomicAdd(dbias + 4 * i, acc[k].x); atomicAdd(dbias + 4 * i + 1, acc[k].y);
+        atomicAdd(dbias + 4 * i + 2, acc[k].z); atomicAdd(dbias + 4 * i + 3, acc[k].w);
+      }
+    }
+  }
+}
+
 // loss[0] = bce mean, loss[1] = kl mean, loss[2] = bce + reg*kl   (fixed summation order)
 __global__ void __launch_bounds__(1024)
 loss_finalize_kernel(const double* __restrict__ bce_rows, int nb, double bce_div, const double* __restrict__ kl_rows,
@@ -429,15 +592,44 @@ int cc_bce_logits_fwd_bwd(const float* z, int64_t ldz, const uint32_t* ybits, in
   return CC_OK;
 }
 
+// dbias (nullable, float [num_cards]): receives the column sums of dz (= the softmax layer's bias gradient).  Fused into
+// the persistent kernel when it applies (float atomics: last bits vary between runs); otherwise the caller still has
+// cc_colsum_f32 -- the return value of cc_softmax_kl_fuses_dbias tells which.
+int cc_softmax_kl_fuses_dbias(int32_t num_cards, int32_t ncols_pad, int64_t ldz, int64_t ldt, int64_t lddz) {
+  return (num_cards % 4 == 0) && (ldz % 4 == 0) && (ldt % 4 == 0) && (ncols_pad % 4 == 0) && (lddz % 4 == 0) &&
+         size_t(num_cards) * 8 <= 200 * 1024 && (ncols_pad >> 2) <= (KLP_ACC + 1) * KLP_THREADS &&
+         (num_cards >> 2) <= KLP_ACC * KLP_THREADS;
+}
+
 int cc_softmax_kl_fwd_bwd(const float* z, int64_t ldz, const float* target, int64_t ldt, const int32_t* target_rows,
                           int32_t rows, int32_t num_cards, int32_t ncols_pad, double grad_scale, float* dz,
-                          int64_t lddz, double* row_loss, int round_tf32, void* stream) {
+                          int64_t lddz, double* row_loss, int round_tf32, float* dbias, void* stream) {
   CC_REQUIRE(z && target && row_loss, "cc_softmax_kl_fwd_bwd: null pointer");
   CC_REQUIRE(num_cards > 0 && ncols_pad >= num_cards, "cc_softmax_kl_fwd_bwd: bad sizes");
   CC_REQUIRE(!dz || lddz >= ncols_pad, "cc_softmax_kl_fwd_bwd: lddz too small");
+  cudaStream_t st = as_stream(stream);
+  if (dbias) {
+    CC_REQUIRE(dz && cc_softmax_kl_fuses_dbias(num_cards, ncols_pad, ldz, ldt, lddz) &&
+                   ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(dz)) % 16 == 0),
+               "cc_softmax_kl_fwd_bwd: dbias needs the persistent kernel (see cc_softmax_kl_fuses_dbias) and 16-byte aligned buffers");
+    CC_CHECK_CUDA(cudaMemsetAsync(dbias, 0, size_t(num_cards) * sizeof(float), st));
+    if (rows == 0) return CC_OK;
+    const size_t smem = size_t(num_cards) * 8;
+    const int grid = rows < sm_count() ? rows : sm_count();
+    if (round_tf32) {
+      CC_CHECK_CUDA(cudaFuncSetAttribute(softmax_kl_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      softmax_kl_persistent_kernel<true><<<grid, KLP_THREADS, smem, st>>>(z, ldz, target, ldt, target_rows, rows, num_cards,
+                                                                         ncols_pad, float(grad_scale), dz, lddz, row_loss, 1, dbias);
+    } else {
+      CC_CHECK_CUDA(cudaFuncSetAttribute(softmax_kl_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      softmax_kl_persistent_kernel<false><<<grid, KLP_THREADS, smem, st>>>(z, ldz, target, ldt, target_rows, rows, num_cards,
+                                                                          ncols_pad, float(grad_scale), dz, lddz, row_loss, 0, dbias);
+    }
+    CC_CHECK_LAUNCH();
+    return CC_OK;
+  }
   if (rows == 0) return CC_OK;
   const size_t cache_bytes = size_t(num_cards) * 2 * sizeof(float);
-  cudaStream_t st = as_stream(stream);
   const bool aligned = (num_cards % 4 == 0) && (ldz % 4 == 0) && (ldt % 4 == 0) && (ncols_pad % 4 == 0) &&
                        (!dz || lddz % 4 == 0) &&
                        ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(dz)) % 16 == 0);

@@ -266,11 +266,16 @@ class DAEEngine:
                      self.cpad, float(self.global_B) * float(self.C), ptr(self.z1), self.z1.stride(0),
                      ptr(self.row_bce), st)
             n_launch += 1
+        reg_dbias_fused = False
         if R:
+            # the persistent softmax-KL kernel also reduces dlogits' columns into the reg tower's output bias gradient
+            reg_dbias_fused = bool(_lib.load().cc_softmax_kl_fuses_dbias(self.C, self.cpad, self.z2.stride(0),
+                                                                         self.mhat.stride(0), self.z2.stride(0)))
             with self._timed("softmax_kl"):
                 call("cc_softmax_kl_fwd_bwd", ptr(self.z2), self.z2.stride(0), ptr(self.mhat), self.mhat.stride(0),
                      ptr(self.reg_rows), R, self.C, self.cpad, self.reg / float(self.global_R), ptr(self.z2),
-                     self.z2.stride(0), ptr(self.row_kl), int(tc), st)
+                     self.z2.stride(0), ptr(self.row_kl), int(tc),
+                     ptr(G(dec_names("reg")[3] + "/bias")) if reg_dbias_fused else None, st)
             n_launch += 1
         call("cc_loss_finalize", ptr(bce_rows), bce_n, float(self.global_B) * float(self.C), ptr(self.row_kl), R,
              float(self.global_R), self.reg, ptr(self.loss3), st)
@@ -299,7 +304,8 @@ class DAEEngine:
             with self._timed("big_gemm"):
                 gemm(acts[2], dzc, G(names[3] + "/kernel"), transa=True, precision=pr)
             n_launch += 1
-            if not (tc and prefix == "main"):       # (the fused BCE epilogue already produced the main tower's)
+            # (the fused BCE epilogue / the persistent softmax-KL kernel already produced this bias gradient)
+            if not ((tc and prefix == "main") or (prefix == "reg" and reg_dbias_fused)):
                 with self._timed("colsum_big"):
                     colsum(dzc, G(names[3] + "/bias"), self.cs_ws)
                 n_launch += 2

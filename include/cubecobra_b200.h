@@ -200,10 +200,14 @@ int cc_relu_mask_f32(float* x, int64_t ldx, const float* act, int64_t lda, int m
 int cc_bce_logits_fwd_bwd(const float* z, int64_t ldz, const uint32_t* ybits, int64_t ywords, int32_t batch,
                           int32_t num_cards, int32_t ncols_pad, double count, float* dz, int64_t lddz,
                           double* row_loss, void* stream);
-/* row r uses target row target_rows[r] (nullable = r); dz = grad_scale*(q*S - t'*1[unclipped]). */
+/* row r uses target row target_rows[r] (nullable = r); dz = grad_scale*(q*S - t'*1[unclipped]).
+ * dbias (nullable, float [num_cards]): also emit the column sums of dz, i.e. the softmax layer's bias gradient, from
+ * the persistent form of the kernel (one CTA per SM walks the rows, next row prefetched with cp.async, column sums
+ * kept in registers and added with float atomics at the end).  Only where cc_softmax_kl_fuses_dbias(...) != 0. */
+int cc_softmax_kl_fuses_dbias(int32_t num_cards, int32_t ncols_pad, int64_t ldz, int64_t ldt, int64_t lddz);
 int cc_softmax_kl_fwd_bwd(const float* z, int64_t ldz, const float* target, int64_t ldt, const int32_t* target_rows,
                           int32_t rows, int32_t num_cards, int32_t ncols_pad, double grad_scale, float* dz,
-                          int64_t lddz, double* row_loss, int round_tf32, void* stream);
+                          int64_t lddz, double* row_loss, int round_tf32, float* dbias, void* stream);
 /* out3 (float64 [3]) = { sum(bce_rows)/bce_div, sum(kl_rows)/kl_div, bce + reg*kl } */
 int cc_loss_finalize(const double* bce_rows, int32_t nb, double bce_div, const double* kl_rows, int32_t nr,
                      double kl_div, double reg, double* out3, void* stream);

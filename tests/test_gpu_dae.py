@@ -104,7 +104,7 @@ def test_loss_kernels_vs_oracle():
     tt = torch.tensor(t.astype(np.float32)).cuda()
     dz2 = torch.full((b, cpad), 9.0, device="cuda")
     E.call("cc_softmax_kl_fwd_bwd", E.ptr(z2t), cpad, E.ptr(tt), c, E.ptr(torch.tensor(rows).cuda()), b, c, cpad,
-           0.1 / b, E.ptr(dz2), cpad, E.ptr(rl), 0, E.stream_ptr())
+           0.1 / b, E.ptr(dz2), cpad, E.ptr(rl), 0, None, E.stream_ptr())
     t32 = t.astype(np.float32).astype(np.float64)[rows]
     q = od.softmax_np(z2.astype(np.float64))
     assert abs(rl.sum().item() / b - od.kld_np(t32, q)) < 2e-6 * abs(od.kld_np(t32, q))
@@ -115,6 +115,25 @@ def test_loss_kernels_vs_oracle():
     edge = np.abs(q - 1e-7) < 1e-12
     assert np.abs(got - ref)[~edge].max() < 1e-8
     assert (dz2[:, c:] == 0).all()
+    # persistent form (one CTA per SM walks the rows, next row prefetched): same dz and loss, plus the column sums of
+    # dz = the layer's bias gradient; exact (expf/logf) and fast (MUFU) variants, more rows than CTAs
+    from cubecobrarecommender_b200 import _lib
+    if _lib.load().cc_softmax_kl_fuses_dbias(c, cpad, cpad, c, cpad):
+        for fast in (0, 1):
+            reps = 7                                        # 7 * b rows > 148 CTAs: every CTA loops
+            zr = z2t.repeat(reps, 1).contiguous(); rr = torch.tensor(np.tile(rows, reps)).cuda()
+            dz_a = torch.full((reps * b, cpad), 9.0, device="cuda"); dz_b = torch.full((reps * b, cpad), 9.0, device="cuda")
+            rl_a = torch.zeros(reps * b, dtype=torch.float64, device="cuda"); rl_b = torch.zeros_like(rl_a)
+            db = torch.full((c,), 3.0, device="cuda")
+            E.call("cc_softmax_kl_fwd_bwd", E.ptr(zr), cpad, E.ptr(tt), c, E.ptr(rr), reps * b, c, cpad, 0.1 / b,
+                   E.ptr(dz_a), cpad, E.ptr(rl_a), fast, None, E.stream_ptr())
+            E.call("cc_softmax_kl_fwd_bwd", E.ptr(zr), cpad, E.ptr(tt), c, E.ptr(rr), reps * b, c, cpad, 0.1 / b,
+                   E.ptr(dz_b), cpad, E.ptr(rl_b), fast, E.ptr(db), E.stream_ptr())
+            # same formulas, different reduction trees (1024 vs 512 threads): equal to rounding
+            assert torch.allclose(dz_a, dz_b, rtol=2e-5, atol=1e-12) and torch.allclose(rl_a, rl_b, rtol=1e-6)
+            assert (dz_b[:, c:] == 0).all()
+            ref_db = dz_b[:, :c].double().sum(0)
+            assert (db.double() - ref_db).abs().max().item() < 1e-6 * ref_db.abs().max().item() + 1e-12
 
 
 def test_adam_matches_tf_style_oracle():
