@@ -36,6 +36,12 @@ def alias_table(p: np.ndarray, device):
     return torch.from_numpy(prob).to(device), torch.from_numpy(alias).to(device)
 
 
+def full_identity_shard(num_cards: int, rank: int = 0, world: int = 1):
+    """Rows of I (cards) that rank ``rank`` of ``world`` regularises in full-I mode: an exact partition of
+    ``[0, C)`` (shard sizes differ by at most one; each rank builds its engine with its own shard size)."""
+    return (num_cards * rank) // world, (num_cards * (rank + 1)) // world
+
+
 class DAEEngine:
     def __init__(self, model: CC_Recommender, mhat: torch.Tensor, *, batch: int, reg_rows: int | None = None,
                  reg: float = 0.1, max_cube_size: int = 720, global_batch: int | None = None,
@@ -76,6 +82,7 @@ class DAEEngine:
             raise ValueError(f"CC_DP_MODE={self.dp_mode!r}: expected p2p, nccl_overlap or nccl")
         self.overlap = self.dp_mode == "nccl_overlap"
         self._dp_ready = False
+        self._fixed_reg_rows = False
         self._dynamic_tiles = None
         # the small layers' weight-gradient GEMMs ([x | 1]^T dY, a few microseconds each, <= 64 CTAs) run on a side
         # stream, off the dY -> dX -> dY chain that backward is serialised on (CC_SIDE_STREAM=0 keeps one stream)
@@ -186,11 +193,22 @@ class DAEEngine:
                  ptr(alias_idx), float(noise), float(noise_std), int(seed), ptr(self.store.step), self.max_cube_size,
                  self.x_stride, ptr(self.x_idx), ptr(self.x_len), ptr(self.y_bits), self.yw, ptr(self.flips),
                  ptr(self.overflow), ptr(self.x_dense), self.cpad if self.x_dense is not None else 0, st)
-        if self.R:
+        if self.R and not self._fixed_reg_rows:
             call("cc_sample_reg_rows", ptr(alias_prob), ptr(alias_idx), self.C, self.R, int(seed) ^ 0x5DEECE66D,
                  ptr(self.store.step), ptr(self.reg_rows), st)
         self._x = SparseBatch(self.x_idx, self.x_start, self.x_len)
         self.launches += 2
+
+    def set_full_identity_rows(self, rank: int = 0, world: int = 1):
+        """"Full-I" regulariser (README formula KL(M-hat, D2(E(I))) over ALL rows of I, the reference code samples
+        B of them per step, generator.py:47-51): this rank takes the contiguous shard ``[rank*C/world, (rank+1)*C/world)``
+        of the rows, every step, instead of drawing rows.  The engine must have been built with ``reg_rows`` equal to
+        the shard size (``full_identity_shard``) and ``global_reg_rows = C``."""
+        lo, hi = full_identity_shard(self.C, rank, world)
+        if hi - lo != self.R:
+            raise ValueError(f"engine has {self.R} reg rows, the full-I shard of rank {rank}/{world} has {hi - lo}")
+        self.reg_rows[:self.R].copy_(torch.arange(lo, hi, dtype=torch.int32, device=self.dev))
+        self._fixed_reg_rows = True
 
     # -- the step -------------------------------------------------------------------
     def forward_backward(self):

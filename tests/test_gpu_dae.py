@@ -425,3 +425,41 @@ def test_host_batch_stream_equals_device_resident_steps(precision):
     # the last bits of a step vary from run to run, so the two runs agree to rounding, not bit for bit
     assert np.array_equal(losses[0][0], losses[1][0])          # first step: identical weights, identical batch
     assert np.allclose(losses[0], losses[1], rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_full_identity_regulariser_and_its_row_shards(precision):
+    """README form of the regulariser, KL(M-hat, D2(E(I))) over ALL rows of I (BASELINE configs[2]): (a) one engine
+    with reg_rows = arange(C) matches the oracle; (b) two engines taking the two row shards, each scaling by the
+    GLOBAL row count, produce losses and gradients that sum to (a) -- the data-parallel partition of the KL term."""
+    c, x, y, _, mh = _problem(c=200, b=16, r=1)
+    params = od.init_params(c, seed=2)
+    tol = TOL[precision]
+    mhat = torch.tensor(mh.astype(np.float32)).cuda()
+    sb = M.SparseBatch.from_csr(CubeCSR.from_dense(x), "cuda")
+    yb = torch.tensor(_bits_from_dense(y)).cuda()
+    rows_all = np.arange(c)
+    t32 = mh.astype(np.float32).astype(np.float64)
+    (tot, bce, kl), grads = od.loss_and_grads_np({k: v.astype(np.float64) for k, v in params.items()}, x, y, rows_all, t32, 0.1)
+
+    def run(lo, hi, main_rows):
+        model = M.CC_Recommender(c, device="cuda", precision=precision)
+        model.set_weights_dict(params)
+        eng = E.DAEEngine(model, mhat, batch=x.shape[0], reg_rows=hi - lo, reg=0.1, max_cube_size=80,
+                          global_batch=x.shape[0], global_reg_rows=c)
+        eng.set_batch(sb, yb, torch.arange(lo, hi, dtype=torch.int32, device="cuda"))
+        eng.forward_backward()
+        return eng.loss3.cpu().numpy().copy(), model.store.to_dict(model.store.grads)
+
+    l_full, g_full = run(0, c, True)
+    assert abs(l_full[1] - kl) / kl < tol["loss"] and abs(l_full[2] - tot) / tot < tol["loss"]
+    for kname, gref in grads.items():       # (C reg rows on top of the batch: twice the single-step tf32 allowance)
+        assert np.abs(g_full[kname] - gref).max() / (np.abs(gref).max() + 1e-30) < 2 * tol["grad"], kname
+    # two row shards (as two ranks would hold them): KL parts add up; BCE is computed by both here, so compare KL only
+    lo0, hi0 = E.full_identity_shard(c, 0, 2); lo1, hi1 = E.full_identity_shard(c, 1, 2)
+    assert (lo0, hi1) == (0, c) and hi0 == lo1
+    l0, g0 = run(lo0, hi0, True); l1, g1 = run(lo1, hi1, True)
+    assert abs((l0[1] + l1[1]) - l_full[1]) / l_full[1] < 1e-5
+    for kname in ("reg_reconstruction/kernel", "reg_d1/kernel", "reg_reconstruction/bias"):
+        ssum = g0[kname] + g1[kname]
+        assert np.abs(ssum - g_full[kname]).max() / (np.abs(g_full[kname]).max() + 1e-30) < (1e-5 if precision == "fp32" else 2e-3), kname
