@@ -50,6 +50,7 @@ SIGNATURES = {
     "cc_alias_build_host": (I, [P, I32, P, P]),
     "cc_noise_smem_bytes": (I64, [I32, I32]),
     "cc_noise": (I, [P, P, P, I32, I32, P, P, F, F, U64, P, I32, I32, P, P, P, I64, P, P, P, I64, P]),
+    "cc_noise_ex": (I, [P, P, P, I32, I32, P, P, F, F, U64, P, I32, I32, P, P, P, I64, P, P, P, I64, I, P]),
     "cc_sample_reg_rows": (I, [P, P, I32, I32, U64, P, P, P]),
     "cc_cubes_to_bits": (I, [P, P, P, I32, I32, P, I64, P]),
     "cc_step_increment": (I, [P, P]),
@@ -59,7 +60,7 @@ SIGNATURES = {
     # (5) dense
     "cc_gemm_f32_simt": (I, [I, I, I, I, I, P, I64, P, I64, P, I64, P, I, P, I64, I, P]),
     "cc_gemm_tc": (I, [I, I, I, I, I, I, P, I64, P, I64, P, I64, P, I, P, I64, I, I, I, I, P]),
-    "cc_gemm_bce_tc": (I, [I, I, I, I, P, I64, P, I64, P, P, I64, D, P, I64, P, P, I, P]),
+    "cc_gemm_bce_tc": (I, [I, I, I, I, P, I64, P, I64, P, P, I64, D, P, I64, P, P, I, I, P]),
     "cc_gemm_bce_partial_count": (I64, [I, I]),
     "cc_gemm_tc_set_pair_mode": (I, [I]),
     "cc_gemm_tc_set_dynamic_tiles": (I, [I]),
@@ -71,6 +72,8 @@ SIGNATURES = {
     "cc_bce_logits_fwd_bwd": (I, [P, I64, P, I64, I32, I32, I32, D, P, I64, P, P]),
     "cc_softmax_kl_fuses_dbias": (I, [I32, I32, I64, I64, I64]),
     "cc_softmax_kl_fwd_bwd": (I, [P, I64, P, I64, P, I32, I32, I32, D, P, I64, P, I, P, P]),
+    "cc_softmax_kl_fwd_bwd_ex": (I, [P, I64, P, I64, P, I32, I32, I32, D, P, I64, P, I, P, P, I64, P]),
+    "cc_convert_f32_bf16": (I, [P, I64, P, I64, I32, I32, P]),
     "cc_loss_finalize": (I, [P, I32, D, P, I32, D, D, P, P]),
     "cc_adam_step_p2p": (I, [P, P, I, I, P, P, I64, I64, P, F, F, F, F, P, P, P]),
     "cc_adam_step": (I, [P, P, P, P, I64, P, F, F, F, F, P, P]),

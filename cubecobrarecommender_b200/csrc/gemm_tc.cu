@@ -49,7 +49,8 @@ template <int BN, int CTAS> struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + BAR_BYTES + 1024 /*align slack*/;
 };
 
-enum Epilogue : int { EPI_STORE = 0, EPI_BCE = 1, EPI_COUNT = 2 };
+// EPI_BCE16: the fused sigmoid-BCE epilogue writing dlogits as bf16 (they feed the bf16 dW / dX GEMMs of the "bf16" mode)
+enum Epilogue : int { EPI_STORE = 0, EPI_BCE = 1, EPI_COUNT = 2, EPI_BCE16 = 3 };
 // operand kinds: fp32 storage / kind::tf32, bf16 storage / kind::f16, uint8 storage / kind::i8 (int32 accumulators:
 // the co-occurrence contraction X^T X over 0/1 bytes is exact)
 enum Kind : int { KIND_TF32 = 0, KIND_BF16 = 1, KIND_U8 = 2 };
@@ -275,6 +276,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const __grid_constant__ CUtensorMap map_c, const Params p) {
   using C = Cfg<BN, CTAS>;
   constexpr bool BF16 = KIND == KIND_BF16;
+  constexpr bool IS_BCE = EPI == EPI_BCE || EPI == EPI_BCE16;
+  constexpr bool OUT16 = EPI == EPI_BCE16;        // output elements are bf16 (32 x 32 block = 64-byte rows)
   constexpr int BN_LOAD = BN / CTAS;             // rows of the B tile this CTA stages
   constexpr int STAGES = C::STAGES;
   constexpr int STAGE_BYTES = C::STAGE_BYTES;
@@ -509,7 +512,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         bias_r[cb] = (p.bias && col < p.n) ? __ldg(p.bias + col) : 0.f;
         y_r[cb] = 0u;
       }
-      if (EPI == EPI_BCE && row_ok) {
+      if (IS_BCE && row_ok) {
         const uint32_t* yrow = p.ybits + (long long)row * p.ywords + (colw >> 5);
         const bool in_range = colw + BN / 2 <= p.ywords * 32;
         if (NCH == 4 && in_range && ((reinterpret_cast<uintptr_t>(yrow) & 15) == 0)) {
@@ -527,7 +530,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       float row_loss = 0.f;
       // The BCE body is long (a rolled loop keeps it inside the instruction cache: unrolling it 8x cost 300 -> 442 us),
       // so the prefetched registers are ROTATED instead of indexed; the short store body is fully unrolled.
-#pragma unroll(EPI == EPI_BCE ? 1 : NCH)
+#pragma unroll(IS_BCE ? 1 : NCH)
       for (int cb = 0; cb < NCH; ++cb) {
         const int col0 = colw + cb * 32;
         if (col0 >= p.n_store || row0 >= p.m || !has_k) break;      // warp-uniform
@@ -554,7 +557,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
           }
-        } else if (EPI == EPI_BCE) {
+        } else if (IS_BCE) {
           // softplus(z) - z*y and sigmoid(z) from one exp: e = exp(-|z|) (ex2, rcp, lg2: 3 MUFU ops per element)
           auto bce_elem = [&](int j, float& l, float& g) {
             const float z = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, b_cur, j);
@@ -606,10 +609,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // registers -> swizzled staging (row = lane, 16-byte chunk c at position c ^ (lane & 7)) -> TMA store
         if (lane == 0) tma_wait_group_read<0>();        // the store that last read this buffer has drained
         __syncwarp();
+        if (OUT16) {
+          // bf16 block: plain row-major 64-byte rows (the C tensor map is unswizzled with a 32 x 32 box)
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<float4*>(sbuf + lane * 128 + ((c ^ (lane & 7)) << 4)) =
-              make_float4(out[4 * c], out[4 * c + 1], out[4 * c + 2], out[4 * c + 3]);
+          for (int c = 0; c < 4; ++c) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __nv_bfloat162 h = __floats2bfloat162_rn(out[8 * c + 2 * e], out[8 * c + 2 * e + 1]);
+              w[e] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(sbuf + lane * 64 + (c << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(sbuf + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                make_float4(out[4 * c], out[4 * c + 1], out[4 * c + 2], out[4 * c + 3]);
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -617,18 +634,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           else              tma_store_2d(&map_c, sbuf, col0, row0);
           tma_commit_group();
         }
-        if (EPI == EPI_BCE && p.dbias) {
+        if (IS_BCE && p.dbias) {
           // bias gradient = column sums of dlogits: lane j adds up column j of the staged 32 x 32 block (for a fixed
-          // row the 32 lanes hit 32 different banks of the swizzled row) and issues one coalesced RED per chunk.
-          // Rows beyond m and columns beyond n hold zeros.
+          // row the 32 lanes hit 32 different banks of the swizzled row -- or, bf16, 16 banks two lanes a word) and
+          // issues one coalesced RED per chunk.  Rows beyond m and columns beyond n hold zeros.
           float cs = 0.f;
 #pragma unroll
-          for (int r = 0; r < 32; ++r)
-            cs += *reinterpret_cast<const float*>(sbuf + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
+          for (int r = 0; r < 32; ++r) {
+            if (OUT16) cs += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sbuf + r * 64 + (lane << 1)));
+            else cs += *reinterpret_cast<const float*>(sbuf + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
+          }
           if (col0 + lane < p.n) atomicAdd(p.dbias + col0 + lane, cs);
         }
       }
-      if (EPI == EPI_BCE) {
+      if (IS_BCE) {
         // one float64 partial per (tile, warp): fixed summation order downstream
         const float s = row_ok ? row_loss : 0.f;
         const double d = warp_sum(double(s));
@@ -693,19 +712,20 @@ static EncodeTiledFn encode_fn() {
 // box = box_rows x (128 bytes of columns), 128B swizzle (32-byte atoms for 4-byte MN-major operands).
 enum MapType : int { MAP_F32 = 0, MAP_BF16 = 1, MAP_U8 = 2, MAP_S32 = 3 };
 static int make_map(CUtensorMap* map, const void* base, int elem, int mtype, long long rows, long long cols,
-                    long long ld, int box_rows, bool atom32) {
+                    long long ld, int box_rows, bool atom32, int box_cols = 0 /* 0: 128 bytes, swizzled; else unswizzled */) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return CC_ERR_CUDA; }
   cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
   cuuint64_t strides[1] = {cuuint64_t(ld) * elem};
-  cuuint32_t box[2] = {cuuint32_t(128 / elem), cuuint32_t(box_rows)};
+  cuuint32_t box[2] = {cuuint32_t(box_cols ? box_cols : 128 / elem), cuuint32_t(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   const CUtensorMapDataType dt = mtype == MAP_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                  : mtype == MAP_U8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
                                  : mtype == MAP_S32 ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   const CUresult r = fn(map, dt, 2,
                         const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        box_cols ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                 : (atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): base=%p rows=%lld cols=%lld ld=%lld", int(r), base, rows, cols, ld);
@@ -801,7 +821,8 @@ static int launch_bn(const Problem& pr, Params p, cudaStream_t st) {
   else           rc = make_map(&map_b, pr.b, elem, mt, pr.k, pr.n, pr.ldb, bk, TF32);
   if (rc != CC_OK) return rc;
   // C: fp32 (int32 counts) [M][n_store] boxes of 32 rows x 32 columns (TMA clips rows >= M and columns >= n_store)
-  rc = make_map(&map_c, pr.c, 4, EPI == EPI_COUNT ? MAP_S32 : MAP_F32, pr.m, p.n_store, pr.ldc, 32, false);
+  if (EPI == EPI_BCE16) rc = make_map(&map_c, pr.c, 2, MAP_BF16, pr.m, p.n_store, pr.ldc, 32, false, 32);
+  else rc = make_map(&map_c, pr.c, 4, EPI == EPI_COUNT ? MAP_S32 : MAP_F32, pr.m, p.n_store, pr.ldc, 32, false);
   if (rc != CC_OK) return rc;
   p.a_mn_major = pr.transa ? 1 : 0;
   p.b_mn_major = pr.transb ? 0 : 1;
@@ -861,7 +882,7 @@ static int launch(const Problem& pr, Params p, int bn, int ctas, cudaStream_t st
   CC_REQUIRE((reinterpret_cast<uintptr_t>(pr.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(pr.b) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(pr.c) & 15) == 0,
              "cc_gemm_tc: base pointers must be 16-byte aligned");
-  CC_REQUIRE((pr.lda * elem) % 16 == 0 && (pr.ldb * elem) % 16 == 0 && (pr.ldc * 4) % 16 == 0,
+  CC_REQUIRE((pr.lda * elem) % 16 == 0 && (pr.ldb * elem) % 16 == 0 && (pr.ldc * (EPI == EPI_BCE16 ? 2 : 4)) % 16 == 0,
              "cc_gemm_tc: leading dimensions must be multiples of 16 bytes (lda=%lld ldb=%lld ldc=%lld)", pr.lda,
              pr.ldb, pr.ldc);
   if (ctas == 2) return launch_bn<KIND, EPI, 256, 2>(pr, p, st);
@@ -955,8 +976,8 @@ int cc_gemm_tc(int precision, int transa, int transb, int m, int n, int k, const
 // dlogits = (sigmoid(z) - y)/count written to dz[M][lddz] (columns [N, lddz) zeroed).
 // loss_partial: float64 [cc_gemm_bce_partial_count(m, lddz)]  (sum it with cc_loss_finalize).
 int cc_gemm_bce_tc(int precision, int m, int n, int k, const void* a, int64_t lda, const void* w, int64_t ldw,
-                   const float* bias, const uint32_t* ybits, int64_t ywords, double count, float* dz, int64_t lddz,
-                   double* loss_partial, float* dbias, int round_tf32, void* stream) {
+                   const float* bias, const uint32_t* ybits, int64_t ywords, double count, void* dz, int64_t lddz,
+                   double* loss_partial, float* dbias, int round_tf32, int dz_bf16, void* stream) {
   CC_REQUIRE(a && w && bias && ybits && dz && loss_partial, "cc_gemm_bce_tc: null pointer");
   CC_REQUIRE(precision == 1 || precision == 2, "cc_gemm_bce_tc: precision must be 1 (tf32) or 2 (bf16)");
   CC_REQUIRE(m > 0 && n > 0 && k > 0 && count > 0, "cc_gemm_bce_tc: bad sizes");
@@ -968,8 +989,13 @@ int cc_gemm_bce_tc(int precision, int m, int n, int k, const void* a, int64_t ld
   p.ybits = ybits; p.ywords = ywords; p.inv_count = float(1.0 / count); p.loss_partial = loss_partial;
   p.dbias = dbias;
   if (dbias) CC_CHECK_CUDA(cudaMemsetAsync(dbias, 0, size_t(n) * sizeof(float), as_stream(stream)));
-  tc::Problem pr{0, 0, m, n, k, a, lda, w, ldw, dz, lddz, precision == 2 ? tc::KIND_BF16 : tc::KIND_TF32};
+  tc::Problem pr{0, 0, m, n, k, a, lda, w, ldw, static_cast<float*>(dz), lddz, precision == 2 ? tc::KIND_BF16 : tc::KIND_TF32};
   const int ctas = tc::g_pair_mode == 0 ? 1 : 2;
+  if (dz_bf16) {
+    CC_REQUIRE(precision == 2, "cc_gemm_bce_tc: bf16 dlogits come with bf16 operands (precision 2)");
+    p.round_tf32 = 0;
+    return tc::launch<tc::KIND_BF16, tc::EPI_BCE16>(pr, p, 256, ctas, as_stream(stream));
+  }
   if (precision == 2) return tc::launch<tc::KIND_BF16, tc::EPI_BCE>(pr, p, 256, ctas, as_stream(stream));
   return tc::launch<tc::KIND_TF32, tc::EPI_BCE>(pr, p, 256, ctas, as_stream(stream));
 }

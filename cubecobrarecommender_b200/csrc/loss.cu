@@ -11,6 +11,8 @@
 // * Adam: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v updates; theta -= lr_t*m/(sqrt(v)+eps),
 //   eps = 1e-7 outside the bias correction, dense over every parameter.
 // These are the unfused forms; gemm_tc.cu carries the BCE math inside the GEMM epilogue.
+#include <cuda_bf16.h>
+
 #include "cc_common.cuh"
 
 namespace cc {
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(KLP_THREADS, 1)
 softmax_kl_persistent_kernel(const float* __restrict__ z, int64_t ldz, const float* __restrict__ target, int64_t ldt,
                              const int32_t* __restrict__ target_rows, int32_t rows, int32_t num_cards, int32_t ncols_pad,
                              float grad_scale, float* __restrict__ dz, int64_t lddz, double* __restrict__ row_loss,
-                             int round_tf32, float* __restrict__ dbias) {
+                             int round_tf32, float* __restrict__ dbias, __nv_bfloat16* __restrict__ dz16, int64_t lddz16) {
   auto EXPF = [](float x) { return FAST ? fast_exp(x) : expf(x); };
   auto LOGF = [](float x) { return FAST ? fast_log(x) : logf(x); };
   extern __shared__ __align__(16) float sz[];           // two rows of logits
@@ -365,7 +367,8 @@ softmax_kl_persistent_kernel(const float* __restrict__ z, int64_t ldz, const flo
     const float2 ls = block_sum2_p(loss, sun, red);
     if (threadIdx.x == 0) row_loss[r] = double(ls.x);
     const float S = ls.y;
-    float4* d4 = reinterpret_cast<float4*>(dz + int64_t(r) * lddz);
+    float4* d4 = dz16 ? nullptr : reinterpret_cast<float4*>(dz + int64_t(r) * lddz);
+    uint2* d16 = dz16 ? reinterpret_cast<uint2*>(dz16 + int64_t(r) * lddz16) : nullptr;   // bf16 dlogits ("bf16" mode)
 #pragma unroll
     for (int k = 0; k < KLP_ACC + 1; ++k) {
       const int i = threadIdx.x + k * KLP_THREADS;
@@ -387,7 +390,12 @@ softmax_kl_persistent_kernel(const float* __restrict__ z, int64_t ldz, const flo
         g = make_float4(gg[0], gg[1], gg[2], gg[3]);
         if (k < KLP_ACC) { acc[k].x += g.x; acc[k].y += g.y; acc[k].z += g.z; acc[k].w += g.w; }
       }
-      d4[i] = g;
+      if (d16) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(g.x, g.y), hi = __floats2bfloat162_rn(g.z, g.w);
+        d16[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+      } else {
+        d4[i] = g;
+      }
     }
     __syncthreads();          // every thread is done with sz[buf] before the prefetch after next overwrites it
     buf ^= 1;
@@ -561,6 +569,19 @@ adam_p2p_kernel(const PeerPtrs pp, int world, int rank, float* __restrict__ m, f
   // completion makes the peer stores visible, and the caller's cross-rank barrier only starts after it
 }
 
+// fp32 [rows][ld_src] -> bf16 [rows][ld_dst] (round to nearest even), 4 elements per thread; columns in
+// [cols, ld_dst) are left untouched
+__global__ void convert_f32_bf16_kernel(const float* __restrict__ src, int64_t ld_src, __nv_bfloat16* __restrict__ dst,
+                                        int64_t ld_dst, int rows, int cols4) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= int64_t(rows) * cols4) return;
+  const int r = int(i / cols4), c4 = int(i % cols4);
+  const float4 v = *reinterpret_cast<const float4*>(src + int64_t(r) * ld_src + 4 * c4);
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(dst + int64_t(r) * ld_dst + 4 * c4) =
+      make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+}
+
 __global__ void round_tf32_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) { float v = x[i]; v = rn_tf32(v); out[i] = v; }
@@ -604,7 +625,19 @@ int cc_softmax_kl_fuses_dbias(int32_t num_cards, int32_t ncols_pad, int64_t ldz,
 int cc_softmax_kl_fwd_bwd(const float* z, int64_t ldz, const float* target, int64_t ldt, const int32_t* target_rows,
                           int32_t rows, int32_t num_cards, int32_t ncols_pad, double grad_scale, float* dz,
                           int64_t lddz, double* row_loss, int round_tf32, float* dbias, void* stream) {
+  return cc_softmax_kl_fwd_bwd_ex(z, ldz, target, ldt, target_rows, rows, num_cards, ncols_pad, grad_scale, dz, lddz, row_loss,
+                                  round_tf32, dbias, nullptr, 0, stream);
+}
+
+int cc_softmax_kl_fwd_bwd_ex(const float* z, int64_t ldz, const float* target, int64_t ldt, const int32_t* target_rows,
+                             int32_t rows, int32_t num_cards, int32_t ncols_pad, double grad_scale, float* dz,
+                             int64_t lddz, double* row_loss, int round_tf32, float* dbias, void* dz_bf16, int64_t lddz_bf16,
+                             void* stream) {
   CC_REQUIRE(z && target && row_loss, "cc_softmax_kl_fwd_bwd: null pointer");
+  CC_REQUIRE(!dz_bf16 || (dbias && lddz_bf16 >= ncols_pad && lddz_bf16 % 4 == 0 && (reinterpret_cast<uintptr_t>(dz_bf16) & 7) == 0),
+             "cc_softmax_kl_fwd_bwd: bf16 dlogits need the persistent kernel (dbias != NULL), lddz_bf16 %% 4 == 0 >= ncols_pad");
+  __nv_bfloat16* dz16 = static_cast<__nv_bfloat16*>(dz_bf16);
+  if (dz16 && !dz) { dz = const_cast<float*>(z); lddz = ldz; }      // (unused: the kernel writes dz16 only)
   CC_REQUIRE(num_cards > 0 && ncols_pad >= num_cards, "cc_softmax_kl_fwd_bwd: bad sizes");
   CC_REQUIRE(!dz || lddz >= ncols_pad, "cc_softmax_kl_fwd_bwd: lddz too small");
   cudaStream_t st = as_stream(stream);
@@ -619,11 +652,13 @@ int cc_softmax_kl_fwd_bwd(const float* z, int64_t ldz, const float* target, int6
     if (round_tf32) {
       CC_CHECK_CUDA(cudaFuncSetAttribute(softmax_kl_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       softmax_kl_persistent_kernel<true><<<grid, KLP_THREADS, smem, st>>>(z, ldz, target, ldt, target_rows, rows, num_cards,
-                                                                         ncols_pad, float(grad_scale), dz, lddz, row_loss, 1, dbias);
+                                                                         ncols_pad, float(grad_scale), dz, lddz, row_loss,
+                                                                         dz16 ? 0 : 1, dbias, dz16, lddz_bf16);
     } else {
       CC_CHECK_CUDA(cudaFuncSetAttribute(softmax_kl_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       softmax_kl_persistent_kernel<false><<<grid, KLP_THREADS, smem, st>>>(z, ldz, target, ldt, target_rows, rows, num_cards,
-                                                                          ncols_pad, float(grad_scale), dz, lddz, row_loss, 0, dbias);
+                                                                          ncols_pad, float(grad_scale), dz, lddz, row_loss, 0, dbias,
+                                                                          dz16, lddz_bf16);
     }
     CC_CHECK_LAUNCH();
     return CC_OK;
@@ -712,6 +747,19 @@ int cc_adam_step_p2p(const void* const* grads_ptrs, void* const* params_ptrs, in
   else if (world <= 8) CC_P2P_LAUNCH(8, false);
   else CC_P2P_LAUNCH(16, false);
 #undef CC_P2P_LAUNCH
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+int cc_convert_f32_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int32_t rows, int32_t cols, void* stream) {
+  CC_REQUIRE(src && dst && rows >= 0 && cols >= 0 && ld_src >= cols && ld_dst >= cols, "cc_convert_f32_bf16: bad arguments");
+  CC_REQUIRE(cols % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(dst) & 7) == 0,
+             "cc_convert_f32_bf16: cols and leading dimensions must be multiples of 4, buffers 16/8-byte aligned");
+  if (rows == 0 || cols == 0) return CC_OK;
+  const int64_t total = int64_t(rows) * (cols / 4);
+  convert_f32_bf16_kernel<<<(unsigned)ceil_div<int64_t>(total, 256), 256, 0, as_stream(stream)>>>(
+      src, ld_src, static_cast<__nv_bfloat16*>(dst), ld_dst, rows, cols / 4);
   CC_CHECK_LAUNCH();
   return CC_OK;
 }

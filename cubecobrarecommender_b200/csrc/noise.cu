@@ -73,7 +73,7 @@ noise_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ ind
              int32_t max_size, int32_t x_stride,
              int32_t* __restrict__ x_idx, int32_t* __restrict__ x_len, uint32_t* __restrict__ y_bits,
              int64_t y_words, int32_t* __restrict__ flips_out, int* __restrict__ overflow,
-             float* __restrict__ x_dense, int64_t ld_dense) {
+             float* __restrict__ x_dense, int64_t ld_dense, int dense_bf16) {
   extern __shared__ uint32_t sm[];
   const int W = (num_cards + 31) >> 5;
   const int FW = (max_size + 31) >> 5;
@@ -174,12 +174,22 @@ noise_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ ind
     for (int p = threadIdx.x; p < s; p += blockDim.x)
       if ((rem_flag[p >> 5] >> (p & 31)) & 1u) atomicAnd(&cube_mask[inc[p] >> 5], ~(1u << (inc[p] & 31)));
     __syncthreads();
-    float4* xo4 = reinterpret_cast<float4*>(x_dense + int64_t(b) * ld_dense);
     const int groups = int(ld_dense >> 2);
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-      const int w = g >> 3, sh = (g & 7) << 2;
-      const uint32_t bits = (w < W) ? ((cube_mask[w] | add_mask[w]) >> sh) & 0xfu : 0u;
-      xo4[g] = make_float4(float(bits & 1u), float((bits >> 1) & 1u), float((bits >> 2) & 1u), float((bits >> 3) & 1u));
+    if (dense_bf16) {      // the same 0/1 rows as bf16 (1.0 = 0x3F80): 8 bytes per group of four cards
+      uint2* xo2 = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(x_dense) + int64_t(b) * ld_dense);
+      for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        const int w = g >> 3, sh = (g & 7) << 2;
+        const uint32_t bits = (w < W) ? ((cube_mask[w] | add_mask[w]) >> sh) & 0xfu : 0u;
+        xo2[g] = make_uint2(((bits & 1u) ? 0x3F80u : 0u) | ((bits & 2u) ? 0x3F800000u : 0u),
+                            ((bits & 4u) ? 0x3F80u : 0u) | ((bits & 8u) ? 0x3F800000u : 0u));
+      }
+    } else {
+      float4* xo4 = reinterpret_cast<float4*>(x_dense + int64_t(b) * ld_dense);
+      for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        const int w = g >> 3, sh = (g & 7) << 2;
+        const uint32_t bits = (w < W) ? ((cube_mask[w] | add_mask[w]) >> sh) & 0xfu : 0u;
+        xo4[g] = make_float4(float(bits & 1u), float((bits >> 1) & 1u), float((bits >> 2) & 1u), float((bits >> 3) & 1u));
+      }
     }
   }
 }
@@ -253,6 +263,16 @@ int cc_noise(const int64_t* indptr, const int32_t* indices, const int32_t* batch
              uint64_t seed, const int64_t* step_ptr, int32_t max_size, int32_t x_stride, int32_t* x_idx,
              int32_t* x_len, uint32_t* y_bits, int64_t y_words, int32_t* flips_out, int* overflow_flag,
              float* x_dense, int64_t ld_dense, void* stream) {
+  return cc_noise_ex(indptr, indices, batch_ids, batch, num_cards, alias_prob, alias_idx, noise_mean, noise_std, seed, step_ptr,
+                     max_size, x_stride, x_idx, x_len, y_bits, y_words, flips_out, overflow_flag, x_dense, ld_dense, 0, stream);
+}
+
+int cc_noise_ex(const int64_t* indptr, const int32_t* indices, const int32_t* batch_ids, int32_t batch,
+                int32_t num_cards, const float* alias_prob, const int32_t* alias_idx, float noise_mean, float noise_std,
+                uint64_t seed, const int64_t* step_ptr, int32_t max_size, int32_t x_stride, int32_t* x_idx,
+                int32_t* x_len, uint32_t* y_bits, int64_t y_words, int32_t* flips_out, int* overflow_flag,
+                void* x_dense_v, int64_t ld_dense, int dense_bf16, void* stream) {
+  float* x_dense = static_cast<float*>(x_dense_v);
   CC_REQUIRE(indptr && indices && alias_prob && alias_idx && x_idx && x_len && overflow_flag, "cc_noise: null pointer");
   CC_REQUIRE(!x_dense || (ld_dense % 4 == 0 && ld_dense >= num_cards && (reinterpret_cast<uintptr_t>(x_dense) & 15) == 0),
              "cc_noise: x_dense needs ld_dense % 4 == 0, ld_dense >= num_cards and a 16-byte aligned base");
@@ -265,7 +285,7 @@ int cc_noise(const int64_t* indptr, const int32_t* indices, const int32_t* batch
   CC_CHECK_CUDA(cudaFuncSetAttribute(noise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   noise_kernel<<<batch, NOISE_THREADS, smem, as_stream(stream)>>>(
       indptr, indices, batch_ids, batch, num_cards, alias_prob, alias_idx, noise_mean, noise_std, seed, step_ptr,
-      max_size, x_stride, x_idx, x_len, y_bits, y_words, flips_out, overflow_flag, x_dense, ld_dense);
+      max_size, x_stride, x_idx, x_len, y_bits, y_words, flips_out, overflow_flag, x_dense, ld_dense, dense_bf16);
   CC_CHECK_LAUNCH();
   return CC_OK;
 }

@@ -122,7 +122,7 @@ class DAEEngine:
         self.a_1 = [b_[:, :w + 1] for b_, w in zip(self.a_buf, HIDDEN)]
         self.md_1 = [b_[:, :w + 1] for b_, w in zip(self.md_buf, (128, 256, 512))]
         self.rd_1 = [b_[:, :w + 1] for b_, w in zip(self.rd_buf, (128, 256, 512))]
-        self.z1 = e(B, self.cpad)                                    # logits -> dlogits in place
+        self.z1 = e(B if self.precision != "bf16" else 1, self.cpad)   # logits -> dlogits in place (bf16 mode: dz1_16)
         self.z2 = e(max(R, 1), self.cpad)
         self.ga = [e(T, w) for w in HIDDEN]
         self.gmd = [e(B, w) for w in (128, 256, 512)]
@@ -132,8 +132,15 @@ class DAEEngine:
         self.loss3 = torch.zeros(3, dtype=torch.float64, device=d)
         self.bce_partial = None
         self.x_dense = None               # dense 0/1 rows of x: operand of the tensor-core dW1 = x^T g1 GEMM
+        self.big16 = self.precision == "bf16"     # the seven 512 <-> C passes on bf16 operands (kind::f16)
+        if self.big16:
+            bf = torch.bfloat16
+            zb = lambda *s_: torch.zeros(s_, dtype=bf, device=d)
+            self.md2_16, self.rd2_16, self.g1_16 = zb(B, 512), zb(max(R, 1), 512), zb(B, 512)
+            self.dz1_16, self.dz2_16 = zb(B, self.cpad), zb(max(R, 1), self.cpad)      # dlogits only ever exist as bf16
+            self.w4_16 = {"main": zb(512, self.cpad), "reg": zb(512, self.cpad)}         # bf16 copies of the two 512 x C kernels
         if self.precision != "fp32":
-            self.x_dense = torch.zeros((B, self.cpad), dtype=f32, device=d)
+            self.x_dense = torch.zeros((B, self.cpad), dtype=torch.bfloat16 if self.big16 else f32, device=d)
             if self.C % 4:
                 raise ValueError("tensor-core precision modes need num_cards % 4 == 0 (16-byte TMA rows)")
             from . import tensorcore
@@ -189,10 +196,11 @@ class DAEEngine:
         """Noise function F + reg-row draw on the device (reference generator.py:38-103)."""
         st = stream_ptr()
         with self._timed("noise"):
-            call("cc_noise", ptr(indptr), ptr(indices), ptr(batch_ids), self.B, self.C, ptr(alias_prob),
+            call("cc_noise_ex", ptr(indptr), ptr(indices), ptr(batch_ids), self.B, self.C, ptr(alias_prob),
                  ptr(alias_idx), float(noise), float(noise_std), int(seed), ptr(self.store.step), self.max_cube_size,
                  self.x_stride, ptr(self.x_idx), ptr(self.x_len), ptr(self.y_bits), self.yw, ptr(self.flips),
-                 ptr(self.overflow), ptr(self.x_dense), self.cpad if self.x_dense is not None else 0, st)
+                 ptr(self.overflow), ptr(self.x_dense), self.cpad if self.x_dense is not None else 0,
+                 int(self.big16), st)
         if self.R and not self._fixed_reg_rows:
             call("cc_sample_reg_rows", ptr(alias_prob), ptr(alias_idx), self.C, self.R, int(seed) ^ 0x5DEECE66D,
                  ptr(self.store.step), ptr(self.reg_rows), st)
@@ -213,13 +221,22 @@ class DAEEngine:
     # -- the step -------------------------------------------------------------------
     def forward_backward(self):
         s, B, R, T = self.store, self.B, self.R, self.B + self.R
-        pr = self.precision
+        big16 = self.big16
+        pr = "tf32" if big16 else self.precision     # every layer but the 512 <-> C passes of the "bf16" mode
         tc = pr != "fp32"               # tensor-core modes: operands rounded to tf32 where produced
+
+        def to_bf16(src, dst):          # fp32 (rows, cols) view -> bf16 matrix
+            call("cc_convert_f32_bf16", ptr(src), src.stride(0), ptr(dst), dst.stride(0), src.shape[0], src.shape[1],
+                 stream_ptr())
         x = self._x
         P, G, W = s.p, s.g, s.w         # master params, grads, the copy of the kernels the GEMMs read
         n_launch = 0
         st = stream_ptr()
         # ---------------- forward ----------------
+        if big16:                       # bf16 copies of the two 512 x C kernels, from the fp32 masters
+            for prefix in ("main", "reg") if R else ("main",):
+                to_bf16(P(dec_names(prefix)[3] + "/kernel"), self.w4_16[prefix])
+                n_launch += 1
         a1 = self.a[0]
         with self._timed("bag_fwd"):
             bag_fwd(P("encoder_e1/kernel"), x.idx, x.row_start, x.row_len, P("encoder_e1/bias"), a1[:B], round_tf32=tc)
@@ -265,17 +282,29 @@ class DAEEngine:
                     gemm(h, W(names[i] + "/kernel"), acts[i], bias=P(names[i] + "/bias"), relu=True, precision=pr,
                          round_out=tc)
                     h = acts[i]; n_launch += 1
+            if big16:                   # the 512-wide activation as a bf16 operand
+                h16 = self.md2_16 if prefix == "main" else self.rd2_16
+                to_bf16(h, h16)
+                n_launch += 1
             if tc and prefix == "main":
                 # fused 512 -> C layer + sigmoid-BCE: logits stay in TMEM, only dlogits are written
                 from . import tensorcore
                 with self._timed("big_gemm"):       # the epilogue also reduces dlogits' columns into the bias gradient
-                    tensorcore.gemm_bce(h, W(names[3] + "/kernel"), P(names[3] + "/bias"), self.y_bits,
-                                        float(self.global_B) * float(self.C), self.z1, self.bce_partial, precision=pr,
-                                        dbias=G(names[3] + "/bias"))
+                    if big16:
+                        tensorcore.gemm_bce(h16, self.w4_16["main"][:, :self.C], P(names[3] + "/bias"), self.y_bits,
+                                            float(self.global_B) * float(self.C), self.dz1_16, self.bce_partial,
+                                            precision="bf16", dbias=G(names[3] + "/bias"))
+                    else:
+                        tensorcore.gemm_bce(h, W(names[3] + "/kernel"), P(names[3] + "/bias"), self.y_bits,
+                                            float(self.global_B) * float(self.C), self.z1, self.bce_partial, precision=pr,
+                                            dbias=G(names[3] + "/bias"))
                 bce_rows, bce_n = self.bce_partial, self.bce_partial.numel()
             else:
                 with self._timed("big_gemm"):
-                    gemm(h, W(names[3] + "/kernel"), z[:, :self.C], bias=P(names[3] + "/bias"), precision=pr)
+                    if big16:
+                        gemm(h16, self.w4_16[prefix][:, :self.C], z[:, :self.C], bias=P(names[3] + "/bias"), precision="bf16")
+                    else:
+                        gemm(h, W(names[3] + "/kernel"), z[:, :self.C], bias=P(names[3] + "/bias"), precision=pr)
             n_launch += 1
         # ---------------- losses (logits -> dlogits in place) ----------------
         if not tc:
@@ -290,10 +319,18 @@ class DAEEngine:
             reg_dbias_fused = bool(_lib.load().cc_softmax_kl_fuses_dbias(self.C, self.cpad, self.z2.stride(0),
                                                                          self.mhat.stride(0), self.z2.stride(0)))
             with self._timed("softmax_kl"):
-                call("cc_softmax_kl_fwd_bwd", ptr(self.z2), self.z2.stride(0), ptr(self.mhat), self.mhat.stride(0),
-                     ptr(self.reg_rows), R, self.C, self.cpad, self.reg / float(self.global_R), ptr(self.z2),
-                     self.z2.stride(0), ptr(self.row_kl), int(tc),
-                     ptr(G(dec_names("reg")[3] + "/bias")) if reg_dbias_fused else None, st)
+                if big16:
+                    if not reg_dbias_fused:
+                        raise RuntimeError("bf16 mode needs the persistent softmax-KL kernel (num_cards % 4 == 0, C <= 25600)")
+                    call("cc_softmax_kl_fwd_bwd_ex", ptr(self.z2), self.z2.stride(0), ptr(self.mhat), self.mhat.stride(0),
+                         ptr(self.reg_rows), R, self.C, self.cpad, self.reg / float(self.global_R), None, 0,
+                         ptr(self.row_kl), 1, ptr(G(dec_names("reg")[3] + "/bias")), ptr(self.dz2_16),
+                         self.dz2_16.stride(0), st)
+                else:
+                    call("cc_softmax_kl_fwd_bwd", ptr(self.z2), self.z2.stride(0), ptr(self.mhat), self.mhat.stride(0),
+                         ptr(self.reg_rows), R, self.C, self.cpad, self.reg / float(self.global_R), ptr(self.z2),
+                         self.z2.stride(0), ptr(self.row_kl), int(tc),
+                         ptr(G(dec_names("reg")[3] + "/bias")) if reg_dbias_fused else None, st)
             n_launch += 1
         call("cc_loss_finalize", ptr(bce_rows), bce_n, float(self.global_B) * float(self.C), ptr(self.row_kl), R,
              float(self.global_R), self.reg, ptr(self.loss3), st)
@@ -318,18 +355,29 @@ class DAEEngine:
             gtowers.append(("reg", self.a[3][B:], self.a_1[3][B:], self.rd, self.rd_1, self.grd, self.z2, ga4[B:]))
         for prefix, h_in, h_in_1, acts, acts_1, gacts, dz, g_in in gtowers:
             names = dec_names(prefix)
-            dzc = dz[:, :self.C]
-            with self._timed("big_gemm"):
-                gemm(acts[2], dzc, G(names[3] + "/kernel"), transa=True, precision=pr)
-            n_launch += 1
+            if big16:                   # bf16 dlogits, bf16 activation copy, bf16 kernel copy
+                dzc = (self.dz1_16 if prefix == "main" else self.dz2_16)[:, :self.C]
+                a16 = self.md2_16 if prefix == "main" else self.rd2_16
+                with self._timed("big_gemm"):
+                    gemm(a16, dzc, G(names[3] + "/kernel"), transa=True, precision="bf16")
+                with self._timed("big_gemm"):
+                    gemm(dzc, self.w4_16[prefix][:, :self.C], gacts[2], transb=True, mask=acts[2], precision="bf16",
+                         round_out=True)
+                n_launch += 2
+            else:
+                dzc = dz[:, :self.C]
+                with self._timed("big_gemm"):
+                    gemm(acts[2], dzc, G(names[3] + "/kernel"), transa=True, precision=pr)
+                n_launch += 1
             # (the fused BCE epilogue / the persistent softmax-KL kernel already produced this bias gradient)
-            if not ((tc and prefix == "main") or (prefix == "reg" and reg_dbias_fused)):
+            if not big16 and not ((tc and prefix == "main") or (prefix == "reg" and reg_dbias_fused)):
                 with self._timed("colsum_big"):
                     colsum(dzc, G(names[3] + "/bias"), self.cs_ws)
                 n_launch += 2
-            with self._timed("big_gemm"):
-                gemm(dzc, W(names[3] + "/kernel"), gacts[2], transb=True, mask=acts[2], precision=pr, round_out=tc)
-            n_launch += 1
+            if not big16:
+                with self._timed("big_gemm"):
+                    gemm(dzc, W(names[3] + "/kernel"), gacts[2], transb=True, mask=acts[2], precision=pr, round_out=tc)
+                n_launch += 1
             for i in (2, 1):
                 small_dw(acts_1[i - 1], gacts[i], GKB(names[i]))
                 gemm(gacts[i], W(names[i] + "/kernel"), gacts[i - 1], transb=True, mask=acts[i - 1], precision=pr,
@@ -353,7 +401,12 @@ class DAEEngine:
         g1 = self.ga[0]
         colsum(g1, G("encoder_e1/bias"), self.cs_ws); n_launch += 2
         gw1 = G("encoder_e1/kernel")
-        if tc:
+        if big16:
+            to_bf16(g1[:B], self.g1_16)
+            with self._timed("dw1_gemm"):
+                gemm(self.x_dense[:, :self.C], self.g1_16, gw1, transa=True, precision="bf16")
+            n_launch += 1
+        elif tc:
             # dW1 = x^T g1 on the tensor cores (x dense 0/1 is exact in tf32); beats 1.1e9 L2 atomics
             with self._timed("dw1_gemm"):
                 gemm(self.x_dense[:, :self.C], g1[:B], gw1, transa=True, precision=pr)

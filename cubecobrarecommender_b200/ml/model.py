@@ -255,10 +255,13 @@ class CC_Recommender:
         self.device = torch.device(device)
         self.precision = precision
         self.store = ParamStore(self.N, self.device)
-        if precision == "tf32":
+        # "fp32": exact FFMA GEMMs; "tf32": tcgen05 kind::tf32 everywhere; "bf16": the seven 512 <-> C passes of the
+        # train step on kind::f16 with bf16 operands (fp32 accumulation, fp32 master weights), everything else as tf32
+        if precision in ("tf32", "bf16"):
             self.store.enable_tf32_shadow()
         elif precision not in ("fp32",):
-            raise NotImplementedError(f"precision {precision!r}: supported modes are 'fp32' (exact FFMA) and 'tf32' (tcgen05)")
+            raise NotImplementedError(f"precision {precision!r}: supported modes are 'fp32', 'tf32' and 'bf16'")
+        self.gemm_precision = "tf32" if precision == "bf16" else precision      # model-level (inference) GEMMs
         self.store.init_glorot(seed)
         self.encoder = _Tower(self, "encoder")
         self.decoder = _Tower(self, "decoder")
@@ -269,11 +272,11 @@ class CC_Recommender:
         s = self.store
         b = sb.batch
         h = torch.empty((b, 512), dtype=torch.float32, device=self.device)
-        rnd = self.precision == "tf32"
+        rnd = self.precision != "fp32"
         bag_fwd(s.p("encoder_e1/kernel"), sb.idx, sb.row_start, sb.row_len, s.p("encoder_e1/bias"), h, round_tf32=rnd)
         for name, width in zip(ENC_NAMES[1:], HIDDEN[1:]):
             o = torch.empty((b, width), dtype=torch.float32, device=self.device)
-            gemm(h, s.w(name + "/kernel"), o, bias=s.p(name + "/bias"), relu=True, precision=self.precision,
+            gemm(h, s.w(name + "/kernel"), o, bias=s.p(name + "/bias"), relu=True, precision=self.gemm_precision,
                  round_out=rnd)
             h = o
         return h
@@ -283,7 +286,7 @@ class CC_Recommender:
         s = self.store
         b = h.shape[0]
         names = dec_names(prefix)
-        rnd = self.precision == "tf32"
+        rnd = self.precision != "fp32"
         h = h.contiguous()
         if rnd:   # a caller-supplied latent is an operand of a kind::tf32 GEMM: round it like every other one
             hr = torch.empty_like(h)
@@ -291,12 +294,12 @@ class CC_Recommender:
             h = hr
         for name, width in zip(names[:3], (128, 256, 512)):
             o = torch.empty((b, width), dtype=torch.float32, device=self.device)
-            gemm(h, s.w(name + "/kernel"), o, bias=s.p(name + "/bias"), relu=True, precision=self.precision,
+            gemm(h, s.w(name + "/kernel"), o, bias=s.p(name + "/bias"), relu=True, precision=self.gemm_precision,
                  round_out=rnd)
             h = o
         cpad = (self.N + 3) // 4 * 4
         z = torch.empty((b, cpad), dtype=torch.float32, device=self.device)[:, :self.N]
-        gemm(h, s.w(names[3] + "/kernel"), z, bias=s.p(names[3] + "/bias"), precision=self.precision)
+        gemm(h, s.w(names[3] + "/kernel"), z, bias=s.p(names[3] + "/bias"), precision=self.gemm_precision)
         return z
 
     def call(self, inputs, training=None):

@@ -20,7 +20,8 @@ def _sms():
 def gemm(a, b, c, *, transa=False, transb=False, bias=None, relu=False, mask=None, accumulate=False,
          precision="tf32", split_k=0, tile_n=0, round_out=False):
     """split_k = 0 / tile_n = 0: the library picks the tile width (128 | 256) and the K split from a
-    wave-quantisation model (csrc/gemm_tc.cu plan_eff)."""
+    wave-quantisation model (csrc/gemm_tc.cu plan_eff).  ``round_out``: round the fp32 output to tf32 (it feeds a
+    kind::tf32 GEMM), whatever the operand kind of this GEMM."""
     m, n = c.shape
     k = a.shape[0] if transa else a.shape[1]
     want = torch.float32 if precision == "tf32" else torch.bfloat16
@@ -28,7 +29,7 @@ def gemm(a, b, c, *, transa=False, transb=False, bias=None, relu=False, mask=Non
         raise TypeError(f"precision {precision} needs {want} operands, got {a.dtype} / {b.dtype}")
     call("cc_gemm_tc", PRECISION_CODE[precision], int(transa), int(transb), m, n, k, ptr(a), a.stride(0), ptr(b),
          b.stride(0), ptr(c), c.stride(0), ptr(bias), int(relu), ptr(mask), mask.stride(0) if mask is not None else 0,
-         int(accumulate), int(split_k or 0), int(tile_n), int(round_out and precision == "tf32"), stream_ptr())
+         int(accumulate), int(split_k or 0), int(tile_n), int(round_out), stream_ptr())
     return c
 
 
@@ -37,9 +38,12 @@ def gemm_bce(a, w, bias, ybits, count, dz, loss_partial, precision="tf32", round
     receives the column sums of dlogits = the gradient of ``bias``."""
     m, k = a.shape
     n = w.shape[1]
+    dz16 = dz.dtype == torch.bfloat16        # bf16 dlogits for the bf16 dW / dX GEMMs ("bf16" mode)
+    if dz16 and precision != "bf16":
+        raise TypeError("bf16 dlogits come with bf16 operands")
     call("cc_gemm_bce_tc", PRECISION_CODE[precision], m, n, k, ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(bias),
          ptr(ybits), ybits.stride(0), float(count), ptr(dz), dz.stride(0), ptr(loss_partial), ptr(dbias),
-         int(round_out and precision == "tf32"), stream_ptr())
+         int(round_out and precision == "tf32"), int(dz16), stream_ptr())
 
 
 def bce_partial_count(m, lddz):

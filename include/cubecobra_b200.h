@@ -133,6 +133,13 @@ int cc_noise(const int64_t* indptr, const int32_t* indices, const int32_t* batch
              uint64_t seed, const int64_t* step_ptr, int32_t max_size, int32_t x_stride, int32_t* x_idx,
              int32_t* x_len, uint32_t* y_bits, int64_t y_words, int32_t* flips_out, int* overflow_flag,
              float* x_dense /* nullable: dense 0/1 rows of x, [batch][ld_dense] */, int64_t ld_dense, void* stream);
+/* Same, with the dense 0/1 rows optionally written as bf16 (dense_bf16 != 0; x_dense then points at bf16 rows of
+ * ld_dense elements) for the bf16 form of the dW1 = x^T g1 GEMM. */
+int cc_noise_ex(const int64_t* indptr, const int32_t* indices, const int32_t* batch_ids, int32_t batch,
+                int32_t num_cards, const float* alias_prob, const int32_t* alias_idx, float noise_mean, float noise_std,
+                uint64_t seed, const int64_t* step_ptr, int32_t max_size, int32_t x_stride, int32_t* x_idx,
+                int32_t* x_len, uint32_t* y_bits, int64_t y_words, int32_t* flips_out, int* overflow_flag,
+                void* x_dense, int64_t ld_dense, int dense_bf16, void* stream);
 int cc_sample_reg_rows(const float* alias_prob, const int32_t* alias_idx, int32_t num_cards, int32_t n, uint64_t seed,
                        const int64_t* step_ptr, int32_t* rows, void* stream);
 int cc_cubes_to_bits(const int32_t* idx, const int64_t* row_start, const int32_t* row_len, int32_t batch,
@@ -170,10 +177,11 @@ int cc_gemm_tc(int precision, int transa, int transb, int m, int n, int k, const
  * never stored; dz[M][lddz] = (sigmoid(z) - y)/count (columns [N, lddz) zeroed, lddz % 32 == 0), loss_partial
  * float64 [cc_gemm_bce_partial_count(m, lddz)] holds per-(tile, warp) loss sums for cc_loss_finalize.  dbias (nullable,
  * float [n]) receives the column sums of dz, i.e. the gradient of the layer's bias (zeroed, then accumulated with float
- * atomics by the epilogue: summation order, hence the last bits, can differ between runs). */
+ * atomics by the epilogue: summation order, hence the last bits, can differ between runs).  dz_bf16 != 0 (precision 2
+ * only): dz is a bf16 matrix (lddz in elements), the form the bf16 dW / dX GEMMs consume. */
 int cc_gemm_bce_tc(int precision, int m, int n, int k, const void* a, int64_t lda, const void* w, int64_t ldw,
-                   const float* bias, const uint32_t* ybits, int64_t ywords, double count, float* dz, int64_t lddz,
-                   double* loss_partial, float* dbias, int round_tf32, void* stream);
+                   const float* bias, const uint32_t* ybits, int64_t ywords, double count, void* dz, int64_t lddz,
+                   double* loss_partial, float* dbias, int round_tf32, int dz_bf16, void* stream);
 int64_t cc_gemm_bce_partial_count(int m, int lddz);
 /* CTA-pair tiling of the tcgen05 GEMMs (256 x 256 tiles on two SMs, tcgen05.mma.cta_group::2):
  * -1 = the planner decides per problem (default), 0 = never, 1 = whenever the shape allows it. */
@@ -208,6 +216,12 @@ int cc_softmax_kl_fuses_dbias(int32_t num_cards, int32_t ncols_pad, int64_t ldz,
 int cc_softmax_kl_fwd_bwd(const float* z, int64_t ldz, const float* target, int64_t ldt, const int32_t* target_rows,
                           int32_t rows, int32_t num_cards, int32_t ncols_pad, double grad_scale, float* dz,
                           int64_t lddz, double* row_loss, int round_tf32, float* dbias, void* stream);
+/* Same with the dlogits written as bf16 into dz_bf16 [rows][lddz_bf16] instead of dz (needs dbias != NULL, i.e. the
+ * persistent kernel); dz may then be NULL. */
+int cc_softmax_kl_fwd_bwd_ex(const float* z, int64_t ldz, const float* target, int64_t ldt, const int32_t* target_rows,
+                             int32_t rows, int32_t num_cards, int32_t ncols_pad, double grad_scale, float* dz,
+                             int64_t lddz, double* row_loss, int round_tf32, float* dbias, void* dz_bf16,
+                             int64_t lddz_bf16, void* stream);
 /* out3 (float64 [3]) = { sum(bce_rows)/bce_div, sum(kl_rows)/kl_div, bce + reg*kl } */
 int cc_loss_finalize(const double* bce_rows, int32_t nb, double bce_div, const double* kl_rows, int32_t nr,
                      double kl_div, double reg, double* out3, void* stream);
@@ -229,6 +243,8 @@ int cc_adam_step(float* params, const float* grads, float* m, float* v, int64_t 
 int cc_adam_step_p2p(const void* const* grads_ptrs, void* const* params_ptrs, int world, int rank, float* m, float* v,
                      int64_t lo, int64_t hi, const int64_t* step_ptr, float lr, float beta1, float beta2, float eps,
                      const void* grads_multicast, void* params_multicast, void* stream);
+/* fp32 [rows][ld_src] -> bf16 [rows][ld_dst], round to nearest even (cols, ld_src, ld_dst multiples of 4). */
+int cc_convert_f32_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int32_t rows, int32_t cols, void* stream);
 int cc_round_tf32(const float* x, float* out, int64_t n, void* stream);
 int cc_sigmoid_f32(const float* z, float* out, int64_t n, void* stream);
 

@@ -321,11 +321,14 @@ def test_gemm_bce_fused_epilogue_vs_oracle(m, c, pair, pair_mode):
 # tf32: the north-star bar is the per-step loss (1e-3 relative).  Gradients are held to 1e-2 of their max on
 # the first step (identical weights); afterwards Adam's m/sqrt(v) (= sign(g) on step 1) amplifies rounding
 # of near-zero gradients into +-lr weight differences, so later steps compare two slightly different nets.
+# bf16 (reported separately from the fp32/tf32 headline, BASELINE north star): bf16 operands (8-bit mantissa) in the seven
+# 512 <-> C passes, fp32 accumulation and master weights; stated tolerance: loss 2e-3 relative, gradients 5e-2 of their max.
 TOL = {"fp32": dict(loss=1e-5, grad=2e-4, grad_later=2e-4, weight=3e-4),
-       "tf32": dict(loss=1e-3, grad=1e-2, grad_later=6e-2, weight=2.5e-3)}
+       "tf32": dict(loss=1e-3, grad=1e-2, grad_later=6e-2, weight=2.5e-3),
+       "bf16": dict(loss=2e-3, grad=5e-2, grad_later=0.2, weight=4e-3)}
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
 @pytest.mark.parametrize("r", [48, 0])
 def test_train_steps_match_oracle(r, precision):
     c, x, y, rows, mh = _problem(r=max(r, 1))
@@ -463,3 +466,77 @@ def test_full_identity_regulariser_and_its_row_shards(precision):
     for kname in ("reg_reconstruction/kernel", "reg_d1/kernel", "reg_reconstruction/bias"):
         ssum = g0[kname] + g1[kname]
         assert np.abs(ssum - g_full[kname]).max() / (np.abs(g_full[kname]).max() + 1e-30) < (1e-5 if precision == "fp32" else 2e-3), kname
+
+
+@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("ta,tb,m,n,k", [(0, 0, 130, 72, 136), (0, 1, 64, 264, 104), (1, 0, 136, 128, 304), (1, 1, 24, 24, 40),
+                                         (0, 0, 4096, 512, 256), (1, 0, 512, 264, 4096), (0, 1, 300, 520, 20992)])
+def test_gemm_tcgen05_bf16_all_layouts(ta, tb, m, n, k, pair, pair_mode):
+    """tcgen05 kind::f16 GEMM on bf16 operands (fp32 accumulation, fp32 output): products of bf16 values are exact in
+    fp32, so only the accumulation order differs from the float64 reference.  K-major and MN-major operands, ragged
+    tiles, CTA pairs.  (Leading dimensions are multiples of 8 elements: TMA rows are multiples of 16 bytes.)"""
+    from cubecobrarecommender_b200.ml import tensorcore as TC
+    pair_mode(pair)
+    g = torch.Generator(device="cuda").manual_seed(m * n + k)
+    a = torch.randn((k, m) if ta else (m, k), device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randn((n, k) if tb else (k, n), device="cuda", generator=g).to(torch.bfloat16)
+    ref = (a.t() if ta else a).double() @ (b.t() if tb else b).double()
+    scale = ref.abs().max().item()
+    c = torch.full((m, n), 7.0, device="cuda")
+    TC.gemm(a, b, c, transa=bool(ta), transb=bool(tb), precision="bf16", split_k=1, tile_n=256 if n > 128 else 128)
+    assert (c.double() - ref).abs().max().item() / scale < 2e-5 + 4e-9 * k
+    bias = torch.randn(n, device="cuda", generator=g)
+    c2 = torch.full((m, n), 7.0, device="cuda")
+    TC.gemm(a, b, c2, transa=bool(ta), transb=bool(tb), bias=bias, relu=True, precision="bf16")
+    assert (c2.double() - torch.relu(ref + bias.double())).abs().max().item() / scale < 2e-5 + 4e-9 * k
+
+
+def test_bf16_mode_pieces():
+    """The extra pieces of the "bf16" mode: fp32 -> bf16 conversion (round to nearest even), the fused BCE epilogue
+    writing bf16 dlogits (+ bias gradient from the rounded values), the noise kernel's bf16 dense rows, the
+    persistent softmax-KL kernel writing bf16 dlogits."""
+    from cubecobrarecommender_b200.ml import tensorcore as TC
+    g = torch.Generator(device="cuda").manual_seed(8)
+    # (1) conversion
+    src = torch.randn(37, 520, device="cuda", generator=g)
+    dst = torch.zeros(37, 512, dtype=torch.bfloat16, device="cuda")
+    E.call("cc_convert_f32_bf16", E.ptr(src), src.stride(0), E.ptr(dst), dst.stride(0), 37, 512, E.stream_ptr())
+    assert torch.equal(dst, src[:, :512].to(torch.bfloat16))
+    # (2) fused BCE with bf16 dlogits
+    m, k, c = 200, 512, 1000
+    cpad = 1024
+    a = torch.randn(m, k, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(k, cpad, device="cuda", generator=g) * 0.2).to(torch.bfloat16)
+    bias = torch.randn(c, device="cuda", generator=g)
+    y = (torch.rand(m, c, device="cuda", generator=g) < 0.05).double().cpu().numpy()
+    yb = torch.tensor(_bits_from_dense(y)).cuda()
+    dz = torch.full((m, cpad), 9.0, dtype=torch.bfloat16, device="cuda")
+    part = torch.zeros(TC.bce_partial_count(m, cpad), dtype=torch.float64, device="cuda")
+    dbias = torch.full((c,), 5.0, device="cuda")
+    TC.gemm_bce(a, w[:, :c], bias, yb, float(m * c), dz, part, precision="bf16", dbias=dbias)
+    z = (a.double() @ w[:, :c].double() + bias.double()).cpu().numpy()
+    ref_loss = od.bce_from_logits_np(z, y)
+    assert abs(part.sum().item() / (m * c) - ref_loss) / ref_loss < 1e-5
+    ref_dz = (1 / (1 + np.exp(-z)) - y) / (m * c)
+    got = dz[:, :c].float().cpu().numpy()
+    assert np.abs(got - ref_dz).max() <= 2.0 ** -8 * np.abs(ref_dz).max()          # bf16: 8 significant bits
+    assert (dz[:, c:] == 0).all()
+    assert np.abs(dbias.cpu().numpy() - got.astype(np.float64).sum(0)).max() < 1e-5 * np.abs(got.sum(0)).max() + 1e-12
+    # (3) noise kernel: bf16 dense rows == float dense rows
+    from cubecobrarecommender_b200 import graph as G
+    cc, kk, b = 384, 96, 32
+    ip, ix = synth_cubes_csr(kk, cc, size_lo=12, size_hi=70, seed=7)
+    csr = CubeCSR(ip, ix, cc)
+    gr = G.build_graph(csr, "cuda", want_m64=False)
+    prob, alias = E.alias_table(gr.neg_sampler.cpu().numpy(), "cuda")
+    indptr, indices = G.upload_csr(csr, "cuda")
+    dense = {}
+    for prec in ("tf32", "bf16"):
+        model = M.CC_Recommender(cc, device="cuda", precision=prec)
+        eng = E.DAEEngine(model, gr.mhat, batch=b, reg_rows=b, reg=0.1, max_cube_size=80)
+        eng.sample_batch(indptr, indices, torch.arange(b, dtype=torch.int32, device="cuda"), prob, alias, seed=5)
+        dense[prec] = eng.x_dense.float().clone()
+        if prec == "bf16":
+            loss = eng.train_step().cpu().numpy()          # one whole step runs (bf16 dlogits out of the softmax-KL kernel)
+            assert np.isfinite(loss).all()
+    assert torch.equal(dense["tf32"], dense["bf16"]) and dense["bf16"].sum() > 0
