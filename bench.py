@@ -240,6 +240,41 @@ def measure_extras(dev, peaks, log):
         "cpu_baseline": {"seconds_extrapolated": t_cpu_sub * nnz_ratio, "cores": 1, "kind": "port",
                          "sample": f"create_adjacency_matrix loop restatement on {ksub} cubes x {C} cards: {t_cpu_sub:.1f}s, scaled by nnz x{nnz_ratio:.0f}"},
     }
+    # ---------------- recommend.py top-50 (configs[0], second half): graph scoring + masked select ----------------
+    try:
+        G.count_cooccurrence(indptr, indices, K, C, counts=counts, workspace=ws, method="tensor")
+        gr = G.normalise(counts, want_m64=True, want_mhat=False, want_neg=False)
+        grec = G.GraphRecommender(gr.m64)
+        one = csr.rows(np.arange(1))
+        many = csr.rows(np.arange(256))
+        grec.recs(one, 50); grec.recs(many, 50)
+        torch.cuda.synchronize()
+        t5 = time.time()
+        ids1, _, _ = grec.recs(one, 50); ids1 = ids1.cpu().numpy()
+        t_one = time.time() - t5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); grec.recs(many, 50); e1.record(); torch.cuda.synchronize()
+        t_many = e0.elapsed_time(e1) / 1e3
+        nnz_many = int(many.indptr[-1])
+        m_host = gr.m64.cpu().numpy()                       # the 3.5 GB matrix the reference np.load()s per invocation
+        t6 = time.time()
+        ref_ids = og.simple_recs(one.to_dense()[0], m_host)[:50]
+        t_cpu_one = time.time() - t6
+        out["graph_recommend"] = {
+            "workload": f"recommend.py top-50: sum of the cube's rows of M (float64, C={C}) + masked select",
+            "one_cube_seconds": t_one, "one_cube_note": "host CSR in, ids out, M resident on the GPU",
+            "batch256_cubes_per_s": 256 / t_many,
+            "roofline": {"kernel": "gather_leaf_kernel (+ combine, select)", "bound": "hbm",
+                         "achieved": nnz_many * C * 8.0 / t_many / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": nnz_many * C * 8.0 / t_many / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                         "note": "algorithmic bytes s*C*8 per cube (SURVEY.md 8d config 1b) over the whole batched call"},
+            "ids_equal_reference_ranking": bool(np.array_equal(ids1[0], np.asarray(ref_ids))),
+            "cpu_baseline": {"seconds": t_cpu_one, "cores": 1, "kind": "port",
+                             "sample": "simple_recs restatement on one cube, M already in host memory (the reference "
+                                       "also np.load()s the 3.5 GB file on every invocation)"}}
+        del gr, grec, m_host
+    except Exception as e:  # side measurement: never take the headline down
+        out["graph_recommend"] = {"error": repr(e)}
     del counts, bits, ws
     torch.cuda.empty_cache()
     # ---------------- batched ML recommend: top-50 with in-cube masking ----------------

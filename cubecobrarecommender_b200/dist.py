@@ -46,6 +46,15 @@ def loss_scales(global_batch: int, global_reg_rows: int, num_cards: int, reg: fl
     return 1.0 / (float(global_batch) * float(num_cards)), (reg / float(global_reg_rows)) if global_reg_rows else 0.0
 
 
+def owner_slice(total: int, rank: int, world: int):
+    """Slice ``[lo, hi)`` of the flat parameter buffer that ``rank`` owns in the peer-memory data-parallel step
+    (cc_adam_step_p2p): the slices tile ``[0, total)`` exactly and start on 4-element (16-byte) boundaries."""
+    quarter = total // 4
+    lo = (quarter * rank // world) * 4
+    hi = (quarter * (rank + 1) // world) * 4 if rank + 1 < world else total
+    return lo, hi
+
+
 class GradBuckets:
     """Contiguous slices of the flat gradient buffer in the order backward finishes them:
     "main" decoder, "reg" decoder, then the shared "enc"oder (whose 512 x C first-layer gradient is

@@ -104,8 +104,8 @@ class ParamStore:
         self.peer_params = np.array(pp, dtype=np.uint64)
         self.peer_grads = np.array(gp, dtype=np.uint64)
         self.dp_rank, self.dp_world = rank, world
-        quarter = self.total // 4                   # slices are 16-byte aligned (offsets are padded to 4 floats)
-        self.dp_slice = ((quarter * rank // world) * 4, (quarter * (rank + 1) // world) * 4 if rank + 1 < world else self.total)
+        from ..dist import owner_slice
+        self.dp_slice = owner_slice(self.total, rank, world)   # 16-byte aligned (offsets are padded to 4 floats)
         torch.cuda.synchronize(self.device)
         dist.barrier(group)
 

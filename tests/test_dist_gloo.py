@@ -131,3 +131,17 @@ def test_gradient_buckets_tile_the_flat_buffer_and_match_one_allreduce():
         assert spans[0][0] == 0 and spans[-1][1] == total
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))          # no gap, no overlap
         assert all(lo % 4 == 0 for lo, _ in spans)                          # 16-byte aligned for the Adam kernel
+
+
+def test_owner_slices_and_full_identity_shards_partition_exactly():
+    from cubecobrarecommender_b200.ml.engine import full_identity_shard
+    from cubecobrarecommender_b200.ml.model import ParamStore
+    total = ParamStore(20884, "cpu").total
+    for world in (1, 2, 3, 4, 8, 16):
+        spans = [D.owner_slice(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert all(lo % 4 == 0 and hi % 4 == 0 for lo, hi in spans)           # float4 / 16-byte aligned
+        assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 4 + total % 4
+        rows = [full_identity_shard(20884, r, world) for r in range(world)]
+        assert rows[0][0] == 0 and rows[-1][1] == 20884 and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
