@@ -63,6 +63,7 @@ SIGNATURES = {
     "cc_gemm_bce_tc": (I, [I, I, I, I, P, I64, P, I64, P, P, I64, D, P, I64, P, P, I, I, P]),
     "cc_gemm_bce_partial_count": (I64, [I, I]),
     "cc_gemm_tc_set_pair_mode": (I, [I]),
+    "cc_gemm_tc_plan": (I, [I, I, I, I, I, I, P]),
     "cc_gemm_tc_set_dynamic_tiles": (I, [I]),
     "cc_gemm_tc_set_pdl": (I, [I]),
     "cc_colsum_workspace_bytes": (I64, [I, I]),

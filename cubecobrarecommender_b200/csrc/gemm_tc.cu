@@ -915,6 +915,33 @@ using namespace cc;
 
 extern "C" {
 
+// The planner behind cc_gemm_tc (host logic only: no device work): plan = {tile width, K split, CTAs per tile}.
+// Candidates: (tile width, CTA pairing, K split); pairs only come as 256 x 256 tiles.
+int cc_gemm_tc_plan(int precision, int m, int n, int k, int tile_n, int split_k, int* plan) {
+  CC_REQUIRE(plan && (precision == 1 || precision == 2) && m > 0 && n > 0 && k > 0, "cc_gemm_tc_plan: bad arguments");
+  const int kblocks = ceil_div(k, precision == 2 ? 64 : 32);
+  const int sms = sm_count();
+  int bn = tile_n, split = split_k, ctas = 1;
+  double best = -1.0;
+  const int bns[3] = {256, 256, 128};
+  const int cts[3] = {2, 1, 1};
+  for (int bi = 0; bi < 3; ++bi) {
+    if (tile_n && bns[bi] != tile_n) continue;
+    if (!tile_n && bns[bi] == 256 && n <= 128) continue;
+    if (cts[bi] == 2 && tc::g_pair_mode == 0) continue;
+    // small layers are latency-bound: single CTAs spread them over more SMs and skip the cluster handshakes
+    if (cts[bi] == 2 && tc::g_pair_mode < 0 && 2.0 * m * n * double(k) < 2.0e10) continue;
+    if (cts[bi] == 1 && tc::g_pair_mode == 1 && (tile_n == 0 || tile_n == 256) && n > 128) continue;
+    const int smax = split_k > 0 ? split_k : (kblocks >= 16 ? (kblocks / 8 < 64 ? kblocks / 8 : 64) : 1);
+    for (int s = (split_k > 0 ? split_k : 1); s <= smax; ++s) {
+      const double e = tc::plan_eff(m, n, kblocks, bns[bi], s, sms, cts[bi]);
+      if (e > best + 1e-9) { best = e; bn = bns[bi]; split = s; ctas = cts[bi]; }
+    }
+  }
+  plan[0] = bn; plan[1] = split; plan[2] = ctas;
+  return CC_OK;
+}
+
 // precision: 1 = tf32 (float operands), 2 = bf16 (__nv_bfloat16 operands; C, bias, mask stay float).
 // split_k: 0 = choose (tile width and split) automatically, >= 1 = as given (tile_n: 0 auto | 128 | 256).
 int cc_gemm_tc(int precision, int transa, int transb, int m, int n, int k, const void* a, int64_t lda, const void* b,
@@ -926,28 +953,9 @@ int cc_gemm_tc(int precision, int transa, int transb, int m, int n, int k, const
   CC_REQUIRE(tile_n == 0 || tile_n == 128 || tile_n == 256, "cc_gemm_tc: tile_n must be 0, 128 or 256");
   if (m == 0 || n == 0) return CC_OK;
   cudaStream_t st = as_stream(stream);
-  const int kblocks = ceil_div(k, precision == 2 ? 64 : 32);
-  const int sms = sm_count();
-  // candidates: (tile width, CTA pairing, K split); pairs only come as 256 x 256 tiles
-  int bn = tile_n, split = split_k, ctas = 1;
-  {
-    double best = -1.0;
-    const int bns[3] = {256, 256, 128};
-    const int cts[3] = {2, 1, 1};
-    for (int bi = 0; bi < 3; ++bi) {
-      if (tile_n && bns[bi] != tile_n) continue;
-      if (!tile_n && bns[bi] == 256 && n <= 128) continue;
-      if (cts[bi] == 2 && tc::g_pair_mode == 0) continue;
-      // small layers are latency-bound: single CTAs spread them over more SMs and skip the cluster handshakes
-      if (cts[bi] == 2 && tc::g_pair_mode < 0 && 2.0 * m * n * double(k) < 2.0e10) continue;
-      if (cts[bi] == 1 && tc::g_pair_mode == 1 && (tile_n == 0 || tile_n == 256) && n > 128) continue;
-      const int smax = split_k > 0 ? split_k : (kblocks >= 16 ? (kblocks / 8 < 64 ? kblocks / 8 : 64) : 1);
-      for (int s = (split_k > 0 ? split_k : 1); s <= smax; ++s) {
-        const double e = tc::plan_eff(m, n, kblocks, bns[bi], s, sms, cts[bi]);
-        if (e > best + 1e-9) { best = e; bn = bns[bi]; split = s; ctas = cts[bi]; }
-      }
-    }
-  }
+  int plan[3];
+  cc_gemm_tc_plan(precision, m, n, k, tile_n, split_k, plan);
+  const int bn = plan[0], split = plan[1], ctas = plan[2];
   const bool nonlinear = bias || relu || mask || round_tf32;
   const bool two_pass = split > 1 && nonlinear;
   CC_REQUIRE(!(two_pass && accumulate), "cc_gemm_tc: accumulate with a split-K non-linear epilogue is not supported");

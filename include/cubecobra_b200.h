@@ -186,6 +186,9 @@ int64_t cc_gemm_bce_partial_count(int m, int lddz);
 /* CTA-pair tiling of the tcgen05 GEMMs (256 x 256 tiles on two SMs, tcgen05.mma.cta_group::2):
  * -1 = the planner decides per problem (default), 0 = never, 1 = whenever the shape allows it. */
 int cc_gemm_tc_set_pair_mode(int mode);
+/* The planner cc_gemm_tc uses (host logic, no device work): plan[0] = tile width (128 | 256), plan[1] = K split,
+ * plan[2] = CTAs per tile (1, or 2 = a 256 x 256 CTA-pair tile), from a wave-quantisation model over the SM count. */
+int cc_gemm_tc_plan(int precision, int m, int n, int k, int tile_n, int split_k, int* plan);
 /* Tile scheduling of the persistent tcgen05 GEMMs: 0 (default) = static round-robin, 1 = tiles drawn at run time from
  * a global atomic counter, so CTAs that start late or lose their SM to a concurrent kernel (an NCCL all_reduce
  * overlapping backward) take fewer tiles instead of stretching the GEMM. */

@@ -66,3 +66,26 @@ def test_missing_library_fails_loudly(tmp_path, monkeypatch):
     monkeypatch.setattr(_lib, "_lib", None)
     with pytest.raises(_lib.CubeCobraError):
         _lib.load(str(tmp_path / "nope.so"))
+
+
+def test_gemm_planner_choices(lib):
+    """Host-side planner of the tcgen05 GEMMs (no GPU needed; 148 SMs assumed without a device): the 512 <-> C
+    passes of the train step run on 256 x 256 CTA-pair tiles with enough tiles to fill the 74 pairs, the small layers
+    stay on single CTAs, explicit requests are honoured."""
+    def plan(m, n, k, precision=1, tile_n=0, split_k=0):
+        out = np.zeros(3, dtype=np.int32)
+        _lib.call("cc_gemm_tc_plan", precision, m, n, k, tile_n, split_k, _lib.ptr(out))
+        return tuple(int(v) for v in out)
+    B, C, H = 4096, 20884, 512
+    for m, n, k in ((B, C, H), (H, C, B), (B, H, C), (C, H, B)):          # fwd, dW, dX, dW1
+        bn, split, ctas = plan(m, n, k)
+        assert (bn, ctas) == (256, 2)
+        tiles = -(-m // 256) * -(-n // 256) * split
+        assert tiles >= 74                                                  # at least one full wave of CTA pairs
+    assert plan(B, C, H)[1] == 1 and plan(B, H, C)[1] > 1                    # only the long-K pass is split
+    for m, n, k in ((8192, 256, 512), (8192, 128, 256), (4096, 512, 256), (512, 256, 8192), (64, 128, 4096)):
+        assert plan(m, n, k)[2] == 1                                        # small layers: latency-bound, single CTAs
+    assert plan(8192, 64, 128)[0] == 128                                    # narrow outputs never take 256-wide tiles
+    assert plan(B, C, H, tile_n=128, split_k=1) == (128, 1, 1)
+    assert plan(B, H, C, tile_n=256, split_k=7)[:2] == (256, 7)
+    assert plan(B, C, H, precision=2)[0] == 256
