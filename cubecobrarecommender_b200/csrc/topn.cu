@@ -467,8 +467,289 @@ static int warpselect_launch(const float* scores, int64_t ld, int32_t num_cards,
   return CC_OK;
 }
 
-// the radix-select kernel stays the general path (any n, float64); float32 with n <= 128 takes the streaming select
+// ------------------------------------------------------------- CTA-per-cube row select (float32, n <= 128)
+// The HBM-bound form of the select.  A persistent CTA per SM walks the cubes; each cube's score row (4C bytes,
+// 83.5 KB at C = 20 884) is pulled into shared memory by bulk asynchronous copies (cp.async.bulk, completion on an
+// mbarrier), double-buffered, so the row of cube i+1 streams in from HBM while cube i is being ranked and no thread
+// ever waits on a global load.  Ranking a resident row takes two conflict-free sweeps of it:
+//   sweep 1  every thread keeps the best element of its stride; the 512 thread leaders are merged to 128 and their
+//            n-th largest composite key T is found by rank counting.  T is the key of a real element and at least n
+//            elements have keys >= T, so T is a valid lower bound of the answer's last key; with the row spread over
+//            128 strides only ~1.3 n elements lie above it (n = 50: ~63).
+//   sweep 2  the elements with key >= T (pre-filtered by one float compare against the raw-value bound of T) are
+//            appended to a small buffer, ranked against each other by counting, and written at their rank.
+// Masked cards are overwritten with a NaN sentinel in the shared copy of the row (every compare with it is false), so
+// the sweeps carry no mask test.  If an adversarial row leaves more than RS_CAP survivors, T is raised to the n-th
+// largest of the first RS_CAP of them (again a valid bound, strictly tighter) and sweep 2 is repeated.  Same total
+// order on (score, index) as the two kernels above => identical ids.  NaN scores are never selected.
+constexpr int RS_THREADS = 512;
+constexpr int RS_CAP = 1024;
+constexpr int RS_LEADERS = 128;
+constexpr uint32_t RS_SENTINEL = 0x7fc0babeu;      // quiet NaN with a payload no arithmetic produces
+constexpr uint32_t RS_COPY_BYTES = 16384;          // one bulk copy; a row is a handful of them on one barrier
+static_assert(RS_THREADS == 4 * RS_LEADERS, "rs_rank_partial splits the compare range into RS_THREADS / RS_LEADERS = 4 parts");
+
+__device__ __forceinline__ uint32_t rs_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void rs_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rs_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void rs_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rs_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rs_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = rs_smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) break;
+    if (++spins > (1u << 26)) __trap();            // watchdog: a protocol bug must not hang the GPU
+  }
+}
+__device__ __forceinline__ void rs_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(rs_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(rs_smem_u32(bar)) : "memory");
+}
+
+// rk[i] += #{ j in this thread's quarter of [0, m) : keys[j] > keys[i] }.  The caller zeroes rk[0, m) and
+// synchronises before, and synchronises after; then rk[i] is the rank of keys[i] (0 = largest).  The inner loop reads
+// one key per iteration for the whole warp (a broadcast), so it is conflict-free.
+__device__ __forceinline__ void rs_rank_partial(const unsigned long long* keys, int m, int* rk, int tid) {
+  const int g = tid & (RS_LEADERS - 1), q = tid / RS_LEADERS;
+  const int chunk = (m + 3) >> 2;
+  const int j0 = q * chunk, j1 = min(m, j0 + chunk);
+  for (int i = g; i < m; i += RS_LEADERS) {
+    const unsigned long long mine = keys[i];
+    int c = 0;
+    for (int j = j0; j < j1; ++j) c += (keys[j] > mine) ? 1 : 0;
+    if (c) atomicAdd(&rk[i], c);
+  }
+}
+
+// a bound on the RAW value such that no element whose key is >= thr fails `maybe` (same construction as in the
+// streaming select above: the threshold's own score, or -- fused sigmoid -- its logit taken 1e-6 relative on the safe side)
+template <bool SIGMOID>
+__device__ __forceinline__ float rs_raw_bound(unsigned long long thr, int descending) {
+  if (thr == 0ull) return descending ? -INFINITY : INFINITY;
+  uint32_t u = (uint32_t)(thr >> 32);
+  if (!descending) u = ~u;
+  const float pthr = __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
+  if (!SIGMOID) return pthr;
+  const double p = double(pthr);
+  if (descending) {
+    const double pm = p * (1.0 - 1e-6) - 1e-40;
+    return pm <= 0.0 ? -INFINITY : float(log(pm / (1.0 - pm))) - 1e-3f;
+  }
+  const double pp = p * (1.0 + 1e-6) + 1e-40;
+  return pp >= 1.0 ? INFINITY : float(log(pp / (1.0 - pp))) + 1e-3f;
+}
+
+template <bool SIGMOID>
+__global__ void __launch_bounds__(RS_THREADS, 1)
+topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_cards, int32_t batch,
+                      const int64_t* __restrict__ mask_ptr, const int32_t* __restrict__ mask_idx,
+                      int mode_only_listed, int descending, int32_t n, int32_t* __restrict__ out_ids,
+                      float* __restrict__ out_vals, int32_t* __restrict__ out_count) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ unsigned long long s_T;
+  __shared__ float s_zb;
+  __shared__ int s_cnt, s_listed;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int cr = (num_cards + 3) & ~3;                      // row length in shared memory (<= ld: ld % 4 == 0)
+  const uint32_t row_bytes = uint32_t(cr) * 4u;
+  const int words = (num_cards + 31) >> 5;
+  float* const row_base = reinterpret_cast<float*>(smem_raw);                                           // 2 rows of cr floats
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + 2 * size_t(row_bytes));   // RS_CAP
+  unsigned long long* tkey = keys + RS_CAP;                                                            // RS_THREADS
+  int* rk = reinterpret_cast<int*>(tkey + RS_THREADS);                                                 // RS_CAP
+  uint32_t* bm = reinterpret_cast<uint32_t*>(rk + RS_CAP);                                             // words
+
+  auto issue = [&](int cube, int b) {                       // one thread: the whole row on barrier b
+    const char* src = reinterpret_cast<const char*>(scores + int64_t(cube) * ld);
+    char* dst = reinterpret_cast<char*>(row_base + size_t(b) * cr);
+    rs_mbar_expect_tx(&bar[b], row_bytes);
+    for (uint32_t off = 0; off < row_bytes; off += RS_COPY_BYTES)
+      rs_bulk_g2s(dst + off, src + off, min(RS_COPY_BYTES, row_bytes - off), &bar[b]);
+  };
+
+  const int stride = gridDim.x;
+  if (tid == 0) {
+    rs_mbar_init(&bar[0], 1);
+    rs_mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if ((int)blockIdx.x < batch) issue(blockIdx.x, 0);
+    if ((int)blockIdx.x + stride < batch) issue(blockIdx.x + stride, 1);
+  }
+
+  auto maybe = [&](float x, float zb) -> bool { return descending ? x >= zb : x <= zb; };
+
+  int it = 0;
+  for (int cube = blockIdx.x; cube < batch; cube += stride, ++it) {
+    const int b = it & 1;
+    float* row = row_base + size_t(b) * cr;
+    const int64_t mb = mask_ptr[cube], me = mask_ptr[cube + 1];
+    if (tid == 0) { s_cnt = 0; s_listed = 0; s_T = 0ull; s_zb = descending ? -INFINITY : INFINITY; }
+    for (int i = tid; i < RS_LEADERS; i += RS_THREADS) rk[i] = 0;
+    __syncthreads();
+    rs_mbar_wait(&bar[b], uint32_t(it >> 1) & 1u);
+
+    if (!mode_only_listed) {
+      // masked cards -> sentinel; the exchange also de-duplicates the list for the candidate count
+      int local = 0;
+      for (int64_t p = mb + tid; p < me; p += RS_THREADS) {
+        const int32_t c = mask_idx[p];
+        if (c >= 0 && c < num_cards) {
+          const uint32_t old = atomicExch(reinterpret_cast<uint32_t*>(row) + c, RS_SENTINEL);
+          local += (old != RS_SENTINEL) ? 1 : 0;
+        }
+      }
+      local = warp_sum(local);
+      if (lane == 0 && local) atomicAdd(&s_listed, local);
+      __syncthreads();
+      // sweep 1: the best element of this thread's stride (ties: the index the total order prefers)
+      float best = descending ? -INFINITY : INFINITY;
+      int bi = -1;
+      if (descending) {
+        for (int e = tid; e < num_cards; e += RS_THREADS) { const float x = row[e]; if (x >= best) { best = x; bi = e; } }
+      } else {
+        for (int e = tid; e < num_cards; e += RS_THREADS) { const float x = row[e]; if (x < best) { best = x; bi = e; } }
+      }
+      tkey[tid] = bi >= 0 ? make_key<float>(SIGMOID ? sigmoid_f32(best) : best, (uint32_t)bi, descending) : 0ull;
+      __syncthreads();
+      if (tid < RS_LEADERS) {
+        const unsigned long long a = tkey[tid], c2 = tkey[tid + RS_LEADERS], d = tkey[tid + 2 * RS_LEADERS],
+                                 f = tkey[tid + 3 * RS_LEADERS];
+        const unsigned long long ac = a > c2 ? a : c2, df = d > f ? d : f;
+        keys[tid] = ac > df ? ac : df;
+      }
+      __syncthreads();
+      rs_rank_partial(keys, RS_LEADERS, rk, tid);
+      __syncthreads();
+      if (tid < RS_LEADERS) {
+        if (rk[tid] == n - 1) { const unsigned long long t = keys[tid]; s_T = t; s_zb = rs_raw_bound<SIGMOID>(t, descending); }
+      }
+      __syncthreads();
+    }
+
+    // sweep 2 (repeated with a raised threshold if more than RS_CAP elements survive)
+    int m = 0;
+    for (int round = 0;; ++round) {
+      const unsigned long long T = s_T;
+      const float zb = s_zb;
+      if (mode_only_listed) {
+        for (int w = tid; w < words; w += RS_THREADS) bm[w] = 0u;
+        __syncthreads();
+        for (int64_t p = mb + tid; p < me; p += RS_THREADS) {
+          const int32_t c = mask_idx[p];
+          if (c < 0 || c >= num_cards) continue;
+          const uint32_t bit = 1u << (c & 31);
+          if (atomicOr(&bm[c >> 5], bit) & bit) continue;            // duplicate entry of the list
+          const float x = row[c];
+          if (!maybe(x, zb)) continue;
+          const unsigned long long key = make_key<float>(SIGMOID ? sigmoid_f32(x) : x, (uint32_t)c, descending);
+          if (key >= T) { const int slot = atomicAdd(&s_cnt, 1); if (slot < RS_CAP) keys[slot] = key; }
+        }
+      } else {
+        for (int e = tid; e < num_cards; e += RS_THREADS) {
+          const float x = row[e];
+          if (!maybe(x, zb)) continue;
+          const unsigned long long key = make_key<float>(SIGMOID ? sigmoid_f32(x) : x, (uint32_t)e, descending);
+          if (key >= T) { const int slot = atomicAdd(&s_cnt, 1); if (slot < RS_CAP) keys[slot] = key; }
+        }
+      }
+      __syncthreads();
+      m = s_cnt;
+      if (m <= RS_CAP) break;
+      // overflow: T <- n-th largest of the RS_CAP survivors kept (n <= 128 < RS_CAP), then sweep again
+      for (int i = tid; i < RS_CAP; i += RS_THREADS) rk[i] = 0;
+      __syncthreads();
+      rs_rank_partial(keys, RS_CAP, rk, tid);
+      if (tid == 0) s_cnt = 0;
+      __syncthreads();
+      for (int i = tid; i < RS_CAP; i += RS_THREADS) {
+        if (rk[i] == n - 1) { const unsigned long long t = keys[i]; s_T = t; s_zb = rs_raw_bound<SIGMOID>(t, descending); }
+      }
+      __syncthreads();
+    }
+
+    // rank the m survivors among themselves and write the first n at their rank
+    for (int i = tid; i < m; i += RS_THREADS) rk[i] = 0;
+    __syncthreads();
+    rs_rank_partial(keys, m, rk, tid);
+    __syncthreads();
+    for (int i = tid; i < m; i += RS_THREADS) {
+      const int r = rk[i];
+      if (r < n) {
+        const unsigned long long key = keys[i];
+        uint32_t t = (uint32_t)(key & 0xffffffffu), u = (uint32_t)(key >> 32);
+        if (!descending) { t = ~t; u = ~u; }
+        out_ids[int64_t(cube) * n + r] = (int32_t)t;
+        if (out_vals) out_vals[int64_t(cube) * n + r] = __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
+      }
+    }
+    for (int i = m + tid; i < n; i += RS_THREADS) {
+      out_ids[int64_t(cube) * n + i] = -1;
+      if (out_vals) out_vals[int64_t(cube) * n + i] = 0.f;
+    }
+    if (tid == 0 && out_count) out_count[cube] = min(n, m);
+
+    // this buffer is free again: order the sentinel writes before the asynchronous proxy overwrites them
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0 && cube + 2 * stride < batch) issue(cube + 2 * stride, b);
+  }
+}
+
+static size_t rowselect_smem_bytes(int32_t num_cards) {
+  const size_t cr = (size_t(num_cards) + 3) & ~size_t(3);
+  return 2 * cr * 4 + size_t(RS_CAP) * 8 + size_t(RS_THREADS) * 8 + size_t(RS_CAP) * 4 +
+         size_t((num_cards + 31) / 32) * 4;
+}
+
+// rows must be 16-byte aligned and a whole number of 16-byte units (bulk copies), and two of them must fit in shared memory
+static bool rowselect_eligible(const float* scores, int64_t ld, int32_t num_cards, int32_t n) {
+  return n <= WS_MAX_N && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(scores) & 15) == 0 &&
+         rowselect_smem_bytes(num_cards) + 64 <= 227 * 1024;
+}
+
+template <bool SIGMOID>
+static int rowselect_launch(const float* scores, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
+                            const int32_t* mask_idx, int mode_only_listed, int descending, int32_t n,
+                            int32_t* out_ids, float* out_vals, int32_t* out_count, cudaStream_t st) {
+  const size_t smem = rowselect_smem_bytes(num_cards);
+  CC_CHECK_CUDA(cudaFuncSetAttribute(topn_rowselect_kernel<SIGMOID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = batch < sm_count() ? batch : sm_count();
+  topn_rowselect_kernel<SIGMOID><<<grid, RS_THREADS, smem, st>>>(
+      scores, ld, num_cards, batch, mask_ptr, mask_idx, mode_only_listed, descending, n, out_ids, out_vals, out_count);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+// float32, n <= 128: 0 = automatic (row select when the rows qualify, else the streaming select), 1 = streaming select,
+// 2 = row select (error if the rows do not qualify).  The radix-select kernel stays the general path (any n, float64).
+static int g_topn_algo = 0;
 static int g_topn_force_radix = 0;
+
+template <bool SIGMOID>
+static int select_small_n(const float* scores, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
+                          const int32_t* mask_idx, int mode_only_listed, int descending, int32_t n,
+                          int32_t* out_ids, float* out_vals, int32_t* out_count, cudaStream_t st) {
+  const bool ok = rowselect_eligible(scores, ld, num_cards, n);
+  CC_REQUIRE(ok || g_topn_algo != 2, "cc_topn_masked: the row select needs ld %% 4 == 0, 16-byte aligned rows and C <= ~26 000");
+  if (ok && g_topn_algo != 1)
+    return rowselect_launch<SIGMOID>(scores, ld, num_cards, batch, mask_ptr, mask_idx, mode_only_listed, descending, n,
+                                     out_ids, out_vals, out_count, st);
+  return warpselect_launch<SIGMOID>(scores, ld, num_cards, batch, mask_ptr, mask_idx, mode_only_listed, descending, n,
+                                    out_ids, out_vals, out_count, st);
+}
 
 // ------------------------------------------------------------------ card similarity
 // dist[r] = -cos(emb[r], emb[q]) with Keras' l2_normalize (x * rsqrt(max(sum x^2, 1e-12))), one warp per row
@@ -504,8 +785,8 @@ int topn_launch(const T* scores, int64_t ld, int32_t num_cards, int32_t batch, c
   const size_t mask_bytes = size_t((num_cards + 31) / 32) * 4;
   if constexpr (sizeof(T) == 4) {
     if (n <= WS_MAX_N && !g_topn_force_radix)
-      return warpselect_launch<false>(scores, ld, num_cards, batch, mask_ptr, mask_idx, mode_only_listed, descending, n,
-                                      out_ids, out_vals, out_count, st);
+      return select_small_n<false>(scores, ld, num_cards, batch, mask_ptr, mask_idx, mode_only_listed, descending, n,
+                                   out_ids, out_vals, out_count, st);
   }
   if (n <= TOPN_MAX_SMEM_N) {
     const int n_pad = next_pow2(n < 2 ? 2 : n);
@@ -606,8 +887,8 @@ int cc_topn_masked_sigmoid_f32(const float* logits, int64_t ld, int32_t num_card
   CC_REQUIRE(num_cards > 0 && batch >= 0 && n > 0 && ld >= num_cards, "cc_topn_masked_sigmoid_f32: bad sizes");
   CC_REQUIRE(n <= WS_MAX_N, "cc_topn_masked_sigmoid_f32: n must be <= %d (use cc_sigmoid_f32 + cc_topn_masked_f32)", WS_MAX_N);
   if (batch == 0) return CC_OK;
-  return warpselect_launch<true>(logits, ld, num_cards, batch, mask_ptr, mask_idx, mode_only_listed, descending, n,
-                                 out_ids, out_probs, out_count, as_stream(stream));
+  return select_small_n<true>(logits, ld, num_cards, batch, mask_ptr, mask_idx, mode_only_listed, descending, n,
+                              out_ids, out_probs, out_count, as_stream(stream));
 }
 
 int cc_cosine_neg_f32(const float* emb, int64_t ld, int32_t rows, int32_t dim, int32_t query, float* out, void* stream) {
@@ -619,6 +900,13 @@ int cc_cosine_neg_f32(const float* emb, int64_t ld, int32_t rows, int32_t dim, i
 
 // 1 = keep float32 top-N on the radix-select kernel even for small n (tests compare the two kernels)
 int cc_topn_set_force_radix(int on) { g_topn_force_radix = on ? 1 : 0; return CC_OK; }
+
+// float32 top-N with n <= 128: 0 = automatic, 1 = warp-per-cube streaming select, 2 = CTA-per-cube row select
+int cc_topn_set_algo(int algo) {
+  CC_REQUIRE(algo >= 0 && algo <= 2, "cc_topn_set_algo: algo must be 0, 1 or 2");
+  g_topn_algo = algo;
+  return CC_OK;
+}
 
 int cc_topn_masked_f64(const double* scores, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
                        const int32_t* mask_idx, int mode_only_listed, int descending, int32_t n, void* workspace,

@@ -102,14 +102,18 @@ int64_t cc_topn_workspace_bytes(int32_t num_cards, int32_t batch, int32_t n, int
 int cc_topn_masked_f32(const float* scores, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
                        const int32_t* mask_idx, int mode_only_listed, int descending, int32_t n, void* workspace,
                        int64_t workspace_bytes, int32_t* out_ids, float* out_vals, int32_t* out_count, void* stream);
-/* float32 with n <= 128 runs as a warp-per-cube streaming select (one pass over the row); larger n and float64 use
- * the radix select / full bitonic ranking.  cc_topn_masked_sigmoid_f32 takes LOGITS, ranks sigmoid(logit) (the float32
+/* float32 with n <= 128 runs as a CTA-per-cube row select (the row is staged in shared memory by bulk asynchronous
+ * copies, double-buffered; needs ld % 4 == 0, a 16-byte aligned base and C <= ~26 000) or, for rows that do not
+ * qualify, as a warp-per-cube streaming select (one pass over the row); larger n and float64 use the radix select /
+ * full bitonic ranking.  All of them implement one total order on (score, index).  NaN scores: the row select never
+ * selects them.  cc_topn_set_algo: 0 = automatic (default), 1 = streaming select, 2 = row select (tests compare them).  cc_topn_masked_sigmoid_f32 takes LOGITS, ranks sigmoid(logit) (the float32
  * probabilities the reference ranks, ml_recommend.py:78-104) and returns the winners' probabilities; n <= 128.
  * cc_topn_set_force_radix(1) pins float32 top-N to the radix kernel (tests compare the two). */
 int cc_topn_masked_sigmoid_f32(const float* logits, int64_t ld, int32_t num_cards, int32_t batch,
                                const int64_t* mask_ptr, const int32_t* mask_idx, int mode_only_listed, int descending,
                                int32_t n, int32_t* out_ids, float* out_probs, int32_t* out_count, void* stream);
 int cc_topn_set_force_radix(int on);
+int cc_topn_set_algo(int algo);
 /* Card similarity (src/scripts/similarity.py:25-29): out[r] = -cos(emb[r], emb[query]) with Keras' l2_normalize
  * (epsilon 1e-12), emb float32 [rows][ld >= dim]; rank ascending with cc_topn_masked_f32. */
 int cc_cosine_neg_f32(const float* emb, int64_t ld, int32_t rows, int32_t dim, int32_t query, float* out, void* stream);

@@ -246,6 +246,85 @@ def test_topn_fused_sigmoid_equals_sigmoid_then_select():
             assert torch.equal(x, y), (only_listed, desc)
 
 
+def _algo(a):
+    from cubecobrarecommender_b200 import _lib
+    _lib.call("cc_topn_set_algo", a)
+
+
+@pytest.mark.parametrize("c,ld,batch,n", [(5000, 5000, 6, 50), (4999, 5008, 11, 128), (97, 100, 3, 7),
+                                          (20884, 20992, 9, 50), (2001, 2004, 700, 50), (20884, 20992, 5, 1)])
+def test_topn_row_select_equals_streaming_select(c, ld, batch, n):
+    """The CTA-per-cube row select (rows staged in shared memory by bulk copies, two sweeps) against the warp-per-cube
+    streaming select and numpy's stable argsort: heavy ties, rows sorted both ways, a row whose large values all sit
+    in 40 of the 512 thread strides (more than RS_CAP survivors: the threshold is raised and the sweep repeated),
+    masks that leave fewer than n candidates, duplicate and out-of-range list entries, padded row strides whose
+    padding holds huge values, and more cubes than two per CTA (both row buffers and both barrier phases reused)."""
+    rng = np.random.default_rng(c + n + batch)
+    vals = rng.integers(0, 30, size=(batch, c)).astype(np.float32) / 4 - 3
+    vals[0] = np.sort(rng.standard_normal(c).astype(np.float32))
+    vals[1] = np.sort(rng.standard_normal(c).astype(np.float32))[::-1]
+    vals[2] = rng.standard_normal(c).astype(np.float32)
+    vals[2][(np.arange(c) % 512) < 40] += 100.0
+    if batch > 4:
+        vals[3] = rng.standard_normal(c).astype(np.float32)
+        vals[4] = -vals[2]
+    if batch > 100:
+        vals[5:] = rng.standard_normal((batch - 5, c)).astype(np.float32)
+    lists = [np.sort(rng.choice(c, size=rng.integers(0, min(c, 700)), replace=False)) for _ in range(batch)]
+    lists[-1] = np.arange(3, c)                                               # only 3 candidates left
+    lists[0] = np.concatenate([lists[0], lists[0][:5], [-1, c, c + 7]]).astype(np.int64)   # duplicates, out of range
+    ip = np.zeros(batch + 1, np.int64); ip[1:] = np.cumsum([len(x) for x in lists])
+    ix = np.concatenate(lists).astype(np.int32)
+    mp = torch.from_numpy(ip).cuda(); mi = torch.from_numpy(ix).cuda()
+    full = torch.full((batch, ld), 1e30, dtype=torch.float32, device="cuda")
+    full[:, :c] = torch.from_numpy(vals).cuda()
+    scores = full[:, :c]
+    assert scores.stride(0) == ld
+    try:
+        for only_listed, desc in ((False, True), (True, False), (False, False), (True, True)):
+            _algo(2)
+            a = G.topn_masked(scores, mp, mi, n, only_listed=only_listed, descending=desc)
+            _algo(1)
+            b = G.topn_masked(scores, mp, mi, n, only_listed=only_listed, descending=desc)
+            for x, y in zip(a, b):
+                assert torch.equal(x, y), (only_listed, desc)
+        _algo(2)
+        ids, v, cnt = (t.cpu().numpy() for t in G.topn_masked(scores, mp, mi, n))
+        # fused sigmoid: the same rows as logits
+        logits = full.clone(); logits[:, :c] *= 6.0
+        _algo(2)
+        a = G.topn_masked(logits[:, :c], mp, mi, n, sigmoid=True)
+        _algo(1)
+        b = G.topn_masked(logits[:, :c], mp, mi, n, sigmoid=True)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    finally:
+        _algo(0)
+    for r in range(min(batch, 12)):
+        order = vals[r].argsort(kind="stable")[::-1]
+        inm = np.zeros(c, bool); inm[[i for i in lists[r] if 0 <= i < c]] = True
+        expect = [i for i in order if not inm[i]][:n]
+        assert cnt[r] == len(expect) and np.array_equal(ids[r][:cnt[r]], expect)
+        assert np.array_equal(v[r][:cnt[r]], vals[r][expect])
+        assert (ids[r][cnt[r]:] == -1).all()
+
+
+def test_topn_row_select_is_the_default_for_padded_rows():
+    """Rows that qualify (ld % 4 == 0, aligned) take the row select automatically; algo 2 on rows that do not is an error."""
+    from cubecobrarecommender_b200 import _lib
+    rng = np.random.default_rng(1)
+    scores = torch.from_numpy(rng.standard_normal((4, 999)).astype(np.float32)).cuda()      # ld = 999: not eligible
+    mp = torch.zeros(5, dtype=torch.int64, device="cuda"); mi = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ids, _, _ = G.topn_masked(scores, mp, mi, 10)                       # automatic: streaming select
+    assert np.array_equal(ids.cpu().numpy(), np.argsort(-scores.cpu().numpy(), axis=1, kind="stable")[:, :10])
+    _algo(2)
+    try:
+        with pytest.raises(_lib.CubeCobraError):
+            G.topn_masked(scores, mp, mi, 10)
+    finally:
+        _algo(0)
+
+
 def test_scale_up_card_count_properties():
     """configs[4] card count (C = 100 000; the reference cannot even allocate this dense): one pass of the tensor-core
     count kernel over 8 192 cubes, checked through size-independent properties (the oracle would take hours):
