@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Masked top-50 select alone (BASELINE configs[3]'s HBM-bound half): `batch` logit rows of C = 20 884 (row stride
 20 992, as the decoder GEMM writes them), in-cube cards masked, sigmoid fused.  Times the warp-per-cube streaming select
-(algo 1) and the CTA-per-cube row select (algo 2) with CUDA events, L2 flushed between launches, and checks that the
+(algo 1) and the two launch shapes of the CTA-per-cube row select (algo 2, 3) with CUDA events, L2 flushed between launches, and checks that the
 two return identical ids.  Algorithmic bytes per cube: 4C (scores) + 4s (mask ids) + 8n + 4 (outputs).
 Prints one JSON line per (algo, batch)."""
 import json
@@ -20,7 +20,7 @@ dev = torch.device("cuda", 0)
 peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else {}
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 reps = int(os.environ.get("TOPN_REPS", 10))
-for batch in (2048, 4096):
+for batch in [int(x) for x in os.environ.get("TOPN_BATCHES", "2048,4096").split(",")]:
     g = torch.Generator(device=dev).manual_seed(batch)
     S = 540                                       # in-cube cards per cube (uniform draws; duplicates collapse in the mask)
     mp = torch.arange(batch + 1, dtype=torch.int64, device=dev) * S
@@ -28,7 +28,7 @@ for batch in (2048, 4096):
     logits = torch.randn((batch, LD), device=dev, generator=g) * 3 - 4
     view = logits[:, :C]
     out = {}
-    for algo in (1, 2):
+    for algo in (1, 2, 3):
         _lib.call("cc_topn_set_algo", algo)
         res = G.topn_masked(view, mp, mi, N, sigmoid=True)           # warm-up
         torch.cuda.synchronize()
@@ -44,11 +44,12 @@ for batch in (2048, 4096):
         out[algo] = [t.clone() for t in res]
         ms = float(np.median(times))
         nbytes = batch * (4 * C + 8 * N + 4) + 4 * int(mi.numel())
-        print(json.dumps({"kernel": {1: "topn_warpselect_kernel<sigmoid>", 2: "topn_rowselect_kernel<sigmoid>"}[algo],
+        print(json.dumps({"kernel": {1: "topn_warpselect_kernel<sigmoid>", 2: "topn_rowselect_kernel<sigmoid> 1 CTA/SM, 2 row buffers",
+                                     3: "topn_rowselect_kernel<sigmoid> 2 CTAs/SM, 1 row buffer"}[algo],
                           "batch": batch, "C": C, "ld": LD, "n": N, "ms": ms, "min_ms": float(min(times)),
                           "algorithmic_GB": nbytes / 1e9, "GBps": nbytes / ms / 1e6,
                           "frac_of_hbm_peak": nbytes / ms / 1e6 / float(peaks.get("hbm_gbs", 6546.9)),
                           "cubes_per_s": batch / ms * 1e3}), flush=True)
     _lib.call("cc_topn_set_algo", 0)
-    same = all(torch.equal(a, b) for a, b in zip(out[1], out[2]))
+    same = all(torch.equal(a, b) and torch.equal(a, c) for a, b, c in zip(out[1], out[2], out[3]))
     print(json.dumps({"batch": batch, "identical_ids_vals_counts": same}), flush=True)

@@ -282,22 +282,24 @@ def test_topn_row_select_equals_streaming_select(c, ld, batch, n):
     assert scores.stride(0) == ld
     try:
         for only_listed, desc in ((False, True), (True, False), (False, False), (True, True)):
-            _algo(2)
-            a = G.topn_masked(scores, mp, mi, n, only_listed=only_listed, descending=desc)
             _algo(1)
             b = G.topn_masked(scores, mp, mi, n, only_listed=only_listed, descending=desc)
-            for x, y in zip(a, b):
-                assert torch.equal(x, y), (only_listed, desc)
+            for variant in (2, 3):
+                _algo(variant)
+                a = G.topn_masked(scores, mp, mi, n, only_listed=only_listed, descending=desc)
+                for x, y in zip(a, b):
+                    assert torch.equal(x, y), (only_listed, desc, variant)
         _algo(2)
         ids, v, cnt = (t.cpu().numpy() for t in G.topn_masked(scores, mp, mi, n))
         # fused sigmoid: the same rows as logits
         logits = full.clone(); logits[:, :c] *= 6.0
-        _algo(2)
-        a = G.topn_masked(logits[:, :c], mp, mi, n, sigmoid=True)
         _algo(1)
         b = G.topn_masked(logits[:, :c], mp, mi, n, sigmoid=True)
-        for x, y in zip(a, b):
-            assert torch.equal(x, y)
+        for variant in (2, 3):
+            _algo(variant)
+            a = G.topn_masked(logits[:, :c], mp, mi, n, sigmoid=True)
+            for x, y in zip(a, b):
+                assert torch.equal(x, y), variant
     finally:
         _algo(0)
     for r in range(min(batch, 12)):
