@@ -268,8 +268,12 @@ def test_topn_row_select_equals_streaming_select(c, ld, batch, n):
     if batch > 4:
         vals[3] = rng.standard_normal(c).astype(np.float32)
         vals[4] = -vals[2]
+        vals[3][rng.random(c) < 0.7] = -np.inf                                # most leaders are infinities
+        vals[3][rng.random(c) < 0.05] = -0.0
+        vals[3][rng.random(c) < 0.05] = 0.0
     if batch > 100:
         vals[5:] = rng.standard_normal((batch - 5, c)).astype(np.float32)
+        vals[6][rng.random(c) < 0.7] = np.inf
     lists = [np.sort(rng.choice(c, size=rng.integers(0, min(c, 700)), replace=False)) for _ in range(batch)]
     lists[-1] = np.arange(3, c)                                               # only 3 candidates left
     lists[0] = np.concatenate([lists[0], lists[0][:5], [-1, c, c + 7]]).astype(np.int64)   # duplicates, out of range
