@@ -315,6 +315,35 @@ def measure_extras(dev, peaks, log):
         "cpu_baseline": {"value": nb / t_cpu, "unit": "cubes/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{nb} cubes: torch-CPU forward + argsort walk (model load excluded)"},
     }
+    # ---------------- the masked top-50 select alone (the HBM-bound half of configs[3]) ----------------
+    try:
+        nb_sel = 4096
+        ld = (C2 + 127) // 128 * 128                         # the row stride the decoder GEMM writes
+        gsel = torch.Generator(device=dev).manual_seed(4)
+        logits = torch.randn((nb_sel, ld), device=dev, generator=gsel) * 3 - 4
+        sub = csr2.rows(np.arange(nb_sel))
+        mp, mi = G.upload_csr(sub, dev)
+        res = G.topn_masked(logits[:, :C2], mp, mi, 50, sigmoid=True)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # larger than the 126 MB L2
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); G.topn_masked(logits[:, :C2], mp, mi, 50, sigmoid=True, out=res); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t_sel = float(np.median(ts)) * 1e-3
+        sel_bytes = nb_sel * (4.0 * C2 + 8 * 50 + 4) + 4.0 * int(sub.indptr[-1])   # 4C + 4s + out
+        out["ml_recommend"]["select_roofline"] = {
+            "kernel": "topn_rowselect_kernel<sigmoid> (CTA per cube, row staged in shared memory by bulk copies)",
+            "bound": "hbm", "achieved": sel_bytes / t_sel / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": sel_bytes / t_sel / 1e9 / peaks["hbm_gbs"], "traffic": 357570000,
+            "launch_us": t_sel * 1e6, "cubes": nb_sel,
+            "note": "one launch over 4096 logit rows, L2 flushed between launches, median of 10; traffic = ncu "
+                    "dram read + write of the same launch shape (profiles/r01e_topn_rowselect_v2_ncu_full.csv)"}
+        del logits, flush
+    except Exception as e:  # side measurement: never take the headline down
+        out["ml_recommend"]["select_roofline"] = {"error": repr(e)}
     return out
 
 

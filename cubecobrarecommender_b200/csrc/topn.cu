@@ -529,8 +529,12 @@ __device__ __forceinline__ void rs_rank_partial(const unsigned long long* keys, 
   }
 }
 
-// a bound on the RAW value such that no element whose key is >= thr fails `maybe` (same construction as in the
-// streaming select above: the threshold's own score, or -- fused sigmoid -- its logit taken 1e-6 relative on the safe side)
+// a bound on the RAW value such that no element whose key is >= thr fails `pass`: the threshold's own score, or --
+// fused sigmoid -- its logit.  The logit is evaluated in float32 (one thread computes it while the CTA waits, and a
+// double-precision log costs that thread several hundred cycles): the probability is first moved 2e-6 relative to the
+// safe side (30 float32 ulps: covers the few-ulp error of sigmoid_f32 and keeps 1 - p >= 2e-6, so that the rounding of
+// p costs at most 3% of 1 - p, i.e. 0.03 in the logit) and the result another 0.08.  A looser bound only lets a few
+// more elements into the survivor buffer; it never loses one (checked densely against float32 sigmoid on the host).
 template <bool SIGMOID>
 __device__ __forceinline__ float rs_raw_bound(unsigned long long thr, int descending) {
   if (thr == 0ull) return descending ? -INFINITY : INFINITY;
@@ -538,13 +542,12 @@ __device__ __forceinline__ float rs_raw_bound(unsigned long long thr, int descen
   if (!descending) u = ~u;
   const float pthr = __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
   if (!SIGMOID) return pthr;
-  const double p = double(pthr);
   if (descending) {
-    const double pm = p * (1.0 - 1e-6) - 1e-40;
-    return pm <= 0.0 ? -INFINITY : float(log(pm / (1.0 - pm))) - 1e-3f;
+    const float pm = pthr * (1.f - 2e-6f) - 1e-37f;
+    return pm <= 0.f ? -INFINITY : logf(pm / (1.f - pm)) - 0.08f;
   }
-  const double pp = p * (1.0 + 1e-6) + 1e-40;
-  return pp >= 1.0 ? INFINITY : float(log(pp / (1.0 - pp))) + 1e-3f;
+  const float pp = pthr * (1.f + 2e-6f) + 1e-37f;
+  return pp >= 1.f ? INFINITY : logf(pp / (1.f - pp)) + 0.08f;
 }
 
 // The 128 merged leaders are ranked on 32-bit stand-ins: the score word of the key with its 7 low bits replaced by the
@@ -564,12 +567,23 @@ __device__ __forceinline__ void rs_rank32_partial(const uint32_t* a, int* rk, in
   if (c) atomicAdd(&rk[g], c);
 }
 
-template <bool SIGMOID, bool DESC>
+// PROF: thread 0 accumulates clock64() deltas per phase and writes them to prof[blockIdx.x][RS_PROF_SLOTS] (diagnostic
+// instantiation behind cc_topn_rowselect_profile; the product instantiations compile the stamps out)
+constexpr int RS_PROF_SLOTS = 10;
+template <bool SIGMOID, bool DESC, bool PROF = false>
 __global__ void __launch_bounds__(RS_THREADS, 2)
 topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_cards, int32_t batch,
                       const int64_t* __restrict__ mask_ptr, const int32_t* __restrict__ mask_idx,
                       int mode_only_listed, int32_t n, int nbuf, int32_t* __restrict__ out_ids,
-                      float* __restrict__ out_vals, int32_t* __restrict__ out_count) {
+                      float* __restrict__ out_vals, int32_t* __restrict__ out_count, long long* __restrict__ prof = nullptr) {
+  long long acc[RS_PROF_SLOTS] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tprev = 0;
+  auto stamp = [&](int slot) {
+    if constexpr (PROF) {
+      if (threadIdx.x == 0) { const long long t = clock64(); acc[slot] += t - tprev; tprev = t; }
+    }
+  };
+  if constexpr (PROF) tprev = clock64();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar[2];
   __shared__ unsigned long long s_T;
@@ -644,11 +658,13 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
       if (mb1 + tid + RS_THREADS < me1) nc1 = mask_idx[mb1 + tid + RS_THREADS];
     }
     if (cube + 2 * stride < batch) { mb2 = mask_ptr[cube + 2 * stride]; me2 = mask_ptr[cube + 2 * stride + 1]; }
+    stamp(0);
     auto for_each_listed = [&](auto&& f) {
       f(c0); f(c1);
       for (int64_t p = mb + 2 * RS_THREADS + tid; p < me; p += RS_THREADS) f(mask_idx[p]);
     };
     rs_mbar_wait(&bar[b], parity);
+    stamp(1);                                               // 0: loop top + prefetch (stamped below), 1: wait for the row
 
     if (!mode_only_listed) {
       // masked cards (and the up to three floats of row padding) -> sentinel
@@ -656,6 +672,7 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
       if (tid < cr - num_cards) reinterpret_cast<uint32_t*>(row)[num_cards + tid] = RS_SENTINEL;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // before the next bulk copy overwrites them
       __syncthreads();
+      stamp(2);                                             // 2: sentinels + fence + barrier
       // sweep 1: the best element of this thread's float4 stride.  Per group of four only its extreme is compared
       // (NaN sentinels drop out of fmaxf / fminf); the winner's position inside its group is resolved afterwards, to
       // the index the total order prefers among equal scores (descending: the largest, ascending: the smallest).
@@ -666,6 +683,7 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
         if (DESC) { const float g = fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)); if (g >= best) { best = g; bv = v; } }
         else      { const float g = fminf(fminf(q.x, q.y), fminf(q.z, q.w)); if (g < best) { best = g; bv = v; } }
       }
+      stamp(3);                                             // 3: sweep 1
       unsigned long long k = 0ull;
       if (bv >= 0) {
         const float4 q = row4[bv];
@@ -691,6 +709,7 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
         rk[tid] = 0;
       }
       __syncthreads();
+      stamp(4);                                             // 4: leaders: keys, merge, ranking, threshold
     }
 
     // sweep 2 (repeated with a raised threshold if more than RS_CAP elements survive)
@@ -725,6 +744,7 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
       }
       __syncthreads();
       m = s_cnt;
+      stamp(5);                                             // 5: sweep 2 (+ barrier)
       // raw survivors -> composite keys (each thread its own slots)
       for (int i = tid; i < min(m, RS_CAP); i += RS_THREADS) {
         const unsigned long long raw = keys[i];
@@ -732,6 +752,7 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
         keys[i] = make_key<float>(SIGMOID ? sigmoid_f32(x) : x, (uint32_t)(raw & 0xffffffffu), DESC);
       }
       __syncthreads();
+      stamp(6);                                             // 6: survivors -> keys (+ barrier)
       if (m <= RS_CAP) break;
       // overflow: T <- n-th largest of the RS_CAP survivors kept (n <= 128 < RS_CAP), then sweep again, exactly
       rs_rank_partial(keys, RS_CAP, rk, tid);
@@ -749,6 +770,7 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
     // rank the m survivors among themselves and write the first n at their rank
     rs_rank_partial(keys, m, rk, tid);
     __syncthreads();
+    stamp(7);                                               // 7: issue of the next row + final ranking (+ barrier)
     // every thread has read s_cnt, s_T and s_zb by now; their next use lies behind the next cube's barriers
     if (tid == 0) { s_cnt = 0; s_T = 0ull; s_zb = WORST; }
     for (int i = tid; i < m; i += RS_THREADS) {
@@ -768,6 +790,13 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
     }
     if (tid == 0 && out_count) out_count[cube] = min(n, m);
     mb = mb1; me = me1; c0 = nc0; c1 = nc1; mb1 = mb2; me1 = me2;
+    stamp(8);                                               // 8: write-out
+  }
+  if constexpr (PROF) {
+    if (threadIdx.x == 0 && prof) {
+      acc[9] = it;                                          // cubes this CTA ranked
+      for (int i = 0; i < RS_PROF_SLOTS; ++i) prof[int64_t(blockIdx.x) * RS_PROF_SLOTS + i] = acc[i];
+    }
   }
 }
 
@@ -975,6 +1004,27 @@ int cc_cosine_neg_f32(const float* emb, int64_t ld, int32_t rows, int32_t dim, i
 
 // 1 = keep float32 top-N on the radix-select kernel even for small n (tests compare the two kernels)
 int cc_topn_set_force_radix(int on) { g_topn_force_radix = on ? 1 : 0; return CC_OK; }
+
+// Diagnostic: the fused-sigmoid, descending row select with per-phase clock64() sums of every CTA's thread 0
+// (prof: int64 [grid][10] on the device, grid = cc_topn_rowselect_profile_grid(batch, variant); slots: see RS_PROF_SLOTS).
+int64_t cc_topn_rowselect_profile_grid(int32_t batch, int variant) {
+  const int ctas = variant == 1 ? 2 : 1;
+  return batch < ctas * sm_count() ? batch : ctas * sm_count();
+}
+int cc_topn_rowselect_profile(const float* logits, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
+                              const int32_t* mask_idx, int32_t n, int variant, int32_t* out_ids, float* out_probs,
+                              int32_t* out_count, long long* prof, void* stream) {
+  CC_REQUIRE(logits && mask_ptr && out_ids && prof, "cc_topn_rowselect_profile: null pointer");
+  CC_REQUIRE(batch > 0 && n > 0 && rowselect_eligible(logits, ld, num_cards, n), "cc_topn_rowselect_profile: rows do not qualify");
+  const int nbuf = variant == 1 ? 1 : 2;
+  const size_t smem = rowselect_smem_bytes(num_cards, nbuf);
+  const int grid = (int)cc_topn_rowselect_profile_grid(batch, variant);
+  CC_CHECK_CUDA(cudaFuncSetAttribute(topn_rowselect_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  topn_rowselect_kernel<true, true, true><<<grid, RS_THREADS, smem, as_stream(stream)>>>(
+      logits, ld, num_cards, batch, mask_ptr, mask_idx, 0, n, nbuf, out_ids, out_probs, out_count, prof);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
 
 // float32 top-N with n <= 128: 0 = automatic, 1 = warp-per-cube streaming select, 2 / 3 = CTA-per-cube row select
 // (one CTA per SM with two row buffers / two CTAs per SM with one)

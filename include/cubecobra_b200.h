@@ -114,6 +114,13 @@ int cc_topn_masked_sigmoid_f32(const float* logits, int64_t ld, int32_t num_card
                                int32_t n, int32_t* out_ids, float* out_probs, int32_t* out_count, void* stream);
 int cc_topn_set_force_radix(int on);
 int cc_topn_set_algo(int algo);
+/* Diagnostic build of the row select (fused sigmoid, descending): same results, plus per-phase clock64() sums of each
+ * CTA's thread 0 in prof (int64 [cc_topn_rowselect_profile_grid(batch, variant)][10], device memory).  variant 0 = one
+ * CTA per SM with two row buffers, 1 = two CTAs per SM with one. */
+int64_t cc_topn_rowselect_profile_grid(int32_t batch, int variant);
+int cc_topn_rowselect_profile(const float* logits, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
+                              const int32_t* mask_idx, int32_t n, int variant, int32_t* out_ids, float* out_probs,
+                              int32_t* out_count, long long* prof, void* stream);
 /* Card similarity (src/scripts/similarity.py:25-29): out[r] = -cos(emb[r], emb[query]) with Keras' l2_normalize
  * (epsilon 1e-12), emb float32 [rows][ld >= dim]; rank ascending with cc_topn_masked_f32. */
 int cc_cosine_neg_f32(const float* emb, int64_t ld, int32_t rows, int32_t dim, int32_t query, float* out, void* stream);

@@ -1,0 +1,55 @@
+"""The selection algorithm of the CTA-per-cube row select (csrc/topn.cu, topn_rowselect_kernel), restated on the host in
+tests/rowselect_model.py, against numpy's stable argsort under the documented tie rule (descending: larger index first,
+ascending: smaller index first).  The CUDA kernel itself is compared with the other two select kernels and with numpy in
+tests/test_gpu_graph.py; this test pins the ARGUMENT the kernel relies on: the n-th largest thread leader (taken on
+32-bit stand-ins, low bits cleared) is a valid lower bound of the answer, and raising it after an overflow terminates."""
+import numpy as np
+import pytest
+
+from rowselect_model import NT, expect, rowselect
+
+
+def _row(kind, c, rng):
+    if kind == "normal":
+        return rng.standard_normal(c).astype(np.float32)
+    if kind == "ties":
+        return (rng.integers(0, 30, c) / 4 - 3).astype(np.float32)
+    if kind == "ascending":
+        return np.sort(rng.standard_normal(c).astype(np.float32))
+    if kind == "descending":
+        return np.sort(rng.standard_normal(c).astype(np.float32))[::-1].copy()
+    if kind == "few_strides":                  # the large values sit in 40 of the 512 thread strides
+        row = rng.standard_normal(c).astype(np.float32)
+        row[((np.arange(c) // 4) % NT) < 40] += 100
+        return row
+    row = rng.standard_normal(c).astype(np.float32)          # infinities and signed zeros
+    row[rng.random(c) < 0.7] = -np.inf if c % 2 else np.inf
+    row[rng.random(c) < 0.05] = -0.0
+    row[rng.random(c) < 0.05] = 0.0
+    return row
+
+
+@pytest.mark.parametrize("kind", ["normal", "ties", "ascending", "descending", "few_strides", "infinities"])
+@pytest.mark.parametrize("c,n", [(97, 7), (700, 50), (5001, 128), (5000, 1)])
+def test_rowselect_model_equals_stable_argsort(kind, c, n):
+    rng = np.random.default_rng(c * 131 + n)
+    row = _row(kind, c, rng)
+    listed = [int(i) for i in rng.choice(c, size=int(rng.integers(0, min(c, 700))), replace=False)]
+    listed += listed[:3] + [-1, c, c + 5]                     # duplicates and out-of-range entries are ignored
+    for only_listed, desc in ((False, True), (True, False), (False, False), (True, True)):
+        for cap in (1024, 160):                               # 160: forces the overflow / re-sweep path
+            got, cnt, rounds, m = rowselect(row, listed, only_listed, desc, n, cap)
+            exp = expect(row, listed, only_listed, desc, n)
+            assert got == exp and cnt == len(exp), (kind, c, n, only_listed, desc, cap)
+
+
+def test_rowselect_model_few_candidates_and_survivor_count():
+    rng = np.random.default_rng(5)
+    c, n = 20884, 50
+    row = (rng.standard_normal(c) * 3 - 4).astype(np.float32)
+    listed = [int(i) for i in rng.choice(c, size=540, replace=False)]
+    got, cnt, rounds, m = rowselect(row, listed, False, True, n)
+    assert got == expect(row, listed, False, True, n) and rounds == 0
+    assert n <= m <= 2 * n                    # ~1.3 n elements lie above the leaders' threshold
+    got, cnt, _, _ = rowselect(row, list(range(3, c)), False, True, n)          # only three candidates are left
+    assert cnt == 3 and got == expect(row, list(range(3, c)), False, True, n)
