@@ -884,7 +884,6 @@ int topn_launch(const T* scores, int64_t ld, int32_t num_cards, int32_t batch, c
   using K = typename KeyOf<T>::K;
   CC_REQUIRE(scores && mask_ptr && out_ids, "cc_topn_masked: null pointer");
   CC_REQUIRE(num_cards > 0 && batch >= 0 && n > 0 && ld >= num_cards, "cc_topn_masked: bad sizes");
-  CC_REQUIRE(mask_idx || true, "unused");
   if (batch == 0) return CC_OK;
   const size_t mask_bytes = size_t((num_cards + 31) / 32) * 4;
   if constexpr (sizeof(T) == 4) {
