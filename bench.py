@@ -125,9 +125,17 @@ REF_BATCH = 1024      # cubes per CPU step: a bounded sample of the 4096-cube ba
                       # batch -- 126 / 182 / 320 cubes/s at 64 / 256 / 1024 on 8 cores -- so this favours the reference)
 
 
-def cpu_reference(num_cards, steps, warmup, batch=REF_BATCH, num_cubes=REF_BATCH, mhat64=None, log=None):
+REF_BUDGET_S = 150.0  # the whole --steps K --warmup W run of the CPU arm should end within a few minutes
+
+
+def cpu_reference(num_cards, steps, warmup, batch=REF_BATCH, num_cubes=REF_BATCH, mhat64=None, log=None,
+                  budget_s=None):
     """Oracle port of the reference CPU train path: DataGenerator (restated from
-    src/ml/generator.py) + torch-CPU restatement of the Keras step.  Returns cubes/s."""
+    src/ml/generator.py) + torch-CPU restatement of the Keras step.  Returns cubes/s.
+
+    ``budget_s``: if the (warmup + steps) steps at ``batch`` cubes would take longer than this, the per-step sample is
+    halved (down to the reference's default batch_size of 64) until they fit; the estimate comes from one calibration
+    step at 64 cubes (after a cold one) and the measured scaling of the CPU path with the batch (cubes/s ~ batch^(1/3))."""
     import torch
     from cubecobrarecommender_b200.workload import TRAIN_STEP, make_cubes
     from oracle import dae as od, graph as og, noise as on
@@ -140,8 +148,20 @@ def cpu_reference(num_cards, steps, warmup, batch=REF_BATCH, num_cubes=REF_BATCH
         mhat64 = og.m_hat(og.adjacency_from_counts(cnt))
         del cnt, x32
     np.random.seed(0)
-    gen = on.DataGenerator(mhat64, dense, batch_size=batch, noise=TRAIN_STEP["noise"])
     model = od.TorchDAE(od.init_params(num_cards, seed=0))
+    if budget_s is not None and batch > 64:
+        cal = on.DataGenerator(mhat64, dense, batch_size=64, noise=TRAIN_STEP["noise"])
+        for _ in range(2):                                 # the second step is the estimate (the first one is cold)
+            tc = time.perf_counter()
+            (x, xr), (y, yr) = cal[0]
+            model.train_step(torch.from_numpy(x.astype(np.float32)), torch.from_numpy(y.astype(np.float32)),
+                             torch.from_numpy(np.argmax(xr, 1)), torch.from_numpy(yr.astype(np.float32)), TRAIN_STEP["reg"])
+            cps64 = 64 / (time.perf_counter() - tc)
+        while batch > 64 and (warmup + steps) * batch / (cps64 * (batch / 64.0) ** (1.0 / 3.0)) > budget_s:
+            batch //= 2
+        if log:
+            log(f"cpu reference: {cps64:.0f} cubes/s at 64 cubes per step -> {batch} cubes per step for {warmup}+{steps} steps")
+    gen = on.DataGenerator(mhat64, dense, batch_size=batch, noise=TRAIN_STEP["noise"])
     if log:
         log(f"cpu reference setup {time.time() - t0:.1f}s, threads={torch.get_num_threads()}")
     t_gen = t_model = 0.0
@@ -164,7 +184,8 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from cubecobrarecommender_b200.workload import TRAIN_STEP
-    r = cpu_reference(TRAIN_STEP["num_cards"], args.steps, args.warmup, log=lambda m: print(m, file=sys.stderr))
+    r = cpu_reference(TRAIN_STEP["num_cards"], args.steps, args.warmup, log=lambda m: print(m, file=sys.stderr),
+                      budget_s=REF_BUDGET_S)
     sample = (f"{args.steps} steps x {r['batch']} cubes (a bounded sample of the {TRAIN_STEP['batch']}-cube batch), "
               f"C={TRAIN_STEP['num_cards']}; generator {r['gen_seconds']:.2f}s + model {r['model_seconds']:.2f}s")
     line = {
