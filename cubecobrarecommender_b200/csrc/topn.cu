@@ -569,8 +569,19 @@ __device__ __forceinline__ void rs_rank32_partial(const uint32_t* a, int* rk, in
 
 // PROF: thread 0 accumulates clock64() deltas per phase and writes them to prof[blockIdx.x][RS_PROF_SLOTS] (diagnostic
 // instantiation behind cc_topn_rowselect_profile; the product instantiations compile the stamps out)
+//
+// NEXT: the round-2 candidate (cc_topn_set_algo(4); not the default, NOT yet run on a GPU).  It answers the phase
+// profile of the shipped kernel: (a) the (begin, end) pair of the mask list two cubes ahead is loaded by
+// ONE thread and handed over through shared memory behind a barrier -- the compiler turned the per-thread prefetch into
+// an immediate R2UR wait on the load; (b) the survivor append is a plain atom.shared instead of the compiler's
+// warp-aggregated sequence (S2R, votes, shuffle) that every diverged push paid; (c) a leader / a survivor is ranked by
+// four NEIGHBOURING lanes that add their counts with two shuffles, so the rank array, its atomics and two of the
+// seven barriers per cube go away, and the ranks are written out where they are computed; (d) the next row is
+// issued by a thread of a warp that has no ranking work.
 constexpr int RS_PROF_SLOTS = 10;
-template <bool SIGMOID, bool DESC, bool PROF = false>
+constexpr int RS_PTR_THREAD = 64;                  // loads the mask_ptr pair two cubes ahead (NEXT)
+constexpr int RS_ISSUE_THREAD_NEXT = 480;          // issues the bulk copies (NEXT): warp 15 ranks survivors 120..127 only
+template <bool SIGMOID, bool DESC, bool PROF = false, bool NEXT = false>
 __global__ void __launch_bounds__(RS_THREADS, 2)
 topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_cards, int32_t batch,
                       const int64_t* __restrict__ mask_ptr, const int32_t* __restrict__ mask_idx,
@@ -589,7 +600,9 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
   __shared__ unsigned long long s_T;
   __shared__ float s_zb;
   __shared__ int s_cnt;
+  __shared__ long long s_mp[2];                             // NEXT: (begin, end) of the mask list two cubes ahead
   const int tid = threadIdx.x, lane = tid & 31;
+  const int issue_tid = NEXT ? RS_ISSUE_THREAD_NEXT : 0;
   const int cr = (num_cards + 3) & ~3;                      // row length in shared memory (<= ld: ld % 4 == 0)
   const int cr4 = cr >> 2;
   const uint32_t row_bytes = uint32_t(cr) * 4u;
@@ -620,7 +633,7 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
   }
   for (int i = tid; i < RS_CAP; i += RS_THREADS) rk[i] = 0;
   __syncthreads();
-  if (tid == 0) {
+  if (tid == issue_tid) {
     for (int b = 0; b < nbuf; ++b)
       if (cube0 + b * stride < batch) issue(cube0 + b * stride, b);
   }
@@ -641,7 +654,12 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
   // of {key >= T}: the final ranking is exact anyway); exact = 1 (after an overflow) tests the key itself.
   auto push = [&](float x, int e, unsigned long long T, bool exact) {
     if (exact && make_key<float>(SIGMOID ? sigmoid_f32(x) : x, (uint32_t)e, DESC) < T) return;
-    const int slot = atomicAdd(&s_cnt, 1);
+    int slot;
+    if constexpr (NEXT) {
+      asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(slot) : "r"(rs_smem_u32(&s_cnt)), "r"(1) : "memory");
+    } else {
+      slot = atomicAdd(&s_cnt, 1);
+    }
     if (slot < RS_CAP) keys[slot] = ((unsigned long long)__float_as_uint(x) << 32) | (unsigned long long)(uint32_t)e;
   };
 
@@ -657,7 +675,11 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
       if (mb1 + tid < me1) nc0 = mask_idx[mb1 + tid];
       if (mb1 + tid + RS_THREADS < me1) nc1 = mask_idx[mb1 + tid + RS_THREADS];
     }
-    if (cube + 2 * stride < batch) { mb2 = mask_ptr[cube + 2 * stride]; me2 = mask_ptr[cube + 2 * stride + 1]; }
+    if constexpr (NEXT) {
+      if (tid == RS_PTR_THREAD && cube + 2 * stride < batch) { mb2 = mask_ptr[cube + 2 * stride]; me2 = mask_ptr[cube + 2 * stride + 1]; }
+    } else {
+      if (cube + 2 * stride < batch) { mb2 = mask_ptr[cube + 2 * stride]; me2 = mask_ptr[cube + 2 * stride + 1]; }
+    }
     stamp(0);
     auto for_each_listed = [&](auto&& f) {
       f(c0); f(c1);
@@ -697,16 +719,32 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
       }
       if ((lane & 3) == 0) lead32[tid >> 2] = ((uint32_t)(k >> 32) & ~0x7fu) | (uint32_t)(tid >> 2);
       __syncthreads();
-      rs_rank32_partial(lead32, rk, tid);
-      __syncthreads();
-      if (tid < RS_LEADERS) {
-        if (rk[tid] == n - 1) {
-          // score words at or below the code of the worst infinity (its low bits cleared would decode to a NaN): no bound
-          const uint32_t uw = lead32[tid] & ~0x7fu;
-          const unsigned long long t = uw > 0x007fffffu ? (unsigned long long)uw << 32 : 0ull;
-          s_T = t; s_zb = rs_raw_bound<SIGMOID>(t, DESC);
+      // score words at or below the code of the worst infinity (its low bits cleared would decode to a NaN): no bound
+      auto publish = [&](uint32_t stand_in) {
+        const uint32_t uw = stand_in & ~0x7fu;
+        const unsigned long long t = uw > 0x007fffffu ? (unsigned long long)uw << 32 : 0ull;
+        s_T = t; s_zb = rs_raw_bound<SIGMOID>(t, DESC);
+      };
+      if constexpr (NEXT) {
+        // leader tid / 4, a quarter of the 128 stand-ins per lane, counts added over the four neighbouring lanes
+        const uint32_t mine = lead32[tid >> 2];
+        const uint4* a4 = reinterpret_cast<const uint4*>(lead32) + (tid & 3) * (RS_LEADERS / 16);
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < RS_LEADERS / 16; ++j) {
+          const uint4 w = a4[j];
+          c += (w.x > mine) + (w.y > mine) + (w.z > mine) + (w.w > mine);
         }
-        rk[tid] = 0;
+        c += __shfl_xor_sync(0xffffffffu, c, 1);
+        c += __shfl_xor_sync(0xffffffffu, c, 2);
+        if ((lane & 3) == 0 && c == n - 1) publish(mine);
+      } else {
+        rs_rank32_partial(lead32, rk, tid);
+        __syncthreads();
+        if (tid < RS_LEADERS) {
+          if (rk[tid] == n - 1) publish(lead32[tid]);
+          rk[tid] = 0;
+        }
       }
       __syncthreads();
       stamp(4);                                             // 4: leaders: keys, merge, ranking, threshold
@@ -744,6 +782,9 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
       }
       __syncthreads();
       m = s_cnt;
+      if constexpr (NEXT) {
+        if (tid == RS_PTR_THREAD) { s_mp[0] = mb2; s_mp[1] = me2; }      // read by everyone behind the next barrier
+      }
       stamp(5);                                             // 5: sweep 2 (+ barrier)
       // raw survivors -> composite keys (each thread its own slots)
       for (int i = tid; i < min(m, RS_CAP); i += RS_THREADS) {
@@ -765,23 +806,44 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
       __syncthreads();
     }
     // the row is not needed any more: its buffer takes the row of the cube nbuf turns ahead while this one is ranked
-    if (tid == 0 && cube + nbuf * stride < batch) issue(cube + nbuf * stride, b);
+    if (tid == issue_tid && cube + nbuf * stride < batch) issue(cube + nbuf * stride, b);
 
     // rank the m survivors among themselves and write the first n at their rank
-    rs_rank_partial(keys, m, rk, tid);
-    __syncthreads();
-    stamp(7);                                               // 7: issue of the next row + final ranking (+ barrier)
-    // every thread has read s_cnt, s_T and s_zb by now; their next use lies behind the next cube's barriers
-    if (tid == 0) { s_cnt = 0; s_T = 0ull; s_zb = WORST; }
-    for (int i = tid; i < m; i += RS_THREADS) {
-      const int r = rk[i];
-      rk[i] = 0;
-      if (r < n) {
-        const unsigned long long key = keys[i];
-        uint32_t t = (uint32_t)(key & 0xffffffffu), u = (uint32_t)(key >> 32);
-        if (!DESC) { t = ~t; u = ~u; }
-        out_ids[int64_t(cube) * n + r] = (int32_t)t;
-        if (out_vals) out_vals[int64_t(cube) * n + r] = __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
+    auto write_ranked = [&](unsigned long long key, int r) {
+      uint32_t t = (uint32_t)(key & 0xffffffffu), u = (uint32_t)(key >> 32);
+      if (!DESC) { t = ~t; u = ~u; }
+      out_ids[int64_t(cube) * n + r] = (int32_t)t;
+      if (out_vals) out_vals[int64_t(cube) * n + r] = __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
+    };
+    if constexpr (NEXT) {
+      // every thread has read s_cnt, s_T and s_zb (before the barrier above); their next use lies behind the next cube's barriers
+      if (tid == 0) { s_cnt = 0; s_T = 0ull; s_zb = WORST; }
+      { const long long a = s_mp[0], e = s_mp[1]; mb2 = a; me2 = e; }
+      const int chunk = (m + 3) >> 2;
+      const int j0 = (tid & 3) * chunk, j1 = min(m, j0 + chunk);
+      for (int i0 = 0; i0 < m; i0 += RS_LEADERS) {            // survivor i0 + tid / 4, a quarter of the buffer per lane
+        const int i = i0 + (tid >> 2);
+        unsigned long long mine = 0ull;
+        int c = 0;
+        if (i < m) {
+          mine = keys[i];
+          for (int j = j0; j < j1; ++j) c += (keys[j] > mine) ? 1 : 0;
+        }
+        c += __shfl_xor_sync(0xffffffffu, c, 1);
+        c += __shfl_xor_sync(0xffffffffu, c, 2);
+        if ((lane & 3) == 0 && i < m && c < n) write_ranked(mine, c);
+      }
+      stamp(7);                                             // 7: issue of the next row + final ranking and write-out
+    } else {
+      rs_rank_partial(keys, m, rk, tid);
+      __syncthreads();
+      stamp(7);                                             // 7: issue of the next row + final ranking (+ barrier)
+      // every thread has read s_cnt, s_T and s_zb by now; their next use lies behind the next cube's barriers
+      if (tid == 0) { s_cnt = 0; s_T = 0ull; s_zb = WORST; }
+      for (int i = tid; i < m; i += RS_THREADS) {
+        const int r = rk[i];
+        rk[i] = 0;
+        if (r < n) write_ranked(keys[i], r);
       }
     }
     for (int i = m + tid; i < n; i += RS_THREADS) {
@@ -811,17 +873,24 @@ static bool rowselect_eligible(const float* scores, int64_t ld, int32_t num_card
          rowselect_smem_bytes(num_cards, 2) + 1024 <= 227 * 1024;
 }
 
-// variant 0: one CTA per SM, two row buffers; variant 1: two CTAs per SM, one row buffer each
+// variant 0: one CTA per SM, two row buffers; variant 1: two CTAs per SM, one row buffer each; variant 2: the NEXT
+// candidate of the kernel in the launch shape of variant 1
 template <bool SIGMOID, bool DESC>
 static int rowselect_launch_t(int variant, const float* scores, int64_t ld, int32_t num_cards, int32_t batch,
                               const int64_t* mask_ptr, const int32_t* mask_idx, int mode_only_listed, int32_t n,
                               int32_t* out_ids, float* out_vals, int32_t* out_count, cudaStream_t st) {
-  const int nbuf = variant == 1 ? 1 : 2, ctas = variant == 1 ? 2 : 1;
+  const int nbuf = variant == 0 ? 2 : 1, ctas = variant == 0 ? 1 : 2;
   const size_t smem = rowselect_smem_bytes(num_cards, nbuf);
   const int grid = batch < ctas * sm_count() ? batch : ctas * sm_count();
-  CC_CHECK_CUDA(cudaFuncSetAttribute(topn_rowselect_kernel<SIGMOID, DESC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  topn_rowselect_kernel<SIGMOID, DESC><<<grid, RS_THREADS, smem, st>>>(
-      scores, ld, num_cards, batch, mask_ptr, mask_idx, mode_only_listed, n, nbuf, out_ids, out_vals, out_count);
+  if (variant == 2) {
+    CC_CHECK_CUDA(cudaFuncSetAttribute(topn_rowselect_kernel<SIGMOID, DESC, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topn_rowselect_kernel<SIGMOID, DESC, false, true><<<grid, RS_THREADS, smem, st>>>(
+        scores, ld, num_cards, batch, mask_ptr, mask_idx, mode_only_listed, n, nbuf, out_ids, out_vals, out_count);
+  } else {
+    CC_CHECK_CUDA(cudaFuncSetAttribute(topn_rowselect_kernel<SIGMOID, DESC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topn_rowselect_kernel<SIGMOID, DESC><<<grid, RS_THREADS, smem, st>>>(
+        scores, ld, num_cards, batch, mask_ptr, mask_idx, mode_only_listed, n, nbuf, out_ids, out_vals, out_count);
+  }
   CC_CHECK_LAUNCH();
   return CC_OK;
 }
@@ -838,7 +907,7 @@ static int rowselect_launch(int variant, const float* scores, int64_t ld, int32_
 
 // float32, n <= 128: 0 = automatic (row select when the rows qualify, else the streaming select), 1 = streaming select,
 // 2 / 3 = row select, variant 0 / 1 (error if the rows do not qualify); automatic takes variant 1, the faster one
-// on a B200.  The radix-select kernel stays the general path (any n, float64).
+// on a B200; 4 = the NEXT candidate of the row select (opt-in until it has been run and measured on a GPU).  The radix-select kernel stays the general path (any n, float64).
 static int g_topn_algo = 0;
 static int g_topn_force_radix = 0;
 
@@ -849,7 +918,7 @@ static int select_small_n(const float* scores, int64_t ld, int32_t num_cards, in
   const bool ok = rowselect_eligible(scores, ld, num_cards, n);
   CC_REQUIRE(ok || g_topn_algo < 2, "cc_topn_masked: the row select needs ld %% 4 == 0, 16-byte aligned rows and C <= ~26 000");
   if (ok && g_topn_algo != 1)
-    return rowselect_launch<SIGMOID>(g_topn_algo == 2 ? 0 : 1, scores, ld, num_cards, batch, mask_ptr, mask_idx,
+    return rowselect_launch<SIGMOID>(g_topn_algo == 2 ? 0 : g_topn_algo == 4 ? 2 : 1, scores, ld, num_cards, batch, mask_ptr, mask_idx,
                                      mode_only_listed, descending, n, out_ids, out_vals, out_count, st);
   return warpselect_launch<SIGMOID>(scores, ld, num_cards, batch, mask_ptr, mask_idx, mode_only_listed, descending, n,
                                     out_ids, out_vals, out_count, st);
@@ -1007,7 +1076,7 @@ int cc_topn_set_force_radix(int on) { g_topn_force_radix = on ? 1 : 0; return CC
 // Diagnostic: the fused-sigmoid, descending row select with per-phase clock64() sums of every CTA's thread 0
 // (prof: int64 [grid][10] on the device, grid = cc_topn_rowselect_profile_grid(batch, variant); slots: see RS_PROF_SLOTS).
 int64_t cc_topn_rowselect_profile_grid(int32_t batch, int variant) {
-  const int ctas = variant == 1 ? 2 : 1;
+  const int ctas = variant == 0 ? 1 : 2;
   return batch < ctas * sm_count() ? batch : ctas * sm_count();
 }
 int cc_topn_rowselect_profile(const float* logits, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
@@ -1015,12 +1084,18 @@ int cc_topn_rowselect_profile(const float* logits, int64_t ld, int32_t num_cards
                               int32_t* out_count, long long* prof, void* stream) {
   CC_REQUIRE(logits && mask_ptr && out_ids && prof, "cc_topn_rowselect_profile: null pointer");
   CC_REQUIRE(batch > 0 && n > 0 && rowselect_eligible(logits, ld, num_cards, n), "cc_topn_rowselect_profile: rows do not qualify");
-  const int nbuf = variant == 1 ? 1 : 2;
+  const int nbuf = variant == 0 ? 2 : 1;
   const size_t smem = rowselect_smem_bytes(num_cards, nbuf);
   const int grid = (int)cc_topn_rowselect_profile_grid(batch, variant);
-  CC_CHECK_CUDA(cudaFuncSetAttribute(topn_rowselect_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  topn_rowselect_kernel<true, true, true><<<grid, RS_THREADS, smem, as_stream(stream)>>>(
-      logits, ld, num_cards, batch, mask_ptr, mask_idx, 0, n, nbuf, out_ids, out_probs, out_count, prof);
+  if (variant == 2) {
+    CC_CHECK_CUDA(cudaFuncSetAttribute(topn_rowselect_kernel<true, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topn_rowselect_kernel<true, true, true, true><<<grid, RS_THREADS, smem, as_stream(stream)>>>(
+        logits, ld, num_cards, batch, mask_ptr, mask_idx, 0, n, nbuf, out_ids, out_probs, out_count, prof);
+  } else {
+    CC_CHECK_CUDA(cudaFuncSetAttribute(topn_rowselect_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topn_rowselect_kernel<true, true, true><<<grid, RS_THREADS, smem, as_stream(stream)>>>(
+        logits, ld, num_cards, batch, mask_ptr, mask_idx, 0, n, nbuf, out_ids, out_probs, out_count, prof);
+  }
   CC_CHECK_LAUNCH();
   return CC_OK;
 }
@@ -1028,7 +1103,7 @@ int cc_topn_rowselect_profile(const float* logits, int64_t ld, int32_t num_cards
 // float32 top-N with n <= 128: 0 = automatic, 1 = warp-per-cube streaming select, 2 / 3 = CTA-per-cube row select
 // (one CTA per SM with two row buffers / two CTAs per SM with one)
 int cc_topn_set_algo(int algo) {
-  CC_REQUIRE(algo >= 0 && algo <= 3, "cc_topn_set_algo: algo must be 0..3");
+  CC_REQUIRE(algo >= 0 && algo <= 4, "cc_topn_set_algo: algo must be 0..4");
   g_topn_algo = algo;
   return CC_OK;
 }

@@ -106,7 +106,9 @@ int cc_topn_masked_f32(const float* scores, int64_t ld, int32_t num_cards, int32
  * copies, double-buffered; needs ld % 4 == 0, a 16-byte aligned base and C <= ~26 000) or, for rows that do not
  * qualify, as a warp-per-cube streaming select (one pass over the row); larger n and float64 use the radix select /
  * full bitonic ranking.  All of them implement one total order on (score, index).  NaN scores: the row select never
- * selects them.  cc_topn_set_algo: 0 = automatic (default), 1 = streaming select, 2 = row select (tests compare them).  cc_topn_masked_sigmoid_f32 takes LOGITS, ranks sigmoid(logit) (the float32
+ * selects them.  cc_topn_set_algo: 0 = automatic (default: the row select with two CTAs per SM when the rows qualify),
+ * 1 = streaming select, 2 = row select with one CTA per SM and two row buffers, 3 = row select with two CTAs per SM and
+ * one row buffer each (tests compare them), 4 = the next revision of the row select (opt-in: compiled, not yet run on a GPU).  cc_topn_masked_sigmoid_f32 takes LOGITS, ranks sigmoid(logit) (the float32
  * probabilities the reference ranks, ml_recommend.py:78-104) and returns the winners' probabilities; n <= 128.
  * cc_topn_set_force_radix(1) pins float32 top-N to the radix kernel (tests compare the two). */
 int cc_topn_masked_sigmoid_f32(const float* logits, int64_t ld, int32_t num_cards, int32_t batch,
@@ -116,7 +118,7 @@ int cc_topn_set_force_radix(int on);
 int cc_topn_set_algo(int algo);
 /* Diagnostic build of the row select (fused sigmoid, descending): same results, plus per-phase clock64() sums of each
  * CTA's thread 0 in prof (int64 [cc_topn_rowselect_profile_grid(batch, variant)][10], device memory).  variant 0 = one
- * CTA per SM with two row buffers, 1 = two CTAs per SM with one. */
+ * CTA per SM with two row buffers, 1 = two CTAs per SM with one, 2 = the next revision (algo 4) in the shape of 1. */
 int64_t cc_topn_rowselect_profile_grid(int32_t batch, int variant);
 int cc_topn_rowselect_profile(const float* logits, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
                               const int32_t* mask_idx, int32_t n, int variant, int32_t* out_ids, float* out_probs,

@@ -28,7 +28,7 @@ for batch in [int(x) for x in os.environ.get("TOPN_BATCHES", "2048,4096").split(
     logits = torch.randn((batch, LD), device=dev, generator=g) * 3 - 4
     view = logits[:, :C]
     out = {}
-    for algo in (1, 2, 3):
+    for algo in ((1, 2, 3, 4) if os.environ.get("CC_TOPN_EXPERIMENTAL") == "1" else (1, 2, 3)):
         _lib.call("cc_topn_set_algo", algo)
         res = G.topn_masked(view, mp, mi, N, sigmoid=True)           # warm-up
         torch.cuda.synchronize()
@@ -45,11 +45,12 @@ for batch in [int(x) for x in os.environ.get("TOPN_BATCHES", "2048,4096").split(
         ms = float(np.median(times))
         nbytes = batch * (4 * C + 8 * N + 4) + 4 * int(mi.numel())
         print(json.dumps({"kernel": {1: "topn_warpselect_kernel<sigmoid>", 2: "topn_rowselect_kernel<sigmoid> 1 CTA/SM, 2 row buffers",
-                                     3: "topn_rowselect_kernel<sigmoid> 2 CTAs/SM, 1 row buffer"}[algo],
+                                     3: "topn_rowselect_kernel<sigmoid> 2 CTAs/SM, 1 row buffer",
+                                     4: "topn_rowselect_kernel<sigmoid, NEXT> 2 CTAs/SM, 1 row buffer"}[algo],
                           "batch": batch, "C": C, "ld": LD, "n": N, "ms": ms, "min_ms": float(min(times)),
                           "algorithmic_GB": nbytes / 1e9, "GBps": nbytes / ms / 1e6,
                           "frac_of_hbm_peak": nbytes / ms / 1e6 / float(peaks.get("hbm_gbs", 6546.9)),
                           "cubes_per_s": batch / ms * 1e3}), flush=True)
     _lib.call("cc_topn_set_algo", 0)
-    same = all(torch.equal(a, b) and torch.equal(a, c) for a, b, c in zip(out[1], out[2], out[3]))
+    same = all(all(torch.equal(x, y) for x, y in zip(out[1], out[k])) for k in out if k != 1)
     print(json.dumps({"batch": batch, "identical_ids_vals_counts": same}), flush=True)
