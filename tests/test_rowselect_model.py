@@ -53,3 +53,42 @@ def test_rowselect_model_few_candidates_and_survivor_count():
     assert n <= m <= 2 * n                    # ~1.3 n elements lie above the leaders' threshold
     got, cnt, _, _ = rowselect(row, list(range(3, c)), False, True, n)          # only three candidates are left
     assert cnt == 3 and got == expect(row, list(range(3, c)), False, True, n)
+
+
+def _sigmoid_f32(z):
+    f = np.float32
+    with np.errstate(over="ignore"):
+        return (f(1) / (f(1) + np.exp(-z.astype(f)).astype(f))).astype(f)
+
+
+def _raw_bound_sigmoid(p, descending):
+    """rs_raw_bound<SIGMOID=true> of csrc/topn.cu in float32 arithmetic: the logit of the threshold probability,
+    moved 2e-6 relative in probability and 0.08 in the logit to the safe side."""
+    f = np.float32
+    p = p.astype(f)
+    with np.errstate(all="ignore"):
+        if descending:
+            pm = (p * f(1 - 2e-6)).astype(f) - f(1e-37)
+            zb = np.log((pm / (f(1) - pm)).astype(f)).astype(f) - f(0.08)
+            return np.where(pm <= 0, -np.inf, zb).astype(f)
+        pp = (p * f(1 + 2e-6)).astype(f) + f(1e-37)
+        zb = np.log((pp / (f(1) - pp)).astype(f)).astype(f) + f(0.08)
+        return np.where(pp >= 1, np.inf, zb).astype(f)
+
+
+def test_fused_sigmoid_logit_bound_never_rejects_a_qualifying_element():
+    """The pre-filter of the fused-sigmoid select compares raw logits with a float32 bound derived from the threshold
+    probability.  It must be safe: every logit whose float32 sigmoid is at least (descending) / at most (ascending) the
+    threshold probability passes the bound -- including the plateaus where the sigmoid saturates to exactly 1.0 / 0.0."""
+    rng = np.random.default_rng(0)
+    z = np.concatenate([rng.uniform(-110, 20, 1_500_000), rng.uniform(10, 18, 500_000), rng.uniform(-20, -5, 500_000),
+                        np.array([-np.inf, -104.0, -88.0, 0.0, 16.0, 16.7, 17.0, 30.0, np.inf])]).astype(np.float32)
+    order = np.argsort(z, kind="stable")
+    zs, ps = z[order], _sigmoid_f32(z[order])
+    # descending: the smallest logit whose probability is >= ps[i] must satisfy z >= bound(ps[i])
+    first = np.searchsorted(np.maximum.accumulate(ps), ps, side="left")
+    assert not (zs[first] < _raw_bound_sigmoid(ps, True)).any()
+    # ascending: the largest logit whose probability is <= ps[i] must satisfy z <= bound(ps[i])
+    last = np.searchsorted(np.minimum.accumulate(ps[::-1])[::-1], ps, side="right") - 1
+    assert not (zs[last] > _raw_bound_sigmoid(ps, False)).any()
+    assert (ps == 1.0).any() and (ps == 0.0).any()          # both saturation plateaus were exercised
