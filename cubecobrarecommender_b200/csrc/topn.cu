@@ -573,8 +573,10 @@ __device__ __forceinline__ void rs_rank32_partial(const uint32_t* a, int* rk, in
 // NEXT: the round-2 candidate (cc_topn_set_algo(4); not the default, NOT yet run on a GPU).  It answers the phase
 // profile of the shipped kernel: (a) the (begin, end) pair of the mask list two cubes ahead is loaded by
 // ONE thread and handed over through shared memory behind a barrier -- the compiler turned the per-thread prefetch into
-// an immediate R2UR wait on the load; (b) the survivor append is a plain atom.shared instead of the compiler's
-// warp-aggregated sequence (S2R, votes, shuffle) that every diverged push paid; (c) a leader / a survivor is ranked by
+// an immediate R2UR wait on the load; (b) a thread parks its first two survivors of a sweep in registers and the warp
+// appends them afterwards with one prefix sum and ONE shared-memory atomic, instead of a diverged vote -> ATOMS -> SHFL
+// chain per survivor (the slowest warp's chains are what the other fifteen wait for at the barrier: sweep 2 took four
+// times as long as sweep 1 over the same data); (c) a leader / a survivor is ranked by
 // four NEIGHBOURING lanes that add their counts with two shuffles, so the rank array, its atomics and two of the
 // seven barriers per cube go away, and the ranks are written out where they are computed; (d) the next row is
 // issued by a thread of a warp that has no ranking work.
@@ -652,15 +654,35 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
   // survivors are stored raw (score bits, index); their keys are made afterwards, one survivor per thread, instead of
   // one sigmoid at a time in a diverged warp.  exact = 0 keeps every element that passes the raw-value bound (a superset
   // of {key >= T}: the final ranking is exact anyway); exact = 1 (after an overflow) tests the key itself.
+  // NEXT: a thread parks its first two survivors of a sweep in registers (a diverged push that waits for the round trip
+  // of a shared-memory atomic is what made sweep 2 four times as long as sweep 1); the warp appends them after the sweep
+  // with one prefix sum and one atomic (flush_parked).  A third survivor of the same thread takes the direct path.
+  unsigned long long parked0 = 0ull, parked1 = 0ull;
+  int nparked = 0;
   auto push = [&](float x, int e, unsigned long long T, bool exact) {
     if (exact && make_key<float>(SIGMOID ? sigmoid_f32(x) : x, (uint32_t)e, DESC) < T) return;
-    int slot;
+    const unsigned long long raw = ((unsigned long long)__float_as_uint(x) << 32) | (unsigned long long)(uint32_t)e;
     if constexpr (NEXT) {
-      asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(slot) : "r"(rs_smem_u32(&s_cnt)), "r"(1) : "memory");
-    } else {
-      slot = atomicAdd(&s_cnt, 1);
+      if (nparked == 0) { parked0 = raw; nparked = 1; return; }
+      if (nparked == 1) { parked1 = raw; nparked = 2; return; }
     }
-    if (slot < RS_CAP) keys[slot] = ((unsigned long long)__float_as_uint(x) << 32) | (unsigned long long)(uint32_t)e;
+    const int slot = atomicAdd(&s_cnt, 1);
+    if (slot < RS_CAP) keys[slot] = raw;
+  };
+  auto flush_parked = [&]() {                               // all 32 lanes of the warp, converged
+    int incl = nparked;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total) {                                            // warp-uniform
+      int base = 0;
+      if (lane == 31) base = atomicAdd(&s_cnt, total);
+      base = __shfl_sync(0xffffffffu, base, 31);
+      const int pos = base + incl - nparked;
+      if (nparked > 0 && pos < RS_CAP) keys[pos] = parked0;
+      if (nparked > 1 && pos + 1 < RS_CAP) keys[pos + 1] = parked1;
+    }
+    nparked = 0;
   };
 
   int it = 0;
@@ -780,6 +802,7 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
           }
         }
       }
+      if constexpr (NEXT) flush_parked();
       __syncthreads();
       m = s_cnt;
       if constexpr (NEXT) {
