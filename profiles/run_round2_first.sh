@@ -20,3 +20,5 @@ CC_TOPN_EXPERIMENTAL=1 TOPN_REPS=1 TOPN_BATCHES=4096 timeout 150 ncu --set full 
 echo "ncu rc=$?"
 [ -f $OUT/${TAG}_topn_rs.ncu-rep ] && ncu -i $OUT/${TAG}_topn_rs.ncu-rep --page raw --csv > $OUT/${TAG}_topn_rs_raw.csv 2>/dev/null
 ls -la $OUT | tail -12
+# (separately, on 8 GPUs:  gpurun --gpus 8 --timeout 300 -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
+#   --master-addr 127.0.0.1 --master-port 29511 profiles/scale_up_8gpu.py > gpurun_out/r02_scale_up_8gpu.json')
