@@ -80,12 +80,16 @@ def count_cooccurrence(indptr: torch.Tensor, indices: torch.Tensor, num_cubes: i
 
 
 def normalise(counts: torch.Tensor, *, want_m64=True, want_mhat=True, want_neg=True, force_diag=None,
-              mhat_ld: int | None = None) -> CoocGraph:
+              mhat_ld: int | None = None, mhat: torch.Tensor | None = None) -> CoocGraph:
+    """M (float64), M-hat (float32) and the negative-sampling distribution from int32 counts in one pass.
+    ``mhat``: caller-owned float32 (C, >= C) output (at C = 100 000 the 40 GB allocation costs as much as the pass)."""
     c = counts.shape[0]
     dev = counts.device
     m64 = torch.empty((c, c), dtype=torch.float64, device=dev) if want_m64 else None
-    mhat = None
-    if want_mhat:
+    if mhat is not None:
+        if mhat.dtype != torch.float32 or mhat.shape[0] != c or mhat.shape[1] < c or mhat.stride(1) != 1:
+            raise ValueError("mhat must be float32 (C, >= C) with unit column stride")
+    elif want_mhat:
         ld = mhat_ld or c
         mhat = torch.zeros((c, ld), dtype=torch.float32, device=dev) if ld != c else \
             torch.empty((c, c), dtype=torch.float32, device=dev)
