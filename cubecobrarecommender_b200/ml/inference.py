@@ -39,10 +39,12 @@ class MLRecommender:
 
     FUSED_MAX_N = 128        # cc_topn_masked_sigmoid_f32's limit (warp-per-cube streaming select)
 
-    def recommend_device(self, csr: CubeCSR, amount: int):
+    def recommend_device(self, csr: CubeCSR, amount: int, want_cuts: bool = False):
         """The cubes run through encoder, decoder and the masked select in chunks of ``self.chunk`` with NO host
         synchronisation in between; chunk i+1's CSR rows are uploaded on a copy stream while chunk i computes, and
-        the results stay on the device: (add_ids int32 (K, n), add_scores float32 (K, n), counts int32 (K,))."""
+        the results stay on the device: (add_ids int32 (K, n), add_scores float32 (K, n), counts int32 (K,)).
+        ``want_cuts``: also return the probability of every in-cube card, float32 (nnz,) aligned with ``csr.indices``
+        (the reference's ``cuts`` dict, ml_recommend.py:105-108, for the whole batch) as a fourth element."""
         m = self.model
         dev = m.device
         k = csr.num_cubes
@@ -52,6 +54,7 @@ class MLRecommender:
         ids = torch.empty((k, n), dtype=torch.int32, device=dev)
         vals = torch.empty((k, n), dtype=torch.float32, device=dev)
         cnts = torch.empty(k, dtype=torch.int32, device=dev)
+        cuts = torch.empty(max(int(ip[-1]), 1), dtype=torch.float32, device=dev) if want_cuts else None
         fused = n <= self.FUSED_MAX_N
         compute = torch.cuda.current_stream(dev)
         copier = self._copy_stream = getattr(self, "_copy_stream", None) or torch.cuda.Stream(device=dev)
@@ -83,11 +86,20 @@ class MLRecommender:
                 full = z._base if z._base is not None else z
                 call("cc_sigmoid_f32", ptr(full), ptr(full), full.numel(), stream_ptr())
                 topn_masked(z, ptr_, idx, n, out=out)
+            if want_cuts and ip[hi] > ip[lo]:      # z holds logits (fused) or probabilities (sigmoid pass above)
+                call("cc_cuts_gather_f32", ptr(z), z.stride(0), m.N, hi - lo, ptr(ptr_), ptr(idx), int(fused),
+                     ptr(cuts[int(ip[lo]):int(ip[hi])]), stream_ptr())
+        if want_cuts:
+            return ids, vals, cnts, cuts[:int(ip[-1])]
         return ids, vals, cnts
 
-    def recommend(self, csr: CubeCSR, amount: int, copy: bool = True):
+    def recommend(self, csr: CubeCSR, amount: int, copy: bool = True, want_cuts: bool = False):
         """Returns (add_ids int32 (K, n), add_scores float32 (K, n), counts int32 (K,)) on the host.  Pass a
-        ``csr.pin_memory()`` batch to make the chunk uploads asynchronous."""
+        ``csr.pin_memory()`` batch to make the chunk uploads asynchronous.  ``want_cuts``: a fourth array, float32 (nnz,),
+        the probability of every in-cube card in ``csr.indices`` order (the reference's ``cuts`` scores)."""
+        if want_cuts:
+            ids, vals, cnts, cuts = self.recommend_device(csr, amount, want_cuts=True)
+            return ids.cpu().numpy(), vals.cpu().numpy(), cnts.cpu().numpy(), cuts.cpu().numpy()
         ids, vals, cnts = self.recommend_device(csr, amount)
         if not copy:
             # results land in page-locked buffers owned by this recommender (asynchronous DMA, no page faults on

@@ -123,6 +123,11 @@ int64_t cc_topn_rowselect_profile_grid(int32_t batch, int variant);
 int cc_topn_rowselect_profile(const float* logits, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
                               const int32_t* mask_idx, int32_t n, int variant, int32_t* out_ids, float* out_probs,
                               int32_t* out_count, long long* prof, void* stream);
+/* In-cube ("cuts") scores for a batch (src/scripts/ml_recommend.py:105-108, web/ml_recommend_web.py:61-64: results[idx] for
+ * every in-cube idx): out[p] = scores[b][idx[p]] for the CSR entries p in [row_ptr[b], row_ptr[b+1]) of cube b, through
+ * the float32 sigmoid when apply_sigmoid != 0 (scores are logits then).  out: float32 [row_ptr[batch]]. */
+int cc_cuts_gather_f32(const float* scores, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* row_ptr,
+                       const int32_t* idx, int apply_sigmoid, float* out, void* stream);
 /* Card similarity (src/scripts/similarity.py:25-29): out[r] = -cos(emb[r], emb[query]) with Keras' l2_normalize
  * (epsilon 1e-12), emb float32 [rows][ld >= dim]; rank ascending with cc_topn_masked_f32. */
 int cc_cosine_neg_f32(const float* emb, int64_t ld, int32_t rows, int32_t dim, int32_t query, float* out, void* stream);
