@@ -468,20 +468,23 @@ static int warpselect_launch(const float* scores, int64_t ld, int32_t num_cards,
 }
 
 // ------------------------------------------------------------- CTA-per-cube row select (float32, n <= 128)
-// The HBM-bound form of the select.  A persistent CTA per SM walks the cubes; each cube's score row (4C bytes,
-// 83.5 KB at C = 20 884) is pulled into shared memory by bulk asynchronous copies (cp.async.bulk, completion on an
-// mbarrier), double-buffered, so the row of cube i+1 streams in from HBM while cube i is being ranked and no thread
-// ever waits on a global load.  Ranking a resident row takes two conflict-free sweeps of it:
-//   sweep 1  every thread keeps the best element of its stride; the 512 thread leaders are merged to 128 and their
-//            n-th largest composite key T is found by rank counting.  T is the key of a real element and at least n
-//            elements have keys >= T, so T is a valid lower bound of the answer's last key; with the row spread over
-//            128 strides only ~1.3 n elements lie above it (n = 50: ~63).
-//   sweep 2  the elements with key >= T (pre-filtered by one float compare against the raw-value bound of T) are
-//            appended to a small buffer, ranked against each other by counting, and written at their rank.
+// The HBM-bound form of the select.  Persistent CTAs walk the cubes; each cube's score row (4C bytes, 83.5 KB at
+// C = 20 884) is pulled into shared memory by bulk asynchronous copies (cp.async.bulk, completion on an mbarrier), so
+// no thread ever waits on a global load of scores and the next row streams in from HBM while this one is ranked (two
+// CTAs per SM with one row buffer each, or one CTA with two buffers).  Ranking a resident row takes two sweeps of it:
+//   sweep 1  every thread keeps the extreme of its float4 stride (one compare per four elements); four neighbouring
+//            threads merge to one of 128 leaders; the leaders are ranked by counting on 32-bit stand-ins and the n-th
+//            largest, low bits cleared, becomes the threshold T.  T is a lower bound of the key of a real element with
+//            at least n elements at or above it, so the answer's last key is >= T; with the row spread over 128 leader
+//            strides only ~1.3 n elements lie above it (n = 50: ~63).
+//   sweep 2  the elements that pass the raw-value bound of T (one float compare per group of four) are appended raw
+//            to a small buffer, keyed one survivor per thread, ranked against each other by counting, and written at
+//            their rank.
 // Masked cards are overwritten with a NaN sentinel in the shared copy of the row (every compare with it is false), so
 // the sweeps carry no mask test.  If an adversarial row leaves more than RS_CAP survivors, T is raised to the n-th
-// largest of the first RS_CAP of them (again a valid bound, strictly tighter) and sweep 2 is repeated.  Same total
-// order on (score, index) as the two kernels above => identical ids.  NaN scores are never selected.
+// largest of the first RS_CAP of them (again a valid bound, strictly tighter) and sweep 2 is repeated with the exact key
+// test.  Same total order on (score, index) as the two kernels above => identical ids.  NaN scores are never selected.
+// The selection logic is restated on the host in tests/rowselect_model.py.
 constexpr int RS_THREADS = 512;
 constexpr int RS_CAP = 1024;
 constexpr int RS_LEADERS = 128;
