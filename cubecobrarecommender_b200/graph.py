@@ -10,7 +10,6 @@ int32 ``(C, C)`` and one NCCL ``all_reduce(SUM)`` combines them (exact, order in
 """
 from __future__ import annotations
 
-import ctypes
 from dataclasses import dataclass
 
 import numpy as np

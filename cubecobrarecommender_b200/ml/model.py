@@ -11,7 +11,6 @@ forward of both towers, BCE + reg*KLD, backward, TF-style Adam.
 """
 from __future__ import annotations
 
-import math
 
 import numpy as np
 import torch

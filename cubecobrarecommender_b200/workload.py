@@ -1,7 +1,6 @@
 """Synthetic workloads named by BASELINE.json `configs` (shared by bench.py, smoke() and tests)."""
 from __future__ import annotations
 
-import numpy as np
 
 from .sparse import CubeCSR
 from .synth import synth_cubes_csr

@@ -7,7 +7,6 @@ tests/test_gpu_graph.py::test_scale_up_card_count_properties.  Prints one JSON l
 import json
 import os
 import sys
-import time
 
 import torch
 

@@ -9,7 +9,6 @@ import argparse
 import os
 import sys
 
-import numpy as np
 import torch
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -2,7 +2,6 @@
 """Per-phase clock64() breakdown of topn_rowselect_kernel (diagnostic instantiation, cc_topn_rowselect_profile) on the
 topn_bench.py workload: 4096 logit rows of C = 20 884, top-50, in-cube cards masked, fused sigmoid.  For each launch
 shape prints the mean cycles per cube that thread 0 of a CTA spends in every phase (all CTAs, all cubes)."""
-import ctypes
 import json
 import os
 import sys

@@ -1,6 +1,5 @@
 """Host-side drop-in logic that needs no GPU: loaders (reference src/non_ml/utils.py:6-73), name
 normalisation (recommend.py:53), the WSGI route's error strings (web/__init__.py:18-30), CSR helpers."""
-import io
 import json
 import os
 

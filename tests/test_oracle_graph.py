@@ -2,7 +2,6 @@
 hand-computed known answers for reference src/non_ml/utils.py:75-92,
 src/ml/train.py:69-71, src/scripts/recommend.py:7-18, cut_cards.py:7-18."""
 import numpy as np
-import pytest
 from hypothesis import given, settings, strategies as st
 
 from cubecobrarecommender_b200.synth import csr_to_dense, dense_to_csr, synth_cubes_csr
