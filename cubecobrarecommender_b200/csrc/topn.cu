@@ -600,6 +600,8 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
     }
   };
   if constexpr (PROF) tprev = clock64();
+  // (nvcc warns that the other kernels of this file declare the array with 16-byte alignment: harmless, and left alone
+  // because the build that was verified on the GPU has it)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar[2];
   __shared__ unsigned long long s_T;
