@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""BASELINE configs[3] on N GPUs: 100 000 cubes, top-50 with in-cube masking, cubes sharded over the ranks (inference has
+no exchange step: every rank ranks its own cubes with a replica of the model).  Launch:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 \
+        profiles/ml_recommend_ngpu.py            (or plain `python profiles/ml_recommend_ngpu.py` for one GPU)
+
+Times: CUDA events around MLRecommender.recommend_device on every rank (pinned host CSR in, results left on the device),
+max over ranks; throughput = all cubes / that time.  NOT run in round 1 at N > 1 (GPU budget)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from cubecobrarecommender_b200.dist import shard_range  # noqa: E402
+from cubecobrarecommender_b200.ml import inference as INF, model as M  # noqa: E402
+from cubecobrarecommender_b200.workload import make_cubes  # noqa: E402
+
+C, K, N = 20884, int(os.environ.get("RECOMMEND_CUBES", 100000)), 50
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+lo, hi = shard_range(K, rank, world)
+csr = make_cubes(K, C, cfg=4).rows(np.arange(lo, hi)).pin_memory()      # every rank builds the same cubes, keeps its shard
+model = M.CC_Recommender(C, device=dev, seed=0, precision="tf32")          # same seed: identical replicas
+rec = INF.MLRecommender(model, chunk=4096)
+rec.recommend_device(csr, N)                                               # warm-up
+torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+ids, vals, cnt = rec.recommend_device(csr, N)
+e1.record()
+torch.cuda.synchronize()
+t = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device=dev)
+ok = torch.tensor([int((cnt == N).all().item())], device=dev)
+if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(json.dumps({"workload": f"ml_recommend top-{N}, {K} cubes, C={C}, in-cube masking, {world} GPU(s), cubes sharded",
+                      "seconds": t.item(), "recs_per_s": K / t.item(), "n_gpus": world, "all_counts_full": bool(ok.item()),
+                      "timing": "CUDA events around recommend_device (pinned CSR upload included), max over ranks"}))
+if world > 1:
+    dist.destroy_process_group()

@@ -22,3 +22,5 @@ echo "ncu rc=$?"
 ls -la $OUT | tail -12
 # (separately, on 8 GPUs:  gpurun --gpus 8 --timeout 300 -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
 #   --master-addr 127.0.0.1 --master-port 29511 profiles/scale_up_8gpu.py > gpurun_out/r02_scale_up_8gpu.json')
+# (and configs[3] on 8 GPUs:  gpurun --gpus 8 --timeout 300 -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
+#   --master-addr 127.0.0.1 --master-port 29512 profiles/ml_recommend_ngpu.py > gpurun_out/r02_ml_recommend_8gpu.json')
