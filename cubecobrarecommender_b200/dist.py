@@ -3,8 +3,11 @@ the CPU tests).  SURVEY.md §8e: the path shards by cubes with one exchange step
 
 * graph build: every rank counts its own cube shard, ``all_reduce(SUM)`` of the int32 counts (exact);
 * train step : batch and regulariser rows split B/G and R/G per rank, each rank scales its loss
-  terms by the GLOBAL B*C and R, ``all_reduce(SUM)`` of the flat gradient buffer and of the 3 loss
-  scalars; weights and Adam state are replicated and stay bit-identical across ranks;
+  terms by the GLOBAL B*C and R, the gradients are summed over the ranks (``all_reduce(SUM)`` of the flat
+  buffer in the NCCL modes; reduce-scatter + Adam + all-gather in one peer-memory kernel in the default p2p
+  mode) and the 3 loss scalars all_reduced; the weights are replicated and stay bit-identical across
+  ranks.  Adam's m / v are replicated in the NCCL modes and SLICED in p2p mode (a rank only updates the
+  slice it owns, ``owner_slice``): ``DAEEngine.gather_adam_state()`` completes them before a checkpoint;
 * inference  : cubes are independent, no collective.
 """
 from __future__ import annotations

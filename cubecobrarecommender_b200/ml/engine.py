@@ -45,7 +45,7 @@ def full_identity_shard(num_cards: int, rank: int = 0, world: int = 1):
 class DAEEngine:
     def __init__(self, model: CC_Recommender, mhat: torch.Tensor, *, batch: int, reg_rows: int | None = None,
                  reg: float = 0.1, max_cube_size: int = 720, global_batch: int | None = None,
-                 global_reg_rows: int | None = None, group=None, adam=None):
+                 global_reg_rows: int | None = None, group=None, adam=None, data_parallel: bool = True):
         self.model = model
         self.store = model.store
         self.dev = model.device
@@ -57,6 +57,7 @@ class DAEEngine:
         self.global_B = int(global_batch or self.B)
         self.global_R = int(global_reg_rows or self.R)
         self.group = group
+        self.data_parallel = bool(data_parallel)   # False: never exchange, even under torchrun (single-GPU reference runs)
         self.adam = dict(KERAS_ADAM, **(adam or {}))
         self.mhat = mhat
         assert mhat.dtype == torch.float32 and mhat.shape[0] == self.C and mhat.shape[1] >= self.C
@@ -427,7 +428,8 @@ class DAEEngine:
     # -- data-parallel exchange ---------------------------------------------------------
     def _distributed(self):
         import torch.distributed as dist
-        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        return (self.data_parallel and dist.is_available() and dist.is_initialized()
+                and dist.get_world_size(self.group) > 1)
 
     def _grads_ready(self, bucket):
         """Backward has finished every gradient of `bucket`: start its all_reduce (NCCL's own stream; it first
@@ -436,22 +438,25 @@ class DAEEngine:
             self.buckets.launch(self.store.grads, bucket, self.group)
 
     def _dp_setup(self):
-        """First distributed step: move params/grads to symmetric memory for the p2p mode (collective).  If the
-        rendezvous is not possible on this system every rank falls back to the blocking NCCL all_reduce."""
+        """First distributed step: move params/grads to symmetric memory for the p2p mode (collective).  There is no
+        silent downgrade: if the peer-memory rendezvous is impossible on this system every rank raises, and the NCCL
+        all_reduce path has to be asked for explicitly (CC_DP_MODE=nccl)."""
         import torch.distributed as dist
         self._dp_ready = True
         if not self._distributed() or self.dp_mode != "p2p":
             return
         ok = torch.ones(1, dtype=torch.int32, device=self.dev)
+        err = None
         try:
             self.store.make_symmetric(self.group)
         except Exception as e:                      # no peer access / no symmetric-memory support
-            import warnings
-            warnings.warn(f"CC_DP_MODE=p2p unavailable ({e!r}); using the NCCL all_reduce path")
+            err = e
             ok.zero_()
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)      # every rank fails together, nobody hangs
         if int(ok.item()) == 0:
-            self.dp_mode = "nccl"
+            raise RuntimeError("CC_DP_MODE=p2p: symmetric-memory rendezvous failed on at least one rank"
+                               + (f" (here: {err!r})" if err is not None else "")
+                               + "; set CC_DP_MODE=nccl to use the NCCL all_reduce exchange instead")
         self._sync_flag = torch.zeros(1, dtype=torch.float32, device=self.dev)
         # in-switch reduction / broadcast (multimem.ld_reduce / multimem.st) when the fabric offers multicast
         import os
@@ -494,6 +499,22 @@ class DAEEngine:
             self.launches += 1
         call("cc_step_increment", ptr(s.step), st)
         self.launches += 2
+
+    def gather_adam_state(self):
+        """p2p mode: every rank keeps Adam's m and v only for the slice of the parameters it owns (the fused exchange
+        kernel updates nothing else).  Before a checkpoint is written the slices are exchanged so that every rank --
+        rank 0 writes the file -- holds the complete, current m and v.  Collective; a no-op in every other mode."""
+        import torch.distributed as dist
+        if not (self._distributed() and self.dp_mode == "p2p" and self._dp_ready):
+            return
+        from ..dist import owner_slice
+        s = self.store
+        world = dist.get_world_size(self.group)
+        for r in range(world):
+            lo, hi = owner_slice(s.total, r, world)
+            src = dist.get_global_rank(self.group, r) if self.group is not None else r
+            for buf in (s.adam_m, s.adam_v):
+                dist.broadcast(buf[lo:hi], src=src, group=self.group)
 
     def apply_adam(self):
         """TF-style Adam over all parameters, then the step counter advances."""

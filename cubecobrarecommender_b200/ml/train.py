@@ -58,6 +58,7 @@ def fit(model, generator, epochs, reg, *, group=None, log=print, steps_per_epoch
         log(f"{nsteps}/{nsteps} - {time.time() - t0:.0f}s - loss: {mean[2]:.4f} - output_1_loss: {mean[0]:.4f} "
             f"- output_2_loss: {mean[1]:.4f}")
         generator.on_epoch_end()
+    eng.gather_adam_state()      # p2p data parallel: m / v live sliced over the ranks until a checkpoint needs them
     return history
 
 

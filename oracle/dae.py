@@ -67,13 +67,22 @@ def _dense_fwd(x, w, b, relu=True):
     return np.maximum(z, 0) if relu else z
 
 
-def forward_np(params, x, reg_rows):
+def forward_np(params, x, reg_rows, onehot_rows_as_gather=False):
     """Returns (logits_main (B,C), logits_reg (R,C), cache).  ``x`` dense
     (B,C); ``reg_rows`` int (R,) = the rows of I fed to the second tower
-    (reference ``model.py:117-125``; ``generator.py:47-51,76``)."""
+    (reference ``model.py:117-125``; ``generator.py:47-51,76``).
+
+    ``onehot_rows_as_gather``: evaluate the first layer of the second tower as
+    ``relu(W1[r] + b1)`` instead of ``relu(I[r] @ W1 + b1)`` -- the same float64
+    numbers (a one-hot row contributes one exact product and exact zeros) without
+    the (R, C) one-hot matrix; for the BASELINE-sized parity cases."""
     p = {k: v.astype(np.float64) for k, v in params.items()}
     c = p["encoder_e1/kernel"].shape[0]
-    eye_rows = np.zeros((len(reg_rows), c)); eye_rows[np.arange(len(reg_rows)), reg_rows] = 1
+    reg_rows = np.asarray(reg_rows, dtype=np.int64)
+    if onehot_rows_as_gather:
+        eye_rows = None
+    else:
+        eye_rows = np.zeros((len(reg_rows), c)); eye_rows[np.arange(len(reg_rows)), reg_rows] = 1
     cache = {}
     outs = []
     for tower, inp, dec in (("main", np.asarray(x, np.float64), "main"), ("reg", eye_rows, "reg")):
@@ -81,7 +90,10 @@ def forward_np(params, x, reg_rows):
         names = ["encoder_e1", "encoder_e2", "encoder_e3", "encoder_bottleneck",
                  f"{dec}_d1", f"{dec}_d2", f"{dec}_d3"]
         for n in names:
-            acts.append(_dense_fwd(acts[-1], p[n + "/kernel"], p[n + "/bias"]))
+            if acts[-1] is None:        # one-hot rows through the first layer = a row gather of its kernel
+                acts.append(np.maximum(p[n + "/kernel"][reg_rows] + p[n + "/bias"], 0))
+            else:
+                acts.append(_dense_fwd(acts[-1], p[n + "/kernel"], p[n + "/bias"]))
         z = _dense_fwd(acts[-1], p[f"{dec}_reconstruction/kernel"],
                        p[f"{dec}_reconstruction/bias"], relu=False)
         cache[tower] = (names + [f"{dec}_reconstruction"], acts)
@@ -107,10 +119,12 @@ def kld_np(t, q):
     return float(np.mean(np.sum(tc * np.log(tc / qc), axis=1)))
 
 
-def loss_and_grads_np(params, x, y, reg_rows, t_reg, reg):
+def loss_and_grads_np(params, x, y, reg_rows, t_reg, reg, onehot_rows_as_gather=False):
     """float64 loss (total, bce, kl) and hand-derived gradients for every
-    parameter.  ``t_reg`` = M-hat[reg_rows] (R,C).  Follows SURVEY.md §8a-6."""
-    z1, z2, cache = forward_np(params, x, reg_rows)
+    parameter.  ``t_reg`` = M-hat[reg_rows] (R,C).  Follows SURVEY.md §8a-6.
+    ``onehot_rows_as_gather``: see :func:`forward_np` (the first-layer gradient of
+    the one-hot rows is then a row scatter-add, again the same numbers)."""
+    z1, z2, cache = forward_np(params, x, reg_rows, onehot_rows_as_gather)
     y = np.asarray(y, np.float64); t = np.asarray(t_reg, np.float64)
     b, c = z1.shape; r = z2.shape[0]
     bce = bce_from_logits_np(z1, y)
@@ -132,7 +146,10 @@ def loss_and_grads_np(params, x, y, reg_rows, t_reg, reg):
         for li in range(len(names) - 1, -1, -1):
             n = names[li]
             a_in = acts[li]
-            grads[n + "/kernel"] += a_in.T @ d
+            if a_in is None:            # one-hot input rows: I[r]^T d adds row i of d to row r_i of the kernel gradient
+                np.add.at(grads[n + "/kernel"], np.asarray(reg_rows, dtype=np.int64), d)
+            else:
+                grads[n + "/kernel"] += a_in.T @ d
             grads[n + "/bias"] += d.sum(0)
             if li > 0:
                 d = d @ p[n + "/kernel"].T

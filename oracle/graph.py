@@ -23,11 +23,39 @@ def cooc_counts(indptr: np.ndarray, indices: np.ndarray, num_cards: int) -> np.n
     ``utils.py:82-84`` (sums of 0/1 values are exact in float64)."""
     import scipy.sparse as sp
     k = len(indptr) - 1
-    x = sp.csr_matrix((np.ones(len(indices), dtype=np.int64), indices, indptr),
+    # (copies: sum_duplicates() compacts the index arrays in place, and the matrix would share the caller's)
+    x = sp.csr_matrix((np.ones(len(indices), dtype=np.int64), np.array(indices, copy=True), np.array(indptr, copy=True)),
                       shape=(k, num_cards))
     x.sum_duplicates()
     x.data[:] = 1  # duplicates collapse: build_cubes assigns 1 (utils.py:71)
     return np.ascontiguousarray((x.T @ x).todense(), dtype=np.int64)
+
+
+def cooc_counts_blocked(indptr: np.ndarray, indices: np.ndarray, num_cards: int, block: int = 3072,
+                        out_dtype=np.int32) -> np.ndarray:
+    """The same ``cnt = X^T X`` as :func:`cooc_counts` for BASELINE-sized inputs (K = 20 000, C = 21 000), where the
+    sparse product needs minutes and ~10 GB: dense float32 column blocks of X multiplied on all host cores.  A count is
+    a sum of at most K products of 0/1 values; K < 2**24, so every partial sum is an integer float32 holds exactly and
+    the result is exact whatever the summation order.  Only the upper-triangular blocks are computed and mirrored
+    (X^T X is symmetric).  ``tests/test_oracle_graph.py`` holds it equal to :func:`cooc_counts`."""
+    import torch
+    k = len(indptr) - 1
+    if k >= 1 << 24:
+        raise ValueError("float32 partial sums are exact only below 2**24 cubes")
+    x = torch.zeros((k, num_cards), dtype=torch.float32)
+    x[torch.from_numpy(np.repeat(np.arange(k), np.diff(indptr))), torch.from_numpy(indices.astype(np.int64))] = 1.0
+    cnt = np.zeros((num_cards, num_cards), dtype=out_dtype)      # (duplicates collapse: assignment, utils.py:71)
+    starts = list(range(0, num_cards, block))
+    for bi, lo in enumerate(starts):
+        hi = min(lo + block, num_cards)
+        xi_t = x[:, lo:hi].t().contiguous()
+        for lo2 in starts[bi:]:
+            hi2 = min(lo2 + block, num_cards)
+            blk = (xi_t @ x[:, lo2:hi2]).numpy()
+            cnt[lo:hi, lo2:hi2] = blk
+            if lo2 != lo:
+                cnt[lo2:hi2, lo:hi] = blk.T
+    return cnt
 
 
 def adjacency_from_counts(cnt: np.ndarray, force_diag=None) -> np.ndarray:
@@ -71,6 +99,27 @@ def m_hat(adj_mtx: np.ndarray) -> np.ndarray:
     y = adj_mtx.copy()
     np.fill_diagonal(y, 1)
     return y / y.sum(1)[:, None]
+
+
+def m_hat_rows(indptr: np.ndarray, indices: np.ndarray, num_cards: int, rows: np.ndarray) -> np.ndarray:
+    """Rows ``rows`` of M-hat (float64, (R, C)) for BASELINE-sized inputs, without the (C, C) matrices: exactly the
+    reference's arithmetic on those rows -- ``cnt[r, :]`` = sum of the cubes containing card r (``utils.py:82-84``),
+    divided by ``cnt[r, r]`` when non-zero (``:85-89``), diagonal <- 1 and the row divided by its sum
+    (``train.py:69-71``).  ``tests/test_oracle_graph.py`` holds it equal to ``m_hat(...)[rows]``."""
+    import scipy.sparse as sp
+    k = len(indptr) - 1
+    rows = np.asarray(rows, dtype=np.int64)
+    x = sp.csr_matrix((np.ones(len(indices)), np.array(indices, copy=True), np.array(indptr, copy=True)),
+                      shape=(k, num_cards))
+    x.sum_duplicates()
+    x.data[:] = 1
+    cnt = np.asarray((x.T.tocsr()[rows] @ x).todense(), dtype=np.float64)          # exact integers
+    at = np.arange(len(rows))
+    diag = cnt[at, rows].copy()
+    nz = diag != 0
+    cnt[nz] = cnt[nz] / diag[nz, None]
+    cnt[at, rows] = 1.0
+    return cnt / cnt.sum(1)[:, None]
 
 
 def neg_sampler(y_mtx: np.ndarray) -> np.ndarray:

@@ -1,0 +1,161 @@
+"""Parity at the configurations BASELINE.json names -- not scaled-down stand-ins:
+
+* configs[1] / [2]: ONE train step at C = 20 884 cards, B = R = 4096, noise output held fixed, against
+  ``oracle/dae.py:loss_and_grads_np`` (float64) in the three precision modes -- bce / kl / total and the three 512 x C
+  gradients by max-norm.  Reference semantics: ``src/ml/train.py:83-88``, ``src/ml/model.py:117-125``.
+* configs[0]: counts and M at K = 20 000 cubes x C = 21 000 cards, bit-exact (``src/non_ml/utils.py:75-92``).
+* configs[3]: top-50 additions of 1024 of the 100 000 cubes against ``oracle/dae.py:rank_additions`` on the same
+  float32 probabilities (``src/scripts/ml_recommend.py:78-104``).
+
+The oracle side costs tens of seconds of host time per case (float64 GEMMs at full width); it is computed once per
+module.  Tolerances (per-step loss, relative): fp32 1e-5, tf32 1e-3 (the north-star bar), bf16 2e-3 (stated tolerance of
+the separately reported bf16 mode)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from cubecobrarecommender_b200 import graph as G
+from cubecobrarecommender_b200.ml import engine as E, inference as INF, model as M
+from cubecobrarecommender_b200.workload import TRAIN_STEP, make_cubes
+from oracle import dae as od, graph as og
+
+LOSS_TOL = {"fp32": 1e-5, "tf32": 1e-3, "bf16": 2e-3}
+GRAD_TOL = {"fp32": 2e-4, "tf32": 1e-2, "bf16": 5e-2}          # of the gradient's max-norm (tests/test_gpu_dae.py TOL)
+BIG_GRADS = ("main_reconstruction/kernel", "reg_reconstruction/kernel", "encoder_e1/kernel",
+             "main_reconstruction/bias", "reg_reconstruction/bias")
+
+
+@pytest.fixture(scope="module")
+def headline_step():
+    """The bench's own workload (workload.TRAIN_STEP): cubes, graph, noise output of the CUDA noise kernel read back,
+    and the float64 oracle's loss and gradients on exactly that (x, y, r)."""
+    W = TRAIN_STEP
+    c, b, r = W["num_cards"], W["batch"], W["reg_rows"]
+    csr = make_cubes(W["num_cubes"], c, cfg=W["cfg"] * 1000)
+    gr = G.build_graph(csr, "cuda", want_m64=False, want_mhat=True, want_neg=True)
+    prob, alias = E.alias_table(gr.neg_sampler.cpu().numpy(), "cuda")
+    params = od.init_params(c, seed=0)
+    rng = np.random.default_rng(9)
+    for kname in params:                                   # non-zero biases so that every bias gradient matters
+        if kname.endswith("bias"):
+            params[kname] = (rng.standard_normal(params[kname].shape) * 0.02).astype(np.float32)
+    model = M.CC_Recommender(c, device="cuda", precision="tf32")
+    eng = E.DAEEngine(model, gr.mhat, batch=b, reg_rows=r, reg=W["reg"], max_cube_size=720)
+    indptr, indices = G.upload_csr(csr, "cuda")
+    eng.sample_batch(indptr, indices, torch.arange(b, dtype=torch.int32, device="cuda"), prob, alias, W["noise"],
+                     W["noise_std"], seed=1234)
+    eng.check_overflow()
+    xl = eng.x_len.cpu().numpy(); xi = eng.x_idx.cpu().numpy()
+    x = np.zeros((b, c)); y = np.zeros((b, c))
+    for i in range(b):
+        x[i, xi[i, :xl[i]]] = 1
+    bits = eng.y_bits.cpu().numpy().view(np.uint32)
+    y = ((bits[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(b, -1)[:, :c].astype(np.float64)
+    rows = eng.reg_rows[:r].cpu().numpy().astype(np.int64)
+    fixed = dict(x_idx=eng.x_idx.clone(), x_len=eng.x_len.clone(), y_bits=eng.y_bits.clone(), reg_rows=eng.reg_rows.clone())
+    # targets as the reference feeds them: float64 M-hat rows cast to float32 by Keras; here from the ORACLE's counts
+    t_rows = og.m_hat_rows(csr.indptr, csr.indices, c, rows)
+    got_rows = gr.mhat[torch.from_numpy(rows).cuda(), :c].cpu().numpy().astype(np.float64)
+    nz = t_rows > 0
+    assert (np.abs(got_rows[nz] - t_rows[nz]) / t_rows[nz]).max() < 1e-6 and (got_rows[~nz] == 0).all()
+    t32 = t_rows.astype(np.float32).astype(np.float64)
+    p64 = {k: v.astype(np.float64) for k, v in params.items()}
+    (tot, bce, kl), grads = od.loss_and_grads_np(p64, x, y, rows, t32, W["reg"], onehot_rows_as_gather=True)
+    keep = {k: grads[k] for k in BIG_GRADS}
+    del eng, model, x, y, grads
+    torch.cuda.empty_cache()
+    return dict(c=c, b=b, r=r, params=params, mhat=gr.mhat, fixed=fixed, loss=(tot, bce, kl), grads=keep, reg=W["reg"])
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16", "fp32"])
+def test_train_step_at_baseline_shape_vs_oracle(headline_step, precision):
+    h = headline_step
+    model = M.CC_Recommender(h["c"], device="cuda", precision=precision)
+    model.set_weights_dict(h["params"])
+    eng = E.DAEEngine(model, h["mhat"], batch=h["b"], reg_rows=h["r"], reg=h["reg"], max_cube_size=720)
+    f = h["fixed"]
+    eng.x_idx.copy_(f["x_idx"]); eng.x_len.copy_(f["x_len"])
+    sb = M.SparseBatch(eng.x_idx.view(-1), eng.x_start, eng.x_len)
+    eng.set_batch(sb, f["y_bits"], f["reg_rows"][:h["r"]])
+    eng.forward_backward()
+    got = eng.loss3.cpu().numpy()
+    tot, bce, kl = h["loss"]
+    tol = LOSS_TOL[precision]
+    assert abs(got[0] - bce) / bce < tol, (got, h["loss"])
+    assert abs(got[1] - kl) / kl < tol, (got, h["loss"])
+    assert abs(got[2] - tot) / tot < tol, (got, h["loss"])
+    gd = model.store
+    for kname, gref in h["grads"].items():
+        g = gd.g(kname).cpu().numpy().astype(np.float64)
+        scale = np.abs(gref).max()
+        assert scale > 0
+        assert np.abs(g - gref).max() / scale < GRAD_TOL[precision], (precision, kname)
+    # the step then runs to completion (Adam) and a second forward still gives a finite, smaller-or-similar loss
+    eng.apply_adam()
+    eng.forward_backward()
+    got2 = eng.loss3.cpu().numpy()
+    assert np.isfinite(got2).all() and got2[2] < got[2] * 1.01
+
+
+def test_graph_build_at_baseline_shape_bit_exact():
+    """configs[0]: K = 20 000 cubes x C = 21 000 cards.  Counts bit-exact on both count kernels against the oracle's
+    blocked dense form (held equal to the pinned sparse form on the CPU), M bit-exact in float64, M-hat <= 1e-6 rel."""
+    k, c = 20000, 21000
+    csr = make_cubes(k, c, cfg=1)
+    cnt = og.cooc_counts_blocked(csr.indptr, csr.indices, c)
+    assert int(np.diagonal(cnt).sum()) == int(csr.indptr[-1])
+    indptr, indices = G.upload_csr(csr, "cuda")
+    ref = torch.from_numpy(cnt).cuda()
+    for method in ("tensor", "popcount"):
+        got = G.count_cooccurrence(indptr, indices, k, c, method=method)
+        assert torch.equal(got, ref), method
+    del ref
+    gr = G.normalise(got, want_m64=True, want_mhat=True, want_neg=True)
+    m = og.adjacency_from_counts(cnt)
+    m_got = gr.m64.cpu().numpy()
+    assert np.array_equal(m_got, m)
+    del m_got, gr.m64
+    # M-hat and the negative sampler on a row sample (the full float64 M-hat costs another 7 GB of host memory)
+    rows = np.unique(np.concatenate([np.arange(0, c, 97), np.where(np.diagonal(cnt) == 0)[0][:50]]))
+    y = m[rows].copy(); y[np.arange(len(rows)), rows] = 1.0
+    mh = y / y.sum(1, keepdims=True)
+    got_mh = gr.mhat[torch.from_numpy(rows).cuda()].cpu().numpy().astype(np.float64)
+    nz = mh > 0
+    assert (np.abs(got_mh[nz] - mh[nz]) / mh[nz]).max() < 1e-6 and (got_mh[~nz] == 0).all()
+    np.fill_diagonal(m, 1.0)
+    rs = m.sum(1)
+    assert np.abs(gr.rowsum.cpu().numpy() - rs).max() <= 1e-12 * rs.max()
+    m /= rs[:, None]
+    ns = m.sum(0) / m.sum()
+    assert np.abs(gr.neg_sampler.cpu().numpy() - ns).max() < 1e-12
+
+
+def test_ml_recommend_at_baseline_shape_ids_vs_oracle():
+    """configs[3]: 100 000 cubes, C = 20 884, top-50 with in-cube masking through the batched path; 1024 of the cubes
+    (spread over every chunk) are ranked by the oracle's argsort walk on the float32 probabilities of the same model."""
+    c, k, n = 20884, 100000, 50
+    csr = make_cubes(k, c, cfg=4)
+    model = M.CC_Recommender(c, device="cuda", seed=0, precision="tf32")
+    rec = INF.MLRecommender(model, chunk=4096)
+    ids, vals, cnt = rec.recommend(csr, n)
+    assert ids.shape == (k, n) and (cnt == n).all()
+    pick = np.unique(np.concatenate([np.arange(0, k, 98), [k - 1, 4095, 4096]]))
+    assert len(pick) >= 1000
+    # probabilities of the picked cubes, evaluated inside the SAME 4096-cube chunks the batched call used (a GEMM's
+    # accumulation order depends on its shape, so a differently shaped batch may differ in the last bit)
+    for lo in range(0, k, 4096):
+        sel = pick[(pick >= lo) & (pick < lo + 4096)]
+        if not len(sel):
+            continue
+        chunk = csr.rows(np.arange(lo, min(lo + 4096, k)))
+        probs = rec.probabilities(chunk)
+        sub = probs[torch.from_numpy(sel - lo).cuda()].cpu().numpy()
+        for j, row in enumerate(sel):
+            in_cube = np.zeros(c, dtype=np.int8)
+            in_cube[csr.indices[csr.indptr[row]:csr.indptr[row + 1]]] = 1
+            expect = od.rank_additions(sub[j], in_cube, n)
+            assert ids[row].tolist() == expect, row
+            assert np.array_equal(vals[row], sub[j][expect])

@@ -1,0 +1,68 @@
+"""Multi-GPU correctness on hardware (skipped on a one-GPU box): N ranks on a FIXED global batch of 4096 cubes at
+C = 20 884 must reproduce the 1-GPU train step -- loss to 1e-6 on the first step, weights after three steps to the Adam
+tolerance, replicas bit-identical across ranks -- in the peer-memory exchange (unicast AND NVSwitch multicast,
+``adam_p2p_kernel``'s ``multimem.ld_reduce`` / ``multimem.st`` branch) and in the NCCL all_reduce mode; and the Adam state
+a p2p run keeps sliced over the ranks is complete after ``gather_adam_state()``.  The checker is
+``cubecobrarecommender_b200/dp_check.py``, launched under torchrun exactly like ``bench.py``."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    return port
+
+
+def _torchrun(nproc, module_args, timeout=900):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port())] + module_args
+    env = dict(os.environ, PYTHONPATH=REPO + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    for k in ("CC_DP_MODE", "CC_P2P_MULTICAST", "CC_DP_OVERLAP"):
+        env.pop(k, None)
+    return subprocess.run(cmd, cwd=REPO, env=env, capture_output=True, text=True, timeout=timeout)
+
+
+def _ngpus():
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs")
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_n_gpu_step_equals_one_gpu_step(precision):
+    from cubecobrarecommender_b200 import dp_check
+    n = 8 if _ngpus() >= 8 else 4 if _ngpus() >= 4 else 2
+    r = _torchrun(n, ["-m", "cubecobrarecommender_b200.dp_check", "--precision", precision, "--steps", "3"])
+    assert r.stdout.strip(), r.stderr[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["world"] == n
+    ran = [m for m, v in out["modes"].items() if "skipped" not in v]
+    assert "p2p_unicast" in ran and "nccl" in ran
+    assert dp_check.verdict(out) == [], (out, r.stderr[-2000:])
+    assert r.returncode == 0, r.stderr[-3000:]
+    if "p2p_multicast" in ran:
+        assert out["modes"]["p2p_multicast"]["multicast"] is True
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs")
+def test_bench_strong_scaling_and_check_leg():
+    """bench.py under torchrun with --scaling strong (global batch fixed at 4096) and --check (the equality checker
+    above as a bench leg): one JSON line, the check green."""
+    n = 2
+    r = _torchrun(n, ["bench.py", "--gpus", str(n), "--steps", "5", "--warmup", "3", "--scaling", "strong", "--check",
+                      "--no-extras", "--no-cpu-baseline"])
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["scaling"] == "strong" and line["n_gpus"] == n
+    assert line["config"]["global_batch"] == 4096 and line["config"]["batch_per_gpu"] == 4096 // n
+    assert line["check"]["violations"] == []

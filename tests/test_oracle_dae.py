@@ -120,3 +120,16 @@ def test_similarity_restatement_known_answers():
     for n in ("encoder_e1", "encoder_e2", "encoder_e3", "encoder_bottleneck"):
         h = np.maximum(h @ p[n + "/kernel"] + p[n + "/bias"], 0.0)
     assert np.allclose(od.card_embeddings_np(params), h, atol=1e-14)
+
+
+def test_onehot_rows_as_gather_is_the_same_arithmetic():
+    """The BASELINE-sized parity cases evaluate the second tower's first layer as a row gather of its kernel (and its
+    gradient as a row scatter-add) instead of multiplying by one-hot rows of I: identical float64 numbers."""
+    params, x, y, reg_rows, t = _setup()
+    reg_rows = reg_rows.copy(); reg_rows[1] = reg_rows[0]            # a row drawn twice
+    t = t.copy(); t[1] = t[0]
+    (la, ga) = dae.loss_and_grads_np(params, x, y, reg_rows, t, reg=0.1)
+    (lb, gb) = dae.loss_and_grads_np(params, x, y, reg_rows, t, reg=0.1, onehot_rows_as_gather=True)
+    assert la == lb
+    for kname in ga:
+        assert np.abs(ga[kname] - gb[kname]).max() <= 1e-18 + 1e-15 * np.abs(ga[kname]).max(), kname

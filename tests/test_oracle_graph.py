@@ -2,6 +2,7 @@
 hand-computed known answers for reference src/non_ml/utils.py:75-92,
 src/ml/train.py:69-71, src/scripts/recommend.py:7-18, cut_cards.py:7-18."""
 import numpy as np
+import pytest
 from hypothesis import given, settings, strategies as st
 
 from cubecobrarecommender_b200.synth import csr_to_dense, dense_to_csr, synth_cubes_csr
@@ -117,3 +118,25 @@ def test_golden_pairwise_recs(pairwise_golden):
         ourcut = np.array(graph.simple_cuts(cube, adj.copy()))
         cs = g["cut_scores"][n]
         assert np.array_equal(cs[ourcut], cs[refcut])
+
+
+@pytest.mark.parametrize("k,c,block", [(300, 1000, 384), (64, 130, 50), (500, 257, 4096)])
+def test_blocked_dense_counts_equal_sparse_counts(k, c, block):
+    """oracle.graph.cooc_counts_blocked (the form used for the BASELINE-sized GPU parity test: K = 20 000, C = 21 000)
+    equals the pinned cooc_counts, including duplicate card ids inside a cube."""
+    from cubecobrarecommender_b200.synth import synth_cubes_csr
+    ip, ix = synth_cubes_csr(k, c, size_lo=1, size_hi=min(c, 120), seed=k + c)
+    ix = ix.copy(); ix[1] = ix[0]                              # a duplicate id in the first cube
+    a = graph.cooc_counts(ip, ix, c)
+    b = graph.cooc_counts_blocked(ip, ix, c, block=block)
+    assert b.dtype == np.int32 and np.array_equal(a, b)
+
+
+def test_m_hat_rows_equals_full_m_hat():
+    from cubecobrarecommender_b200.synth import synth_cubes_csr
+    k, c = 120, 300
+    ip, ix = synth_cubes_csr(k, c, size_lo=3, size_hi=40, seed=5)
+    full = graph.m_hat(graph.adjacency_from_counts(graph.cooc_counts(ip, ix, c)))
+    assert (np.diagonal(graph.cooc_counts(ip, ix, c)) == 0).any()          # unseen cards exercise the e_i rows
+    rows = np.array([0, 7, 7, 299, 150] + list(np.where(np.diagonal(graph.cooc_counts(ip, ix, c)) == 0)[0][:3]))
+    assert np.array_equal(graph.m_hat_rows(ip, ix, c, rows), full[rows])
