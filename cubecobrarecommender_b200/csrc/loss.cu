@@ -269,12 +269,17 @@ __device__ __forceinline__ float block_max1_p(float a, float2* red) {
   return warp_max(red[lane].x);
 }
 
+// The row is swept three times out of shared memory: (1) online max / sum of exponentials, (2) loss and S -- here
+// exp(z - max) is written back over the logit, so that (3), the gradient sweep, costs no MUFU at all.  With `tlogt`
+// (sum_c t'_c log t'_c of every target row, a property of M-hat alone, built once per graph by cc_kl_target_table)
+// sweep 2 needs no logarithm either: one ex2 per element in total instead of two ex2 + one lg2 + sweep 1's.
 template <bool FAST>
 __global__ void __launch_bounds__(KLP_THREADS, 1)
 softmax_kl_persistent_kernel(const float* __restrict__ z, int64_t ldz, const float* __restrict__ target, int64_t ldt,
                              const int32_t* __restrict__ target_rows, int32_t rows, int32_t num_cards, int32_t ncols_pad,
                              float grad_scale, float* __restrict__ dz, int64_t lddz, double* __restrict__ row_loss,
-                             int round_tf32, float* __restrict__ dbias, __nv_bfloat16* __restrict__ dz16, int64_t lddz16) {
+                             int round_tf32, float* __restrict__ dbias, __nv_bfloat16* __restrict__ dz16, int64_t lddz16,
+                             const double* __restrict__ tlogt) {
   auto EXPF = [](float x) { return FAST ? fast_exp(x) : expf(x); };
   auto LOGF = [](float x) { return FAST ? fast_log(x) : logf(x); };
   extern __shared__ __align__(16) float sz[];           // two rows of logits
@@ -310,8 +315,9 @@ softmax_kl_persistent_kernel(const float* __restrict__ z, int64_t ldz, const flo
     }
     else asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    const float4* s4 = reinterpret_cast<const float4*>(sz) + size_t(buf) * n4;
-    const float4* t4 = reinterpret_cast<const float4*>(target + int64_t(target_rows ? target_rows[r] : r) * ldt);
+    float4* s4 = reinterpret_cast<float4*>(sz) + size_t(buf) * n4;
+    const int64_t trow = target_rows ? target_rows[r] : r;
+    const float4* t4 = reinterpret_cast<const float4*>(target + trow * ldt);
 
     // row maximum and sum of exponentials in ONE sweep and ONE block reduction: every thread keeps (m, s) with
     // s = sum exp(v - m) over its elements, rescaling s when m grows; pairs merge the same way
@@ -349,24 +355,31 @@ softmax_kl_persistent_kernel(const float* __restrict__ z, int64_t ldz, const flo
     const float inv_sum = 1.f / sumexp;
     const float lse = mx + LOGF(sumexp);
     const float log_eps = -16.11809565095832f;               // log(1e-7)
+    // sweep 2: loss = sum t' (log t' - log q'), S = sum of t' over the cards whose q survives the clip; the logit in
+    // shared memory is replaced by e = exp(z - max) on the way (each thread rewrites only what it read itself)
     float loss = 0.f, sun = 0.f;
     for (int i = threadIdx.x; i < n4; i += KLP_THREADS) {
       const float4 v = s4[i];
       const float4 t = __ldg(t4 + i);
       const float zz[4] = {v.x, v.y, v.z, v.w}, tt[4] = {t.x, t.y, t.z, t.w};
+      float ee[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float q = EXPF(zz[k] - mx) * inv_sum;
+        ee[k] = EXPF(zz[k] - mx);
+        const float q = ee[k] * inv_sum;
         const float tc = fminf(fmaxf(tt[k], KERAS_EPS), 1.f);
         const bool un = (q >= KERAS_EPS) && (q <= 1.f);
         const float logq = q >= KERAS_EPS ? fminf(zz[k] - lse, 0.f) : log_eps;   // log(clip(q, 1e-7, 1))
-        loss += tc * (LOGF(tc) - logq);
+        if (tlogt) loss -= tc * logq;
+        else loss += tc * (LOGF(tc) - logq);
         sun += un ? tc : 0.f;
       }
+      s4[i] = make_float4(ee[0], ee[1], ee[2], ee[3]);
     }
     const float2 ls = block_sum2_p(loss, sun, red);
-    if (threadIdx.x == 0) row_loss[r] = double(ls.x);
+    if (threadIdx.x == 0) row_loss[r] = tlogt ? tlogt[trow] + double(ls.x) : double(ls.x);
     const float S = ls.y;
+    const float qs = inv_sum * S * grad_scale;            // dz = (q S - t' 1[unclipped]) scale = e (S scale / sum) - ...
     float4* d4 = dz16 ? nullptr : reinterpret_cast<float4*>(dz + int64_t(r) * lddz);
     uint2* d16 = dz16 ? reinterpret_cast<uint2*>(dz16 + int64_t(r) * lddz16) : nullptr;   // bf16 dlogits ("bf16" mode)
 #pragma unroll
@@ -375,16 +388,16 @@ softmax_kl_persistent_kernel(const float* __restrict__ z, int64_t ldz, const flo
       if (i >= p4) break;
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
       if (i < n4) {
-        const float4 v = s4[i];
+        const float4 v = s4[i];                             // e = exp(z - max), left there by sweep 2
         const float4 t = __ldg(t4 + i);
-        const float zz[4] = {v.x, v.y, v.z, v.w}, tt[4] = {t.x, t.y, t.z, t.w};
+        const float ev[4] = {v.x, v.y, v.z, v.w}, tt[4] = {t.x, t.y, t.z, t.w};
         float gg[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float q = EXPF(zz[e] - mx) * inv_sum;
+          const float q = ev[e] * inv_sum;
           const float tc = fminf(fmaxf(tt[e], KERAS_EPS), 1.f);
           const bool un = (q >= KERAS_EPS) && (q <= 1.f);
-          gg[e] = (q * S - (un ? tc : 0.f)) * grad_scale;
+          gg[e] = FAST ? fmaf(ev[e], qs, un ? -tc * grad_scale : 0.f) : (q * S - (un ? tc : 0.f)) * grad_scale;
           if (round_tf32) gg[e] = rn_tf32(gg[e]);
         }
         g = make_float4(gg[0], gg[1], gg[2], gg[3]);
@@ -410,6 +423,21 @@ softmax_kl_persistent_kernel(const float* __restrict__ z, int64_t ldz, const flo
       }
     }
   }
+}
+
+// sum_c t'_c log t'_c, t' = clip(t, 1e-7, 1), of every row of the target matrix (M-hat), in float64: the part of the
+// Keras KLD that does not depend on the model.  One CTA per row; built once per graph.
+__global__ void __launch_bounds__(256)
+kl_target_table_kernel(const float* __restrict__ target, int64_t ldt, int32_t num_cards, double* __restrict__ out) {
+  __shared__ double red[32];
+  const float* tr = target + int64_t(blockIdx.x) * ldt;
+  double s = 0.0;
+  for (int c = threadIdx.x; c < num_cards; c += blockDim.x) {
+    const double tc = double(fminf(fmaxf(tr[c], KERAS_EPS), 1.f));
+    s += tc * log(tc);
+  }
+  s = block_sum_double(s, red);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;
 }
 
 // loss[0] = bce mean, loss[1] = kl mean, loss[2] = bce + reg*kl   (fixed summation order)
@@ -626,13 +654,22 @@ int cc_softmax_kl_fwd_bwd(const float* z, int64_t ldz, const float* target, int6
                           int32_t rows, int32_t num_cards, int32_t ncols_pad, double grad_scale, float* dz,
                           int64_t lddz, double* row_loss, int round_tf32, float* dbias, void* stream) {
   return cc_softmax_kl_fwd_bwd_ex(z, ldz, target, ldt, target_rows, rows, num_cards, ncols_pad, grad_scale, dz, lddz, row_loss,
-                                  round_tf32, dbias, nullptr, 0, stream);
+                                  round_tf32, dbias, nullptr, 0, nullptr, stream);
+}
+
+int cc_kl_target_table(const float* target, int64_t ldt, int32_t target_rows, int32_t num_cards, double* tlogt, void* stream) {
+  CC_REQUIRE(target && tlogt && target_rows >= 0 && num_cards > 0 && ldt >= num_cards, "cc_kl_target_table: bad arguments");
+  if (target_rows == 0) return CC_OK;
+  kl_target_table_kernel<<<target_rows, 256, 0, as_stream(stream)>>>(target, ldt, num_cards, tlogt);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
 }
 
 int cc_softmax_kl_fwd_bwd_ex(const float* z, int64_t ldz, const float* target, int64_t ldt, const int32_t* target_rows,
                              int32_t rows, int32_t num_cards, int32_t ncols_pad, double grad_scale, float* dz,
                              int64_t lddz, double* row_loss, int round_tf32, float* dbias, void* dz_bf16, int64_t lddz_bf16,
-                             void* stream) {
+                             const double* tlogt, void* stream) {
+  CC_REQUIRE(!tlogt || dbias, "cc_softmax_kl_fwd_bwd: the target table is used by the persistent kernel only (dbias != NULL)");
   CC_REQUIRE(z && target && row_loss, "cc_softmax_kl_fwd_bwd: null pointer");
   CC_REQUIRE(!dz_bf16 || (dbias && lddz_bf16 >= ncols_pad && lddz_bf16 % 4 == 0 && (reinterpret_cast<uintptr_t>(dz_bf16) & 7) == 0),
              "cc_softmax_kl_fwd_bwd: bf16 dlogits need the persistent kernel (dbias != NULL), lddz_bf16 %% 4 == 0 >= ncols_pad");
@@ -653,12 +690,12 @@ int cc_softmax_kl_fwd_bwd_ex(const float* z, int64_t ldz, const float* target, i
       CC_CHECK_CUDA(cudaFuncSetAttribute(softmax_kl_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       softmax_kl_persistent_kernel<true><<<grid, KLP_THREADS, smem, st>>>(z, ldz, target, ldt, target_rows, rows, num_cards,
                                                                          ncols_pad, float(grad_scale), dz, lddz, row_loss,
-                                                                         dz16 ? 0 : 1, dbias, dz16, lddz_bf16);
+                                                                         dz16 ? 0 : 1, dbias, dz16, lddz_bf16, tlogt);
     } else {
       CC_CHECK_CUDA(cudaFuncSetAttribute(softmax_kl_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       softmax_kl_persistent_kernel<false><<<grid, KLP_THREADS, smem, st>>>(z, ldz, target, ldt, target_rows, rows, num_cards,
                                                                           ncols_pad, float(grad_scale), dz, lddz, row_loss, 0, dbias,
-                                                                          dz16, lddz_bf16);
+                                                                          dz16, lddz_bf16, tlogt);
     }
     CC_CHECK_LAUNCH();
     return CC_OK;

@@ -150,6 +150,14 @@ class DAEEngine:
         ws = max(lib.cc_colsum_workspace_bytes(T, max(self.cpad, max(HIDDEN))), 1024)
         self.cs_ws = torch.empty(ws // 4, dtype=f32, device=d)
 
+    def kl_table(self):
+        """sum_c t' log t' of every row of M-hat (float64 (C,)): the model-independent half of the KLD, built on first
+        use (one pass over M-hat) and kept with the engine -- the per-step kernel then needs no logarithm per element."""
+        if getattr(self, "_kl_table", None) is None:
+            self._kl_table = torch.empty(self.C, dtype=torch.float64, device=self.dev)
+            call("cc_kl_target_table", ptr(self.mhat), self.mhat.stride(0), self.C, self.C, ptr(self._kl_table), stream_ptr())
+        return self._kl_table
+
     # -- per-kernel CUDA-event timing (bench.py's roofline leg) ------------------------
     def enable_kernel_timing(self, on=True):
         self.prof = {} if on else None
@@ -326,12 +334,13 @@ class DAEEngine:
                     call("cc_softmax_kl_fwd_bwd_ex", ptr(self.z2), self.z2.stride(0), ptr(self.mhat), self.mhat.stride(0),
                          ptr(self.reg_rows), R, self.C, self.cpad, self.reg / float(self.global_R), None, 0,
                          ptr(self.row_kl), 1, ptr(G(dec_names("reg")[3] + "/bias")), ptr(self.dz2_16),
-                         self.dz2_16.stride(0), st)
+                         self.dz2_16.stride(0), ptr(self.kl_table()), st)
                 else:
-                    call("cc_softmax_kl_fwd_bwd", ptr(self.z2), self.z2.stride(0), ptr(self.mhat), self.mhat.stride(0),
+                    call("cc_softmax_kl_fwd_bwd_ex", ptr(self.z2), self.z2.stride(0), ptr(self.mhat), self.mhat.stride(0),
                          ptr(self.reg_rows), R, self.C, self.cpad, self.reg / float(self.global_R), ptr(self.z2),
                          self.z2.stride(0), ptr(self.row_kl), int(tc),
-                         ptr(G(dec_names("reg")[3] + "/bias")) if reg_dbias_fused else None, st)
+                         ptr(G(dec_names("reg")[3] + "/bias")) if reg_dbias_fused else None, None, 0,
+                         ptr(self.kl_table()) if reg_dbias_fused else None, st)
             n_launch += 1
         call("cc_loss_finalize", ptr(bce_rows), bce_n, float(self.global_B) * float(self.C), ptr(self.row_kl), R,
              float(self.global_R), self.reg, ptr(self.loss3), st)

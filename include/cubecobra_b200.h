@@ -238,11 +238,16 @@ int cc_softmax_kl_fwd_bwd(const float* z, int64_t ldz, const float* target, int6
                           int32_t rows, int32_t num_cards, int32_t ncols_pad, double grad_scale, float* dz,
                           int64_t lddz, double* row_loss, int round_tf32, float* dbias, void* stream);
 /* Same with the dlogits written as bf16 into dz_bf16 [rows][lddz_bf16] instead of dz (needs dbias != NULL, i.e. the
- * persistent kernel); dz may then be NULL. */
+ * persistent kernel); dz may then be NULL.  tlogt (nullable, float64 [rows of target]; persistent kernel only): the
+ * table written by cc_kl_target_table -- with it the kernel evaluates no logarithm per element. */
 int cc_softmax_kl_fwd_bwd_ex(const float* z, int64_t ldz, const float* target, int64_t ldt, const int32_t* target_rows,
                              int32_t rows, int32_t num_cards, int32_t ncols_pad, double grad_scale, float* dz,
                              int64_t lddz, double* row_loss, int round_tf32, float* dbias, void* dz_bf16,
-                             int64_t lddz_bf16, void* stream);
+                             int64_t lddz_bf16, const double* tlogt, void* stream);
+/* tlogt[i] = sum_c t' log t', t' = clip(target[i][c], 1e-7, 1), float64: the model-independent half of Keras'
+ * kullback_leibler_divergence (src/ml/train.py:85) for every row of M-hat; built once per graph. */
+int cc_kl_target_table(const float* target, int64_t ldt, int32_t target_rows, int32_t num_cards, double* tlogt,
+                       void* stream);
 /* out3 (float64 [3]) = { sum(bce_rows)/bce_div, sum(kl_rows)/kl_div, bce + reg*kl } */
 int cc_loss_finalize(const double* bce_rows, int32_t nb, double bce_div, const double* kl_rows, int32_t nr,
                      double kl_div, double reg, double* out3, void* stream);

@@ -134,6 +134,20 @@ def test_loss_kernels_vs_oracle():
             assert (dz_b[:, c:] == 0).all()
             ref_db = dz_b[:, :c].double().sum(0)
             assert (db.double() - ref_db).abs().max().item() < 1e-6 * ref_db.abs().max().item() + 1e-12
+            # with the per-target-row table sum t' log t' (cc_kl_target_table) the kernel evaluates no logarithm per
+            # element: same dlogits bit for bit, row losses equal to rounding (and closer to the float64 oracle)
+            table = torch.zeros(c, dtype=torch.float64, device="cuda")
+            E.call("cc_kl_target_table", E.ptr(tt), c, c, c, E.ptr(table), E.stream_ptr())
+            tcl = np.clip(t.astype(np.float32).astype(np.float64), 1e-7, 1.0)
+            assert np.abs(table.cpu().numpy() - (tcl * np.log(tcl)).sum(1)).max() < 1e-12
+            dz_c = torch.full((reps * b, cpad), 9.0, device="cuda"); rl_c = torch.zeros_like(rl_a)
+            db_c = torch.zeros(c, device="cuda")
+            E.call("cc_softmax_kl_fwd_bwd_ex", E.ptr(zr), cpad, E.ptr(tt), c, E.ptr(rr), reps * b, c, cpad, 0.1 / b,
+                   E.ptr(dz_c), cpad, E.ptr(rl_c), fast, E.ptr(db_c), None, 0, E.ptr(table), E.stream_ptr())
+            assert torch.equal(dz_c, dz_b)
+            assert torch.allclose(rl_c, rl_b, rtol=2e-6)
+            kl_ref = od.kld_np(t32, q)
+            assert abs(rl_c[:b].sum().item() / b - kl_ref) <= abs(rl_b[:b].sum().item() / b - kl_ref) + 1e-7 * abs(kl_ref)
 
 
 def test_adam_matches_tf_style_oracle():
