@@ -45,6 +45,9 @@ def test_n_gpu_step_equals_one_gpu_step(precision):
     r = _torchrun(n, ["-m", "cubecobrarecommender_b200.dp_check", "--precision", precision, "--steps", "3"])
     assert r.stdout.strip(), r.stderr[-3000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
+    if os.environ.get("CC_SAVE_JSON"):                      # evidence for profiles/: the checker's whole verdict
+        with open(os.path.join(os.environ["CC_SAVE_JSON"], f"dp_check_n{n}_{precision}.json"), "w") as f:
+            json.dump(out, f)
     assert out["world"] == n
     ran = [m for m, v in out["modes"].items() if "skipped" not in v]
     assert "p2p_unicast" in ran and "nccl" in ran
@@ -63,6 +66,9 @@ def test_bench_strong_scaling_and_check_leg():
                       "--no-extras", "--no-cpu-baseline"])
     assert r.returncode == 0, r.stderr[-3000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
+    if os.environ.get("CC_SAVE_JSON"):
+        with open(os.path.join(os.environ["CC_SAVE_JSON"], f"bench_strong_check_n{n}.json"), "w") as f:
+            json.dump(line, f)
     assert line["scaling"] == "strong" and line["n_gpus"] == n
     assert line["config"]["global_batch"] == 4096 and line["config"]["batch_per_gpu"] == 4096 // n
     assert line["check"]["violations"] == []
