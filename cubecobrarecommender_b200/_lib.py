@@ -35,6 +35,9 @@ SIGNATURES = {
     "cc_row_normalise": (I, [P, I64, I32, P, I64, P, I64, P, I, D, P]),
     "cc_col_mass_workspace_bytes": (I64, [I32]),
     "cc_col_mass": (I, [P, I64, I32, P, P, P, P]),
+    "cc_row_normalise_rows": (I, [P, I64, I32, I32, I32, P, I64, P, I64, P, I, D, P]),
+    "cc_col_mass_rows": (I, [P, I64, I32, I32, I32, P, P, P, P]),
+    "cc_col_mass_scale": (I, [P, I32, P]),
     "cc_create_adjacency_matrix_host": (I, [P, P, I64, I32, I, D, P, P]),
     # (2) scoring / top-N
     "cc_pairwise_leaf_count": (I64, [I64]),

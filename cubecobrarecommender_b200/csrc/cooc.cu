@@ -144,14 +144,16 @@ template <bool VEC>
 __global__ void __launch_bounds__(256)
 row_normalise_kernel(const int32_t* __restrict__ counts, int64_t ld, int32_t num_cards,
                      double* __restrict__ m64, int64_t ld_m, float* __restrict__ mhat, int64_t ld_mhat,
-                     double* __restrict__ rowsum, int has_force_diag, double force_diag) {
-  const int i = blockIdx.x;
-  const int32_t* row = counts + int64_t(i) * ld;
+                     double* __restrict__ rowsum, int has_force_diag, double force_diag, int32_t row0) {
+  // row0 != 0: the buffers hold the row block [row0, row0 + gridDim.x) of the matrices (a rank's shard of a
+  // reduce-scattered build); local row blockIdx.x is card i = row0 + blockIdx.x
+  const int i = row0 + blockIdx.x;
+  const int32_t* row = counts + int64_t(blockIdx.x) * ld;
   const int32_t d = row[i];
   const double dd = double(d);
   __shared__ double red[8];
   double s = 0.0;
-  double* mrow = m64 ? m64 + int64_t(i) * ld_m : nullptr;
+  double* mrow = m64 ? m64 + int64_t(blockIdx.x) * ld_m : nullptr;
   const int nvec = VEC ? (num_cards >> 2) : 0;
   for (int q = threadIdx.x; q < nvec; q += blockDim.x) {
     const int4 c4 = *reinterpret_cast<const int4*>(row + 4 * q);
@@ -185,11 +187,11 @@ row_normalise_kernel(const int32_t* __restrict__ counts, int64_t ld, int32_t num
   }
   __syncthreads();
   const double total = red[0];
-  if (threadIdx.x == 0 && rowsum) rowsum[i] = total;
+  if (threadIdx.x == 0 && rowsum) rowsum[blockIdx.x] = total;
   if (mhat) {
     const double scale = d != 0 ? 1.0 / (dd * total) : 1.0 / total;     // y[i,j]/rowsum = cnt * scale off the diagonal
     const float diag = float(1.0 / total);
-    float* hrow = mhat + int64_t(i) * ld_mhat;
+    float* hrow = mhat + int64_t(blockIdx.x) * ld_mhat;
     for (int q = threadIdx.x; q < nvec; q += blockDim.x) {
       const int4 c4 = *reinterpret_cast<const int4*>(row + 4 * q);
       float4 o = make_float4(float(double(c4.x) * scale), float(double(c4.y) * scale), float(double(c4.z) * scale),
@@ -210,14 +212,16 @@ constexpr int COL_ROWS = 256;
 // element (the kernel was bound by the FP64 divider, not by HBM)
 __global__ void __launch_bounds__(128)
 col_mass_partial_kernel(const int32_t* __restrict__ counts, int64_t ld, int32_t num_cards,
-                        const double* __restrict__ rowsum, double* __restrict__ partial) {
+                        const double* __restrict__ rowsum, double* __restrict__ partial, int32_t row0, int32_t nrows) {
+  // counts / rowsum hold the row block [row0, row0 + nrows) (row0 = 0, nrows = num_cards: the whole matrix); i below
+  // is the LOCAL row, its card (= the column of its diagonal element) is row0 + i
   __shared__ double s_scale[COL_ROWS], s_diag[COL_ROWS];
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i0 = blockIdx.y * COL_ROWS;
-  const int i1 = min(i0 + COL_ROWS, num_cards);
+  const int i1 = min(i0 + COL_ROWS, nrows);
   for (int r = threadIdx.x; r < i1 - i0; r += blockDim.x) {
     const int i = i0 + r;
-    const int32_t d = counts[int64_t(i) * ld + i];
+    const int32_t d = counts[int64_t(i) * ld + row0 + i];
     const double rs = rowsum[i];
     s_diag[r] = 1.0 / rs;
     s_scale[r] = d != 0 ? 1.0 / (double(d) * rs) : 1.0 / rs;
@@ -228,7 +232,7 @@ col_mass_partial_kernel(const int32_t* __restrict__ counts, int64_t ld, int32_t 
 #pragma unroll 8
   for (int i = i0; i < i1; ++i) {
     const double c = double(counts[int64_t(i) * ld + j]);
-    s += (j == i) ? s_diag[i - i0] : c * s_scale[i - i0];
+    s += (j == row0 + i) ? s_diag[i - i0] : c * s_scale[i - i0];
   }
   partial[int64_t(blockIdx.y) * num_cards + j] = s;
 }
@@ -305,7 +309,17 @@ int cc_cooc_count(const uint32_t* bits, int64_t num_cubes, int32_t num_cards, in
 int cc_row_normalise(const int32_t* counts, int64_t ld, int32_t num_cards, double* m64, int64_t ld_m,
                      float* mhat, int64_t ld_mhat, double* rowsum, int has_force_diag, double force_diag,
                      void* stream) {
+  return cc_row_normalise_rows(counts, ld, 0, num_cards, num_cards, m64, ld_m, mhat, ld_mhat, rowsum, has_force_diag,
+                               force_diag, stream);
+}
+
+int cc_row_normalise_rows(const int32_t* counts, int64_t ld, int32_t row0, int32_t nrows, int32_t num_cards, double* m64,
+                          int64_t ld_m, float* mhat, int64_t ld_mhat, double* rowsum, int has_force_diag,
+                          double force_diag, void* stream) {
   CC_REQUIRE(counts && num_cards > 0 && ld >= num_cards, "cc_row_normalise: bad arguments");
+  CC_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= num_cards, "cc_row_normalise: row block [%d, %d) outside [0, %d)",
+             row0, row0 + nrows, num_cards);
+  if (nrows == 0) return CC_OK;
   CC_REQUIRE(!m64 || ld_m >= num_cards, "cc_row_normalise: ld_m too small");
   CC_REQUIRE(!mhat || ld_mhat >= num_cards, "cc_row_normalise: ld_mhat too small");
   // 16-byte vector path when every row of every buffer starts 16-byte aligned
@@ -313,11 +327,11 @@ int cc_row_normalise(const int32_t* counts, int64_t ld, int32_t num_cards, doubl
                    (!m64 || (ld_m % 2 == 0 && (reinterpret_cast<uintptr_t>(m64) & 15) == 0)) &&
                    (!mhat || (ld_mhat % 4 == 0 && (reinterpret_cast<uintptr_t>(mhat) & 15) == 0));
   if (vec)
-    row_normalise_kernel<true><<<num_cards, 256, 0, as_stream(stream)>>>(counts, ld, num_cards, m64, ld_m, mhat, ld_mhat,
-                                                                        rowsum, has_force_diag, force_diag);
+    row_normalise_kernel<true><<<nrows, 256, 0, as_stream(stream)>>>(counts, ld, num_cards, m64, ld_m, mhat, ld_mhat,
+                                                                    rowsum, has_force_diag, force_diag, row0);
   else
-    row_normalise_kernel<false><<<num_cards, 256, 0, as_stream(stream)>>>(counts, ld, num_cards, m64, ld_m, mhat,
-                                                                         ld_mhat, rowsum, has_force_diag, force_diag);
+    row_normalise_kernel<false><<<nrows, 256, 0, as_stream(stream)>>>(counts, ld, num_cards, m64, ld_m, mhat,
+                                                                     ld_mhat, rowsum, has_force_diag, force_diag, row0);
   CC_CHECK_LAUNCH();
   return CC_OK;
 }
@@ -328,15 +342,31 @@ int64_t cc_col_mass_workspace_bytes(int32_t num_cards) {
 
 int cc_col_mass(const int32_t* counts, int64_t ld, int32_t num_cards, const double* rowsum, double* workspace,
                 double* neg_sampler, void* stream) {
-  CC_REQUIRE(counts && rowsum && workspace && neg_sampler, "cc_col_mass: null pointer");
-  const int chunks = ceil_div(num_cards, COL_ROWS);
+  int rc = cc_col_mass_rows(counts, ld, 0, num_cards, num_cards, rowsum, workspace, neg_sampler, stream);
+  if (rc != CC_OK) return rc;
+  return cc_col_mass_scale(neg_sampler, num_cards, stream);
+}
+
+// Row-block form for a reduce-scattered build: col_mass[j] = sum over the block's rows of M-hat[i][j], NOT yet
+// normalised -- the caller sums the blocks' vectors over the ranks (all_reduce of C doubles), then cc_col_mass_scale.
+int cc_col_mass_rows(const int32_t* counts, int64_t ld, int32_t row0, int32_t nrows, int32_t num_cards, const double* rowsum,
+                     double* workspace, double* col_mass, void* stream) {
+  CC_REQUIRE(counts && rowsum && workspace && col_mass, "cc_col_mass: null pointer");
+  CC_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= num_cards, "cc_col_mass: row block outside the matrix");
   cudaStream_t st = as_stream(stream);
+  if (nrows == 0) { CC_CHECK_CUDA(cudaMemsetAsync(col_mass, 0, size_t(num_cards) * sizeof(double), st)); return CC_OK; }
+  const int chunks = ceil_div(nrows, COL_ROWS);
   dim3 grid(ceil_div(num_cards, 128), chunks);
-  col_mass_partial_kernel<<<grid, 128, 0, st>>>(counts, ld, num_cards, rowsum, workspace);
+  col_mass_partial_kernel<<<grid, 128, 0, st>>>(counts, ld, num_cards, rowsum, workspace, row0, nrows);
   CC_CHECK_LAUNCH();
-  col_mass_final_kernel<<<ceil_div(num_cards, 256), 256, 0, st>>>(workspace, chunks, num_cards, neg_sampler);
+  col_mass_final_kernel<<<ceil_div(num_cards, 256), 256, 0, st>>>(workspace, chunks, num_cards, col_mass);
   CC_CHECK_LAUNCH();
-  col_mass_scale_kernel<<<1, 1024, 0, st>>>(neg_sampler, num_cards);
+  return CC_OK;
+}
+
+int cc_col_mass_scale(double* col_mass, int32_t num_cards, void* stream) {
+  CC_REQUIRE(col_mass && num_cards > 0, "cc_col_mass_scale: bad arguments");
+  col_mass_scale_kernel<<<1, 1024, 0, as_stream(stream)>>>(col_mass, num_cards);
   CC_CHECK_LAUNCH();
   return CC_OK;
 }

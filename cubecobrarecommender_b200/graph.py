@@ -105,6 +105,63 @@ def normalise(counts: torch.Tensor, *, want_m64=True, want_mhat=True, want_neg=T
     return CoocGraph(c, counts, m64, mhat, rowsum, neg)
 
 
+def normalise_rows(counts_rows: torch.Tensor, row0: int, num_cards: int, *, want_m64=False, want_mhat=True,
+                   mhat: torch.Tensor | None = None, group=None) -> CoocGraph:
+    """Row block ``[row0, row0 + nrows)`` of M / M-hat from the matching block of the (summed) int32 counts, plus the
+    FULL negative-sampling distribution (the blocks' column masses are all_reduced: C doubles).  The sharded form of
+    :func:`normalise` for a build whose counts were reduce-scattered by row block."""
+    import torch.distributed as dist
+    nrows = counts_rows.shape[0]
+    dev = counts_rows.device
+    m64 = torch.empty((nrows, num_cards), dtype=torch.float64, device=dev) if want_m64 else None
+    if mhat is None and want_mhat:
+        mhat = torch.empty((nrows, num_cards), dtype=torch.float32, device=dev)
+    rowsum = torch.empty(max(nrows, 1), dtype=torch.float64, device=dev)
+    st = stream_ptr()
+    call("cc_row_normalise_rows", ptr(counts_rows), counts_rows.stride(0), int(row0), nrows, num_cards, ptr(m64),
+         num_cards, ptr(mhat), mhat.stride(0) if mhat is not None else 0, ptr(rowsum), 0, 0.0, st)
+    ws = torch.empty(_lib.load().cc_col_mass_workspace_bytes(num_cards) // 8, dtype=torch.float64, device=dev)
+    neg = torch.empty(num_cards, dtype=torch.float64, device=dev)
+    call("cc_col_mass_rows", ptr(counts_rows), counts_rows.stride(0), int(row0), nrows, num_cards, ptr(rowsum), ptr(ws),
+         ptr(neg), st)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(neg, op=dist.ReduceOp.SUM, group=group)
+    call("cc_col_mass_scale", ptr(neg), num_cards, st)
+    return CoocGraph(num_cards, counts_rows, m64, mhat, rowsum[:nrows], neg)
+
+
+def reduce_scatter_counts(counts: torch.Tensor, rank: int, world: int, group=None):
+    """Sum the ranks' private (C, ld) int32 counts and leave rank r with the row block ``[r*blk, min((r+1)*blk, C))``,
+    ``blk = ceil(C / world)``, of the sum -- IN PLACE in its own buffer (returned as a view, with the block's first
+    row): half the NVLink traffic of an all_reduce and no replicated (C, C) result.  Exact (integer sum).  The
+    collective runs on ``world`` equal blocks; rows >= C of the last one are zero padding (``alloc_counts``)."""
+    import torch.distributed as dist
+    c, ld = counts.shape[0], counts.stride(0)
+    if world == 1:
+        return counts, 0
+    blk = -(-c // world)
+    flat = counts._base if counts._base is not None else counts
+    flat = flat.view(-1)
+    need = blk * world * ld
+    if flat.numel() < need:
+        raise ValueError(f"reduce_scatter_counts: the counts buffer needs {blk * world} rows of storage (has {flat.numel() // ld}); "
+                         f"allocate it with graph.alloc_counts(num_cards, world)")
+    # equal blocks of `blk` rows: block r = rows [r*blk, (r+1)*blk) (rows >= C are zero padding)
+    out = flat[rank * blk * ld:(rank + 1) * blk * ld]
+    dist.reduce_scatter_tensor(out, flat[:need], op=dist.ReduceOp.SUM, group=group)
+    r0 = rank * blk
+    nrows = max(0, min(blk, c - r0))
+    return out.view(blk, ld)[:nrows, :c], r0
+
+
+def alloc_counts(num_cards: int, world: int, device="cuda") -> torch.Tensor:
+    """int32 (C, ld) counts whose storage is padded to ``world`` equal row blocks (see reduce_scatter_counts)."""
+    ld = (num_cards + 3) // 4 * 4
+    blk = -(-num_cards // world)
+    buf = torch.zeros((blk * world, ld), dtype=torch.int32, device=device)
+    return buf[:num_cards, :num_cards] if ld != num_cards else buf[:num_cards]
+
+
 def build_graph(csr: CubeCSR, device="cuda", *, allreduce=True, group=None, method="auto", **kw) -> CoocGraph:
     """Counts of this rank's cubes (+ all_reduce when torch.distributed is initialised with
     more than one rank, i.e. the cubes are sharded) and the normalised matrices."""

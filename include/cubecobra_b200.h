@@ -68,10 +68,21 @@ int cc_cooc_count_tc(const int64_t* indptr, const int32_t* indices, int64_t num_
 int cc_row_normalise(const int32_t* counts, int64_t ld, int32_t num_cards, double* m64, int64_t ld_m,
                      float* mhat, int64_t ld_mhat, double* rowsum, int has_force_diag, double force_diag,
                      void* stream);
+/* The same on a ROW BLOCK: counts / m64 / mhat / rowsum hold rows [row0, row0 + nrows) of the (C, C) matrices -- a
+ * rank's shard after the int32 counts of a cube-sharded build were reduce-scattered by row block over NVLink instead
+ * of all_reduced (a row of M needs nothing but its own counts row, whose diagonal element sits in column row0 + i). */
+int cc_row_normalise_rows(const int32_t* counts, int64_t ld, int32_t row0, int32_t nrows, int32_t num_cards, double* m64,
+                          int64_t ld_m, float* mhat, int64_t ld_mhat, double* rowsum, int has_force_diag,
+                          double force_diag, void* stream);
 int64_t cc_col_mass_workspace_bytes(int32_t num_cards);
 /* neg_sampler[j] = sum_i Mhat[i][j] / sum(Mhat), float64, deterministic order. */
 int cc_col_mass(const int32_t* counts, int64_t ld, int32_t num_cards, const double* rowsum, double* workspace,
                 double* neg_sampler, void* stream);
+/* Row-block form: col_mass[j] = sum of M-hat[i][j] over the block's rows, not normalised; the blocks' vectors are summed
+ * over the ranks (an all_reduce of C doubles) and cc_col_mass_scale divides by the total (generator.py:30). */
+int cc_col_mass_rows(const int32_t* counts, int64_t ld, int32_t row0, int32_t nrows, int32_t num_cards, const double* rowsum,
+                     double* workspace, double* col_mass, void* stream);
+int cc_col_mass_scale(double* col_mass, int32_t num_cards, void* stream);
 /* Host-buffer drop-in for utils.create_adjacency_matrix: CSR in, float64 (C, C) out
  * (and the int32 counts if counts_host != NULL).  H2D + kernels + D2H inside the call. */
 int cc_create_adjacency_matrix_host(const int64_t* indptr_host, const int32_t* indices_host, int64_t num_cubes,

@@ -361,3 +361,35 @@ def test_scale_up_card_count_properties():
     sub_ip = torch.cat([torch.zeros(1, dtype=torch.int64, device="cuda"), sub_len.cumsum(0)])
     ref = G.count_cooccurrence(sub_ip, b[keep].contiguous(), k, 2048, method="popcount")
     assert torch.equal(cnt[:2048, :2048], ref)
+
+
+@pytest.mark.parametrize("c,world", [(515, 4), (1000, 8), (64, 3)])
+def test_row_block_normalise_equals_whole_matrix(c, world):
+    """The reduce-scattered form of the sharded build (configs[4]): every rank normalises only its row block of the summed
+    counts (cc_row_normalise_rows / cc_col_mass_rows / cc_col_mass_scale).  Emulated on one GPU: the blocks'
+    M / M-hat / row sums are bit-identical to the whole-matrix pass, the summed column masses give the same sampler."""
+    from cubecobrarecommender_b200._lib import call, ptr, stream_ptr
+    ip, ix = synth_cubes_csr(300, c, size_lo=3, size_hi=min(c, 90), seed=c + world)
+    csr = CubeCSR(ip, ix, c)
+    indptr, indices = G.upload_csr(csr, "cuda")
+    counts = G.alloc_counts(c, world)
+    G.count_cooccurrence(indptr, indices, csr.num_cubes, c, counts=counts)
+    whole = G.normalise(counts, want_m64=True, want_mhat=True, want_neg=True)
+    assert np.array_equal(whole.counts.cpu().numpy(), og.cooc_counts(ip, ix, c))
+    blk = -(-c // world)
+    mass = torch.zeros(c, dtype=torch.float64, device="cuda")
+    for r in range(world):
+        r0 = r * blk
+        nrows = max(0, min(blk, c - r0))
+        part = G.normalise_rows(counts[r0:r0 + nrows], r0, c, want_m64=True)          # (no process group: no all_reduce)
+        assert torch.equal(part.m64, whole.m64[r0:r0 + nrows])
+        assert torch.equal(part.mhat, whole.mhat[r0:r0 + nrows, :c])
+        assert torch.equal(part.rowsum, whole.rowsum[r0:r0 + nrows])
+        # normalise_rows scales its own block's masses; undo that to emulate the all_reduce of the raw masses
+        ws = torch.empty(G._lib.load().cc_col_mass_workspace_bytes(c) // 8, dtype=torch.float64, device="cuda")
+        raw = torch.empty(c, dtype=torch.float64, device="cuda")
+        call("cc_col_mass_rows", ptr(counts[r0:r0 + nrows]), counts.stride(0), r0, nrows, c, ptr(part.rowsum), ptr(ws), ptr(raw),
+             stream_ptr())
+        mass += raw
+    call("cc_col_mass_scale", ptr(mass), c, stream_ptr())
+    assert (mass - whole.neg_sampler).abs().max().item() < 1e-14
