@@ -82,6 +82,7 @@ SIGNATURES = {
     "cc_softmax_kl_fwd_bwd": (I, [P, I64, P, I64, P, I32, I32, I32, D, P, I64, P, I, P, P]),
     "cc_softmax_kl_fwd_bwd_ex": (I, [P, I64, P, I64, P, I32, I32, I32, D, P, I64, P, I, P, P, I64, P, P]),
     "cc_kl_target_table": (I, [P, I64, I32, I32, P, P]),
+    "cc_softmax_kl_set_variant": (I, [I]),
     "cc_convert_f32_bf16": (I, [P, I64, P, I64, I32, I32, P]),
     "cc_loss_finalize": (I, [P, I32, D, P, I32, D, D, P, P]),
     "cc_adam_step_p2p": (I, [P, P, I, I, P, P, I64, I64, P, F, F, F, F, P, P, P]),

@@ -425,6 +425,205 @@ softmax_kl_persistent_kernel(const float* __restrict__ z, int64_t ldz, const flo
   }
 }
 
+// Register-resident form (the shipped one for C <= 4 * KLR_ITERS * KLR_THREADS = 22 528 cards).  The 1024-thread kernel
+// above has ONE 16-byte target load in flight per thread (16 KB per SM) and re-reads the target row in its third sweep:
+// it is bound by load latency, not by HBM or by the MUFU pipe (measured 0.30 ms for 1.03 GB = 52% of the HBM peak, and
+// unchanged when three of its four MUFU ops per element were removed).  Here a CTA has 512 threads with up to 128
+// registers each: a thread issues ALL of its target loads for the row (<= 11 x 16 bytes, 88 KB in flight per SM) before
+// the first sweep, keeps them in registers for sweeps 2 and 3, and keeps the bias-gradient column sums in registers
+// across rows as before.  The logits row still arrives by cp.async one row ahead, the next target row is prefetched
+// into L2.
+constexpr int KLR_THREADS = 512;
+constexpr int KLR_ITERS = 11;
+
+__device__ __forceinline__ float2 block_sum2_r(float a, float b, float2* red /* smem[16] */) {
+  a = warp_sum(a); b = warp_sum(b);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = make_float2(a, b);
+  __syncthreads();
+  float2 t = red[lane & 15];               // 16 warps; both half-warps reduce the same 16 partials
+  t.x += __shfl_xor_sync(0xffffffffu, t.x, 8); t.y += __shfl_xor_sync(0xffffffffu, t.y, 8);
+  t.x += __shfl_xor_sync(0xffffffffu, t.x, 4); t.y += __shfl_xor_sync(0xffffffffu, t.y, 4);
+  t.x += __shfl_xor_sync(0xffffffffu, t.x, 2); t.y += __shfl_xor_sync(0xffffffffu, t.y, 2);
+  t.x += __shfl_xor_sync(0xffffffffu, t.x, 1); t.y += __shfl_xor_sync(0xffffffffu, t.y, 1);
+  return t;
+}
+
+template <bool FAST, int ITERS>
+__global__ void __launch_bounds__(KLR_THREADS, 1)
+softmax_kl_regs_kernel(const float* __restrict__ z, int64_t ldz, const float* __restrict__ target, int64_t ldt,
+                       const int32_t* __restrict__ target_rows, int32_t rows, int32_t num_cards, int32_t ncols_pad,
+                       float grad_scale, float* __restrict__ dz, int64_t lddz, double* __restrict__ row_loss,
+                       int round_tf32, float* __restrict__ dbias, __nv_bfloat16* __restrict__ dz16, int64_t lddz16,
+                       const double* __restrict__ tlogt) {
+  auto EXPF = [](float x) { return FAST ? fast_exp(x) : expf(x); };
+  auto LOGF = [](float x) { return FAST ? fast_log(x) : logf(x); };
+  extern __shared__ __align__(16) float sz[];           // two rows of logits
+  __shared__ float2 red[KLR_THREADS / 32];
+  const int n4 = num_cards >> 2;
+  const int p4 = ncols_pad >> 2;
+  float4 acc[ITERS];
+#pragma unroll
+  for (int k = 0; k < ITERS; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  auto prefetch = [&](int r, int b) {
+    const float4* src = reinterpret_cast<const float4*>(z + int64_t(r) * ldz);
+    float4* dst = reinterpret_cast<float4*>(sz) + size_t(b) * n4;
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k) {
+      const int i = threadIdx.x + k * KLR_THREADS;
+      if (i < n4) {
+        const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst + i));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + i) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int buf = 0;
+  int r = blockIdx.x;
+  if (r < rows) prefetch(r, 0);
+  for (; r < rows; r += gridDim.x) {
+    const int64_t trow = target_rows ? target_rows[r] : r;
+    const float4* t4 = reinterpret_cast<const float4*>(target + trow * ldt);
+    // this row's targets: every load is issued now and lands while the logits are reduced
+    float4 tv[ITERS];
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k) {
+      const int i = threadIdx.x + k * KLR_THREADS;
+      tv[k] = i < n4 ? ld_nc_f4(t4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int rn = r + gridDim.x;
+    if (rn < rows) {
+      prefetch(rn, buf ^ 1);
+      const char* tn = reinterpret_cast<const char*>(target + int64_t(target_rows ? target_rows[rn] : rn) * ldt);
+      for (int l = threadIdx.x; l * 128 < num_cards * 4; l += KLR_THREADS)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(tn + size_t(l) * 128));
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    float4* s4 = reinterpret_cast<float4*>(sz) + size_t(buf) * n4;
+
+    // sweep 1: row maximum, then the sum of exponentials
+    float tm = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k) {
+      const int i = threadIdx.x + k * KLR_THREADS;
+      if (i < n4) {
+        const float4 v = s4[i];
+        tm = fmaxf(tm, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+      }
+    }
+    tm = warp_max(tm);
+    {
+      const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+      if (lane == 0) red[wid].x = tm;
+      __syncthreads();
+      float t = red[lane & 15].x;
+      t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 8)); t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 4));
+      t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 2)); t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 1));
+      tm = t;
+    }
+    const float mx = tm;
+    float ts = 0.f;
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k) {
+      const int i = threadIdx.x + k * KLR_THREADS;
+      if (i < n4) {
+        const float4 v = s4[i];
+        ts += (EXPF(v.x - mx) + EXPF(v.y - mx)) + (EXPF(v.z - mx) + EXPF(v.w - mx));
+      }
+    }
+    const float sumexp = block_sum2_r(ts, 0.f, red).x;
+    const float inv_sum = 1.f / sumexp;
+    const float lse = mx + LOGF(sumexp);
+    const float log_eps = -16.11809565095832f;               // log(1e-7)
+    // sweep 2: loss = sum t' (log t' - log q'), S = sum of t' over the cards whose q survives the clip.  The logit is
+    // needed one last time here (log q = z - lse); e = exp(z - max) replaces it in shared memory for sweep 3 (keeping
+    // both z and e in registers across the reduction would not fit beside the targets and the column sums)
+    float loss = 0.f, sun = 0.f;
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k) {
+      const int i = threadIdx.x + k * KLR_THREADS;
+      if (i < n4) {
+        const float4 v = s4[i];
+        const float zz[4] = {v.x, v.y, v.z, v.w};
+        const float tt[4] = {tv[k].x, tv[k].y, tv[k].z, tv[k].w};
+        float ee[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          ee[c] = EXPF(zz[c] - mx);
+          const float q = ee[c] * inv_sum;
+          const float tc = fminf(fmaxf(tt[c], KERAS_EPS), 1.f);
+          const bool un = (q >= KERAS_EPS) && (q <= 1.f);
+          const float logq = q >= KERAS_EPS ? fminf(zz[c] - lse, 0.f) : log_eps;   // log(clip(q, 1e-7, 1))
+          if (tlogt) loss -= tc * logq;
+          else loss += tc * (LOGF(tc) - logq);
+          sun += un ? tc : 0.f;
+        }
+        s4[i] = make_float4(ee[0], ee[1], ee[2], ee[3]);
+      }
+    }
+    const float2 ls = block_sum2_r(loss, sun, red);
+    if (threadIdx.x == 0) row_loss[r] = tlogt ? tlogt[trow] + double(ls.x) : double(ls.x);
+    const float S = ls.y;
+    const float qs = inv_sum * S * grad_scale;
+    float4* d4 = dz16 ? nullptr : reinterpret_cast<float4*>(dz + int64_t(r) * lddz);
+    uint2* d16 = dz16 ? reinterpret_cast<uint2*>(dz16 + int64_t(r) * lddz16) : nullptr;
+    // sweep 3: dlogits = (q S - t' 1[unclipped]) scale, column sums, store
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k) {
+      const int i = threadIdx.x + k * KLR_THREADS;
+      if (i < p4) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n4) {
+          const float4 e4 = s4[i];
+          const float ev[4] = {e4.x, e4.y, e4.z, e4.w}, tt[4] = {tv[k].x, tv[k].y, tv[k].z, tv[k].w};
+          float gg[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float q = ev[c] * inv_sum;
+            const float tc = fminf(fmaxf(tt[c], KERAS_EPS), 1.f);
+            const bool un = (q >= KERAS_EPS) && (q <= 1.f);
+            gg[c] = FAST ? fmaf(ev[c], qs, un ? -tc * grad_scale : 0.f) : (q * S - (un ? tc : 0.f)) * grad_scale;
+            if (round_tf32) gg[c] = rn_tf32(gg[c]);
+          }
+          g = make_float4(gg[0], gg[1], gg[2], gg[3]);
+          acc[k].x += g.x; acc[k].y += g.y; acc[k].z += g.z; acc[k].w += g.w;
+        }
+        if (d16) {
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(g.x, g.y), hi = __floats2bfloat162_rn(g.z, g.w);
+          d16[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+        } else {
+          d4[i] = g;
+        }
+      }
+    }
+    // pad columns beyond the last register slot (ncols_pad - num_cards < 128 columns: one more slot at most)
+    {
+      const int i = threadIdx.x + ITERS * KLR_THREADS;
+      if (i < p4) {
+        if (d16) d16[i] = make_uint2(0u, 0u); else d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    __syncthreads();          // every thread is done with sz[buf] before the prefetch after next overwrites it
+    buf ^= 1;
+  }
+  if (dbias) {
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k) {
+      const int i = threadIdx.x + k * KLR_THREADS;
+      if (i < n4) {
+        atomicAdd(dbias + 4 * i, acc[k].x); atomicAdd(dbias + 4 * i + 1, acc[k].y);
+        atomicAdd(dbias + 4 * i + 2, acc[k].z); atomicAdd(dbias + 4 * i + 3, acc[k].w);
+      }
+    }
+  }
+}
+
 // sum_c t'_c log t'_c, t' = clip(t, 1e-7, 1), of every row of the target matrix (M-hat), in float64: the part of the
 // Keras KLD that does not depend on the model.  One CTA per row; built once per graph.
 __global__ void __launch_bounds__(256)
@@ -625,7 +824,17 @@ __global__ void sigmoid_kernel(const float* __restrict__ z, float* __restrict__ 
 
 using namespace cc;
 
+// 0 = choose (the register-resident kernel when the row fits its 11 slots per thread), 1 = always the 1024-thread
+// kernel (cc_softmax_kl_set_variant; tests and A/B measurements)
+static int g_kl_variant = 0;
+
 extern "C" {
+
+int cc_softmax_kl_set_variant(int variant) {
+  CC_REQUIRE(variant == 0 || variant == 1, "cc_softmax_kl_set_variant: 0 (auto) or 1 (1024-thread kernel)");
+  g_kl_variant = variant;
+  return CC_OK;
+}
 
 int cc_bce_logits_fwd_bwd(const float* z, int64_t ldz, const uint32_t* ybits, int64_t ywords, int32_t batch,
                           int32_t num_cards, int32_t ncols_pad, double count /* global B*C */, float* dz,
@@ -686,7 +895,19 @@ int cc_softmax_kl_fwd_bwd_ex(const float* z, int64_t ldz, const float* target, i
     if (rows == 0) return CC_OK;
     const size_t smem = size_t(num_cards) * 8;
     const int grid = rows < sm_count() ? rows : sm_count();
-    if (round_tf32) {
+    const bool fits_regs = (ncols_pad >> 2) <= (KLR_ITERS + 1) * KLR_THREADS && (num_cards >> 2) <= KLR_ITERS * KLR_THREADS;
+    if (fits_regs && g_kl_variant != 1) {
+#define CC_KL_REGS(FAST_, RT_)                                                                                        \
+      do {                                                                                                            \
+        CC_CHECK_CUDA(cudaFuncSetAttribute(softmax_kl_regs_kernel<FAST_, KLR_ITERS>,                                  \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
+        softmax_kl_regs_kernel<FAST_, KLR_ITERS><<<grid, KLR_THREADS, smem, st>>>(                                    \
+            z, ldz, target, ldt, target_rows, rows, num_cards, ncols_pad, float(grad_scale), dz, lddz, row_loss, RT_,  \
+            dbias, dz16, lddz_bf16, tlogt);                                                                           \
+      } while (0)
+      if (round_tf32) CC_KL_REGS(true, dz16 ? 0 : 1); else CC_KL_REGS(false, 0);
+#undef CC_KL_REGS
+    } else if (round_tf32) {
       CC_CHECK_CUDA(cudaFuncSetAttribute(softmax_kl_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       softmax_kl_persistent_kernel<true><<<grid, KLP_THREADS, smem, st>>>(z, ldz, target, ldt, target_rows, rows, num_cards,
                                                                          ncols_pad, float(grad_scale), dz, lddz, row_loss,

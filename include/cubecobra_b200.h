@@ -255,6 +255,9 @@ int cc_softmax_kl_fwd_bwd_ex(const float* z, int64_t ldz, const float* target, i
                              int32_t rows, int32_t num_cards, int32_t ncols_pad, double grad_scale, float* dz,
                              int64_t lddz, double* row_loss, int round_tf32, float* dbias, void* dz_bf16,
                              int64_t lddz_bf16, const double* tlogt, void* stream);
+/* Which persistent kernel serves dbias != NULL: 0 = choose (512 threads with the target row and the column sums in
+ * registers when num_cards <= 22 528, else the 1024-thread form), 1 = always the 1024-thread form (tests, A/B runs). */
+int cc_softmax_kl_set_variant(int variant);
 /* tlogt[i] = sum_c t' log t', t' = clip(target[i][c], 1e-7, 1), float64: the model-independent half of Keras'
  * kullback_leibler_divergence (src/ml/train.py:85) for every row of M-hat; built once per graph. */
 int cc_kl_target_table(const float* target, int64_t ldt, int32_t target_rows, int32_t num_cards, double* tlogt,

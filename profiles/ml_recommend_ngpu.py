@@ -27,27 +27,41 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
-lo, hi = shard_range(K, rank, world)
-csr = make_cubes(K, C, cfg=4).rows(np.arange(lo, hi)).pin_memory()      # every rank builds the same cubes, keeps its shard
+full = make_cubes(K, C, cfg=4)                                              # every rank builds the same cubes
 model = M.CC_Recommender(C, device=dev, seed=0, precision="tf32")          # same seed: identical replicas
 rec = INF.MLRecommender(model, chunk=4096)
-rec.recommend_device(csr, N)                                               # warm-up
-torch.cuda.synchronize()
-if world > 1:
-    dist.barrier()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-ids, vals, cnt = rec.recommend_device(csr, N)
-e1.record()
-torch.cuda.synchronize()
-t = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device=dev)
-ok = torch.tensor([int((cnt == N).all().item())], device=dev)
-if world > 1:
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+lines = []
+# one launch measures every N in {1, 2, 4, ..., world}: for a given N only ranks < N take a shard, the others idle
+ns = [n for n in (1, 2, 4, 8, 16) if n <= world]
+for n in ns:
+    active = rank < n
+    if active:
+        lo, hi = shard_range(K, rank, n)
+        csr = full.rows(np.arange(lo, hi)).pin_memory()
+        rec.recommend_device(csr, N)                                       # warm-up (allocator, copy stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.zeros(1, dtype=torch.float64, device=dev)
+    ok = torch.ones(1, dtype=torch.int32, device=dev)
+    if active:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ids, vals, cnt = rec.recommend_device(csr, N)
+        e1.record()
+        torch.cuda.synchronize()
+        t[0] = e0.elapsed_time(e1) / 1e3
+        ok[0] = int((cnt == N).all().item())
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    lines.append({"workload": f"ml_recommend top-{N}, {K} cubes, C={C}, in-cube masking, {n} GPU(s), cubes sharded",
+                  "seconds": t.item(), "recs_per_s": K / t.item(), "n_gpus": n, "all_counts_full": bool(ok.item()),
+                  "timing": "CUDA events around recommend_device (pinned CSR upload included), max over ranks"})
 if rank == 0:
-    print(json.dumps({"workload": f"ml_recommend top-{N}, {K} cubes, C={C}, in-cube masking, {world} GPU(s), cubes sharded",
-                      "seconds": t.item(), "recs_per_s": K / t.item(), "n_gpus": world, "all_counts_full": bool(ok.item()),
-                      "timing": "CUDA events around recommend_device (pinned CSR upload included), max over ranks"}))
+    base = lines[0]["recs_per_s"]
+    for ln in lines:
+        ln["scaling_efficiency_vs_1gpu"] = ln["recs_per_s"] / (base * ln["n_gpus"])
+        print(json.dumps(ln))
 if world > 1:
     dist.destroy_process_group()

@@ -554,3 +554,73 @@ def test_bf16_mode_pieces():
             loss = eng.train_step().cpu().numpy()          # one whole step runs (bf16 dlogits out of the softmax-KL kernel)
             assert np.isfinite(loss).all()
     assert torch.equal(dense["tf32"], dense["bf16"]) and dense["bf16"].sum() > 0
+
+
+@pytest.mark.parametrize("c,rows", [(340, 700), (20884, 333), (22528, 160)])
+@pytest.mark.parametrize("fast", [0, 1])
+def test_softmax_kl_persistent_kernels_vs_oracle(c, rows, fast):
+    """The two persistent softmax-KL kernels (512 threads with the target row and the column sums in registers -- the
+    shipped one up to 22 528 cards -- and the 1024-thread form) against the float64 oracle and against each other, with
+    and without the per-target-row table, float32 and bf16 dlogits, more rows than CTAs, rows with clipped entries."""
+    from cubecobrarecommender_b200 import _lib
+    cpad = (c + 127) // 128 * 128
+    assert _lib.load().cc_softmax_kl_fuses_dbias(c, cpad, cpad, c, cpad)
+    rng = np.random.default_rng(c + rows)
+    g = torch.Generator(device="cuda").manual_seed(c)
+    z = torch.randn(rows, cpad, device="cuda", generator=g) * 3
+    z[1, 5] = 45.0                                           # drives most of row 1 below the 1e-7 clip
+    z[:, c:] = 0
+    nt = 64                                                  # distinct target rows
+    t = torch.rand(nt, c, device="cuda", generator=g)
+    t = torch.where(t < 0.7, torch.zeros_like(t), t)
+    t = (t / t.sum(1, keepdim=True)).contiguous()
+    tr = torch.from_numpy(rng.integers(0, nt, size=rows).astype(np.int32)).cuda()
+    table = torch.zeros(nt, dtype=torch.float64, device="cuda")
+    E.call("cc_kl_target_table", E.ptr(t), c, nt, c, E.ptr(table), E.stream_ptr())
+    scale = 0.1 / rows
+    # oracle on a sample of rows (float64)
+    pick = np.unique(np.concatenate([[0, 1, rows - 1], rng.integers(0, rows, size=12)]))
+    zz = z[torch.from_numpy(pick).cuda(), :c].double().cpu().numpy()
+    tt = t[tr[torch.from_numpy(pick).cuda()].long()].double().cpu().numpy()
+    q = od.softmax_np(zz)
+    tcl = np.clip(tt, 1e-7, 1.0); qcl = np.clip(q, 1e-7, 1.0)
+    ref_rows = (tcl * np.log(tcl / qcl)).sum(1)
+    un = (q >= 1e-7) & (q <= 1)
+    ref_dz = scale * (q * (tcl * un).sum(1, keepdims=True) - tcl * un)
+    outs = {}
+    try:
+        for variant in (0, 1):
+            E.call("cc_softmax_kl_set_variant", variant)
+            for use_table in (False, True):
+                dz = torch.full((rows, cpad), 9.0, device="cuda")
+                rl = torch.zeros(rows, dtype=torch.float64, device="cuda")
+                db = torch.full((c,), 3.0, device="cuda")
+                E.call("cc_softmax_kl_fwd_bwd_ex", E.ptr(z), cpad, E.ptr(t), c, E.ptr(tr), rows, c, cpad, scale, E.ptr(dz), cpad,
+                       E.ptr(rl), fast, E.ptr(db), None, 0, E.ptr(table) if use_table else None, E.stream_ptr())
+                outs[(variant, use_table)] = (dz, rl, db)
+                got_rows = rl[torch.from_numpy(pick).cuda()].cpu().numpy()
+                assert np.abs(got_rows - ref_rows).max() < (2e-5 if fast else 5e-6) * np.abs(ref_rows).max()
+                got_dz = dz[torch.from_numpy(pick).cuda(), :c].double().cpu().numpy()
+                edge = np.abs(q - 1e-7) < 1e-10
+                tol = (2e-3 if fast else 2e-5) * np.abs(ref_dz).max()      # fast: MUFU exp + tf32-rounded dlogits
+                assert np.abs(got_dz - ref_dz)[~edge].max() < tol
+                assert (dz[:, c:] == 0).all()
+                ref_db = dz[:, :c].double().sum(0)
+                assert (db.double() - ref_db).abs().max().item() < 2e-6 * ref_db.abs().max().item() + 1e-12
+            # bf16 dlogits
+            dz16 = torch.full((rows, cpad), 9.0, dtype=torch.bfloat16, device="cuda")
+            rl16 = torch.zeros(rows, dtype=torch.float64, device="cuda")
+            db16 = torch.zeros(c, device="cuda")
+            E.call("cc_softmax_kl_fwd_bwd_ex", E.ptr(z), cpad, E.ptr(t), c, E.ptr(tr), rows, c, cpad, scale, None, 0,
+                   E.ptr(rl16), 1, E.ptr(db16), E.ptr(dz16), cpad, E.ptr(table), E.stream_ptr())
+            ref16 = outs[(variant, True)][0] if fast else None
+            assert (dz16[:, c:] == 0).all()
+            if fast:        # the same float values before the bf16 rounding, up to the skipped tf32 rounding
+                assert (dz16.float() - ref16).abs().max().item() <= 2.0 ** -8 * ref16.abs().max().item()
+        # the two kernels: same formulas, different reduction trees
+        for use_table in (False, True):
+            a, b = outs[(0, use_table)], outs[(1, use_table)]
+            assert torch.allclose(a[0], b[0], rtol=3e-3 if fast else 3e-5, atol=1e-12)
+            assert torch.allclose(a[1], b[1], rtol=1e-5)
+    finally:
+        E.call("cc_softmax_kl_set_variant", 0)

@@ -111,6 +111,7 @@ def test_web_get_ml_recommend_resident(tmp_path, monkeypatch):
     monkeypatch.setenv("CUBECOBRA_MODEL_DIR", str(tmp_path / "ml_files/recommender"))
     monkeypatch.setenv("CUBECOBRA_ID_MAP", str(tmp_path / "idmap.json"))
     monkeypatch.setitem(W._state, "rec", None)
+    monkeypatch.setitem(W._state, "batcher", None)
     names = ["Card 5", "CARD 17", "not a card", "card 99"]
     out = W.get_ml_recommend("ignored", 10, card_names=names)
     assert len(out["additions"]) == 10 and set(out["cuts"]) == {"card 5", "card 17", "card 99"}
@@ -119,6 +120,60 @@ def test_web_get_ml_recommend_resident(tmp_path, monkeypatch):
     loaded = M.load_model(str(tmp_path / "ml_files/recommender"))
     a, b = model.get_weights_dict(), loaded.get_weights_dict()
     assert all(np.array_equal(a[k], b[k]) for k in a)
+
+
+def test_web_requests_are_micro_batched(monkeypatch):
+    """concurrent get_ml_recommend calls (request threads of the WSGI server) are collected by the
+    RequestBatcher and served by ONE batched recommend_device call; every request still gets exactly the answer the
+    one-cube path gives (same ids in rank order, same scores, cuts in cubelist order), whatever it was batched with."""
+    import threading
+    from cubecobrarecommender_b200.web import ml_recommend_web as W
+    c, k = 400, 24
+    ip, ix = synth_cubes_csr(k, c, size_lo=1, size_hi=120, seed=12)
+    model = M.CC_Recommender(c, device="cuda", seed=5, precision="tf32")
+    rec = INF.MLRecommender(model, chunk=64)
+    i2c = {i: f"card {i}" for i in range(c)}
+    saved = dict(W._state)
+    batcher = W.install(rec, i2c, max_batch=64, max_wait_ms=200.0)
+    try:
+        cubes = []
+        for r in range(k):
+            idx = [int(v) for v in ix[ip[r]:ip[r + 1]]]
+            rng = np.random.default_rng(r)
+            rng.shuffle(idx)                                  # cubelist order is not sorted
+            if r % 5 == 0 and idx:
+                idx.append(idx[0])                            # a card listed twice
+            cubes.append(idx)
+        cubes[3] = []                                         # an empty cube list (all cards unknown)
+        amounts = [7 + (r % 4) * 50 for r in range(k)]        # 7, 57, 107, 157: fused and unfused select in one batch
+        outs = [None] * k
+        gate = threading.Barrier(k)
+
+        def request(r):
+            gate.wait()
+            outs[r] = W.get_ml_recommend("ignored", amounts[r], card_names=[f"Card {i}" for i in cubes[r]])
+        threads = [threading.Thread(target=request, args=(r,)) for r in range(k)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(timeout=120)
+        assert all(o is not None for o in outs)
+        assert batcher.stats["requests"] == k and batcher.stats["batches"] < k and batcher.stats["max_batch"] > 1
+        for r in range(k):
+            one = rec.recommend_one(cubes[r], amounts[r], i2c)
+            assert list(outs[r]["additions"]) == list(one["additions"]), r           # same cards, same order
+            assert list(outs[r]["cuts"]) == list(one["cuts"]), r
+            a = np.array(list(outs[r]["additions"].values())); b = np.array(list(one["additions"].values()))
+            assert np.abs(a - b).max() < 1e-6 if len(a) else True    # (a different GEMM batch shape: last-bit differences)
+            assert len(outs[r]["additions"]) == min(amounts[r], c - len(set(cubes[r])))
+        # a lone request is served too (the worker does not wait for company beyond max_wait_ms)
+        solo = W.get_ml_recommend("ignored", 5, card_names=["card 1", "card 2"])
+        assert len(solo["additions"]) == 5 and set(solo["cuts"]) == {"card 1", "card 2"}
+        assert W.get_ml_recommend("ignored", 3, non_json=True, card_names=["card 1"]) is None
+    finally:
+        batcher.close()
+        W._state.update(saved)
+        W._state["batcher"] = None          # (install() closed whatever batcher was there before)
 
 
 def test_datagenerator_mirror_and_fit():
