@@ -96,7 +96,27 @@ noise_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ ind
 
   for (int w = threadIdx.x; w < 3 * W + FW; w += blockDim.x) sm[w] = 0;
   __syncthreads();
-  if (s > max_size) { if (threadIdx.x == 0) atomicExch(overflow, 1); return; }
+  if (s > max_size) {
+    // a cube larger than the engine was sized for: flag it AND leave a well-defined empty row behind (x empty, y and
+    // the dense row all zero) -- never the previous step's data -- so a caller that only checks the flag at the end of
+    // an epoch has trained on nothing worse than an empty cube meanwhile
+    if (threadIdx.x == 0) { atomicExch(overflow, 1); x_len[b] = 0; if (flips_out) flips_out[b] = 0; }
+    if (y_bits) {
+      uint32_t* yo = y_bits + int64_t(b) * y_words;
+      for (int w = threadIdx.x; w < y_words; w += blockDim.x) yo[w] = 0u;
+    }
+    if (x_dense) {
+      const int groups = int(ld_dense >> 2);
+      if (dense_bf16) {
+        uint2* xo2 = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(x_dense) + int64_t(b) * ld_dense);
+        for (int g = threadIdx.x; g < groups; g += blockDim.x) xo2[g] = make_uint2(0u, 0u);
+      } else {
+        float4* xo4 = reinterpret_cast<float4*>(x_dense + int64_t(b) * ld_dense);
+        for (int g = threadIdx.x; g < groups; g += blockDim.x) xo4[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    return;
+  }
   for (int p = threadIdx.x; p < s; p += blockDim.x) {
     const int32_t c = inc[p];
     atomicOr(&cube_mask[c >> 5], 1u << (c & 31));

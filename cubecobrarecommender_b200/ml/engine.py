@@ -603,6 +603,7 @@ class HostBatchStream:
         self.copied = [torch.cuda.Event() for _ in range(2)]       # slot filled (copy stream)
         self.consumed = [torch.cuda.Event() for _ in range(2)]     # slot read by the noise kernel (compute stream)
         self.loss_host = [torch.zeros(3, dtype=torch.float64).pin_memory() for _ in range(2)]
+        self.ovf_host = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(2)]   # the noise kernel's overflow flag
         self.loss_done = [torch.cuda.Event() for _ in range(2)]
         self.h2d_bytes = int(np.mean([h[0].numel() * 8 + h[1].numel() * 4 for h in self.host]))
         self._next_prefetched = -1
@@ -630,18 +631,27 @@ class HostBatchStream:
         self._prefetch(i + 1)                                      # overlaps this step's compute
         l3 = self.eng.train_step()
         self.loss_host[slot].copy_(l3, non_blocking=True)
+        self.ovf_host[slot].copy_(self.eng.overflow, non_blocking=True)       # rides along with the loss: no extra sync
         self.loss_done[slot].record(cur)
         prev = self._pending
         self._pending = slot
         if prev is None:
             return None
         self.loss_done[prev].synchronize()                         # finished long ago: step i was queued meanwhile
+        self._raise_on_overflow(prev)
         return self.loss_host[prev].clone().numpy()
+
+    def _raise_on_overflow(self, slot):
+        v = int(self.ovf_host[slot][0])
+        if v:
+            raise RuntimeError("noise kernel overflow: " + ("cube larger than max_cube_size" if v == 1
+                                                            else "x list longer than x_stride"))
 
     def drain(self):
         if self._pending is None:
             return None
         self.loss_done[self._pending].synchronize()
+        self._raise_on_overflow(self._pending)
         out = self.loss_host[self._pending].clone().numpy()
         self._pending = None
         return out

@@ -10,7 +10,11 @@ Same constructor arguments and attributes (``indices``, ``neg_sampler``, ``N_cub
   the GPU and leave x as index lists, y as bit rows and r as row ids inside ``engine``'s buffers.
 
 The draws come from Philox streams seeded by ``seed`` and the step counter, not from NumPy's global
-MT19937 state (the epoch shuffle still uses ``np.random.shuffle`` like the reference, generator.py:63-66).
+MT19937 state.  The epoch shuffle (reference generator.py:63-72) runs ON THE DEVICE: a permutation drawn from a
+generator seeded by ``(seed, epoch)``, so (a) every data-parallel rank holds the same permutation whether or not a
+CLI seed was given, (b) a resumed run continues with the permutation the interrupted one would have used, and (c) a
+step's batch ids are a slice of a device tensor -- no host array, no H2D copy per step.  ``indices`` stays available
+as the NumPy array the reference exposes (one small D2H per epoch).
 """
 from __future__ import annotations
 
@@ -35,6 +39,7 @@ class DataGenerator:
         self.csr = cubes if isinstance(cubes, CubeCSR) else CubeCSR.from_dense(np.asarray(cubes))
         self.N_cubes = self.csr.num_cubes
         self.N_cards = self.csr.num_cards
+        self.epoch = 0
         self.reset_indices()
         if isinstance(adj_mtx, torch.Tensor):
             col = adj_mtx[:, :self.N_cards].double().sum(0)
@@ -58,17 +63,33 @@ class DataGenerator:
     def __len__(self):
         return self.N_cubes // self.batch_size                               # generator.py:36
 
-    def reset_indices(self):
-        self.indices = np.arange(self.N_cubes)
+    def reset_indices(self, epoch: int | None = None):
+        """The epoch's cube order (reference generator.py:63-66), drawn on the device from ``(seed, epoch)``."""
+        if epoch is not None:
+            self.epoch = int(epoch)
         if self.shuffle == True:  # noqa: E712
-            np.random.shuffle(self.indices)
+            if self.device.type == "cuda":
+                g = torch.Generator(device=self.device)
+                g.manual_seed((self.seed * 1_000_003 + self.epoch * 7919 + 12345) & 0x7FFFFFFFFFFFFFFF)
+                self.indices_dev_order = torch.randperm(self.N_cubes, generator=g, device=self.device).to(torch.int32)
+            else:   # host-only use of the mirror (no kernels can run there anyway)
+                rng = np.random.default_rng([self.seed, self.epoch])
+                self.indices_dev_order = torch.from_numpy(rng.permutation(self.N_cubes).astype(np.int32))
+        else:
+            self.indices_dev_order = torch.arange(self.N_cubes, dtype=torch.int32, device=self.device)
+        self.indices = self.indices_dev_order.cpu().numpy().astype(np.int64)
 
     def on_epoch_end(self):
+        self.epoch += 1
         self.reset_indices()
 
-    def batch_ids(self, batch_number) -> torch.Tensor:
-        ids = self.indices[batch_number * self.batch_size:(batch_number + 1) * self.batch_size]
-        return torch.from_numpy(np.ascontiguousarray(ids, dtype=np.int32)).to(self.device)
+    def batch_ids(self, batch_number, rank: int = 0, world: int = 1) -> torch.Tensor:
+        """Device int32 ids of batch ``batch_number`` (of rank ``rank``'s share of it): a view of the epoch's permutation."""
+        ids = self.indices_dev_order[batch_number * self.batch_size:(batch_number + 1) * self.batch_size]
+        if world > 1:
+            per = self.batch_size // world
+            ids = ids[rank * per:(rank + 1) * per]
+        return ids
 
     def device_batch(self, batch_number, engine):
         """Noise + reg rows for batch ``batch_number`` straight into ``engine`` (no host round trip)."""

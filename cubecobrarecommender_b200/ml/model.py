@@ -326,21 +326,36 @@ class CC_Recommender:
     def set_weights_dict(self, params):
         self.store.load_dict(params)
 
-    def save(self, path):
-        """Own checkpoint format (npz of the 24 Keras-named tensors + Adam slots + step);
-        replaces ``autoencoder.save(dest, save_format='tf')`` (reference train.py:112-115)."""
+    completed_epochs = 0        # epochs of training behind these weights (written by save(), restored by load())
+
+    def save(self, path, epoch=None):
+        """Own checkpoint format (npz of the 24 Keras-named tensors + Adam slots + step + completed epochs);
+        replaces ``autoencoder.save(dest, save_format='tf')`` (reference train.py:112-115).  The file is written
+        under a temporary name and renamed, so an interrupted save never leaves a truncated checkpoint behind."""
         import os
         os.makedirs(path, exist_ok=True)
+        if epoch is not None:
+            self.completed_epochs = int(epoch)
         blob = {k: v for k, v in self.store.to_dict().items()}
         blob.update({"adam_m/" + k: v for k, v in self.store.to_dict(self.store.adam_m).items()})
         blob.update({"adam_v/" + k: v for k, v in self.store.to_dict(self.store.adam_v).items()})
         blob["step"] = self.store.step.cpu().numpy()
         blob["num_cards"] = np.int64(self.N)
-        np.savez(os.path.join(path, "cc_recommender.npz"), **blob)
+        blob["completed_epochs"] = np.int64(self.completed_epochs)
+        tmp = os.path.join(path, "cc_recommender.tmp.npz")
+        np.savez(tmp, **blob)
+        os.replace(tmp, os.path.join(path, "cc_recommender.npz"))
 
     @classmethod
     def load(cls, path, device="cuda", precision="fp32"):
         import os
+        if not os.path.exists(os.path.join(path, "cc_recommender.npz")):
+            if os.path.exists(os.path.join(path, "saved_model.pb")):
+                raise FileNotFoundError(
+                    f"{path} holds a TensorFlow SavedModel (the reference's format, train.py:112-115), which this package "
+                    f"cannot read without TensorFlow.  Convert it once on a machine that has TensorFlow with "
+                    f"`python -m cubecobrarecommender_b200.scripts.convert_savedmodel {path} <out_dir>` and load <out_dir>.")
+            raise FileNotFoundError(f"no cc_recommender.npz under {path} (save one with CC_Recommender.save)")
         blob = np.load(os.path.join(path, "cc_recommender.npz"))
         model = cls(int(blob["num_cards"]), device=device, precision=precision)
         model.store.load_dict({k: blob[k] for k in model.store.layout})
@@ -350,6 +365,8 @@ class CC_Recommender:
                 model.store.view(model.store.adam_v, k).copy_(torch.as_tensor(blob["adam_v/" + k]))
         if "step" in blob:
             model.store.step.copy_(torch.as_tensor(blob["step"]))
+        if "completed_epochs" in blob:
+            model.completed_epochs = int(blob["completed_epochs"])
         return model
 
 

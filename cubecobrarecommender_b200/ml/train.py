@@ -26,9 +26,15 @@ def reset_random_seeds(seed):
     random.seed(seed)
 
 
-def fit(model, generator, epochs, reg, *, group=None, log=print, steps_per_epoch=None, max_cube_size=None):
+def fit(model, generator, epochs, reg, *, group=None, log=print, steps_per_epoch=None, max_cube_size=None,
+        initial_epoch=0, checkpoint_dir=None, save_every=None, overflow_check_every=50):
     """``autoencoder.fit(generator, epochs=epochs)`` (reference train.py:99-102).  Returns the history
-    ``[{"loss", "output_1_loss", "output_2_loss"}]`` per epoch (means over the epoch's steps)."""
+    ``[{"loss", "output_1_loss", "output_2_loss"}]`` per epoch (means over the epoch's steps).
+
+    Beyond the reference: ``initial_epoch`` (Keras' own argument name) continues a run -- the epoch
+    shuffle is a function of (seed, epoch), Adam's step counter lives in the model -- and every ``save_every`` epochs the
+    model, its Adam slots and the number of completed epochs are written to ``checkpoint_dir`` (rank 0 writes; in p2p
+    data-parallel mode the sliced Adam slots are gathered first)."""
     import torch.distributed as dist
     from .engine import DAEEngine
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -42,31 +48,49 @@ def fit(model, generator, epochs, reg, *, group=None, log=print, steps_per_epoch
                     global_reg_rows=gb, group=group)
     history = []
     nsteps = steps_per_epoch or len(generator)
-    for epoch in range(epochs):
+    if initial_epoch:
+        generator.reset_indices(initial_epoch)
+    for epoch in range(initial_epoch, epochs):
         log(f"Epoch {epoch + 1}/{epochs}")
         t0 = time.time()
         acc = torch.zeros(3, dtype=torch.float64, device=model.device)
         for b in range(nsteps):
-            ids = generator.indices[b * gb:(b + 1) * gb][rank * lb:(rank + 1) * lb]
-            ids_t = torch.from_numpy(np.ascontiguousarray(ids, dtype=np.int32)).to(model.device)
+            ids_t = generator.batch_ids(b, rank, world)           # a slice of the epoch's device-side permutation
             eng.sample_batch(generator.indptr, generator.indices_dev, ids_t, generator.alias_prob, generator.alias_idx,
                              generator.noise, generator.noise_std, seed=generator.seed + 7919 * rank)
             acc += eng.train_step()
+            if overflow_check_every and (b + 1) % overflow_check_every == 0:
+                eng.check_overflow()                                # (one 4-byte read: the only host sync inside an epoch)
         eng.check_overflow()
         mean = (acc / max(nsteps, 1)).cpu().numpy()
         history.append({"loss": float(mean[2]), "output_1_loss": float(mean[0]), "output_2_loss": float(mean[1])})
         log(f"{nsteps}/{nsteps} - {time.time() - t0:.0f}s - loss: {mean[2]:.4f} - output_1_loss: {mean[0]:.4f} "
             f"- output_2_loss: {mean[1]:.4f}")
         generator.on_epoch_end()
+        if checkpoint_dir and save_every and (epoch + 1) % save_every == 0 and epoch + 1 < epochs:
+            eng.gather_adam_state()
+            if rank == 0:
+                model.save(checkpoint_dir, epoch=epoch + 1)
     eng.gather_adam_state()      # p2p data parallel: m / v live sliced over the ranks until a checkpoint needs them
     return history
 
 
 def main(argv=None):
+    """``train.py epochs batch_size name reg noise [seed]`` (reference train.py:28-38), plus two optional flags the
+    reference does not have: ``--save-every N`` writes a checkpoint to ``ml_files/<name>`` every N epochs, ``--resume``
+    continues from the checkpoint found there (weights, Adam slots, step counter, completed epochs)."""
     from ..non_ml import utils
     from .generator import DataGenerator
     from .model import CC_Recommender
-    args = sys.argv[1:] if argv is None else argv
+    args = list(sys.argv[1:] if argv is None else argv)
+    resume = "--resume" in args
+    if resume:
+        args.remove("--resume")
+    save_every = None
+    if "--save-every" in args:
+        i = args.index("--save-every")
+        save_every = int(args[i + 1])
+        del args[i:i + 2]
     epochs, batch_size, name = int(args[0]), int(args[1]), args[2]
     reg, noise = float(args[3]), float(args[4])
     seed = 0
@@ -90,12 +114,19 @@ def main(argv=None):
     y_mtx = (y_mtx / y_mtx.sum(1)[:, None])                                   # train.py:69-71
     print('Setting Up Data for Training . . .\n')
     print('Setting Up Model . . . \n')
-    autoencoder = CC_Recommender(num_cards, device="cuda", seed=seed, precision=os.environ.get("CC_PRECISION", "tf32"))
-    generator = DataGenerator(y_mtx, cubes, batch_size=batch_size, noise=noise, seed=seed)
-    fit(autoencoder, generator, epochs, reg)
     dest = f'././ml_files/{name}'
+    precision = os.environ.get("CC_PRECISION", "tf32")
+    initial_epoch = 0
+    if resume and os.path.exists(os.path.join(dest, "cc_recommender.npz")):
+        autoencoder = CC_Recommender.load(dest, device="cuda", precision=precision)
+        initial_epoch = autoencoder.completed_epochs
+        print(f'Resuming from {dest}: {initial_epoch} epochs done, Adam step {int(autoencoder.store.step.item())}\n')
+    else:
+        autoencoder = CC_Recommender(num_cards, device="cuda", seed=seed, precision=precision)
+    generator = DataGenerator(y_mtx, cubes, batch_size=batch_size, noise=noise, seed=seed)
+    fit(autoencoder, generator, epochs, reg, initial_epoch=initial_epoch, checkpoint_dir=dest, save_every=save_every)
     if not dist.is_initialized() or dist.get_rank() == 0:
-        autoencoder.save(dest)
+        autoencoder.save(dest, epoch=epochs)
     if dist.is_initialized():
         dist.destroy_process_group()
 

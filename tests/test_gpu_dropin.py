@@ -196,6 +196,67 @@ def test_datagenerator_mirror_and_fit():
     assert int(model.store.step.item()) == 18
 
 
+def test_fit_periodic_save_and_resume(tmp_path):
+    """a run interrupted after a periodic checkpoint and resumed from it ends where the uninterrupted
+    run ends -- the epoch shuffle is a function of (seed, epoch), the noise draws of (seed, Adam step), both restored
+    from the checkpoint together with the weights and the Adam slots."""
+    c, k, b = 256, 96, 32
+    ip, ix = synth_cubes_csr(k, c, size_lo=10, size_hi=60, seed=8)
+    dense = csr_to_dense(ip, ix, c)
+    mh = og.m_hat(og.create_adjacency_matrix(dense))
+    quiet = lambda *_: None
+
+    def run(epochs, model, initial_epoch=0, ckpt=None, save_every=None):
+        gen = GEN.DataGenerator(mh, dense, batch_size=b, noise=0.2, seed=11)
+        return T.fit(model, gen, epochs=epochs, reg=0.1, log=quiet, initial_epoch=initial_epoch, checkpoint_dir=ckpt,
+                     save_every=save_every), gen
+    straight = M.CC_Recommender(c, device="cuda", seed=0, precision="fp32")
+    h_all, gen_all = run(4, straight)
+    ck = str(tmp_path / "ml_files/run")
+    first = M.CC_Recommender(c, device="cuda", seed=0, precision="fp32")
+    h_first, _ = run(3, first, ckpt=ck, save_every=2)             # checkpoint after epoch 2, "crash" after epoch 3
+    resumed = M.CC_Recommender.load(ck, device="cuda", precision="fp32")
+    assert resumed.completed_epochs == 2 and int(resumed.store.step.item()) == 2 * (k // b)
+    h_rest, gen_rest = run(4, resumed, initial_epoch=resumed.completed_epochs)
+    assert len(h_rest) == 2
+    assert np.array_equal(gen_rest.indices, gen_all.indices)       # same permutation at the same epoch
+    # exact-fp32 mode: only float atomics (first-layer scatter-add) separate the two runs
+    for a, bb in zip(h_all[2:], h_rest):
+        assert abs(a["loss"] - bb["loss"]) < 1e-5 * abs(a["loss"])
+    wa, wb = straight.get_weights_dict(), resumed.get_weights_dict()
+    assert max(np.abs(wa[n] - wb[n]).max() for n in wa) < 2e-4
+    assert int(resumed.store.step.item()) == int(straight.store.step.item()) == 4 * (k // b)
+    # two generators with the same seed agree epoch by epoch (what keeps data-parallel ranks on the same permutation)
+    g1 = GEN.DataGenerator(mh, dense, batch_size=b, seed=3); g2 = GEN.DataGenerator(mh, dense, batch_size=b, seed=3)
+    for _ in range(3):
+        assert np.array_equal(g1.indices, g2.indices) and sorted(g1.indices.tolist()) == list(range(k))
+        prev = g1.indices.copy(); g1.on_epoch_end(); g2.on_epoch_end()
+        assert not np.array_equal(prev, g1.indices)
+
+
+def test_noise_kernel_overflow_leaves_an_empty_row():
+    """A cube larger than the engine's max_cube_size sets the overflow flag AND leaves x empty / y zero for that row
+    (never the previous batch's data); fit() and the host-fed stream check the flag."""
+    from cubecobrarecommender_b200 import graph as G
+    from cubecobrarecommender_b200.ml import engine as E
+    c, b = 384, 8
+    lists = [list(range(0, 20 + 3 * i)) for i in range(b)]
+    lists[5] = list(range(0, 200))                                 # larger than max_cube_size = 64
+    csr = CubeCSR.from_lists(lists, c)
+    gr = G.build_graph(csr, "cuda", want_m64=False)
+    prob, alias = E.alias_table(gr.neg_sampler.cpu().numpy(), "cuda")
+    model = M.CC_Recommender(c, device="cuda", precision="tf32")
+    eng = E.DAEEngine(model, gr.mhat, batch=b, reg_rows=b, reg=0.1, max_cube_size=64)
+    eng.x_len.fill_(7); eng.y_bits.fill_(-1); eng.x_dense.fill_(1.0)
+    indptr, indices = G.upload_csr(csr, "cuda")
+    eng.sample_batch(indptr, indices, None, prob, alias, seed=1)
+    assert int(eng.overflow.item()) == 1
+    assert int(eng.x_len[5].item()) == 0 and (eng.y_bits[5] == 0).all() and (eng.x_dense[5] == 0).all()
+    assert int(eng.x_len[4].item()) > 0 and (eng.x_dense[4].sum() == eng.x_len[4]).item()
+    with pytest.raises(RuntimeError, match="overflow"):
+        eng.check_overflow()
+
+
 def test_similarity_script_and_kernel_vs_oracle(tmp_path, capsys):
     """scripts/similarity.py (reference src/scripts/similarity.py): encoder embeddings of all one-hot cards, Keras
     CosineSimilarity loss against one card, ascending argsort.  Checked against the float64 restatement; ids must

@@ -74,3 +74,31 @@ def test_csr_rows_and_lists():
     assert sub.indptr.tolist() == [0, 2, 4] and sub.indices.tolist() == [0, 2, 1, 4]
     with pytest.raises(ValueError):
         CubeCSR.from_lists([[7]], 5)
+
+
+def test_savedmodel_key_mapping_and_clear_error(tmp_path):
+    """The reference's SavedModel directories cannot be read without TensorFlow: load() says so and names the offline
+    converter, whose checkpoint-key mapping (pure string logic) covers all 24 tensors, Adam slots and the step."""
+    from cubecobrarecommender_b200.scripts import convert_savedmodel as CV
+    sfx = CV.SUFFIX
+    keys = []
+    for (owner, attr) in CV.ATTR_TO_LAYER:
+        for p in ("kernel", "bias"):
+            keys.append(f"{owner}/{attr}/{p}{sfx}")
+            keys.append(f"{owner}/{attr}/{p}/.OPTIMIZER_SLOT/optimizer/m{sfx}")
+            keys.append(f"{owner}/{attr}/{p}/.OPTIMIZER_SLOT/optimizer/v{sfx}")
+    keys += [f"optimizer/iter{sfx}", f"optimizer/beta_1{sfx}", "_CHECKPOINTABLE_OBJECT_GRAPH", f"keras_api/metrics/0/total{sfx}"]
+    m = CV.map_checkpoint_keys(keys)
+    names = set(m.values())
+    assert len(m) == 24 * 3 + 1 and "step" in names
+    assert {"encoder_e1/kernel", "main_reconstruction/bias", "reg_d2/kernel", "adam_m/encoder_bottleneck/bias",
+            "adam_v/reg_reconstruction/kernel"} <= names
+    assert m[f"decoder_for_reg/reconstruct/kernel{sfx}"] == "reg_reconstruction/kernel"
+    # a SavedModel directory: load() fails loudly and points at the converter (torch is imported by the model module)
+    pytest.importorskip("torch")
+    from cubecobrarecommender_b200.ml.model import CC_Recommender
+    d = tmp_path / "recommender"
+    (d / "variables").mkdir(parents=True)
+    (d / "saved_model.pb").write_bytes(b"\x00")
+    with pytest.raises(FileNotFoundError, match="convert_savedmodel"):
+        CC_Recommender.load(str(d), device="cpu")
