@@ -73,7 +73,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             list(ex.map(compile_one, jobs))
     if jobs or not os.path.exists(LIB):
         cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                      "-lcudart"]
+                                                      "-lcudart", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

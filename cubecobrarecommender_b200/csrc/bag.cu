@@ -94,6 +94,7 @@ extern "C" {
 int cc_bag_fwd(const float* w, int64_t ldw, int32_t hidden, const int32_t* idx, const int64_t* row_start,
                const int32_t* row_len, int32_t batch, const float* bias, float* out, int64_t ldo, int relu,
                int round_tf32, void* stream) {
+  CC_NVTX("cc_bag_fwd");
   CC_REQUIRE(w && idx && row_start && row_len && out, "cc_bag_fwd: null pointer");
   CC_REQUIRE(hidden > 0 && hidden % 4 == 0 && hidden <= 4096 && ldw % 4 == 0 && ldo % 4 == 0 && ldw >= hidden &&
                  ldo >= hidden, "cc_bag_fwd: hidden=%d ldw=%lld ldo=%lld must be multiples of 4", hidden,
@@ -110,6 +111,7 @@ int cc_bag_fwd(const float* w, int64_t ldw, int32_t hidden, const int32_t* idx, 
 
 int cc_bag_bwd(const float* g, int64_t ldg, int32_t hidden, const int32_t* idx, const int64_t* row_start,
                const int32_t* row_len, int32_t batch, float* dw, int64_t ldw, void* stream) {
+  CC_NVTX("cc_bag_bwd");
   CC_REQUIRE(g && idx && row_start && row_len && dw, "cc_bag_bwd: null pointer");
   CC_REQUIRE(hidden > 0 && hidden % 4 == 0 && hidden <= 4096 && ldw % 4 == 0 && ldg % 4 == 0, "cc_bag_bwd: bad sizes");
   CC_REQUIRE((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(dw)) % 16 == 0,

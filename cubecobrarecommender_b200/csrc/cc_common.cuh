@@ -1,6 +1,7 @@
 // Shared helpers for the cubecobra_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -34,6 +35,16 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
   } while (0)
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// NVTX range around every C-ABI entry point that enqueues work (header-only NVTX v3: a no-op unless a tool such as
+// Nsight Systems / ncu --nvtx injects itself), so a timeline shows which host call a kernel belongs to.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define CC_NVTX(name) cc::NvtxRange cc_nvtx_range_(name)
 
 int sm_count();
 

@@ -276,6 +276,7 @@ int64_t cc_bits_cpad(int32_t num_cards) { return ceil_div<int64_t>(num_cards, TI
 
 int cc_bitpack_cubes(const int64_t* indptr, const int32_t* indices, int64_t num_cubes, int32_t num_cards,
                      uint32_t* bits, int* bad_flag, void* stream) {
+  CC_NVTX("cc_bitpack_cubes");
   CC_REQUIRE(num_cubes >= 0 && num_cards > 0, "cc_bitpack_cubes: bad sizes K=%lld C=%d", (long long)num_cubes, num_cards);
   CC_REQUIRE(bits && bad_flag, "cc_bitpack_cubes: null output");
   cudaStream_t st = as_stream(stream);
@@ -292,6 +293,7 @@ int cc_bitpack_cubes(const int64_t* indptr, const int32_t* indices, int64_t num_
 
 int cc_cooc_count(const uint32_t* bits, int64_t num_cubes, int32_t num_cards, int32_t* counts, int64_t ld,
                   int accumulate, void* stream) {
+  CC_NVTX("cc_cooc_count");
   CC_REQUIRE(bits && counts && num_cards > 0 && ld >= num_cards, "cc_cooc_count: bad arguments");
   const int64_t kw = cc_bits_words(num_cubes), cpad = cc_bits_cpad(num_cards);
   const int tiles = int(cpad / TILE);
@@ -309,6 +311,7 @@ int cc_cooc_count(const uint32_t* bits, int64_t num_cubes, int32_t num_cards, in
 int cc_row_normalise(const int32_t* counts, int64_t ld, int32_t num_cards, double* m64, int64_t ld_m,
                      float* mhat, int64_t ld_mhat, double* rowsum, int has_force_diag, double force_diag,
                      void* stream) {
+  CC_NVTX("cc_row_normalise");
   return cc_row_normalise_rows(counts, ld, 0, num_cards, num_cards, m64, ld_m, mhat, ld_mhat, rowsum, has_force_diag,
                                force_diag, stream);
 }
@@ -316,6 +319,7 @@ int cc_row_normalise(const int32_t* counts, int64_t ld, int32_t num_cards, doubl
 int cc_row_normalise_rows(const int32_t* counts, int64_t ld, int32_t row0, int32_t nrows, int32_t num_cards, double* m64,
                           int64_t ld_m, float* mhat, int64_t ld_mhat, double* rowsum, int has_force_diag,
                           double force_diag, void* stream) {
+  CC_NVTX("cc_row_normalise_rows");
   CC_REQUIRE(counts && num_cards > 0 && ld >= num_cards, "cc_row_normalise: bad arguments");
   CC_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= num_cards, "cc_row_normalise: row block [%d, %d) outside [0, %d)",
              row0, row0 + nrows, num_cards);
@@ -342,6 +346,7 @@ int64_t cc_col_mass_workspace_bytes(int32_t num_cards) {
 
 int cc_col_mass(const int32_t* counts, int64_t ld, int32_t num_cards, const double* rowsum, double* workspace,
                 double* neg_sampler, void* stream) {
+  CC_NVTX("cc_col_mass");
   int rc = cc_col_mass_rows(counts, ld, 0, num_cards, num_cards, rowsum, workspace, neg_sampler, stream);
   if (rc != CC_OK) return rc;
   return cc_col_mass_scale(neg_sampler, num_cards, stream);
@@ -351,6 +356,7 @@ int cc_col_mass(const int32_t* counts, int64_t ld, int32_t num_cards, const doub
 // normalised -- the caller sums the blocks' vectors over the ranks (all_reduce of C doubles), then cc_col_mass_scale.
 int cc_col_mass_rows(const int32_t* counts, int64_t ld, int32_t row0, int32_t nrows, int32_t num_cards, const double* rowsum,
                      double* workspace, double* col_mass, void* stream) {
+  CC_NVTX("cc_col_mass_rows");
   CC_REQUIRE(counts && rowsum && workspace && col_mass, "cc_col_mass: null pointer");
   CC_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= num_cards, "cc_col_mass: row block outside the matrix");
   cudaStream_t st = as_stream(stream);
@@ -365,6 +371,7 @@ int cc_col_mass_rows(const int32_t* counts, int64_t ld, int32_t row0, int32_t nr
 }
 
 int cc_col_mass_scale(double* col_mass, int32_t num_cards, void* stream) {
+  CC_NVTX("cc_col_mass_scale");
   CC_REQUIRE(col_mass && num_cards > 0, "cc_col_mass_scale: bad arguments");
   col_mass_scale_kernel<<<1, 1024, 0, as_stream(stream)>>>(col_mass, num_cards);
   CC_CHECK_LAUNCH();

@@ -33,6 +33,7 @@ extern "C" {
 
 int cc_cuts_gather_f32(const float* scores, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* row_ptr,
                        const int32_t* idx, int apply_sigmoid, float* out, void* stream) {
+  CC_NVTX("cc_cuts_gather_f32");
   CC_REQUIRE(scores && row_ptr && out, "cc_cuts_gather_f32: null pointer");
   CC_REQUIRE(num_cards > 0 && batch >= 0 && ld >= num_cards, "cc_cuts_gather_f32: bad sizes");
   if (batch == 0) return CC_OK;

@@ -150,6 +150,7 @@ extern "C" {
 int cc_gemm_f32_simt(int transa, int transb, int m, int n, int k, const float* a, int64_t lda, const float* b,
                      int64_t ldb, float* c, int64_t ldc, const float* bias, int relu, const float* mask,
                      int64_t ldmask, int accumulate, void* stream) {
+  CC_NVTX("cc_gemm_f32_simt");
   CC_REQUIRE(a && b && c, "cc_gemm_f32_simt: null pointer");
   CC_REQUIRE(m >= 0 && n >= 0 && k >= 0, "cc_gemm_f32_simt: negative size");
   if (m == 0 || n == 0) return CC_OK;
@@ -171,6 +172,7 @@ int64_t cc_colsum_workspace_bytes(int m, int n) { return int64_t(ceil_div(m, CS_
 
 int cc_colsum_f32(const float* x, int64_t ld, int m, int n, float* workspace, float* out, int accumulate,
                   void* stream) {
+  CC_NVTX("cc_colsum_f32");
   CC_REQUIRE(x && workspace && out && m >= 0 && n > 0, "cc_colsum_f32: bad arguments");
   cudaStream_t st = as_stream(stream);
   const int chunks = ceil_div(m, CS_ROWS);
@@ -184,6 +186,7 @@ int cc_colsum_f32(const float* x, int64_t ld, int m, int n, float* workspace, fl
 }
 
 int cc_relu_mask_f32(float* x, int64_t ldx, const float* act, int64_t lda, int m, int n, void* stream) {
+  CC_NVTX("cc_relu_mask_f32");
   CC_REQUIRE(x && act, "cc_relu_mask_f32: null pointer");
   if (m == 0 || n == 0) return CC_OK;
   const int64_t total = int64_t(m) * n;

@@ -947,6 +947,7 @@ int cc_gemm_tc_plan(int precision, int m, int n, int k, int tile_n, int split_k,
 int cc_gemm_tc(int precision, int transa, int transb, int m, int n, int k, const void* a, int64_t lda, const void* b,
                int64_t ldb, float* c, int64_t ldc, const float* bias, int relu, const float* mask, int64_t ldmask,
                int accumulate, int split_k, int tile_n, int round_tf32, void* stream) {
+  CC_NVTX("cc_gemm_tc");
   CC_REQUIRE(a && b && c, "cc_gemm_tc: null pointer");
   CC_REQUIRE(precision == 1 || precision == 2, "cc_gemm_tc: precision must be 1 (tf32) or 2 (bf16)");
   CC_REQUIRE(m >= 0 && n >= 0 && k > 0, "cc_gemm_tc: bad sizes m=%d n=%d k=%d", m, n, k);
@@ -986,6 +987,7 @@ int cc_gemm_tc(int precision, int transa, int transb, int m, int n, int k, const
 int cc_gemm_bce_tc(int precision, int m, int n, int k, const void* a, int64_t lda, const void* w, int64_t ldw,
                    const float* bias, const uint32_t* ybits, int64_t ywords, double count, void* dz, int64_t lddz,
                    double* loss_partial, float* dbias, int round_tf32, int dz_bf16, void* stream) {
+  CC_NVTX("cc_gemm_bce_tc");
   CC_REQUIRE(a && w && bias && ybits && dz && loss_partial, "cc_gemm_bce_tc: null pointer");
   CC_REQUIRE(precision == 1 || precision == 2, "cc_gemm_bce_tc: precision must be 1 (tf32) or 2 (bf16)");
   CC_REQUIRE(m > 0 && n > 0 && k > 0 && count > 0, "cc_gemm_bce_tc: bad sizes");
@@ -1030,6 +1032,7 @@ int64_t cc_cooc_tc_workspace_bytes(int64_t num_cubes, int32_t num_cards) {
 int cc_cooc_count_tc(const int64_t* indptr, const int32_t* indices, int64_t num_cubes, int32_t num_cards,
                      void* workspace, int64_t workspace_bytes, int32_t* counts, int64_t ldc, int accumulate,
                      int32_t* bad, void* stream) {
+  CC_NVTX("cc_cooc_count_tc");
   CC_REQUIRE(indptr && indices && workspace && counts, "cc_cooc_count_tc: null pointer");
   CC_REQUIRE(num_cubes >= 0 && num_cards > 0 && ldc >= num_cards, "cc_cooc_count_tc: bad sizes");
   CC_REQUIRE(ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(counts) & 15) == 0,

@@ -839,6 +839,7 @@ int cc_softmax_kl_set_variant(int variant) {
 int cc_bce_logits_fwd_bwd(const float* z, int64_t ldz, const uint32_t* ybits, int64_t ywords, int32_t batch,
                           int32_t num_cards, int32_t ncols_pad, double count /* global B*C */, float* dz,
                           int64_t lddz, double* row_loss, void* stream) {
+  CC_NVTX("cc_bce_logits_fwd_bwd");
   CC_REQUIRE(z && ybits && row_loss, "cc_bce_logits_fwd_bwd: null pointer");
   CC_REQUIRE(num_cards > 0 && ncols_pad >= num_cards && ywords * 32 >= num_cards && count > 0,
              "cc_bce_logits_fwd_bwd: bad sizes");
@@ -862,11 +863,13 @@ int cc_softmax_kl_fuses_dbias(int32_t num_cards, int32_t ncols_pad, int64_t ldz,
 int cc_softmax_kl_fwd_bwd(const float* z, int64_t ldz, const float* target, int64_t ldt, const int32_t* target_rows,
                           int32_t rows, int32_t num_cards, int32_t ncols_pad, double grad_scale, float* dz,
                           int64_t lddz, double* row_loss, int round_tf32, float* dbias, void* stream) {
+  CC_NVTX("cc_softmax_kl_fwd_bwd");
   return cc_softmax_kl_fwd_bwd_ex(z, ldz, target, ldt, target_rows, rows, num_cards, ncols_pad, grad_scale, dz, lddz, row_loss,
                                   round_tf32, dbias, nullptr, 0, nullptr, stream);
 }
 
 int cc_kl_target_table(const float* target, int64_t ldt, int32_t target_rows, int32_t num_cards, double* tlogt, void* stream) {
+  CC_NVTX("cc_kl_target_table");
   CC_REQUIRE(target && tlogt && target_rows >= 0 && num_cards > 0 && ldt >= num_cards, "cc_kl_target_table: bad arguments");
   if (target_rows == 0) return CC_OK;
   kl_target_table_kernel<<<target_rows, 256, 0, as_stream(stream)>>>(target, ldt, num_cards, tlogt);
@@ -878,6 +881,7 @@ int cc_softmax_kl_fwd_bwd_ex(const float* z, int64_t ldz, const float* target, i
                              int32_t rows, int32_t num_cards, int32_t ncols_pad, double grad_scale, float* dz,
                              int64_t lddz, double* row_loss, int round_tf32, float* dbias, void* dz_bf16, int64_t lddz_bf16,
                              const double* tlogt, void* stream) {
+  CC_NVTX("cc_softmax_kl_fwd_bwd_ex");
   CC_REQUIRE(!tlogt || dbias, "cc_softmax_kl_fwd_bwd: the target table is used by the persistent kernel only (dbias != NULL)");
   CC_REQUIRE(z && target && row_loss, "cc_softmax_kl_fwd_bwd: null pointer");
   CC_REQUIRE(!dz_bf16 || (dbias && lddz_bf16 >= ncols_pad && lddz_bf16 % 4 == 0 && (reinterpret_cast<uintptr_t>(dz_bf16) & 7) == 0),
@@ -952,6 +956,7 @@ int cc_softmax_kl_fwd_bwd_ex(const float* z, int64_t ldz, const float* target, i
 
 int cc_loss_finalize(const double* bce_rows, int32_t nb, double bce_div, const double* kl_rows, int32_t nr,
                      double kl_div, double reg, double* out3, void* stream) {
+  CC_NVTX("cc_loss_finalize");
   CC_REQUIRE(out3 && (nb == 0 || bce_rows) && (nr == 0 || kl_rows), "cc_loss_finalize: null pointer");
   loss_finalize_kernel<<<1, 1024, 0, as_stream(stream)>>>(bce_rows, nb, bce_div, kl_rows, nr, kl_div, reg, out3);
   CC_CHECK_LAUNCH();
@@ -960,6 +965,7 @@ int cc_loss_finalize(const double* bce_rows, int32_t nb, double bce_div, const d
 
 int cc_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, const int64_t* step_ptr, float lr,
                  float beta1, float beta2, float eps, float* shadow_tf32, void* stream) {
+  CC_NVTX("cc_adam_step");
   CC_REQUIRE(params && grads && m && v && step_ptr && n >= 0, "cc_adam_step: bad arguments");
   CC_REQUIRE((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(m) |
               reinterpret_cast<uintptr_t>(v)) % 16 == 0, "cc_adam_step: buffers must be 16-byte aligned");
@@ -974,6 +980,7 @@ int cc_adam_step(float* params, const float* grads, float* m, float* v, int64_t 
 int cc_adam_step_p2p(const void* const* grads_ptrs, void* const* params_ptrs, int world, int rank, float* m, float* v,
                      int64_t lo, int64_t hi, const int64_t* step_ptr, float lr, float beta1, float beta2, float eps,
                      const void* grads_multicast, void* params_multicast, void* stream) {
+  CC_NVTX("cc_adam_step_p2p");
   CC_REQUIRE(grads_ptrs && params_ptrs && m && v && step_ptr, "cc_adam_step_p2p: null pointer");
   CC_REQUIRE(world >= 1 && world <= P2P_MAX_WORLD && rank >= 0 && rank < world, "cc_adam_step_p2p: bad world/rank");
   CC_REQUIRE(lo >= 0 && hi >= lo && lo % 4 == 0 && hi % 4 == 0, "cc_adam_step_p2p: the slice must be 4-element aligned");
@@ -1010,6 +1017,7 @@ int cc_adam_step_p2p(const void* const* grads_ptrs, void* const* params_ptrs, in
 }
 
 int cc_convert_f32_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int32_t rows, int32_t cols, void* stream) {
+  CC_NVTX("cc_convert_f32_bf16");
   CC_REQUIRE(src && dst && rows >= 0 && cols >= 0 && ld_src >= cols && ld_dst >= cols, "cc_convert_f32_bf16: bad arguments");
   CC_REQUIRE(cols % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(dst) & 7) == 0,
@@ -1023,6 +1031,7 @@ int cc_convert_f32_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_
 }
 
 int cc_round_tf32(const float* x, float* out, int64_t n, void* stream) {
+  CC_NVTX("cc_round_tf32");
   CC_REQUIRE(x && out && n >= 0, "cc_round_tf32: bad arguments");
   if (n == 0) return CC_OK;
   round_tf32_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, as_stream(stream)>>>(x, out, n);
@@ -1031,6 +1040,7 @@ int cc_round_tf32(const float* x, float* out, int64_t n, void* stream) {
 }
 
 int cc_sigmoid_f32(const float* z, float* out, int64_t n, void* stream) {
+  CC_NVTX("cc_sigmoid_f32");
   CC_REQUIRE(z && out && n >= 0, "cc_sigmoid_f32: bad arguments");
   if (n == 0) return CC_OK;
   sigmoid_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, as_stream(stream)>>>(z, out, n);

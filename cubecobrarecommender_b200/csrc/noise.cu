@@ -283,6 +283,7 @@ int cc_noise(const int64_t* indptr, const int32_t* indices, const int32_t* batch
              uint64_t seed, const int64_t* step_ptr, int32_t max_size, int32_t x_stride, int32_t* x_idx,
              int32_t* x_len, uint32_t* y_bits, int64_t y_words, int32_t* flips_out, int* overflow_flag,
              float* x_dense, int64_t ld_dense, void* stream) {
+  CC_NVTX("cc_noise");
   return cc_noise_ex(indptr, indices, batch_ids, batch, num_cards, alias_prob, alias_idx, noise_mean, noise_std, seed, step_ptr,
                      max_size, x_stride, x_idx, x_len, y_bits, y_words, flips_out, overflow_flag, x_dense, ld_dense, 0, stream);
 }
@@ -292,6 +293,7 @@ int cc_noise_ex(const int64_t* indptr, const int32_t* indices, const int32_t* ba
                 uint64_t seed, const int64_t* step_ptr, int32_t max_size, int32_t x_stride, int32_t* x_idx,
                 int32_t* x_len, uint32_t* y_bits, int64_t y_words, int32_t* flips_out, int* overflow_flag,
                 void* x_dense_v, int64_t ld_dense, int dense_bf16, void* stream) {
+  CC_NVTX("cc_noise_ex");
   float* x_dense = static_cast<float*>(x_dense_v);
   CC_REQUIRE(indptr && indices && alias_prob && alias_idx && x_idx && x_len && overflow_flag, "cc_noise: null pointer");
   CC_REQUIRE(!x_dense || (ld_dense % 4 == 0 && ld_dense >= num_cards && (reinterpret_cast<uintptr_t>(x_dense) & 15) == 0),
@@ -312,6 +314,7 @@ int cc_noise_ex(const int64_t* indptr, const int32_t* indices, const int32_t* ba
 
 int cc_sample_reg_rows(const float* alias_prob, const int32_t* alias_idx, int32_t num_cards, int32_t n, uint64_t seed,
                        const int64_t* step_ptr, int32_t* rows, void* stream) {
+  CC_NVTX("cc_sample_reg_rows");
   CC_REQUIRE(alias_prob && alias_idx && rows && num_cards > 0 && n >= 0, "cc_sample_reg_rows: bad arguments");
   if (n == 0) return CC_OK;
   reg_rows_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(alias_prob, alias_idx, num_cards, n, seed,
@@ -322,6 +325,7 @@ int cc_sample_reg_rows(const float* alias_prob, const int32_t* alias_idx, int32_
 
 int cc_cubes_to_bits(const int32_t* idx, const int64_t* row_start, const int32_t* row_len, int32_t batch,
                      int32_t num_cards, uint32_t* bits, int64_t words, void* stream) {
+  CC_NVTX("cc_cubes_to_bits");
   CC_REQUIRE(idx && row_start && row_len && bits && words * 32 >= num_cards, "cc_cubes_to_bits: bad arguments");
   if (batch == 0) return CC_OK;
   cudaStream_t st = as_stream(stream);
@@ -332,6 +336,7 @@ int cc_cubes_to_bits(const int32_t* idx, const int64_t* row_start, const int32_t
 }
 
 int cc_step_increment(int64_t* step_ptr, void* stream) {
+  CC_NVTX("cc_step_increment");
   CC_REQUIRE(step_ptr, "cc_step_increment: null pointer");
   step_increment_kernel<<<1, 1, 0, as_stream(stream)>>>(step_ptr);
   CC_CHECK_LAUNCH();

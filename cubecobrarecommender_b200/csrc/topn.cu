@@ -1050,6 +1050,7 @@ int cc_pairwise_plan_host(const int64_t* row_ptr_host, int32_t batch, int32_t* p
 int cc_score_gather_f64(const double* m, int64_t ld, int32_t num_cards, const int32_t* rows, const int64_t* row_ptr,
                         int32_t batch, const int32_t* plan, const int32_t* leaf_ptr, int32_t total_leaves,
                         int zero_diag, double* partial_ws, double* scores, int64_t ld_scores, void* stream) {
+  CC_NVTX("cc_score_gather_f64");
   CC_REQUIRE(m && rows && row_ptr && plan && leaf_ptr && partial_ws && scores, "cc_score_gather_f64: null pointer");
   CC_REQUIRE(num_cards > 0 && batch >= 0 && ld >= num_cards && ld_scores >= num_cards, "cc_score_gather_f64: bad sizes");
   if (batch == 0) return CC_OK;
@@ -1074,6 +1075,7 @@ int64_t cc_topn_workspace_bytes(int32_t num_cards, int32_t batch, int32_t n, int
 int cc_topn_masked_f32(const float* scores, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
                        const int32_t* mask_idx, int mode_only_listed, int descending, int32_t n, void* workspace,
                        int64_t workspace_bytes, int32_t* out_ids, float* out_vals, int32_t* out_count, void* stream) {
+  CC_NVTX("cc_topn_masked_f32");
   return topn_launch<float>(scores, ld, num_cards, batch, mask_ptr, mask_idx, mode_only_listed, descending, n,
                             workspace, workspace_bytes, out_ids, out_vals, out_count, as_stream(stream));
 }
@@ -1083,6 +1085,7 @@ int cc_topn_masked_f32(const float* scores, int64_t ld, int32_t num_cards, int32
 int cc_topn_masked_sigmoid_f32(const float* logits, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
                                const int32_t* mask_idx, int mode_only_listed, int descending, int32_t n,
                                int32_t* out_ids, float* out_probs, int32_t* out_count, void* stream) {
+  CC_NVTX("cc_topn_masked_sigmoid_f32");
   CC_REQUIRE(logits && mask_ptr && out_ids, "cc_topn_masked_sigmoid_f32: null pointer");
   CC_REQUIRE(num_cards > 0 && batch >= 0 && n > 0 && ld >= num_cards, "cc_topn_masked_sigmoid_f32: bad sizes");
   CC_REQUIRE(n <= WS_MAX_N, "cc_topn_masked_sigmoid_f32: n must be <= %d (use cc_sigmoid_f32 + cc_topn_masked_f32)", WS_MAX_N);
@@ -1092,6 +1095,7 @@ int cc_topn_masked_sigmoid_f32(const float* logits, int64_t ld, int32_t num_card
 }
 
 int cc_cosine_neg_f32(const float* emb, int64_t ld, int32_t rows, int32_t dim, int32_t query, float* out, void* stream) {
+  CC_NVTX("cc_cosine_neg_f32");
   CC_REQUIRE(emb && out && rows > 0 && dim > 0 && ld >= dim && query >= 0 && query < rows, "cc_cosine_neg_f32: bad arguments");
   cosine_neg_kernel<<<ceil_div(rows, 8), 256, 0, as_stream(stream)>>>(emb, ld, rows, dim, query, out);
   CC_CHECK_LAUNCH();
@@ -1104,12 +1108,14 @@ int cc_topn_set_force_radix(int on) { g_topn_force_radix = on ? 1 : 0; return CC
 // Diagnostic: the fused-sigmoid, descending row select with per-phase clock64() sums of every CTA's thread 0
 // (prof: int64 [grid][10] on the device, grid = cc_topn_rowselect_profile_grid(batch, variant); slots: see RS_PROF_SLOTS).
 int64_t cc_topn_rowselect_profile_grid(int32_t batch, int variant) {
+  CC_NVTX("cc_topn_set_force_radix");
   const int ctas = variant == 0 ? 1 : 2;
   return batch < ctas * sm_count() ? batch : ctas * sm_count();
 }
 int cc_topn_rowselect_profile(const float* logits, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
                               const int32_t* mask_idx, int32_t n, int variant, int32_t* out_ids, float* out_probs,
                               int32_t* out_count, long long* prof, void* stream) {
+  CC_NVTX("cc_topn_rowselect_profile");
   CC_REQUIRE(logits && mask_ptr && out_ids && prof, "cc_topn_rowselect_profile: null pointer");
   CC_REQUIRE(batch > 0 && n > 0 && rowselect_eligible(logits, ld, num_cards, n), "cc_topn_rowselect_profile: rows do not qualify");
   const int nbuf = variant == 0 ? 2 : 1;
@@ -1139,6 +1145,7 @@ int cc_topn_set_algo(int algo) {
 int cc_topn_masked_f64(const double* scores, int64_t ld, int32_t num_cards, int32_t batch, const int64_t* mask_ptr,
                        const int32_t* mask_idx, int mode_only_listed, int descending, int32_t n, void* workspace,
                        int64_t workspace_bytes, int32_t* out_ids, double* out_vals, int32_t* out_count, void* stream) {
+  CC_NVTX("cc_topn_masked_f64");
   return topn_launch<double>(scores, ld, num_cards, batch, mask_ptr, mask_idx, mode_only_listed, descending, n,
                              workspace, workspace_bytes, out_ids, out_vals, out_count, as_stream(stream));
 }

@@ -41,11 +41,20 @@ class RequestBatcher:
         self.q: "queue.Queue" = queue.Queue()
         self.stats = {"requests": 0, "batches": 0, "max_batch": 0}
         self._stop = False
+        self._dead = None                   # the exception that killed the worker, if any
+        dev = recommender.model.device      # the worker thread must run on the model's GPU (a new thread starts on device 0)
+        self._cuda_index = None
+        if dev.type == "cuda":
+            import torch
+            self._cuda_index = dev.index if dev.index is not None else torch.cuda.current_device()
         self.worker = threading.Thread(target=self._run, name="cubecobra-batcher", daemon=True)
         self.worker.start()
 
     def submit(self, cube_indices, amount: int) -> Future:
         fut: Future = Future()
+        if self._dead is not None or not self.worker.is_alive():
+            fut.set_exception(RuntimeError(f"the request batcher's worker thread is not running ({self._dead!r})"))
+            return fut
         self.q.put((list(cube_indices), int(amount), fut))
         return fut
 
@@ -74,20 +83,35 @@ class RequestBatcher:
         return batch
 
     def _run(self):
-        import torch
-        dev = self.rec.model.device
-        if dev.type == "cuda":
-            torch.cuda.set_device(dev)
-        while not self._stop:
-            batch = self._collect()
-            if not batch:
-                break
-            try:
-                self._serve(batch)
-            except Exception as e:  # every waiting request sees the failure (the reference re-raises per request)
-                for _, _, fut in batch:
-                    if not fut.done():
-                        fut.set_exception(e)
+        batch = []
+        try:
+            if self._cuda_index is not None:
+                import torch
+                torch.cuda.set_device(self._cuda_index)
+            while not self._stop:
+                batch = self._collect()
+                if not batch:
+                    break
+                try:
+                    self._serve(batch)
+                except Exception as e:  # every waiting request sees the failure (the reference re-raises per request)
+                    for _, _, fut in batch:
+                        if not fut.done():
+                            fut.set_exception(e)
+                batch = []
+        except BaseException as e:      # the worker itself died: nobody may be left waiting on a future
+            self._dead = e
+            pending = list(batch or [])
+            while True:
+                try:
+                    item = self.q.get_nowait()
+                except queue.Empty:
+                    break
+                if item is not None:
+                    pending.append(item)
+            for _, _, fut in pending:
+                if not fut.done():
+                    fut.set_exception(RuntimeError(f"request batcher worker died: {e!r}"))
 
     def _serve(self, batch):
         from ..sparse import CubeCSR
@@ -149,7 +173,8 @@ def get_ml_recommend(cube_name, amount, root=ROOT, non_json=False, card_names=No
         card_names = fetch_cube_list(cube_name, root)
     batcher, (int_to_card, card_to_int) = _resident()
     idxs = cube_indices(card_names, card_to_int)
-    ids, scores, results_at = batcher.submit(idxs, amount).result()     # blocks this request's thread only
+    # blocks this request's thread only; the timeout turns a wedged GPU into an error instead of a hung server thread
+    ids, scores, results_at = batcher.submit(idxs, amount).result(timeout=float(os.environ.get("CUBECOBRA_REQUEST_TIMEOUT_S", "600")))
     if non_json:
         for rec in ids:
             print(int_to_card[int(rec)])

@@ -15,6 +15,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run by the driver with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """Every test gets a wall-clock limit (pytest-timeout, when installed): a hung test must cost minutes, not a GPU
+    call's whole time limit."""
+    if config.pluginmanager.hasplugin("timeout"):
+        for item in items:
+            if item.get_closest_marker("timeout") is None:
+                item.add_marker(pytest.mark.timeout(600))
+
+
 @pytest.fixture(scope="session")
 def graph_golden():
     return dict(np.load(os.path.join(GOLDEN, "graph_small.npz")))

@@ -102,3 +102,62 @@ def test_savedmodel_key_mapping_and_clear_error(tmp_path):
     (d / "saved_model.pb").write_bytes(b"\x00")
     with pytest.raises(FileNotFoundError, match="convert_savedmodel"):
         CC_Recommender.load(str(d), device="cpu")
+
+
+def test_request_batcher_host_logic():
+    """web.ml_recommend_web.RequestBatcher with a stand-in recommender (no GPU): concurrent requests are served by one
+    batched call, every request gets its own slice (per-request amount, cuts in cubelist order, unknown cards skipped),
+    a recommender failure reaches every waiting request, and a dead worker never leaves a request hanging."""
+    import threading
+    torch = pytest.importorskip("torch")
+    from cubecobrarecommender_b200.web import ml_recommend_web as W
+
+    class FakeModel:
+        N = 50
+        device = torch.device("cpu")
+
+    class FakeRec:
+        model = FakeModel()
+        fail = False
+
+        def recommend(self, csr, n, want_cuts=False):
+            if self.fail:
+                raise ValueError("boom")
+            k = csr.num_cubes
+            ids = np.tile(np.arange(n, dtype=np.int32)[::-1], (k, 1))
+            vals = np.tile(np.linspace(1, 0, n, dtype=np.float32), (k, 1))
+            cnt = np.array([n - (r % 2) for r in range(k)], dtype=np.int32)
+            return ids, vals, cnt, (csr.indices.astype(np.float32) / 100)
+
+    rec = FakeRec()
+    saved = dict(W._state)
+    b = W.install(rec, {i: f"c{i}" for i in range(50)}, max_batch=8, max_wait_ms=300)
+    try:
+        outs = [None] * 6
+        errs = [None] * 6
+
+        def req(r):
+            try:
+                outs[r] = W.get_ml_recommend("x", 3 + r, card_names=[f"C{r + 1}", "custom card", f"c{r}", f"c{r}"])
+            except Exception as e:
+                errs[r] = e
+        ts = [threading.Thread(target=req, args=(r,)) for r in range(6)]
+        [t.start() for t in ts]
+        [t.join(30) for t in ts]
+        assert errs == [None] * 6 and b.stats["requests"] == 6 and b.stats["batches"] <= 2 and b.stats["max_batch"] >= 3
+        for r in range(6):
+            assert list(outs[r]["cuts"]) == [f"c{r + 1}", f"c{r}"]                      # cubelist order, repeats collapse
+            assert outs[r]["cuts"][f"c{r}"] == pytest.approx(r / 100)
+            assert len(outs[r]["additions"]) >= 3 + r - 1
+        rec.fail = True
+        with pytest.raises(ValueError, match="boom"):
+            W.get_ml_recommend("x", 3, card_names=["c1"])
+        rec.fail = False
+        assert W.get_ml_recommend("x", 0, card_names=["c1"])["additions"]              # amount <= 0 still yields one card
+        b.close()
+        with pytest.raises(RuntimeError, match="not running"):
+            W.get_ml_recommend("x", 3, card_names=["c1"])
+    finally:
+        b.close()
+        W._state.update(saved)
+        W._state["batcher"] = None
