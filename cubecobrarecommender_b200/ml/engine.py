@@ -25,6 +25,8 @@ from .._lib import call, ptr, stream_ptr
 from .model import (CC_Recommender, ENC_NAMES, HIDDEN, SparseBatch, bag_bwd, bag_fwd, colsum, dec_names, gemm)
 
 KERAS_ADAM = dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)
+FIRST_LAYER_TENSOR_WHEN = ("tensor",)        # which CC_FIRST_LAYER values select the tensor-core first layer ("auto" joins
+                                             # the tuple once a measurement on the B200 says it wins)
 
 
 def alias_table(p: np.ndarray, device):
@@ -88,6 +90,12 @@ class DAEEngine:
         # the small layers' weight-gradient GEMMs ([x | 1]^T dY, a few microseconds each, <= 64 CTAs) run on a side
         # stream, off the dY -> dX -> dY chain that backward is serialised on (CC_SIDE_STREAM=0 keeps one stream)
         self.use_side = os.environ.get("CC_SIDE_STREAM", "1") != "0" and self.dp_mode != "nccl_overlap"
+        # first layer of the main rows: "gather" = warp-per-cube embedding bag over W1 (exact fp32 sums), "tensor" = dense
+        # 0/1 rows x W1 on the tensor cores (tensor-core precision modes only).  CC_FIRST_LAYER overrides; see DESIGN.md
+        fl = os.environ.get("CC_FIRST_LAYER", "auto")
+        if fl not in ("auto", "gather", "tensor"):
+            raise ValueError(f"CC_FIRST_LAYER={fl!r}: expected auto, gather or tensor")
+        self.first_layer_tc = model.precision != "fp32" and fl in FIRST_LAYER_TENSOR_WHEN
         self._side = None
         self._side_events = []
         self._alloc()
@@ -140,6 +148,8 @@ class DAEEngine:
             self.md2_16, self.rd2_16, self.g1_16 = zb(B, 512), zb(max(R, 1), 512), zb(B, 512)
             self.dz1_16, self.dz2_16 = zb(B, self.cpad), zb(max(R, 1), self.cpad)      # dlogits only ever exist as bf16
             self.w4_16 = {"main": zb(512, self.cpad), "reg": zb(512, self.cpad)}         # bf16 copies of the two 512 x C kernels
+            if self.first_layer_tc:
+                self.w1_16 = zb(self.C, 512)                                             # and of the C x 512 first-layer kernel
         if self.precision != "fp32":
             self.x_dense = torch.zeros((B, self.cpad), dtype=torch.bfloat16 if self.big16 else f32, device=d)
             if self.C % 4:
@@ -247,8 +257,23 @@ class DAEEngine:
                 to_bf16(P(dec_names(prefix)[3] + "/kernel"), self.w4_16[prefix])
                 n_launch += 1
         a1 = self.a[0]
-        with self._timed("bag_fwd"):
-            bag_fwd(P("encoder_e1/kernel"), x.idx, x.row_start, x.row_len, P("encoder_e1/bias"), a1[:B], round_tf32=tc)
+        if self.first_layer_tc:
+            # first layer of the main rows on the tensor cores: x W1 over the dense 0/1 rows the noise kernel already
+            # writes for the dW1 GEMM (x is exact in tf32 / bf16; W1 from the tf32 shadow, or a bf16 copy).  The gather
+            # moves s * 2 KB = 1.1 MB per cube out of L2 and sits on the L2 -> SM cap; this is one more 2*B*512*C pass
+            if big16:
+                to_bf16(P("encoder_e1/kernel"), self.w1_16)
+                n_launch += 1
+            with self._timed("fw1_gemm"):
+                if big16:
+                    gemm(self.x_dense[:, :self.C], self.w1_16, a1[:B], bias=P("encoder_e1/bias"), relu=True,
+                         precision="bf16", round_out=True)
+                else:
+                    gemm(self.x_dense[:, :self.C], W("encoder_e1/kernel"), a1[:B], bias=P("encoder_e1/bias"), relu=True,
+                         precision=pr, round_out=True)
+        else:
+            with self._timed("bag_fwd"):
+                bag_fwd(P("encoder_e1/kernel"), x.idx, x.row_start, x.row_len, P("encoder_e1/bias"), a1[:B], round_tf32=tc)
         n_launch += 1
         if R:
             bag_fwd(P("encoder_e1/kernel"), self.reg_rows, self.reg_start, self.reg_len, P("encoder_e1/bias"), a1[B:],
@@ -503,7 +528,7 @@ class DAEEngine:
         if s.shadow is not None:
             # tf32 copy of the parameters for the tensor-core GEMMs.  The first-layer kernel (a third of all
             # parameters) is skipped: it is only ever read by the embedding-bag gather, which takes the master copy.
-            off = s.layout["encoder_e1/bias"][0]
+            off = 0 if (self.first_layer_tc and not self.big16) else s.layout["encoder_e1/bias"][0]
             call("cc_round_tf32", ptr(s.params[off:]), ptr(s.shadow[off:]), s.total - off, st)
             self.launches += 1
         call("cc_step_increment", ptr(s.step), st)

@@ -345,6 +345,19 @@ TOL = {"fp32": dict(loss=1e-5, grad=2e-4, grad_later=2e-4, weight=3e-4),
 @pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
 @pytest.mark.parametrize("r", [48, 0])
 def test_train_steps_match_oracle(r, precision):
+    _train_steps_vs_oracle(r, precision)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_train_steps_match_oracle_first_layer_on_tensor_cores(precision, monkeypatch):
+    """CC_FIRST_LAYER=tensor: the main rows' first layer as a dense x W1 GEMM on the tensor cores instead of the
+    embedding-bag gather -- same tolerances against the float64 oracle."""
+    monkeypatch.setenv("CC_FIRST_LAYER", "tensor")
+    eng = _train_steps_vs_oracle(48, precision)
+    assert eng.first_layer_tc
+
+
+def _train_steps_vs_oracle(r, precision):
     c, x, y, rows, mh = _problem(r=max(r, 1))
     rows = rows[:r]
     params = od.init_params(c, seed=0)
@@ -388,6 +401,7 @@ def test_train_steps_match_oracle(r, precision):
         if not r and kname.startswith("reg_"):
             continue
         assert np.abs(pd[kname] - pref).max() < tol["weight"], kname   # 3 Adam steps move weights by <= 3e-3
+    return eng
 
 
 def test_model_call_api_parity():
