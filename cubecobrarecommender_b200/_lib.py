@@ -71,6 +71,8 @@ SIGNATURES = {
     "cc_gemm_bce_partial_count": (I64, [I, I]),
     "cc_gemm_tc_set_pair_mode": (I, [I]),
     "cc_gemm_tc_plan": (I, [I, I, I, I, I, I, P]),
+    "cc_gemm_tc_plan_ex": (I, [I, I, I, I, I, I, P]),
+    "cc_gemm_tc_set_stream_k": (I, [I]),
     "cc_gemm_tc_set_dynamic_tiles": (I, [I]),
     "cc_gemm_tc_set_pdl": (I, [I]),
     "cc_colsum_workspace_bytes": (I64, [I, I]),

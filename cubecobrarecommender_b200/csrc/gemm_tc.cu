@@ -25,6 +25,9 @@
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "cc_common.cuh"
 
 namespace cc {
@@ -70,6 +73,10 @@ struct Params {
   float* dbias;                          // EPI_BCE: column sums of dlogits (= the output layer's bias gradient), atomically added
   int a_mn_major, b_mn_major;
   int* sched;                            // {next-tile counter, finished units}: self-resetting (see TileRing)
+  // hybrid stream-K (static scheduling only): the first dp_tiles output tiles are walked round-robin with their whole
+  // K range and stored; the LAST sk_tiles tiles are cut along K into num_units contiguous spans of k-blocks, one per
+  // unit, and every span is TMA-reduce-added into the (pre-zeroed) tile.  sk_tiles = 0: off.
+  int dp_tiles, sk_tiles;
   // EPI_COUNT: C = A A^T is symmetric -> only tiles with nt >= mt are computed (square 256 x 256 pair tiles) and every
   // off-diagonal tile is also written transposed
   int symmetric;
@@ -270,6 +277,32 @@ __device__ __forceinline__ void decode_tile(const Params& p, int tile, int& mt, 
   }
 }
 
+// One unit's walk over its work in hybrid stream-K mode: its share of the data-parallel tiles first, then its span of
+// the stream-K tiles' k-blocks (which may cover the tail of one tile, whole tiles, and the head of another).  Every
+// role of the CTA (TMA producer, MMA issuer, epilogue warps) runs the same walk.
+struct SkWalk {
+  int dp_next; long long cur, hi;
+  __device__ __forceinline__ void init(const Params& p, int unit, int num_units) {
+    dp_next = unit;
+    const long long total = (long long)p.sk_tiles * p.total_k_blocks;
+    cur = total * unit / num_units;
+    hi = total * (unit + 1) / num_units;
+  }
+  __device__ __forceinline__ bool next(const Params& p, int num_units, int& tile, int& kb0, int& kb1) {
+    if (dp_next < p.dp_tiles) { tile = dp_next; dp_next += num_units; kb0 = 0; kb1 = p.total_k_blocks; return true; }
+    if (cur < hi) {
+      const int t = int(cur / p.total_k_blocks);
+      kb0 = int(cur - (long long)t * p.total_k_blocks);
+      const long long left = hi - cur;
+      kb1 = (long long)(p.total_k_blocks - kb0) <= left ? p.total_k_blocks : kb0 + int(left);
+      tile = p.dp_tiles + t;
+      cur += kb1 - kb0;
+      return true;
+    }
+    return false;
+  }
+};
+
 template <int KIND, int EPI, int BN, int CTAS>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -349,16 +382,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int t = cur < 0 ? unit : cur + num_units;
     return t < total_tiles ? t : -1;
   };
+  const bool stream_k = p.sk_tiles > 0;         // (never together with the dynamic scheduler or the symmetric GEMM)
+  SkWalk walk;
+  walk.init(p, unit, num_units);
+  // next piece of work for the calling role: tile (-1: done) and its k-block range
+  auto next_work = [&](int& tile, int& kb0, int& kb1) {
+    if (stream_k) {
+      if (!walk.next(p, num_units, tile, kb0, kb1)) tile = -1;
+      return;
+    }
+    tile = next_tile(tile);
+    if (tile < 0) return;
+    int mt_, nt_, ks_;
+    decode_tile(p, tile, mt_, nt_, ks_);
+    kb0 = ks_ * p.k_blocks;
+    kb1 = min(kb0 + p.k_blocks, p.total_k_blocks);
+  };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = next_tile(-1); tile >= 0; tile = next_tile(tile)) {
+      int tile = -1, kb0 = 0, kb1 = 0;
+      for (next_work(tile, kb0, kb1); tile >= 0; next_work(tile, kb0, kb1)) {
         int mt, nt, ks;
         decode_tile(p, tile, mt, nt, ks);
-        const int kb0 = ks * p.k_blocks;
-        const int kb1 = min(kb0 + p.k_blocks, p.total_k_blocks);
         const int a_row0 = (mt * CTAS + cta_rank) * BM;             // this CTA's 128 rows of the (pair) tile
         const int b_row0 = nt * BN + cta_rank * BN_LOAD;            // and its share of the B tile
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -422,11 +470,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t a_kstep = p.a_mn_major ? UMMA_K * 128 : 32, b_kstep = p.b_mn_major ? UMMA_K * 128 : 32;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = next_tile(-1); tile >= 0; tile = next_tile(tile)) {
-        int mt_, nt_, ks;
-        decode_tile(p, tile, mt_, nt_, ks);
-        const int kb0 = ks * p.k_blocks;
-        const int kb1 = min(kb0 + p.k_blocks, p.total_k_blocks);
+      int tile = -1, kb0 = 0, kb1 = 0;
+      for (next_work(tile, kb0, kb1); tile >= 0; next_work(tile, kb0, kb1)) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -485,18 +530,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint8_t* sbuf = epi_smem + (warp - 4) * 4096;           // one 4 KB staging buffer (32 rows x 128 B, 128B-swizzled)
     int acc = 0; uint32_t acc_phase = 0;
     const uint32_t leader_tmem_empty = CTAS == 2 ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : 0u;
-    int tile = -1;
+    int tile = -1, wkb0 = 0, wkb1 = 0;
     while (true) {
       if (dynamic) {
         if (lane == 0) tile = ring_next<CTAS>(ring);
         tile = __shfl_sync(0xffffffffu, tile, 0);
       } else {
-        tile = next_tile(tile);
+        next_work(tile, wkb0, wkb1);
       }
       if (tile < 0) break;
       int mt, nt, ks;
       decode_tile(p, tile, mt, nt, ks);
-      const bool has_k = ks * p.k_blocks < p.total_k_blocks;
+      const bool has_k = stream_k ? (wkb0 < wkb1) : (ks * p.k_blocks < p.total_k_blocks);
+      // a stream-K span that does not cover its tile's whole K range is one of several contributions to it
+      const bool red_add = p.reduce_add || (stream_k && (wkb0 != 0 || wkb1 != p.total_k_blocks));
       const int row0 = (mt * CTAS + cta_rank) * BM + q * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.m;
@@ -630,7 +677,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (p.reduce_add) tma_reduce_add_2d(&map_c, sbuf, col0, row0);
+          if (red_add) tma_reduce_add_2d(&map_c, sbuf, col0, row0);
           else              tma_store_2d(&map_c, sbuf, col0, row0);
           tma_commit_group();
         }
@@ -765,16 +812,41 @@ static double plan_eff(int m, int n, int kblocks, int bn, int split, int sms, in
 constexpr int SCHED_POOL = 4096;
 static int* sched_slot() {
   static int* pools[64] = {nullptr};
-  static unsigned next[64] = {0};
+  static std::atomic<unsigned> next[64];
+  static std::mutex mu;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  if (!pools[dev]) {
-    int* ptr = nullptr;
-    if (cudaMalloc(&ptr, SCHED_POOL * 2 * sizeof(int)) != cudaSuccess) return nullptr;
-    if (cudaMemset(ptr, 0, SCHED_POOL * 2 * sizeof(int)) != cudaSuccess) return nullptr;
-    pools[dev] = ptr;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!pools[dev]) {
+      int* ptr = nullptr;
+      if (cudaMalloc(&ptr, SCHED_POOL * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+      if (cudaMemset(ptr, 0, SCHED_POOL * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+      pools[dev] = ptr;
+    }
   }
-  return pools[dev] + 2 * (next[dev]++ % SCHED_POOL);
+  return pools[dev] + 2 * (next[dev].fetch_add(1) % SCHED_POOL);
+}
+
+// Hybrid stream-K plan: how many of the m_tiles x n_tiles output tiles (the last ones) are cut along K and spread over
+// all `units`.  Whole waves of tiles stay data-parallel (stored once, no reduction); what does not fill a wave -- the
+// 16 left-over tiles of the 164-tile dW pass on 74 CTA pairs, or all 32 tiles of the long-K dX pass -- is spread evenly,
+// so no unit idles through a ragged last wave and only those tiles pay read-modify-write traffic (with plain split-K
+// EVERY tile is reduce-added split_k times: ncu showed 131 MB written for a 42.8 MB dW).  0 = plain data-parallel.
+// Only for long-K passes (>= 64 k-blocks): a short-K pass loses little to its ragged wave and its spans would be all
+// prologue.
+static int stream_k_tiles(int m_tiles, int n_tiles, int k_blocks, int units) {
+  const int t = m_tiles * n_tiles;
+  if (units <= 0 || k_blocks < 64) return 0;
+  const int full = t / units, rem = t - full * units;
+  if (rem == 0) return 0;
+  int sk = rem;
+  // spans shorter than ~16 k-blocks are all prologue/epilogue: fold one full wave into the stream-K part instead
+  if (full >= 1 && (long long)rem * k_blocks / units < 16) sk = rem + units;
+  if (sk > t) sk = t;
+  // not worth it when the stream-K part is nearly a full wave anyway (the ragged wave wastes < 10%)
+  if (full >= 1 && rem * 10 >= units * 9) return 0;
+  return sk;
 }
 
 // programmatic dependent launch of consecutive GEMMs (cc_gemm_tc_set_pdl; on by default, CC_GEMM_PDL=0 disables)
@@ -787,6 +859,25 @@ static int g_dynamic_tiles = 0;
 
 // -1 = planner decides, 0 = never pair, 1 = always pair (cc_gemm_tc_set_pair_mode; experiments and tests)
 static int g_pair_mode = -1;
+
+// -1 = planner decides between plain split-K and hybrid stream-K, 0 = never stream-K, 1 = stream-K whenever the tile count
+// leaves a ragged wave (cc_gemm_tc_set_stream_k; tests and A/B measurements)
+static int g_stream_k = getenv("CC_GEMM_STREAM_K") ? atoi(getenv("CC_GEMM_STREAM_K")) : -1;
+
+// the waves model of plan_eff for the hybrid stream-K schedule of (bn, ctas): full data-parallel waves, then every
+// unit's span of the stream-K k-blocks (two partial tiles' worth of prologue/epilogue)
+static double plan_eff_sk(int m, int n, int kblocks, int bn, int sms, int ctas) {
+  const int units = sms / ctas;
+  const int mt = ceil_div(m, BM * ctas), nt = ceil_div(n, bn);
+  const int sk = stream_k_tiles(mt, nt, kblocks, units);
+  if (sk == 0) return -1.0;
+  const int dp = mt * nt - sk;
+  const long long span = (long long)ceil_div(dp, units) * (kblocks + 6) + ceil_div<long long>((long long)sk * kblocks, units) + 12;
+  const double busy = double(m) / (BM * ctas) * nt * kblocks;
+  double eff = busy / (double(units) * double(span));
+  if (ctas == 1) eff *= (bn == 128 ? 0.68 : 0.80);
+  return eff * 0.99;          // zero fill + reduce traffic of the stream-K tiles only
+}
 
 static int max_pair_clusters(const void* kern, int smem_bytes) {
   cudaLaunchConfig_t cfg = {};
@@ -832,26 +923,64 @@ static int launch_bn(const Problem& pr, Params p, cudaStream_t st) {
   if (p.split_k < 1) p.split_k = 1;
   p.k_blocks = ceil_div(p.total_k_blocks, p.split_k);
   p.split_k = ceil_div(p.total_k_blocks, p.k_blocks);
-  const int tiles = p.symmetric ? p.n_tiles * (p.n_tiles + 1) / 2 : p.m_tiles * p.n_tiles * p.split_k;
+  int tiles = p.symmetric ? p.n_tiles * (p.n_tiles + 1) / 2 : p.m_tiles * p.n_tiles * p.split_k;
   p.sched = nullptr;
   if (g_dynamic_tiles) {
     p.sched = sched_slot();
     if (!p.sched) { set_error("cc_gemm_tc: could not allocate the tile-scheduler counters"); return CC_ERR_CUDA; }
   }
   auto kern = gemm_tc_kernel<KIND, EPI, BN, CTAS>;
-  static bool attr_done = false;
-  static int max_clusters = 0;
-  if (!attr_done) {
-    CC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    if (CTAS == 2) {
-      max_clusters = max_pair_clusters(reinterpret_cast<const void*>(kern), C::SMEM_BYTES);
-      if (max_clusters <= 0) { set_error("cc_gemm_tc: no CTA-pair cluster can be resident (occupancy query)"); return CC_ERR_CUDA; }
-      if (max_clusters > sm_count() / 2) max_clusters = sm_count() / 2;
+  // per-device one-time setup (a process may drive several GPUs: one host thread or process per device)
+  static std::mutex setup_mu;
+  static bool attr_done[64] = {false};
+  static int max_clusters_dev[64] = {0};
+  int dev = 0;
+  CC_CHECK_CUDA(cudaGetDevice(&dev));
+  CC_REQUIRE(dev >= 0 && dev < 64, "cc_gemm_tc: device ordinal %d out of range", dev);
+  {
+    std::lock_guard<std::mutex> lk(setup_mu);
+    if (!attr_done[dev]) {
+      CC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+      if (CTAS == 2) {
+        int mc = max_pair_clusters(reinterpret_cast<const void*>(kern), C::SMEM_BYTES);
+        if (mc <= 0) { set_error("cc_gemm_tc: no CTA-pair cluster can be resident (occupancy query)"); return CC_ERR_CUDA; }
+        if (mc > sm_count() / 2) mc = sm_count() / 2;
+        max_clusters_dev[dev] = mc;
+      }
+      attr_done[dev] = true;
     }
-    attr_done = true;
+  }
+  const int max_units = CTAS == 2 ? max_clusters_dev[dev] : sm_count();
+  // hybrid stream-K (p.sk_tiles < 0 on entry = "choose"): see Params.  Only with static scheduling.
+  if (p.sk_tiles < 0) {
+    p.sk_tiles = 0;
+    if (!p.symmetric && !p.sched && p.split_k == 1) p.sk_tiles = stream_k_tiles(p.m_tiles, p.n_tiles, p.total_k_blocks, max_units);
+  }
+  p.dp_tiles = 0;
+  if (p.sk_tiles > 0) {
+    p.dp_tiles = p.m_tiles * p.n_tiles - p.sk_tiles;
+    if (!p.reduce_add) {
+      // the stream-K tiles are the last sk_tiles of the row-fastest tile order: the lower part of tile column nt0 (from
+      // tile row mt0 on) and every column after it.  They are zeroed (two 2-D memsets); every span is reduce-added.
+      const int nt0 = p.dp_tiles / p.m_tiles, mt0 = p.dp_tiles % p.m_tiles;
+      const long long col0 = (long long)nt0 * BN, row0 = (long long)mt0 * BM * CTAS;
+      long long colf = col0;                                 // first FULL stream-K column
+      if (mt0 > 0 && col0 < p.n_store) {
+        const long long w = (col0 + BN < p.n_store ? BN : p.n_store - col0);
+        if (row0 < pr.m)
+          CC_CHECK_CUDA(cudaMemset2DAsync(pr.c + row0 * pr.ldc + col0, size_t(pr.ldc) * 4, 0, size_t(w) * 4, size_t(pr.m - row0), st));
+        colf = col0 + BN;
+      }
+      if (colf < p.n_store)
+        CC_CHECK_CUDA(cudaMemset2DAsync(pr.c + colf, size_t(pr.ldc) * 4, 0, size_t(p.n_store - colf) * 4, pr.m, st));
+    }
   }
   {
-    const int units = CTAS == 2 ? (tiles < max_clusters ? tiles : max_clusters) : (tiles < sm_count() ? tiles : sm_count());
+    int units = tiles < max_units ? tiles : max_units;
+    if (p.sk_tiles > 0) {       // every unit takes a span of the stream-K k-blocks
+      const long long iters = (long long)p.sk_tiles * p.total_k_blocks;
+      units = iters < max_units ? int(iters) : max_units;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(unsigned(CTAS * units));
     cfg.blockDim = dim3(THREADS);
@@ -918,13 +1047,25 @@ extern "C" {
 // The planner behind cc_gemm_tc (host logic only: no device work): plan = {tile width, K split, CTAs per tile}.
 // Candidates: (tile width, CTA pairing, K split); pairs only come as 256 x 256 tiles.
 int cc_gemm_tc_plan(int precision, int m, int n, int k, int tile_n, int split_k, int* plan) {
+  int p4[4];
+  const int rc = cc_gemm_tc_plan_ex(precision, m, n, k, tile_n, split_k, p4);
+  if (rc != CC_OK) return rc;
+  CC_REQUIRE(plan, "cc_gemm_tc_plan: null plan");
+  plan[0] = p4[0]; plan[1] = p4[1]; plan[2] = p4[2];
+  return CC_OK;
+}
+
+// plan = {tile width, K split, CTAs per tile, hybrid stream-K (0 | 1)}.  Stream-K is only considered when the caller
+// leaves the split to the planner (split_k == 0) and the dynamic tile scheduler is off; it comes with K split 1.
+int cc_gemm_tc_plan_ex(int precision, int m, int n, int k, int tile_n, int split_k, int* plan) {
   CC_REQUIRE(plan && (precision == 1 || precision == 2) && m > 0 && n > 0 && k > 0, "cc_gemm_tc_plan: bad arguments");
   const int kblocks = ceil_div(k, precision == 2 ? 64 : 32);
   const int sms = sm_count();
-  int bn = tile_n, split = split_k, ctas = 1;
+  int bn = tile_n, split = split_k, ctas = 1, sk = 0;
   double best = -1.0;
   const int bns[3] = {256, 256, 128};
   const int cts[3] = {2, 1, 1};
+  const bool sk_allowed = split_k == 0 && tc::g_stream_k != 0 && !tc::g_dynamic_tiles;
   for (int bi = 0; bi < 3; ++bi) {
     if (tile_n && bns[bi] != tile_n) continue;
     if (!tile_n && bns[bi] == 256 && n <= 128) continue;
@@ -935,10 +1076,16 @@ int cc_gemm_tc_plan(int precision, int m, int n, int k, int tile_n, int split_k,
     const int smax = split_k > 0 ? split_k : (kblocks >= 16 ? (kblocks / 8 < 64 ? kblocks / 8 : 64) : 1);
     for (int s = (split_k > 0 ? split_k : 1); s <= smax; ++s) {
       const double e = tc::plan_eff(m, n, kblocks, bns[bi], s, sms, cts[bi]);
-      if (e > best + 1e-9) { best = e; bn = bns[bi]; split = s; ctas = cts[bi]; }
+      if (e > best + 1e-9) { best = e; bn = bns[bi]; split = s; ctas = cts[bi]; sk = 0; }
+    }
+    // stream-K pays off on the big passes only (a small layer is a handful of tiles: latency-bound either way)
+    if (sk_allowed && (tc::g_stream_k == 1 || 2.0 * m * n * double(k) >= 2.0e10)) {
+      double e = tc::plan_eff_sk(m, n, kblocks, bns[bi], sms, cts[bi]);
+      if (tc::g_stream_k == 1 && e > 0) e += 1.0;           // forced: beats every split plan of this shape
+      if (e > best + 1e-9) { best = e; bn = bns[bi]; split = 1; ctas = cts[bi]; sk = 1; }
     }
   }
-  plan[0] = bn; plan[1] = split; plan[2] = ctas;
+  plan[0] = bn; plan[1] = split; plan[2] = ctas; plan[3] = sk;
   return CC_OK;
 }
 
@@ -954,17 +1101,18 @@ int cc_gemm_tc(int precision, int transa, int transb, int m, int n, int k, const
   CC_REQUIRE(tile_n == 0 || tile_n == 128 || tile_n == 256, "cc_gemm_tc: tile_n must be 0, 128 or 256");
   if (m == 0 || n == 0) return CC_OK;
   cudaStream_t st = as_stream(stream);
-  int plan[3];
-  cc_gemm_tc_plan(precision, m, n, k, tile_n, split_k, plan);
-  const int bn = plan[0], split = plan[1], ctas = plan[2];
+  int plan[4];
+  cc_gemm_tc_plan_ex(precision, m, n, k, tile_n, split_k, plan);
+  const int bn = plan[0], split = plan[1], ctas = plan[2], sk = plan[3];
   const bool nonlinear = bias || relu || mask || round_tf32;
-  const bool two_pass = split > 1 && nonlinear;
+  const bool two_pass = (split > 1 || sk) && nonlinear;
   CC_REQUIRE(!(two_pass && accumulate), "cc_gemm_tc: accumulate with a split-K non-linear epilogue is not supported");
   tc::Params p{};
   p.m = m; p.n = n; p.k = k; p.n_store = n;
   p.bias = two_pass ? nullptr : bias; p.mask = two_pass ? nullptr : mask; p.ldmask = ldmask;
   p.relu = two_pass ? 0 : relu; p.round_tf32 = two_pass ? 0 : round_tf32;
   p.split_k = split;
+  p.sk_tiles = sk ? -1 : 0;              // -1: launch_bn sizes the stream-K part for the units it can actually run
   p.reduce_add = (accumulate || split > 1) ? 1 : 0;
   if (split > 1 && !accumulate)
     CC_CHECK_CUDA(cudaMemset2DAsync(c, size_t(ldc) * 4, 0, size_t(n) * 4, m, st));
@@ -1087,6 +1235,12 @@ int cc_gemm_tc_set_pdl(int on) {
 
 int cc_gemm_tc_set_dynamic_tiles(int on) {
   tc::g_dynamic_tiles = on ? 1 : 0;
+  return CC_OK;
+}
+
+int cc_gemm_tc_set_stream_k(int mode) {
+  CC_REQUIRE(mode >= -1 && mode <= 1, "cc_gemm_tc_set_stream_k: mode must be -1 (auto), 0 (off) or 1 (on)");
+  tc::g_stream_k = mode;
   return CC_OK;
 }
 

@@ -218,6 +218,12 @@ int cc_gemm_tc_set_pair_mode(int mode);
 /* The planner cc_gemm_tc uses (host logic, no device work): plan[0] = tile width (128 | 256), plan[1] = K split,
  * plan[2] = CTAs per tile (1, or 2 = a 256 x 256 CTA-pair tile), from a wave-quantisation model over the SM count. */
 int cc_gemm_tc_plan(int precision, int m, int n, int k, int tile_n, int split_k, int* plan);
+/* plan4 = {tile width, K split, CTAs per tile, hybrid stream-K (0 | 1)}.  Hybrid stream-K: whole waves of output tiles
+ * stay data-parallel, the tiles that would leave a ragged last wave are cut along K into one contiguous span of k-blocks
+ * per CTA (pair) and TMA-reduce-added -- only those tiles pay read-modify-write traffic. */
+int cc_gemm_tc_plan_ex(int precision, int m, int n, int k, int tile_n, int split_k, int* plan4);
+/* -1 = the planner decides between split-K and hybrid stream-K (default), 0 = never stream-K, 1 = whenever possible. */
+int cc_gemm_tc_set_stream_k(int mode);
 /* Tile scheduling of the persistent tcgen05 GEMMs: 0 (default) = static round-robin, 1 = tiles drawn at run time from
  * a global atomic counter, so CTAs that start late or lose their SM to a concurrent kernel (an NCCL all_reduce
  * overlapping backward) take fewer tiles instead of stretching the GEMM. */

@@ -265,6 +265,51 @@ def test_gemm_tcgen05_tf32_all_layouts(ta, tb, m, n, k, split, tile_n, pair_mode
         assert (c4.double() - torch.relu(ref + bias.double())).abs().max().item() / scale < tol
 
 
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("ta,tb,m,n,k", [(1, 0, 512, 5000, 4096),      # dW-like: fewer tiles than units, all stream-K
+                                         (0, 1, 2500, 512, 20992),     # dX-like: long K, non-linear epilogue (two passes)
+                                         (1, 0, 768, 20000, 2048),     # data-parallel waves + a stream-K tail that starts
+                                         (1, 1, 1030, 3000, 4104)])    # mid-column; ragged M/N/K
+def test_gemm_tcgen05_hybrid_stream_k(ta, tb, m, n, k, pair, precision, pair_mode):
+    """Hybrid stream-K schedule (forced on): whole tile waves data-parallel, the rest cut along K into one span per CTA
+    (pair) and TMA-reduce-added into pre-zeroed tiles.  Against float64 on exactly representable operands; plain
+    store, accumulate, and the non-linear epilogue (bias + ReLU + mask + tf32 rounding as a second pass)."""
+    from cubecobrarecommender_b200 import _lib
+    from cubecobrarecommender_b200.ml import tensorcore as TC
+    pair_mode(pair)
+    _lib.call("cc_gemm_tc_set_stream_k", 1)
+    try:
+        plan = np.zeros(4, dtype=np.int32)
+        _lib.call("cc_gemm_tc_plan_ex", 1 if precision == "tf32" else 2, m, n, k, 0, 0, _lib.ptr(plan))
+        assert plan[3] == 1 and plan[1] == 1 and plan[2] == 1 + pair
+        g = torch.Generator(device="cuda").manual_seed(m + n + k)
+        cast = (lambda t: _rn_tf32(t)) if precision == "tf32" else (lambda t: t.to(torch.bfloat16))
+        a = cast(torch.randn((k, m) if ta else (m, k), device="cuda", generator=g))
+        b = cast(torch.randn((n, k) if tb else (k, n), device="cuda", generator=g))
+        ref = (a.t() if ta else a).double() @ (b.t() if tb else b).double()
+        scale = ref.abs().max().item()
+        tol = 2e-5 + 4e-9 * k
+        c = torch.full((m, n), 7.0, device="cuda")            # garbage: the stream-K tiles must be zeroed by the call
+        TC.gemm(a, b, c, transa=bool(ta), transb=bool(tb), precision=precision)
+        assert (c.double() - ref).abs().max().item() / scale < tol
+        c2 = torch.ones((m, n), device="cuda")
+        TC.gemm(a, b, c2, transa=bool(ta), transb=bool(tb), accumulate=True, precision=precision)
+        assert (c2.double() - ref - 1).abs().max().item() / scale < tol
+        bias = torch.randn(n, device="cuda", generator=g)
+        mask = torch.randn(m, n, device="cuda", generator=g)
+        c3 = torch.full((m, n), 7.0, device="cuda")
+        TC.gemm(a, b, c3, transa=bool(ta), transb=bool(tb), bias=bias, relu=True, mask=mask, precision=precision, round_out=True)
+        ref3 = torch.relu(ref + bias.double()) * (mask > 0)
+        assert (c3.double() - ref3).abs().max().item() / scale < 6e-4 and torch.equal(c3, _rn_tf32(c3))
+        # a padded output (leading dimension > n): the zero fill and the reduce-adds respect the row stride
+        buf = torch.full((m, n + 12), 5.0, device="cuda")
+        TC.gemm(a, b, buf[:, :n], transa=bool(ta), transb=bool(tb), precision=precision)
+        assert (buf[:, :n].double() - ref).abs().max().item() / scale < tol and (buf[:, n:] == 5.0).all()
+    finally:
+        _lib.call("cc_gemm_tc_set_stream_k", -1)
+
+
 @pytest.mark.parametrize("pair", [0, 1])
 def test_gemm_tcgen05_dynamic_tile_scheduler_many_tiles(pair, pair_mode):
     """Far more tiles than persistent CTAs (or CTA pairs): after its first tile every unit draws the rest from the

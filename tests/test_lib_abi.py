@@ -81,8 +81,23 @@ def test_gemm_planner_choices(lib):
         bn, split, ctas = plan(m, n, k)
         assert (bn, ctas) == (256, 2)
         tiles = -(-m // 256) * -(-n // 256) * split
-        assert tiles >= 74                                                  # at least one full wave of CTA pairs
-    assert plan(B, C, H)[1] == 1 and plan(B, H, C)[1] > 1                    # only the long-K pass is split
+        sk = np.zeros(4, dtype=np.int32)
+        _lib.call("cc_gemm_tc_plan_ex", 1, m, n, k, 0, 0, _lib.ptr(sk))
+        assert tiles >= 74 or sk[3] == 1       # a full wave of CTA pairs, or stream-K spans spread over all of them
+    def plan4(m, n, k, precision=1):
+        out = np.zeros(4, dtype=np.int32)
+        _lib.call("cc_gemm_tc_plan_ex", precision, m, n, k, 0, 0, _lib.ptr(out))
+        return tuple(int(v) for v in out)
+    # the forward pass (16 k-blocks, bias epilogue) stays data-parallel and unsplit; the three gradient passes (K = 4096
+    # or 20 884: ragged tile waves) take the hybrid stream-K schedule, which comes with K split 1
+    assert plan4(B, C, H) == (256, 1, 2, 0)
+    for m, n, k in ((H, C, B), (B, H, C), (C, H, B)):
+        assert plan4(m, n, k) == (256, 1, 2, 1) and plan4(m, n, k, precision=2) == (256, 1, 2, 1)
+    _lib.call("cc_gemm_tc_set_stream_k", 0)
+    try:
+        assert plan(B, C, H)[1] == 1 and plan(B, H, C)[1] > 1 and plan4(B, H, C)[3] == 0      # plain split-K when switched off
+    finally:
+        _lib.call("cc_gemm_tc_set_stream_k", -1)
     for m, n, k in ((8192, 256, 512), (8192, 128, 256), (4096, 512, 256), (512, 256, 8192), (64, 128, 4096)):
         assert plan(m, n, k)[2] == 1                                        # small layers: latency-bound, single CTAs
     assert plan(8192, 64, 128)[0] == 128                                    # narrow outputs never take 256-wide tiles
