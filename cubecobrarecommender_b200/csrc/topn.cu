@@ -573,20 +573,19 @@ __device__ __forceinline__ void rs_rank32_partial(const uint32_t* a, int* rk, in
 // PROF: thread 0 accumulates clock64() deltas per phase and writes them to prof[blockIdx.x][RS_PROF_SLOTS] (diagnostic
 // instantiation behind cc_topn_rowselect_profile; the product instantiations compile the stamps out)
 //
-// NEXT: the round-2 candidate (cc_topn_set_algo(4); not the default, NOT yet run on a GPU).  It answers the phase
-// profile of the shipped kernel: (a) the (begin, end) pair of the mask list two cubes ahead is loaded by
-// ONE thread and handed over through shared memory behind a barrier -- the compiler turned the per-thread prefetch into
-// an immediate R2UR wait on the load; (b) a thread parks its first two survivors of a sweep in registers and the warp
-// appends them afterwards with one prefix sum and ONE shared-memory atomic, instead of a diverged vote -> ATOMS -> SHFL
-// chain per survivor (the slowest warp's chains are what the other fifteen wait for at the barrier: sweep 2 took four
-// times as long as sweep 1 over the same data); (c) a leader / a survivor is ranked by
-// four NEIGHBOURING lanes that add their counts with two shuffles, so the rank array, its atomics and two of the
-// seven barriers per cube go away, and the ranks are written out where they are computed; (d) the next row is
-// issued by a thread of a warp that has no ranking work.
+// REGS (cc_topn_set_algo(4), the default since round 2 when the row fits RS_GROUPS float4 per thread): the ncu source
+// view of the kernel without it (profiles/r02/topn_rowselect_stalls.txt) shows where a cube's ~14 000 cycles go -- 3% waiting
+// for the row (HBM), 32% in sweep 2 (branch-resolve and shared-memory-atomic stalls of the diverged push path), 25% at
+// barriers behind the slowest warp of a sweep.  REGS keeps the per-group maxima of sweep 1 in registers (11 floats), so
+// sweep 2 re-reads NOTHING from shared memory: it is 11 register compares and warp votes per thread; only a group that
+// holds a survivor is fetched again.  Survivors are appended by warp-wide ballots into the warp's OWN 64-slot segment
+// of the buffer (position = warp-uniform counter + popc of the lower lanes' votes): no atomics, no divergence, every warp
+// does the same work, and the barrier behind the sweep waits for nobody.  A warp whose segment overflows (adversarial
+// rows) sends the cube down the sweep-2 path of the kernel without REGS, which keeps its own overflow handling.
 constexpr int RS_PROF_SLOTS = 10;
-constexpr int RS_PTR_THREAD = 64;                  // loads the mask_ptr pair two cubes ahead (NEXT)
-constexpr int RS_ISSUE_THREAD_NEXT = 480;          // issues the bulk copies (NEXT): warp 15 ranks survivors 120..127 only
-template <bool SIGMOID, bool DESC, bool PROF = false, bool NEXT = false>
+constexpr int RS_GROUPS = 11;                      // float4 groups per thread held in registers: C <= 4 * 11 * 512 = 22 528
+constexpr int RS_SEG = RS_CAP / (RS_THREADS / 32); // 64 survivor slots per warp
+template <bool SIGMOID, bool DESC, bool PROF = false, bool REGS = false>
 __global__ void __launch_bounds__(RS_THREADS, 2)
 topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_cards, int32_t batch,
                       const int64_t* __restrict__ mask_ptr, const int32_t* __restrict__ mask_idx,
@@ -607,9 +606,8 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
   __shared__ unsigned long long s_T;
   __shared__ float s_zb;
   __shared__ int s_cnt;
-  __shared__ long long s_mp[2];                             // NEXT: (begin, end) of the mask list two cubes ahead
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int issue_tid = NEXT ? RS_ISSUE_THREAD_NEXT : 0;
+  __shared__ int s_wc[RS_THREADS / 32];                     // REGS: survivors per warp segment
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int cr = (num_cards + 3) & ~3;                      // row length in shared memory (<= ld: ld % 4 == 0)
   const int cr4 = cr >> 2;
   const uint32_t row_bytes = uint32_t(cr) * 4u;
@@ -640,7 +638,7 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
   }
   for (int i = tid; i < RS_CAP; i += RS_THREADS) rk[i] = 0;
   __syncthreads();
-  if (tid == issue_tid) {
+  if (tid == 0) {
     for (int b = 0; b < nbuf; ++b)
       if (cube0 + b * stride < batch) issue(cube0 + b * stride, b);
   }
@@ -659,36 +657,17 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
   // survivors are stored raw (score bits, index); their keys are made afterwards, one survivor per thread, instead of
   // one sigmoid at a time in a diverged warp.  exact = 0 keeps every element that passes the raw-value bound (a superset
   // of {key >= T}: the final ranking is exact anyway); exact = 1 (after an overflow) tests the key itself.
-  // NEXT: a thread parks its first two survivors of a sweep in registers (a diverged push that waits for the round trip
-  // of a shared-memory atomic is what made sweep 2 four times as long as sweep 1); the warp appends them after the sweep
-  // with one prefix sum and one atomic (flush_parked).  A third survivor of the same thread takes the direct path.
-  unsigned long long parked0 = 0ull, parked1 = 0ull;
-  int nparked = 0;
   auto push = [&](float x, int e, unsigned long long T, bool exact) {
     if (exact && make_key<float>(SIGMOID ? sigmoid_f32(x) : x, (uint32_t)e, DESC) < T) return;
     const unsigned long long raw = ((unsigned long long)__float_as_uint(x) << 32) | (unsigned long long)(uint32_t)e;
-    if constexpr (NEXT) {
-      if (nparked == 0) { parked0 = raw; nparked = 1; return; }
-      if (nparked == 1) { parked1 = raw; nparked = 2; return; }
-    }
     const int slot = atomicAdd(&s_cnt, 1);
     if (slot < RS_CAP) keys[slot] = raw;
   };
-  auto flush_parked = [&]() {                               // all 32 lanes of the warp, converged
-    int incl = nparked;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total) {                                            // warp-uniform
-      int base = 0;
-      if (lane == 31) base = atomicAdd(&s_cnt, total);
-      base = __shfl_sync(0xffffffffu, base, 31);
-      const int pos = base + incl - nparked;
-      if (nparked > 0 && pos < RS_CAP) keys[pos] = parked0;
-      if (nparked > 1 && pos + 1 < RS_CAP) keys[pos + 1] = parked1;
-    }
-    nparked = 0;
+  auto raw_to_key = [&](unsigned long long raw) {
+    const float x = __uint_as_float((uint32_t)(raw >> 32));
+    return make_key<float>(SIGMOID ? sigmoid_f32(x) : x, (uint32_t)(raw & 0xffffffffu), DESC);
   };
+  const uint32_t lt_mask = (1u << lane) - 1u;
 
   int it = 0;
   for (int cube = cube0; cube < batch; cube += stride, ++it) {
@@ -702,11 +681,7 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
       if (mb1 + tid < me1) nc0 = mask_idx[mb1 + tid];
       if (mb1 + tid + RS_THREADS < me1) nc1 = mask_idx[mb1 + tid + RS_THREADS];
     }
-    if constexpr (NEXT) {
-      if (tid == RS_PTR_THREAD && cube + 2 * stride < batch) { mb2 = mask_ptr[cube + 2 * stride]; me2 = mask_ptr[cube + 2 * stride + 1]; }
-    } else {
-      if (cube + 2 * stride < batch) { mb2 = mask_ptr[cube + 2 * stride]; me2 = mask_ptr[cube + 2 * stride + 1]; }
-    }
+    if (cube + 2 * stride < batch) { mb2 = mask_ptr[cube + 2 * stride]; me2 = mask_ptr[cube + 2 * stride + 1]; }
     stamp(0);
     auto for_each_listed = [&](auto&& f) {
       f(c0); f(c1);
@@ -715,6 +690,7 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
     rs_mbar_wait(&bar[b], parity);
     stamp(1);                                               // 0: loop top + prefetch (stamped below), 1: wait for the row
 
+    float gmax[RS_GROUPS];                                  // REGS: extreme of each of this thread's float4 groups
     if (!mode_only_listed) {
       // masked cards (and the up to three floats of row padding) -> sentinel
       for_each_listed([&](int32_t c) { if (c >= 0 && c < num_cards) reinterpret_cast<uint32_t*>(row)[c] = RS_SENTINEL; });
@@ -727,10 +703,24 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
       // the index the total order prefers among equal scores (descending: the largest, ascending: the smallest).
       float best = WORST;
       int bv = -1;
-      for (int v = tid; v < cr4; v += RS_THREADS) {
-        const float4 q = row4[v];
-        if (DESC) { const float g = fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)); if (g >= best) { best = g; bv = v; } }
-        else      { const float g = fminf(fminf(q.x, q.y), fminf(q.z, q.w)); if (g < best) { best = g; bv = v; } }
+      if constexpr (REGS) {
+#pragma unroll
+        for (int j = 0; j < RS_GROUPS; ++j) {
+          const int v = tid + j * RS_THREADS;
+          float g = DESC ? -INFINITY : INFINITY;
+          if (v < cr4) {
+            const float4 q = row4[v];
+            g = DESC ? fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)) : fminf(fminf(q.x, q.y), fminf(q.z, q.w));
+            if (DESC ? g >= best : g < best) { best = g; bv = v; }
+          }
+          gmax[j] = g;
+        }
+      } else {
+        for (int v = tid; v < cr4; v += RS_THREADS) {
+          const float4 q = row4[v];
+          if (DESC) { const float g = fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)); if (g >= best) { best = g; bv = v; } }
+          else      { const float g = fminf(fminf(q.x, q.y), fminf(q.z, q.w)); if (g < best) { best = g; bv = v; } }
+        }
       }
       stamp(3);                                             // 3: sweep 1
       unsigned long long k = 0ull;
@@ -752,34 +742,81 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
         const unsigned long long t = uw > 0x007fffffu ? (unsigned long long)uw << 32 : 0ull;
         s_T = t; s_zb = rs_raw_bound<SIGMOID>(t, DESC);
       };
-      if constexpr (NEXT) {
-        // leader tid / 4, a quarter of the 128 stand-ins per lane, counts added over the four neighbouring lanes
-        const uint32_t mine = lead32[tid >> 2];
-        const uint4* a4 = reinterpret_cast<const uint4*>(lead32) + (tid & 3) * (RS_LEADERS / 16);
-        int c = 0;
-#pragma unroll
-        for (int j = 0; j < RS_LEADERS / 16; ++j) {
-          const uint4 w = a4[j];
-          c += (w.x > mine) + (w.y > mine) + (w.z > mine) + (w.w > mine);
-        }
-        c += __shfl_xor_sync(0xffffffffu, c, 1);
-        c += __shfl_xor_sync(0xffffffffu, c, 2);
-        if ((lane & 3) == 0 && c == n - 1) publish(mine);
-      } else {
-        rs_rank32_partial(lead32, rk, tid);
-        __syncthreads();
-        if (tid < RS_LEADERS) {
-          if (rk[tid] == n - 1) publish(lead32[tid]);
-          rk[tid] = 0;
-        }
+      rs_rank32_partial(lead32, rk, tid);
+      __syncthreads();
+      if (tid < RS_LEADERS) {
+        if (rk[tid] == n - 1) publish(lead32[tid]);
+        rk[tid] = 0;
       }
       __syncthreads();
       stamp(4);                                             // 4: leaders: keys, merge, ranking, threshold
     }
 
-    // sweep 2 (repeated with a raised threshold if more than RS_CAP elements survive)
     int m = 0;
-    for (int round = 0;; ++round) {
+    bool ranked_from_regs = false;
+    if constexpr (REGS) {
+      if (!mode_only_listed) {
+        // sweep 2 over registers: a group is fetched again only if its extreme passes the bound; the warp appends its
+        // survivors to its own segment with ballots (see the kernel's header comment)
+        const float zb = s_zb;
+        unsigned long long* seg = keys + wid * RS_SEG;
+        int wcnt = 0;                                       // warp-uniform
+#pragma unroll
+        for (int j = 0; j < RS_GROUPS; ++j) {
+          const bool hit = pass(gmax[j], zb);               // (lanes beyond the row hold the worst value: no bound passes
+          const uint32_t any = __ballot_sync(0xffffffffu, hit);   //  unless zb itself is the worst value, handled below)
+          if (any) {                                        // warp-uniform
+            const int v = tid + j * RS_THREADS;
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool live = hit && v < cr4;
+            if (live) q = row4[v];
+            const bool px = live && pass(q.x, zb), py = live && pass(q.y, zb), pz = live && pass(q.z, zb), pw = live && pass(q.w, zb);
+            const uint32_t m0 = __ballot_sync(0xffffffffu, px), m1 = __ballot_sync(0xffffffffu, py);
+            const uint32_t m2 = __ballot_sync(0xffffffffu, pz), m3 = __ballot_sync(0xffffffffu, pw);
+            int pos = wcnt + __popc(m0 & lt_mask) + __popc(m1 & lt_mask) + __popc(m2 & lt_mask) + __popc(m3 & lt_mask);
+            auto put = [&](bool p_, float x, int e) {
+              if (p_) {
+                if (pos < RS_SEG) seg[pos] = ((unsigned long long)__float_as_uint(x) << 32) | (unsigned long long)(uint32_t)e;
+                ++pos;
+              }
+            };
+            put(px, q.x, 4 * v); put(py, q.y, 4 * v + 1); put(pz, q.z, 4 * v + 2); put(pw, q.w, 4 * v + 3);
+            wcnt += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+          }
+        }
+        if (lane == 0) s_wc[wid] = wcnt;
+        __syncthreads();
+        stamp(5);                                           // 5: sweep 2 (+ barrier)
+        // densify: segment slot -> position = survivors of the lower warps + slot; raw -> composite key on the way.  Every
+        // thread owns two slots (one in the lower eight segments, one in the upper eight); all reads precede all writes.
+        int total = 0, base_lo = 0, base_hi = 0;
+        bool over = false;
+        const int w_lo = tid >> 6, w_hi = 8 + (tid >> 6);
+#pragma unroll
+        for (int w = 0; w < RS_THREADS / 32; ++w) {
+          const int c = s_wc[w];
+          if (w == w_lo) base_lo = total;
+          if (w == w_hi) base_hi = total;
+          over |= c > RS_SEG;
+          total += c;
+        }
+        if (!over) {                                        // CTA-uniform
+          const int sl = tid & (RS_SEG - 1);
+          const bool v_lo = sl < s_wc[w_lo], v_hi = sl < s_wc[w_hi];
+          const unsigned long long r_lo = v_lo ? keys[w_lo * RS_SEG + sl] : 0ull, r_hi = v_hi ? keys[w_hi * RS_SEG + sl] : 0ull;
+          __syncthreads();
+          if (v_lo) keys[base_lo + sl] = raw_to_key(r_lo);
+          if (v_hi) keys[base_hi + sl] = raw_to_key(r_hi);
+          __syncthreads();
+          stamp(6);                                         // 6: survivors -> keys (+ barriers)
+          m = total;
+          ranked_from_regs = true;
+        }
+      }
+    }
+    // sweep 2 over the shared row (the kernel without REGS; with REGS: only-listed mode and cubes whose survivors
+    // overflowed a warp segment), repeated with a raised threshold if more than RS_CAP elements survive
+    for (int round = 0; !ranked_from_regs; ++round) {
       if (mode_only_listed) {
         for (int w = tid; w < words; w += RS_THREADS) bm[w] = 0u;
         __syncthreads();
@@ -807,19 +844,11 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
           }
         }
       }
-      if constexpr (NEXT) flush_parked();
       __syncthreads();
       m = s_cnt;
-      if constexpr (NEXT) {
-        if (tid == RS_PTR_THREAD) { s_mp[0] = mb2; s_mp[1] = me2; }      // read by everyone behind the next barrier
-      }
       stamp(5);                                             // 5: sweep 2 (+ barrier)
       // raw survivors -> composite keys (each thread its own slots)
-      for (int i = tid; i < min(m, RS_CAP); i += RS_THREADS) {
-        const unsigned long long raw = keys[i];
-        const float x = __uint_as_float((uint32_t)(raw >> 32));
-        keys[i] = make_key<float>(SIGMOID ? sigmoid_f32(x) : x, (uint32_t)(raw & 0xffffffffu), DESC);
-      }
+      for (int i = tid; i < min(m, RS_CAP); i += RS_THREADS) keys[i] = raw_to_key(keys[i]);
       __syncthreads();
       stamp(6);                                             // 6: survivors -> keys (+ barrier)
       if (m <= RS_CAP) break;
@@ -834,7 +863,7 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
       __syncthreads();
     }
     // the row is not needed any more: its buffer takes the row of the cube nbuf turns ahead while this one is ranked
-    if (tid == issue_tid && cube + nbuf * stride < batch) issue(cube + nbuf * stride, b);
+    if (tid == 0 && cube + nbuf * stride < batch) issue(cube + nbuf * stride, b);
 
     // rank the m survivors among themselves and write the first n at their rank
     auto write_ranked = [&](unsigned long long key, int r) {
@@ -843,36 +872,15 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
       out_ids[int64_t(cube) * n + r] = (int32_t)t;
       if (out_vals) out_vals[int64_t(cube) * n + r] = __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
     };
-    if constexpr (NEXT) {
-      // every thread has read s_cnt, s_T and s_zb (before the barrier above); their next use lies behind the next cube's barriers
-      if (tid == 0) { s_cnt = 0; s_T = 0ull; s_zb = WORST; }
-      { const long long a = s_mp[0], e = s_mp[1]; mb2 = a; me2 = e; }
-      const int chunk = (m + 3) >> 2;
-      const int j0 = (tid & 3) * chunk, j1 = min(m, j0 + chunk);
-      for (int i0 = 0; i0 < m; i0 += RS_LEADERS) {            // survivor i0 + tid / 4, a quarter of the buffer per lane
-        const int i = i0 + (tid >> 2);
-        unsigned long long mine = 0ull;
-        int c = 0;
-        if (i < m) {
-          mine = keys[i];
-          for (int j = j0; j < j1; ++j) c += (keys[j] > mine) ? 1 : 0;
-        }
-        c += __shfl_xor_sync(0xffffffffu, c, 1);
-        c += __shfl_xor_sync(0xffffffffu, c, 2);
-        if ((lane & 3) == 0 && i < m && c < n) write_ranked(mine, c);
-      }
-      stamp(7);                                             // 7: issue of the next row + final ranking and write-out
-    } else {
-      rs_rank_partial(keys, m, rk, tid);
-      __syncthreads();
-      stamp(7);                                             // 7: issue of the next row + final ranking (+ barrier)
-      // every thread has read s_cnt, s_T and s_zb by now; their next use lies behind the next cube's barriers
-      if (tid == 0) { s_cnt = 0; s_T = 0ull; s_zb = WORST; }
-      for (int i = tid; i < m; i += RS_THREADS) {
-        const int r = rk[i];
-        rk[i] = 0;
-        if (r < n) write_ranked(keys[i], r);
-      }
+    rs_rank_partial(keys, m, rk, tid);
+    __syncthreads();
+    stamp(7);                                               // 7: issue of the next row + final ranking (+ barrier)
+    // every thread has read s_cnt, s_T and s_zb by now; their next use lies behind the next cube's barriers
+    if (tid == 0) { s_cnt = 0; s_T = 0ull; s_zb = WORST; }
+    for (int i = tid; i < m; i += RS_THREADS) {
+      const int r = rk[i];
+      rk[i] = 0;
+      if (r < n) write_ranked(keys[i], r);
     }
     for (int i = m + tid; i < n; i += RS_THREADS) {
       out_ids[int64_t(cube) * n + i] = -1;
@@ -901,8 +909,8 @@ static bool rowselect_eligible(const float* scores, int64_t ld, int32_t num_card
          rowselect_smem_bytes(num_cards, 2) + 1024 <= 227 * 1024;
 }
 
-// variant 0: one CTA per SM, two row buffers; variant 1: two CTAs per SM, one row buffer each; variant 2: the NEXT
-// candidate of the kernel in the launch shape of variant 1
+// variant 0: one CTA per SM, two row buffers; variant 1: two CTAs per SM, one row buffer each; variant 2: the REGS form
+// of the kernel (group maxima in registers, ballot-compacted survivors) in the launch shape of variant 1
 template <bool SIGMOID, bool DESC>
 static int rowselect_launch_t(int variant, const float* scores, int64_t ld, int32_t num_cards, int32_t batch,
                               const int64_t* mask_ptr, const int32_t* mask_idx, int mode_only_listed, int32_t n,
@@ -935,7 +943,7 @@ static int rowselect_launch(int variant, const float* scores, int64_t ld, int32_
 
 // float32, n <= 128: 0 = automatic (row select when the rows qualify, else the streaming select), 1 = streaming select,
 // 2 / 3 = row select, variant 0 / 1 (error if the rows do not qualify); automatic takes variant 1, the faster one
-// on a B200; 4 = the NEXT candidate of the row select (opt-in until it has been run and measured on a GPU).  The radix-select kernel stays the general path (any n, float64).
+// without REGS; 4 = the REGS form (rows of up to 22 528 cards).  The radix-select kernel stays the general path (any n, float64).
 static int g_topn_algo = 0;
 static int g_topn_force_radix = 0;
 
@@ -945,9 +953,13 @@ static int select_small_n(const float* scores, int64_t ld, int32_t num_cards, in
                           int32_t* out_ids, float* out_vals, int32_t* out_count, cudaStream_t st) {
   const bool ok = rowselect_eligible(scores, ld, num_cards, n);
   CC_REQUIRE(ok || g_topn_algo < 2, "cc_topn_masked: the row select needs ld %% 4 == 0, 16-byte aligned rows and C <= ~26 000");
-  if (ok && g_topn_algo != 1)
-    return rowselect_launch<SIGMOID>(g_topn_algo == 2 ? 0 : g_topn_algo == 4 ? 2 : 1, scores, ld, num_cards, batch, mask_ptr, mask_idx,
+  const bool regs_ok = ((num_cards + 3) >> 2) <= RS_GROUPS * RS_THREADS;
+  CC_REQUIRE(regs_ok || g_topn_algo != 4, "cc_topn_masked: the REGS row select holds rows of up to %d cards", 4 * RS_GROUPS * RS_THREADS);
+  if (ok && g_topn_algo != 1) {
+    const int variant = g_topn_algo == 2 ? 0 : g_topn_algo == 3 ? 1 : (regs_ok ? 2 : 1);        // 0 (automatic) and 4: REGS
+    return rowselect_launch<SIGMOID>(variant, scores, ld, num_cards, batch, mask_ptr, mask_idx,
                                      mode_only_listed, descending, n, out_ids, out_vals, out_count, st);
+  }
   return warpselect_launch<SIGMOID>(scores, ld, num_cards, batch, mask_ptr, mask_idx, mode_only_listed, descending, n,
                                     out_ids, out_vals, out_count, st);
 }
@@ -1108,7 +1120,6 @@ int cc_topn_set_force_radix(int on) { g_topn_force_radix = on ? 1 : 0; return CC
 // Diagnostic: the fused-sigmoid, descending row select with per-phase clock64() sums of every CTA's thread 0
 // (prof: int64 [grid][10] on the device, grid = cc_topn_rowselect_profile_grid(batch, variant); slots: see RS_PROF_SLOTS).
 int64_t cc_topn_rowselect_profile_grid(int32_t batch, int variant) {
-  CC_NVTX("cc_topn_set_force_radix");
   const int ctas = variant == 0 ? 1 : 2;
   return batch < ctas * sm_count() ? batch : ctas * sm_count();
 }

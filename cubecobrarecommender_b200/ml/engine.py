@@ -25,8 +25,9 @@ from .._lib import call, ptr, stream_ptr
 from .model import (CC_Recommender, ENC_NAMES, HIDDEN, SparseBatch, bag_bwd, bag_fwd, colsum, dec_names, gemm)
 
 KERAS_ADAM = dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)
-FIRST_LAYER_TENSOR_WHEN = ("tensor",)        # which CC_FIRST_LAYER values select the tensor-core first layer ("auto" joins
-                                             # the tuple once a measurement on the B200 says it wins)
+# which CC_FIRST_LAYER values select the tensor-core first layer.  "auto" is in: measured on the B200 at B = 4096,
+# C = 20 884 (profiles/r02/ab_first_layer.txt): x W1 as a kind::tf32 GEMM 144 us against 225 us for the gather (bf16: 79 us)
+FIRST_LAYER_TENSOR_WHEN = ("tensor", "auto")
 
 
 def alias_table(p: np.ndarray, device):

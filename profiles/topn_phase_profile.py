@@ -26,7 +26,7 @@ logits = torch.randn((batch, LD), device=dev, generator=g) * 3 - 4
 ids = torch.empty((batch, N), dtype=torch.int32, device=dev)
 vals = torch.empty((batch, N), dtype=torch.float32, device=dev)
 cnt = torch.empty(batch, dtype=torch.int32, device=dev)
-for variant in ((2, 1, 0) if os.environ.get("CC_TOPN_EXPERIMENTAL") == "1" else (1, 0)):
+for variant in (2, 1, 0):
     grid = int(lib.cc_topn_rowselect_profile_grid(batch, variant))
     prof = torch.zeros((grid, 10), dtype=torch.int64, device=dev)
     for _ in range(2):                      # second launch: warm
@@ -36,6 +36,6 @@ for variant in ((2, 1, 0) if os.environ.get("CC_TOPN_EXPERIMENTAL") == "1" else 
     p = prof.cpu().double()
     cubes = p[:, 9].sum().item()
     per_cube = (p[:, :9].sum(0) / cubes).tolist()
-    print(json.dumps({"variant": {0: "1 CTA/SM, 2 row buffers", 1: "2 CTAs/SM, 1 row buffer", 2: "NEXT revision, 2 CTAs/SM, 1 row buffer"}[variant], "grid": grid,
+    print(json.dumps({"variant": {0: "1 CTA/SM, 2 row buffers", 1: "2 CTAs/SM, 1 row buffer", 2: "REGS form (default), 2 CTAs/SM, 1 row buffer"}[variant], "grid": grid,
                       "batch": batch, "cycles_per_cube_total": sum(per_cube),
                       "cycles_per_cube": {k: round(v, 1) for k, v in zip(PHASES, per_cube)}}), flush=True)

@@ -251,10 +251,9 @@ def _algo(a):
     _lib.call("cc_topn_set_algo", a)
 
 
-# the launch shapes of the row select that are compared with the streaming select; CC_TOPN_EXPERIMENTAL=1 adds algo 4,
-# the next revision of the kernel (opt-in until it has been run on a GPU)
-import os as _os
-ROW_SELECT_ALGOS = (2, 3, 4) if _os.environ.get("CC_TOPN_EXPERIMENTAL") == "1" else (2, 3)
+# the forms of the row select that are compared with the streaming select: 2 / 3 = both sweeps over shared memory (one
+# CTA per SM with two row buffers / two CTAs per SM), 4 = the register form (the default when the row fits)
+ROW_SELECT_ALGOS = (2, 3, 4)
 
 
 @pytest.mark.parametrize("c,ld,batch,n", [(5000, 5000, 6, 50), (4999, 5008, 11, 128), (97, 100, 3, 7),
