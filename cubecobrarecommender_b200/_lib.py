@@ -68,6 +68,7 @@ SIGNATURES = {
     "cc_gemm_f32_simt": (I, [I, I, I, I, I, P, I64, P, I64, P, I64, P, I, P, I64, I, P]),
     "cc_gemm_tc": (I, [I, I, I, I, I, I, P, I64, P, I64, P, I64, P, I, P, I64, I, I, I, I, P]),
     "cc_gemm_bce_tc": (I, [I, I, I, I, P, I64, P, I64, P, P, I64, D, P, I64, P, P, I, I, P]),
+    "cc_gemm_bce_tc_ex": (I, [I, I, I, I, P, I64, P, I64, P, P, I64, D, P, I64, P, P, I, I, P, P]),
     "cc_gemm_bce_partial_count": (I64, [I, I]),
     "cc_gemm_tc_set_pair_mode": (I, [I]),
     "cc_gemm_tc_plan": (I, [I, I, I, I, I, I, P]),
@@ -85,6 +86,9 @@ SIGNATURES = {
     "cc_softmax_kl_fwd_bwd_ex": (I, [P, I64, P, I64, P, I32, I32, I32, D, P, I64, P, I, P, P, I64, P, P]),
     "cc_kl_target_table": (I, [P, I64, I32, I32, P, P]),
     "cc_softmax_kl_set_variant": (I, [I]),
+    "cc_softmax_kl_fwd_bwd_metrics": (I, [P, I64, P, I64, P, I32, I32, I32, D, P, I64, P, I, P, P, I64, P, P, P, P]),
+    "cc_kl_target_argmax": (I, [P, I64, I32, I32, P, P]),
+    "cc_binary_accuracy_rows": (I, [P, I64, P, I64, I32, I32, P, P]),
     "cc_convert_f32_bf16": (I, [P, I64, P, I64, I32, I32, P]),
     "cc_loss_finalize": (I, [P, I32, D, P, I32, D, D, P, P]),
     "cc_adam_step_p2p": (I, [P, P, I, I, P, P, I64, I64, P, F, F, F, F, P, P, P]),

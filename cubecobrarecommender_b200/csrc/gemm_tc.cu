@@ -70,6 +70,7 @@ struct Params {
   const uint32_t* ybits; long long ywords;
   float inv_count;
   double* loss_partial;                  // [tiles][EPI_WARPS]
+  double* acc_partial;                   // nullable, same layout: number of cells with round(sigmoid(z)) == y (Keras binary_accuracy)
   float* dbias;                          // EPI_BCE: column sums of dlogits (= the output layer's bias gradient), atomically added
   int a_mn_major, b_mn_major;
   int* sched;                            // {next-tile counter, finished units}: self-resetting (see TileRing)
@@ -574,7 +575,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const float inv_row = row_ok ? p.inv_count : 0.f;     // rows beyond m: zero gradient (they feed the column sums)
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      float row_loss = 0.f;
+      float row_loss = 0.f, row_hits = 0.f;
       // The BCE body is long (a rolled loop keeps it inside the instruction cache: unrolling it 8x cost 300 -> 442 us),
       // so the prefetched registers are ROTATED instead of indexed; the short store body is fully unrolled.
 #pragma unroll(IS_BCE ? 1 : NCH)
@@ -606,9 +607,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         } else if (IS_BCE) {
           // softplus(z) - z*y and sigmoid(z) from one exp: e = exp(-|z|) (ex2, rcp, lg2: 3 MUFU ops per element)
-          auto bce_elem = [&](int j, float& l, float& g) {
+          auto bce_elem = [&](int j, float& l, float& g, float& hit) {
             const float z = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, b_cur, j);
             const float y = float((ybw >> j) & 1u);
+            hit = ((z > 0.f) == (y != 0.f)) ? 1.f : 0.f;     // round(sigmoid(z)) == y: sigmoid(0) = 0.5 rounds to 0 (half to even)
             const float e = exp2f_approx(-1.4426950408889634f * fabsf(z));
             const float s1 = 1.f + e;
             const float r = rcp_approx(s1);
@@ -618,18 +620,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (col0 + 32 <= p.n) {                       // warp-uniform: only the last column tile is ragged
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              float l, g;
-              bce_elem(j, l, g);
+              float l, g, h;
+              bce_elem(j, l, g, h);
               row_loss += l;
+              row_hits += h;
               out[j] = p.round_tf32 ? rn_tf32_bits(g) : g;
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              float l, g;
-              bce_elem(j, l, g);
+              float l, g, h;
+              bce_elem(j, l, g, h);
               const bool live = (col0 + j < p.n);
               row_loss += live ? l : 0.f;
+              row_hits += live ? h : 0.f;
               g = live ? g : 0.f;
               out[j] = p.round_tf32 ? rn_tf32_bits(g) : g;
             }
@@ -699,6 +703,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const float s = row_ok ? row_loss : 0.f;
         const double d = warp_sum(double(s));
         if (lane == 0) p.loss_partial[((long long)tile * CTAS + cta_rank) * EPI_WARPS + (warp - 4)] = d;
+        if (p.acc_partial) {                              // warp-uniform
+          const double a = warp_sum(double(row_ok ? row_hits : 0.f));
+          if (lane == 0) p.acc_partial[((long long)tile * CTAS + cta_rank) * EPI_WARPS + (warp - 4)] = a;
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -1135,6 +1143,15 @@ int cc_gemm_tc(int precision, int transa, int transb, int m, int n, int k, const
 int cc_gemm_bce_tc(int precision, int m, int n, int k, const void* a, int64_t lda, const void* w, int64_t ldw,
                    const float* bias, const uint32_t* ybits, int64_t ywords, double count, void* dz, int64_t lddz,
                    double* loss_partial, float* dbias, int round_tf32, int dz_bf16, void* stream) {
+  return cc_gemm_bce_tc_ex(precision, m, n, k, a, lda, w, ldw, bias, ybits, ywords, count, dz, lddz, loss_partial, dbias,
+                           round_tf32, dz_bf16, nullptr, stream);
+}
+
+// acc_partial (nullable, float64, same size and layout as loss_partial): per-(tile, warp) counts of the cells whose
+// rounded probability equals the label, i.e. Keras' binary_accuracy numerator (metrics=['accuracy'], train.py:87).
+int cc_gemm_bce_tc_ex(int precision, int m, int n, int k, const void* a, int64_t lda, const void* w, int64_t ldw,
+                      const float* bias, const uint32_t* ybits, int64_t ywords, double count, void* dz, int64_t lddz,
+                      double* loss_partial, float* dbias, int round_tf32, int dz_bf16, double* acc_partial, void* stream) {
   CC_NVTX("cc_gemm_bce_tc");
   CC_REQUIRE(a && w && bias && ybits && dz && loss_partial, "cc_gemm_bce_tc: null pointer");
   CC_REQUIRE(precision == 1 || precision == 2, "cc_gemm_bce_tc: precision must be 1 (tf32) or 2 (bf16)");
@@ -1146,6 +1163,7 @@ int cc_gemm_bce_tc(int precision, int m, int n, int k, const void* a, int64_t ld
   p.bias = bias; p.split_k = 1; p.round_tf32 = round_tf32;
   p.ybits = ybits; p.ywords = ywords; p.inv_count = float(1.0 / count); p.loss_partial = loss_partial;
   p.dbias = dbias;
+  p.acc_partial = acc_partial;
   if (dbias) CC_CHECK_CUDA(cudaMemsetAsync(dbias, 0, size_t(n) * sizeof(float), as_stream(stream)));
   tc::Problem pr{0, 0, m, n, k, a, lda, w, ldw, static_cast<float*>(dz), lddz, precision == 2 ? tc::KIND_BF16 : tc::KIND_TF32};
   const int ctas = tc::g_pair_mode == 0 ? 1 : 2;

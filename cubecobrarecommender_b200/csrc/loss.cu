@@ -81,6 +81,22 @@ bce_rows_kernel(const float* __restrict__ z, int64_t ldz, const uint32_t* __rest
   if (threadIdx.x == 0) row_loss[b] = tot;
 }
 
+// Keras binary_accuracy numerator per row: cells with (z > 0) == y  (exact-fp32 mode; the tensor-core modes count
+// inside the fused GEMM epilogue)
+__global__ void __launch_bounds__(256)
+binary_accuracy_rows_kernel(const float* __restrict__ z, int64_t ldz, const uint32_t* __restrict__ ybits, int64_t ywords,
+                            int32_t num_cards, double* __restrict__ row_correct) {
+  __shared__ double red[32];
+  const int b = blockIdx.x;
+  const float* zr = z + int64_t(b) * ldz;
+  const uint32_t* yr = ybits + int64_t(b) * ywords;
+  int hits = 0;
+  for (int c = threadIdx.x; c < num_cards; c += blockDim.x)
+    hits += ((zr[c] > 0.f) == (((yr[c >> 5] >> (c & 31)) & 1u) != 0u)) ? 1 : 0;
+  const double tot = block_sum_double(double(hits), red);
+  if (threadIdx.x == 0) row_correct[b] = tot;
+}
+
 // ---------------------------------------------------------------- softmax-KL
 template <bool CACHE>
 __global__ void __launch_bounds__(1024)
@@ -279,11 +295,13 @@ softmax_kl_persistent_kernel(const float* __restrict__ z, int64_t ldz, const flo
                              const int32_t* __restrict__ target_rows, int32_t rows, int32_t num_cards, int32_t ncols_pad,
                              float grad_scale, float* __restrict__ dz, int64_t lddz, double* __restrict__ row_loss,
                              int round_tf32, float* __restrict__ dbias, __nv_bfloat16* __restrict__ dz16, int64_t lddz16,
-                             const double* __restrict__ tlogt) {
+                             const double* __restrict__ tlogt, const int32_t* __restrict__ target_argmax,
+                             int32_t* __restrict__ row_hit) {
   auto EXPF = [](float x) { return FAST ? fast_exp(x) : expf(x); };
   auto LOGF = [](float x) { return FAST ? fast_log(x) : logf(x); };
   extern __shared__ __align__(16) float sz[];           // two rows of logits
   __shared__ float2 red[KLP_THREADS / 32];
+  __shared__ int red_i[KLP_THREADS / 32];
   const int n4 = num_cards >> 2;
   const int p4 = ncols_pad >> 2;
   float4 acc[KLP_ACC];
@@ -358,6 +376,23 @@ softmax_kl_persistent_kernel(const float* __restrict__ z, int64_t ldz, const flo
     // sweep 2: loss = sum t' (log t' - log q'), S = sum of t' over the cards whose q survives the clip; the logit in
     // shared memory is replaced by e = exp(z - max) on the way (each thread rewrites only what it read itself)
     float loss = 0.f, sun = 0.f;
+    if (row_hit) {                                          // CTA-uniform: categorical accuracy (see softmax_kl_regs_kernel)
+      int cand = 0x7fffffff;
+      for (int i = threadIdx.x; i < n4; i += KLP_THREADS) {
+        const float4 v = s4[i];
+        const int first = v.x == mx ? 0 : v.y == mx ? 1 : v.z == mx ? 2 : v.w == mx ? 3 : -1;
+        if (first >= 0) cand = min(cand, 4 * i + first);
+      }
+      cand = __reduce_min_sync(0xffffffffu, cand);
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) red_i[threadIdx.x >> 5] = cand;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int best = red_i[0];
+        for (int w = 1; w < KLP_THREADS / 32; ++w) best = min(best, red_i[w]);
+        row_hit[r] = (best == target_argmax[trow]) ? 1 : 0;
+      }
+    }
     for (int i = threadIdx.x; i < n4; i += KLP_THREADS) {
       const float4 v = s4[i];
       const float4 t = __ldg(t4 + i);
@@ -456,11 +491,13 @@ softmax_kl_regs_kernel(const float* __restrict__ z, int64_t ldz, const float* __
                        const int32_t* __restrict__ target_rows, int32_t rows, int32_t num_cards, int32_t ncols_pad,
                        float grad_scale, float* __restrict__ dz, int64_t lddz, double* __restrict__ row_loss,
                        int round_tf32, float* __restrict__ dbias, __nv_bfloat16* __restrict__ dz16, int64_t lddz16,
-                       const double* __restrict__ tlogt) {
+                       const double* __restrict__ tlogt, const int32_t* __restrict__ target_argmax,
+                       int32_t* __restrict__ row_hit) {
   auto EXPF = [](float x) { return FAST ? fast_exp(x) : expf(x); };
   auto LOGF = [](float x) { return FAST ? fast_log(x) : logf(x); };
   extern __shared__ __align__(16) float sz[];           // two rows of logits
   __shared__ float2 red[KLR_THREADS / 32];
+  __shared__ int red_i[KLR_THREADS / 32];
   const int n4 = num_cards >> 2;
   const int p4 = ncols_pad >> 2;
   float4 acc[ITERS];
@@ -529,15 +566,33 @@ softmax_kl_regs_kernel(const float* __restrict__ z, int64_t ldz, const float* __
     }
     const float mx = tm;
     float ts = 0.f;
+    int cand = 0x7fffffff;                                  // first column holding the row maximum (metrics only)
 #pragma unroll
     for (int k = 0; k < ITERS; ++k) {
       const int i = threadIdx.x + k * KLR_THREADS;
       if (i < n4) {
         const float4 v = s4[i];
         ts += (EXPF(v.x - mx) + EXPF(v.y - mx)) + (EXPF(v.z - mx) + EXPF(v.w - mx));
+        if (row_hit) {                                      // CTA-uniform
+          const int first = v.x == mx ? 0 : v.y == mx ? 1 : v.z == mx ? 2 : v.w == mx ? 3 : -1;
+          if (first >= 0) cand = min(cand, 4 * i + first);
+        }
       }
     }
     const float sumexp = block_sum2_r(ts, 0.f, red).x;
+    if (row_hit) {
+      // Keras categorical_accuracy (metrics=['accuracy'] on the softmax output): argmax of the prediction (first maximal
+      // column, like tf.argmax) against the argmax of the target row, a per-row table
+      cand = __reduce_min_sync(0xffffffffu, cand);
+      if ((threadIdx.x & 31) == 0) red_i[threadIdx.x >> 5] = cand;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int best = red_i[0];
+#pragma unroll
+        for (int w = 1; w < KLR_THREADS / 32; ++w) best = min(best, red_i[w]);
+        row_hit[r] = (best == target_argmax[trow]) ? 1 : 0;
+      }
+    }
     const float inv_sum = 1.f / sumexp;
     const float lse = mx + LOGF(sumexp);
     const float log_eps = -16.11809565095832f;               // log(1e-7)
@@ -851,6 +906,16 @@ int cc_bce_logits_fwd_bwd(const float* z, int64_t ldz, const uint32_t* ybits, in
   return CC_OK;
 }
 
+int cc_binary_accuracy_rows(const float* z, int64_t ldz, const uint32_t* ybits, int64_t ywords, int32_t batch,
+                            int32_t num_cards, double* row_correct, void* stream) {
+  CC_NVTX("cc_binary_accuracy_rows");
+  CC_REQUIRE(z && ybits && row_correct && num_cards > 0 && ywords * 32 >= num_cards, "cc_binary_accuracy_rows: bad arguments");
+  if (batch == 0) return CC_OK;
+  binary_accuracy_rows_kernel<<<batch, 256, 0, as_stream(stream)>>>(z, ldz, ybits, ywords, num_cards, row_correct);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
 // dbias (nullable, float [num_cards]): receives the column sums of dz (= the softmax layer's bias gradient).  Fused into
 // the persistent kernel when it applies (float atomics: last bits vary between runs); otherwise the caller still has
 // cc_colsum_f32 -- the return value of cc_softmax_kl_fuses_dbias tells which.
@@ -881,7 +946,54 @@ int cc_softmax_kl_fwd_bwd_ex(const float* z, int64_t ldz, const float* target, i
                              int32_t rows, int32_t num_cards, int32_t ncols_pad, double grad_scale, float* dz,
                              int64_t lddz, double* row_loss, int round_tf32, float* dbias, void* dz_bf16, int64_t lddz_bf16,
                              const double* tlogt, void* stream) {
+  return cc_softmax_kl_fwd_bwd_metrics(z, ldz, target, ldt, target_rows, rows, num_cards, ncols_pad, grad_scale, dz, lddz,
+                                       row_loss, round_tf32, dbias, dz_bf16, lddz_bf16, tlogt, nullptr, nullptr, stream);
+}
+
+// target_argmax[i] = first maximal column of target row i (int32, one entry per row of the target matrix).
+__global__ void __launch_bounds__(256)
+kl_target_argmax_kernel(const float* __restrict__ target, int64_t ldt, int32_t num_cards, int32_t* __restrict__ out) {
+  __shared__ float redv[8];
+  __shared__ int redi[8];
+  const float* tr = target + int64_t(blockIdx.x) * ldt;
+  float bv = -INFINITY; int bi = 0x7fffffff;
+  for (int c = threadIdx.x; c < num_cards; c += blockDim.x) {
+    const float v = tr[c];
+    if (v > bv) { bv = v; bi = c; }                       // strict: a thread's columns ascend, the first maximum stays
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { redv[threadIdx.x >> 5] = bv; redi[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) if (redv[w] > bv || (redv[w] == bv && redi[w] < bi)) { bv = redv[w]; bi = redi[w]; }
+    out[blockIdx.x] = bi;
+  }
+}
+
+int cc_kl_target_argmax(const float* target, int64_t ldt, int32_t target_rows, int32_t num_cards, int32_t* out, void* stream) {
+  CC_NVTX("cc_kl_target_argmax");
+  CC_REQUIRE(target && out && target_rows >= 0 && num_cards > 0 && ldt >= num_cards, "cc_kl_target_argmax: bad arguments");
+  if (target_rows == 0) return CC_OK;
+  kl_target_argmax_kernel<<<target_rows, 256, 0, as_stream(stream)>>>(target, ldt, num_cards, out);
+  CC_CHECK_LAUNCH();
+  return CC_OK;
+}
+
+// row_hit (nullable, int32 [rows]) with target_argmax (int32, one entry per target row, cc_kl_target_argmax): 1 where
+// the first maximal logit of the row is the target row's argmax -- Keras' categorical_accuracy on the softmax output
+// (metrics=['accuracy'], src/ml/train.py:87).  Persistent kernels only (dbias != NULL).
+int cc_softmax_kl_fwd_bwd_metrics(const float* z, int64_t ldz, const float* target, int64_t ldt, const int32_t* target_rows,
+                                  int32_t rows, int32_t num_cards, int32_t ncols_pad, double grad_scale, float* dz,
+                                  int64_t lddz, double* row_loss, int round_tf32, float* dbias, void* dz_bf16,
+                                  int64_t lddz_bf16, const double* tlogt, const int32_t* target_argmax, int32_t* row_hit,
+                                  void* stream) {
   CC_NVTX("cc_softmax_kl_fwd_bwd_ex");
+  CC_REQUIRE((row_hit == nullptr) || (target_argmax && dbias),
+             "cc_softmax_kl_fwd_bwd: row_hit needs target_argmax and the persistent kernel (dbias != NULL)");
   CC_REQUIRE(!tlogt || dbias, "cc_softmax_kl_fwd_bwd: the target table is used by the persistent kernel only (dbias != NULL)");
   CC_REQUIRE(z && target && row_loss, "cc_softmax_kl_fwd_bwd: null pointer");
   CC_REQUIRE(!dz_bf16 || (dbias && lddz_bf16 >= ncols_pad && lddz_bf16 % 4 == 0 && (reinterpret_cast<uintptr_t>(dz_bf16) & 7) == 0),
@@ -907,7 +1019,7 @@ int cc_softmax_kl_fwd_bwd_ex(const float* z, int64_t ldz, const float* target, i
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
         softmax_kl_regs_kernel<FAST_, KLR_ITERS><<<grid, KLR_THREADS, smem, st>>>(                                    \
             z, ldz, target, ldt, target_rows, rows, num_cards, ncols_pad, float(grad_scale), dz, lddz, row_loss, RT_,  \
-            dbias, dz16, lddz_bf16, tlogt);                                                                           \
+            dbias, dz16, lddz_bf16, tlogt, target_argmax, row_hit);                                                   \
       } while (0)
       if (round_tf32) CC_KL_REGS(true, dz16 ? 0 : 1); else CC_KL_REGS(false, 0);
 #undef CC_KL_REGS
@@ -915,12 +1027,12 @@ int cc_softmax_kl_fwd_bwd_ex(const float* z, int64_t ldz, const float* target, i
       CC_CHECK_CUDA(cudaFuncSetAttribute(softmax_kl_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       softmax_kl_persistent_kernel<true><<<grid, KLP_THREADS, smem, st>>>(z, ldz, target, ldt, target_rows, rows, num_cards,
                                                                          ncols_pad, float(grad_scale), dz, lddz, row_loss,
-                                                                         dz16 ? 0 : 1, dbias, dz16, lddz_bf16, tlogt);
+                                                                         dz16 ? 0 : 1, dbias, dz16, lddz_bf16, tlogt, target_argmax, row_hit);
     } else {
       CC_CHECK_CUDA(cudaFuncSetAttribute(softmax_kl_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       softmax_kl_persistent_kernel<false><<<grid, KLP_THREADS, smem, st>>>(z, ldz, target, ldt, target_rows, rows, num_cards,
                                                                           ncols_pad, float(grad_scale), dz, lddz, row_loss, 0, dbias,
-                                                                          dz16, lddz_bf16, tlogt);
+                                                                          dz16, lddz_bf16, tlogt, target_argmax, row_hit);
     }
     CC_CHECK_LAUNCH();
     return CC_OK;

@@ -48,7 +48,8 @@ def full_identity_shard(num_cards: int, rank: int = 0, world: int = 1):
 class DAEEngine:
     def __init__(self, model: CC_Recommender, mhat: torch.Tensor, *, batch: int, reg_rows: int | None = None,
                  reg: float = 0.1, max_cube_size: int = 720, global_batch: int | None = None,
-                 global_reg_rows: int | None = None, group=None, adam=None, data_parallel: bool = True):
+                 global_reg_rows: int | None = None, group=None, adam=None, data_parallel: bool = True,
+                 metrics: bool = False):
         self.model = model
         self.store = model.store
         self.dev = model.device
@@ -61,6 +62,9 @@ class DAEEngine:
         self.global_R = int(global_reg_rows or self.R)
         self.group = group
         self.data_parallel = bool(data_parallel)   # False: never exchange, even under torchrun (single-GPU reference runs)
+        # Keras metrics=['accuracy'] (reference train.py:87): binary accuracy of the sigmoid tower and categorical
+        # accuracy of the softmax tower, counted inside the loss kernels; off by default (bench, parity tests)
+        self.want_metrics = bool(metrics)
         self.adam = dict(KERAS_ADAM, **(adam or {}))
         self.mhat = mhat
         assert mhat.dtype == torch.float32 and mhat.shape[0] == self.C and mhat.shape[1] >= self.C
@@ -140,6 +144,10 @@ class DAEEngine:
         self.row_bce = torch.zeros(B, dtype=torch.float64, device=d)
         self.row_kl = torch.zeros(max(R, 1), dtype=torch.float64, device=d)
         self.loss3 = torch.zeros(3, dtype=torch.float64, device=d)
+        self.metrics2 = torch.zeros(2, dtype=torch.float64, device=d)     # [output_1_accuracy, output_2_accuracy]
+        self.acc_partial = None
+        self.row_hit = torch.zeros(max(R, 1), dtype=torch.int32, device=d) if self.want_metrics else None
+        self.row_correct = torch.zeros(B, dtype=torch.float64, device=d) if self.want_metrics else None
         self.bce_partial = None
         self.x_dense = None               # dense 0/1 rows of x: operand of the tensor-core dW1 = x^T g1 GEMM
         self.big16 = self.precision == "bf16"     # the seven 512 <-> C passes on bf16 operands (kind::f16)
@@ -157,9 +165,18 @@ class DAEEngine:
                 raise ValueError("tensor-core precision modes need num_cards % 4 == 0 (16-byte TMA rows)")
             from . import tensorcore
             self.bce_partial = torch.zeros(tensorcore.bce_partial_count(B, self.cpad), dtype=torch.float64, device=d)
+            if self.want_metrics:
+                self.acc_partial = torch.zeros_like(self.bce_partial)
         lib = _lib.load()
         ws = max(lib.cc_colsum_workspace_bytes(T, max(self.cpad, max(HIDDEN))), 1024)
         self.cs_ws = torch.empty(ws // 4, dtype=f32, device=d)
+
+    def kl_argmax(self):
+        """First maximal column of every row of M-hat (int32 (C,)): the target side of Keras' categorical_accuracy."""
+        if getattr(self, "_kl_argmax", None) is None:
+            self._kl_argmax = torch.empty(self.C, dtype=torch.int32, device=self.dev)
+            call("cc_kl_target_argmax", ptr(self.mhat), self.mhat.stride(0), self.C, self.C, ptr(self._kl_argmax), stream_ptr())
+        return self._kl_argmax
 
     def kl_table(self):
         """sum_c t' log t' of every row of M-hat (float64 (C,)): the model-independent half of the KLD, built on first
@@ -328,11 +345,11 @@ class DAEEngine:
                     if big16:
                         tensorcore.gemm_bce(h16, self.w4_16["main"][:, :self.C], P(names[3] + "/bias"), self.y_bits,
                                             float(self.global_B) * float(self.C), self.dz1_16, self.bce_partial,
-                                            precision="bf16", dbias=G(names[3] + "/bias"))
+                                            precision="bf16", dbias=G(names[3] + "/bias"), acc_partial=self.acc_partial)
                     else:
                         tensorcore.gemm_bce(h, W(names[3] + "/kernel"), P(names[3] + "/bias"), self.y_bits,
                                             float(self.global_B) * float(self.C), self.z1, self.bce_partial, precision=pr,
-                                            dbias=G(names[3] + "/bias"))
+                                            dbias=G(names[3] + "/bias"), acc_partial=self.acc_partial)
                 bce_rows, bce_n = self.bce_partial, self.bce_partial.numel()
             else:
                 with self._timed("big_gemm"):
@@ -343,6 +360,10 @@ class DAEEngine:
             n_launch += 1
         # ---------------- losses (logits -> dlogits in place) ----------------
         if not tc:
+            if self.want_metrics:           # the exact-fp32 mode keeps its logits in memory: count before they become dlogits
+                call("cc_binary_accuracy_rows", ptr(self.z1), self.z1.stride(0), ptr(self.y_bits), self.yw, B, self.C,
+                     ptr(self.row_correct), st)
+                n_launch += 1
             with self._timed("bce"):
                 call("cc_bce_logits_fwd_bwd", ptr(self.z1), self.z1.stride(0), ptr(self.y_bits), self.yw, B, self.C,
                      self.cpad, float(self.global_B) * float(self.C), ptr(self.z1), self.z1.stride(0),
@@ -357,20 +378,29 @@ class DAEEngine:
                 if big16:
                     if not reg_dbias_fused:
                         raise RuntimeError("bf16 mode needs the persistent softmax-KL kernel (num_cards % 4 == 0, C <= 25600)")
-                    call("cc_softmax_kl_fwd_bwd_ex", ptr(self.z2), self.z2.stride(0), ptr(self.mhat), self.mhat.stride(0),
+                    call("cc_softmax_kl_fwd_bwd_metrics", ptr(self.z2), self.z2.stride(0), ptr(self.mhat), self.mhat.stride(0),
                          ptr(self.reg_rows), R, self.C, self.cpad, self.reg / float(self.global_R), None, 0,
                          ptr(self.row_kl), 1, ptr(G(dec_names("reg")[3] + "/bias")), ptr(self.dz2_16),
-                         self.dz2_16.stride(0), ptr(self.kl_table()), st)
+                         self.dz2_16.stride(0), ptr(self.kl_table()), ptr(self.kl_argmax()) if self.want_metrics else None,
+                         ptr(self.row_hit) if self.want_metrics else None, st)
                 else:
-                    call("cc_softmax_kl_fwd_bwd_ex", ptr(self.z2), self.z2.stride(0), ptr(self.mhat), self.mhat.stride(0),
+                    if self.want_metrics and not reg_dbias_fused:
+                        raise RuntimeError("metrics need the persistent softmax-KL kernel (num_cards % 4 == 0, C <= 25600)")
+                    call("cc_softmax_kl_fwd_bwd_metrics", ptr(self.z2), self.z2.stride(0), ptr(self.mhat), self.mhat.stride(0),
                          ptr(self.reg_rows), R, self.C, self.cpad, self.reg / float(self.global_R), ptr(self.z2),
                          self.z2.stride(0), ptr(self.row_kl), int(tc),
                          ptr(G(dec_names("reg")[3] + "/bias")) if reg_dbias_fused else None, None, 0,
-                         ptr(self.kl_table()) if reg_dbias_fused else None, st)
+                         ptr(self.kl_table()) if reg_dbias_fused else None,
+                         ptr(self.kl_argmax()) if self.want_metrics else None,
+                         ptr(self.row_hit) if self.want_metrics else None, st)
             n_launch += 1
         call("cc_loss_finalize", ptr(bce_rows), bce_n, float(self.global_B) * float(self.C), ptr(self.row_kl), R,
              float(self.global_R), self.reg, ptr(self.loss3), st)
         n_launch += 1
+        if self.want_metrics:       # this rank's share of the two accuracies (summed over the ranks with the losses)
+            hits1 = (self.acc_partial if tc else self.row_correct).sum()
+            self.metrics2[0] = hits1 / (float(self.global_B) * float(self.C))
+            self.metrics2[1] = (self.row_hit[:R].sum().double() / float(self.global_R)) if R else 0.0
         # ---------------- backward: decoders ----------------
         ga4 = self.ga[3]
         GKB = s.g_kernel_and_bias           # (in + 1, out) view: kernel gradient rows + the bias gradient row
@@ -511,6 +541,8 @@ class DAEEngine:
             if self.dp_mode == "nccl":
                 dist.all_reduce(self.store.grads, op=dist.ReduceOp.SUM, group=self.group)
             dist.all_reduce(self.loss3, op=dist.ReduceOp.SUM, group=self.group)
+            if self.want_metrics:
+                dist.all_reduce(self.metrics2, op=dist.ReduceOp.SUM, group=self.group)
 
     def _adam_p2p(self):
         """Reduce-scatter + Adam + all-gather in one kernel over NVLink peer memory (cc_adam_step_p2p).  The loss

@@ -33,17 +33,18 @@ def gemm(a, b, c, *, transa=False, transb=False, bias=None, relu=False, mask=Non
     return c
 
 
-def gemm_bce(a, w, bias, ybits, count, dz, loss_partial, precision="tf32", round_out=True, dbias=None):
+def gemm_bce(a, w, bias, ybits, count, dz, loss_partial, precision="tf32", round_out=True, dbias=None, acc_partial=None):
     """Fused  z = a @ w + bias -> BCE loss partials + dlogits  (z never stored); ``dbias`` (optional, float [n])
-    receives the column sums of dlogits = the gradient of ``bias``."""
+    receives the column sums of dlogits = the gradient of ``bias``; ``acc_partial`` (optional, float64 like
+    ``loss_partial``) the counts of correctly rounded cells (Keras binary_accuracy)."""
     m, k = a.shape
     n = w.shape[1]
     dz16 = dz.dtype == torch.bfloat16        # bf16 dlogits for the bf16 dW / dX GEMMs ("bf16" mode)
     if dz16 and precision != "bf16":
         raise TypeError("bf16 dlogits come with bf16 operands")
-    call("cc_gemm_bce_tc", PRECISION_CODE[precision], m, n, k, ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(bias),
+    call("cc_gemm_bce_tc_ex", PRECISION_CODE[precision], m, n, k, ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(bias),
          ptr(ybits), ybits.stride(0), float(count), ptr(dz), dz.stride(0), ptr(loss_partial), ptr(dbias),
-         int(round_out and precision == "tf32"), int(dz16), stream_ptr())
+         int(round_out and precision == "tf32"), int(dz16), ptr(acc_partial), stream_ptr())
 
 
 def bce_partial_count(m, lddz):

@@ -27,9 +27,12 @@ def reset_random_seeds(seed):
 
 
 def fit(model, generator, epochs, reg, *, group=None, log=print, steps_per_epoch=None, max_cube_size=None,
-        initial_epoch=0, checkpoint_dir=None, save_every=None, overflow_check_every=50):
+        initial_epoch=0, checkpoint_dir=None, save_every=None, overflow_check_every=50, metrics=True):
     """``autoencoder.fit(generator, epochs=epochs)`` (reference train.py:99-102).  Returns the history
-    ``[{"loss", "output_1_loss", "output_2_loss"}]`` per epoch (means over the epoch's steps).
+    ``[{"loss", "output_1_loss", "output_2_loss", "output_1_accuracy", "output_2_accuracy"}]`` per epoch (means over
+    the epoch's steps, like Keras' progress line).  ``metrics`` mirrors ``compile(..., metrics=['accuracy'])`` (reference
+    train.py:87): Keras resolves the name to binary accuracy on the sigmoid output and categorical accuracy on the
+    softmax output; both are counted inside the loss kernels.
 
     Beyond the reference: ``initial_epoch`` (Keras' own argument name) continues a run -- the epoch
     shuffle is a function of (seed, epoch), Adam's step counter lives in the model -- and every ``save_every`` epochs the
@@ -45,7 +48,7 @@ def fit(model, generator, epochs, reg, *, group=None, log=print, steps_per_epoch
     lb = gb // world
     eng = DAEEngine(model, generator.mhat_device(), batch=lb, reg_rows=lb, reg=reg,
                     max_cube_size=max_cube_size or max(generator.csr.max_size, 1), global_batch=gb,
-                    global_reg_rows=gb, group=group)
+                    global_reg_rows=gb, group=group, metrics=metrics)
     history = []
     nsteps = steps_per_epoch or len(generator)
     if initial_epoch:
@@ -54,18 +57,26 @@ def fit(model, generator, epochs, reg, *, group=None, log=print, steps_per_epoch
         log(f"Epoch {epoch + 1}/{epochs}")
         t0 = time.time()
         acc = torch.zeros(3, dtype=torch.float64, device=model.device)
+        macc = torch.zeros(2, dtype=torch.float64, device=model.device)
         for b in range(nsteps):
             ids_t = generator.batch_ids(b, rank, world)           # a slice of the epoch's device-side permutation
             eng.sample_batch(generator.indptr, generator.indices_dev, ids_t, generator.alias_prob, generator.alias_idx,
                              generator.noise, generator.noise_std, seed=generator.seed + 7919 * rank)
             acc += eng.train_step()
+            if metrics:
+                macc += eng.metrics2
             if overflow_check_every and (b + 1) % overflow_check_every == 0:
                 eng.check_overflow()                                # (one 4-byte read: the only host sync inside an epoch)
         eng.check_overflow()
         mean = (acc / max(nsteps, 1)).cpu().numpy()
         history.append({"loss": float(mean[2]), "output_1_loss": float(mean[0]), "output_2_loss": float(mean[1])})
-        log(f"{nsteps}/{nsteps} - {time.time() - t0:.0f}s - loss: {mean[2]:.4f} - output_1_loss: {mean[0]:.4f} "
-            f"- output_2_loss: {mean[1]:.4f}")
+        line = (f"{nsteps}/{nsteps} - {time.time() - t0:.0f}s - loss: {mean[2]:.4f} - output_1_loss: {mean[0]:.4f} "
+                f"- output_2_loss: {mean[1]:.4f}")
+        if metrics:
+            mm = (macc / max(nsteps, 1)).cpu().numpy()
+            history[-1].update({"output_1_accuracy": float(mm[0]), "output_2_accuracy": float(mm[1])})
+            line += f" - output_1_accuracy: {mm[0]:.4f} - output_2_accuracy: {mm[1]:.4f}"
+        log(line)
         generator.on_epoch_end()
         if checkpoint_dir and save_every and (epoch + 1) % save_every == 0 and epoch + 1 < epochs:
             eng.gather_adam_state()

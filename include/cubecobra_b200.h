@@ -213,6 +213,13 @@ int cc_gemm_tc(int precision, int transa, int transb, int m, int n, int k, const
 int cc_gemm_bce_tc(int precision, int m, int n, int k, const void* a, int64_t lda, const void* w, int64_t ldw,
                    const float* bias, const uint32_t* ybits, int64_t ywords, double count, void* dz, int64_t lddz,
                    double* loss_partial, float* dbias, int round_tf32, int dz_bf16, void* stream);
+/* The same with Keras' binary_accuracy (metrics=['accuracy'], src/ml/train.py:87) counted on the way: acc_partial
+ * (nullable, float64, sized and laid out like loss_partial) receives per-(tile, warp) counts of the cells with
+ * round(sigmoid(z)) == y; their sum / (B*C) is the metric Keras reports as output_1_accuracy. */
+int cc_gemm_bce_tc_ex(int precision, int m, int n, int k, const void* a, int64_t lda, const void* w, int64_t ldw,
+                      const float* bias, const uint32_t* ybits, int64_t ywords, double count, void* dz, int64_t lddz,
+                      double* loss_partial, float* dbias, int round_tf32, int dz_bf16, double* acc_partial,
+                      void* stream);
 int64_t cc_gemm_bce_partial_count(int m, int lddz);
 /* CTA-pair tiling of the tcgen05 GEMMs (256 x 256 tiles on two SMs, tcgen05.mma.cta_group::2):
  * -1 = the planner decides per problem (default), 0 = never, 1 = whenever the shape allows it. */
@@ -248,6 +255,10 @@ int cc_relu_mask_f32(float* x, int64_t ldx, const float* act, int64_t lda, int m
 int cc_bce_logits_fwd_bwd(const float* z, int64_t ldz, const uint32_t* ybits, int64_t ywords, int32_t batch,
                           int32_t num_cards, int32_t ncols_pad, double count, float* dz, int64_t lddz,
                           double* row_loss, void* stream);
+/* row_correct[b] = number of cells with (z > 0) == y: the numerator of Keras' binary_accuracy (metrics=['accuracy'],
+ * src/ml/train.py:87) for the exact-fp32 mode, which keeps its logits in memory (the fused GEMM counts in its epilogue). */
+int cc_binary_accuracy_rows(const float* z, int64_t ldz, const uint32_t* ybits, int64_t ywords, int32_t batch,
+                            int32_t num_cards, double* row_correct, void* stream);
 /* row r uses target row target_rows[r] (nullable = r); dz = grad_scale*(q*S - t'*1[unclipped]).
  * dbias (nullable, float [num_cards]): also emit the column sums of dz, i.e. the softmax layer's bias gradient, from
  * the persistent form of the kernel (one CTA per SM walks the rows, next row prefetched with cp.async, column sums
@@ -263,6 +274,15 @@ int cc_softmax_kl_fwd_bwd_ex(const float* z, int64_t ldz, const float* target, i
                              int32_t rows, int32_t num_cards, int32_t ncols_pad, double grad_scale, float* dz,
                              int64_t lddz, double* row_loss, int round_tf32, float* dbias, void* dz_bf16,
                              int64_t lddz_bf16, const double* tlogt, void* stream);
+/* The same with Keras' categorical_accuracy counted on the way (metrics=['accuracy'], src/ml/train.py:87): row_hit[r] = 1
+ * where the first maximal logit of row r sits in column target_argmax[target row] (cc_kl_target_argmax builds that table:
+ * first maximal column of every row of M-hat, like tf.argmax).  Persistent kernels only (dbias != NULL). */
+int cc_softmax_kl_fwd_bwd_metrics(const float* z, int64_t ldz, const float* target, int64_t ldt, const int32_t* target_rows,
+                                  int32_t rows, int32_t num_cards, int32_t ncols_pad, double grad_scale, float* dz,
+                                  int64_t lddz, double* row_loss, int round_tf32, float* dbias, void* dz_bf16,
+                                  int64_t lddz_bf16, const double* tlogt, const int32_t* target_argmax, int32_t* row_hit,
+                                  void* stream);
+int cc_kl_target_argmax(const float* target, int64_t ldt, int32_t target_rows, int32_t num_cards, int32_t* out, void* stream);
 /* Which persistent kernel serves dbias != NULL: 0 = choose (512 threads with the target row and the column sums in
  * registers when num_cards <= 22 528, else the 1024-thread form), 1 = always the 1024-thread form (tests, A/B runs). */
 int cc_softmax_kl_set_variant(int variant);

@@ -157,6 +157,19 @@ def loss_and_grads_np(params, x, y, reg_rows, t_reg, reg, onehot_rows_as_gather=
     return (total, bce, kl), grads
 
 
+def binary_accuracy_np(z1, y):
+    """Keras ``metrics=['accuracy']`` on the sigmoid output trained with binary_crossentropy (reference
+    ``train.py:87``) resolves to ``binary_accuracy``: mean over all cells of ``(sigmoid(z) > 0.5) == y``  [Keras-2.5
+    metrics.binary_accuracy, threshold 0.5], i.e. ``(z > 0) == y``."""
+    return float(np.mean((np.asarray(z1) > 0) == (np.asarray(y) != 0)))
+
+
+def categorical_accuracy_np(z2, t):
+    """The same list entry on the softmax output (target = a probability row) resolves to ``categorical_accuracy``:
+    mean over rows of ``argmax(y_true) == argmax(y_pred)``, first maximal index on ties  [Keras-2.5]."""
+    return float(np.mean(np.argmax(np.asarray(t), axis=1) == np.argmax(np.asarray(z2), axis=1)))
+
+
 def adam_step_np(params, grads, m, v, t, lr=1e-3, b1=0.9, b2=0.999, eps=KERAS_EPS):
     """TF/Keras-2.5 ``Adam`` dense update at (1-based) step ``t``; in place."""
     lr_t = lr * np.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)

@@ -683,3 +683,43 @@ def test_softmax_kl_persistent_kernels_vs_oracle(c, rows, fast):
             assert torch.allclose(a[1], b[1], rtol=1e-5)
     finally:
         E.call("cc_softmax_kl_set_variant", 0)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_keras_accuracy_metrics_vs_oracle(precision):
+    """metrics=['accuracy'] (reference train.py:87): binary accuracy of the sigmoid tower (counted in the fused BCE
+    epilogue, or by cc_binary_accuracy_rows in the exact-fp32 mode) and categorical accuracy of the softmax tower (first
+    maximal logit against the target row's argmax, counted in the softmax-KL kernel), against the float64 oracle."""
+    c, x, y, rows, mh = _problem(c=400, k=300, b=96, r=80, seed=21)
+    params = od.init_params(c, seed=3)
+    rng = np.random.default_rng(2)
+    for kname in params:          # larger weights: logits away from zero, peaked softmax rows
+        params[kname] = (params[kname] * 3 + (rng.standard_normal(params[kname].shape) * 0.2 if kname.endswith("bias") else 0)).astype(np.float32)
+    model = M.CC_Recommender(c, device="cuda", precision=precision)
+    model.set_weights_dict(params)
+    mhat = torch.tensor(mh.astype(np.float32)).cuda()
+    eng = E.DAEEngine(model, mhat, batch=x.shape[0], reg_rows=len(rows), reg=0.1, max_cube_size=80, metrics=True)
+    sb = M.SparseBatch.from_csr(CubeCSR.from_dense(x), "cuda")
+    eng.set_batch(sb, torch.tensor(_bits_from_dense(y)).cuda(), torch.tensor(rows).cuda())
+    eng.forward_backward()
+    got = eng.metrics2.cpu().numpy()
+    z1, z2, _ = od.forward_np(params, x, rows)
+    t32 = mh.astype(np.float32)[rows]
+    ref1, ref2 = od.binary_accuracy_np(z1, y), od.categorical_accuracy_np(z2, t32)
+    # cells whose logit is within the mode's rounding of zero, rows whose two best logits are that close, may flip
+    band = {"fp32": 1e-5, "tf32": 5e-3, "bf16": 3e-2}[precision]
+    near1 = float(np.mean(np.abs(z1) < band * np.abs(z1).max()))
+    top2 = np.sort(z2, axis=1)[:, -2:]
+    near2 = float(np.mean((top2[:, 1] - top2[:, 0]) < band * np.abs(z2).max()))
+    assert abs(got[0] - ref1) <= near1 + 1e-12, (got, ref1, near1)
+    assert abs(got[1] - ref2) <= near2 + 1e-12, (got, ref2, near2)
+    assert 0.5 < ref1 < 1.0
+    # the table behind the target side: first maximal column of every M-hat row
+    assert np.array_equal(eng.kl_argmax().cpu().numpy(), np.argmax(mh.astype(np.float32), axis=1))
+    # metrics ride along without touching losses or gradients
+    ref_eng = E.DAEEngine(M.CC_Recommender(c, device="cuda", precision=precision), mhat, batch=x.shape[0], reg_rows=len(rows),
+                          reg=0.1, max_cube_size=80)
+    ref_eng.model.set_weights_dict(params)
+    ref_eng.set_batch(sb, torch.tensor(_bits_from_dense(y)).cuda(), torch.tensor(rows).cuda())
+    ref_eng.forward_backward()
+    assert torch.allclose(ref_eng.loss3, eng.loss3, rtol=1e-12)

@@ -192,6 +192,8 @@ def test_datagenerator_mirror_and_fit():
     model = M.CC_Recommender(c, device="cuda", seed=0, precision="tf32")
     hist = T.fit(model, gen, epochs=6, reg=0.1, log=lambda *_: None)
     assert len(hist) == 6 and hist[-1]["loss"] < hist[0]["loss"]                 # it trains
+    assert 0.0 <= hist[0]["output_2_accuracy"] <= 1.0 and hist[-1]["output_1_accuracy"] >= hist[0]["output_1_accuracy"] - 0.05
+    assert set(hist[0]) == {"loss", "output_1_loss", "output_2_loss", "output_1_accuracy", "output_2_accuracy"}
     assert abs(hist[0]["loss"] - (hist[0]["output_1_loss"] + 0.1 * hist[0]["output_2_loss"])) < 1e-9
     assert int(model.store.step.item()) == 18
 
