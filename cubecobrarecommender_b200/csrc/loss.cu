@@ -565,6 +565,12 @@ softmax_kl_regs_kernel(const float* __restrict__ z, int64_t ldz, const float* __
       tm = t;
     }
     const float mx = tm;
+    // exp(z - max): FAST folds the subtraction into the exponent's scaling, ex2(z * log2e - max * log2e): one FFMA + MUFU
+    const float mxl = mx * 1.4426950408889634f;
+    auto EXPM = [&](float zc) -> float {
+      if (FAST) { float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(zc, 1.4426950408889634f, -mxl))); return e; }
+      return expf(zc - mx);
+    };
     float ts = 0.f;
     int cand = 0x7fffffff;                                  // first column holding the row maximum (metrics only)
 #pragma unroll
@@ -572,7 +578,7 @@ softmax_kl_regs_kernel(const float* __restrict__ z, int64_t ldz, const float* __
       const int i = threadIdx.x + k * KLR_THREADS;
       if (i < n4) {
         const float4 v = s4[i];
-        ts += (EXPF(v.x - mx) + EXPF(v.y - mx)) + (EXPF(v.z - mx) + EXPF(v.w - mx));
+        ts += (EXPM(v.x) + EXPM(v.y)) + (EXPM(v.z) + EXPM(v.w));
         if (row_hit) {                                      // CTA-uniform
           const int first = v.x == mx ? 0 : v.y == mx ? 1 : v.z == mx ? 2 : v.w == mx ? 3 : -1;
           if (first >= 0) cand = min(cand, 4 * i + first);
@@ -596,9 +602,13 @@ softmax_kl_regs_kernel(const float* __restrict__ z, int64_t ldz, const float* __
     const float inv_sum = 1.f / sumexp;
     const float lse = mx + LOGF(sumexp);
     const float log_eps = -16.11809565095832f;               // log(1e-7)
+    // q = e / sumexp is clipped to [1e-7, 1] by Keras.  q <= 1 holds by construction (every e <= 1 and the maximum
+    // contributes exp(0) = 1 to the sum), so the clip acts iff e < 1e-7 * sumexp: one compare against a row constant
+    const float e_clip = KERAS_EPS * sumexp;
     // sweep 2: loss = sum t' (log t' - log q'), S = sum of t' over the cards whose q survives the clip.  The logit is
     // needed one last time here (log q = z - lse); e = exp(z - max) replaces it in shared memory for sweep 3 (keeping
-    // both z and e in registers across the reduction would not fit beside the targets and the column sums)
+    // both z and e in registers across the reduction would not fit beside the targets and the column sums), and the
+    // clipped target t' replaces the raw one in the registers
     float loss = 0.f, sun = 0.f;
 #pragma unroll
     for (int k = 0; k < ITERS; ++k) {
@@ -606,20 +616,21 @@ softmax_kl_regs_kernel(const float* __restrict__ z, int64_t ldz, const float* __
       if (i < n4) {
         const float4 v = s4[i];
         const float zz[4] = {v.x, v.y, v.z, v.w};
-        const float tt[4] = {tv[k].x, tv[k].y, tv[k].z, tv[k].w};
+        float tt[4] = {tv[k].x, tv[k].y, tv[k].z, tv[k].w};
         float ee[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          ee[c] = EXPF(zz[c] - mx);
-          const float q = ee[c] * inv_sum;
-          const float tc = fminf(fmaxf(tt[c], KERAS_EPS), 1.f);
-          const bool un = (q >= KERAS_EPS) && (q <= 1.f);
-          const float logq = q >= KERAS_EPS ? fminf(zz[c] - lse, 0.f) : log_eps;   // log(clip(q, 1e-7, 1))
-          if (tlogt) loss -= tc * logq;
-          else loss += tc * (LOGF(tc) - logq);
-          sun += un ? tc : 0.f;
+          ee[c] = EXPM(zz[c]);
+          tt[c] = fminf(fmaxf(tt[c], KERAS_EPS), 1.f);
+          const bool un = ee[c] >= e_clip;
+          const float zl = FAST ? zz[c] - lse : fminf(zz[c] - lse, 0.f);
+          const float logq = un ? zl : log_eps;             // log(clip(q, 1e-7, 1))
+          if (tlogt) loss = fmaf(-tt[c], logq, loss);
+          else loss += tt[c] * (LOGF(tt[c]) - logq);
+          sun += un ? tt[c] : 0.f;
         }
         s4[i] = make_float4(ee[0], ee[1], ee[2], ee[3]);
+        tv[k] = make_float4(tt[0], tt[1], tt[2], tt[3]);
       }
     }
     const float2 ls = block_sum2_r(loss, sun, red);
@@ -628,7 +639,7 @@ softmax_kl_regs_kernel(const float* __restrict__ z, int64_t ldz, const float* __
     const float qs = inv_sum * S * grad_scale;
     float4* d4 = dz16 ? nullptr : reinterpret_cast<float4*>(dz + int64_t(r) * lddz);
     uint2* d16 = dz16 ? reinterpret_cast<uint2*>(dz16 + int64_t(r) * lddz16) : nullptr;
-    // sweep 3: dlogits = (q S - t' 1[unclipped]) scale, column sums, store
+    // sweep 3: dlogits = (q S - t' 1[unclipped]) scale = e (S scale / sumexp) - (t' scale) 1[unclipped]; column sums; store
 #pragma unroll
     for (int k = 0; k < ITERS; ++k) {
       const int i = threadIdx.x + k * KLR_THREADS;
@@ -640,11 +651,10 @@ softmax_kl_regs_kernel(const float* __restrict__ z, int64_t ldz, const float* __
           float gg[4];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const float q = ev[c] * inv_sum;
-            const float tc = fminf(fmaxf(tt[c], KERAS_EPS), 1.f);
-            const bool un = (q >= KERAS_EPS) && (q <= 1.f);
-            gg[c] = FAST ? fmaf(ev[c], qs, un ? -tc * grad_scale : 0.f) : (q * S - (un ? tc : 0.f)) * grad_scale;
-            if (round_tf32) gg[c] = rn_tf32(gg[c]);
+            const bool un = ev[c] >= e_clip;
+            gg[c] = FAST ? fmaf(ev[c], qs, un ? -tt[c] * grad_scale : 0.f)
+                         : (ev[c] * inv_sum * S - (un ? tt[c] : 0.f)) * grad_scale;
+            if (round_tf32) gg[c] = rn_tf32_bits(gg[c]);
           }
           g = make_float4(gg[0], gg[1], gg[2], gg[3]);
           acc[k].x += g.x; acc[k].y += g.y; acc[k].z += g.z; acc[k].w += g.w;

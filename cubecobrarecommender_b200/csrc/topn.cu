@@ -616,7 +616,8 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + size_t(nbuf) * row_bytes);   // RS_CAP
   uint32_t* lead32 = reinterpret_cast<uint32_t*>(keys);            // the leaders' stand-ins live here before sweep 2
   int* rk = reinterpret_cast<int*>(keys + RS_CAP);                                                        // RS_CAP, zero between uses
-  uint32_t* bm = reinterpret_cast<uint32_t*>(rk + RS_CAP);                                                // words
+  unsigned long long* keys2 = reinterpret_cast<unsigned long long*>(rk + RS_CAP);                         // RS_CAP (REGS: the dense keys)
+  uint32_t* bm = reinterpret_cast<uint32_t*>(keys2 + RS_CAP);                                             // words
   constexpr float WORST = DESC ? -INFINITY : INFINITY;
 
   auto issue = [&](int cube, int b) {                       // one thread: the whole row on barrier b
@@ -787,28 +788,24 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
         if (lane == 0) s_wc[wid] = wcnt;
         __syncthreads();
         stamp(5);                                           // 5: sweep 2 (+ barrier)
-        // densify: segment slot -> position = survivors of the lower warps + slot; raw -> composite key on the way.  Every
-        // thread owns two slots (one in the lower eight segments, one in the upper eight); all reads precede all writes.
-        int total = 0, base_lo = 0, base_hi = 0;
-        bool over = false;
-        const int w_lo = tid >> 6, w_hi = 8 + (tid >> 6);
+        // densify: segment slot -> position = survivors of the lower warps + slot, raw -> composite key on the way,
+        // into a second buffer (no read-before-write hazard, hence no barrier in between).  Every warp scans the 16
+        // counts itself; every thread owns two slots (one in the lower eight segments, one in the upper eight).
+        const int c = lane < RS_THREADS / 32 ? s_wc[lane] : 0;
+        const bool over = __any_sync(0xffffffffu, c > RS_SEG);
+        int incl = c;
 #pragma unroll
-        for (int w = 0; w < RS_THREADS / 32; ++w) {
-          const int c = s_wc[w];
-          if (w == w_lo) base_lo = total;
-          if (w == w_hi) base_hi = total;
-          over |= c > RS_SEG;
-          total += c;
-        }
-        if (!over) {                                        // CTA-uniform
+        for (int o = 1; o < RS_THREADS / 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int total = __shfl_sync(0xffffffffu, incl, RS_THREADS / 32 - 1);
+        const int w_lo = tid >> 6, w_hi = 8 + (tid >> 6);
+        const int base_lo = __shfl_sync(0xffffffffu, incl - c, w_lo), base_hi = __shfl_sync(0xffffffffu, incl - c, w_hi);
+        const int cnt_lo = __shfl_sync(0xffffffffu, c, w_lo), cnt_hi = __shfl_sync(0xffffffffu, c, w_hi);
+        if (!over) {                                        // CTA-uniform (every warp scanned the same counts)
           const int sl = tid & (RS_SEG - 1);
-          const bool v_lo = sl < s_wc[w_lo], v_hi = sl < s_wc[w_hi];
-          const unsigned long long r_lo = v_lo ? keys[w_lo * RS_SEG + sl] : 0ull, r_hi = v_hi ? keys[w_hi * RS_SEG + sl] : 0ull;
+          if (sl < cnt_lo) keys2[base_lo + sl] = raw_to_key(keys[w_lo * RS_SEG + sl]);
+          if (sl < cnt_hi) keys2[base_hi + sl] = raw_to_key(keys[w_hi * RS_SEG + sl]);
           __syncthreads();
-          if (v_lo) keys[base_lo + sl] = raw_to_key(r_lo);
-          if (v_hi) keys[base_hi + sl] = raw_to_key(r_hi);
-          __syncthreads();
-          stamp(6);                                         // 6: survivors -> keys (+ barriers)
+          stamp(6);                                         // 6: survivors -> keys (+ barrier)
           m = total;
           ranked_from_regs = true;
         }
@@ -872,7 +869,8 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
       out_ids[int64_t(cube) * n + r] = (int32_t)t;
       if (out_vals) out_vals[int64_t(cube) * n + r] = __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
     };
-    rs_rank_partial(keys, m, rk, tid);
+    const unsigned long long* kfin = ranked_from_regs ? keys2 : keys;
+    rs_rank_partial(kfin, m, rk, tid);
     __syncthreads();
     stamp(7);                                               // 7: issue of the next row + final ranking (+ barrier)
     // every thread has read s_cnt, s_T and s_zb by now; their next use lies behind the next cube's barriers
@@ -880,7 +878,7 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
     for (int i = tid; i < m; i += RS_THREADS) {
       const int r = rk[i];
       rk[i] = 0;
-      if (r < n) write_ranked(keys[i], r);
+      if (r < n) write_ranked(kfin[i], r);
     }
     for (int i = m + tid; i < n; i += RS_THREADS) {
       out_ids[int64_t(cube) * n + i] = -1;
@@ -900,7 +898,7 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
 
 static size_t rowselect_smem_bytes(int32_t num_cards, int nbuf) {
   const size_t cr = (size_t(num_cards) + 3) & ~size_t(3);
-  return size_t(nbuf) * cr * 4 + size_t(RS_CAP) * 8 + size_t(RS_CAP) * 4 + size_t((num_cards + 31) / 32) * 4;
+  return size_t(nbuf) * cr * 4 + size_t(RS_CAP) * 8 + size_t(RS_CAP) * 4 + size_t(RS_CAP) * 8 + size_t((num_cards + 31) / 32) * 4;
 }
 
 // rows must be 16-byte aligned and a whole number of 16-byte units (bulk copies), and two of them must fit in shared memory

@@ -270,7 +270,7 @@ def test_gemm_tcgen05_tf32_all_layouts(ta, tb, m, n, k, split, tile_n, pair_mode
 @pytest.mark.parametrize("ta,tb,m,n,k", [(1, 0, 512, 5000, 4096),      # dW-like: fewer tiles than units, all stream-K
                                          (0, 1, 2500, 512, 20992),     # dX-like: long K, non-linear epilogue (two passes)
                                          (1, 0, 768, 20000, 4096),     # data-parallel waves + a stream-K tail that starts
-                                         (1, 1, 1030, 3000, 4104)])    # mid-column; ragged M/N/K
+                                         (1, 1, 1032, 3000, 4104)])    # mid-column; ragged M/N/K
 def test_gemm_tcgen05_hybrid_stream_k(ta, tb, m, n, k, pair, precision, pair_mode):
     """Hybrid stream-K schedule (forced on): whole tile waves data-parallel, the rest cut along K into one span per CTA
     (pair) and TMA-reduce-added into pre-zeroed tiles.  Against float64 on exactly representable operands; plain
