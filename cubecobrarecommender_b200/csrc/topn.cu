@@ -801,12 +801,16 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
         const int base_lo = __shfl_sync(0xffffffffu, incl - c, w_lo), base_hi = __shfl_sync(0xffffffffu, incl - c, w_hi);
         const int cnt_lo = __shfl_sync(0xffffffffu, c, w_lo), cnt_hi = __shfl_sync(0xffffffffu, c, w_hi);
         if (!over) {                                        // CTA-uniform (every warp scanned the same counts)
+          // (the raw entries are moved first and keyed afterwards from the dense array: keying -- a sigmoid per entry --
+          // where they lie would run in all 16 warps with a few active lanes each, measured 2 400 cycles per cube)
           const int sl = tid & (RS_SEG - 1);
-          if (sl < cnt_lo) keys2[base_lo + sl] = raw_to_key(keys[w_lo * RS_SEG + sl]);
-          if (sl < cnt_hi) keys2[base_hi + sl] = raw_to_key(keys[w_hi * RS_SEG + sl]);
+          if (sl < cnt_lo) keys2[base_lo + sl] = keys[w_lo * RS_SEG + sl];
+          if (sl < cnt_hi) keys2[base_hi + sl] = keys[w_hi * RS_SEG + sl];
           __syncthreads();
-          stamp(6);                                         // 6: survivors -> keys (+ barrier)
           m = total;
+          for (int i = tid; i < m; i += RS_THREADS) keys2[i] = raw_to_key(keys2[i]);
+          __syncthreads();
+          stamp(6);                                         // 6: survivors -> keys (+ barriers)
           ranked_from_regs = true;
         }
       }

@@ -382,8 +382,10 @@ def test_gemm_bce_fused_epilogue_vs_oracle(m, c, pair, pair_mode):
 # of near-zero gradients into +-lr weight differences, so later steps compare two slightly different nets.
 # bf16 (reported separately from the fp32/tf32 headline, BASELINE north star): bf16 operands (8-bit mantissa) in the seven
 # 512 <-> C passes, fp32 accumulation and master weights; stated tolerance: loss 2e-3 relative, gradients 5e-2 of their max.
+# (tf32 "grad": 2e-2 since the first layer of the main rows runs on the tensor cores too -- W1 enters rounded to tf32 -- and
+#  the small problem below has cubes of 10-60 cards; at the BASELINE shape the bar stays 1e-2, tests/test_gpu_baseline_shapes.py)
 TOL = {"fp32": dict(loss=1e-5, grad=2e-4, grad_later=2e-4, weight=3e-4),
-       "tf32": dict(loss=1e-3, grad=1e-2, grad_later=6e-2, weight=2.5e-3),
+       "tf32": dict(loss=1e-3, grad=2e-2, grad_later=6e-2, weight=2.5e-3),
        "bf16": dict(loss=2e-3, grad=5e-2, grad_later=0.2, weight=4e-3)}
 
 
