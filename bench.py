@@ -525,9 +525,19 @@ def run_native(args, rank, world, local_rank):
     if world == 1 and not args.no_loss_check:
         loss_check = oracle_loss_check(eng, csr, batch_ids[0], prob, alias, indptr, indices, W, log)
 
+    def batch_args(i):
+        return dict(indptr=indptr, indices=indices, batch_ids=batch_ids[i % nb], alias_prob=prob, alias_idx=alias,
+                    noise=W["noise"], noise_std=W["noise_std"], seed=1234 + rank)
+
     def step(i):
-        eng.sample_batch(indptr, indices, batch_ids[i % nb], prob, alias, W["noise"], W["noise_std"], seed=1234 + rank)
-        return eng.train_step()
+        # one step = noise F + reg-row draw for ITS batch, forward, losses, backward, exchange, Adam.  The engine draws
+        # batch i+1 on a side stream under step i's optimiser (DAEEngine.train_step(next_batch=...)), so inside the timed
+        # region every step still pays for exactly one noise launch: batch i+1's instead of its own
+        if not eng.has_prefetched_batch():
+            a = batch_args(i)
+            eng.sample_batch(a["indptr"], a["indices"], a["batch_ids"], a["alias_prob"], a["alias_idx"], a["noise"],
+                             a["noise_std"], seed=a["seed"])
+        return eng.train_step(next_batch=batch_args(i + 1))
 
     def barrier():
         if world > 1:

@@ -103,6 +103,9 @@ class DAEEngine:
         self.first_layer_tc = model.precision != "fp32" and fl in FIRST_LAYER_TENSOR_WHEN
         self._side = None
         self._side_events = []
+        self._noise_stream = None
+        self._prefetch_ready = None
+        self.noise_step = self.store.step.clone()      # batches drawn so far (see _launch_noise)
         self._alloc()
 
     # -- buffers --------------------------------------------------------------------
@@ -229,20 +232,59 @@ class DAEEngine:
         if self.R:
             self.reg_rows[:self.R].copy_(reg_rows.to(torch.int32))
 
-    def sample_batch(self, indptr, indices, batch_ids, alias_prob, alias_idx, noise=0.2, noise_std=0.1, seed=0):
-        """Noise function F + reg-row draw on the device (reference generator.py:38-103)."""
+    def _launch_noise(self, indptr, indices, batch_ids, alias_prob, alias_idx, noise, noise_std, seed):
+        """The noise kernel + reg-row draw + counter increment on the CURRENT stream.  The draws are keyed by
+        (seed, cube position, batch counter); the counter is the engine's own (``noise_step``, started from the model's
+        Adam step, so a resumed run continues the sequence) because a prefetched batch is drawn before the Adam step
+        of the batch in flight has advanced the model's counter."""
         st = stream_ptr()
         with self._timed("noise"):
             call("cc_noise_ex", ptr(indptr), ptr(indices), ptr(batch_ids), self.B, self.C, ptr(alias_prob),
-                 ptr(alias_idx), float(noise), float(noise_std), int(seed), ptr(self.store.step), self.max_cube_size,
+                 ptr(alias_idx), float(noise), float(noise_std), int(seed), ptr(self.noise_step), self.max_cube_size,
                  self.x_stride, ptr(self.x_idx), ptr(self.x_len), ptr(self.y_bits), self.yw, ptr(self.flips),
                  ptr(self.overflow), ptr(self.x_dense), self.cpad if self.x_dense is not None else 0,
                  int(self.big16), st)
         if self.R and not self._fixed_reg_rows:
             call("cc_sample_reg_rows", ptr(alias_prob), ptr(alias_idx), self.C, self.R, int(seed) ^ 0x5DEECE66D,
-                 ptr(self.store.step), ptr(self.reg_rows), st)
+                 ptr(self.noise_step), ptr(self.reg_rows), st)
+        call("cc_step_increment", ptr(self.noise_step), st)
         self._x = SparseBatch(self.x_idx, self.x_start, self.x_len)
-        self.launches += 2
+        self.launches += 3
+
+    def sample_batch(self, indptr, indices, batch_ids, alias_prob, alias_idx, noise=0.2, noise_std=0.1, seed=0):
+        """Noise function F + reg-row draw on the device (reference generator.py:38-103), on the current stream."""
+        self._join_prefetch()               # (a prefetched batch is simply replaced)
+        self._launch_noise(indptr, indices, batch_ids, alias_prob, alias_idx, noise, noise_std, seed)
+
+    # -- batch prefetch: the NEXT batch's noise kernel under this step's gradient exchange / Adam ------------------
+    def has_prefetched_batch(self):
+        return self._prefetch_ready is not None
+
+    def _join_prefetch(self):
+        if self._prefetch_ready is not None:
+            torch.cuda.current_stream(self.dev).wait_event(self._prefetch_ready)
+            self._prefetch_ready = None
+
+    def _prefetch_batch(self, nb):
+        """``nb``: dict(indptr, indices, batch_ids, alias_prob, alias_idx, noise, noise_std, seed[, wait_event, done_event]).
+        Called between backward and the optimiser: backward was the last reader of x / y / the dense rows, the
+        optimiser touches none of them, so the latency-bound noise kernel (0.09 ms) runs on a side stream under the
+        HBM-bound Adam pass instead of in front of the next forward."""
+        main = torch.cuda.current_stream(self.dev)
+        if self._noise_stream is None:
+            self._noise_stream = torch.cuda.Stream(device=self.dev)
+            self._noise_fork, self._noise_join = torch.cuda.Event(), torch.cuda.Event()
+        self._noise_fork.record(main)
+        with torch.cuda.stream(self._noise_stream):
+            self._noise_stream.wait_event(self._noise_fork)
+            if nb.get("wait_event") is not None:
+                self._noise_stream.wait_event(nb["wait_event"])
+            self._launch_noise(nb["indptr"], nb["indices"], nb.get("batch_ids"), nb["alias_prob"], nb["alias_idx"],
+                               nb.get("noise", 0.2), nb.get("noise_std", 0.1), nb.get("seed", 0))
+            if nb.get("done_event") is not None:
+                nb["done_event"].record(self._noise_stream)
+            self._noise_join.record(self._noise_stream)
+        self._prefetch_ready = self._noise_join
 
     def set_full_identity_rows(self, rank: int = 0, world: int = 1):
         """"Full-I" regulariser (README formula KL(M-hat, D2(E(I))) over ALL rows of I, the reference code samples
@@ -600,8 +642,9 @@ class DAEEngine:
                  ptr(s.step), a["lr"], a["beta1"], a["beta2"], a["eps"], ptr(sl(s.shadow)), st)
         self.launches += 1
 
-    def train_step(self):
-        """forward + backward + (all_reduce) + Adam on the batch set by set_batch/sample_batch.
+    def train_step(self, next_batch=None):
+        """forward + backward + (all_reduce) + Adam on the batch set by set_batch/sample_batch (or prefetched by the
+        previous call).  ``next_batch`` (see _prefetch_batch): draw the NEXT step's batch under this step's optimiser.
         Returns the device tensor loss3 = [bce, kl, bce + reg*kl] (no synchronisation)."""
         if self._dynamic_tiles is None:
             # overlapped all_reduces take SMs away from the persistent GEMMs at unpredictable moments: hand tiles
@@ -613,7 +656,10 @@ class DAEEngine:
                 call("cc_gemm_tc_set_dynamic_tiles", int(self._dynamic_tiles))
         if not self._dp_ready:
             self._dp_setup()
+        self._join_prefetch()
         self.forward_backward()
+        if next_batch is not None:
+            self._prefetch_batch(next_batch)
         self.allreduce_grads()
         if self.dp_mode == "p2p" and self._distributed():
             self._adam_p2p()
@@ -678,16 +724,22 @@ class HostBatchStream:
         self._next_prefetched = i
 
     def step(self, i, alias_prob, alias_idx, noise=0.2, noise_std=0.1, seed=0):
-        if self._next_prefetched < i:
-            self._prefetch(i)
-        slot = i % 2
+        slot, nslot = i % 2, (i + 1) % 2
         cur = torch.cuda.current_stream()
-        cur.wait_event(self.copied[slot])
-        self.eng.sample_batch(self.slots[slot][0], self.slots[slot][1], None, alias_prob, alias_idx, noise, noise_std,
-                              seed=seed)
-        self.consumed[slot].record(cur)
-        self._prefetch(i + 1)                                      # overlaps this step's compute
-        l3 = self.eng.train_step()
+        if not self.eng.has_prefetched_batch():                    # first step (or after a gap): draw this batch now
+            if self._next_prefetched < i:
+                self._prefetch(i)
+            cur.wait_event(self.copied[slot])
+            self.eng.sample_batch(self.slots[slot][0], self.slots[slot][1], None, alias_prob, alias_idx, noise, noise_std,
+                                  seed=seed)
+            self.consumed[slot].record(cur)
+        if self._next_prefetched < i + 1:
+            self._prefetch(i + 1)                                  # H2D of the next batch: overlaps this step's compute
+        # the next batch's noise kernel runs under this step's optimiser, as soon as its CSR has landed
+        nxt = dict(indptr=self.slots[nslot][0], indices=self.slots[nslot][1], batch_ids=None, alias_prob=alias_prob,
+                   alias_idx=alias_idx, noise=noise, noise_std=noise_std, seed=seed, wait_event=self.copied[nslot],
+                   done_event=self.consumed[nslot])
+        l3 = self.eng.train_step(next_batch=nxt)
         self.loss_host[slot].copy_(l3, non_blocking=True)
         self.ovf_host[slot].copy_(self.eng.overflow, non_blocking=True)       # rides along with the loss: no extra sync
         self.loss_done[slot].record(cur)

@@ -46,6 +46,9 @@ blk = -(-C // world)
 mhat = torch.empty((C, C), dtype=torch.float32, device=dev) if MODE != "reduce_scatter" else None   # outside the timed region
 mhat_rows = torch.empty((blk, C), dtype=torch.float32, device=dev)
 G.count_cooccurrence(indptr[:4097], indices[:4096 * S], 4096, C, counts=counts, workspace=ws, method="tensor")   # warm-up
+G.normalise_rows(counts[:64], 0, C, want_mhat=True, mhat=mhat_rows[:64])     # (first use loads the kernels: ~30 ms)
+if mhat is not None:
+    G.normalise(counts[:64, :64].contiguous(), want_m64=False, want_mhat=True, want_neg=True)
 if world > 1:
     warm = torch.ones(1 << 20, dtype=torch.int32, device=dev)
     dist.all_reduce(warm)
