@@ -573,7 +573,7 @@ __device__ __forceinline__ void rs_rank32_partial(const uint32_t* a, int* rk, in
 // PROF: thread 0 accumulates clock64() deltas per phase and writes them to prof[blockIdx.x][RS_PROF_SLOTS] (diagnostic
 // instantiation behind cc_topn_rowselect_profile; the product instantiations compile the stamps out)
 //
-// REGS (cc_topn_set_algo(4), the default since round 2 when the row fits RS_GROUPS float4 per thread): the ncu source
+// REGS (cc_topn_set_algo(4); opt-in, for rows that fit RS_GROUPS float4 per thread): the ncu source
 // view of the kernel without it (profiles/r02/topn_rowselect_stalls.txt) shows where a cube's ~14 000 cycles go -- 3% waiting
 // for the row (HBM), 32% in sweep 2 (branch-resolve and shared-memory-atomic stalls of the diverged push path), 25% at
 // barriers behind the slowest warp of a sweep.  REGS keeps the per-group maxima of sweep 1 in registers (11 floats), so
@@ -945,7 +945,7 @@ static int rowselect_launch(int variant, const float* scores, int64_t ld, int32_
 
 // float32, n <= 128: 0 = automatic (row select when the rows qualify, else the streaming select), 1 = streaming select,
 // 2 / 3 = row select, variant 0 / 1 (error if the rows do not qualify); automatic takes variant 1, the faster one
-// without REGS; 4 = the REGS form (rows of up to 22 528 cards).  The radix-select kernel stays the general path (any n, float64).
+// without REGS (the automatic choice); 4 = the REGS form (rows of up to 22 528 cards; measured no faster).  The radix-select kernel stays the general path (any n, float64).
 static int g_topn_algo = 0;
 static int g_topn_force_radix = 0;
 
@@ -958,7 +958,10 @@ static int select_small_n(const float* scores, int64_t ld, int32_t num_cards, in
   const bool regs_ok = ((num_cards + 3) >> 2) <= RS_GROUPS * RS_THREADS;
   CC_REQUIRE(regs_ok || g_topn_algo != 4, "cc_topn_masked: the REGS row select holds rows of up to %d cards", 4 * RS_GROUPS * RS_THREADS);
   if (ok && g_topn_algo != 1) {
-    const int variant = g_topn_algo == 2 ? 0 : g_topn_algo == 3 ? 1 : (regs_ok ? 2 : 1);        // 0 (automatic) and 4: REGS
+    // automatic = 2 CTAs per SM, both sweeps over shared memory: measured 105-106 us per 4096 cubes against 108-113 us for
+    // the REGS form (profiles/r02/topn_bench_regs.jsonl) -- the kernel is bound by barrier / dependency latency, not by
+    // the instructions REGS removes
+    const int variant = g_topn_algo == 2 ? 0 : g_topn_algo == 4 ? 2 : 1;
     return rowselect_launch<SIGMOID>(variant, scores, ld, num_cards, batch, mask_ptr, mask_idx,
                                      mode_only_listed, descending, n, out_ids, out_vals, out_count, st);
   }

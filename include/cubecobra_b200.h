@@ -117,11 +117,11 @@ int cc_topn_masked_f32(const float* scores, int64_t ld, int32_t num_cards, int32
  * copies, double-buffered; needs ld % 4 == 0, a 16-byte aligned base and C <= ~26 000) or, for rows that do not
  * qualify, as a warp-per-cube streaming select (one pass over the row); larger n and float64 use the radix select /
  * full bitonic ranking.  All of them implement one total order on (score, index).  NaN scores: the row select never
- * selects them.  cc_topn_set_algo: 0 = automatic (default: the row select with two CTAs per SM when the rows qualify, in
- * its register form -- per-group maxima of the first sweep kept in registers, survivors compacted by warp ballots -- for
- * rows of up to 22 528 cards), 1 = streaming select, 2 = row select with one CTA per SM and two row buffers, 3 = row
- * select with two CTAs per SM and one row buffer each, both sweeps over shared memory, 4 = the register form (an error if
- * the row is too long); tests compare all of them.  cc_topn_masked_sigmoid_f32 takes LOGITS, ranks sigmoid(logit) (the float32
+ * selects them.  cc_topn_set_algo: 0 = automatic (default: the row select with two CTAs per SM when the rows qualify),
+ * 1 = streaming select, 2 = row select with one CTA per SM and two row buffers, 3 = row select with two CTAs per SM and
+ * one row buffer each (= automatic), 4 = its register form -- per-group maxima of the first sweep kept in registers,
+ * survivors compacted by warp ballots, rows of up to 22 528 cards; measured no faster, kept as an option -- (tests
+ * compare all of them).  cc_topn_masked_sigmoid_f32 takes LOGITS, ranks sigmoid(logit) (the float32
  * probabilities the reference ranks, ml_recommend.py:78-104) and returns the winners' probabilities; n <= 128.
  * cc_topn_set_force_radix(1) pins float32 top-N to the radix kernel (tests compare the two). */
 int cc_topn_masked_sigmoid_f32(const float* logits, int64_t ld, int32_t num_cards, int32_t batch,
