@@ -58,6 +58,12 @@ def owner_slice(total: int, rank: int, world: int):
     return lo, hi
 
 
+def bucket_owner_slice(lo: int, hi: int, rank: int, world: int):
+    """``owner_slice`` inside the bucket ``[lo, hi)`` of the flat buffer (bucket bounds are 4-element aligned)."""
+    a, b = owner_slice(hi - lo, rank, world)
+    return lo + a, lo + b
+
+
 class GradBuckets:
     """Contiguous slices of the flat gradient buffer in the order backward finishes them:
     "main" decoder, "reg" decoder, then the shared "enc"oder (whose 512 x C first-layer gradient is

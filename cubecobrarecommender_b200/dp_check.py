@@ -28,6 +28,7 @@ import torch
 
 MODES = {"p2p_unicast": dict(CC_DP_MODE="p2p", CC_P2P_MULTICAST="0"),
          "p2p_multicast": dict(CC_DP_MODE="p2p", CC_P2P_MULTICAST="1"),
+         "p2p_overlap": dict(CC_DP_MODE="p2p_overlap"),
          "nccl": dict(CC_DP_MODE="nccl"),
          "nccl_overlap": dict(CC_DP_MODE="nccl_overlap")}
 

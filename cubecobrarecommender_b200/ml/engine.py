@@ -78,6 +78,9 @@ class DAEEngine:
         #   "p2p"  (default) Adam fused with the gradient exchange over NVLink peer memory: every rank owns 1/world of
         #          the parameters, reduces that slice of all ranks' gradients with peer loads, updates it and stores
         #          the result into every rank's parameters (cc_adam_step_p2p; symmetric memory)
+        #   "p2p_overlap"    the same kernel per gradient bucket (main decoder, reg decoder, encoder) on a side stream,
+        #          started as soon as backward has finished the bucket, between two symmetric-memory barriers: the two
+        #          decoders' exchange (2/3 of the bytes) runs under the rest of backward
         #   "nccl_overlap"   bucketed asynchronous NCCL all_reduce overlapped with backward (dist.GradBuckets)
         #   "nccl"           one blocking all_reduce of the whole flat gradient buffer after backward
         import os
@@ -86,9 +89,13 @@ class DAEEngine:
         self.dp_mode = os.environ.get("CC_DP_MODE", "p2p")
         if os.environ.get("CC_DP_OVERLAP") is not None:          # older switch: 1 = overlapped buckets, 0 = blocking
             self.dp_mode = "nccl_overlap" if os.environ["CC_DP_OVERLAP"] != "0" else "nccl"
-        if self.dp_mode not in ("p2p", "nccl_overlap", "nccl"):
-            raise ValueError(f"CC_DP_MODE={self.dp_mode!r}: expected p2p, nccl_overlap or nccl")
+        if self.dp_mode not in ("p2p", "p2p_overlap", "nccl_overlap", "nccl"):
+            raise ValueError(f"CC_DP_MODE={self.dp_mode!r}: expected p2p, p2p_overlap, nccl_overlap or nccl")
         self.overlap = self.dp_mode == "nccl_overlap"
+        self.p2p_buckets = self.dp_mode == "p2p_overlap"
+        if self.p2p_buckets:
+            self.dp_mode = "p2p"                 # same memory layout and kernel; only the schedule and the slicing differ
+        self._xchg = None
         self._dp_ready = False
         self._fixed_reg_rows = False
         self._dynamic_tiles = None
@@ -543,6 +550,63 @@ class DAEEngine:
         waits for the kernels enqueued so far) while the compute stream carries on with the next bucket."""
         if self.overlap and self._distributed():
             self.buckets.launch(self.store.grads, bucket, self.group)
+        if self.p2p_buckets and self._distributed():
+            self._xchg_bucket(bucket)
+
+    def _p2p_slice(self, bucket=None, rank=None):
+        """[lo, hi) of the flat buffer whose Adam state rank ``rank`` (default: this one) owns -- of the whole buffer in the
+        plain p2p mode, of every bucket in the overlapped one."""
+        from ..dist import bucket_owner_slice, owner_slice
+        s = self.store
+        rank = s.dp_rank if rank is None else rank
+        if bucket is None:
+            return owner_slice(s.total, rank, s.dp_world)
+        lo, hi = self.buckets.ranges[bucket]
+        return bucket_owner_slice(lo, hi, rank, s.dp_world)
+
+    def _xchg_bucket(self, bucket):
+        """p2p_overlap: exchange + Adam of one gradient bucket on the exchange stream, behind everything enqueued so far on
+        the compute stream and the weight-gradient side stream.  Barrier 1: every rank has finished this bucket's gradients
+        AND its last read of this bucket's parameters (a peer's all-gather stores land in them); barrier 2: every rank's
+        slice has landed; then the local tf32 shadow of the bucket."""
+        s, a = self.store, self.adam
+        main = torch.cuda.current_stream(self.dev)
+        if self._xchg is None:
+            self._xchg = torch.cuda.Stream(device=self.dev)
+            self._xchg_ev = [torch.cuda.Event() for _ in range(8)]
+            self._xchg_n = 0
+        ev = self._xchg_ev[self._xchg_n % 8]; self._xchg_n += 1
+        ev.record(main)
+        evs = None
+        if self._side is not None:
+            evs = self._xchg_ev[self._xchg_n % 8]; self._xchg_n += 1
+            evs.record(self._side)
+        lo, hi = self._p2p_slice(bucket)
+        blo, bhi = self.buckets.ranges[bucket]
+        with torch.cuda.stream(self._xchg):
+            self._xchg.wait_event(ev)
+            if evs is not None:
+                self._xchg.wait_event(evs)
+            st = stream_ptr()
+            s._g_hdl.barrier(channel=0)
+            with self._timed("adam"):
+                call("cc_adam_step_p2p", ptr(s.peer_grads), ptr(s.peer_params), s.dp_world, s.dp_rank, ptr(s.adam_m),
+                     ptr(s.adam_v), lo, hi, ptr(s.step), a["lr"], a["beta1"], a["beta2"], a["eps"],
+                     ctypes.c_void_p(s.mc_grads) if self._multicast else None,
+                     ctypes.c_void_p(s.mc_params) if self._multicast else None, st)
+            s._g_hdl.barrier(channel=0)
+            if s.shadow is not None:
+                off = blo
+                if bucket == "enc" and not (self.first_layer_tc and not self.big16):
+                    off = s.layout["encoder_e1/bias"][0]     # the first-layer kernel's shadow is never read then
+                call("cc_round_tf32", ptr(s.params[off:bhi]), ptr(s.shadow[off:bhi]), bhi - off, st)
+                self.launches += 1
+            self.launches += 3
+            if bucket == "enc":                              # the last bucket of a step
+                call("cc_step_increment", ptr(s.step), st)
+                self.launches += 1
+                self._xchg_done = self._xchg_ev[self._xchg_n % 8]; self._xchg_n += 1
+                self._xchg_done.record(self._xchg)
 
     def _dp_setup(self):
         """First distributed step: move params/grads to symmetric memory for the p2p mode (collective).  There is no
@@ -616,14 +680,15 @@ class DAEEngine:
         import torch.distributed as dist
         if not (self._distributed() and self.dp_mode == "p2p" and self._dp_ready):
             return
-        from ..dist import owner_slice
         s = self.store
         world = dist.get_world_size(self.group)
-        for r in range(world):
-            lo, hi = owner_slice(s.total, r, world)
-            src = dist.get_global_rank(self.group, r) if self.group is not None else r
-            for buf in (s.adam_m, s.adam_v):
-                dist.broadcast(buf[lo:hi], src=src, group=self.group)
+        for bucket in (self.buckets.ORDER if self.p2p_buckets else (None,)):
+            for r in range(world):
+                lo, hi = self._p2p_slice(bucket, r)
+                src = dist.get_global_rank(self.group, r) if self.group is not None else r
+                for buf in (s.adam_m, s.adam_v):
+                    if hi > lo:
+                        dist.broadcast(buf[lo:hi], src=src, group=self.group)
 
     def apply_adam(self):
         """TF-style Adam over all parameters, then the step counter advances."""
@@ -661,7 +726,9 @@ class DAEEngine:
         if next_batch is not None:
             self._prefetch_batch(next_batch)
         self.allreduce_grads()
-        if self.dp_mode == "p2p" and self._distributed():
+        if self.p2p_buckets and self._distributed():
+            torch.cuda.current_stream(self.dev).wait_event(self._xchg_done)    # all three buckets exchanged and applied
+        elif self.dp_mode == "p2p" and self._distributed():
             self._adam_p2p()
         elif self.overlap and self._distributed():
             for bucket in self.buckets.ORDER:          # Adam follows the reductions bucket by bucket
