@@ -460,32 +460,30 @@ softmax_kl_persistent_kernel(const float* __restrict__ z, int64_t ldz, const flo
   }
 }
 
-// Register-resident form (the shipped one for C <= 4 * KLR_ITERS * KLR_THREADS = 22 528 cards).  The 1024-thread kernel
+// Register-resident form (the shipped one for C <= 22 528 cards).  The 1024-thread kernel
 // above has ONE 16-byte target load in flight per thread (16 KB per SM) and re-reads the target row in its third sweep:
 // it is bound by load latency, not by HBM or by the MUFU pipe (measured 0.30 ms for 1.03 GB = 52% of the HBM peak, and
-// unchanged when three of its four MUFU ops per element were removed).  Here a CTA has 512 threads with up to 128
-// registers each: a thread issues ALL of its target loads for the row (<= 11 x 16 bytes, 88 KB in flight per SM) before
+// unchanged when three of its four MUFU ops per element were removed).  Here a CTA has 512-768 threads with 85-128
+// registers each: a thread issues ALL of its target loads for the row (7-11 x 16 bytes, 84-88 KB in flight per SM) before
 // the first sweep, keeps them in registers for sweeps 2 and 3, and keeps the bias-gradient column sums in registers
 // across rows as before.  The logits row still arrives by cp.async one row ahead, the next target row is prefetched
 // into L2.
-constexpr int KLR_THREADS = 512;
-constexpr int KLR_ITERS = 11;
-
-__device__ __forceinline__ float2 block_sum2_r(float a, float b, float2* red /* smem[16] */) {
+// Two launch shapes, chosen by the row length: 768 threads x 7 slots (85 registers per thread, 24 warps: rows of up to
+// 21 504 cards -- the 20 884 of the shipped checkpoints) and 512 threads x 11 slots (128 registers, 16 warps: up to 22 528).
+// More warps hide more of the shared-memory / MUFU latencies the kernel stalls on (ncu: profiles/r02/kl_regs_v1_stalls.txt).
+template <int WARPS>
+__device__ __forceinline__ float2 block_sum2_r(float a, float b, float2* red /* smem[WARPS] */) {
   a = warp_sum(a); b = warp_sum(b);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   __syncthreads();
   if (lane == 0) red[wid] = make_float2(a, b);
   __syncthreads();
-  float2 t = red[lane & 15];               // 16 warps; both half-warps reduce the same 16 partials
-  t.x += __shfl_xor_sync(0xffffffffu, t.x, 8); t.y += __shfl_xor_sync(0xffffffffu, t.y, 8);
-  t.x += __shfl_xor_sync(0xffffffffu, t.x, 4); t.y += __shfl_xor_sync(0xffffffffu, t.y, 4);
-  t.x += __shfl_xor_sync(0xffffffffu, t.x, 2); t.y += __shfl_xor_sync(0xffffffffu, t.y, 2);
-  t.x += __shfl_xor_sync(0xffffffffu, t.x, 1); t.y += __shfl_xor_sync(0xffffffffu, t.y, 1);
+  float2 t = lane < WARPS ? red[lane] : make_float2(0.f, 0.f);      // every warp reduces the same partials
+  t.x = warp_sum(t.x); t.y = warp_sum(t.y);
   return t;
 }
 
-template <bool FAST, int ITERS>
+template <bool FAST, int KLR_THREADS, int ITERS>
 __global__ void __launch_bounds__(KLR_THREADS, 1)
 softmax_kl_regs_kernel(const float* __restrict__ z, int64_t ldz, const float* __restrict__ target, int64_t ldt,
                        const int32_t* __restrict__ target_rows, int32_t rows, int32_t num_cards, int32_t ncols_pad,
@@ -559,10 +557,7 @@ softmax_kl_regs_kernel(const float* __restrict__ z, int64_t ldz, const float* __
       const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
       if (lane == 0) red[wid].x = tm;
       __syncthreads();
-      float t = red[lane & 15].x;
-      t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 8)); t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 4));
-      t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 2)); t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 1));
-      tm = t;
+      tm = warp_max(lane < KLR_THREADS / 32 ? red[lane].x : -INFINITY);
     }
     const float mx = tm;
     // exp(z - max): FAST folds the subtraction into the exponent's scaling, ex2(z * log2e - max * log2e): one FFMA + MUFU
@@ -585,7 +580,7 @@ softmax_kl_regs_kernel(const float* __restrict__ z, int64_t ldz, const float* __
         }
       }
     }
-    const float sumexp = block_sum2_r(ts, 0.f, red).x;
+    const float sumexp = block_sum2_r<KLR_THREADS / 32>(ts, 0.f, red).x;
     if (row_hit) {
       // Keras categorical_accuracy (metrics=['accuracy'] on the softmax output): argmax of the prediction (first maximal
       // column, like tf.argmax) against the argmax of the target row, a per-row table
@@ -633,7 +628,7 @@ softmax_kl_regs_kernel(const float* __restrict__ z, int64_t ldz, const float* __
         tv[k] = make_float4(tt[0], tt[1], tt[2], tt[3]);
       }
     }
-    const float2 ls = block_sum2_r(loss, sun, red);
+    const float2 ls = block_sum2_r<KLR_THREADS / 32>(loss, sun, red);
     if (threadIdx.x == 0) row_loss[r] = tlogt ? tlogt[trow] + double(ls.x) : double(ls.x);
     const float S = ls.y;
     const float qs = inv_sum * S * grad_scale;
@@ -889,14 +884,15 @@ __global__ void sigmoid_kernel(const float* __restrict__ z, float* __restrict__ 
 
 using namespace cc;
 
-// 0 = choose (the register-resident kernel when the row fits its 11 slots per thread), 1 = always the 1024-thread
-// kernel (cc_softmax_kl_set_variant; tests and A/B measurements)
+// 0 = choose (the register-resident kernel when the row fits: 768 threads x 7 slots, else 512 x 11), 1 = always the
+// 1024-thread kernel, 2 = the register-resident kernel in its 512-thread shape only (cc_softmax_kl_set_variant; tests
+// and A/B measurements)
 static int g_kl_variant = 0;
 
 extern "C" {
 
 int cc_softmax_kl_set_variant(int variant) {
-  CC_REQUIRE(variant == 0 || variant == 1, "cc_softmax_kl_set_variant: 0 (auto) or 1 (1024-thread kernel)");
+  CC_REQUIRE(variant >= 0 && variant <= 2, "cc_softmax_kl_set_variant: 0 (auto), 1 (1024-thread kernel) or 2 (512-thread register kernel)");
   g_kl_variant = variant;
   return CC_OK;
 }
@@ -1021,17 +1017,19 @@ int cc_softmax_kl_fwd_bwd_metrics(const float* z, int64_t ldz, const float* targ
     if (rows == 0) return CC_OK;
     const size_t smem = size_t(num_cards) * 8;
     const int grid = rows < sm_count() ? rows : sm_count();
-    const bool fits_regs = (ncols_pad >> 2) <= (KLR_ITERS + 1) * KLR_THREADS && (num_cards >> 2) <= KLR_ITERS * KLR_THREADS;
-    if (fits_regs && g_kl_variant != 1) {
-#define CC_KL_REGS(FAST_, RT_)                                                                                        \
+    auto fits = [&](int threads, int iters) { return (ncols_pad >> 2) <= (iters + 1) * threads && (num_cards >> 2) <= iters * threads; };
+    const bool fits768 = fits(768, 7) && g_kl_variant != 2, fits512 = fits(512, 11);
+    if ((fits768 || fits512) && g_kl_variant != 1) {
+#define CC_KL_REGS(FAST_, RT_, THREADS_, ITERS_)                                                                      \
       do {                                                                                                            \
-        CC_CHECK_CUDA(cudaFuncSetAttribute(softmax_kl_regs_kernel<FAST_, KLR_ITERS>,                                  \
+        CC_CHECK_CUDA(cudaFuncSetAttribute(softmax_kl_regs_kernel<FAST_, THREADS_, ITERS_>,                            \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
-        softmax_kl_regs_kernel<FAST_, KLR_ITERS><<<grid, KLR_THREADS, smem, st>>>(                                    \
+        softmax_kl_regs_kernel<FAST_, THREADS_, ITERS_><<<grid, THREADS_, smem, st>>>(                                 \
             z, ldz, target, ldt, target_rows, rows, num_cards, ncols_pad, float(grad_scale), dz, lddz, row_loss, RT_,  \
             dbias, dz16, lddz_bf16, tlogt, target_argmax, row_hit);                                                   \
       } while (0)
-      if (round_tf32) CC_KL_REGS(true, dz16 ? 0 : 1); else CC_KL_REGS(false, 0);
+      if (fits768) { if (round_tf32) CC_KL_REGS(true, dz16 ? 0 : 1, 768, 7); else CC_KL_REGS(false, 0, 768, 7); }
+      else         { if (round_tf32) CC_KL_REGS(true, dz16 ? 0 : 1, 512, 11); else CC_KL_REGS(false, 0, 512, 11); }
 #undef CC_KL_REGS
     } else if (round_tf32) {
       CC_CHECK_CUDA(cudaFuncSetAttribute(softmax_kl_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

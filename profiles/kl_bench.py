@@ -28,7 +28,9 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 reps = int(os.environ.get("KL_REPS", 10))
 rl = torch.zeros(R, dtype=torch.float64, device=dev)
 db = torch.zeros(C, device=dev)
-for variant in (0, 1):
+NAMES = {0: "softmax_kl_regs_kernel (auto: 768 threads x 7 slots when the row fits, else 512 x 11)",
+         2: "softmax_kl_regs_kernel (512 threads x 11 slots)", 1: "softmax_kl_persistent_kernel (1024 threads)"}
+for variant in (0, 2, 1):
     call("cc_softmax_kl_set_variant", variant)
     times = []
     for it in range(reps + 1):
@@ -44,8 +46,7 @@ for variant in (0, 1):
             times.append(e0.elapsed_time(e1))
     ms = sorted(times)[len(times) // 2]
     gb = R * 3.0 * 4 * C / 1e9
-    print(json.dumps({"kernel": "softmax_kl_regs_kernel (512 threads, targets + column sums in registers)" if variant == 0
-                      else "softmax_kl_persistent_kernel (1024 threads)", "rows": R, "C": C, "ms": ms, "min_ms": min(times),
+    print(json.dumps({"kernel": NAMES[variant], "rows": R, "C": C, "ms": ms, "min_ms": min(times),
                       "algorithmic_GB": gb, "GBps": gb / ms * 1e3,
                       "frac_of_hbm_peak": gb / ms * 1e3 / peaks.get("hbm_gbs", 6546.9), "kl_mean": float(rl.sum().item() / R)}))
 call("cc_softmax_kl_set_variant", 0)
