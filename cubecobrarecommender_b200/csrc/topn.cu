@@ -534,10 +534,18 @@ __device__ __forceinline__ void rs_rank_partial(const unsigned long long* keys, 
 
 // a bound on the RAW value such that no element whose key is >= thr fails `pass`: the threshold's own score, or --
 // fused sigmoid -- its logit.  The logit is evaluated in float32 (one thread computes it while the CTA waits, and a
-// double-precision log costs that thread several hundred cycles): the probability is first moved 2e-6 relative to the
-// safe side (30 float32 ulps: covers the few-ulp error of sigmoid_f32 and keeps 1 - p >= 2e-6, so that the rounding of
-// p costs at most 3% of 1 - p, i.e. 0.03 in the logit) and the result another 0.08.  A looser bound only lets a few
-// more elements into the survivor buffer; it never loses one (checked densely against float32 sigmoid on the host).
+// double-precision log costs that thread several hundred cycles).  The probability is first moved 2e-6 relative to the
+// safe side (16-33 float32 ulps: covers the <= 3 ulp error of sigmoid_f32 = 1 / (1 + expf(-z)) with IEEE division, and
+// keeps 1 - p >= 2e-6); the float32 logit of the moved probability is then moved by a bound on its own evaluation error:
+// 1e-5 (1 + |L|) for the quotient and logf (~80 ulps of L) plus 2.5e-7 / (1 - p) for the rounding of p next to 1 (half
+// an ulp of p is 3e-8 of the 1 - p it is subtracted from).  A constant slack of 0.08 (round 1) was safe but let EVERY
+// element of a row whose logits lie within 0.08 of each other (an untrained model) into the survivor buffer, sending
+// the cube through the overflow path; the slack here is 1e-5 for logits near 0 and grows to 0.125 only where the sigmoid
+// saturates.  A looser bound only lets a few more elements into the survivor buffer; it never loses one (checked densely
+// against float32 sigmoid on the host, tests/test_rowselect_model.py).
+__device__ __forceinline__ float rs_logit_slack(float logit, float one_minus_p) {
+  return 1e-5f * (1.f + fabsf(logit)) + 2.5e-7f / one_minus_p;
+}
 template <bool SIGMOID>
 __device__ __forceinline__ float rs_raw_bound(unsigned long long thr, int descending) {
   if (thr == 0ull) return descending ? -INFINITY : INFINITY;
@@ -547,10 +555,14 @@ __device__ __forceinline__ float rs_raw_bound(unsigned long long thr, int descen
   if (!SIGMOID) return pthr;
   if (descending) {
     const float pm = pthr * (1.f - 2e-6f) - 1e-37f;
-    return pm <= 0.f ? -INFINITY : logf(pm / (1.f - pm)) - 0.08f;
+    if (pm <= 0.f) return -INFINITY;
+    const float l = logf(pm / (1.f - pm));
+    return l - rs_logit_slack(l, 1.f - pm);
   }
   const float pp = pthr * (1.f + 2e-6f) + 1e-37f;
-  return pp >= 1.f ? INFINITY : logf(pp / (1.f - pp)) + 0.08f;
+  if (pp >= 1.f) return INFINITY;
+  const float l = logf(pp / (1.f - pp));
+  return l + rs_logit_slack(l, 1.f - pp);
 }
 
 // The 128 merged leaders are ranked on 32-bit stand-ins: the score word of the key with its 7 low bits replaced by the

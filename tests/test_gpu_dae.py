@@ -400,9 +400,10 @@ def test_train_steps_match_oracle(r, precision, monkeypatch):
 def test_train_steps_match_oracle_first_layer_on_tensor_cores(precision):
     """The default in the tensor-core modes: the main rows' first layer as a dense x W1 GEMM (W1 enters rounded to tf32 /
     bf16).  Same loss bar; on THIS small problem (cubes of 10-60 cards: no averaging over hundreds of products) the
-    first-step gradients are held to 4e-2 of their max-norm -- at the BASELINE shape the tf32 bar stays 1e-2
+    first-step gradients are held to 4e-2 (tf32) / 1e-1 (bf16: W1 itself enters with 2^-9 relative error; measured 8e-2
+    on encoder_e2/kernel) of their max-norm -- at the BASELINE shape the bars stay 1e-2 / 5e-2
     (tests/test_gpu_baseline_shapes.py)."""
-    eng = _train_steps_vs_oracle(48, precision, grad_tol=4e-2)
+    eng = _train_steps_vs_oracle(48, precision, grad_tol={"tf32": 4e-2, "bf16": 1e-1}[precision])
     assert eng.first_layer_tc
 
 

@@ -244,6 +244,20 @@ def test_topn_fused_sigmoid_equals_sigmoid_then_select():
         b = G.topn_masked(probs, mp, mi, n, only_listed=only_listed, descending=desc)
         for x, y in zip(a, b):
             assert torch.equal(x, y), (only_listed, desc)
+    # an untrained model: every logit of a row within a few hundredths of the others (and of zero, of +-9, of 15, where
+    # the sigmoid is steep / flat) -- the regime in which the float32 logit bound of the row select is tightest
+    for centre, spread in ((0.0, 0.03), (-9.0, 0.02), (9.0, 0.05), (15.5, 0.5), (0.0, 1e-4)):
+        z3 = (centre + rng.standard_normal((batch, c)) * spread).astype(np.float32)
+        logits3 = torch.from_numpy(z3).cuda()
+        call("cc_sigmoid_f32", ptr(logits3), ptr(probs), logits3.numel(), stream_ptr())
+        padded = torch.zeros((batch, c + 3), device="cuda")      # row stride % 4 == 0: the CTA-per-cube row select
+        padded[:, :c] = logits3
+        for desc in (True, False):
+            b = G.topn_masked(probs, mp, mi, n, descending=desc)
+            for src in (logits3, padded[:, :c]):                 # (stride 3001: the warp-per-cube streaming select)
+                a = G.topn_masked(src, mp, mi, n, sigmoid=True, descending=desc)
+                for x, y in zip(a, b):
+                    assert torch.equal(x, y), (centre, spread, desc, src.stride(0))
 
 
 def _algo(a):

@@ -63,16 +63,18 @@ def _sigmoid_f32(z):
 
 def _raw_bound_sigmoid(p, descending):
     """rs_raw_bound<SIGMOID=true> of csrc/topn.cu in float32 arithmetic: the logit of the threshold probability,
-    moved 2e-6 relative in probability and 0.08 in the logit to the safe side."""
+    moved 2e-6 relative in probability and 1e-5 (1 + |L|) + 2.5e-7 / (1 - p) in the logit to the safe side."""
     f = np.float32
     p = p.astype(f)
     with np.errstate(all="ignore"):
         if descending:
             pm = (p * f(1 - 2e-6)).astype(f) - f(1e-37)
-            zb = np.log((pm / (f(1) - pm)).astype(f)).astype(f) - f(0.08)
+            lg = np.log((pm / (f(1) - pm)).astype(f)).astype(f)
+            zb = (lg - (f(1e-5) * (f(1) + np.abs(lg)) + f(2.5e-7) / (f(1) - pm)).astype(f)).astype(f)
             return np.where(pm <= 0, -np.inf, zb).astype(f)
         pp = (p * f(1 + 2e-6)).astype(f) + f(1e-37)
-        zb = np.log((pp / (f(1) - pp)).astype(f)).astype(f) + f(0.08)
+        lg = np.log((pp / (f(1) - pp)).astype(f)).astype(f)
+        zb = (lg + (f(1e-5) * (f(1) + np.abs(lg)) + f(2.5e-7) / (f(1) - pp)).astype(f)).astype(f)
         return np.where(pp >= 1, np.inf, zb).astype(f)
 
 
@@ -82,6 +84,7 @@ def test_fused_sigmoid_logit_bound_never_rejects_a_qualifying_element():
     threshold probability passes the bound -- including the plateaus where the sigmoid saturates to exactly 1.0 / 0.0."""
     rng = np.random.default_rng(0)
     z = np.concatenate([rng.uniform(-110, 20, 1_500_000), rng.uniform(10, 18, 500_000), rng.uniform(-20, -5, 500_000),
+                        rng.uniform(-1, 1, 1_000_000), rng.uniform(-0.05, 0.05, 500_000), rng.uniform(3, 12, 500_000),
                         np.array([-np.inf, -104.0, -88.0, 0.0, 16.0, 16.7, 17.0, 30.0, np.inf])]).astype(np.float32)
     order = np.argsort(z, kind="stable")
     zs, ps = z[order], _sigmoid_f32(z[order])
