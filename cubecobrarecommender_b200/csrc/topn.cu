@@ -585,18 +585,20 @@ __device__ __forceinline__ void rs_rank32_partial(const uint32_t* a, int* rk, in
 // PROF: thread 0 accumulates clock64() deltas per phase and writes them to prof[blockIdx.x][RS_PROF_SLOTS] (diagnostic
 // instantiation behind cc_topn_rowselect_profile; the product instantiations compile the stamps out)
 //
-// REGS (cc_topn_set_algo(4); opt-in, for rows that fit RS_GROUPS float4 per thread): the ncu source
-// view of the kernel without it (profiles/r02/topn_rowselect_stalls.txt) shows where a cube's ~14 000 cycles go -- 3% waiting
-// for the row (HBM), 32% in sweep 2 (branch-resolve and shared-memory-atomic stalls of the diverged push path), 25% at
-// barriers behind the slowest warp of a sweep.  REGS keeps the per-group maxima of sweep 1 in registers (11 floats), so
-// sweep 2 re-reads NOTHING from shared memory: it is 11 register compares and warp votes per thread; only a group that
-// holds a survivor is fetched again.  Survivors are appended by warp-wide ballots into the warp's OWN 64-slot segment
-// of the buffer (position = warp-uniform counter + popc of the lower lanes' votes): no atomics, no divergence, every warp
-// does the same work, and the barrier behind the sweep waits for nobody.  A warp whose segment overflows (adversarial
-// rows) sends the cube down the sweep-2 path of the kernel without REGS, which keeps its own overflow handling.
+// REGS (cc_topn_set_algo(4); for rows that fit RS_GROUPS float4 per thread): the ncu source view of the kernel without
+// it (profiles/r02/topn_rowselect_stalls.txt) shows where a cube's ~14 000 cycles go -- 3% waiting for the row (HBM), 32%
+// in sweep 2 (branch-resolve and shared-memory-atomic stalls of the diverged push path, entered anew for every float4
+// group that holds a survivor), 25% at barriers behind the slowest warp of a sweep.  REGS keeps the per-group extremes
+// of sweep 1 in registers (11 floats), so sweep 2 re-reads NOTHING from shared memory: it is 11 predicated register
+// compares per thread that leave a bit mask of the groups to look at again.  The ~70 threads of 512 whose mask is not
+// empty then enter ONE diverged block per warp (fetch the group, append each survivor already keyed -- sigmoid
+// included -- with one shared-memory atomic), instead of one excursion per group.  Both counting ranks (the 128 leaders,
+// the ~70 survivors) are summed over four NEIGHBOURING lanes with shuffles: no rank array, no atomics, and the thread
+// that holds a rank acts on it directly -- four barriers per cube instead of nine.  The survivor counter alternates
+// between two words so that its reset needs no barrier of its own.  More than RS_CAP survivors (adversarial rows) and
+// the only-listed mode take the path of the kernel without REGS, which keeps its own overflow handling.
 constexpr int RS_PROF_SLOTS = 10;
 constexpr int RS_GROUPS = 11;                      // float4 groups per thread held in registers: C <= 4 * 11 * 512 = 22 528
-constexpr int RS_SEG = RS_CAP / (RS_THREADS / 32); // 64 survivor slots per warp
 template <bool SIGMOID, bool DESC, bool PROF = false, bool REGS = false>
 __global__ void __launch_bounds__(RS_THREADS, 2)
 topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_cards, int32_t batch,
@@ -618,7 +620,7 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
   __shared__ unsigned long long s_T;
   __shared__ float s_zb;
   __shared__ int s_cnt;
-  __shared__ int s_wc[RS_THREADS / 32];                     // REGS: survivors per warp segment
+  __shared__ int s_cnt2[2];                                 // REGS: the survivor counter of even / odd cubes
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int cr = (num_cards + 3) & ~3;                      // row length in shared memory (<= ld: ld % 4 == 0)
   const int cr4 = cr >> 2;
@@ -628,8 +630,7 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + size_t(nbuf) * row_bytes);   // RS_CAP
   uint32_t* lead32 = reinterpret_cast<uint32_t*>(keys);            // the leaders' stand-ins live here before sweep 2
   int* rk = reinterpret_cast<int*>(keys + RS_CAP);                                                        // RS_CAP, zero between uses
-  unsigned long long* keys2 = reinterpret_cast<unsigned long long*>(rk + RS_CAP);                         // RS_CAP (REGS: the dense keys)
-  uint32_t* bm = reinterpret_cast<uint32_t*>(keys2 + RS_CAP);                                             // words
+  uint32_t* bm = reinterpret_cast<uint32_t*>(rk + RS_CAP);                                                // words
   constexpr float WORST = DESC ? -INFINITY : INFINITY;
 
   auto issue = [&](int cube, int b) {                       // one thread: the whole row on barrier b
@@ -647,7 +648,7 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
     rs_mbar_init(&bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    s_cnt = 0; s_T = 0ull; s_zb = WORST;
+    s_cnt = 0; s_T = 0ull; s_zb = WORST; s_cnt2[0] = 0; s_cnt2[1] = 0;
   }
   for (int i = tid; i < RS_CAP; i += RS_THREADS) rk[i] = 0;
   __syncthreads();
@@ -755,81 +756,96 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
         const unsigned long long t = uw > 0x007fffffu ? (unsigned long long)uw << 32 : 0ull;
         s_T = t; s_zb = rs_raw_bound<SIGMOID>(t, DESC);
       };
-      rs_rank32_partial(lead32, rk, tid);
-      __syncthreads();
-      if (tid < RS_LEADERS) {
-        if (rk[tid] == n - 1) publish(lead32[tid]);
-        rk[tid] = 0;
+      if constexpr (REGS) {
+        // leader tid / 4 against quarter tid % 4 of the stand-ins; the four partial counts meet by shuffles
+        const uint32_t mine = lead32[tid >> 2];
+        const uint4* a4 = reinterpret_cast<const uint4*>(lead32) + (tid & 3) * (RS_LEADERS / 16);
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < RS_LEADERS / 16; ++j) {
+          const uint4 w = a4[j];
+          c += (w.x > mine) + (w.y > mine) + (w.z > mine) + (w.w > mine);
+        }
+        c += __shfl_xor_sync(0xffffffffu, c, 1);
+        c += __shfl_xor_sync(0xffffffffu, c, 2);
+        if ((tid & 3) == 0 && c == n - 1) publish(mine);
+        if (tid == 0) s_cnt2[(it + 1) & 1] = 0;             // the next cube's counter (last read behind the previous cube's barriers)
+      } else {
+        rs_rank32_partial(lead32, rk, tid);
+        __syncthreads();
+        if (tid < RS_LEADERS) {
+          if (rk[tid] == n - 1) publish(lead32[tid]);
+          rk[tid] = 0;
+        }
       }
       __syncthreads();
       stamp(4);                                             // 4: leaders: keys, merge, ranking, threshold
     }
 
     int m = 0;
-    bool ranked_from_regs = false;
     if constexpr (REGS) {
       if (!mode_only_listed) {
-        // sweep 2 over registers: a group is fetched again only if its extreme passes the bound; the warp appends its
-        // survivors to its own segment with ballots (see the kernel's header comment)
+        // sweep 2 over registers: which of this thread's groups hold an element at or above the bound
         const float zb = s_zb;
-        unsigned long long* seg = keys + wid * RS_SEG;
-        int wcnt = 0;                                       // warp-uniform
+        int* const cnt = &s_cnt2[it & 1];
+        uint32_t hits = 0u;
 #pragma unroll
-        for (int j = 0; j < RS_GROUPS; ++j) {
-          const bool hit = pass(gmax[j], zb);               // (lanes beyond the row hold the worst value: no bound passes
-          const uint32_t any = __ballot_sync(0xffffffffu, hit);   //  unless zb itself is the worst value, handled below)
-          if (any) {                                        // warp-uniform
-            const int v = tid + j * RS_THREADS;
-            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-            const bool live = hit && v < cr4;
-            if (live) q = row4[v];
-            const bool px = live && pass(q.x, zb), py = live && pass(q.y, zb), pz = live && pass(q.z, zb), pw = live && pass(q.w, zb);
-            const uint32_t m0 = __ballot_sync(0xffffffffu, px), m1 = __ballot_sync(0xffffffffu, py);
-            const uint32_t m2 = __ballot_sync(0xffffffffu, pz), m3 = __ballot_sync(0xffffffffu, pw);
-            int pos = wcnt + __popc(m0 & lt_mask) + __popc(m1 & lt_mask) + __popc(m2 & lt_mask) + __popc(m3 & lt_mask);
-            auto put = [&](bool p_, float x, int e) {
-              if (p_) {
-                if (pos < RS_SEG) seg[pos] = ((unsigned long long)__float_as_uint(x) << 32) | (unsigned long long)(uint32_t)e;
-                ++pos;
+        for (int j = 0; j < RS_GROUPS; ++j) hits |= pass(gmax[j], zb) ? (1u << j) : 0u;
+        while (hits) {                                      // ~1 thread in 7 enters, nearly always for one group
+          const int j = __ffs(hits) - 1;
+          hits &= hits - 1u;
+          const int v = tid + j * RS_THREADS;
+          if (v < cr4) {                                    // (a bound of -inf / +inf also passes the groups beyond the row)
+            const float4 q = row4[v];
+            const float x[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (pass(x[e], zb)) {
+                const int slot = atomicAdd(cnt, 1);
+                if (slot < RS_CAP) keys[slot] = make_key<float>(SIGMOID ? sigmoid_f32(x[e]) : x[e], (uint32_t)(4 * v + e), DESC);
               }
-            };
-            put(px, q.x, 4 * v); put(py, q.y, 4 * v + 1); put(pz, q.z, 4 * v + 2); put(pw, q.w, 4 * v + 3);
-            wcnt += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+            }
           }
         }
-        if (lane == 0) s_wc[wid] = wcnt;
         __syncthreads();
-        stamp(5);                                           // 5: sweep 2 (+ barrier)
-        // densify: segment slot -> position = survivors of the lower warps + slot, raw -> composite key on the way,
-        // into a second buffer (no read-before-write hazard, hence no barrier in between).  Every warp scans the 16
-        // counts itself; every thread owns two slots (one in the lower eight segments, one in the upper eight).
-        const int c = lane < RS_THREADS / 32 ? s_wc[lane] : 0;
-        const bool over = __any_sync(0xffffffffu, c > RS_SEG);
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < RS_THREADS / 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        const int total = __shfl_sync(0xffffffffu, incl, RS_THREADS / 32 - 1);
-        const int w_lo = tid >> 6, w_hi = 8 + (tid >> 6);
-        const int base_lo = __shfl_sync(0xffffffffu, incl - c, w_lo), base_hi = __shfl_sync(0xffffffffu, incl - c, w_hi);
-        const int cnt_lo = __shfl_sync(0xffffffffu, c, w_lo), cnt_hi = __shfl_sync(0xffffffffu, c, w_hi);
-        if (!over) {                                        // CTA-uniform (every warp scanned the same counts)
-          // (the raw entries are moved first and keyed afterwards from the dense array: keying -- a sigmoid per entry --
-          // where they lie would run in all 16 warps with a few active lanes each, measured 2 400 cycles per cube)
-          const int sl = tid & (RS_SEG - 1);
-          if (sl < cnt_lo) keys2[base_lo + sl] = keys[w_lo * RS_SEG + sl];
-          if (sl < cnt_hi) keys2[base_hi + sl] = keys[w_hi * RS_SEG + sl];
-          __syncthreads();
-          m = total;
-          for (int i = tid; i < m; i += RS_THREADS) keys2[i] = raw_to_key(keys2[i]);
-          __syncthreads();
-          stamp(6);                                         // 6: survivors -> keys (+ barriers)
-          ranked_from_regs = true;
+        m = *cnt;
+        stamp(5);                                           // 5: sweep 2, survivors keyed and appended (+ barrier)
+        if (m <= RS_CAP) {
+          // the row is not needed any more; the last warp has no ranking work unless m > 120
+          if (tid == RS_THREADS - 32 && cube + nbuf * stride < batch) issue(cube + nbuf * stride, b);
+          // survivor base + tid / 4 against quarter tid % 4 of the keys; the thread that holds the rank writes the result
+          const int chunk = (m + 3) >> 2;
+          const int j0 = (tid & 3) * chunk, j1 = min(m, j0 + chunk);
+          for (int base = 0; base < m; base += RS_LEADERS) {
+            const int i = base + (tid >> 2);
+            const unsigned long long mine = i < m ? keys[i] : ~0ull;
+            int c = 0;
+#pragma unroll 4
+            for (int j = j0; j < j1; ++j) c += (keys[j] > mine) ? 1 : 0;
+            c += __shfl_xor_sync(0xffffffffu, c, 1);
+            c += __shfl_xor_sync(0xffffffffu, c, 2);
+            if (i < m && (tid & 3) == 0 && c < n) {
+              uint32_t t = (uint32_t)(mine & 0xffffffffu), u = (uint32_t)(mine >> 32);
+              if (!DESC) { t = ~t; u = ~u; }
+              out_ids[int64_t(cube) * n + c] = (int32_t)t;
+              if (out_vals) out_vals[int64_t(cube) * n + c] = __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
+            }
+          }
+          stamp(7);                                         // 7: issue of the next row + final ranking + write-out
+          for (int i = m + tid; i < n; i += RS_THREADS) {
+            out_ids[int64_t(cube) * n + i] = -1;
+            if (out_vals) out_vals[int64_t(cube) * n + i] = 0.f;
+          }
+          if (tid == 0 && out_count) out_count[cube] = min(n, m);
+          mb = mb1; me = me1; c0 = nc0; c1 = nc1; mb1 = mb2; me1 = me2;
+          stamp(8);
+          continue;
         }
       }
     }
     // sweep 2 over the shared row (the kernel without REGS; with REGS: only-listed mode and cubes whose survivors
-    // overflowed a warp segment), repeated with a raised threshold if more than RS_CAP elements survive
-    for (int round = 0; !ranked_from_regs; ++round) {
+    // number more than RS_CAP), repeated with a raised threshold if more than RS_CAP elements survive
+    for (int round = 0;; ++round) {
       if (mode_only_listed) {
         for (int w = tid; w < words; w += RS_THREADS) bm[w] = 0u;
         __syncthreads();
@@ -885,8 +901,7 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
       out_ids[int64_t(cube) * n + r] = (int32_t)t;
       if (out_vals) out_vals[int64_t(cube) * n + r] = __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
     };
-    const unsigned long long* kfin = ranked_from_regs ? keys2 : keys;
-    rs_rank_partial(kfin, m, rk, tid);
+    rs_rank_partial(keys, m, rk, tid);
     __syncthreads();
     stamp(7);                                               // 7: issue of the next row + final ranking (+ barrier)
     // every thread has read s_cnt, s_T and s_zb by now; their next use lies behind the next cube's barriers
@@ -894,7 +909,7 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
     for (int i = tid; i < m; i += RS_THREADS) {
       const int r = rk[i];
       rk[i] = 0;
-      if (r < n) write_ranked(kfin[i], r);
+      if (r < n) write_ranked(keys[i], r);
     }
     for (int i = m + tid; i < n; i += RS_THREADS) {
       out_ids[int64_t(cube) * n + i] = -1;
@@ -914,7 +929,7 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
 
 static size_t rowselect_smem_bytes(int32_t num_cards, int nbuf) {
   const size_t cr = (size_t(num_cards) + 3) & ~size_t(3);
-  return size_t(nbuf) * cr * 4 + size_t(RS_CAP) * 8 + size_t(RS_CAP) * 4 + size_t(RS_CAP) * 8 + size_t((num_cards + 31) / 32) * 4;
+  return size_t(nbuf) * cr * 4 + size_t(RS_CAP) * 8 + size_t(RS_CAP) * 4 + size_t((num_cards + 31) / 32) * 4;
 }
 
 // rows must be 16-byte aligned and a whole number of 16-byte units (bulk copies), and two of them must fit in shared memory
