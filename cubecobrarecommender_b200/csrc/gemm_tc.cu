@@ -78,6 +78,11 @@ struct Params {
   // K range and stored; the LAST sk_tiles tiles are cut along K into num_units contiguous spans of k-blocks, one per
   // unit, and every span is TMA-reduce-added into the (pre-zeroed) tile.  sk_tiles = 0: off.
   int dp_tiles, sk_tiles;
+  // tile order of the plain GEMM: 0 = tile row fastest (tile = mt + m_tiles * nt), 1 = tile column fastest.  The tiles
+  // that run at the same time should share operand panels: with many tile rows and only 2-4 tile columns (dW1 =
+  // x^T g1: 82 x 2) row-fastest order puts the two tiles that read the SAME 4.2 MB panel of x a whole wave apart, and
+  // the panel comes from DRAM twice (ncu: 702 MB read for 353 MB of operands); column-fastest makes them neighbours.
+  int nt_fastest;
   // EPI_COUNT: C = A A^T is symmetric -> only tiles with nt >= mt are computed (square 256 x 256 pair tiles) and every
   // off-diagonal tile is also written transposed
   int symmetric;
@@ -272,8 +277,13 @@ __device__ __forceinline__ void decode_tile(const Params& p, int tile, int& mt, 
     }
     ks = 0;
   } else {
-    mt = tile % p.m_tiles;
-    nt = (tile / p.m_tiles) % p.n_tiles;
+    if (p.nt_fastest) {
+      nt = tile % p.n_tiles;
+      mt = (tile / p.n_tiles) % p.m_tiles;
+    } else {
+      mt = tile % p.m_tiles;
+      nt = (tile / p.m_tiles) % p.n_tiles;
+    }
     ks = tile / (p.m_tiles * p.n_tiles);
   }
 }
@@ -872,6 +882,10 @@ static int g_pair_mode = -1;
 // leaves a ragged wave (cc_gemm_tc_set_stream_k; tests and A/B measurements)
 static int g_stream_k = getenv("CC_GEMM_STREAM_K") ? atoi(getenv("CC_GEMM_STREAM_K")) : -1;
 
+// -1 = column-fastest tile order where it saves operand re-reads (see Params::nt_fastest), 0 = always row-fastest
+// (CC_GEMM_TILE_ORDER=0; A/B measurements)
+static int g_tile_order = getenv("CC_GEMM_TILE_ORDER") ? atoi(getenv("CC_GEMM_TILE_ORDER")) : -1;
+
 // the waves model of plan_eff for the hybrid stream-K schedule of (bn, ctas): full data-parallel waves, then every
 // unit's span of the stream-K k-blocks (two partial tiles' worth of prologue/epilogue)
 static double plan_eff_sk(int m, int n, int kblocks, int bn, int sms, int ctas) {
@@ -964,10 +978,27 @@ static int launch_bn(const Problem& pr, Params p, cudaStream_t st) {
     p.sk_tiles = 0;
     if (!p.symmetric && !p.sched && p.split_k == 1) p.sk_tiles = stream_k_tiles(p.m_tiles, p.n_tiles, p.total_k_blocks, max_units);
   }
+  // column-fastest tile order (see Params): few tile columns, many tile rows, at least one full data-parallel wave
+  p.nt_fastest = (!p.symmetric && g_tile_order != 0 && p.split_k == 1 && p.n_tiles < p.m_tiles && p.n_tiles <= 4 &&
+                  p.m_tiles * p.n_tiles - (p.sk_tiles > 0 ? p.sk_tiles : 0) >= max_units) ? 1 : 0;
   p.dp_tiles = 0;
   if (p.sk_tiles > 0) {
     p.dp_tiles = p.m_tiles * p.n_tiles - p.sk_tiles;
-    if (!p.reduce_add) {
+    if (!p.reduce_add && p.nt_fastest) {
+      // the stream-K tiles are the last sk_tiles of the column-fastest order: the right part of tile row mt0 (from tile
+      // column nt0 on) and every row after it
+      const int mt0 = p.dp_tiles / p.n_tiles, nt0 = p.dp_tiles % p.n_tiles;
+      const long long row0 = (long long)mt0 * BM * CTAS, col0 = (long long)nt0 * BN;
+      long long rowf = row0;                                 // first FULL stream-K row
+      if (nt0 > 0 && row0 < pr.m) {
+        const long long h = (row0 + BM * CTAS < pr.m ? BM * CTAS : pr.m - row0);
+        if (col0 < p.n_store)
+          CC_CHECK_CUDA(cudaMemset2DAsync(pr.c + row0 * pr.ldc + col0, size_t(pr.ldc) * 4, 0, size_t(p.n_store - col0) * 4, size_t(h), st));
+        rowf = row0 + BM * CTAS;
+      }
+      if (rowf < pr.m)
+        CC_CHECK_CUDA(cudaMemset2DAsync(pr.c + rowf * pr.ldc, size_t(pr.ldc) * 4, 0, size_t(p.n_store) * 4, size_t(pr.m - rowf), st));
+    } else if (!p.reduce_add) {
       // the stream-K tiles are the last sk_tiles of the row-fastest tile order: the lower part of tile column nt0 (from
       // tile row mt0 on) and every column after it.  They are zeroed (two 2-D memsets); every span is reduce-added.
       const int nt0 = p.dp_tiles / p.m_tiles, mt0 = p.dp_tiles % p.m_tiles;

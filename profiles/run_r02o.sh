@@ -1,0 +1,15 @@
+#!/bin/bash
+# Round 2, call o: full suite; ncu source-level capture of the register-form row select; GEMM tile-order A/B.
+OUT=gpurun_out/r02o; mkdir -p $OUT
+timeout 700 python -m pytest tests -m gpu -x -q --timeout=200 > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 $OUT/pytest_gpu.log | cut -c1-300
+TOPN_REPS=1 TOPN_BATCHES=4096 timeout 300 ncu --set full --import-source on --clock-control none \
+    --kernel-name-base mangled -k regex:topn_rowselect_kernelILb1ELb1ELb0ELb1E -c 2 -f -o $OUT/topn_regs python profiles/topn_bench.py > $OUT/topn_ncu.log 2>&1
+echo "ncu rc=$?"
+if [ -f $OUT/topn_regs.ncu-rep ]; then
+  ncu -i $OUT/topn_regs.ncu-rep --page source --csv --print-source cuda,sass --kernel-id :::2 > $OUT/topn_regs_source.csv 2>/dev/null
+  ncu -i $OUT/topn_regs.ncu-rep --page source --csv --print-source sass --kernel-id :::2 > $OUT/topn_regs_sass.csv 2>/dev/null
+  ncu -i $OUT/topn_regs.ncu-rep --page raw --csv > $OUT/topn_regs_raw.csv 2>/dev/null
+  python profiles/ncu_source_hotspots.py $OUT/topn_regs_source.csv 45 > $OUT/topn_regs_stalls.txt; head -50 $OUT/topn_regs_stalls.txt | cut -c1-230
+fi
+bash profiles/run_ab.sh r02o "CC_GEMM_TILE_ORDER=0"
+ls -la $OUT
