@@ -758,12 +758,15 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
       };
       if constexpr (REGS) {
         // leader tid / 4 against quarter tid % 4 of the stand-ins; the four partial counts meet by shuffles
+        // (the quarters are 128 bytes apart, i.e. in the same banks: each starts two 16-byte words further into its
+        // quarter, so the four addresses of an 8-lane load phase fall into different bank groups)
         const uint32_t mine = lead32[tid >> 2];
-        const uint4* a4 = reinterpret_cast<const uint4*>(lead32) + (tid & 3) * (RS_LEADERS / 16);
+        const int q = tid & 3;
+        const uint4* a4 = reinterpret_cast<const uint4*>(lead32) + q * (RS_LEADERS / 16);
         int c = 0;
 #pragma unroll
         for (int j = 0; j < RS_LEADERS / 16; ++j) {
-          const uint4 w = a4[j];
+          const uint4 w = a4[(j + 2 * q) & (RS_LEADERS / 16 - 1)];
           c += (w.x > mine) + (w.y > mine) + (w.z > mine) + (w.w > mine);
         }
         c += __shfl_xor_sync(0xffffffffu, c, 1);
@@ -797,31 +800,42 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
           const int v = tid + j * RS_THREADS;
           if (v < cr4) {                                    // (a bound of -inf / +inf also passes the groups beyond the row)
             const float4 q = row4[v];
-            const float x[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (pass(x[e], zb)) {
-                const int slot = atomicAdd(cnt, 1);
-                if (slot < RS_CAP) keys[slot] = make_key<float>(SIGMOID ? sigmoid_f32(x[e]) : x[e], (uint32_t)(4 * v + e), DESC);
-              }
+            uint32_t em = (pass(q.x, zb) ? 1u : 0u) | (pass(q.y, zb) ? 2u : 0u) | (pass(q.z, zb) ? 4u : 0u) | (pass(q.w, zb) ? 8u : 0u);
+            while (em) {                                    // one instance of the push code, nearly always run once
+              const int e = __ffs(em) - 1;
+              em &= em - 1u;
+              const float x = e == 0 ? q.x : e == 1 ? q.y : e == 2 ? q.z : q.w;
+              const int slot = atomicAdd(cnt, 1);
+              if (slot < RS_CAP) keys[slot] = ((unsigned long long)__float_as_uint(x) << 32) | (unsigned long long)(uint32_t)(4 * v + e);
             }
           }
         }
         __syncthreads();
         m = *cnt;
-        stamp(5);                                           // 5: sweep 2, survivors keyed and appended (+ barrier)
+        stamp(5);                                           // 5: sweep 2, raw survivors appended (+ barrier)
+        // raw survivors -> composite keys, one per thread (a sigmoid each: three warps' worth instead of a few lanes of all 16)
+        if (tid < min(m, RS_CAP)) keys[tid] = raw_to_key(keys[tid]);
+        if (tid + RS_THREADS < min(m, RS_CAP)) keys[tid + RS_THREADS] = raw_to_key(keys[tid + RS_THREADS]);
+        if (tid == RS_THREADS - 1 && (m & 1) && m < RS_CAP) keys[m] = 0ull;    // the final ranking reads keys two at a time
+        __syncthreads();
+        stamp(6);                                           // 6: survivors -> keys (+ barrier)
         if (m <= RS_CAP) {
           // the row is not needed any more; the last warp has no ranking work unless m > 120
           if (tid == RS_THREADS - 32 && cube + nbuf * stride < batch) issue(cube + nbuf * stride, b);
           // survivor base + tid / 4 against quarter tid % 4 of the keys; the thread that holds the rank writes the result
-          const int chunk = (m + 3) >> 2;
-          const int j0 = (tid & 3) * chunk, j1 = min(m, j0 + chunk);
+          // (quarters of an even number of keys, read two at a time; the slot behind an odd m holds a zero key)
+          const int chunk = (((m + 3) >> 2) + 1) & ~1;
+          const int j0 = (tid & 3) * chunk, j1 = min((m + 1) & ~1, j0 + chunk);
+          const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(keys);
           for (int base = 0; base < m; base += RS_LEADERS) {
             const int i = base + (tid >> 2);
             const unsigned long long mine = i < m ? keys[i] : ~0ull;
             int c = 0;
-#pragma unroll 4
-            for (int j = j0; j < j1; ++j) c += (keys[j] > mine) ? 1 : 0;
+#pragma unroll 8
+            for (int j = j0; j < j1; j += 2) {
+              const ulonglong2 w = k2[j >> 1];
+              c += ((w.x > mine) ? 1 : 0) + ((w.y > mine) ? 1 : 0);
+            }
             c += __shfl_xor_sync(0xffffffffu, c, 1);
             c += __shfl_xor_sync(0xffffffffu, c, 2);
             if (i < m && (tid & 3) == 0 && c < n) {

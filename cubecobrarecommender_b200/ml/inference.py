@@ -23,7 +23,10 @@ from .model import CC_Recommender, SparseBatch
 
 
 class MLRecommender:
-    def __init__(self, model: CC_Recommender, chunk: int = 2048):
+    def __init__(self, model: CC_Recommender, chunk: int = 8192):
+        # cubes per pass through the model.  [B200] 100 000 cubes, top-50: 4.9 M recs/s at 2048 (the host cannot enqueue
+        # 49 x 14 launches as fast as the GPU runs them), 6.8 M at 4096, 7.2-7.7 M at 8192 (0.68 GB of logits per pass);
+        # profiles/r02/ml_recommend_profile.jsonl
         self.model = model
         self.chunk = int(chunk)
 

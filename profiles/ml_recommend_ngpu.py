@@ -29,7 +29,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 full = make_cubes(K, C, cfg=4)                                              # every rank builds the same cubes
 model = M.CC_Recommender(C, device=dev, seed=0, precision="tf32")          # same seed: identical replicas
-rec = INF.MLRecommender(model, chunk=4096)
+rec = INF.MLRecommender(model, chunk=8192)
 lines = []
 # one launch measures every N in {1, 2, 4, ..., world}: for a given N only ranks < N take a shard, the others idle
 ns = [n for n in (1, 2, 4, 8, 16) if n <= world]

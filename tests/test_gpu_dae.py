@@ -272,7 +272,7 @@ def test_gemm_tcgen05_tf32_all_layouts(ta, tb, m, n, k, split, tile_n, pair_mode
                                          (1, 0, 768, 20000, 4096),     # data-parallel waves + a stream-K tail that starts
                                          (1, 1, 1032, 3000, 4104),     # mid-column; ragged M/N/K
                                          (1, 0, 21000, 512, 4096),     # dW1-like: 83 x 2 tiles in column-fastest order
-                                         (1, 0, 15300, 600, 4096)])    # column-fastest, stream-K tail starting mid-row
+                                         (1, 0, 15296, 600, 4096)])    # column-fastest, stream-K tail starting mid-row
 def test_gemm_tcgen05_hybrid_stream_k(ta, tb, m, n, k, pair, precision, pair_mode):
     """Hybrid stream-K schedule (forced on): whole tile waves data-parallel, the rest cut along K into one span per CTA
     (pair) and TMA-reduce-added into pre-zeroed tiles.  Against float64 on exactly representable operands; plain
