@@ -816,24 +816,25 @@ topn_rowselect_kernel(const float* __restrict__ scores, int64_t ld, int32_t num_
         // raw survivors -> composite keys, one per thread (a sigmoid each: three warps' worth instead of a few lanes of all 16)
         if (tid < min(m, RS_CAP)) keys[tid] = raw_to_key(keys[tid]);
         if (tid + RS_THREADS < min(m, RS_CAP)) keys[tid + RS_THREADS] = raw_to_key(keys[tid + RS_THREADS]);
-        if (tid == RS_THREADS - 1 && (m & 1) && m < RS_CAP) keys[m] = 0ull;    // the final ranking reads keys two at a time
+        // the final ranking reads four equal, even-sized quarters of the keys: zero keys (nothing ranks below them) fill
+        // the up to seven slots behind the last one (past RS_CAP they land on the zeroed rank array: harmless)
+        const int chunk = (((min(m, RS_CAP) + 3) >> 2) + 1) & ~1;
+        if (tid >= RS_THREADS - 8 && m <= RS_CAP && m + (tid - (RS_THREADS - 8)) < 4 * chunk) keys[m + (tid - (RS_THREADS - 8))] = 0ull;
         __syncthreads();
         stamp(6);                                           // 6: survivors -> keys (+ barrier)
         if (m <= RS_CAP) {
           // the row is not needed any more; the last warp has no ranking work unless m > 120
           if (tid == RS_THREADS - 32 && cube + nbuf * stride < batch) issue(cube + nbuf * stride, b);
           // survivor base + tid / 4 against quarter tid % 4 of the keys; the thread that holds the rank writes the result
-          // (quarters of an even number of keys, read two at a time; the slot behind an odd m holds a zero key)
-          const int chunk = (((m + 3) >> 2) + 1) & ~1;
-          const int j0 = (tid & 3) * chunk, j1 = min((m + 1) & ~1, j0 + chunk);
-          const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(keys);
+          // (every quarter holds `chunk` keys, read two at a time: the same trip count for every thread)
+          const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(keys) + (tid & 3) * (chunk >> 1);
           for (int base = 0; base < m; base += RS_LEADERS) {
             const int i = base + (tid >> 2);
             const unsigned long long mine = i < m ? keys[i] : ~0ull;
             int c = 0;
-#pragma unroll 8
-            for (int j = j0; j < j1; j += 2) {
-              const ulonglong2 w = k2[j >> 1];
+#pragma unroll 4
+            for (int j = 0; j < (chunk >> 1); ++j) {
+              const ulonglong2 w = k2[j];
               c += ((w.x > mine) ? 1 : 0) + ((w.y > mine) ? 1 : 0);
             }
             c += __shfl_xor_sync(0xffffffffu, c, 1);
@@ -985,8 +986,9 @@ static int rowselect_launch(int variant, const float* scores, int64_t ld, int32_
 }
 
 // float32, n <= 128: 0 = automatic (row select when the rows qualify, else the streaming select), 1 = streaming select,
-// 2 / 3 = row select, variant 0 / 1 (error if the rows do not qualify); automatic takes variant 1, the faster one
-// without REGS (the automatic choice); 4 = the REGS form (rows of up to 22 528 cards; measured no faster).  The radix-select kernel stays the general path (any n, float64).
+// 2 / 3 = row select with both sweeps over shared memory, one CTA per SM with two row buffers / two CTAs per SM (error
+// if the rows do not qualify); 4 = its register form (rows of up to 22 528 cards); automatic takes the register form when
+// the row fits and the whole row is ranked, else 3.  The radix-select kernel stays the general path (any n, float64).
 static int g_topn_algo = 0;
 static int g_topn_force_radix = 0;
 
@@ -999,10 +1001,10 @@ static int select_small_n(const float* scores, int64_t ld, int32_t num_cards, in
   const bool regs_ok = ((num_cards + 3) >> 2) <= RS_GROUPS * RS_THREADS;
   CC_REQUIRE(regs_ok || g_topn_algo != 4, "cc_topn_masked: the REGS row select holds rows of up to %d cards", 4 * RS_GROUPS * RS_THREADS);
   if (ok && g_topn_algo != 1) {
-    // automatic = 2 CTAs per SM, both sweeps over shared memory: measured 105-106 us per 4096 cubes against 108-113 us for
-    // the REGS form (profiles/r02/topn_bench_regs.jsonl) -- the kernel is bound by barrier / dependency latency, not by
-    // the instructions REGS removes
-    const int variant = g_topn_algo == 2 ? 0 : g_topn_algo == 4 ? 2 : 1;
+    // automatic = 2 CTAs per SM; the register form when the row fits its 11 float4 groups per thread and the whole row
+    // is ranked (measured 92 us per 4096 cubes against 103 us with both sweeps over shared memory,
+    // profiles/r02/topn_bench_regs_v3.jsonl); the only-listed mode never reaches the register path
+    const int variant = g_topn_algo == 2 ? 0 : g_topn_algo == 3 ? 1 : (g_topn_algo == 4 || (regs_ok && !mode_only_listed)) ? 2 : 1;
     return rowselect_launch<SIGMOID>(variant, scores, ld, num_cards, batch, mask_ptr, mask_idx,
                                      mode_only_listed, descending, n, out_ids, out_vals, out_count, st);
   }

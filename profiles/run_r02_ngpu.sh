@@ -8,7 +8,7 @@ N=${1:-8}; SMALL=$2
 OUT=gpurun_out/r02_n$N; mkdir -p $OUT
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 if [ -n "$SMALL" ]; then export SCALE_UP_CUBES=65536 SCALE_UP_CARDS=8192 RECOMMEND_CUBES=8192; fi
-timeout 300 $TR --master-port 29501 -m cubecobrarecommender_b200.dp_check --precision tf32 --steps 3 > $OUT/dp_check_tf32.json 2> $OUT/dp_check_tf32.err
+timeout 300 $TR --master-port 29501 -m cubecobrarecommender_b200.dp_check --precision tf32 --steps 3 --modes p2p_unicast,p2p_multicast,nccl,p2p_overlap > $OUT/dp_check_tf32.json 2> $OUT/dp_check_tf32.err
 echo "dp_check rc=$?"; python -c "
 import json,sys
 d=json.load(open('$OUT/dp_check_tf32.json')); print('violations', d['violations'])
@@ -19,7 +19,9 @@ if [ -z "$SMALL" ]; then
   timeout 300 $TR --master-port 29504 bench.py --gpus $N --steps 50 --warmup 5 --scaling strong --no-extras --no-cpu-baseline > $OUT/bench_strong_tf32.json 2> $OUT/bench_strong_tf32.err; echo "strong rc=$?"
   timeout 300 $TR --master-port 29505 bench.py --gpus $N --steps 50 --warmup 5 --scaling strong --precision bf16 --reg-mode full --no-extras --no-cpu-baseline > $OUT/bench_strong_bf16_full.json 2> $OUT/bench_strong_bf16_full.err; echo "bf16 full rc=$?"
   timeout 300 $TR --master-port 29506 bench.py --gpus $N --steps 50 --warmup 5 --no-extras --no-cpu-baseline > $OUT/bench_weak_tf32.json 2> $OUT/bench_weak_tf32.err; echo "weak rc=$?"
-  for f in bench_strong_tf32 bench_strong_bf16_full bench_weak_tf32; do python -c "
+  CC_DP_MODE=p2p_overlap timeout 300 $TR --master-port 29507 bench.py --gpus $N --steps 50 --warmup 5 --no-extras --no-cpu-baseline > $OUT/bench_weak_tf32_overlap.json 2> $OUT/bench_weak_tf32_overlap.err; echo "weak overlap rc=$?"
+  timeout 300 $TR --master-port 29508 bench.py --gpus $N --steps 50 --warmup 5 --precision bf16 --no-extras --no-cpu-baseline > $OUT/bench_weak_bf16.json 2> $OUT/bench_weak_bf16.err; echo "weak bf16 rc=$?"
+  for f in bench_strong_tf32 bench_strong_bf16_full bench_weak_tf32 bench_weak_tf32_overlap bench_weak_bf16; do python -c "
 import json; d=json.load(open('$OUT/$f.json')); print('$f', d['value'], d['ms_per_step'], d['config']['batch_per_gpu'], d['config']['reg_rows_per_gpu'], d['scaling'], d['dtype'])"; done
 fi
 ls $OUT

@@ -45,8 +45,8 @@ for batch in [int(x) for x in os.environ.get("TOPN_BATCHES", "2048,4096").split(
         ms = float(np.median(times))
         nbytes = batch * (4 * C + 8 * N + 4) + 4 * int(mi.numel())
         print(json.dumps({"kernel": {1: "topn_warpselect_kernel<sigmoid>", 2: "topn_rowselect_kernel<sigmoid> 1 CTA/SM, 2 row buffers",
-                                     3: "topn_rowselect_kernel<sigmoid> 2 CTAs/SM, 1 row buffer (default)",
-                                     4: "topn_rowselect_kernel<sigmoid, REGS> 2 CTAs/SM, 1 row buffer (register form: one diverged block per warp, lane-neighbour ranking)"}[algo],
+                                     3: "topn_rowselect_kernel<sigmoid> 2 CTAs/SM, 1 row buffer, both sweeps over shared memory",
+                                     4: "topn_rowselect_kernel<sigmoid, REGS> 2 CTAs/SM, 1 row buffer (register form, the default: one diverged block per warp, lane-neighbour ranking)"}[algo],
                           "batch": batch, "C": C, "ld": LD, "n": N, "ms": ms, "min_ms": float(min(times)),
                           "algorithmic_GB": nbytes / 1e9, "GBps": nbytes / ms / 1e6,
                           "frac_of_hbm_peak": nbytes / ms / 1e6 / float(peaks.get("hbm_gbs", 6546.9)),

@@ -36,6 +36,6 @@ for variant in (2, 1, 0):
     p = prof.cpu().double()
     cubes = p[:, 9].sum().item()
     per_cube = (p[:, :9].sum(0) / cubes).tolist()
-    print(json.dumps({"variant": {0: "1 CTA/SM, 2 row buffers", 1: "2 CTAs/SM, 1 row buffer", 2: "REGS form (opt-in), 2 CTAs/SM, 1 row buffer"}[variant], "grid": grid,
+    print(json.dumps({"variant": {0: "1 CTA/SM, 2 row buffers", 1: "2 CTAs/SM, 1 row buffer", 2: "register form (default), 2 CTAs/SM, 1 row buffer"}[variant], "grid": grid,
                       "batch": batch, "cycles_per_cube_total": sum(per_cube),
                       "cycles_per_cube": {k: round(v, 1) for k, v in zip(PHASES, per_cube)}}), flush=True)
