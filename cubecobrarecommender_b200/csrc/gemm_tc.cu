@@ -53,7 +53,9 @@ template <int BN, int CTAS> struct Cfg {
 };
 
 // EPI_BCE16: the fused sigmoid-BCE epilogue writing dlogits as bf16 (they feed the bf16 dW / dX GEMMs of the "bf16" mode)
-enum Epilogue : int { EPI_STORE = 0, EPI_BCE = 1, EPI_COUNT = 2, EPI_BCE16 = 3 };
+// EPI_BCE_ACC / EPI_BCE16_ACC: the same two with the Keras binary_accuracy count (four more instructions per element,
+// compiled in only when the caller asks for metrics)
+enum Epilogue : int { EPI_STORE = 0, EPI_BCE = 1, EPI_COUNT = 2, EPI_BCE16 = 3, EPI_BCE_ACC = 4, EPI_BCE16_ACC = 5 };
 // operand kinds: fp32 storage / kind::tf32, bf16 storage / kind::f16, uint8 storage / kind::i8 (int32 accumulators:
 // the co-occurrence contraction X^T X over 0/1 bytes is exact)
 enum Kind : int { KIND_TF32 = 0, KIND_BF16 = 1, KIND_U8 = 2 };
@@ -320,8 +322,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const __grid_constant__ CUtensorMap map_c, const Params p) {
   using C = Cfg<BN, CTAS>;
   constexpr bool BF16 = KIND == KIND_BF16;
-  constexpr bool IS_BCE = EPI == EPI_BCE || EPI == EPI_BCE16;
-  constexpr bool OUT16 = EPI == EPI_BCE16;        // output elements are bf16 (32 x 32 block = 64-byte rows)
+  constexpr bool IS_BCE = EPI == EPI_BCE || EPI == EPI_BCE16 || EPI == EPI_BCE_ACC || EPI == EPI_BCE16_ACC;
+  constexpr bool OUT16 = EPI == EPI_BCE16 || EPI == EPI_BCE16_ACC;   // output elements are bf16 (32 x 32 block = 64-byte rows)
+  constexpr bool WANT_ACC = EPI == EPI_BCE_ACC || EPI == EPI_BCE16_ACC;
   constexpr int BN_LOAD = BN / CTAS;             // rows of the B tile this CTA stages
   constexpr int STAGES = C::STAGES;
   constexpr int STAGE_BYTES = C::STAGE_BYTES;
@@ -616,38 +619,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
         } else if (IS_BCE) {
-          // softplus(z) - z*y and sigmoid(z) from one exp: e = exp(-|z|) (ex2, rcp, lg2: 3 MUFU ops per element)
-          auto bce_elem = [&](int j, float& l, float& g, float& hit) {
+          // softplus(z) - z*y and sigmoid(z) from one exp: e = exp(-|z|) (ex2, rcp: 2 MUFU ops per element).  The
+          // log terms of a chunk are taken together: sum_j log(1 + e_j) = log(prod_j (1 + e_j)) -- every factor lies in
+          // (1, 2], so the product of 32 stays below 2^32 and costs one multiply per element and ONE lg2 per chunk
+          // instead of a lg2 and a multiply-add per element (relative error of the product <= 32 ulps: 2e-6 in a sum of
+          // order 10)
+          float prod = 1.f;
+          auto bce_elem = [&](int j, bool live, float& g) {
             const float z = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, b_cur, j);
             const float y = float((ybw >> j) & 1u);
-            hit = ((z > 0.f) == (y != 0.f)) ? 1.f : 0.f;     // round(sigmoid(z)) == y: sigmoid(0) = 0.5 rounds to 0 (half to even)
+            if constexpr (WANT_ACC) {                        // round(sigmoid(z)) == y: sigmoid(0) = 0.5 rounds to 0 (half to even)
+              const float hit = ((z > 0.f) == (y != 0.f)) ? 1.f : 0.f;
+              row_hits += live ? hit : 0.f;
+            }
             const float e = exp2f_approx(-1.4426950408889634f * fabsf(z));
             const float s1 = 1.f + e;
             const float r = rcp_approx(s1);
-            l = fmaf(-z, y, fmaxf(z, 0.f)) + 0.6931471805599453f * lg2_approx(s1);
+            const float lin = fmaf(-z, y, fmaxf(z, 0.f));
+            row_loss += live ? lin : 0.f;
+            prod *= live ? s1 : 1.f;
             g = ((z >= 0.f ? r : e * r) - y) * inv_row;
           };
           if (col0 + 32 <= p.n) {                       // warp-uniform: only the last column tile is ragged
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              float l, g, h;
-              bce_elem(j, l, g, h);
-              row_loss += l;
-              row_hits += h;
+              float g;
+              bce_elem(j, true, g);
               out[j] = p.round_tf32 ? rn_tf32_bits(g) : g;
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              float l, g, h;
-              bce_elem(j, l, g, h);
+              float g;
               const bool live = (col0 + j < p.n);
-              row_loss += live ? l : 0.f;
-              row_hits += live ? h : 0.f;
+              bce_elem(j, live, g);
               g = live ? g : 0.f;
               out[j] = p.round_tf32 ? rn_tf32_bits(g) : g;
             }
           }
+          row_loss = fmaf(0.6931471805599453f, lg2_approx(prod), row_loss);
         } else {
           // branch-free inner loops: bias is 0 when absent, ReLU is a max with -inf when off
           const float floor_v = p.relu ? 0.f : -INFINITY;
@@ -713,7 +723,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const float s = row_ok ? row_loss : 0.f;
         const double d = warp_sum(double(s));
         if (lane == 0) p.loss_partial[((long long)tile * CTAS + cta_rank) * EPI_WARPS + (warp - 4)] = d;
-        if (p.acc_partial) {                              // warp-uniform
+        if (WANT_ACC && p.acc_partial) {                  // warp-uniform
           const double a = warp_sum(double(row_ok ? row_hits : 0.f));
           if (lane == 0) p.acc_partial[((long long)tile * CTAS + cta_rank) * EPI_WARPS + (warp - 4)] = a;
         }
@@ -934,7 +944,7 @@ static int launch_bn(const Problem& pr, Params p, cudaStream_t st) {
   else           rc = make_map(&map_b, pr.b, elem, mt, pr.k, pr.n, pr.ldb, bk, TF32);
   if (rc != CC_OK) return rc;
   // C: fp32 (int32 counts) [M][n_store] boxes of 32 rows x 32 columns (TMA clips rows >= M and columns >= n_store)
-  if (EPI == EPI_BCE16) rc = make_map(&map_c, pr.c, 2, MAP_BF16, pr.m, p.n_store, pr.ldc, 32, false, 32);
+  if (EPI == EPI_BCE16 || EPI == EPI_BCE16_ACC) rc = make_map(&map_c, pr.c, 2, MAP_BF16, pr.m, p.n_store, pr.ldc, 32, false, 32);
   else rc = make_map(&map_c, pr.c, 4, EPI == EPI_COUNT ? MAP_S32 : MAP_F32, pr.m, p.n_store, pr.ldc, 32, false);
   if (rc != CC_OK) return rc;
   p.a_mn_major = pr.transa ? 1 : 0;
@@ -1050,7 +1060,7 @@ static int launch(const Problem& pr, Params p, int bn, int ctas, cudaStream_t st
   CC_REQUIRE((reinterpret_cast<uintptr_t>(pr.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(pr.b) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(pr.c) & 15) == 0,
              "cc_gemm_tc: base pointers must be 16-byte aligned");
-  CC_REQUIRE((pr.lda * elem) % 16 == 0 && (pr.ldb * elem) % 16 == 0 && (pr.ldc * (EPI == EPI_BCE16 ? 2 : 4)) % 16 == 0,
+  CC_REQUIRE((pr.lda * elem) % 16 == 0 && (pr.ldb * elem) % 16 == 0 && (pr.ldc * ((EPI == EPI_BCE16 || EPI == EPI_BCE16_ACC) ? 2 : 4)) % 16 == 0,
              "cc_gemm_tc: leading dimensions must be multiples of 16 bytes (lda=%lld ldb=%lld ldc=%lld)", pr.lda,
              pr.ldb, pr.ldc);
   if (ctas == 2) return launch_bn<KIND, EPI, 256, 2>(pr, p, st);
@@ -1201,7 +1211,12 @@ int cc_gemm_bce_tc_ex(int precision, int m, int n, int k, const void* a, int64_t
   if (dz_bf16) {
     CC_REQUIRE(precision == 2, "cc_gemm_bce_tc: bf16 dlogits come with bf16 operands (precision 2)");
     p.round_tf32 = 0;
+    if (acc_partial) return tc::launch<tc::KIND_BF16, tc::EPI_BCE16_ACC>(pr, p, 256, ctas, as_stream(stream));
     return tc::launch<tc::KIND_BF16, tc::EPI_BCE16>(pr, p, 256, ctas, as_stream(stream));
+  }
+  if (acc_partial) {
+    if (precision == 2) return tc::launch<tc::KIND_BF16, tc::EPI_BCE_ACC>(pr, p, 256, ctas, as_stream(stream));
+    return tc::launch<tc::KIND_TF32, tc::EPI_BCE_ACC>(pr, p, 256, ctas, as_stream(stream));
   }
   if (precision == 2) return tc::launch<tc::KIND_BF16, tc::EPI_BCE>(pr, p, 256, ctas, as_stream(stream));
   return tc::launch<tc::KIND_TF32, tc::EPI_BCE>(pr, p, 256, ctas, as_stream(stream));
