@@ -687,7 +687,9 @@ def run_native(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision], "data": "synthetic",
-        "config": workload_config(world, B, R, global_R, args.reg_mode, args.scaling),
+        "config": {**workload_config(world, B, R, global_R, args.reg_mode, args.scaling),
+                   **({"gradient_exchange": ("p2p_overlap" if eng.p2p_buckets else eng.dp_mode)
+                       + (" (multimem)" if getattr(eng, "_multicast", False) else "")} if world > 1 else {})},
         **({"note": "non-headline configuration (--reg-mode full)"} if args.reg_mode == "full" else {}),
         "loss": {"bce": loss_host[0], "kl": loss_host[1], "total": loss_host[2]},
         "loss_rel_err": loss_check["loss_rel_err"] if loss_check else None, "loss_check": loss_check,
