@@ -1086,6 +1086,250 @@ __global__ void expand_cubes_u8_kernel(const int64_t* __restrict__ indptr, const
   }
 }
 
+
+// ------------------------------------------------------------------ chain of small Dense layers in ONE kernel
+// The 512 -> 256 -> 128 -> 64 (-> 128 -> 256 -> 512) layers around the 64-wide bottleneck are latency-bound as separate
+// GEMMs (9-23 us each for a few hundred MFLOP; 27 of them are 18% of the step).  Here a CTA takes 128 rows through up to
+// three consecutive layers without leaving the SM: layer 1 is an ordinary SS tcgen05.mma (A and B staged by TMA), its
+// accumulator is turned into the next layer's operand IN TENSOR MEMORY (tcgen05.ld -> bias / ReLU or ReLU mask -> tf32
+// rounding -> tcgen05.st to the same columns), and layers 2 and 3 are TS tcgen05.mma (A from tensor memory, B = the
+// layer's kernel streamed through the same smem ring -- the producer runs ahead across layers).  Every layer's output
+// is also written to global memory (swizzled staging -> TMA store): backward and the weight-gradient GEMMs need it.
+// Same k order and the same fp32 accumulation as the separate GEMMs, so the results are bit-identical to them.
+// Reference: the Dense stacks of src/ml/model.py:27-33, 58-64 (forward) and their input gradients (backward).
+struct ChainLayer {
+  int n, k;                 // output width (multiple of 64, <= 512) and reduction length (multiple of 32, <= 512)
+  int b_mn_major;           // B = the layer's kernel: [K][N] row-major (forward, 1) or [N][K] row-major (backward, 0)
+  int passes;               // 1, or 2 halves of n / 2 columns (n = 512: the MMA's N is at most 256)
+  int tmem_col;             // first accumulator column
+  int relu, round_tf32;
+  const float* bias;        // nullable
+  const float* mask;        // nullable: keep the value where mask[row][col] > 0 (ReLU backward)
+  long long ldmask;
+};
+struct ChainParams {
+  int m, layers;
+  ChainLayer L[3];
+};
+constexpr int CH_STAGE_B_BYTES = 256 * 128;
+constexpr int CH_STAGE_BYTES = STAGE_A_BYTES + CH_STAGE_B_BYTES;
+constexpr int CH_STAGES = 4;
+constexpr int CH_SMEM_BYTES = CH_STAGES * CH_STAGE_BYTES + EPI_STAGE_BYTES + BAR_BYTES + 1024;
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] B[smem]: A is 128 lanes x 8 columns of tf32 (raw fp32 bits) in tensor memory
+__device__ __forceinline__ void tcgen05_mma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+chain_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b0,
+                const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ CUtensorMap map_b2,
+                const __grid_constant__ CUtensorMap map_c0, const __grid_constant__ CUtensorMap map_c1,
+                const __grid_constant__ CUtensorMap map_c2, const ChainParams p) {
+  constexpr int BK = 32, UMMA_K = 8, MMAS_PER_STAGE = 4, MN_BOX = 32, MN_BOX_BYTES = 32 * 128;
+  constexpr int MAX_PASSES = 4;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi_smem = smem + CH_STAGES * CH_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + EPI_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + CH_STAGES;
+  uint64_t* acc_full = empty_bar + CH_STAGES;          // one per pass (each used once: a CTA owns one row block)
+  uint64_t* a_ready = acc_full + MAX_PASSES;           // layer l's output is back in tensor memory as layer l+1's operand
+  uint64_t* drained = a_ready + 3;                     // the first half of a two-pass layer has been read out
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(drained + 1);
+
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const CUtensorMap* maps_b[3] = {&map_b0, &map_b1, &map_b2};
+  const CUtensorMap* maps_c[3] = {&map_c0, &map_c1, &map_c2};
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    for (int l = 0; l < p.layers; ++l) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(maps_b[l]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(maps_c[l]) : "memory");
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < CH_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int i = 0; i < MAX_PASSES; ++i) mbar_init(&acc_full[i], 1);
+    for (int i = 0; i < 3; ++i) mbar_init(&a_ready[i], EPI_WARPS);
+    mbar_init(drained, EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int row0 = blockIdx.x * BM;
+
+  if (warp == 0) {
+    // ===================== TMA producer: layer 1's rows and every layer's kernel, k-block by k-block =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int l = 0; l < p.layers; ++l) {
+        const ChainLayer& L = p.L[l];
+        const int nw = L.n / L.passes;
+        for (int h = 0; h < L.passes; ++h) {
+          for (int kb = 0; kb < L.k / BK; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * CH_STAGE_BYTES;
+            uint8_t* sb = sa + STAGE_A_BYTES;
+            mbar_expect_tx(&full_bar[stage], (l == 0 ? STAGE_A_BYTES : 0) + nw * 128);
+            if (l == 0) tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, row0);
+            if (L.b_mn_major) {
+              for (int j = 0; j < nw / MN_BOX; ++j)
+                tma_load_2d(sb + j * MN_BOX_BYTES, maps_b[l], &full_bar[stage], h * nw + j * MN_BOX, kb * BK);
+            } else {
+              tma_load_2d(sb, maps_b[l], &full_bar[stage], kb * BK, h * nw);
+            }
+            if (++stage == CH_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int pass = 0;
+      for (int l = 0; l < p.layers; ++l) {
+        const ChainLayer& L = p.L[l];
+        const int nw = L.n / L.passes;
+        // D = f32, A / B = tf32, A K-major (or tensor memory), B as the layer says, N = nw, M = 128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(L.b_mn_major) << 16) |
+                               (uint32_t(nw >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+        const uint32_t b_lbo = L.b_mn_major ? MN_BOX_BYTES : 16;
+        const uint32_t b_lt = L.b_mn_major ? 1u : 2u;
+        const uint32_t b_sbo = b_lt == 1u ? 512u : 1024u;
+        const uint32_t b_kstep = L.b_mn_major ? UMMA_K * 128 : 32;
+        if (l > 0) {                                          // the previous layer's output is in tensor memory
+          mbar_wait(&a_ready[l - 1], 0);
+          tcgen05_fence_after();
+        }
+        for (int h = 0; h < L.passes; ++h, ++pass) {
+          if (h > 0) {                                        // the second half reuses the first half's columns
+            mbar_wait(drained, 0);
+            tcgen05_fence_after();
+          }
+          const uint32_t tmem_d = tmem_base + L.tmem_col;
+          for (int kb = 0; kb < L.k / BK; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * CH_STAGE_BYTES);
+            const uint32_t sb = sa + STAGE_A_BYTES;
+#pragma unroll
+            for (int k = 0; k < MMAS_PER_STAGE; ++k) {
+              const uint64_t bdesc = make_desc(sb + k * b_kstep, b_lbo, b_sbo, b_lt);
+              const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+              if (l == 0) {
+                const uint64_t adesc = make_desc(sa + k * 32, 16, 1024, 2u);
+                tcgen05_mma<KIND_TF32, 1>(tmem_d, adesc, bdesc, idesc, accum);
+              } else {
+                tcgen05_mma_ts_tf32(tmem_d, tmem_base + p.L[l - 1].tmem_col + kb * BK + k * UMMA_K, bdesc, idesc, accum);
+              }
+            }
+            tcgen05_commit<1>(&empty_bar[stage]);
+            if (++stage == CH_STAGES) { stage = 0; phase ^= 1; }
+          }
+          tcgen05_commit<1>(&acc_full[pass]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (8 warps): accumulator -> next operand in place, and -> global =====================
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    uint8_t* sbuf = epi_smem + (warp - 4) * 4096;
+    const int row = row0 + q * 32 + lane;
+    const bool row_ok = row < p.m;
+    int pass = 0;
+    for (int l = 0; l < p.layers; ++l) {
+      const ChainLayer& L = p.L[l];
+      const int nw = L.n / L.passes;
+      const bool feeds_next = l + 1 < p.layers;
+      for (int h = 0; h < L.passes; ++h, ++pass) {
+        mbar_wait(&acc_full[pass], 0);
+        tcgen05_fence_after();
+        const int nch = nw / 64;                              // 32-column chunks of this warp's half
+        for (int cb = 0; cb < nch; ++cb) {
+          const int tcol = half * (nw / 2) + cb * 32;         // column inside the pass
+          const int col0 = h * nw + tcol;                     // column of the layer's output
+          const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(L.tmem_col + tcol);
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld32(taddr, v);
+          const float b_cur = L.bias ? __ldg(L.bias + col0 + lane) : 0.f;
+          const float floor_v = L.relu ? 0.f : -INFINITY;
+          float out[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            out[j] = fmaxf(__uint_as_float(v[j]) + __shfl_sync(0xffffffffu, b_cur, j), floor_v);
+          if (L.mask) {
+            if (row_ok) {
+              const float* mrow = L.mask + (long long)row * L.ldmask + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) out[j] = (__ldg(mrow + j) > 0.f) ? out[j] : 0.f;
+            }
+          }
+          if (L.round_tf32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) out[j] = rn_tf32_bits(out[j]);
+          }
+          if (feeds_next) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(out[j]);
+            tmem_st32(taddr, v);
+          }
+          if (lane == 0) tma_wait_group_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(sbuf + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                make_float4(out[4 * c], out[4 * c + 1], out[4 * c + 2], out[4 * c + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(maps_c[l], sbuf, col0, row0 + q * 32);
+            tma_commit_group();
+          }
+        }
+        if (feeds_next) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (feeds_next) mbar_arrive(&a_ready[l]);
+          else if (L.passes == 2 && h == 0) mbar_arrive(drained);
+        }
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
 }  // namespace tc
 }  // namespace cc
 
@@ -1289,6 +1533,89 @@ int cc_cooc_count_tc(const int64_t* indptr, const int32_t* indices, int64_t num_
     const int rc = tc::launch<tc::KIND_U8, tc::EPI_COUNT>(pr, p, 256, 2, st);
     if (rc != CC_OK) return rc;
   }
+  return CC_OK;
+}
+
+// Up to three consecutive small Dense layers in one launch (see chain_tc_kernel): widths = {k0, n1, ..., n_layers};
+// layer l computes out_l[m][n_l] = epi(in_l W_l) with in_1 = a and in_{l+1} = out_l.  w_is_kn[l] = 1: W_l is the Keras
+// kernel [K][N] (forward), 0: it is [N][K] (the transposed use of a kernel in backward).  bias[l] / mask[l] nullable;
+// relu applies to every layer that has a bias (forward), the mask test (mask > 0) is ReLU's backward.
+int cc_chain_tc(int m, int layers, const int32_t* widths, const float* a, int64_t lda, const float* const* w,
+                const int64_t* ldw, const int32_t* w_is_kn, const float* const* bias, const float* const* mask,
+                const int64_t* ldmask, int relu, float* const* out, const int64_t* ldout, int round_tf32, void* stream) {
+  CC_NVTX("cc_chain_tc");
+  CC_REQUIRE(m > 0 && layers >= 1 && layers <= 3, "cc_chain_tc: 1..3 layers (got %d) and m > 0", layers);
+  CC_REQUIRE(widths && a && w && ldw && w_is_kn && out && ldout, "cc_chain_tc: null argument");
+  tc::ChainParams p{};
+  p.m = m; p.layers = layers;
+  int total = 0;
+  for (int l = 0; l < layers; ++l) {
+    const int k = widths[l], n = widths[l + 1];
+    CC_REQUIRE(k % 32 == 0 && k >= 32 && k <= 512 && n % 64 == 0 && n >= 64 && n <= 512,
+               "cc_chain_tc: layer %d is %d -> %d (k must be a multiple of 32, n of 64, both <= 512)", l, k, n);
+    CC_REQUIRE(n <= 256 || l == layers - 1, "cc_chain_tc: only the last layer may be 512 wide");
+    CC_REQUIRE((reinterpret_cast<uintptr_t>(w[l]) & 15) == 0 && (reinterpret_cast<uintptr_t>(out[l]) & 15) == 0 &&
+                   (ldw[l] * 4) % 16 == 0 && (ldout[l] * 4) % 16 == 0,
+               "cc_chain_tc: layer %d: kernels and outputs must be 16-byte aligned with leading dimensions % 4 == 0", l);
+    tc::ChainLayer& L = p.L[l];
+    L.n = n; L.k = k; L.b_mn_major = w_is_kn[l] ? 1 : 0; L.passes = n > 256 ? 2 : 1;
+    L.relu = (relu && bias && bias[l]) ? 1 : 0; L.round_tf32 = round_tf32;
+    L.bias = bias ? bias[l] : nullptr;
+    L.mask = mask ? mask[l] : nullptr;
+    L.ldmask = (mask && mask[l] && ldmask) ? ldmask[l] : 0;
+    total += n;
+  }
+  CC_REQUIRE((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (lda * 4) % 16 == 0, "cc_chain_tc: a must be 16-byte aligned, lda % 4 == 0");
+  // tensor-memory columns (512 per SM): consecutive accumulators when they fit; otherwise (64 -> 128 -> 256 -> 512) the
+  // last layer's two 256-column halves reuse the columns of the first accumulator, which is dead by then
+  if (total <= 512) {
+    int c = 0;
+    for (int l = 0; l < layers; ++l) { p.L[l].tmem_col = c; c += p.L[l].n / p.L[l].passes; }   // (two halves share their columns)
+  } else {
+    CC_REQUIRE(layers == 3 && p.L[2].passes == 2 && p.L[0].n <= 256 && p.L[1].n <= 256,
+               "cc_chain_tc: accumulators of %d columns do not fit the 512 columns of tensor memory", total);
+    p.L[0].tmem_col = 0; p.L[1].tmem_col = 256; p.L[2].tmem_col = 0;
+  }
+  CUtensorMap map_a, map_b[3], map_c[3];
+  int rc = tc::make_map(&map_a, a, 4, tc::MAP_F32, m, widths[0], lda, tc::BM, false);
+  if (rc != CC_OK) return rc;
+  for (int l = 0; l < 3; ++l) {
+    const int ll = l < layers ? l : layers - 1;               // unused slots repeat the last layer's maps
+    const tc::ChainLayer& L = p.L[ll];
+    const int nw = L.n / L.passes;
+    if (L.b_mn_major) rc = tc::make_map(&map_b[l], w[ll], 4, tc::MAP_F32, L.k, L.n, ldw[ll], 32, true);
+    else              rc = tc::make_map(&map_b[l], w[ll], 4, tc::MAP_F32, L.n, L.k, ldw[ll], nw, false);
+    if (rc != CC_OK) return rc;
+    rc = tc::make_map(&map_c[l], out[ll], 4, tc::MAP_F32, m, L.n, ldout[ll], 32, false);
+    if (rc != CC_OK) return rc;
+  }
+  static std::mutex mu;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  CC_CHECK_CUDA(cudaGetDevice(&dev));
+  CC_REQUIRE(dev >= 0 && dev < 64, "cc_chain_tc: device ordinal %d out of range", dev);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!attr_done[dev]) {
+      CC_CHECK_CUDA(cudaFuncSetAttribute(tc::chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::CH_SMEM_BYTES));
+      attr_done[dev] = true;
+    }
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned((m + tc::BM - 1) / tc::BM));
+  cfg.blockDim = dim3(tc::THREADS);
+  cfg.dynamicSmemBytes = tc::CH_SMEM_BYTES;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute at[1];
+  int na = 0;
+  if (tc::g_pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at; cfg.numAttrs = na;
+  CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc::chain_tc_kernel, map_a, map_b[0], map_b[1], map_b[2], map_c[0], map_c[1], map_c[2], p));
+  CC_CHECK_LAUNCH();
   return CC_OK;
 }
 

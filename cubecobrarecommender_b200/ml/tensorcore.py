@@ -1,6 +1,7 @@
 """tcgen05 tensor-core GEMM wrappers (precision modes "tf32" and "bf16"); see csrc/gemm_tc.cu."""
 from __future__ import annotations
 
+import numpy as np
 import torch
 
 from .. import _lib
@@ -49,3 +50,29 @@ def gemm_bce(a, w, bias, ybits, count, dz, loss_partial, precision="tf32", round
 
 def bce_partial_count(m, lddz):
     return _lib.load().cc_gemm_bce_partial_count(m, lddz)
+
+
+def chain(a, layers, *, relu=True, round_out=True):
+    """Up to three consecutive small Dense layers in one launch (cc_chain_tc): ``layers`` = [(w, w_is_kn, bias, mask,
+    out), ...]; layer l computes ``out = epi(in @ (w if w_is_kn else w.T))`` with ``in`` = ``a`` for the first layer and
+    the previous ``out`` afterwards.  ``bias`` / ``mask`` may be None.  The host-side pointer arrays are built per call
+    (the C side reads them before it returns)."""
+    n = len(layers)
+    widths = np.zeros(n + 1, dtype=np.int32)
+    widths[0] = a.shape[1]
+    addr = lambda t: 0 if t is None else t.data_ptr()
+    w_p, b_p, m_p, o_p = (np.zeros(n, dtype=np.uint64) for _ in range(4))
+    ldw, ldm, ldo = (np.zeros(n, dtype=np.int64) for _ in range(3))
+    kn = np.zeros(n, dtype=np.int32)
+    for l, (w, w_is_kn, bias, mask, out) in enumerate(layers):
+        widths[l + 1] = out.shape[1]
+        k_in = int(widths[l])
+        if (tuple(w.shape) != ((k_in, out.shape[1]) if w_is_kn else (out.shape[1], k_in)) or out.shape[0] != a.shape[0]
+                or w.dtype != torch.float32 or out.dtype != torch.float32):
+            raise ValueError(f"chain layer {l}: shapes {tuple(w.shape)} / {tuple(out.shape)} do not follow {k_in} inputs")
+        w_p[l], b_p[l], m_p[l], o_p[l] = addr(w), addr(bias), addr(mask), addr(out)
+        ldw[l], ldo[l], kn[l] = w.stride(0), out.stride(0), int(bool(w_is_kn))
+        ldm[l] = mask.stride(0) if mask is not None else 0
+    np_ptr = lambda x: x.ctypes.data
+    call("cc_chain_tc", a.shape[0], n, np_ptr(widths), ptr(a), a.stride(0), np_ptr(w_p), np_ptr(ldw), np_ptr(kn),
+         np_ptr(b_p), np_ptr(m_p), np_ptr(ldm), int(relu), np_ptr(o_p), np_ptr(ldo), int(round_out), stream_ptr())

@@ -241,6 +241,17 @@ int cc_gemm_tc_set_dynamic_tiles(int on);
  * scheduled and run their prologue while the previous kernel drains; they wait (griddepcontrol.wait) for its
  * completion before touching global memory. */
 int cc_gemm_tc_set_pdl(int on);
+/* Up to three consecutive small Dense layers in ONE launch (the 512 -> 256 -> 128 -> 64 -> 128 -> 256 -> 512 stack of
+ * model.py:27-33, 58-64 and its input gradients): a CTA takes 128 rows through the chain with the intermediate
+ * activations kept in tensor memory (tcgen05.mma with the A operand in TMEM); every layer's output is also stored.
+ * widths = {k0, n1, ..., n_layers} (k multiples of 32, n multiples of 64, <= 512; only the last layer may be 512 wide);
+ * layer l: out_l[m][n_l] = epi(in_l W_l), in_1 = a, in_{l+1} = out_l.  w_is_kn[l] = 1: W_l is the Keras kernel [K][N]
+ * (forward); 0: [N][K] (a kernel used transposed: backward).  bias / mask: arrays of `layers` nullable pointers (either
+ * array itself nullable); relu applies to layers with a bias, mask keeps values where mask[row][col] > 0 (ReLU's
+ * backward).  Results are bit-identical to the same layers as separate cc_gemm_tc calls. */
+int cc_chain_tc(int m, int layers, const int32_t* widths, const float* a, int64_t lda, const float* const* w,
+                const int64_t* ldw, const int32_t* w_is_kn, const float* const* bias, const float* const* mask,
+                const int64_t* ldmask, int relu, float* const* out, const int64_t* ldout, int round_tf32, void* stream);
 int64_t cc_colsum_workspace_bytes(int m, int n);
 int cc_colsum_f32(const float* x, int64_t ld, int m, int n, float* workspace, float* out, int accumulate,
                   void* stream);

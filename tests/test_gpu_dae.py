@@ -265,6 +265,46 @@ def test_gemm_tcgen05_tf32_all_layouts(ta, tb, m, n, k, split, tile_n, pair_mode
         assert (c4.double() - torch.relu(ref + bias.double())).abs().max().item() / scale < tol
 
 
+@pytest.mark.parametrize("m", [8192, 300])
+@pytest.mark.parametrize("widths", [(512, 256, 128, 64), (64, 128, 256, 512), (512, 256), (256, 512), (128, 64, 128)])
+@pytest.mark.parametrize("backward", [False, True])
+def test_chain_of_small_layers_equals_separate_gemms(widths, m, backward):
+    """cc_chain_tc: up to three consecutive Dense layers in one launch with the intermediate activations kept in tensor
+    memory (tcgen05.mma with A in TMEM) against the same layers as separate cc_gemm_tc calls -- same k order, same fp32
+    accumulation, so every layer's output must be bit-identical.  Forward form (Keras kernels [K][N], bias + ReLU +
+    tf32 rounding) and backward form (kernels used transposed, ReLU mask); full row blocks and a ragged last one."""
+    from cubecobrarecommender_b200.ml import tensorcore as TC
+    g = torch.Generator(device="cuda").manual_seed(sum(widths) + m)
+    a = _rn_tf32(torch.randn((m, widths[0] + 4), device="cuda", generator=g))[:, :widths[0]]      # padded row stride
+    layers_chain, layers_ref = [], []
+    for k, n in zip(widths[:-1], widths[1:]):
+        w = _rn_tf32(torch.randn((n, k) if backward else (k, n), device="cuda", generator=g) / k ** 0.5)
+        bias = None if backward else torch.randn(n, device="cuda", generator=g) * 0.1
+        mask = torch.randn((m, n + 4), device="cuda", generator=g)[:, :n] if backward else None
+        out_c = torch.full((m, n + 4), 7.0, device="cuda")[:, :n]
+        out_r = torch.full((m, n + 4), 7.0, device="cuda")[:, :n]
+        layers_chain.append((w, not backward, bias, mask, out_c))
+        layers_ref.append((w, bias, mask, out_r))
+    h = a
+    for w, bias, mask, out_r in layers_ref:
+        TC.gemm(h, w, out_r, transb=backward, bias=bias, relu=not backward, mask=mask, precision="tf32", round_out=True)
+        h = out_r
+    TC.chain(a, layers_chain, relu=True, round_out=True)
+    torch.cuda.synchronize()
+    h = a
+    for l, ((w, _, bias, mask, out_c), (_, _, _, out_r)) in enumerate(zip(layers_chain, layers_ref)):
+        if m == 8192:       # (at 300 rows the planner splits K for the separate GEMMs: another summation order)
+            assert torch.equal(out_c, out_r), (l, (out_c - out_r).abs().max().item())
+        # layer by layer against float64 on the chain's own input of that layer
+        ref = h.double() @ (w.t() if backward else w).double()
+        ref = ref * (mask > 0) if backward else torch.relu(ref + bias.double())
+        scale = ref.abs().max().item()
+        assert scale > 0 and (out_c.double() - ref).abs().max().item() / scale < 6e-4, l      # output rounded to tf32
+        assert torch.equal(out_c, _rn_tf32(out_c))
+        assert (out_c._base[:, out_c.shape[1]:] == 7.0).all()          # nothing written beyond the layer's width
+        h = out_c
+
+
 @pytest.mark.parametrize("precision", ["tf32", "bf16"])
 @pytest.mark.parametrize("pair", [0, 1])
 @pytest.mark.parametrize("ta,tb,m,n,k", [(1, 0, 512, 5000, 4096),      # dW-like: fewer tiles than units, all stream-K
