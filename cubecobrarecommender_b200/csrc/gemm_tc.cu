@@ -1106,6 +1106,11 @@ struct ChainLayer {
   const float* bias;        // nullable
   const float* mask;        // nullable: keep the value where mask[row][col] > 0 (ReLU backward)
   long long ldmask;
+  // the same test as one BIT per element: word [row][col / 32] of a (m, n / 32) uint32 matrix.  bits_out (forward):
+  // bit j of the word = output column 32 w + j is positive; mask_bits (backward): keep the value where the bit is set.
+  // A lane owns a row, so a 32-column chunk costs it one 4-byte load instead of 128 bytes of activations
+  const uint32_t* mask_bits;
+  uint32_t* bits_out;
 };
 struct ChainParams {
   int m, layers;
@@ -1281,16 +1286,35 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             out[j] = fmaxf(__uint_as_float(v[j]) + __shfl_sync(0xffffffffu, b_cur, j), floor_v);
-          if (L.mask) {
+          if (L.mask_bits) {
+            const uint32_t word = row_ok ? __ldg(L.mask_bits + (long long)row * (L.n >> 5) + (col0 >> 5)) : 0u;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) out[j] = ((word >> j) & 1u) ? out[j] : 0.f;
+          } else if (L.mask) {
             if (row_ok) {
               const float* mrow = L.mask + (long long)row * L.ldmask + col0;
+              if (((reinterpret_cast<uintptr_t>(mrow) | uintptr_t(L.ldmask * 4)) & 15) == 0) {     // 8 x 16 bytes per lane
 #pragma unroll
-              for (int j = 0; j < 32; ++j) out[j] = (__ldg(mrow + j) > 0.f) ? out[j] : 0.f;
+                for (int c = 0; c < 8; ++c) {
+                  const float4 mk = __ldg(reinterpret_cast<const float4*>(mrow) + c);
+                  out[4 * c] = mk.x > 0.f ? out[4 * c] : 0.f;         out[4 * c + 1] = mk.y > 0.f ? out[4 * c + 1] : 0.f;
+                  out[4 * c + 2] = mk.z > 0.f ? out[4 * c + 2] : 0.f; out[4 * c + 3] = mk.w > 0.f ? out[4 * c + 3] : 0.f;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) out[j] = (__ldg(mrow + j) > 0.f) ? out[j] : 0.f;
+              }
             }
           }
           if (L.round_tf32) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) out[j] = rn_tf32_bits(out[j]);
+          }
+          if (L.bits_out && row_ok) {
+            uint32_t word = 0u;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) word |= (out[j] > 0.f ? 1u : 0u) << j;
+            L.bits_out[(long long)row * (L.n >> 5) + (col0 >> 5)] = word;
           }
           if (feeds_next) {
 #pragma unroll
@@ -1539,10 +1563,12 @@ int cc_cooc_count_tc(const int64_t* indptr, const int32_t* indices, int64_t num_
 // Up to three consecutive small Dense layers in one launch (see chain_tc_kernel): widths = {k0, n1, ..., n_layers};
 // layer l computes out_l[m][n_l] = epi(in_l W_l) with in_1 = a and in_{l+1} = out_l.  w_is_kn[l] = 1: W_l is the Keras
 // kernel [K][N] (forward), 0: it is [N][K] (the transposed use of a kernel in backward).  bias[l] / mask[l] nullable;
-// relu applies to every layer that has a bias (forward), the mask test (mask > 0) is ReLU's backward.
+// relu applies to every layer that has a bias (forward), the mask test (mask > 0) is ReLU's backward; mask_bits /
+// bits_out carry the same test as one bit per element ((m, n / 32) uint32 matrices, see ChainLayer).
 int cc_chain_tc(int m, int layers, const int32_t* widths, const float* a, int64_t lda, const float* const* w,
                 const int64_t* ldw, const int32_t* w_is_kn, const float* const* bias, const float* const* mask,
-                const int64_t* ldmask, int relu, float* const* out, const int64_t* ldout, int round_tf32, void* stream) {
+                const int64_t* ldmask, const uint32_t* const* mask_bits, uint32_t* const* bits_out, int relu,
+                float* const* out, const int64_t* ldout, int round_tf32, void* stream) {
   CC_NVTX("cc_chain_tc");
   CC_REQUIRE(m > 0 && layers >= 1 && layers <= 3, "cc_chain_tc: 1..3 layers (got %d) and m > 0", layers);
   CC_REQUIRE(widths && a && w && ldw && w_is_kn && out && ldout, "cc_chain_tc: null argument");
@@ -1563,6 +1589,8 @@ int cc_chain_tc(int m, int layers, const int32_t* widths, const float* a, int64_
     L.bias = bias ? bias[l] : nullptr;
     L.mask = mask ? mask[l] : nullptr;
     L.ldmask = (mask && mask[l] && ldmask) ? ldmask[l] : 0;
+    L.mask_bits = mask_bits ? mask_bits[l] : nullptr;
+    L.bits_out = bits_out ? bits_out[l] : nullptr;
     total += n;
   }
   CC_REQUIRE((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (lda * 4) % 16 == 0, "cc_chain_tc: a must be 16-byte aligned, lda % 4 == 0");

@@ -109,6 +109,10 @@ class DAEEngine:
         # the small layers' weight-gradient GEMMs ([x | 1]^T dY, a few microseconds each, <= 64 CTAs) run on a side
         # stream, off the dY -> dX -> dY chain that backward is serialised on (CC_SIDE_STREAM=0 keeps one stream)
         self.use_side = os.environ.get("CC_SIDE_STREAM", "1") != "0" and self.dp_mode != "nccl_overlap"
+        # the three small layers either side of the bottleneck (and their input gradients) as ONE launch each, the
+        # intermediate activations kept in tensor memory (cc_chain_tc): 5 launches instead of 15 on the step's critical
+        # path.  Bit-identical to the separate GEMMs; CC_SMALL_CHAIN=0 restores them (A/B measurements)
+        self.small_chain = self.precision != "fp32" and os.environ.get("CC_SMALL_CHAIN", "1") != "0"
         # first layer of the main rows: "gather" = warp-per-cube embedding bag over W1 (exact fp32 sums), "tensor" = dense
         # 0/1 rows x W1 on the tensor cores (tensor-core precision modes only).  CC_FIRST_LAYER overrides; see DESIGN.md
         fl = os.environ.get("CC_FIRST_LAYER", "auto")
@@ -155,6 +159,12 @@ class DAEEngine:
         self.rd_1 = [b_[:, :w + 1] for b_, w in zip(self.rd_buf, (128, 256, 512))]
         self.z1 = e(B if self.precision != "bf16" else 1, self.cpad)   # logits -> dlogits in place (bf16 mode: dz1_16)
         self.z2 = e(max(R, 1), self.cpad)
+        # ReLU masks of the activations the small-layer chains produce, one bit per element (cc_chain_tc bits_out /
+        # mask_bits): backward reads 4 bytes per row and 32 columns instead of 128
+        bits = lambda rows, w: torch.zeros((rows, w // 32), dtype=torch.int32, device=d)
+        self.a_bits = [None] + [bits(T, w) for w in HIDDEN[1:]]                 # a2..a4 (a1 comes from the first layer)
+        self.md_bits = [bits(B, w) for w in (128, 256, 512)]
+        self.rd_bits = [bits(max(R, 1), w) for w in (128, 256, 512)]
         self.ga = [e(T, w) for w in HIDDEN]
         self.gmd = [e(B, w) for w in (128, 256, 512)]
         self.grd = [e(max(R, 1), w) for w in (128, 256, 512)]
@@ -353,10 +363,29 @@ class DAEEngine:
             bag_fwd(P("encoder_e1/kernel"), self.reg_rows, self.reg_start, self.reg_len, P("encoder_e1/bias"), a1[B:],
                     round_tf32=tc)
             n_launch += 1
-        for i, name in enumerate(ENC_NAMES[1:]):
-            gemm(self.a[i], W(name + "/kernel"), self.a[i + 1], bias=P(name + "/bias"), relu=True, precision=pr,
-                 round_out=tc)
+        if self.small_chain:
+            from . import tensorcore
+            tensorcore.chain(self.a[0], [(W(name + "/kernel"), True, P(name + "/bias"), None, self.a[i + 1], self.a_bits[i + 1])
+                                         for i, name in enumerate(ENC_NAMES[1:])], relu=True, round_out=tc)
             n_launch += 1
+        else:
+            for i, name in enumerate(ENC_NAMES[1:]):
+                gemm(self.a[i], W(name + "/kernel"), self.a[i + 1], bias=P(name + "/bias"), relu=True, precision=pr,
+                     round_out=tc)
+                n_launch += 1
+
+        def dec_small_fwd(names_, h_, acts_, bits_):
+            """The decoder's three small layers 64 -> 128 -> 256 -> 512 (one chain launch, or three GEMMs)."""
+            if self.small_chain:
+                from . import tensorcore
+                tensorcore.chain(h_, [(W(names_[i] + "/kernel"), True, P(names_[i] + "/bias"), None, acts_[i], bits_[i])
+                                      for i in range(3)], relu=True, round_out=tc)
+                return 1
+            for i in range(3):
+                gemm(h_, W(names_[i] + "/kernel"), acts_[i], bias=P(names_[i] + "/bias"), relu=True, precision=pr,
+                     round_out=tc)
+                h_ = acts_[i]
+            return 3
         towers = [("main", self.a[3][:B], self.md, self.z1, B)]
         if R:
             towers.append(("reg", self.a[3][B:], self.rd, self.z2, R))
@@ -373,12 +402,7 @@ class DAEEngine:
             fork.record(main_stream)                       # the shared encoder's output is complete
             with torch.cuda.stream(self._side):
                 self._side.wait_event(fork)
-                names_r = dec_names("reg")
-                h_r = self.a[3][B:]
-                for i in range(3):
-                    gemm(h_r, W(names_r[i] + "/kernel"), self.rd[i], bias=P(names_r[i] + "/bias"), relu=True, precision=pr,
-                         round_out=tc)
-                    h_r = self.rd[i]; n_launch += 1
+                n_launch += dec_small_fwd(dec_names("reg"), self.a[3][B:], self.rd, self.rd_bits)
                 join.record(self._side)
         for prefix, h, acts, z, rows in towers:
             names = dec_names(prefix)
@@ -386,10 +410,8 @@ class DAEEngine:
                 main_stream.wait_event(join)
                 h = acts[2]
             else:
-                for i in range(3):
-                    gemm(h, W(names[i] + "/kernel"), acts[i], bias=P(names[i] + "/bias"), relu=True, precision=pr,
-                         round_out=tc)
-                    h = acts[i]; n_launch += 1
+                n_launch += dec_small_fwd(names, h, acts, self.md_bits if prefix == "main" else self.rd_bits)
+                h = acts[2]
             if big16:                   # the 512-wide activation as a bf16 operand
                 h16 = self.md2_16 if prefix == "main" else self.rd2_16
                 to_bf16(h, h16)
@@ -500,26 +522,50 @@ class DAEEngine:
                 with self._timed("big_gemm"):
                     gemm(dzc, W(names[3] + "/kernel"), gacts[2], transb=True, mask=acts[2], precision=pr, round_out=tc)
                 n_launch += 1
-            for i in (2, 1):
-                small_dw(acts_1[i - 1], gacts[i], GKB(names[i]))
-                gemm(gacts[i], W(names[i] + "/kernel"), gacts[i - 1], transb=True, mask=acts[i - 1], precision=pr,
-                     round_out=tc)
+            if self.small_chain:
+                # dX chain 512 -> 256 -> 128 -> 64 in one launch; the three weight-gradient GEMMs around it on the side stream
+                from . import tensorcore
+                small_dw(acts_1[1], gacts[2], GKB(names[2]))
+                abits = self.md_bits if prefix == "main" else self.rd_bits
+                hbits = self.a_bits[3][:B] if prefix == "main" else self.a_bits[3][B:]       # (row slices stay contiguous)
+                tensorcore.chain(gacts[2], [(W(names[2] + "/kernel"), False, None, abits[1], gacts[1]),
+                                            (W(names[1] + "/kernel"), False, None, abits[0], gacts[0]),
+                                            (W(names[0] + "/kernel"), False, None, hbits, g_in)], round_out=tc)
+                small_dw(acts_1[0], gacts[1], GKB(names[1]))
+                small_dw(h_in_1, gacts[0], GKB(names[0]))
+                n_launch += 4
+            else:
+                for i in (2, 1):
+                    small_dw(acts_1[i - 1], gacts[i], GKB(names[i]))
+                    gemm(gacts[i], W(names[i] + "/kernel"), gacts[i - 1], transb=True, mask=acts[i - 1], precision=pr,
+                         round_out=tc)
+                    n_launch += 2
+                small_dw(h_in_1, gacts[0], GKB(names[0]))
+                gemm(gacts[0], W(names[0] + "/kernel"), g_in, transb=True, mask=h_in, precision=pr, round_out=tc)
                 n_launch += 2
-            small_dw(h_in_1, gacts[0], GKB(names[0]))
-            gemm(gacts[0], W(names[0] + "/kernel"), g_in, transb=True, mask=h_in, precision=pr, round_out=tc)
-            n_launch += 2
             self._grads_ready(prefix)
         if not R:
             for n_ in dec_names("reg"):
                 G(n_ + "/kernel").zero_(); G(n_ + "/bias").zero_()
             self._grads_ready("reg")
         # ---------------- backward: shared encoder (main + reg rows together) ----------------
-        for i in (3, 2, 1):
-            name = ENC_NAMES[i]
-            small_dw(self.a_1[i - 1], self.ga[i], GKB(name))
-            gemm(self.ga[i], W(name + "/kernel"), self.ga[i - 1], transb=True, mask=self.a[i - 1], precision=pr,
-                 round_out=tc)
-            n_launch += 2
+        if self.small_chain:
+            from . import tensorcore
+            small_dw(self.a_1[2], self.ga[3], GKB(ENC_NAMES[3]))
+            # (a1, the first layer's output, has no bit mask: its float activations are the mask of the last layer)
+            tensorcore.chain(self.ga[3], [(W(ENC_NAMES[i] + "/kernel"), False, None,
+                                           self.a_bits[i - 1] if i > 1 else self.a[0], self.ga[i - 1])
+                                          for i in (3, 2, 1)], round_out=tc)
+            small_dw(self.a_1[1], self.ga[2], GKB(ENC_NAMES[2]))
+            small_dw(self.a_1[0], self.ga[1], GKB(ENC_NAMES[1]))
+            n_launch += 4
+        else:
+            for i in (3, 2, 1):
+                name = ENC_NAMES[i]
+                small_dw(self.a_1[i - 1], self.ga[i], GKB(name))
+                gemm(self.ga[i], W(name + "/kernel"), self.ga[i - 1], transb=True, mask=self.a[i - 1], precision=pr,
+                     round_out=tc)
+                n_launch += 2
         g1 = self.ga[0]
         colsum(g1, G("encoder_e1/bias"), self.cs_ws); n_launch += 2
         gw1 = G("encoder_e1/kernel")

@@ -54,25 +54,36 @@ def bce_partial_count(m, lddz):
 
 def chain(a, layers, *, relu=True, round_out=True):
     """Up to three consecutive small Dense layers in one launch (cc_chain_tc): ``layers`` = [(w, w_is_kn, bias, mask,
-    out), ...]; layer l computes ``out = epi(in @ (w if w_is_kn else w.T))`` with ``in`` = ``a`` for the first layer and
-    the previous ``out`` afterwards.  ``bias`` / ``mask`` may be None.  The host-side pointer arrays are built per call
-    (the C side reads them before it returns)."""
+    out[, bits_out]), ...]; layer l computes ``out = epi(in @ (w if w_is_kn else w.T))`` with ``in`` = ``a`` for the first
+    layer and the previous ``out`` afterwards.  ``bias`` / ``mask`` may be None; ``mask`` is either a float matrix (keep
+    where > 0) or an int32 (m, n / 32) bit matrix as written through ``bits_out`` (one bit per positive output).  The
+    host-side pointer arrays are built per call (the C side reads them before it returns)."""
     n = len(layers)
     widths = np.zeros(n + 1, dtype=np.int32)
     widths[0] = a.shape[1]
     addr = lambda t: 0 if t is None else t.data_ptr()
-    w_p, b_p, m_p, o_p = (np.zeros(n, dtype=np.uint64) for _ in range(4))
+    w_p, b_p, m_p, mb_p, bo_p, o_p = (np.zeros(n, dtype=np.uint64) for _ in range(6))
     ldw, ldm, ldo = (np.zeros(n, dtype=np.int64) for _ in range(3))
     kn = np.zeros(n, dtype=np.int32)
-    for l, (w, w_is_kn, bias, mask, out) in enumerate(layers):
+    for l, layer in enumerate(layers):
+        w, w_is_kn, bias, mask, out = layer[:5]
+        bits_out = layer[5] if len(layer) > 5 else None
         widths[l + 1] = out.shape[1]
-        k_in = int(widths[l])
-        if (tuple(w.shape) != ((k_in, out.shape[1]) if w_is_kn else (out.shape[1], k_in)) or out.shape[0] != a.shape[0]
+        k_in, n_out = int(widths[l]), out.shape[1]
+        if (tuple(w.shape) != ((k_in, n_out) if w_is_kn else (n_out, k_in)) or out.shape[0] != a.shape[0]
                 or w.dtype != torch.float32 or out.dtype != torch.float32):
             raise ValueError(f"chain layer {l}: shapes {tuple(w.shape)} / {tuple(out.shape)} do not follow {k_in} inputs")
-        w_p[l], b_p[l], m_p[l], o_p[l] = addr(w), addr(bias), addr(mask), addr(out)
+        for bits in (bits_out, mask if (mask is not None and mask.dtype == torch.int32) else None):
+            if bits is not None and (bits.dtype != torch.int32 or tuple(bits.shape) != (a.shape[0], n_out // 32)
+                                     or not bits.is_contiguous()):
+                raise ValueError(f"chain layer {l}: a bit matrix must be contiguous int32 ({a.shape[0]}, {n_out // 32})")
+        w_p[l], b_p[l], o_p[l], bo_p[l] = addr(w), addr(bias), addr(out), addr(bits_out)
+        if mask is not None and mask.dtype == torch.int32:
+            mb_p[l] = addr(mask)
+        elif mask is not None:
+            m_p[l], ldm[l] = addr(mask), mask.stride(0)
         ldw[l], ldo[l], kn[l] = w.stride(0), out.stride(0), int(bool(w_is_kn))
-        ldm[l] = mask.stride(0) if mask is not None else 0
     np_ptr = lambda x: x.ctypes.data
     call("cc_chain_tc", a.shape[0], n, np_ptr(widths), ptr(a), a.stride(0), np_ptr(w_p), np_ptr(ldw), np_ptr(kn),
-         np_ptr(b_p), np_ptr(m_p), np_ptr(ldm), int(relu), np_ptr(o_p), np_ptr(ldo), int(round_out), stream_ptr())
+         np_ptr(b_p), np_ptr(m_p), np_ptr(ldm), np_ptr(mb_p), np_ptr(bo_p), int(relu), np_ptr(o_p), np_ptr(ldo),
+         int(round_out), stream_ptr())

@@ -248,10 +248,14 @@ int cc_gemm_tc_set_pdl(int on);
  * layer l: out_l[m][n_l] = epi(in_l W_l), in_1 = a, in_{l+1} = out_l.  w_is_kn[l] = 1: W_l is the Keras kernel [K][N]
  * (forward); 0: [N][K] (a kernel used transposed: backward).  bias / mask: arrays of `layers` nullable pointers (either
  * array itself nullable); relu applies to layers with a bias, mask keeps values where mask[row][col] > 0 (ReLU's
- * backward).  Results are bit-identical to the same layers as separate cc_gemm_tc calls. */
+ * backward).  bits_out[l] (nullable): a (m, n_l / 32) uint32 matrix that receives one bit per output element (set where
+ * the output is positive); mask_bits[l] (nullable, takes precedence over mask[l]): such a matrix used as the ReLU mask --
+ * a 32-column chunk then costs a row 4 bytes of mask instead of 128.  Results are bit-identical to the same layers as
+ * separate cc_gemm_tc calls. */
 int cc_chain_tc(int m, int layers, const int32_t* widths, const float* a, int64_t lda, const float* const* w,
                 const int64_t* ldw, const int32_t* w_is_kn, const float* const* bias, const float* const* mask,
-                const int64_t* ldmask, int relu, float* const* out, const int64_t* ldout, int round_tf32, void* stream);
+                const int64_t* ldmask, const uint32_t* const* mask_bits, uint32_t* const* bits_out, int relu,
+                float* const* out, const int64_t* ldout, int round_tf32, void* stream);
 int64_t cc_colsum_workspace_bytes(int m, int n);
 int cc_colsum_f32(const float* x, int64_t ld, int m, int n, float* workspace, float* out, int accumulate,
                   void* stream);

@@ -303,6 +303,24 @@ def test_chain_of_small_layers_equals_separate_gemms(widths, m, backward):
         assert torch.equal(out_c, _rn_tf32(out_c))
         assert (out_c._base[:, out_c.shape[1]:] == 7.0).all()          # nothing written beyond the layer's width
         h = out_c
+    # the ReLU test as one bit per element: written by the forward form, consumed by the backward form
+    def pack(t):            # (m, n) bool -> (m, n / 32) int32, bit j of word w = column 32 w + j
+        b = t.reshape(t.shape[0], -1, 32).to(torch.int64)
+        v = (b << torch.arange(32, device="cuda")).sum(-1)
+        return torch.where(v >= 2 ** 31, v - 2 ** 32, v).to(torch.int32).contiguous()
+    if backward:
+        again = [(w, False, None, pack(mask > 0), torch.full_like(out_c._base, 7.0)[:, :out_c.shape[1]])
+                 for (w, _, _, mask, out_c) in layers_chain]
+        TC.chain(a, again, round_out=True)
+        for l, (one, two) in enumerate(zip(layers_chain, again)):
+            assert torch.equal(one[4], two[4]), l
+    else:
+        bits = [torch.full((m, lay[4].shape[1] // 32), -1, dtype=torch.int32, device="cuda") for lay in layers_chain]
+        again = [(w, True, bias, None, torch.full_like(out_c._base, 7.0)[:, :out_c.shape[1]], bt)
+                 for (w, _, bias, _, out_c), bt in zip(layers_chain, bits)]
+        TC.chain(a, again, relu=True, round_out=True)
+        for l, (one, two, bt) in enumerate(zip(layers_chain, again, bits)):
+            assert torch.equal(one[4], two[4]) and torch.equal(bt, pack(one[4] > 0)), l
 
 
 @pytest.mark.parametrize("precision", ["tf32", "bf16"])
