@@ -273,12 +273,22 @@ class CC_Recommender:
         h = torch.empty((b, 512), dtype=torch.float32, device=self.device)
         rnd = self.precision != "fp32"
         bag_fwd(s.p("encoder_e1/kernel"), sb.idx, sb.row_start, sb.row_len, s.p("encoder_e1/bias"), h, round_tf32=rnd)
+        if self._small_chain():       # the three layers in one launch (cc_chain_tc): same bits, two launches fewer
+            from . import tensorcore
+            outs = [torch.empty((b, width), dtype=torch.float32, device=self.device) for width in HIDDEN[1:]]
+            tensorcore.chain(h, [(s.w(name + "/kernel"), True, s.p(name + "/bias"), None, o)
+                                 for name, o in zip(ENC_NAMES[1:], outs)], relu=True, round_out=rnd)
+            return outs[-1]
         for name, width in zip(ENC_NAMES[1:], HIDDEN[1:]):
             o = torch.empty((b, width), dtype=torch.float32, device=self.device)
             gemm(h, s.w(name + "/kernel"), o, bias=s.p(name + "/bias"), relu=True, precision=self.gemm_precision,
                  round_out=rnd)
             h = o
         return h
+
+    def _small_chain(self):
+        import os
+        return self.precision != "fp32" and self.gemm_precision == "tf32" and os.environ.get("CC_SMALL_CHAIN", "1") != "0"
 
     def _decode(self, h: torch.Tensor, prefix: str) -> torch.Tensor:
         """Logits (batch, C) of decoder ``prefix`` ('main' | 'reg')."""
@@ -291,11 +301,18 @@ class CC_Recommender:
             hr = torch.empty_like(h)
             call("cc_round_tf32", ptr(h), ptr(hr), h.numel(), stream_ptr())
             h = hr
-        for name, width in zip(names[:3], (128, 256, 512)):
-            o = torch.empty((b, width), dtype=torch.float32, device=self.device)
-            gemm(h, s.w(name + "/kernel"), o, bias=s.p(name + "/bias"), relu=True, precision=self.gemm_precision,
-                 round_out=rnd)
-            h = o
+        if self._small_chain():
+            from . import tensorcore
+            outs = [torch.empty((b, width), dtype=torch.float32, device=self.device) for width in (128, 256, 512)]
+            tensorcore.chain(h, [(s.w(name + "/kernel"), True, s.p(name + "/bias"), None, o)
+                                 for name, o in zip(names[:3], outs)], relu=True, round_out=rnd)
+            h = outs[-1]
+        else:
+            for name, width in zip(names[:3], (128, 256, 512)):
+                o = torch.empty((b, width), dtype=torch.float32, device=self.device)
+                gemm(h, s.w(name + "/kernel"), o, bias=s.p(name + "/bias"), relu=True, precision=self.gemm_precision,
+                     round_out=rnd)
+                h = o
         cpad = (self.N + 3) // 4 * 4
         z = torch.empty((b, cpad), dtype=torch.float32, device=self.device)[:, :self.N]
         gemm(h, s.w(names[3] + "/kernel"), z, bias=s.p(names[3] + "/bias"), precision=self.gemm_precision)
