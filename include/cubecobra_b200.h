@@ -117,11 +117,12 @@ int cc_topn_masked_f32(const float* scores, int64_t ld, int32_t num_cards, int32
  * copies, double-buffered; needs ld % 4 == 0, a 16-byte aligned base and C <= ~26 000) or, for rows that do not
  * qualify, as a warp-per-cube streaming select (one pass over the row); larger n and float64 use the radix select /
  * full bitonic ranking.  All of them implement one total order on (score, index).  NaN scores: the row select never
- * selects them.  cc_topn_set_algo: 0 = automatic (default: the row select with two CTAs per SM when the rows qualify),
- * 1 = streaming select, 2 = row select with one CTA per SM and two row buffers, 3 = row select with two CTAs per SM and
- * one row buffer each (= automatic), 4 = its register form -- per-group maxima of the first sweep kept in registers,
- * survivors compacted by warp ballots, rows of up to 22 528 cards; measured no faster, kept as an option -- (tests
- * compare all of them).  cc_topn_masked_sigmoid_f32 takes LOGITS, ranks sigmoid(logit) (the float32
+ * selects them.  cc_topn_set_algo: 0 = automatic (default: the row select with two CTAs per SM when the rows qualify --
+ * in its register form when the whole row is ranked and holds at most 22 528 cards: group extremes kept in registers,
+ * one diverged block per warp in the second sweep, counting ranks summed over neighbouring lanes; 92 us per 4096 rows of
+ * 20 884 scores against 103 us), 1 = streaming select, 2 / 3 = row select with both sweeps over shared memory (one CTA
+ * per SM with two row buffers / two CTAs per SM), 4 = the register form (tests compare all of them).
+ * cc_topn_masked_sigmoid_f32 takes LOGITS, ranks sigmoid(logit) (the float32
  * probabilities the reference ranks, ml_recommend.py:78-104) and returns the winners' probabilities; n <= 128.
  * cc_topn_set_force_radix(1) pins float32 top-N to the radix kernel (tests compare the two). */
 int cc_topn_masked_sigmoid_f32(const float* logits, int64_t ld, int32_t num_cards, int32_t batch,
