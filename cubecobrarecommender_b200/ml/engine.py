@@ -75,7 +75,7 @@ class DAEEngine:
         self.launches = 0          # kernels launched by the last step (for bench's gpu_launches)
         self.prof = None
         # data parallel (one process per GPU), CC_DP_MODE =
-        #   "auto" (default) p2p_overlap for local batches of >= 3072 cubes, else p2p
+        #   "auto" (default) p2p_overlap for local batches of >= 3072 cubes in the fp32 / tf32 modes, else p2p
         #   "p2p"  Adam fused with the gradient exchange over NVLink peer memory: every rank owns 1/world of
         #          the parameters, reduces that slice of all ranks' gradients with peer loads, updates it and stores
         #          the result into every rank's parameters (cc_adam_step_p2p; symmetric memory)
@@ -92,8 +92,10 @@ class DAEEngine:
             # [B200] weak scaling at 4096 cubes per GPU: p2p_overlap 2.118 vs 2.178 ms at 2 GPUs, 2.226 vs 2.376 ms at 8
             # (92.6% vs 86.8% efficiency); strong scaling at 2048 cubes per GPU (2 GPUs): 1.967 vs 1.794 ms -- with half
             # the backward to hide under, the three bucket exchanges and their six barriers cost more than they save
-            # (profiles/r02/overlap_n2_*.json, profiles/r02/n8_*.json)
-            self.dp_mode = "p2p_overlap" if self.B >= 3072 else "p2p"
+            # (profiles/r02/overlap_n2_*.json, profiles/r02/n8_*.json).  bf16 mode at 8 GPUs: 2.124 ms overlapped against
+            # 1.910 ms plain -- its backward is a third shorter, and the exchange kernels slow the bf16 GEMMs they run beside
+            # (profiles/r02/final_n8/bench_weak_bf16_overlap.json): p2p there
+            self.dp_mode = "p2p_overlap" if (self.B >= 3072 and self.precision != "bf16") else "p2p"
         if os.environ.get("CC_DP_OVERLAP") is not None:          # older switch: 1 = overlapped buckets, 0 = blocking
             self.dp_mode = "nccl_overlap" if os.environ["CC_DP_OVERLAP"] != "0" else "nccl"
         if self.dp_mode not in ("p2p", "p2p_overlap", "nccl_overlap", "nccl"):
