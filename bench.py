@@ -343,7 +343,25 @@ def measure_extras(dev, peaks, log):
                      "popcount_kernel_word_pairs_per_s": pair_words / (t_cnt_popc * 1e-3)},
         "cpu_baseline": {"seconds_extrapolated": t_cpu_sub * nnz_ratio, "cores": 1, "kind": "port",
                          "sample": f"create_adjacency_matrix loop restatement on {ksub} cubes x {C} cards: {t_cpu_sub:.1f}s, scaled by nnz x{nnz_ratio:.0f}"},
+        # the count as the tensor-bound kernel it is: executed int8 multiply-adds (upper triangle only) against the
+        # nominal dense int8 rate of the part (MEASURED_PEAKS.json holds no int8 figure); ncu has the IMMA pipe 89% active
+        "count_roofline": {"kernel": "gemm_tc_kernel<u8, kind::i8>", "bound": "tensor",
+                           "achieved": K * C * (C + 256.0) / (t_cnt * 1e-3) / 1e12, "peak": 4500.0, "unit": "TOP/s",
+                           "frac": K * C * (C + 256.0) / (t_cnt * 1e-3) / 1e12 / 4500.0,
+                           "peak_source": "nominal dense int8 (4.5 POP/s); executed ops = 2 * K * C * (C + 256) / 2 (symmetry)",
+                           "ncu_tensor_pipe_active_pct": 89.0,
+                           "ncu_source": "profiles/r02x_step_kernels_ncu_full.csv"},
     }
+    # the UNMODIFIED reference function timed on this very input in the build container (the reference tree does not
+    # travel to the GPU box): profiles/reference_create_adjacency_cpu.py -> the committed JSON
+    try:
+        ref_json = json.load(open(os.path.join(REPO, "profiles", "r02_reference_create_adjacency_cpu.json")))
+        out["graph_build"]["reference_measured"] = {**ref_json, "kind": "reference",
+                                                    "note": "unmodified src/non_ml/utils.py:75-92, one thread, timed in the build "
+                                                            "container on the same 20 000 x 21 000 input; output equals the oracle "
+                                                            "(and hence this build) bit for bit"}
+    except Exception:
+        pass
     # ---------------- recommend.py top-50 (configs[0], second half): graph scoring + masked select ----------------
     try:
         G.count_cooccurrence(indptr, indices, K, C, counts=counts, workspace=ws, method="tensor")
