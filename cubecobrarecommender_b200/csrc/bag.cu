@@ -16,6 +16,9 @@ __global__ void bag_fwd_kernel(const float* __restrict__ w, int64_t ldw, int32_t
                                const int32_t* __restrict__ idx, const int64_t* __restrict__ row_start,
                                const int32_t* __restrict__ row_len, const float* __restrict__ bias,
                                float* __restrict__ out, int64_t ldo, int relu, int round_tf32) {
+  // lets a dependent tcgen05 GEMM / chain launch (programmatic stream serialisation) be scheduled and run its prologue
+  // while this grid drains; it still waits (griddepcontrol.wait) for this grid's completion before touching memory
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __shared__ int32_t sidx[BAG_CHUNK];
   const int b = blockIdx.x, t = threadIdx.x;
   const int len = row_len[b];

@@ -754,6 +754,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // elementwise epilogue for split-K GEMMs whose epilogue is not linear: c = round(mask(relu(c + bias)))
 __global__ void post_epilogue_kernel(float* __restrict__ c, long long ldc, int m, int n, const float* __restrict__ bias,
                                      int relu, const float* __restrict__ mask, long long ldmask, int round_tf32) {
+  // lets a dependent tcgen05 GEMM / chain launch (programmatic stream serialisation) be scheduled and run its prologue
+  // while this grid drains; it still waits (griddepcontrol.wait) for this grid's completion before touching memory
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)m * n) return;
   const int r = int(i / n), col = int(i % n);

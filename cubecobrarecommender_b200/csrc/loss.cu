@@ -491,6 +491,9 @@ softmax_kl_regs_kernel(const float* __restrict__ z, int64_t ldz, const float* __
                        int round_tf32, float* __restrict__ dbias, __nv_bfloat16* __restrict__ dz16, int64_t lddz16,
                        const double* __restrict__ tlogt, const int32_t* __restrict__ target_argmax,
                        int32_t* __restrict__ row_hit) {
+  // lets the dependent tcgen05 GEMM (programmatic stream serialisation) be scheduled and run its prologue while this grid
+  // drains; it still waits (griddepcontrol.wait) for this grid's completion before touching memory
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   auto EXPF = [](float x) { return FAST ? fast_exp(x) : expf(x); };
   auto LOGF = [](float x) { return FAST ? fast_log(x) : logf(x); };
   extern __shared__ __align__(16) float sz[];           // two rows of logits
