@@ -75,6 +75,7 @@ struct Params {
   double* acc_partial;                   // nullable, same layout: number of cells with round(sigmoid(z)) == y (Keras binary_accuracy)
   float* dbias;                          // EPI_BCE: column sums of dlogits (= the output layer's bias gradient), atomically added
   int a_mn_major, b_mn_major;
+  int a_mn3, b_mn3;                      // the MN-major operand is described by a 3-D tensor map (make_map_mn3): one TMA per k-block
   int* sched;                            // {next-tile counter, finished units}: self-resetting (see TileRing)
   // hybrid stream-K (static scheduling only): the first dp_tiles output tiles are walked round-robin with their whole
   // K range and stored; the LAST sk_tiles tiles are cut along K into num_units contiguous spans of k-blocks, one per
@@ -161,6 +162,18 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+
+// 3-D forms (see make_map_mn3): one instruction fetches every 32-float column group of an MN-major tf32 operand
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope
@@ -431,14 +444,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // both CTAs' boxes are credited to the LEADER's full barrier (the MMA issuer waits there)
             const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
             if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
-            if (p.a_mn_major) {
+            if (p.a_mn3) {
+              tma_load_3d_pair(sa, &map_a, bar, 0, kb * BK, a_row0 / MN_BOX);
+            } else if (p.a_mn_major) {
 #pragma unroll
               for (int j = 0; j < BM / MN_BOX; ++j)
                 tma_load_2d_pair(sa + j * MN_BOX_BYTES, &map_a, bar, a_row0 + j * MN_BOX, kb * BK);
             } else {
               tma_load_2d_pair(sa, &map_a, bar, kb * BK, a_row0);
             }
-            if (p.b_mn_major) {
+            if (p.b_mn3) {
+              tma_load_3d_pair(sb, &map_b, bar, 0, kb * BK, b_row0 / MN_BOX);
+            } else if (p.b_mn_major) {
 #pragma unroll
               for (int j = 0; j < BN_LOAD / MN_BOX; ++j)
                 tma_load_2d_pair(sb + j * MN_BOX_BYTES, &map_b, bar, b_row0 + j * MN_BOX, kb * BK);
@@ -447,14 +464,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           } else {
             mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-            if (p.a_mn_major) {
+            if (p.a_mn3) {
+              tma_load_3d(sa, &map_a, &full_bar[stage], 0, kb * BK, a_row0 / MN_BOX);
+            } else if (p.a_mn_major) {
 #pragma unroll
               for (int j = 0; j < BM / MN_BOX; ++j)
                 tma_load_2d(sa + j * MN_BOX_BYTES, &map_a, &full_bar[stage], a_row0 + j * MN_BOX, kb * BK);
             } else {
               tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, a_row0);
             }
-            if (p.b_mn_major) {
+            if (p.b_mn3) {
+              tma_load_3d(sb, &map_b, &full_bar[stage], 0, kb * BK, b_row0 / MN_BOX);
+            } else if (p.b_mn_major) {
 #pragma unroll
               for (int j = 0; j < BN / MN_BOX; ++j)
                 tma_load_2d(sb + j * MN_BOX_BYTES, &map_b, &full_bar[stage], b_row0 + j * MN_BOX, kb * BK);
@@ -812,6 +833,31 @@ static int make_map(CUtensorMap* map, const void* base, int elem, int mtype, lon
   return CC_OK;
 }
 
+// An MN-major tf32 operand ([K][MN] row-major, MN contiguous) lands in shared memory as consecutive 4 KB boxes of
+// [32 k-rows] x [32 floats] (128B swizzle with 32-byte atoms), one per 32-float column group.  As 2-D boxes that is 4-8
+// TMA instructions per operand per k-block -- measured 5-18% slower than the same GEMM on K-major operands (one box),
+// profiles/r02/gemm_layout_bench.jsonl: the producer's issue rate, not the MMA.  Described as a 3-D tensor
+// {32 floats, K rows (stride ld), MN/32 groups (stride 128 bytes)} with a box of {32, 32, groups}, ONE instruction writes
+// the same bytes to the same places.  The last group of a row may extend past MN (MN % 32 != 0): it then reads the
+// first floats of the next row, which only ever feed output rows / columns that the store clips -- the caller makes
+// sure those bytes exist (ld >= MN rounded up to 32, or the matrix is followed by more of the same buffer).
+static int make_map_mn3(CUtensorMap* map, const void* base, long long k_rows, long long mn, long long ld, int groups) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return CC_ERR_CUDA; }
+  cuuint64_t dims[3] = {32, cuuint64_t(k_rows), cuuint64_t((mn + 31) / 32)};
+  cuuint64_t strides[2] = {cuuint64_t(ld) * 4, 128};
+  cuuint32_t box[3] = {32, 32, cuuint32_t(groups)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3-D MN-major) failed (%d): base=%p k=%lld mn=%lld ld=%lld", int(r), base, k_rows, mn, ld);
+    return CC_ERR_CUDA;
+  }
+  return CC_OK;
+}
+
 struct Problem {
   int transa, transb, m, n, k;
   const void* a; long long lda;
@@ -899,6 +945,11 @@ static int g_stream_k = getenv("CC_GEMM_STREAM_K") ? atoi(getenv("CC_GEMM_STREAM
 // (CC_GEMM_TILE_ORDER=0; A/B measurements)
 static int g_tile_order = getenv("CC_GEMM_TILE_ORDER") ? atoi(getenv("CC_GEMM_TILE_ORDER")) : -1;
 
+// 1 = MN-major tf32 operands through 3-D tensor maps (one TMA per operand per k-block, see make_map_mn3), 0 = 2-D boxes
+// (CC_GEMM_MN3=0; A/B measurements)
+static int g_mn3 = getenv("CC_GEMM_MN3") ? atoi(getenv("CC_GEMM_MN3")) : 1;
+static std::atomic<long long> g_mn3_used{0};       // operands described by 3-D maps so far (cc_gemm_tc_mn3_count)
+
 // the waves model of plan_eff for the hybrid stream-K schedule of (bn, ctas): full data-parallel waves, then every
 // unit's span of the stream-K k-blocks (two partial tiles' worth of prologue/epilogue)
 static double plan_eff_sk(int m, int n, int kblocks, int bn, int sms, int ctas) {
@@ -939,12 +990,19 @@ static int launch_bn(const Problem& pr, Params p, cudaStream_t st) {
   CUtensorMap map_a, map_b, map_c;
   int rc;
   // transa=0: A is [M][K] (K-major)  -> box 128 rows x 128 B;  transa=1: A is [K][M] (MN-major) -> box bk rows x 128 B
-  if (pr.transa) rc = make_map(&map_a, pr.a, elem, mt, pr.k, pr.m, pr.lda, bk, TF32);
-  else           rc = make_map(&map_a, pr.a, elem, mt, pr.m, pr.k, pr.lda, BM, false);
+  // (3-D MN-major maps: tf32 only, and only when the bytes behind a ragged last column group exist inside the row)
+  p.a_mn3 = (TF32 && pr.transa && g_mn3 && (pr.m % 32 == 0 || pr.lda >= ((pr.m + 31) / 32) * 32)) ? 1 : 0;
+  p.b_mn3 = (TF32 && !pr.transb && g_mn3 && (pr.n % 32 == 0 || pr.ldb >= ((pr.n + 31) / 32) * 32)) ? 1 : 0;
+  if (p.a_mn3 && make_map_mn3(&map_a, pr.a, pr.k, pr.m, pr.lda, BM / 32) != CC_OK) p.a_mn3 = 0;    // (driver refused: 2-D boxes)
+  if (p.a_mn3)        { rc = CC_OK; ++g_mn3_used; }
+  else if (pr.transa) rc = make_map(&map_a, pr.a, elem, mt, pr.k, pr.m, pr.lda, bk, TF32);
+  else                rc = make_map(&map_a, pr.a, elem, mt, pr.m, pr.k, pr.lda, BM, false);
   if (rc != CC_OK) return rc;
   // transb=1: B is [N][K] (K-major);  transb=0: B is [K][N] (MN-major); a CTA of a pair loads BN/2 rows
-  if (pr.transb) rc = make_map(&map_b, pr.b, elem, mt, pr.n, pr.k, pr.ldb, BN / CTAS, false);
-  else           rc = make_map(&map_b, pr.b, elem, mt, pr.k, pr.n, pr.ldb, bk, TF32);
+  if (p.b_mn3 && make_map_mn3(&map_b, pr.b, pr.k, pr.n, pr.ldb, (BN / CTAS) / 32) != CC_OK) p.b_mn3 = 0;
+  if (p.b_mn3)        { rc = CC_OK; ++g_mn3_used; }
+  else if (pr.transb) rc = make_map(&map_b, pr.b, elem, mt, pr.n, pr.k, pr.ldb, BN / CTAS, false);
+  else                rc = make_map(&map_b, pr.b, elem, mt, pr.k, pr.n, pr.ldb, bk, TF32);
   if (rc != CC_OK) return rc;
   // C: fp32 (int32 counts) [M][n_store] boxes of 32 rows x 32 columns (TMA clips rows >= M and columns >= n_store)
   if (EPI == EPI_BCE16 || EPI == EPI_BCE16_ACC) rc = make_map(&map_c, pr.c, 2, MAP_BF16, pr.m, p.n_store, pr.ldc, 32, false, 32);
@@ -1103,6 +1161,7 @@ __global__ void expand_cubes_u8_kernel(const int64_t* __restrict__ indptr, const
 struct ChainLayer {
   int n, k;                 // output width (multiple of 64, <= 512) and reduction length (multiple of 32, <= 512)
   int b_mn_major;           // B = the layer's kernel: [K][N] row-major (forward, 1) or [N][K] row-major (backward, 0)
+  int b_mn3;                // the MN-major kernel is described by a 3-D tensor map: one TMA per k-block (make_map_mn3)
   int passes;               // 1, or 2 halves of n / 2 columns (n = 512: the MMA's N is at most 256)
   int tmem_col;             // first accumulator column
   int relu, round_tf32;
@@ -1201,7 +1260,9 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             uint8_t* sb = sa + STAGE_A_BYTES;
             mbar_expect_tx(&full_bar[stage], (l == 0 ? STAGE_A_BYTES : 0) + nw * 128);
             if (l == 0) tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, row0);
-            if (L.b_mn_major) {
+            if (L.b_mn3) {
+              tma_load_3d(sb, maps_b[l], &full_bar[stage], 0, kb * BK, (h * nw) / MN_BOX);
+            } else if (L.b_mn_major) {
               for (int j = 0; j < nw / MN_BOX; ++j)
                 tma_load_2d(sb + j * MN_BOX_BYTES, maps_b[l], &full_bar[stage], h * nw + j * MN_BOX, kb * BK);
             } else {
@@ -1612,10 +1673,16 @@ int cc_chain_tc(int m, int layers, const int32_t* widths, const float* a, int64_
   if (rc != CC_OK) return rc;
   for (int l = 0; l < 3; ++l) {
     const int ll = l < layers ? l : layers - 1;               // unused slots repeat the last layer's maps
-    const tc::ChainLayer& L = p.L[ll];
+    tc::ChainLayer& L = p.L[ll];
     const int nw = L.n / L.passes;
-    if (L.b_mn_major) rc = tc::make_map(&map_b[l], w[ll], 4, tc::MAP_F32, L.k, L.n, ldw[ll], 32, true);
-    else              rc = tc::make_map(&map_b[l], w[ll], 4, tc::MAP_F32, L.n, L.k, ldw[ll], nw, false);
+    if (l == ll) L.b_mn3 = (L.b_mn_major && tc::g_mn3) ? 1 : 0;
+    if (L.b_mn3 && tc::make_map_mn3(&map_b[l], w[ll], L.k, L.n, ldw[ll], nw / 32) != CC_OK) {
+      CC_REQUIRE(l == ll, "cc_chain_tc: tensor map of a repeated slot failed");
+      L.b_mn3 = 0;                                            // (driver refused the 3-D form: 2-D boxes)
+    }
+    if (L.b_mn3)           { rc = CC_OK; if (l == ll) ++tc::g_mn3_used; }
+    else if (L.b_mn_major) rc = tc::make_map(&map_b[l], w[ll], 4, tc::MAP_F32, L.k, L.n, ldw[ll], 32, true);
+    else                   rc = tc::make_map(&map_b[l], w[ll], 4, tc::MAP_F32, L.n, L.k, ldw[ll], nw, false);
     if (rc != CC_OK) return rc;
     rc = tc::make_map(&map_c[l], out[ll], 4, tc::MAP_F32, m, L.n, ldout[ll], 32, false);
     if (rc != CC_OK) return rc;
@@ -1649,6 +1716,10 @@ int cc_chain_tc(int m, int layers, const int32_t* widths, const float* a, int64_
   CC_CHECK_LAUNCH();
   return CC_OK;
 }
+
+// number of MN-major tf32 operands that went through a 3-D tensor map since the library was loaded (0 after MN-major
+// launches means the driver refused the 3-D form and the 2-D boxes were used)
+int64_t cc_gemm_tc_mn3_count(void) { return int64_t(tc::g_mn3_used.load()); }
 
 int cc_gemm_tc_set_pdl(int on) {
   tc::g_pdl = on ? 1 : 0;

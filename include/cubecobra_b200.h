@@ -242,6 +242,10 @@ int cc_gemm_tc_set_dynamic_tiles(int on);
  * scheduled and run their prologue while the previous kernel drains; they wait (griddepcontrol.wait) for its
  * completion before touching global memory. */
 int cc_gemm_tc_set_pdl(int on);
+/* MN-major tf32 operands ([K][MN] row-major: Keras kernels in forward, activations / dlogits in the weight-gradient
+ * GEMMs) are fetched by ONE 3-D TMA per k-block instead of 4-8 two-dimensional boxes (CC_GEMM_MN3=0 restores the boxes);
+ * this returns how many operands took the 3-D form since the library was loaded. */
+int64_t cc_gemm_tc_mn3_count(void);
 /* Up to three consecutive small Dense layers in ONE launch (the 512 -> 256 -> 128 -> 64 -> 128 -> 256 -> 512 stack of
  * model.py:27-33, 58-64 and its input gradients): a CTA takes 128 rows through the chain with the intermediate
  * activations kept in tensor memory (tcgen05.mma with the A operand in TMEM); every layer's output is also stored.
