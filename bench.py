@@ -77,7 +77,7 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.index, self.proc, self.lines = index, None, []
-        self.t0 = self.t1 = None
+        self.t0 = self.t1 = self.t2 = None
 
     def start(self):
         try:
@@ -93,6 +93,9 @@ class ClockSampler:
 
     def mark_end(self):
         self.t1 = time.time()
+
+    def mark_load_end(self):
+        self.t2 = time.time()
 
     def stop(self):
         if not self.proc:
@@ -116,8 +119,12 @@ class ClockSampler:
                 continue
         inside = [r for r in rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1]
         window = "timed region"
-        if not inside:      # region shorter than the sampling period: fall back to everything sampled under load
-            inside, window = rows, "warm-up + timed region"
+        if len(inside) < 3 and self.t0 is not None and self.t2 is not None:
+            # a region of a few sampling periods: add the instrumented pass behind it (the same K steps, the same load)
+            inside = [r for r in rows if self.t0 <= r[0] <= self.t2]
+            window = "timed region + the instrumented pass of the same K steps"
+        if not inside:      # still nothing: everything sampled since the poller started
+            inside, window = rows, "whole run"
         reasons = set()
         for r in inside:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
@@ -534,6 +541,11 @@ def run_native(args, rank, world, local_rank):
     t0 = time.time()
     # every rank owns its own cubes (weak scaling: per-GPU batch fixed); the graph is the
     # all_reduce of the per-rank int32 counts, so M-hat is identical everywhere
+    # the clock poller starts here: nvidia-smi takes a few hundred ms to print its first sample, and the warm-up plus the
+    # timed region of the default run last ~50 ms
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     csr = make_cubes(W["num_cubes"], C, cfg=W["cfg"] * 1000 + rank)
     gr = G.build_graph(csr, dev, want_m64=False, want_mhat=True, want_neg=True)
     log(f"cubes + graph ready in {time.time() - t0:.1f}s")
@@ -572,9 +584,6 @@ def run_native(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     for i in range(args.warmup):
         step(i)
     eng.check_overflow()
@@ -594,7 +603,6 @@ def run_native(args, rank, world, local_rank):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     launches = eng.launches
-    clock_info = clocks.stop() if rank == 0 else None
     # ---- the same K steps again with a CUDA-event pair around every kernel of interest (the roofline leg).  The
     #      event records sit between consecutive GEMM launches and so defeat their programmatic dependent launch:
     #      this pass is a few percent slower than the timed region above, and is reported separately ----
@@ -606,6 +614,10 @@ def run_native(args, rank, world, local_rank):
     evi1.record()
     barrier()
     ms_instr = evi0.elapsed_time(evi1)
+    # clocks: the samples inside the timed region when there are at least three of them (10 ms period), else the
+    # samples from its start to the end of the instrumented pass -- the same K steps under the same load
+    clocks.mark_load_end()
+    clock_info = clocks.stop() if rank == 0 else None
     ktimes = eng.kernel_times_ms()
     eng.enable_kernel_timing(False)
     loss_host = [float(v) for v in loss.cpu().numpy()]
