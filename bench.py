@@ -97,6 +97,18 @@ class ClockSampler:
     def mark_load_end(self):
         self.t2 = time.time()
 
+    def samples_in_timed_region(self):
+        """Samples with a timestamp inside [mark_begin, mark_end] so far (the poller may still be running)."""
+        import datetime
+        n = 0
+        for ln in list(self.lines):
+            try:
+                ts = datetime.datetime.strptime(ln.split(",")[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                continue
+            n += 1 if (self.t0 is not None and self.t1 is not None and self.t0 <= ts <= self.t1) else 0
+        return n
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -606,6 +618,13 @@ def run_native(args, rank, world, local_rank):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     launches = eng.launches
+    # the poller is stopped here when the timed region already holds three samples: nvidia-smi queries take driver locks,
+    # and the instrumented pass below is what the roofline numbers come from
+    clock_info = None
+    if rank == 0:
+        time.sleep(0.05)                                   # (lets the reader thread catch up with the pipe)
+        if clocks.samples_in_timed_region() >= 3:
+            clock_info = clocks.stop()
     # ---- the same K steps again with a CUDA-event pair around every kernel of interest (the roofline leg).  The
     #      event records sit between consecutive GEMM launches and so defeat their programmatic dependent launch:
     #      this pass is a few percent slower than the timed region above, and is reported separately ----
@@ -620,7 +639,8 @@ def run_native(args, rank, world, local_rank):
     # clocks: the samples inside the timed region when there are at least three of them (10 ms period), else the
     # samples from its start to the end of the instrumented pass -- the same K steps under the same load
     clocks.mark_load_end()
-    clock_info = clocks.stop() if rank == 0 else None
+    if rank == 0 and clock_info is None:
+        clock_info = clocks.stop()
     ktimes = eng.kernel_times_ms()
     eng.enable_kernel_timing(False)
     loss_host = [float(v) for v in loss.cpu().numpy()]

@@ -77,6 +77,7 @@ SIGNATURES = {
     "cc_gemm_tc_set_dynamic_tiles": (I, [I]),
     "cc_gemm_tc_set_pdl": (I, [I]),
     "cc_gemm_tc_mn3_count": (I64, []),
+    "cc_gemm_tc_register_readable": (I, [P, I64]),
     "cc_chain_tc": (I, [I, I, P, P, I64, P, P, P, P, P, P, P, P, I, P, P, I, P]),
     "cc_colsum_workspace_bytes": (I64, [I, I]),
     "cc_colsum_f32": (I, [P, I64, I, I, P, P, I, P]),

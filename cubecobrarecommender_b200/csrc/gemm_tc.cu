@@ -949,6 +949,22 @@ static int g_tile_order = getenv("CC_GEMM_TILE_ORDER") ? atoi(getenv("CC_GEMM_TI
 // (CC_GEMM_MN3=0; A/B measurements)
 static int g_mn3 = getenv("CC_GEMM_MN3") ? atoi(getenv("CC_GEMM_MN3")) : 1;
 static std::atomic<long long> g_mn3_used{0};       // operands described by 3-D maps so far (cc_gemm_tc_mn3_count)
+// memory ranges the caller has declared fully readable (cc_gemm_tc_register_readable): an MN-major operand whose rows
+// are not padded to 32 floats may still take the 3-D form when the bytes behind its ragged last column group lie
+// inside such a range (a Keras kernel inside the flat parameter buffer is followed by its bias)
+static std::mutex g_readable_mu;
+static uintptr_t g_readable[32][2];
+static int g_readable_n = 0;
+static int g_use_readable = getenv("CC_GEMM_READABLE") ? atoi(getenv("CC_GEMM_READABLE")) : 1;   // 0: ignore the registered ranges (A/B)
+static bool readable_range(const void* base, long long k_rows, long long mn, long long ld) {
+  if (!g_use_readable) return false;
+  const uintptr_t lo = reinterpret_cast<uintptr_t>(base);
+  const uintptr_t hi = lo + (uintptr_t(k_rows - 1) * uintptr_t(ld) + uintptr_t((mn + 31) / 32 * 32)) * 4;
+  std::lock_guard<std::mutex> lk(g_readable_mu);
+  for (int i = 0; i < g_readable_n; ++i)
+    if (lo >= g_readable[i][0] && hi <= g_readable[i][1]) return true;
+  return false;
+}
 
 // the waves model of plan_eff for the hybrid stream-K schedule of (bn, ctas): full data-parallel waves, then every
 // unit's span of the stream-K k-blocks (two partial tiles' worth of prologue/epilogue)
@@ -991,8 +1007,10 @@ static int launch_bn(const Problem& pr, Params p, cudaStream_t st) {
   int rc;
   // transa=0: A is [M][K] (K-major)  -> box 128 rows x 128 B;  transa=1: A is [K][M] (MN-major) -> box bk rows x 128 B
   // (3-D MN-major maps: tf32 only, and only when the bytes behind a ragged last column group exist inside the row)
-  p.a_mn3 = (TF32 && pr.transa && g_mn3 && (pr.m % 32 == 0 || pr.lda >= ((pr.m + 31) / 32) * 32)) ? 1 : 0;
-  p.b_mn3 = (TF32 && !pr.transb && g_mn3 && (pr.n % 32 == 0 || pr.ldb >= ((pr.n + 31) / 32) * 32)) ? 1 : 0;
+  p.a_mn3 = (TF32 && pr.transa && g_mn3 && (pr.m % 32 == 0 || pr.lda >= ((pr.m + 31) / 32) * 32 ||
+                                            readable_range(pr.a, pr.k, pr.m, pr.lda))) ? 1 : 0;
+  p.b_mn3 = (TF32 && !pr.transb && g_mn3 && (pr.n % 32 == 0 || pr.ldb >= ((pr.n + 31) / 32) * 32 ||
+                                             readable_range(pr.b, pr.k, pr.n, pr.ldb))) ? 1 : 0;
   if (p.a_mn3 && make_map_mn3(&map_a, pr.a, pr.k, pr.m, pr.lda, BM / 32) != CC_OK) p.a_mn3 = 0;    // (driver refused: 2-D boxes)
   if (p.a_mn3)        { rc = CC_OK; ++g_mn3_used; }
   else if (pr.transa) rc = make_map(&map_a, pr.a, elem, mt, pr.k, pr.m, pr.lda, bk, TF32);
@@ -1720,6 +1738,27 @@ int cc_chain_tc(int m, int layers, const int32_t* widths, const float* a, int64_
 // number of MN-major tf32 operands that went through a 3-D tensor map since the library was loaded (0 after MN-major
 // launches means the driver refused the 3-D form and the 2-D boxes were used)
 int64_t cc_gemm_tc_mn3_count(void) { return int64_t(tc::g_mn3_used.load()); }
+
+// Declares [base, base + bytes) readable in full for as long as GEMMs are launched on operands inside it (bytes = 0
+// forgets the range that starts at base).  See readable_range: it lets unpadded MN-major tf32 operands inside the range
+// take the single-TMA 3-D form, whose last column group of a row reads up to 124 bytes past the row's end.
+int cc_gemm_tc_register_readable(const void* base, int64_t bytes) {
+  CC_REQUIRE(base != nullptr && bytes >= 0, "cc_gemm_tc_register_readable: null base or negative size");
+  std::lock_guard<std::mutex> lk(tc::g_readable_mu);
+  const uintptr_t lo = reinterpret_cast<uintptr_t>(base);
+  int slot = -1;
+  for (int i = 0; i < tc::g_readable_n; ++i) if (tc::g_readable[i][0] == lo) slot = i;
+  if (bytes == 0) {
+    if (slot >= 0) { tc::g_readable[slot][0] = tc::g_readable[tc::g_readable_n - 1][0]; tc::g_readable[slot][1] = tc::g_readable[tc::g_readable_n - 1][1]; --tc::g_readable_n; }
+    return CC_OK;
+  }
+  if (slot < 0) {
+    if (tc::g_readable_n == 32) { tc::g_readable_n = 0; }     // (a table of the most recent ranges: start over)
+    slot = tc::g_readable_n++;
+  }
+  tc::g_readable[slot][0] = lo; tc::g_readable[slot][1] = lo + uintptr_t(bytes);
+  return CC_OK;
+}
 
 int cc_gemm_tc_set_pdl(int on) {
   tc::g_pdl = on ? 1 : 0;

@@ -64,7 +64,17 @@ class ParamStore:
     def enable_tf32_shadow(self):
         if self.shadow is None:
             self.shadow = torch.zeros_like(self.params)
+            # the GEMMs read Keras kernels out of this buffer; a kernel's last row is followed by its bias, so the single-TMA
+            # form of an MN-major operand may read the few floats behind a row that is not a multiple of 32 wide
+            call("cc_gemm_tc_register_readable", ptr(self.shadow), self.shadow.numel() * 4)
         self.sync_shadow()
+
+    def __del__(self):
+        try:
+            if getattr(self, "shadow", None) is not None:
+                call("cc_gemm_tc_register_readable", ptr(self.shadow), 0)
+        except Exception:
+            pass
 
     def sync_shadow(self):
         if self.shadow is not None:

@@ -246,6 +246,11 @@ int cc_gemm_tc_set_pdl(int on);
  * GEMMs) are fetched by ONE 3-D TMA per k-block instead of 4-8 two-dimensional boxes (CC_GEMM_MN3=0 restores the boxes);
  * this returns how many operands took the 3-D form since the library was loaded. */
 int64_t cc_gemm_tc_mn3_count(void);
+/* Declares [base, base + bytes) readable in full (bytes = 0 forgets the range starting at base): an MN-major tf32
+ * operand whose rows are NOT padded to 32 floats (a 512 x 20 884 Keras kernel) may take the 3-D form only if the up to
+ * 124 bytes its last column group reads past a row's end are known to exist -- true inside the flat parameter buffer,
+ * where a kernel's last row is followed by its bias.  The ML model registers its parameter shadow. */
+int cc_gemm_tc_register_readable(const void* base, int64_t bytes);
 /* Up to three consecutive small Dense layers in ONE launch (the 512 -> 256 -> 128 -> 64 -> 128 -> 256 -> 512 stack of
  * model.py:27-33, 58-64 and its input gradients): a CTA takes 128 rows through the chain with the intermediate
  * activations kept in tensor memory (tcgen05.mma with the A operand in TMEM); every layer's output is also stored.
