@@ -104,3 +104,26 @@ def test_gemm_planner_choices(lib):
     assert plan(B, C, H, tile_n=128, split_k=1) == (128, 1, 1)
     assert plan(B, H, C, tile_n=256, split_k=7)[:2] == (256, 7)
     assert plan(B, C, H, precision=2)[0] == 256
+
+
+def test_chain_and_readable_range_argument_checks(lib):
+    """Host-side argument checking of the round-2 entry points (no device work is reached): cc_chain_tc rejects layer
+    counts / widths it cannot run, cc_gemm_tc_register_readable takes and forgets ranges."""
+    import ctypes
+    widths = np.array([512, 256, 128, 64], dtype=np.int32)
+    dummy = np.zeros(3, dtype=np.uint64)
+    ld = np.zeros(3, dtype=np.int64)
+    kn = np.zeros(3, dtype=np.int32)
+    args = (_lib.ptr(dummy), _lib.ptr(ld), _lib.ptr(kn), None, None, None, None, None, 1, _lib.ptr(dummy), _lib.ptr(ld), 1, None)
+    rc = lib.cc_chain_tc(128, 0, _lib.ptr(widths), ctypes.c_void_p(16), 512, *args)
+    assert rc == -1 and "1..3 layers" in _lib.last_error()
+    bad = np.array([500, 256], dtype=np.int32)                 # k must be a multiple of 32
+    rc = lib.cc_chain_tc(128, 1, _lib.ptr(bad), ctypes.c_void_p(16), 512, *args)
+    assert rc == -1 and "multiple of 32" in _lib.last_error()
+    wide = np.array([64, 512, 128], dtype=np.int32)            # only the last layer may be 512 wide
+    rc = lib.cc_chain_tc(128, 2, _lib.ptr(wide), ctypes.c_void_p(16), 64, *args)
+    assert rc == -1 and "last layer" in _lib.last_error()
+    assert lib.cc_gemm_tc_register_readable(None, 64) == -1
+    assert lib.cc_gemm_tc_register_readable(ctypes.c_void_p(4096), 1 << 20) == 0
+    assert lib.cc_gemm_tc_register_readable(ctypes.c_void_p(4096), 0) == 0      # forgotten again
+    assert lib.cc_gemm_tc_mn3_count() >= 0
