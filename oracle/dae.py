@@ -26,7 +26,13 @@ TensorFlow / Keras 2.5.2 (reference ``requirements.txt:48``):
 PARITY UNPINNED for this file: TensorFlow cannot be installed in the build
 container and the reference holds no golden outputs, so this restatement is
 cross-checked between its two independent formulations (NumPy float64 with
-hand-derived gradients vs torch-CPU autograd) in ``tests/test_oracle_dae.py``.
+hand-derived gradients vs torch-CPU autograd) in ``tests/test_oracle_dae.py``,
+and held to the only vectors of the dependency itself that exist outside it:
+the worked examples printed in the Keras API documentation (BinaryCrossentropy
+0.815 / [0.916, 0.714], KLDivergence 0.458 / [0.916, -3.08e-06] -- the second
+row is the clip of y_true to 1e-7 at work --, BinaryAccuracy 0.75,
+CategoricalAccuracy 0.5, one Adam step 10.0 -> 9.9;
+``test_published_keras_known_answers``).
 """
 from __future__ import annotations
 

@@ -133,3 +133,29 @@ def test_onehot_rows_as_gather_is_the_same_arithmetic():
     assert la == lb
     for kname in ga:
         assert np.abs(ga[kname] - gb[kname]).max() <= 1e-18 + 1e-15 * np.abs(ga[kname]).max(), kname
+
+
+def test_published_keras_known_answers():
+    """The worked examples of the Keras API documentation (tf.keras.losses.BinaryCrossentropy / KLDivergence,
+    tf.keras.metrics.BinaryAccuracy / CategoricalAccuracy, tf.keras.optimizers.Adam -- the figures printed there, three
+    digits) against the oracle's restatement.  TensorFlow 2.5.2 (requirements.txt:48) is not installable here, so these
+    published numbers are the only vectors of the dependency itself the oracle can be held to."""
+    y_true = np.array([[0.0, 1.0], [0.0, 0.0]]); y_pred = np.array([[0.6, 0.4], [0.4, 0.6]])
+    # BinaryCrossentropy()(y_true, y_pred) = 0.815 (docs); the oracle works from logits
+    z = np.log(y_pred / (1 - y_pred))
+    assert abs(dae.bce_from_logits_np(z, y_true) - 0.815) < 1e-3
+    per_row = [dae.bce_from_logits_np(z[i:i + 1], y_true[i:i + 1]) for i in range(2)]
+    assert abs(per_row[0] - 0.916) < 1e-3 and abs(per_row[1] - 0.714) < 1e-3          # reduction=NONE in the docs
+    # KLDivergence()(y_true, y_pred) = 0.458, per row [0.916, -3.08e-06] (docs): y_true is clipped to [1e-7, 1]
+    assert abs(dae.kld_np(y_true, y_pred) - 0.458) < 1e-3
+    assert abs(dae.kld_np(y_true[1:2], y_pred[1:2]) - (-3.08e-06)) < 1e-8
+    # BinaryAccuracy: y_true [[1],[1],[0],[0]], y_pred [[0.98],[1],[0],[0.6]] -> 0.75 (docs); logits of the predictions
+    yt = np.array([[1.0], [1.0], [0.0], [0.0]]); yp = np.array([[0.98], [1.0 - 1e-12], [1e-12], [0.6]])
+    assert dae.binary_accuracy_np(np.log(yp / (1 - yp)), yt) == 0.75
+    # CategoricalAccuracy: y_true [[0,0,1],[0,1,0]], y_pred [[0.1,0.9,0.8],[0.05,0.95,0]] -> 0.5 (docs)
+    ct = np.array([[0.0, 0.0, 1.0], [0.0, 1.0, 0.0]]); cp = np.array([[0.1, 0.9, 0.8], [0.05, 0.95, 0.0]])
+    assert dae.categorical_accuracy_np(cp, ct) == 0.5                                   # (argmax of logits = argmax of probabilities)
+    # Adam(learning_rate=0.1): var = 10.0, loss = var^2 / 2 -> after one step var = 9.9 (docs)
+    p = {"w": np.array([10.0])}; m = {"w": np.zeros(1)}; v = {"w": np.zeros(1)}
+    dae.adam_step_np(p, {"w": p["w"].copy()}, m, v, 1, lr=0.1)
+    assert abs(p["w"][0] - 9.9) < 1e-6
